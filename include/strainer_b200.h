@@ -1,0 +1,164 @@
+/*
+ * strainer_b200 -- C ABI of the B200-native (sm_100a) straining hot path.
+ *
+ * The reference (hizibu7/Strainer-GAN) is pure Python and has no FFI of its own: its boundary
+ * for this path is a set of Python functions.  Each entry point below is what
+ * the thin Python layer (strainer-gan_b200/api.py, same names/arguments as the reference
+ * functions) binds with ctypes; the comment on each group cites the reference lines whose
+ * work it replaces.  INTEGRATION.md shows the binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; every pointer is a DEVICE pointer unless the
+ *    parameter name starts with h_ (host).  The caller owns every buffer, including
+ *    workspaces (sizes from the *_bytes() queries); the library allocates nothing.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises the device, and is re-entrant per (device, stream).
+ *  - return value: SG_OK (0) or a negative SgStatus; sg_last_error_string() gives the
+ *    thread-local detail.  There is NO CPU fallback: on a device that is not sm_100 every
+ *    compute entry point returns SG_EARCH.
+ */
+#ifndef STRAINER_B200_H_
+#define STRAINER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum SgStatus {
+  SG_OK = 0,
+  SG_EINVAL = -1,   /* bad argument */
+  SG_EARCH = -2,    /* device is not sm_100 / no CUDA device */
+  SG_ECUDA = -3,    /* CUDA runtime / driver error, see sg_last_error_string() */
+  SG_ENOINIT = -4   /* sg_init() not called for the current device */
+} SgStatus;
+
+/* comparison used by the mask / compaction kernels (reference masks: `<` everywhere except
+ * `<=` in "# z_score + DBSCAN.py:325" and `>=` in "# 상위 10% 제거해서 fake image에 concate.py:247") */
+typedef enum SgCmp { SG_LT = 0, SG_LE = 1, SG_GE = 2, SG_GT = 3, SG_NOT = 4 /* OR-ed in: !(v CMP thr), the
+  NaN-correct complement used for the "noisy" half of divide_dataset ("#clean...py:311") */ } SgCmp;
+
+/* interpolation rule for a quantile from two order statistics */
+typedef enum SgLerp {
+  SG_LERP_NUMPY = 0, /* numpy _lerp: a+(b-a)*t, b-(b-a)*(1-t) for t>=.5, no FMA ("#strainer gan.py:381") */
+  SG_LERP_TORCH = 1  /* torch.lerp: fma form ("# 상위 10% 제거해서 fake image에 concate.py:246") */
+} SgLerp;
+
+/* arithmetic of the discriminator convolutions */
+typedef enum SgConvMode {
+  SG_CONV_BF16 = 0,   /* bf16 operands, fp32 accumulate (1 tcgen05 pass) */
+  SG_CONV_BF16X3 = 1  /* fp32-parity mode: bf16 hi/lo split, 3 tcgen05 passes (hi*hi+lo*hi+hi*lo) */
+} SgConvMode;
+
+/* ---- library ------------------------------------------------------------------------- */
+int sg_version(void);
+const char* sg_last_error_string(void);
+/* Binds the library to `device`: checks compute capability 10.x, caches the SM count, resolves
+ * cuTensorMapEncodeTiled through the runtime, raises the dynamic shared-memory limits. */
+int sg_init(int device);
+int sg_sm_count(void);
+
+/* ---- synthetic data (counter based, identical to oracle.synth_images) --- */
+int sg_synth_images(float* out, int64_t start, int64_t count, uint32_t seed, void* stream);
+
+/* ---- D64 scoring: Discriminator.forward + BCE vs label 1 ------------------------------
+ * replaces "#strainer gan.py:230-256" (5 convs, eval-mode BN, LeakyReLU .2, Sigmoid) and the
+ * per-sample BCELoss(reduction='none') of ":369-375" / "#clean...py:279-285".               */
+size_t sg_d64_packed_bytes(int conv_mode);
+/* w1 [64,3,4,4] w2 [128,64,4,4] w3 [256,128,4,4] w4 [512,256,4,4] w5 [1,512,4,4] fp32 OIHW;
+ * bnK = {gamma, beta, running_mean, running_var} of the BatchNorm2d after conv K (K=2,3,4). */
+int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* w4, const float* w5,
+                const float* bn2_gamma, const float* bn2_beta, const float* bn2_mean, const float* bn2_var,
+                const float* bn3_gamma, const float* bn3_beta, const float* bn3_mean, const float* bn3_var,
+                const float* bn4_gamma, const float* bn4_beta, const float* bn4_mean, const float* bn4_var,
+                float bn_eps, int conv_mode, void* packed, void* stream);
+size_t sg_d64_workspace_bytes(int64_t max_batch, int conv_mode);
+/* x: fp32 NCHW [batch,3,64,64].  Writes logit[batch], prob[batch] = sigmoid(logit) and
+ * loss[batch] = -max(log prob, -100) (any of the three may be NULL). */
+int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
+                 float* logit, float* prob, float* loss, void* stream);
+/* debugging / tests: copies the activation of layer `layer` (1..4) of the last sg_d64_score call
+ * on `workspace` into fp32 NCHW `out` ([batch,64,32,32], [batch,128,16,16], ...). */
+/* Synchronises `stream` and reports a pipeline time-out recorded by the conv kernels (tests). */
+int sg_d64_check(const void* workspace, void* stream);
+int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, int layer, float* out,
+                           void* stream);
+
+/* ---- selection: order statistics, thresholds ------------------------------------------
+ * replaces np.percentile "#strainer gan.py:381", "# 종합 loss.py:288-292" and torch.quantile
+ * "# 상위 10% 제거해서 fake image에 concate.py:246", "# z_score + DBSCAN.py:323".
+ * Radix select of the order statistics x_(k) and x_(k+1) (NaNs sort last, -0 == +0), split in
+ * phases so that a multi-GPU caller can all-reduce ws[0..2049) (uint32 histogram + NaN count, SUM)
+ * after each sg_select_hist and ws[SG_SELECT_WS_MINABOVE] (as int32 of key ^ 0x80000000 it is
+ * order preserving; the Python layer reduces it with MIN on the biased value) after
+ * sg_select_min_above.  */
+#define SG_SELECT_WS_WORDS 4096      /* uint32 words of workspace */
+#define SG_SELECT_WS_HIST 0          /* [2048] digit histogram of the current pass */
+#define SG_SELECT_WS_NANCOUNT 2048   /* number of NaNs seen (pass 0); SUM-reduced with the histogram */
+#define SG_SELECT_WS_MINABOVE 2049   /* smallest radix key above the selected one (MIN-reduced) */
+#define SG_SELECT_NUM_PASSES 3
+int sg_select_begin(uint32_t* ws, int64_t k, void* stream);
+int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stream);
+int sg_select_step(uint32_t* ws, int pass, void* stream);
+int sg_select_min_above(const float* v, int64_t n, uint32_t* ws, void* stream);
+/* out2[0] = x_(k), out2[1] = x_(k+1) (== x_(k) when k is the last index); NaN if any NaN. */
+int sg_select_finish(const uint32_t* ws, float* out2, void* stream);
+/* single-device convenience: all phases back to back */
+int sg_radix_select(const float* v, int64_t n, int64_t k, uint32_t* ws, float* out2, void* stream);
+/* thr[0] = lerp(stats2[0], stats2[1], weight) with the named rounding rule */
+int sg_lerp_threshold(const float* stats2, float weight, int lerp_kind, float* thr, void* stream);
+/* Segmented in-block quantile: `segments` consecutive segments of `seg_len` (<= 2048) values each;
+ * per segment a shared-memory bitonic sort, out2[2*s] = x_(k), out2[2*s+1] = x_(k1). */
+int sg_segment_order_stats(const float* v, int64_t segments, int seg_len, int k, int k1, float* out2,
+                           void* stream);
+
+/* ---- compaction ----------------------------------------------------------------------
+ * replaces np.where(losses < thr)[0] "#strainer gan.py:384", the boolean gathers
+ * real_cpu[mask] / real_cpu[~mask] and torch.cat "# 상위 10% 제거...py:247-249,268", and the pool
+ * gather "# strainer gan + concate.py:623-627".                                               */
+size_t sg_compact_workspace_bytes(int64_t n);
+/* idx_out[0..count) = ascending i (+ index_base) with v[i] CMP *thr; *count_out = count.
+ * If mask_out != NULL also writes the 0/1 byte mask. */
+int sg_compact_indices(const float* v, int64_t n, const float* thr, int cmp, int64_t index_base,
+                       int64_t* idx_out, int64_t* count_out, uint8_t* mask_out, void* workspace, void* stream);
+/* Stable two-way partition of rows by mask: kept rows (mask != 0) to `kept`, the others to
+ * `dropped` (either may be NULL); counts_out[0] = #kept, counts_out[1] = #dropped.
+ * row_bytes must be a multiple of 16. */
+int sg_compact_rows(const void* rows, int64_t n, int64_t row_bytes, const uint8_t* mask, void* kept,
+                    void* dropped, int64_t* counts_out, void* workspace, void* stream);
+/* out[i] = rows[idx[i]] for i < count (count read from *count_dev if non-NULL, else `count`). */
+int sg_gather_rows(const void* rows, int64_t row_bytes, const int64_t* idx, int64_t count,
+                   const int64_t* count_dev, void* out, void* stream);
+
+/* ---- moments / z-score / histogram ------------------------------------------------------
+ * replaces err.mean() + k*err.std() "#autoencoder.py:320", the feature z-score
+ * "#z_score.py:286-291" / "# 1,2,8.py:164-168" and np.histogram "#strainer gan.py:293".        */
+#define SG_MOMENT_CHUNK 4096
+/* partial[2*c] = sum, partial[2*c+1] = sum of squares (fp64, fixed pairwise order) of chunk c of
+ * SG_MOMENT_CHUNK values; chunks are in index order so any sharding that aligns to the chunk
+ * size reproduces the single-device partials bit for bit. */
+int sg_chunk_moments(const float* v, int64_t n, double* partial, void* stream);
+/* stats[0] = mean, stats[1] = unbiased std (fp64) of n values from `chunks` partials, summed in
+ * chunk order; thr[0] = (float)mean + k * (float)std as torch evaluates it in fp32. */
+int sg_moments_finish(const double* partial, int64_t chunks, int64_t n, float k, double* stats, float* thr,
+                      void* stream);
+size_t sg_col_moments_workspace_bytes(int64_t n, int d);
+/* mean[d], inv-or-std[d] of the columns of x[n,d]; ddof 1 (torch.std) or 0 (np.std);
+ * denom[j] = std_j + eps_add. */
+int sg_col_moments(const float* x, int64_t n, int d, int ddof, float eps_add, float* mean, float* denom,
+                   void* workspace, void* stream);
+/* out[i] = max_j |(x[i,j] - mean[j]) / denom[j]| (NaN propagates like torch.max) */
+int sg_row_max_absz(const float* x, int64_t n, int d, const float* mean, const float* denom, float* out,
+                    void* stream);
+/* minmax: device buffer of 8 floats; [0] = min, [1] = max (both NaN if any NaN), [2..8) scratch */
+int sg_minmax(const float* v, int64_t n, float* minmax, void* stream);
+/* np.histogram's uniform-bin fast path: edges[bins+1] fp32 (as np.linspace made them),
+ * counts[bins] int64 accumulated (caller zeroes). */
+int sg_hist_uniform(const float* v, int64_t n, const float* edges, int bins, long long* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRAINER_B200_H_ */

@@ -1,0 +1,98 @@
+"""ctypes binding of libstrainer_b200.so (the C ABI declared in include/strainer_b200.h).
+
+There is no fallback of any kind: if the shared library is missing, or the device is not an
+sm_100 GPU, every call raises."""
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libstrainer_b200.so")
+
+SG_LT, SG_LE, SG_GE, SG_GT = 0, 1, 2, 3
+SG_NOT = 4  # OR-ed into a comparison: logical negation (NaN-correct complement)
+SG_LERP_NUMPY, SG_LERP_TORCH = 0, 1
+SG_CONV_BF16, SG_CONV_BF16X3 = 0, 1
+SG_SELECT_WS_WORDS = 4096
+SG_SELECT_WS_NANCOUNT = 2048
+SG_SELECT_WS_MINABOVE = 2049
+SG_SELECT_NUM_PASSES = 3
+SG_MOMENT_CHUNK = 4096
+
+P = c_void_p
+_SIGS = {
+    "sg_version": (c_int, []),
+    "sg_last_error_string": (ctypes.c_char_p, []),
+    "sg_init": (c_int, [c_int]),
+    "sg_sm_count": (c_int, []),
+    "sg_synth_images": (c_int, [P, c_int64, c_int64, c_uint32, P]),
+    "sg_d64_packed_bytes": (c_size_t, [c_int]),
+    "sg_d64_pack": (c_int, [P] * 17 + [c_float, c_int, P, P]),
+    "sg_d64_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "sg_d64_score": (c_int, [P, c_int64, P, P, c_int, P, P, P, P]),
+    "sg_d64_check": (c_int, [P, P]),
+    "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),
+    "sg_select_begin": (c_int, [P, c_int64, P]),
+    "sg_select_hist": (c_int, [P, c_int64, P, c_int, P]),
+    "sg_select_step": (c_int, [P, c_int, P]),
+    "sg_select_min_above": (c_int, [P, c_int64, P, P]),
+    "sg_select_finish": (c_int, [P, P, P]),
+    "sg_radix_select": (c_int, [P, c_int64, c_int64, P, P, P]),
+    "sg_lerp_threshold": (c_int, [P, c_float, c_int, P, P]),
+    "sg_segment_order_stats": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
+    "sg_compact_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_compact_indices": (c_int, [P, c_int64, P, c_int, c_int64, P, P, P, P, P]),
+    "sg_compact_rows": (c_int, [P, c_int64, c_int64, P, P, P, P, P, P]),
+    "sg_gather_rows": (c_int, [P, c_int64, P, c_int64, P, P, P]),
+    "sg_chunk_moments": (c_int, [P, c_int64, P, P]),
+    "sg_moments_finish": (c_int, [P, c_int64, c_int64, c_float, P, P, P]),
+    "sg_col_moments_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "sg_col_moments": (c_int, [P, c_int64, c_int, c_int, c_float, P, P, P, P]),
+    "sg_row_max_absz": (c_int, [P, c_int64, c_int, P, P, P, P]),
+    "sg_minmax": (c_int, [P, c_int64, P, P]),
+    "sg_hist_uniform": (c_int, [P, c_int64, P, c_int, P, P]),
+}
+
+_lib = None
+_inited_device = None
+
+
+def load():
+    """dlopen the library (works without a GPU; compute calls then fail with SG_ENOINIT/SG_EARCH)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is not built. Run `python __graft_entry__.py` (build()) first; "
+                "strainer_b200 has no CPU or PyTorch fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().sg_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"strainer_b200: {what} failed with status {rc}: {last_error()}")
+
+
+def init(device_index):
+    """Bind the library to a CUDA device (once per process / device)."""
+    global _inited_device
+    lib = load()
+    if _inited_device != device_index:
+        check(lib.sg_init(int(device_index)), "sg_init")
+        _inited_device = device_index
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)

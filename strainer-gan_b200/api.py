@@ -1,0 +1,647 @@
+"""Host-side mirror of the reference's straining functions.
+
+Same names, positional parameters, defaults and return types as the functions / inline blocks of
+the reference scripts (cited per function), with the compute moved to libstrainer_b200.so:
+tcgen05 implicit-GEMM discriminator scoring, radix select, single-pass compaction.  PyTorch is used
+only for device memory, streams and torch.distributed.  There is NO CPU fallback: without an
+sm_100 GPU or without the built library every entry point raises.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_c = L  # short alias
+
+
+# ----------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------
+def _dev(device=None) -> torch.device:
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    device = torch.device(device) if device is not None else None
+    if device is None or device.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("strainer_b200 needs a CUDA (sm_100a) device; it has no CPU fallback "
+                           f"(asked for device={device!r})")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _lib_for(device: torch.device):
+    return L.init(device.index)
+
+
+def _stream():
+    return L.P(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return L.P(t.data_ptr()) if t is not None else L.P(0)
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(np.asarray(t))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class _Scratch:
+    """Per-device cache of workspaces (caller-owned buffers of the C ABI)."""
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, device, key, nbytes, dtype=torch.uint8):
+        k = (device.index, key)
+        t = cls._cache.get(k)
+        n = (int(nbytes) + 1023) // 1024 * 1024
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=torch.uint8, device=device)
+            cls._cache[k] = t
+        return t
+
+
+# ----------------------------------------------------------------------------------------------
+# order statistics / thresholds on device
+# ----------------------------------------------------------------------------------------------
+def _np_percentile_plan(n: int, q):
+    """(k_prev, k_next, gamma) exactly as numpy 2.x ``_quantile`` (method 'linear') derives them for
+    a float32 array: q/100 in the array dtype for python scalars, virtual index (n-1)*q."""
+    qq = np.true_divide(q, np.float32(100))
+    v = np.asanyarray((n - 1) * qq)
+    if not (0.0 <= float(qq) <= 1.0):
+        raise ValueError("Percentiles must be in the range [0, 100]")
+    prev = np.floor(v)
+    if v >= n - 1:
+        return n - 1, n - 1, v.dtype.type(v - (n - 1)), v.dtype
+    if v < 0:
+        return 0, 0, v.dtype.type(v), v.dtype
+    return int(prev), int(prev) + 1, v.dtype.type(v - prev), v.dtype
+
+
+def _torch_quantile_plan(n: int, q: float):
+    """(below, above, weight) as ATen ``quantile_compute``: rank = q*(n-1) in fp32."""
+    if not 0.0 <= q <= 1.0:
+        raise RuntimeError("quantile() q values must be in the range [0, 1]")
+    rank = np.float32(q) * np.float32(n - 1)
+    below = np.floor(rank)
+    return int(below), int(np.ceil(rank)), np.float32(rank - below)
+
+
+def order_stats(values: torch.Tensor, k: int, group=None) -> torch.Tensor:
+    """Device tensor [x_(k), x_(k+1)] of a 1-D fp32 CUDA tensor (radix select, no sort).
+    With ``group`` (torch.distributed), ``values`` is this rank's shard and k the GLOBAL rank; the
+    integer histograms are all-reduced so every rank gets identical results."""
+    device = values.device
+    lib = _lib_for(device)
+    n = values.numel()
+    ws = torch.empty(L.SG_SELECT_WS_WORDS, dtype=torch.int32, device=device)
+    out2 = torch.empty(2, dtype=torch.float32, device=device)
+    st = _stream()
+    if group is None:
+        L.check(lib.sg_radix_select(_p(values), n, k, _p(ws), _p(out2), st), "sg_radix_select")
+        return out2
+    import torch.distributed as dist
+    L.check(lib.sg_select_begin(_p(ws), k, st), "sg_select_begin")
+    for p in range(L.SG_SELECT_NUM_PASSES):
+        L.check(lib.sg_select_hist(_p(values), n, _p(ws), p, st), "sg_select_hist")
+        dist.all_reduce(ws[:L.SG_SELECT_WS_NANCOUNT + 1], op=dist.ReduceOp.SUM, group=group)
+        L.check(lib.sg_select_step(_p(ws), p, st), "sg_select_step")
+    L.check(lib.sg_select_min_above(_p(values), n, _p(ws), st), "sg_select_min_above")
+    m = ws[L.SG_SELECT_WS_MINABOVE:L.SG_SELECT_WS_MINABOVE + 1]
+    m ^= -2147483648  # unsigned order -> signed order
+    dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
+    m ^= -2147483648
+    L.check(lib.sg_select_finish(_p(ws), _p(out2), st), "sg_select_finish")
+    return out2
+
+
+def _lerp_dev(stats2: torch.Tensor, weight, kind: int) -> torch.Tensor:
+    thr = torch.empty(1, dtype=torch.float32, device=stats2.device)
+    lib = _lib_for(stats2.device)
+    L.check(lib.sg_lerp_threshold(_p(stats2), float(weight), kind, _p(thr), _stream()), "sg_lerp_threshold")
+    return thr
+
+
+def percentile_device(values: torch.Tensor, q, group=None, n_global=None) -> torch.Tensor:
+    """``np.percentile(values_f32, q)`` evaluated on the GPU; returns a 1-element fp32 device tensor
+    holding bit-for-bit numpy's result for python-scalar q (numpy evaluates q and the lerp in fp32)."""
+    n = values.numel() if n_global is None else int(n_global)
+    k0, k1, gamma, gdt = _np_percentile_plan(n, q)
+    stats2 = order_stats(values, k0, group)
+    if gdt != np.float32:
+        # np.float64 q: numpy interpolates in float64 -> host finish on the two order statistics
+        a, b = stats2.cpu().numpy().astype(np.float64)
+        d = b - a
+        r = a + d * gamma if gamma < 0.5 else b - d * (1 - gamma)
+        return torch.tensor([r], dtype=torch.float64)
+    if k1 == k0:
+        stats2 = torch.stack([stats2[0], stats2[0]])
+    return _lerp_dev(stats2, gamma, L.SG_LERP_NUMPY)
+
+
+def quantile_device(values: torch.Tensor, q: float) -> torch.Tensor:
+    """``torch.quantile(values, q)`` for a 1-D fp32 CUDA tensor; 1-element device tensor."""
+    n = values.numel()
+    k0, k1, w = _torch_quantile_plan(n, float(q))
+    device = values.device
+    lib = _lib_for(device)
+    if n <= 2048:
+        stats2 = torch.empty(2, dtype=torch.float32, device=device)
+        L.check(lib.sg_segment_order_stats(_p(values), 1, n, k0, k1, _p(stats2), _stream()), "sg_segment_order_stats")
+    else:
+        stats2 = order_stats(values, k0)
+        if k1 == k0:
+            stats2 = torch.stack([stats2[0], stats2[0]])
+    return _lerp_dev(stats2, w, L.SG_LERP_TORCH)
+
+
+def _f32_threshold(thr, cmp: int) -> np.float32:
+    """Directed rounding of a (possibly float64) threshold so that the fp32 device comparison
+    ``v CMP thr32`` equals numpy's promoted comparison ``v_f32 CMP thr`` for every fp32 v."""
+    t = np.float64(thr)
+    f = np.float32(t)
+    if np.isnan(t) or np.float64(f) == t:
+        return f
+    lo = f if np.float64(f) < t else np.nextafter(f, np.float32(-np.inf))
+    hi = f if np.float64(f) > t else np.nextafter(f, np.float32(np.inf))
+    return np.float32(hi) if (cmp & 3) in (L.SG_LT, L.SG_GE) else np.float32(lo)
+
+
+def compact_indices(values: torch.Tensor, thr, cmp: int = L.SG_LT, index_base: int = 0, want_mask: bool = False):
+    """Ascending int64 indices i (+index_base) with values[i] CMP thr, as ``np.where(...)[0]``.
+    ``thr`` is a 1-element fp32 device tensor or a host scalar.  Returns (idx_buffer, count_dev, mask)
+    -- all on device, no synchronisation; idx_buffer[:count] is valid."""
+    device = values.device
+    lib = _lib_for(device)
+    n = values.numel()
+    if not isinstance(thr, torch.Tensor):
+        thr = torch.tensor([_f32_threshold(thr, cmp)], dtype=torch.float32).to(device)
+    elif thr.dtype != torch.float32 or thr.device != device:
+        thr = torch.tensor([_f32_threshold(float(thr.reshape(-1)[0]), cmp)], dtype=torch.float32).to(device)
+    idx = torch.empty(max(n, 1), dtype=torch.int64, device=device)
+    count = torch.empty(1, dtype=torch.int64, device=device)
+    mask = torch.empty(max(n, 1), dtype=torch.uint8, device=device) if want_mask else None
+    ws = _Scratch.get(device, "compact", lib.sg_compact_workspace_bytes(n))
+    L.check(lib.sg_compact_indices(_p(values), n, _p(thr), cmp, index_base, _p(idx), _p(count), _p(mask), _p(ws),
+                                   _stream()), "sg_compact_indices")
+    return idx, count, (mask[:n] if want_mask else None)
+
+
+def partition_rows(rows: torch.Tensor, mask: torch.Tensor, kept_out=None, dropped_out=None):
+    """Stable two-way row partition ``(rows[mask], rows[~mask])`` in ONE pass.  ``kept_out`` /
+    ``dropped_out`` may be pre-sized destination views (e.g. the tail of the fake batch).
+    Returns (kept_buffer, dropped_buffer, counts_dev[2])."""
+    device = rows.device
+    lib = _lib_for(device)
+    n = rows.shape[0]
+    rows = rows.contiguous()
+    row_bytes = rows[0].numel() * rows.element_size() if n else 16
+    m8 = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
+    kept = kept_out if kept_out is not None else torch.empty_like(rows)
+    dropped = dropped_out if dropped_out is not None else torch.empty_like(rows)
+    counts = torch.empty(2, dtype=torch.int64, device=device)
+    ws = _Scratch.get(device, "compact", lib.sg_compact_workspace_bytes(n))
+    L.check(lib.sg_compact_rows(_p(rows), n, row_bytes, _p(m8), _p(kept), _p(dropped), _p(counts), _p(ws), _stream()),
+            "sg_compact_rows")
+    return kept, dropped, counts
+
+
+# ----------------------------------------------------------------------------------------------
+# D64 scoring
+# ----------------------------------------------------------------------------------------------
+_MODES = {"bf16": L.SG_CONV_BF16, "fp32": L.SG_CONV_BF16X3, "bf16x3": L.SG_CONV_BF16X3}
+
+
+def _d64_modules(discriminator: nn.Module):
+    """The five Conv2d and three BatchNorm2d of the reference Discriminator ("#strainer gan.py:230-256");
+    anything else is rejected (no fallback)."""
+    mod = discriminator.module if isinstance(discriminator, nn.DataParallel) else discriminator
+    convs = [m for m in mod.modules() if isinstance(m, nn.Conv2d)]
+    bns = [m for m in mod.modules() if isinstance(m, nn.BatchNorm2d)]
+    shapes = [tuple(c.weight.shape) for c in convs]
+    want = [(64, 3, 4, 4), (128, 64, 4, 4), (256, 128, 4, 4), (512, 256, 4, 4), (1, 512, 4, 4)]
+    ok = shapes == want and len(bns) == 3 and all(c.bias is None for c in convs)
+    ok = ok and [c.stride for c in convs] == [(2, 2)] * 4 + [(1, 1)] and [c.padding for c in convs] == [(1, 1)] * 4 + [(0, 0)]
+    if not ok:
+        raise NotImplementedError(
+            "strainer_b200 scores the reference's 64x64 DCGAN Discriminator (nc=3, ndf=64) only; got conv shapes "
+            f"{shapes} with {len(bns)} BatchNorm2d layers")
+    return convs, bns
+
+
+class D64Scorer:
+    """Packs a reference ``Discriminator``'s weights for the tcgen05 kernels and scores batches:
+    eval-mode BN folded into the conv epilogues, sigmoid and BCE-vs-1 fused into the head.
+
+    mode 'bf16': bf16 operands / fp32 accumulate.  mode 'fp32': fp32-parity arithmetic (bf16 hi/lo
+    split, 3 tensor-core passes, ~1e-5 relative on the losses)."""
+
+    def __init__(self, discriminator: nn.Module, device=None, mode: str = "fp32", max_batch: int = 4096):
+        self.device = _dev(device)
+        self.lib = _lib_for(self.device)
+        if mode not in _MODES:
+            raise ValueError(f"mode must be one of {sorted(_MODES)}")
+        self.mode_name = mode
+        self.mode = _MODES[mode]
+        self.max_batch = int(max_batch)
+        self.packed = torch.empty(self.lib.sg_d64_packed_bytes(self.mode), dtype=torch.uint8, device=self.device)
+        self.ws = torch.empty(self.lib.sg_d64_workspace_bytes(self.max_batch, self.mode), dtype=torch.uint8,
+                              device=self.device)
+        self._sig = None
+        self.repack(discriminator)
+
+    @staticmethod
+    def _signature(convs, bns):
+        ts = [c.weight for c in convs]
+        for b in bns:
+            ts += [b.weight, b.bias, b.running_mean, b.running_var]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def repack(self, discriminator: nn.Module, force: bool = False):
+        convs, bns = _d64_modules(discriminator)
+        sig = self._signature(convs, bns)
+        if sig == self._sig and not force:
+            return
+        with torch.no_grad():
+            args = [_f32c(c.weight.detach(), self.device) for c in convs]
+            for b in bns:
+                args += [_f32c(t.detach(), self.device) for t in (b.weight, b.bias, b.running_mean, b.running_var)]
+        eps = {float(b.eps) for b in bns}
+        if len(eps) != 1:
+            raise NotImplementedError("BatchNorm layers with different eps")
+        L.check(self.lib.sg_d64_pack(*[_p(a) for a in args], eps.pop(), self.mode, _p(self.packed), _stream()),
+                "sg_d64_pack")
+        self._keep = args  # stream-ordered: keep alive until the pack kernels ran
+        self._sig = sig
+
+    def score_into(self, x: torch.Tensor, logit=None, prob=None, loss=None):
+        """x: fp32 CUDA [b,3,64,64], b <= max_batch; writes into the given device slices."""
+        b = x.shape[0]
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        L.check(self.lib.sg_d64_score(_p(x), b, _p(self.packed), _p(self.ws), self.mode, _p(logit), _p(prob), _p(loss),
+                                      _stream()), "sg_d64_score")
+
+    def check(self):
+        L.check(self.lib.sg_d64_check(_p(self.ws), _stream()), "sg_d64_check")
+
+    def read_activation(self, batch: int, layer: int) -> torch.Tensor:
+        c, s = {1: (64, 32), 2: (128, 16), 3: (256, 8), 4: (512, 4)}[layer]
+        out = torch.empty(batch, c, s, s, dtype=torch.float32, device=self.device)
+        L.check(self.lib.sg_d64_read_activation(_p(self.ws), batch, self.mode, layer, _p(out), _stream()),
+                "sg_d64_read_activation")
+        return out
+
+    def score(self, images: torch.Tensor, want=("loss",)):
+        """Scores N images (CUDA tensor, or a host tensor streamed through pinned double buffers with the
+        H2D copies overlapped with compute).  Returns a dict of fp32 device tensors [N]."""
+        n = images.shape[0]
+        outs = {k: torch.empty(n, dtype=torch.float32, device=self.device) for k in want}
+        if images.dtype != torch.float32 or tuple(images.shape[1:]) != (3, 64, 64):
+            raise ValueError("images must be float32 [N,3,64,64]")
+
+        def sl(name, i, b):
+            return outs[name][i:i + b] if name in outs else None
+
+        if images.is_cuda:
+            images = images.contiguous()
+            for i in range(0, n, self.max_batch):
+                b = min(self.max_batch, n - i)
+                self.score_into(images[i:i + b], sl("logit", i, b), sl("prob", i, b), sl("loss", i, b))
+            return outs
+        # host path: 2 pinned staging buffers + 2 device buffers, copy stream ahead of compute
+        cb = self.max_batch
+        images = images.contiguous()
+        pinned_src = images.is_pinned()
+        main = torch.cuda.current_stream()
+        copy_stream = _copy_stream(self.device)
+        dev = [torch.empty((cb, 3, 64, 64), dtype=torch.float32, device=self.device) for _ in range(2)]
+        pin = None if pinned_src else [torch.empty((cb, 3, 64, 64), dtype=torch.float32).pin_memory() for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        nchunks = (n + cb - 1) // cb
+        for ci in range(nchunks):
+            s = ci & 1
+            i = ci * cb
+            b = min(cb, n - i)
+            if ci >= 2 and not pinned_src:
+                copied[s].synchronize()  # the H2D copy that last read pin[s] has finished
+            with torch.cuda.stream(copy_stream):
+                if ci >= 2:
+                    copy_stream.wait_event(consumed[s])
+                src = images[i:i + b]
+                if not pinned_src:
+                    pin[s][:b].copy_(src)
+                    src = pin[s][:b]
+                dev[s][:b].copy_(src, non_blocking=True)
+                copied[s].record(copy_stream)
+            main.wait_event(copied[s])
+            self.score_into(dev[s][:b], sl("logit", i, b), sl("prob", i, b), sl("loss", i, b))
+            consumed[s].record(main)
+        return outs
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(device):
+    s = _COPY_STREAMS.get(device.index)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _COPY_STREAMS[device.index] = s
+    return s
+
+
+_SCORERS: dict = {}
+
+
+def get_scorer(discriminator: nn.Module, device=None, mode: str = "fp32", max_batch: int = 4096) -> D64Scorer:
+    device = _dev(device)
+    key = (id(discriminator), device.index, mode, max_batch)
+    sc = _SCORERS.get(key)
+    if sc is None:
+        sc = D64Scorer(discriminator, device, mode, max_batch)
+        _SCORERS[key] = sc
+    else:
+        sc.repack(discriminator)
+    return sc
+
+
+def _dataset_images(dataset):
+    """Resident image tensor of a dataset if it exposes one (TensorDataset / Subset of it), else
+    materialise it through the dataset's own __getitem__ (host side, as the reference's DataLoader)."""
+    from torch.utils.data import Subset, TensorDataset
+    if isinstance(dataset, torch.Tensor):
+        return dataset
+    if isinstance(dataset, TensorDataset):
+        return dataset.tensors[0]
+    if isinstance(dataset, Subset):
+        base = _dataset_images(dataset.dataset)
+        idx = torch.as_tensor(np.asarray(dataset.indices).reshape(-1), dtype=torch.long, device=base.device)
+        return base.index_select(0, idx)
+    return torch.stack([dataset[i][0] for i in range(len(dataset))])
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's function boundary
+# ----------------------------------------------------------------------------------------------
+def evaluate_dataset(netD, dataset, device, *, conv_mode: str = "fp32", return_device: bool = False):
+    """``evaluate_dataset`` ("#clean 분포와 ... .py:272-287", "# 종합 loss.py:315-330"): per-sample
+    BCE(D(x), 1) with eval-mode BN (sticky ``netD.eval()``); returns np.ndarray (N,) float32."""
+    device = _dev(device)
+    netD.eval()
+    images = _dataset_images(dataset)
+    losses = get_scorer(netD, device, conv_mode).score(images, ("loss",))["loss"]
+    return losses if return_device else losses.cpu().numpy()
+
+
+def refine_dataset_by_loss(dataset, discriminator, device, loss_ratio=0.2, *, conv_mode: str = "fp32"):
+    """``refine_dataset_by_loss`` ("#strainer gan.py:364-392"): score every sample, threshold at the
+    (1-loss_ratio)*100 percentile, keep ``loss < threshold`` in ascending index order.
+    Returns (torch.utils.data.Subset, np.float32 threshold)."""
+    device = _dev(device)
+    discriminator.eval()  # sticky, as in the reference
+    images = _dataset_images(dataset)
+    n = images.shape[0]
+    losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
+    clean_indices, threshold = select_below_percentile(losses, (1 - loss_ratio) * 100)
+    if len(clean_indices) == 0:
+        # reference fallback on its (N,1,1)-shaped loss array: argsort along the last axis (len 1) -> zeros
+        clean_indices = np.zeros((max(n // 2, 1), 1, 1), dtype=np.intp)
+    return torch.utils.data.Subset(dataset, clean_indices), threshold
+
+
+def select_below_percentile(losses: torch.Tensor, q, group=None, index_base: int = 0, n_global=None):
+    """threshold = np.percentile(losses, q); indices = np.where(losses < threshold)[0] -- on device.
+    One host sync at the end (count + threshold).  Returns (np.int64 indices, np.float32 threshold)."""
+    thr = percentile_device(losses, q, group, n_global)
+    idx, count, _ = compact_indices(losses, thr, L.SG_LT, index_base)
+    thr_h = thr.cpu().numpy()[0]
+    c = int(count.item())
+    return idx[:c].cpu().numpy(), thr_h
+
+
+def get_percentile_threshold(losses, percentile=75):
+    """"# 종합 loss.py:287-288" on a device (or host) loss vector."""
+    lt = _f32c(losses, _dev()).reshape(-1)
+    return percentile_device(lt, percentile).cpu().numpy()[0]
+
+
+def get_iqr_threshold(losses):
+    """"# 종합 loss.py:290-294": Q3 + 1.5 * (Q3 - Q1)."""
+    lt = _f32c(losses, _dev()).reshape(-1)
+    q1 = percentile_device(lt, 25).cpu().numpy()[0]
+    q3 = percentile_device(lt, 75).cpu().numpy()[0]
+    return q3 + 1.5 * (q3 - q1)
+
+
+def _gmm_intersection(means, stds):
+    ci = np.argmin(means)
+    ni = 1 - ci
+    a = 1 / (2 * stds[ci] ** 2) - 1 / (2 * stds[ni] ** 2)
+    b = means[ni] / (stds[ni] ** 2) - means[ci] / (stds[ci] ** 2)
+    c = means[ci] ** 2 / (2 * stds[ci] ** 2) - means[ni] ** 2 / (2 * stds[ni] ** 2) - np.log(stds[ni] / stds[ci])
+    return (-b + np.sqrt(b ** 2 - 4 * a * c)) / (2 * a)
+
+
+def get_gmm_threshold(losses):
+    """"# 종합 loss.py:270-285".  The 2-component EM fit stays scikit-learn on the host (SURVEY §2.2
+    K18); it is seeded by the global np.random state exactly like the reference."""
+    from sklearn.mixture import GaussianMixture
+    lo = losses.cpu().numpy() if isinstance(losses, torch.Tensor) else np.asarray(losses)
+    gmm = GaussianMixture(n_components=2, max_iter=10, tol=1e-2, reg_covar=5e-4)
+    gmm.fit(lo.reshape(-1, 1))
+    return _gmm_intersection(gmm.means_.flatten(), np.sqrt(gmm.covariances_.flatten()))
+
+
+def get_ensemble_threshold(losses):
+    """"# 종합 loss.py:296-301"."""
+    return np.median([get_gmm_threshold(losses), get_percentile_threshold(losses), get_iqr_threshold(losses)])
+
+
+def _divide(losses, dataset, threshold):
+    lt = _f32c(losses, _dev()).reshape(-1)
+    n = lt.numel()
+    idx, count, _ = compact_indices(lt, threshold, L.SG_LT, 0)
+    nidx, ncount, _ = compact_indices(lt, threshold, L.SG_LT | L.SG_NOT, 0)  # ~(loss < thr): NaNs are noisy
+    c, nc_ = int(count.item()), int(ncount.item())
+    assert c + nc_ == n
+    sub = torch.utils.data.Subset
+    return sub(dataset, idx[:c].cpu().numpy()), sub(dataset, nidx[:nc_].cpu().numpy())
+
+
+def divide_dataset(losses, dataset):
+    """GMM form, "#clean 분포와 ... .py:289-316": clean = losses < intersection threshold."""
+    return _divide(losses, dataset, get_gmm_threshold(losses))
+
+
+def divide_dataset_ensemble(losses, dataset):
+    """Ensemble form, "# 종합 loss.py:303-312"."""
+    return _divide(losses, dataset, get_ensemble_threshold(losses))
+
+
+# ---- feature z-score / elbow -------------------------------------------------------------------
+def zscore_max(features, ddof: int = 1, eps_add: float = 0.0) -> torch.Tensor:
+    """max_j |(x_ij - mean_j) / (std_j + eps_add)| per row of a [N, D] feature matrix
+    ("#z_score.py:286-291" with ddof=1; "# 1,2,8.py:164-168" with ddof=0, eps_add=1e-7). Device tensor."""
+    device = _dev()
+    lib = _lib_for(device)
+    x = _f32c(features, device)
+    n, d = x.shape
+    mean = torch.empty(d, dtype=torch.float32, device=device)
+    denom = torch.empty(d, dtype=torch.float32, device=device)
+    ws = _Scratch.get(device, "colmom", lib.sg_col_moments_workspace_bytes(n, d))
+    L.check(lib.sg_col_moments(_p(x), n, d, ddof, float(np.float32(eps_add)), _p(mean), _p(denom), _p(ws), _stream()),
+            "sg_col_moments")
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    L.check(lib.sg_row_max_absz(_p(x), n, d, _p(mean), _p(denom), _p(out), _stream()), "sg_row_max_absz")
+    return out
+
+
+def find_elbow_threshold(z_scores, bins=100):
+    """``find_elbow_threshold`` ("#strainer gan.py:291-309").  min/max and the 100-bin histogram run
+    on the device with numpy's exact bin arithmetic; the 100-element tail is numpy on the host."""
+    device = _dev()
+    lib = _lib_for(device)
+    z = _f32c(z_scores, device).reshape(-1)
+    n = z.numel()
+    mm = torch.empty(8, dtype=torch.float32, device=device)
+    L.check(lib.sg_minmax(_p(z), n, _p(mm), _stream()), "sg_minmax")
+    first, last = mm[:2].cpu().numpy()
+    if not (np.isfinite(first) and np.isfinite(last)):
+        raise ValueError(f"autodetected range of [{first}, {last}] is not finite")
+    if first == last:
+        first, last = first - 0.5, last + 0.5
+    bin_edges = np.linspace(first, last, bins + 1, endpoint=True, dtype=np.result_type(first, last, np.float32))
+    counts = torch.zeros(bins, dtype=torch.int64, device=device)
+    edges_d = torch.from_numpy(bin_edges.astype(np.float32)).to(device)
+    L.check(lib.sg_hist_uniform(_p(z), n, _p(edges_d), bins, _p(counts), _stream()), "sg_hist_uniform")
+    cnt = counts.cpu().numpy()
+    db = np.array(np.diff(bin_edges), float)
+    hist = cnt / db / cnt.sum()
+    bin_centers = (bin_edges[:-1] + bin_edges[1:]) / 2
+    peak_index = np.argmax(hist)
+    target_index = np.argmin(np.abs(hist[peak_index:] - 0.01))
+    threshold = (bin_centers[peak_index] + bin_centers[peak_index:][target_index]) / 2
+    return threshold, bin_centers, hist
+
+
+def _features_of(dataset, feature_extractor, device):
+    imgs = _dataset_images(dataset)
+    if feature_extractor is None or isinstance(feature_extractor, nn.Identity):
+        return _f32c(imgs, device)
+    feats = []
+    with torch.no_grad():
+        for i in range(0, imgs.shape[0], 64):
+            feats.append(feature_extractor(imgs[i:i + 64].to(device)).float())
+    return torch.cat(feats, dim=0)
+
+
+def detect_outliers(dataset, feature_extractor, user_threshold=None, *, threshold=None, clean_ratio=None):
+    """The four ``detect_outliers`` variants of the reference, selected by keyword:
+      default / ``user_threshold``  -> "#strainer gan.py:331-360" (elbow or user value; numpy bool)
+      ``threshold=5.0``             -> "#z_score.py:276-294" (fixed, strict <; torch bool)
+      ``clean_ratio=r``             -> "# z_score + DBSCAN.py:305-326" (torch.quantile(max_z, r), <=)
+    Feature extraction itself (pretrained ResNet18) is out of scope: pass the module, or nn.Identity()
+    over a dataset of feature rows."""
+    device = _dev()
+    mz = zscore_max(_features_of(dataset, feature_extractor, device))
+    if clean_ratio is not None:
+        thr = quantile_device(mz, float(clean_ratio))
+        _, _, mask = compact_indices(mz, thr, L.SG_LE, 0, want_mask=True)
+        return mask.bool().cpu()
+    if threshold is not None:
+        _, _, mask = compact_indices(mz, float(threshold), L.SG_LT, 0, want_mask=True)
+        return mask.bool().cpu()
+    thr = find_elbow_threshold(mz)[0] if user_threshold is None else user_threshold
+    _, _, mask = compact_indices(mz, thr, L.SG_LT, 0, want_mask=True)
+    return mask.bool().cpu().numpy()
+
+
+def compute_z_scores(dataset, feature_extractor):
+    """``compute_z_scores`` ("# 1,2,8.py:154-170"): np.std (ddof 0) + 1e-7; returns np.ndarray (N,)."""
+    device = _dev()
+    return zscore_max(_features_of(dataset, feature_extractor, device), ddof=0, eps_add=1e-7).cpu().numpy()
+
+
+# ---- in-batch strain + concat --------------------------------------------------------------------
+def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1, fake: torch.Tensor | None = None):
+    """Selection half of the in-batch block ("# 상위 10% 제거해서 fake image에 concate.py:246-249"):
+    threshold = torch.quantile(scores, q); mask = scores >= threshold; real[mask], real[~mask] in one
+    pass.  With ``fake`` given the strained rows are written straight behind the fake rows of a
+    pre-sized buffer (the ``torch.cat`` of ":268" fused away); use ``concat_fake`` for autograd."""
+    device = real.device
+    scores = real_scores.reshape(-1).to(torch.float32).contiguous()
+    thr = quantile_device(scores, q)
+    _, _, mask = compact_indices(scores, thr, L.SG_GE, 0, want_mask=True)
+    kept, dropped, counts = partition_rows(real, mask)
+    c = counts.cpu()
+    nk, nd = int(c[0]), int(c[1])
+    return kept[:nk], dropped[:nd], mask.bool(), thr[0]
+
+
+def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "fp32"):
+    """The in-batch strain block ("# 상위 10% 제거해서 fake image에 concate.py:243-251") for a netD in EVAL
+    mode (after any dataset-scale strain the reference's D is in eval mode for good).
+    Returns (filtered_real, filtered_fake, mask, threshold)."""
+    if netD.training and any(isinstance(m, nn.BatchNorm2d) for m in netD.modules()):
+        raise NotImplementedError("strain_batch: train-mode BatchNorm scoring (batch statistics + running-stat "
+                                  "update) is not built yet; call netD.eval() or score with torch and use strain_scores")
+    device = _dev(real.device)
+    sc = get_scorer(netD, device, conv_mode, max_batch=max(real.shape[0], 512))
+    b = real.shape[0]
+    prob = torch.empty(b, dtype=torch.float32, device=device)
+    sc.score_into(real.contiguous(), None, prob, None)
+    return strain_scores(real, prob, q)
+
+
+class _ConcatFake(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fake, strained):
+        ctx.nf = fake.shape[0]
+        out = torch.empty((fake.shape[0] + strained.shape[0],) + tuple(fake.shape[1:]), dtype=fake.dtype,
+                          device=fake.device)
+        out[:ctx.nf].copy_(fake)
+        out[ctx.nf:].copy_(strained)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:ctx.nf], g[ctx.nf:]
+
+
+def concat_fake(fake: torch.Tensor, strained: torch.Tensor) -> torch.Tensor:
+    """``torch.cat([fake, filtered_fake], dim=0)`` (":268"); gradient flows to the generator rows."""
+    return _ConcatFake.apply(fake, strained)
+
+
+def sample_pool(pool: torch.Tensor, b: int, indices: torch.Tensor | None = None) -> torch.Tensor:
+    """``potential_fake_data[torch.randperm(P)[:b]]`` ("# strainer gan + concate.py:623-624"): the
+    permutation is drawn on the host exactly like the reference (same RNG stream), the 48 KiB-row
+    gather runs as one vectorised kernel."""
+    device = _dev(pool.device)
+    lib = _lib_for(device)
+    if indices is None:
+        indices = torch.randperm(pool.size(0))[:b]
+    idx = indices.to(device=device, dtype=torch.int64)
+    pool = pool.contiguous()
+    out = torch.empty((idx.numel(),) + tuple(pool.shape[1:]), dtype=pool.dtype, device=device)
+    row_bytes = pool[0].numel() * pool.element_size()
+    L.check(lib.sg_gather_rows(_p(pool), row_bytes, _p(idx), idx.numel(), L.P(0), _p(out), _stream()), "sg_gather_rows")
+    return out
+
+
+def synth_images(start: int, count: int, seed: int = 999, device=None) -> torch.Tensor:
+    """Counter-based synthetic fp32 [count,3,64,64] images generated on the device."""
+    device = _dev(device)
+    lib = _lib_for(device)
+    out = torch.empty((count, 3, 64, 64), dtype=torch.float32, device=device)
+    L.check(lib.sg_synth_images(_p(out), start, count, seed, _stream()), "sg_synth_images")
+    return out

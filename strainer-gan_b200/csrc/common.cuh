@@ -1,0 +1,112 @@
+// Shared host/device helpers for libstrainer_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/strainer_b200.h"
+
+extern "C" int sg_d64_init_attributes();  // internal: raises the conv kernels' dynamic smem limit
+
+namespace sg {
+
+// ---- host side state / error plumbing -------------------------------------------------
+struct DeviceState {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  void* encode_tiled = nullptr;  // PFN cuTensorMapEncodeTiled
+};
+DeviceState& state();
+void set_error(const char* fmt, ...);
+int check_ready();  // SG_OK or SG_ENOINIT / SG_EARCH
+
+#define SG_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      sg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SG_ECUDA;                                                             \
+    }                                                                              \
+  } while (0)
+
+#define SG_REQUIRE(cond, msg)                                      \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      sg::set_error("invalid argument: %s (%s)", msg, #cond);      \
+      return SG_EINVAL;                                            \
+    }                                                              \
+  } while (0)
+
+#define SG_READY()                      \
+  do {                                  \
+    int _r = sg::check_ready();         \
+    if (_r != SG_OK) return _r;         \
+  } while (0)
+
+#define SG_LAUNCH_CHECK()                                                          \
+  do {                                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      sg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SG_ECUDA;                                                             \
+    }                                                                              \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- device helpers ----------------------------------------------------------------------
+// Monotone fp32 -> uint32 radix key.  NaN (either sign) -> 0xFFFFFFFF (sorts last, as numpy /
+// torch sort do), -0.0 is canonicalised to +0.0.
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFFFFFFFu;
+  if (b == 0x80000000u) b = 0u;
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  if (k == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+  return __uint_as_float(b);
+}
+
+__device__ __forceinline__ bool cmp_apply(float v, float thr, int cmp) {
+  bool r;
+  switch (cmp & 3) {
+    case SG_LT: r = v < thr; break;
+    case SG_LE: r = v <= thr; break;
+    case SG_GE: r = v >= thr; break;
+    default: r = v > thr; break;
+  }
+  return (cmp & SG_NOT) ? !r : r;
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int4 ldg_stream_i4(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_i4(int4* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace sg

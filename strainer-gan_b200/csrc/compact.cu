@@ -1,0 +1,318 @@
+// Stream compaction.
+// Replaces np.where(losses < thr)[0] ("#strainer gan.py:384"), the boolean gathers real_cpu[mask] /
+// real_cpu[~mask] and torch.cat ("# 상위 10% 제거해서 fake image에 concate.py:247-249,268") and the pool
+// gather ("# strainer gan + concate.py:623-627").  The reference does nonzero + index on the host
+// (one device sync per gather); here one single-pass kernel (decoupled look-back scan over dynamic
+// tile ids) produces ascending indices / stable destinations, and a vectorised row mover copies the
+// 48 KiB image rows with 128-bit streaming loads/stores.
+#include "common.cuh"
+
+namespace sg {
+namespace cmp {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;  // 4096 elements per tile
+
+// tile status word: [63:62] flag (0 invalid, 1 aggregate, 2 inclusive prefix) | [61:0] value
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagIncl = 2ull << 62;
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+struct ScanWs {
+  unsigned int tile_counter;
+  unsigned int pad[3];
+  // followed by tile status words
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of this tile's aggregate over all earlier tiles (decoupled look-back, warp 0).
+// Tiles are claimed from an atomic counter, so every predecessor is already running or done.
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* status, int tile, unsigned long long agg,
+                                                       unsigned long long* s_excl) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    if (lane == 0) st_release_u64(&status[tile], (tile == 0 ? kFlagIncl : kFlagAgg) | agg);
+    unsigned long long excl = 0;
+    int pos = tile - 1;
+    while (pos >= 0) {
+      const int idx = pos - lane;
+      unsigned long long w = kFlagIncl;  // virtual tiles before 0: inclusive prefix 0
+      if (idx >= 0) {
+        do { w = ld_acquire_u64(&status[idx]); } while ((w >> 62) == 0ull);
+      }
+      const unsigned incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+      const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;  // nearest tile with a full prefix
+      unsigned long long contrib = (lane <= first_incl) ? (w & kValMask) : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      excl += contrib;
+      if (incl_mask) break;
+      pos -= 32;
+    }
+    if (lane == 0) {
+      if (tile != 0) st_release_u64(&status[tile], kFlagIncl | (excl + agg));
+      *s_excl = excl;
+    }
+  }
+  __syncthreads();
+  return *s_excl;
+}
+
+// Block-wide exclusive scan of one small count per thread; returns the thread's offset, *total = sum.
+__device__ __forceinline__ int block_excl_scan(int c, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int s = (lane < kThreads / 32) ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane < kThreads / 32) s_warp[lane] = s;
+  }
+  __syncthreads();
+  *total = s_warp[kThreads / 32 - 1];
+  return x - c + (w ? s_warp[w - 1] : 0);
+}
+
+// v[i] CMP thr -> ascending global indices (int64) + optional byte mask.
+__global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* __restrict__ v, int64_t n,
+                                                                   const float* __restrict__ thr_p, int cmp,
+                                                                   int64_t index_base, int64_t* __restrict__ idx_out,
+                                                                   int64_t* __restrict__ count_out,
+                                                                   uint8_t* __restrict__ mask_out, ScanWs* ws,
+                                                                   int num_tiles) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ unsigned long long s_excl;
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(ws + 1);
+  const float thr = *thr_p;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= num_tiles) break;
+    const int64_t base = (int64_t)tile * kTile + (int64_t)threadIdx.x * kItems;
+    float x[kItems];
+    if (base + kItems <= n && (reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < kItems / 4; ++q) {
+        const float4 f = ldg_stream4(reinterpret_cast<const float4*>(v + base) + q);
+        x[4 * q] = f.x; x[4 * q + 1] = f.y; x[4 * q + 2] = f.z; x[4 * q + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) x[j] = (base + j < n) ? v[base + j] : 0.f;
+    }
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+      if (base + j < n && cmp_apply(x[j], thr, cmp)) flags |= 1u << j;
+    const int c = __popc(flags);
+    int total;
+    const int toff = block_excl_scan(c, s_warp, &total);
+    const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);
+    int64_t* dst = idx_out + excl + toff;
+    int w = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+      if (flags & (1u << j)) dst[w++] = index_base + base + j;
+    if (mask_out) {
+      if (base + kItems <= n && (reinterpret_cast<uintptr_t>(mask_out) & 15) == 0) {
+        uint32_t m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          m[q] = ((flags >> (4 * q)) & 1u) | (((flags >> (4 * q + 1)) & 1u) << 8) |
+                 (((flags >> (4 * q + 2)) & 1u) << 16) | (((flags >> (4 * q + 3)) & 1u) << 24);
+        *reinterpret_cast<uint4*>(mask_out + base) = make_uint4(m[0], m[1], m[2], m[3]);
+      } else {
+        for (int j = 0; j < kItems; ++j)
+          if (base + j < n) mask_out[base + j] = (flags >> j) & 1u;
+      }
+    }
+    if (tile == num_tiles - 1 && threadIdx.x == 0) *count_out = (int64_t)(excl + total);
+  }
+}
+
+// Stable two-way partition destinations from a byte mask: dest[i] = rank among kept rows (mask != 0)
+// or -(rank among dropped rows) - 1.  counts_out = {#kept, #dropped}.
+__global__ void __launch_bounds__(kThreads) partition_dest_kernel(const uint8_t* __restrict__ mask, int64_t n,
+                                                                  int64_t* __restrict__ dest,
+                                                                  int64_t* __restrict__ counts_out, ScanWs* ws,
+                                                                  int num_tiles) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ unsigned long long s_excl;
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(ws + 1);
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= num_tiles) break;
+    const int64_t base = (int64_t)tile * kTile + (int64_t)threadIdx.x * kItems;
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+      if (base + j < n && mask[base + j] != 0) flags |= 1u << j;
+    const int c = __popc(flags);
+    int total;
+    const int toff = block_excl_scan(c, s_warp, &total);
+    const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);
+    int64_t kept_rank = (int64_t)excl + toff;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int64_t i = base + j;
+      if (i < n) {
+        if (flags & (1u << j)) dest[i] = kept_rank++;
+        else dest[i] = -(i - kept_rank) - 1;  // dropped rank = i - (#kept before i)
+      }
+    }
+    if (tile == num_tiles - 1 && threadIdx.x == 0) {
+      counts_out[0] = (int64_t)(excl + total);
+      counts_out[1] = n - (int64_t)(excl + total);
+    }
+  }
+}
+
+// One CTA per row: 128-bit streaming copy of row i to kept[dest] or dropped[-dest-1].
+__global__ void __launch_bounds__(256) move_rows_kernel(const int4* __restrict__ rows, int64_t row_vec,
+                                                        const int64_t* __restrict__ dest, int4* __restrict__ kept,
+                                                        int4* __restrict__ dropped) {
+  const int64_t i = blockIdx.x;
+  const int64_t d = dest[i];
+  int4* out = (d >= 0) ? kept : dropped;
+  if (out == nullptr) return;
+  const int64_t r = (d >= 0) ? d : (-d - 1);
+  const int4* src = rows + i * row_vec;
+  int4* dst = out + r * row_vec;
+  int64_t j = threadIdx.x;
+  for (; j + 3 * 256 < row_vec; j += 4 * 256) {
+    const int4 a = ldg_stream_i4(src + j), b = ldg_stream_i4(src + j + 256);
+    const int4 c = ldg_stream_i4(src + j + 512), e = ldg_stream_i4(src + j + 768);
+    stg_stream_i4(dst + j, a); stg_stream_i4(dst + j + 256, b);
+    stg_stream_i4(dst + j + 512, c); stg_stream_i4(dst + j + 768, e);
+  }
+  for (; j < row_vec; j += 256) stg_stream_i4(dst + j, ldg_stream_i4(src + j));
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int4* __restrict__ rows, int64_t row_vec,
+                                                          const int64_t* __restrict__ idx,
+                                                          const int64_t* __restrict__ count_dev,
+                                                          int4* __restrict__ out) {
+  const int64_t i = blockIdx.x;
+  if (count_dev && i >= *count_dev) return;
+  const int4* src = rows + idx[i] * row_vec;
+  int4* dst = out + i * row_vec;
+  int64_t j = threadIdx.x;
+  for (; j + 3 * 256 < row_vec; j += 4 * 256) {
+    const int4 a = ldg_stream_i4(src + j), b = ldg_stream_i4(src + j + 256);
+    const int4 c = ldg_stream_i4(src + j + 512), e = ldg_stream_i4(src + j + 768);
+    stg_stream_i4(dst + j, a); stg_stream_i4(dst + j + 256, b);
+    stg_stream_i4(dst + j + 512, c); stg_stream_i4(dst + j + 768, e);
+  }
+  for (; j < row_vec; j += 256) stg_stream_i4(dst + j, ldg_stream_i4(src + j));
+}
+
+static size_t scan_ws_bytes(int64_t n) {
+  const int64_t tiles = ceil_div(n > 0 ? n : 1, kTile);
+  return align_up(sizeof(ScanWs) + (size_t)tiles * 8, 256);
+}
+
+}  // namespace cmp
+}  // namespace sg
+
+extern "C" {
+
+size_t sg_compact_workspace_bytes(int64_t n) {
+  // scan state + one int64 destination per element (row partition)
+  return sg::cmp::scan_ws_bytes(n) + sg::align_up((size_t)(n > 0 ? n : 1) * 8, 256);
+}
+
+int sg_compact_indices(const float* v, int64_t n, const float* thr, int cmp, int64_t index_base, int64_t* idx_out,
+                       int64_t* count_out, uint8_t* mask_out, void* workspace, void* stream) {
+  using namespace sg::cmp;
+  SG_READY();
+  SG_REQUIRE(n >= 0 && thr && count_out && workspace, "arguments");
+  SG_REQUIRE(n == 0 || (v && idx_out), "v/idx_out");
+  SG_REQUIRE(cmp >= 0 && cmp <= (SG_GT | SG_NOT), "cmp");
+  SG_REQUIRE(n < ((int64_t)1 << 42), "n too large");
+  cudaStream_t st = sg::as_stream(stream);
+  if (n == 0) {
+    SG_CUDA(cudaMemsetAsync(count_out, 0, 8, st));
+    return SG_OK;
+  }
+  const int num_tiles = (int)sg::ceil_div(n, kTile);
+  SG_CUDA(cudaMemsetAsync(workspace, 0, scan_ws_bytes(n), st));
+  int grid = num_tiles;
+  const int cap = sg::state().sm_count * 8;
+  if (grid > cap) grid = cap;
+  compact_indices_kernel<<<grid, kThreads, 0, st>>>(v, n, thr, cmp, index_base, idx_out, count_out, mask_out,
+                                                    static_cast<ScanWs*>(workspace), num_tiles);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_compact_rows(const void* rows, int64_t n, int64_t row_bytes, const uint8_t* mask, void* kept, void* dropped,
+                    int64_t* counts_out, void* workspace, void* stream) {
+  using namespace sg::cmp;
+  SG_READY();
+  SG_REQUIRE(n >= 0 && counts_out && workspace, "arguments");
+  SG_REQUIRE(n == 0 || (rows && mask), "rows/mask");
+  SG_REQUIRE(row_bytes > 0 && (row_bytes & 15) == 0, "row_bytes must be a positive multiple of 16");
+  SG_REQUIRE(n <= 0x7FFFFFFF, "n too large for one launch");
+  SG_REQUIRE(((uintptr_t)rows & 15) == 0 && ((uintptr_t)kept & 15) == 0 && ((uintptr_t)dropped & 15) == 0,
+             "row buffers must be 16-byte aligned");
+  cudaStream_t st = sg::as_stream(stream);
+  if (n == 0) {
+    SG_CUDA(cudaMemsetAsync(counts_out, 0, 16, st));
+    return SG_OK;
+  }
+  const int num_tiles = (int)sg::ceil_div(n, kTile);
+  const size_t sbytes = scan_ws_bytes(n);
+  SG_CUDA(cudaMemsetAsync(workspace, 0, sbytes, st));
+  int64_t* dest = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(workspace) + sbytes);
+  int grid = num_tiles;
+  const int cap = sg::state().sm_count * 8;
+  if (grid > cap) grid = cap;
+  partition_dest_kernel<<<grid, kThreads, 0, st>>>(mask, n, dest, counts_out, static_cast<ScanWs*>(workspace), num_tiles);
+  SG_LAUNCH_CHECK();
+  move_rows_kernel<<<(unsigned)n, 256, 0, st>>>(static_cast<const int4*>(rows), row_bytes / 16, dest,
+                                                static_cast<int4*>(kept), static_cast<int4*>(dropped));
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_gather_rows(const void* rows, int64_t row_bytes, const int64_t* idx, int64_t count, const int64_t* count_dev,
+                   void* out, void* stream) {
+  SG_READY();
+  SG_REQUIRE(count >= 0 && count <= 0x7FFFFFFF, "count");
+  SG_REQUIRE(row_bytes > 0 && (row_bytes & 15) == 0, "row_bytes must be a positive multiple of 16");
+  if (count == 0) return SG_OK;
+  SG_REQUIRE(rows && idx && out, "null pointer");
+  SG_REQUIRE(((uintptr_t)rows & 15) == 0 && ((uintptr_t)out & 15) == 0, "row buffers must be 16-byte aligned");
+  sg::cmp::gather_rows_kernel<<<(unsigned)count, 256, 0, sg::as_stream(stream)>>>(
+      static_cast<const int4*>(rows), row_bytes / 16, idx, count_dev, static_cast<int4*>(out));
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,685 @@
+// D64 scoring path: Discriminator.forward (eval-mode BN) + sigmoid + BCE vs label 1.
+// Replaces "#strainer gan.py:230-256" + ":369-375" (K1..K6 of SURVEY.md §2.3).
+//
+//   L1  conv 3->64 k4s2p1 + LeakyReLU        fp32 NCHW in, CUDA-core direct conv, bf16 out
+//   L2  conv 64->128  + BN + LeakyReLU  \
+//   L3  conv 128->256 + BN + LeakyReLU   }   implicit GEMM on tcgen05: TMA-staged 128x64 activation
+//   L4  conv 256->512 + BN + LeakyReLU  /    tiles and Nx64 weight tiles (SWIZZLE_128B), fp32
+//                                            accumulators in TMEM, fused scale/shift/LeakyReLU epilogue
+//   L5  conv 512->1 k4s1p0 (8192-dot) + sigmoid + BCE: one warp per sample
+//
+// Activation layout between layers ("parity planes"): a 4x4/stride-2/pad-1 conv reads input pixel
+// (2*oh-1+kh, 2*ow-1+kw).  Storing the SxS activation as [n][hp][wp][S/2][S/2][C] (hp = h&1,
+// wp = w&1) makes the im2col slice of one filter tap a dense box of one plane:
+// rows (oh+dh, ow+dw), dh = (kh-1)>>1, dw = (kw-1)>>1, plane ((kh-1)&1, (kw-1)&1).  That box is ONE
+// 5-D tiled TMA load (out-of-range rows/cols are the zero padding), landing in shared memory as the
+// K-major SW128 operand tcgen05.mma wants: 128 output pixels x 64 channels.
+//
+// fp32-parity mode (SG_CONV_BF16X3): every activation/weight is kept as bf16 hi + bf16 lo
+// (hi = rn(x), lo = rn(x - hi)); the GEMM runs three K-segments per (tap, channel chunk):
+// A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, i.e. a 3x longer K loop through the same kernel.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sg {
+namespace d64 {
+
+using namespace ptx;
+
+constexpr int kErrProducer = 1, kErrMma = 2, kErrMmaAcc = 3, kErrEpilogue = 4;
+
+// ------------------------------------------------------------------------------------------
+// Packed parameter block layout (bytes), shared by sg_d64_pack / sg_d64_score
+// ------------------------------------------------------------------------------------------
+struct PackedLayout {
+  size_t w1, w2, w3, w4, w5, ss2, ss3, ss4, total;
+  int nseg;
+};
+static PackedLayout packed_layout(int mode) {
+  PackedLayout L;
+  L.nseg = (mode == SG_CONV_BF16X3) ? 3 : 1;
+  size_t o = 0;
+  L.w1 = o; o += align_up(48 * 64 * 4, 1024);
+  L.w2 = o; o += align_up((size_t)128 * 16 * 64 * L.nseg * 2, 1024);
+  L.w3 = o; o += align_up((size_t)256 * 16 * 128 * L.nseg * 2, 1024);
+  L.w4 = o; o += align_up((size_t)512 * 16 * 256 * L.nseg * 2, 1024);
+  L.w5 = o; o += align_up(16 * 512 * 4, 1024);
+  L.ss2 = o; o += align_up(2 * 128 * 4, 1024);
+  L.ss3 = o; o += align_up(2 * 256 * 4, 1024);
+  L.ss4 = o; o += align_up(2 * 512 * 4, 1024);
+  L.total = o;
+  return L;
+}
+
+struct WorkspaceLayout {
+  size_t flag, act1, act2, act3, act4, total;
+  int sega;
+};
+static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
+  WorkspaceLayout L;
+  L.sega = (mode == SG_CONV_BF16X3) ? 2 : 1;
+  size_t o = 0;
+  L.flag = o; o += 1024;
+  L.act1 = o; o += align_up((size_t)batch * 32 * 32 * 64 * L.sega * 2, 1024);
+  L.act2 = o; o += align_up((size_t)batch * 16 * 16 * 128 * L.sega * 2, 1024);
+  L.act3 = o; o += align_up((size_t)batch * 8 * 8 * 256 * L.sega * 2, 1024);
+  L.act4 = o; o += align_up((size_t)batch * 16 * 512 * L.sega * 2, 1024);
+  L.total = o;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight packing
+// ------------------------------------------------------------------------------------------
+// w [Cout][Cin][4][4] fp32 -> bf16 [Cout][((tap*nchunk + chunk)*nseg + seg)*64 + j], c = chunk*64 + j.
+// seg 0: hi (pairs with A hi), seg 1: hi (pairs with A lo), seg 2: lo (pairs with A hi).
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
+                                        int cin, int nseg) {
+  const int nchunk = cin >> 6;
+  const int64_t kprime = (int64_t)16 * nchunk * nseg * 64;
+  const int64_t total = (int64_t)cout * kprime;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i / kprime);
+    int64_t r = i - (int64_t)co * kprime;
+    const int j = (int)(r & 63); r >>= 6;
+    const int seg = (int)(r % nseg); r /= nseg;
+    const int chunk = (int)(r % nchunk);
+    const int tap = (int)(r / nchunk);
+    const int c = chunk * 64 + j;
+    const float v = w[((int64_t)co * cin + c) * 16 + tap];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = (seg == 2) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
+}
+
+// w1 [64][3][4][4] -> fp32 [k = c*16 + kh*4 + kw][64];  w5 [1][512][4][4] -> fp32 [p = kh*4+kw][512]
+__global__ void pack_small_kernel(const float* __restrict__ w1, const float* __restrict__ w5, float* __restrict__ o1,
+                                  float* __restrict__ o5) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 48 * 64) {
+    const int k = i >> 6, co = i & 63;
+    o1[i] = w1[co * 48 + k];
+  }
+  if (i < 16 * 512) {
+    const int p = i >> 9, c = i & 511;
+    o5[i] = w5[c * 16 + p];
+  }
+}
+
+// eval-mode BatchNorm2d folded to y = x * scale + shift
+__global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps, int c,
+                               float* __restrict__ ss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    ss[i] = s;
+    ss[c + i] = beta[i] - mean[i] * s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// L1: direct conv 3->64, k4 s2 p1, LeakyReLU, fp32 math on CUDA cores.
+// One CTA = 4 output rows x 32 cols of one image (128 threads, one output pixel each, all 64
+// channels in registers).  Output: parity-plane bf16 [n][4][16][16][64*sega].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w1p,
+                                                    __nv_bfloat16* __restrict__ act1, int sega) {
+  __shared__ __align__(16) float s_w[48 * 64];
+  __shared__ float s_in[3][10][68];
+  const int n = blockIdx.x >> 3;
+  const int oh0 = (blockIdx.x & 7) << 2;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 48 * 64 / 4; i += 128)
+    reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(w1p)[i];
+  const float* xin = x + (size_t)n * 3 * 64 * 64;
+  // patch rows ih = 2*oh0-1 .. 2*oh0+8, cols iw = -1 .. 64 stored at [.][.][iw+1]
+  for (int i = tid; i < 3 * 10 * 66; i += 128) {
+    const int c = i / 660, r = (i / 66) % 10, col = i % 66;
+    const int ih = 2 * oh0 - 1 + r, iw = col - 1;
+    float v = 0.f;
+    if (ih >= 0 && ih < 64 && iw >= 0 && iw < 64) v = xin[(c * 64 + ih) * 64 + iw];
+    s_in[c][r][col] = v;
+  }
+  __syncthreads();
+  const int orow = tid >> 5, ow = tid & 31;
+  float in[48];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw) in[c * 16 + kh * 4 + kw] = s_in[c][2 * orow + kh][2 * ow + kw];
+  const int oh = oh0 + orow;
+  const int ct = 64 * sega;
+  const size_t off = ((((size_t)n * 4 + ((oh & 1) * 2 + (ow & 1))) * 16 + (oh >> 1)) * 16 + (ow >> 1)) * ct;
+  __nv_bfloat16* dst = act1 + off;
+#pragma unroll 1
+  for (int cb = 0; cb < 64; cb += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 48; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w + k * 64 + cb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = wr[q];
+        acc[q * 4 + 0] = fmaf(in[k], w4.x, acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(in[k], w4.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(in[k], w4.z, acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(in[k], w4.w, acc[q * 4 + 3]);
+      }
+    }
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[2 * j], b = acc[2 * j + 1];
+      a = a > 0.f ? a : 0.2f * a;
+      b = b > 0.f ? b : 0.2f * b;
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+      const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+      const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+      lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst + cb);
+    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    d[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    if (sega == 2) {
+      uint4* dl = reinterpret_cast<uint4*>(dst + 64 + cb);
+      dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// L2..L4: implicit-GEMM conv on tcgen05.  Warp-specialised persistent kernel:
+//   warp 0   : TMA producer (one elected lane)         smem ring: kStages x (A 128x64 | B BLOCK_N x 64) bf16
+//   warp 1   : tcgen05.mma issuer (one elected lane)   accumulators: 2 x BLOCK_N TMEM columns (ping-pong)
+//   warps 2-5: epilogue, TMEM -> registers -> scale/shift + LeakyReLU -> bf16 (hi[,lo]) -> global
+// ------------------------------------------------------------------------------------------
+struct ConvParams {
+  int total_tiles, n_tiles;   // tiles = m_tiles * n_tiles, n fastest
+  int n_img;                  // images in this launch
+  int ow_log2, bh_log2;       // OW = 1<<ow_log2 (= OH), box rows BH = 1<<bh_log2
+  int bimg;                   // images per M tile (1, 2, 8)
+  int tiles_per_img;          // OH / BH (2 for L2, else 1)
+  int c_in;                   // input channels per segment
+  int nchunk, nseg, k_steps;  // c_in/64, 1|3, 16*nchunk*nseg
+  int c_out;                  // output channels per segment
+  int out_sega;               // 1: hi only, 2: hi|lo
+  int out_planes;             // 1: parity-plane layout for the next conv, 0: plain [n][oh*OW+ow][C]
+  const float* scale;         // [c_out]
+  const float* shift;         // [c_out]
+  __nv_bfloat16* out;
+  int* err;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kBlockM = 128;
+  static constexpr int kBlockK = 64;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kThreads = 192;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  const uint32_t bar0 = base + S * Cfg::kStageBytes;
+  // barrier slots: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] ; then tmem base slot, abort flag
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ow_n = 1 << p.ow_log2;
+  const int bh = 1 << p.bh_log2;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        int img0, oh0;
+        if (p.tiles_per_img > 1) { img0 = mt / p.tiles_per_img; oh0 = (mt % p.tiles_per_img) * bh; }
+        else { img0 = mt * p.bimg; oh0 = 0; }
+        for (int ks = 0; ks < p.k_steps; ++ks) {
+          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer)) { ok = false; break; }
+          const int seg = ks % p.nseg;
+          const int t2 = ks / p.nseg;
+          const int chunk = t2 % p.nchunk;
+          const int tap = t2 / p.nchunk;
+          const int kh = tap >> 2, kw = tap & 3;
+          const int cc = chunk * 64 + (seg == 1 ? p.c_in : 0);
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_5d(sa, &tmap_a, full_bar(stage), cc, (kw - 1) >> 1, oh0 + ((kh - 1) >> 1),
+                      ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img0);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), ks * 64, nt * BLOCK_N);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ks = 0; ks < p.k_steps; ++ks) {
+          if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128-B swizzle row
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ct = p.c_out * p.out_sega;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      int img0, oh0;
+      if (p.tiles_per_img > 1) { img0 = mt / p.tiles_per_img; oh0 = (mt % p.tiles_per_img) * bh; }
+      else { img0 = mt * p.bimg; oh0 = 0; }
+      const int img = img0 + (row >> (p.ow_log2 + p.bh_log2));
+      const int rem = row & ((1 << (p.ow_log2 + p.bh_log2)) - 1);
+      const int oh = oh0 + (rem >> p.ow_log2);
+      const int ow = rem & (ow_n - 1);
+      const bool valid = img < p.n_img;
+      size_t off;
+      if (p.out_planes) {
+        const int half = ow_n >> 1;
+        off = ((((size_t)img * 4 + ((oh & 1) * 2 + (ow & 1))) * half + (oh >> 1)) * half + (ow >> 1)) * ct;
+      } else {
+        off = (((size_t)img * ow_n + oh) * ow_n + ow) * ct;
+      }
+      __nv_bfloat16* dst = p.out + off + (size_t)nt * BLOCK_N;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int cb = 0; cb < BLOCK_N; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        const float* sc = p.scale + nt * BLOCK_N + cb;
+        const float* sh = p.shift + nt * BLOCK_N + cb;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = fmaf(__uint_as_float(v[2 * j]), __ldg(sc + 2 * j), __ldg(sh + 2 * j));
+          float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(sc + 2 * j + 1), __ldg(sh + 2 * j + 1));
+          a = a > 0.f ? a : 0.2f * a;
+          b = b > 0.f ? b : 0.2f * b;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
+          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
+          const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+          const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
+          lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+        }
+        if (valid) {
+          uint4* d = reinterpret_cast<uint4*>(dst + cb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (p.out_sega == 2) {
+            uint4* dl = reinterpret_cast<uint4*>(dst + p.c_out + cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// L5 head: logit = <act4[n], w5>, prob = sigmoid(logit), loss = -max(log prob, -100).
+// One warp per sample; fixed summation order (lane-strided partials, xor-shuffle tree).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restrict__ act4, const float* __restrict__ w5p,
+                                                   int64_t batch, int sega, float* __restrict__ logit,
+                                                   float* __restrict__ prob, float* __restrict__ loss) {
+  const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= batch) return;
+  const int ct = 512 * sega;
+  const __nv_bfloat16* a = act4 + (size_t)n * 16 * ct;
+  float accv = 0.f;
+  for (int pxl = 0; pxl < 16; ++pxl) {
+    const __nv_bfloat16* ap = a + (size_t)pxl * ct;
+    const float* wp = w5p + pxl * 512;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = (h * 32 + lane) * 8;
+      const uint4 raw = *reinterpret_cast<const uint4*>(ap + c);
+      const float4 w0 = *reinterpret_cast<const float4*>(wp + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(wp + c + 4);
+      float xv[8];
+      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xv[2 * q] = __uint_as_float(rw[q] << 16);
+        xv[2 * q + 1] = __uint_as_float(rw[q] & 0xFFFF0000u);
+      }
+      if (sega == 2) {
+        const uint4 rl = *reinterpret_cast<const uint4*>(ap + 512 + c);
+        const uint32_t rlw[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          xv[2 * q] += __uint_as_float(rlw[q] << 16);
+          xv[2 * q + 1] += __uint_as_float(rlw[q] & 0xFFFF0000u);
+        }
+      }
+      accv = fmaf(xv[0], w0.x, accv); accv = fmaf(xv[1], w0.y, accv);
+      accv = fmaf(xv[2], w0.z, accv); accv = fmaf(xv[3], w0.w, accv);
+      accv = fmaf(xv[4], w1.x, accv); accv = fmaf(xv[5], w1.y, accv);
+      accv = fmaf(xv[6], w1.z, accv); accv = fmaf(xv[7], w1.w, accv);
+    }
+  }
+  accv = warp_sum(accv);
+  if (lane == 0) {
+    const float pr = 1.0f / (1.0f + expf(-accv));
+    if (logit) logit[n] = accv;
+    if (prob) prob[n] = pr;
+    // BCELoss(reduction='none') vs target 1: (1-1)*max(log1p(-p),-100) - 1*max(log p,-100); p==1 -> -0.0
+    if (loss) loss[n] = -fmaxf(logf(pr), -100.0f);
+  }
+}
+
+// debug/test: parity-plane (or plain) bf16 activation -> fp32 NCHW (hi + lo)
+__global__ void read_activation_kernel(const __nv_bfloat16* __restrict__ act, int64_t batch, int s, int c, int sega,
+                                       int planes, float* __restrict__ out) {
+  const int64_t total = batch * c * s * s;
+  const int ct = c * sega;
+  const int half = s >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int w = (int)(r % s); r /= s;
+    const int h = (int)(r % s); r /= s;
+    const int ch = (int)(r % c);
+    const int64_t n = r / c;
+    size_t off;
+    if (planes) off = ((((size_t)n * 4 + ((h & 1) * 2 + (w & 1))) * half + (h >> 1)) * half + (w >> 1)) * ct;
+    else off = (((size_t)n * s + h) * s + w) * ct;
+    float v = __bfloat162float(act[off + ch]);
+    if (sega == 2) v += __bfloat162float(act[off + c + ch]);
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode(CUtensorMap* m, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(state().encode_tiled);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return SG_ECUDA;
+  }
+  return SG_OK;
+}
+
+// One conv layer L (2..4): input activation S_in x S_in x c_in (planes), output (S_in/2)^2 x c_out.
+template <int BLOCK_N>
+static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* ss, __nv_bfloat16* act_out,
+                       int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega, int out_planes, int* err,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  const int ow = s_in / 2;
+  int bh = 128 / ow;
+  if (bh > ow) bh = ow;
+  const int bimg = 128 / (ow * bh);
+  const int tiles_per_img = ow / bh;
+  const int ct_in = c_in * sega;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)ct_in, (cuuint64_t)ow, (cuuint64_t)ow, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)ow * ct_in * 2, (cuuint64_t)ow * ow * ct_in * 2,
+                             (cuuint64_t)4 * ow * ow * ct_in * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)ow, (cuuint32_t)bh, 1, (cuuint32_t)bimg};
+    int r = encode(&ta, 5, act_in, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  const int nchunk = c_in / 64;
+  const int k_steps = 16 * nchunk * nseg;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, (cuuint64_t)c_out};
+    cuuint64_t strides[1] = {(cuuint64_t)k_steps * 64 * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BLOCK_N};
+    int r = encode(&tb, 2, wpk, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  ConvParams p;
+  p.n_tiles = c_out / BLOCK_N;
+  const int64_t m_tiles = (tiles_per_img > 1) ? batch * tiles_per_img : ceil_div(batch, bimg);
+  p.total_tiles = (int)(m_tiles * p.n_tiles);
+  p.n_img = (int)batch;
+  p.ow_log2 = __builtin_ctz(ow);
+  p.bh_log2 = __builtin_ctz(bh);
+  p.bimg = bimg;
+  p.tiles_per_img = tiles_per_img;
+  p.c_in = c_in;
+  p.nchunk = nchunk;
+  p.nseg = nseg;
+  p.k_steps = k_steps;
+  p.c_out = c_out;
+  p.out_sega = sega;
+  p.out_planes = out_planes;
+  p.scale = ss;
+  p.shift = ss + c_out;
+  p.out = act_out;
+  p.err = err;
+  int grid = p.total_tiles < state().sm_count ? p.total_tiles : state().sm_count;
+  conv_umma_kernel<BLOCK_N><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+}  // namespace d64
+}  // namespace sg
+
+extern "C" {
+
+int sg_d64_init_attributes() {
+  using namespace sg::d64;
+  SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<128>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               ConvCfg<256>::kSmemBytes));
+  return SG_OK;
+}
+
+size_t sg_d64_packed_bytes(int conv_mode) { return sg::d64::packed_layout(conv_mode).total; }
+
+size_t sg_d64_workspace_bytes(int64_t max_batch, int conv_mode) {
+  if (max_batch < 1) max_batch = 1;
+  return sg::d64::workspace_layout(max_batch, conv_mode).total;
+}
+
+int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* w4, const float* w5,
+                const float* bn2_gamma, const float* bn2_beta, const float* bn2_mean, const float* bn2_var,
+                const float* bn3_gamma, const float* bn3_beta, const float* bn3_mean, const float* bn3_var,
+                const float* bn4_gamma, const float* bn4_beta, const float* bn4_mean, const float* bn4_var,
+                float bn_eps, int conv_mode, void* packed, void* stream) {
+  using namespace sg::d64;
+  SG_READY();
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
+  SG_REQUIRE(w1 && w2 && w3 && w4 && w5 && packed, "null weight pointer");
+  SG_REQUIRE(((uintptr_t)packed & 1023) == 0, "packed buffer must be 1024-byte aligned");
+  const PackedLayout L = packed_layout(conv_mode);
+  cudaStream_t st = sg::as_stream(stream);
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  pack_small_kernel<<<32, 256, 0, st>>>(w1, w5, reinterpret_cast<float*>(pk + L.w1), reinterpret_cast<float*>(pk + L.w5));
+  SG_LAUNCH_CHECK();
+  pack_conv_weight_kernel<<<256, 256, 0, st>>>(w2, reinterpret_cast<__nv_bfloat16*>(pk + L.w2), 128, 64, L.nseg);
+  pack_conv_weight_kernel<<<512, 256, 0, st>>>(w3, reinterpret_cast<__nv_bfloat16*>(pk + L.w3), 256, 128, L.nseg);
+  pack_conv_weight_kernel<<<1024, 256, 0, st>>>(w4, reinterpret_cast<__nv_bfloat16*>(pk + L.w4), 512, 256, L.nseg);
+  SG_LAUNCH_CHECK();
+  fold_bn_kernel<<<1, 128, 0, st>>>(bn2_gamma, bn2_beta, bn2_mean, bn2_var, bn_eps, 128, reinterpret_cast<float*>(pk + L.ss2));
+  fold_bn_kernel<<<1, 256, 0, st>>>(bn3_gamma, bn3_beta, bn3_mean, bn3_var, bn_eps, 256, reinterpret_cast<float*>(pk + L.ss3));
+  fold_bn_kernel<<<1, 512, 0, st>>>(bn4_gamma, bn4_beta, bn4_mean, bn4_var, bn_eps, 512, reinterpret_cast<float*>(pk + L.ss4));
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, float* logit,
+                 float* prob, float* loss, void* stream) {
+  using namespace sg::d64;
+  SG_READY();
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
+  SG_REQUIRE(x && packed && workspace, "null pointer");
+  SG_REQUIRE(batch >= 0 && batch <= (1 << 22), "batch out of range");
+  SG_REQUIRE(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)workspace & 1023) == 0,
+             "packed/workspace must be 1024-byte aligned");
+  SG_REQUIRE(((uintptr_t)x & 15) == 0, "x must be 16-byte aligned");
+  if (batch == 0) return SG_OK;
+  const PackedLayout P = packed_layout(conv_mode);
+  const WorkspaceLayout W = workspace_layout(batch, conv_mode);
+  cudaStream_t st = sg::as_stream(stream);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* err = reinterpret_cast<int*>(ws + W.flag);
+  __nv_bfloat16* act1 = reinterpret_cast<__nv_bfloat16*>(ws + W.act1);
+  __nv_bfloat16* act2 = reinterpret_cast<__nv_bfloat16*>(ws + W.act2);
+  __nv_bfloat16* act3 = reinterpret_cast<__nv_bfloat16*>(ws + W.act3);
+  __nv_bfloat16* act4 = reinterpret_cast<__nv_bfloat16*>(ws + W.act4);
+  SG_CUDA(cudaMemsetAsync(err, 0, 4, st));
+  conv1_kernel<<<(unsigned)(batch * 8), 128, 0, st>>>(x, reinterpret_cast<const float*>(pk + P.w1), act1, W.sega);
+  SG_LAUNCH_CHECK();
+  int r;
+  r = launch_conv<128>(act1, reinterpret_cast<const __nv_bfloat16*>(pk + P.w2), reinterpret_cast<const float*>(pk + P.ss2),
+                       act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
+  if (r != SG_OK) return r;
+  r = launch_conv<256>(act2, reinterpret_cast<const __nv_bfloat16*>(pk + P.w3), reinterpret_cast<const float*>(pk + P.ss3),
+                       act3, batch, 16, 128, 256, P.nseg, W.sega, 1, err, st);
+  if (r != SG_OK) return r;
+  r = launch_conv<256>(act3, reinterpret_cast<const __nv_bfloat16*>(pk + P.w4), reinterpret_cast<const float*>(pk + P.ss4),
+                       act4, batch, 8, 256, 512, P.nseg, W.sega, 0, err, st);
+  if (r != SG_OK) return r;
+  head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, reinterpret_cast<const float*>(pk + P.w5), batch,
+                                                                W.sega, logit, prob, loss);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_d64_check(const void* workspace, void* stream) {
+  SG_READY();
+  SG_REQUIRE(workspace != nullptr, "workspace");
+  int flag = 0;
+  SG_CUDA(cudaMemcpyAsync(&flag, workspace, 4, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
+  SG_CUDA(cudaStreamSynchronize(sg::as_stream(stream)));
+  if (flag != 0) {
+    sg::set_error("conv pipeline timed out waiting on an mbarrier (role code %d: 1 producer, 2 mma, 3 mma-acc, 4 epilogue)", flag);
+    return SG_ECUDA;
+  }
+  return SG_OK;
+}
+
+int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, int layer, float* out, void* stream) {
+  using namespace sg::d64;
+  SG_READY();
+  SG_REQUIRE(workspace && out && layer >= 1 && layer <= 4 && batch > 0, "arguments");
+  const WorkspaceLayout W = workspace_layout(batch, conv_mode);
+  const uint8_t* ws = static_cast<const uint8_t*>(workspace);
+  const size_t offs[5] = {0, W.act1, W.act2, W.act3, W.act4};
+  const int s[5] = {0, 32, 16, 8, 4};
+  const int c[5] = {0, 64, 128, 256, 512};
+  const int64_t total = batch * c[layer] * s[layer] * s[layer];
+  int blocks = (int)sg::ceil_div(total, 256);
+  if (blocks > 65535) blocks = 65535;
+  read_activation_kernel<<<blocks, 256, 0, sg::as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(ws + offs[layer]), batch, s[layer], c[layer], W.sega, layer != 4, out);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/strainer_b200.h declares;
+host-side logic that needs no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import strainer_b200
+    return strainer_b200
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "strainer_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(sb):
+    lib = ctypes.CDLL(sb._lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # and the Python binding covers exactly the header
+    assert sorted(sb._lib._SIGS) == names
+
+
+def test_no_gpu_fails_loudly(sb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = sb._lib.load()
+    assert lib.sg_version() == 100
+    assert lib.sg_init(0) == -2  # SG_EARCH: no device, no fallback
+    assert b"no CPU fallback" in lib.sg_last_error_string()
+    with pytest.raises(RuntimeError):
+        sb.synth_images(0, 4)
+    with pytest.raises(RuntimeError):
+        sb.refine_dataset_by_loss(torch.zeros(4, 3, 64, 64), torch.nn.Identity(), "cpu")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "strainer-gan_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_percentile_plan_matches_numpy(sb):
+    from oracle import strainer_oracle as O
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n = int(rng.integers(1, 5000))
+        q = [float(rng.uniform(0, 100)), (1 - 0.8) * 100, 90.0, 75, 0, 100][int(rng.integers(0, 6))]
+        v = np.sort(rng.standard_normal(n).astype(np.float32))
+        k0, k1, g, dt = sb.api._np_percentile_plan(n, q) if hasattr(sb, "api") else sb._np_percentile_plan(n, q)
+        assert dt == np.float32
+        assert O.np_lerp(v[k0], v[k1], g) == np.percentile(v, q)
+
+
+def test_f32_threshold_directed_rounding(sb):
+    f = sb.api._f32_threshold if hasattr(sb, "api") else sb._f32_threshold
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(20000).astype(np.float32)
+    for t in list(rng.standard_normal(50)) + [float(v[3]), float(np.float64(v[7]) + 1e-12)]:
+        t = np.float64(t)
+        assert np.array_equal(v < f(t, 0), v < t)
+        assert np.array_equal(v <= f(t, 1), v <= t)
+        assert np.array_equal(v >= f(t, 2), v >= t)
+        assert np.array_equal(v > f(t, 3), v > t)

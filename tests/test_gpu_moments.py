@@ -1,0 +1,100 @@
+"""GPU parity: z-score, elbow histogram, detect_outliers variants, moments."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import strainer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import strainer_b200
+    assert torch.cuda.is_available()
+    return strainer_b200
+
+
+@pytest.fixture(scope="module")
+def feats():
+    return O.synth_features(4096)
+
+
+def test_zscore_max(sb, feats, golden):
+    got = sb.zscore_max(torch.from_numpy(feats)).cpu().numpy()
+    want = golden["g4_maxz"]
+    assert np.allclose(got, want, rtol=2e-5, atol=1e-6), np.abs(got - want).max()   # fp32 reductions differ in the last bits
+    got0 = sb.zscore_max(torch.from_numpy(feats), ddof=0, eps_add=1e-7).cpu().numpy()
+    assert np.allclose(got0, golden["g7_maxz_np"], rtol=2e-5, atol=1e-6)
+    f2 = feats.copy()
+    f2[:, 5] = 1.0  # constant column -> 0/0 = NaN -> every row NaN
+    assert np.isnan(sb.zscore_max(torch.from_numpy(f2)).cpu().numpy()).all()
+
+
+def test_find_elbow_threshold_bit_exact(sb, golden):
+    """given identical z-scores the histogram, density and threshold are bit exact"""
+    thr, centers, hist = sb.find_elbow_threshold(golden["g4_maxz"])
+    assert thr == golden["g4_threshold"]
+    assert np.array_equal(centers, golden["g4_centers"]) and np.array_equal(hist, golden["g4_hist"])
+    rng = np.random.default_rng(21)
+    for n, scale in ((1, 1.0), (17, 1e-3), (100_003, 37.5), (5, 0.0)):
+        z = (rng.standard_normal(n) * scale).astype(np.float32)
+        t2, c2, h2 = sb.find_elbow_threshold(z)
+        t1, c1, h1 = O.find_elbow_threshold(z)
+        assert t1 == t2 and np.array_equal(c1, c2) and np.array_equal(h1, h2, equal_nan=True)
+    with pytest.raises(ValueError):
+        sb.find_elbow_threshold(np.array([1.0, np.nan], np.float32))
+
+
+def test_detect_outliers_variants(sb, feats, golden):
+    ds = torch.utils.data.TensorDataset(torch.from_numpy(feats), torch.zeros(len(feats)))
+    ident = torch.nn.Identity()
+    mz = golden["g4_maxz"]
+
+    def near(thr, tol=1e-4):
+        return np.abs(mz - thr) <= tol * np.abs(thr)
+
+    got = sb.detect_outliers(ds, ident)
+    assert got.dtype == bool
+    bad = got != golden["g5_elbow_inlier"]
+    assert not (bad & ~near(float(golden["g4_threshold"]))).any()
+    got = sb.detect_outliers(ds, ident, 5)
+    assert not ((got != golden["g5_user5_inlier"]) & ~near(5.0)).any()
+    got = sb.detect_outliers(ds, ident, threshold=5.0)
+    assert isinstance(got, torch.Tensor) and got.dtype == torch.bool
+    assert not ((got.numpy() != golden["g5_fixed5_inlier"]) & ~near(5.0)).any()
+    for tag in "ab":
+        r = float(golden[f"g5_ratio{tag}"])
+        got = sb.detect_outliers(ds, ident, clean_ratio=r).numpy()
+        thr = float(torch.quantile(torch.from_numpy(mz), r))
+        assert not ((got != golden[f"g5_ratio{tag}_inlier"]) & ~near(thr)).any()
+        assert abs(int(got.sum()) - int(golden[f"g5_ratio{tag}_inlier"].sum())) <= 2
+    assert np.allclose(sb.compute_z_scores(ds, ident), golden["g7_maxz_np"], rtol=2e-5, atol=1e-6)
+
+
+def test_moments_threshold(sb):
+    lib = sb._lib.load()
+    L = sb._lib
+    rng = np.random.default_rng(22)
+    for n in (2, 4096, 4097, 100_003):
+        e = rng.random(n).astype(np.float32)
+        d = torch.from_numpy(e).cuda()
+        chunks = (n + L.SG_MOMENT_CHUNK - 1) // L.SG_MOMENT_CHUNK
+        part = torch.empty(2 * chunks, dtype=torch.float64, device="cuda")
+        stats = torch.empty(2, dtype=torch.float64, device="cuda")
+        thr = torch.empty(1, dtype=torch.float32, device="cuda")
+        st = L.P(torch.cuda.current_stream().cuda_stream)
+        L.check(lib.sg_chunk_moments(L.P(d.data_ptr()), n, L.P(part.data_ptr()), st))
+        L.check(lib.sg_moments_finish(L.P(part.data_ptr()), chunks, n, 2.0, L.P(stats.data_ptr()), L.P(thr.data_ptr()), st))
+        te = torch.from_numpy(e)
+        want = (te.mean() + 2.0 * te.std()).item()
+        assert abs(thr.item() - want) <= 2e-6 * abs(want)          # fp32 tolerance: 2e-6 relative
+        s = stats.cpu().numpy()
+        assert abs(s[0] - e.astype(np.float64).mean()) < 1e-12 and abs(s[1] - e.astype(np.float64).std(ddof=1)) < 1e-10
+        # sharding invariance: partials of chunk-aligned shards are the same numbers
+        if n > 8192:
+            half = 4096 * (chunks // 2)
+            p2 = torch.empty(2 * chunks, dtype=torch.float64, device="cuda")
+            L.check(lib.sg_chunk_moments(L.P(d.data_ptr()), half, L.P(p2.data_ptr()), st))
+            L.check(lib.sg_chunk_moments(L.P(d[half:].data_ptr()), n - half, L.P(p2[2 * (chunks // 2):].data_ptr()), st))
+            assert torch.equal(part, p2)

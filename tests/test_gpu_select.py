@@ -1,0 +1,174 @@
+"""GPU parity: selection / compaction kernels vs the oracle (bit exact; integer and index work)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import strainer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import strainer_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return strainer_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def adversarial(n, rng):
+    """ties, -0.0, 100.0 clamps, denormals"""
+    v = O.synth_losses(n, seed=int(rng.integers(1 << 30)))
+    m = rng.random(n)
+    v[m < 0.3] = np.float32(0.25)          # 30 % exact ties
+    v[(m >= 0.3) & (m < 0.35)] = np.float32(-0.0)
+    v[(m >= 0.35) & (m < 0.4)] = np.float32(0.0)
+    v[(m >= 0.4) & (m < 0.45)] = np.float32(100.0)
+    v[(m >= 0.45) & (m < 0.5)] = np.float32(5.9604645e-08)
+    v[(m >= 0.5) & (m < 0.52)] = np.float32(-1.5)
+    return v
+
+
+def test_radix_select_order_stats(sb):
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 31, 1000, 4097, 70001, 1_000_003):
+        for trial in range(3):
+            v = adversarial(n, rng) if trial else rng.standard_normal(n).astype(np.float32)
+            s = np.sort(v)
+            for k in {0, n // 2, max(n - 2, 0), n - 1, int(rng.integers(0, n))}:
+                got = sb.order_stats(dev(v), k).cpu().numpy()
+                want = np.array([s[k], s[min(k + 1, n - 1)]], np.float32)
+                assert np.array_equal(got, want), (n, k, got, want)  # -0.0 == 0.0 under array_equal
+
+
+def test_radix_select_nan(sb):
+    v = np.arange(100, dtype=np.float32)
+    v[17] = np.nan
+    assert np.isnan(sb.order_stats(dev(v), 50).cpu().numpy()).all()
+    assert np.isnan(sb.percentile_device(dev(v), 90.0).cpu().numpy()[0])
+
+
+def test_percentile_bit_exact_vs_numpy(sb):
+    rng = np.random.default_rng(12)
+    for _ in range(60):
+        n = int(rng.integers(1, 20000))
+        q = [float(rng.uniform(0, 100)), (1 - 0.8) * 100, (1 - 0.2) * 100, 90.0, 75, 25, 0.0, 100.0][int(rng.integers(0, 8))]
+        v = adversarial(n, rng) if rng.random() < 0.5 else rng.standard_normal(n).astype(np.float32)
+        got = sb.percentile_device(dev(v), q).cpu().numpy()[0]
+        want = np.percentile(v, q)
+        assert got.dtype == want.dtype == np.float32
+        assert got == want, (n, q, got, want)
+    v = O.synth_losses(1 << 20, seed=5)
+    for q in (90.0, (1 - 0.8) * 100):
+        assert sb.percentile_device(dev(v), q).cpu().numpy()[0] == np.percentile(v, q)
+    # np.float64 q: numpy interpolates in float64
+    got = sb.percentile_device(dev(v), np.float64(33.3))
+    assert float(got[0]) == np.percentile(v, np.float64(33.3))
+
+
+def test_quantile_bit_exact_vs_torch(sb):
+    rng = np.random.default_rng(13)
+    for n in (2, 64, 128, 256, 512, 1000, 2048, 2049, 4096, 65536):
+        for q in (0.1, 0.9, 0.8731, float(rng.uniform(0, 1)), 0.0, 1.0):
+            v = rng.standard_normal(n).astype(np.float32)
+            if n == 128:
+                v = np.round(v, 1)
+            got = sb.quantile_device(dev(v), q).cpu().numpy()[0]
+            want = torch.quantile(torch.from_numpy(v), q).numpy()
+            assert got == want, (n, q, got, want)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 4097, 100_000, 1_000_003])
+def test_compact_indices_vs_np_where(sb, n):
+    rng = np.random.default_rng(14 + n)
+    v = adversarial(n, rng) if n else np.zeros(0, np.float32)
+    if n > 10:
+        v[7] = np.nan
+    for cmp_code, fn in ((0, np.less), (1, np.less_equal), (2, np.greater_equal), (3, np.greater)):
+        for thr in (np.float32(0.25), np.float32(-0.0), np.float32(1e9), np.float32(-1e9)):
+            idx, count, mask = sb.compact_indices(dev(v) if n else torch.zeros(0, device="cuda"), float(thr), cmp_code, 0, True)
+            want = np.where(fn(v, thr))[0]
+            c = int(count.item())
+            assert c == len(want)
+            assert np.array_equal(idx[:c].cpu().numpy(), want)
+            assert np.array_equal(mask.cpu().numpy().astype(bool), fn(v, thr))
+            idx2, count2, _ = sb.compact_indices(dev(v) if n else torch.zeros(0, device="cuda"), float(thr), cmp_code | 4, 1000)
+            assert np.array_equal(idx2[:int(count2.item())].cpu().numpy(), np.where(~fn(v, thr))[0] + 1000)
+
+
+def test_partition_rows_vs_boolean_index(sb):
+    rng = np.random.default_rng(15)
+    for n, shape in ((128, (3, 64, 64)), (7, (4,)), (5000, (8,)), (1, (3, 64, 64))):
+        x = torch.from_numpy(rng.standard_normal((n,) + shape).astype(np.float32))
+        m = torch.from_numpy(rng.random(n) < 0.9)
+        kept, dropped, counts = sb.partition_rows(x.cuda(), m.cuda())
+        c = counts.cpu().numpy()
+        assert c[0] == int(m.sum()) and c[1] == n - int(m.sum())
+        assert torch.equal(kept[:c[0]].cpu(), x[m]) and torch.equal(dropped[:c[1]].cpu(), x[~m])
+
+
+def test_select_below_percentile_golden(sb, golden):
+    """the selection half of refine_dataset_by_loss on the reference's own losses -> its own indices"""
+    losses = golden["g1_losses"]
+    for tag in "abc":
+        q = (1 - float(golden[f"g1{tag}_ratio"])) * 100
+        idx, thr = sb.select_below_percentile(dev(losses), q)
+        assert thr == golden[f"g1{tag}_threshold"] and thr.dtype == np.float32
+        assert np.array_equal(idx, golden[f"g1{tag}_indices"])
+
+
+def test_full_size_properties(sb):
+    """N = 2**20 (config 5): properties that do not need the oracle at full size."""
+    n = 1 << 20
+    rng = np.random.default_rng(16)
+    v = adversarial(n, rng)
+    d = dev(v)
+    idx, thr = sb.select_below_percentile(d, 90.0)
+    assert thr == np.percentile(v, 90.0)
+    assert np.all(np.diff(idx) > 0)                       # ascending, unique
+    assert np.all(v[idx] < thr) and len(idx) == int((v < thr).sum())
+    # idempotence: straining the kept set with q=100 removes only the maximum ties
+    kept = v[idx]
+    idx2, thr2 = sb.select_below_percentile(dev(kept), 100.0)
+    assert thr2 == kept.max() and len(idx2) == int((kept < kept.max()).sum())
+    # all-equal losses: nothing survives (reference fallback case)
+    idx3, thr3 = sb.select_below_percentile(torch.full((n,), 0.5, device="cuda"), 90.0)
+    assert len(idx3) == 0 and thr3 == np.float32(0.5)
+
+
+def test_sharded_select_emulated(sb):
+    """Histogram phases on 4 shards with the all-reduce emulated by summation == single pass."""
+    lib = sb._lib.load()
+    L = sb._lib
+    rng = np.random.default_rng(17)
+    v = adversarial(50_000, rng)
+    n = v.size
+    k = 12345
+    shards = [dev(s) for s in np.array_split(v, 4)]
+    wss = [torch.empty(L.SG_SELECT_WS_WORDS, dtype=torch.int32, device="cuda") for _ in shards]
+    st = L.P(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: L.P(t.data_ptr())
+    for ws in wss:
+        L.check(lib.sg_select_begin(p(ws), k, st))
+    for ps in range(3):
+        for ws, sh in zip(wss, shards):
+            L.check(lib.sg_select_hist(p(sh), sh.numel(), p(ws), ps, st))
+        tot = sum(ws[:2049].clone() for ws in wss)
+        for ws in wss:
+            ws[:2049] = tot
+            L.check(lib.sg_select_step(p(ws), ps, st))
+    for ws, sh in zip(wss, shards):
+        L.check(lib.sg_select_min_above(p(sh), sh.numel(), p(ws), st))
+    mins = torch.stack([ws[2049] ^ -2147483648 for ws in wss]).min() ^ -2147483648
+    outs = []
+    for ws in wss:
+        ws[2049] = mins
+        o = torch.empty(2, device="cuda")
+        L.check(lib.sg_select_finish(p(ws), p(o), st))
+        outs.append(o.cpu().numpy())
+    s = np.sort(v)
+    for o in outs:
+        assert np.array_equal(o, s[k:k + 2])
