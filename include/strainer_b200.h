@@ -79,6 +79,10 @@ size_t sg_d64_workspace_bytes(int64_t max_batch, int conv_mode);
  * loss[batch] = -max(log prob, -100) (any of the three may be NULL). */
 int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
                  float* logit, float* prob, float* loss, void* stream);
+/* One stage of sg_d64_score on the same workspace (1: conv1 ... 4: conv4, 5: head); used by the
+ * benchmark to time each kernel with events on the launching stream, and by the tests. */
+int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
+                     float* logit, float* prob, float* loss, void* stream);
 /* debugging / tests: copies the activation of layer `layer` (1..4) of the last sg_d64_score call
  * on `workspace` into fp32 NCHW `out` ([batch,64,32,32], [batch,128,16,16], ...). */
 /* Synchronises `stream` and reports a pipeline time-out recorded by the conv kernels (tests). */

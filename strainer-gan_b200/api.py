@@ -289,6 +289,11 @@ class D64Scorer:
         L.check(self.lib.sg_d64_score(_p(x), b, _p(self.packed), _p(self.ws), self.mode, _p(logit), _p(prob), _p(loss),
                                       _stream()), "sg_d64_score")
 
+    def run_layer(self, x, layer: int, logit=None, prob=None, loss=None):
+        """One stage (1..5) of score_into on this scorer's workspace (benchmark / tests)."""
+        L.check(self.lib.sg_d64_run_layer(_p(x), x.shape[0], _p(self.packed), _p(self.ws), self.mode, layer, _p(logit),
+                                          _p(prob), _p(loss), _stream()), "sg_d64_run_layer")
+
     def check(self):
         L.check(self.lib.sg_d64_check(_p(self.ws), _stream()), "sg_d64_check")
 

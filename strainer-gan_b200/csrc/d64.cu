@@ -611,16 +611,16 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
   return SG_OK;
 }
 
-int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, float* logit,
-                 float* prob, float* loss, void* stream) {
+int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
+                     float* logit, float* prob, float* loss, void* stream) {
   using namespace sg::d64;
   SG_READY();
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
-  SG_REQUIRE(x && packed && workspace, "null pointer");
+  SG_REQUIRE(packed && workspace, "null pointer");
+  SG_REQUIRE(layer >= 1 && layer <= 5, "layer must be 1..5");
   SG_REQUIRE(batch >= 0 && batch <= (1 << 22), "batch out of range");
   SG_REQUIRE(((uintptr_t)packed & 1023) == 0 && ((uintptr_t)workspace & 1023) == 0,
              "packed/workspace must be 1024-byte aligned");
-  SG_REQUIRE(((uintptr_t)x & 15) == 0, "x must be 16-byte aligned");
   if (batch == 0) return SG_OK;
   const PackedLayout P = packed_layout(conv_mode);
   const WorkspaceLayout W = workspace_layout(batch, conv_mode);
@@ -632,22 +632,37 @@ int sg_d64_score(const float* x, int64_t batch, const void* packed, void* worksp
   __nv_bfloat16* act2 = reinterpret_cast<__nv_bfloat16*>(ws + W.act2);
   __nv_bfloat16* act3 = reinterpret_cast<__nv_bfloat16*>(ws + W.act3);
   __nv_bfloat16* act4 = reinterpret_cast<__nv_bfloat16*>(ws + W.act4);
-  SG_CUDA(cudaMemsetAsync(err, 0, 4, st));
-  conv1_kernel<<<(unsigned)(batch * 8), 128, 0, st>>>(x, reinterpret_cast<const float*>(pk + P.w1), act1, W.sega);
-  SG_LAUNCH_CHECK();
-  int r;
-  r = launch_conv<128>(act1, reinterpret_cast<const __nv_bfloat16*>(pk + P.w2), reinterpret_cast<const float*>(pk + P.ss2),
-                       act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
-  if (r != SG_OK) return r;
-  r = launch_conv<256>(act2, reinterpret_cast<const __nv_bfloat16*>(pk + P.w3), reinterpret_cast<const float*>(pk + P.ss3),
-                       act3, batch, 16, 128, 256, P.nseg, W.sega, 1, err, st);
-  if (r != SG_OK) return r;
-  r = launch_conv<256>(act3, reinterpret_cast<const __nv_bfloat16*>(pk + P.w4), reinterpret_cast<const float*>(pk + P.ss4),
-                       act4, batch, 8, 256, 512, P.nseg, W.sega, 0, err, st);
-  if (r != SG_OK) return r;
-  head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, reinterpret_cast<const float*>(pk + P.w5), batch,
-                                                                W.sega, logit, prob, loss);
-  SG_LAUNCH_CHECK();
+  auto wq = [&](size_t off) { return reinterpret_cast<const __nv_bfloat16*>(pk + off); };
+  auto fq = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+  switch (layer) {
+    case 1:
+      SG_REQUIRE(x != nullptr && ((uintptr_t)x & 15) == 0, "x must be a 16-byte aligned device pointer");
+      conv1_kernel<<<(unsigned)(batch * 8), 128, 0, st>>>(x, fq(P.w1), act1, W.sega);
+      SG_LAUNCH_CHECK();
+      return SG_OK;
+    case 2:
+      return launch_conv<128>(act1, wq(P.w2), fq(P.ss2), act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
+    case 3:
+      return launch_conv<256>(act2, wq(P.w3), fq(P.ss3), act3, batch, 16, 128, 256, P.nseg, W.sega, 1, err, st);
+    case 4:
+      return launch_conv<256>(act3, wq(P.w4), fq(P.ss4), act4, batch, 8, 256, 512, P.nseg, W.sega, 0, err, st);
+    default:
+      head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, fq(P.w5), batch, W.sega, logit, prob, loss);
+      SG_LAUNCH_CHECK();
+      return SG_OK;
+  }
+}
+
+int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, float* logit,
+                 float* prob, float* loss, void* stream) {
+  SG_READY();
+  SG_REQUIRE(x && packed && workspace, "null pointer");
+  if (batch == 0) return SG_OK;
+  SG_CUDA(cudaMemsetAsync(workspace, 0, 4, sg::as_stream(stream)));  // pipeline time-out flag
+  for (int layer = 1; layer <= 5; ++layer) {
+    const int r = sg_d64_run_layer(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, stream);
+    if (r != SG_OK) return r;
+  }
   return SG_OK;
 }
 
