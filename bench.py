@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the straining hot path (BASELINE.json metric: strained samples/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config 5 of BASELINE.json, weak scaling): every GPU holds a shard of SHARD = 131072 synthetic
+64x64x3 fp32 samples (2^20 samples at 8 GPUs); ONE STEP = one full dataset-scale strain =
+  D scoring of every sample (tcgen05 convs + fused sigmoid/BCE head)  ->  global top-10 % cutoff
+  (np.percentile(losses, 90) by radix select; integer histograms all-reduced over NCCL when N > 1)
+  ->  ascending kept-index compaction (np.where(loss < thr)).
+`value` is the whole-job samples/s with the shard resident in HBM; `e2e` is the same strain through the
+reference-facing call (refine_dataset_by_loss on a HOST dataset: H2D of every image and D2H of the kept
+indices inside the timed region).  Under torchrun one process per GPU; timing = CUDA events, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHARD = 131072          # samples per GPU (6.4 GB fp32): inputs are far larger than the 126 MB L2
+CHUNK = 8192            # samples per scoring launch group
+E2E_SAMPLES = 32768     # per-GPU host dataset for the end-to-end leg (1.6 GB pinned)
+LOSS_RATIO = 0.1        # "remove top 10 % loss"
+FLOP_CONV = 2 * (256 * 128 * 1024 + 64 * 256 * 2048 + 16 * 512 * 4096)   # L2..L4 = 201.3 MFLOP / sample
+FLOP_ALL = FLOP_CONV + 2 * (1024 * 64 * 48 + 8192)                      # 207.6 MFLOP / sample
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
+        # under load = the upper half of the samples (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port of refine_dataset_by_loss,
+    "#strainer gan.py:364-392": torch-CPU D forward + np.percentile + np.where) on the host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import strainer_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 1024
+    x = torch.from_numpy(O.synth_images(0, sample))
+    netD = O.make_discriminator(O.SEED)
+    for _ in range(max(args.warmup, 1)):
+        O.refine_dataset_by_loss(x[:256], netD, LOSS_RATIO)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        idx, thr, _ = O.refine_dataset_by_loss(x, netD, LOSS_RATIO)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample / dt
+    line = {"impl": "reference", "metric": "strained_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5 dataset-scale D64 scoring + np.percentile(90) + np.where, CPU oracle port of "
+                                   "refine_dataset_by_loss", "samples_per_step": sample, "loss_ratio": LOSS_RATIO},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} samples/step, torch CPU {torch.get_num_threads()} threads"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--shard", type=int, default=SHARD)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import strainer_b200 as sb
+    from oracle import strainer_oracle as O
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    pk = peaks()
+    shard = args.shard
+    n_global = shard * world
+    base = rank * shard
+
+    netD = O.make_discriminator(O.SEED)   # reference architecture, weights_init + perturbed BN stats
+    netD.eval()
+    images = sb.synth_images(base, shard, O.SEED, device)      # resident shard, generated on device
+    scorer = sb.D64Scorer(netD, device, args.mode, max_batch=CHUNK)
+    losses = torch.empty(shard, dtype=torch.float32, device=device)
+    q = (1 - LOSS_RATIO) * 100
+
+    def strain_step(sc):
+        for i in range(0, shard, CHUNK):
+            b = min(CHUNK, shard - i)
+            sc.score_into(images[i:i + b], None, None, losses[i:i + b])
+        thr = sb.percentile_device(losses, q, group, n_global)
+        idx, count, _ = sb.compact_indices(losses, thr, 0, base)
+        return thr, idx, count
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if group is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, out
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, (thr, idx, count) = timed(lambda: strain_step(scorer), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    scorer.check()
+    value = n_global / (ms_step * 1e-3)
+    kept = int(count.item())
+    nchunks = (shard + CHUNK - 1) // CHUNK
+    launches_per_step = nchunks * 5 + 1 + 3 * 2 + 1 + 1 + 1 + 1     # score | select begin,3x(hist,step),min,finish | lerp | compact
+
+    # ---- per-kernel timing of the conv kernels inside a long loop (sustained clocks) ----------------------
+    def layer_times(sc, reps):
+        xs = images[:CHUNK]
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(reps)]
+        for w in range(2):
+            for layer in range(1, 6):
+                sc.run_layer(xs, layer, None, None, losses[:CHUNK])
+        torch.cuda.synchronize()
+        for r in range(reps):
+            ev[r][0].record()
+            for layer in range(1, 6):
+                sc.run_layer(images[(r % nchunks) * CHUNK:(r % nchunks) * CHUNK + CHUNK], layer, None, None, losses[:CHUNK])
+                ev[r][layer].record()
+        torch.cuda.synchronize()
+        t = np.array([[ev[r][l].elapsed_time(ev[r][l + 1]) for l in range(5)] for r in range(reps)])
+        return t.mean(axis=0)   # ms per launch of [conv1, conv2, conv3, conv4, head] at CHUNK samples
+
+    lt = layer_times(scorer, 24)
+    conv_ms = float(lt[1] + lt[2] + lt[3])
+    nseg = 3 if args.mode == "fp32" else 1
+    achieved_tf = FLOP_CONV * CHUNK / (conv_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (L2+L3+L4 implicit-GEMM launches of one chunk)",
+                "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sust"],
+                "peak_source": f"bf16_tflops_sustained of {pk['src']}", "traffic": None,
+                "algorithmic_flops_per_sample": FLOP_CONV, "samples_per_launch_group": CHUNK,
+                "issued_tensor_flops_factor": nseg}
+    kernels = {"chunk": CHUNK, "ms": {k: float(v) for k, v in zip(["conv1", "conv2", "conv3", "conv4", "head"], lt)},
+               "tflops": {k: float(f * CHUNK / (v * 1e-3) / 1e12) for k, f, v in zip(
+                   ["conv2", "conv3", "conv4"], [2 * 256 * 128 * 1024, 2 * 64 * 256 * 2048, 2 * 16 * 512 * 4096], lt[1:4])}}
+
+    # selection + compaction kernels alone (HBM-bound in theory; 0.5 MB here => launch/L2 bound)
+    def sel_only():
+        t = sb.percentile_device(losses, q, group, n_global)
+        return sb.compact_indices(losses, t, 0, base)
+    ms_sel, _ = timed(sel_only, 20, 3)
+
+    # ---- secondary: the fp32-parity conv mode (or bf16 when the headline is fp32) --------------------------
+    other = "fp32" if args.mode == "bf16" else "bf16"
+    sc2 = sb.D64Scorer(netD, device, other, max_batch=CHUNK)
+    ms2, _ = timed(lambda: strain_step(sc2), max(2, args.steps // 3), 3)
+    sc2.check()
+    del sc2
+
+    # ---- end to end through the reference-facing call, host dataset -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(E2E_SAMPLES, shard)
+        host = torch.empty((ne, 3, 64, 64), dtype=torch.float32).pin_memory()
+        host.copy_(images[:ne])
+        ds = torch.utils.data.TensorDataset(host, torch.zeros(ne, dtype=torch.long))
+
+        def e2e_step():
+            return sb.refine_dataset_by_loss(ds, netD, device, LOSS_RATIO, conv_mode=args.mode)
+        for _ in range(3):
+            sub, _t = e2e_step()
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        es = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(es):
+            sub, _t = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / es], device=device)
+        if group is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": ne * world / dt.item(), "unit": "samples/s", "h2d_bytes_per_step": ne * 49152,
+               "d2h_bytes_per_step": int(len(sub.indices)) * 8 + 12, "samples_per_gpu": ne,
+               "api": "refine_dataset_by_loss(TensorDataset(host pinned fp32), netD, device, 0.1)",
+               "note": "each rank strains its own host dataset (replicas); PCIe H2D of 49152 B/sample is inside the timed region"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port of the reference on the host cores ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ns = 2048
+        xs = torch.from_numpy(O.synth_images(0, ns))
+        O.refine_dataset_by_loss(xs[:256], netD, LOSS_RATIO)
+        t0 = time.perf_counter()
+        O.refine_dataset_by_loss(xs, netD, LOSS_RATIO)
+        dt = time.perf_counter() - t0
+        cpu = {"value": ns / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64)"}
+
+    if rank == 0:
+        line = {"metric": "strained_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "bf16x3 (fp32-parity split)",
+                "data": "synthetic",
+                "config": {"workload": "C5 dataset-scale D64 scoring + global top-10% radix select + index compaction",
+                           "samples_per_gpu": shard, "samples_total": n_global, "chunk": CHUNK, "loss_ratio": LOSS_RATIO,
+                           "conv_mode": args.mode, "l2": "inputs (6.4 GB/GPU) larger than L2; no flush needed",
+                           "kept": kept, "threshold": float(thr.item())},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "frac_of_conv_roofline": value / world / (pk["tf_sust"] * 1e12 / FLOP_ALL),
+                "kernels": kernels, "select_compact_ms": ms_sel,
+                "other_mode": {"conv_mode": other, "value": n_global / (ms2 * 1e-3), "ms_per_step": ms2}}
+        print(json.dumps(line), flush=True)
+    if group is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
