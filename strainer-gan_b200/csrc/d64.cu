@@ -19,6 +19,7 @@
 // (hi = rn(x), lo = rn(x - hi)); the GEMM runs three K-segments per (tap, channel chunk):
 // A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, i.e. a 3x longer K loop through the same kernel.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -29,12 +30,13 @@ namespace d64 {
 using namespace ptx;
 
 constexpr int kErrProducer = 1, kErrMma = 2, kErrMmaAcc = 3, kErrEpilogue = 4;
+constexpr int kIn0Bytes = 66 * 66 * 4 * 2;  // one padded 66x66x4 bf16 image (34848 B)
 
 // ------------------------------------------------------------------------------------------
 // Packed parameter block layout (bytes), shared by sg_d64_pack / sg_d64_score
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
-  size_t w1, w2, w3, w4, w5, ss2, ss3, ss4, total;
+  size_t w1, w1t, w2, w3, w4, w5, ss2, ss3, ss4, total;
   int nseg;
 };
 static PackedLayout packed_layout(int mode) {
@@ -46,6 +48,7 @@ static PackedLayout packed_layout(int mode) {
   L.w3 = o; o += align_up((size_t)256 * 16 * 128 * L.nseg * 2, 1024);
   L.w4 = o; o += align_up((size_t)512 * 16 * 256 * L.nseg * 2, 1024);
   L.w5 = o; o += align_up(16 * 512 * 4, 1024);
+  L.w1t = o; o += align_up(64 * 64 * 2 * 2, 1024);  // conv1 weights, bf16 [64][hi|lo][kh*16 + kw*4 + c]
   L.ss2 = o; o += align_up(2 * 128 * 4, 1024);
   L.ss3 = o; o += align_up(2 * 256 * 4, 1024);
   L.ss4 = o; o += align_up(2 * 512 * 4, 1024);
@@ -54,7 +57,7 @@ static PackedLayout packed_layout(int mode) {
 }
 
 struct WorkspaceLayout {
-  size_t flag, act1, act2, act3, act4, total;
+  size_t flag, act0, act1, act2, act3, act4, total;
   int sega;
 };
 static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
@@ -66,6 +69,7 @@ static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
   L.act2 = o; o += align_up((size_t)batch * 16 * 16 * 128 * L.sega * 2, 1024);
   L.act3 = o; o += align_up((size_t)batch * 8 * 8 * 256 * L.sega * 2, 1024);
   L.act4 = o; o += align_up((size_t)batch * 16 * 512 * L.sega * 2, 1024);
+  L.act0 = o; o += align_up((size_t)batch * kIn0Bytes * L.sega, 1024);  // zero-padded NHWC4 bf16 input
   L.total = o;
   return L;
 }
@@ -96,8 +100,15 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
 
 // w1 [64][3][4][4] -> fp32 [k = c*16 + kh*4 + kw][64];  w5 [1][512][4][4] -> fp32 [p = kh*4+kw][512]
 __global__ void pack_small_kernel(const float* __restrict__ w1, const float* __restrict__ w5, float* __restrict__ o1,
-                                  float* __restrict__ o5) {
+                                  float* __restrict__ o5, __nv_bfloat16* __restrict__ o1t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * 128) {  // o1t [co][seg][kh*16 + kw*4 + c], c == 3 is the zero pad channel
+    const int co = i >> 7, seg = (i >> 6) & 1, k = i & 63;
+    const int kh = k >> 4, kw = (k >> 2) & 3, c = k & 3;
+    const float v = (c < 3) ? w1[co * 48 + c * 16 + kh * 4 + kw] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    o1t[i] = seg ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
   if (i < 48 * 64) {
     const int k = i >> 6, co = i & 63;
     o1[i] = w1[co * 48 + k];
@@ -413,6 +424,204 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// L1 on the tensor cores.
+//  prep_input_kernel : fp32 NCHW -> zero-padded NHWC4 bf16 [n][sega][66][66][4] (hi | lo planes), so that
+//                      for a fixed kh the 16 K-values (kw, c) of an output pixel are 32 contiguous bytes.
+//  conv1_umma_kernel : implicit GEMM M = 128 pixels (4 output rows x 32), N = 64, K = 4 x 16.  The A
+//                      slice of one kh is ONE 5-D TMA box over an overlapping-stride view of the padded
+//                      image (window stride 16 B along ow), landing as a K-major SWIZZLE_32B operand;
+//                      the 8/16 KB of weights stay resident in shared memory for the whole kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_input_kernel(const float* __restrict__ x, uint2* __restrict__ out,
+                                                         int64_t batch, int sega) {
+  const int64_t total = batch * 4356;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / 4356;
+    const int r2 = (int)(i - n * 4356);
+    const int r = r2 / 66, c = r2 - r * 66;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (r >= 1 && r <= 64 && c >= 1 && c <= 64) {
+      const float* px = x + (size_t)n * 12288 + (r - 1) * 64 + (c - 1);
+      v0 = px[0]; v1 = px[4096]; v2 = px[8192];
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1), h2 = __float2bfloat16_rn(v2);
+    uint2 hi;
+    hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    hi.y = (uint32_t)__bfloat16_as_ushort(h2);
+    out[(size_t)n * sega * 4356 + r2] = hi;
+    if (sega == 2) {
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      const __nv_bfloat16 l2 = __float2bfloat16_rn(v2 - __bfloat162float(h2));
+      uint2 lo;
+      lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      lo.y = (uint32_t)__bfloat16_as_ushort(l2);
+      out[((size_t)n * 2 + 1) * 4356 + r2] = lo;
+    }
+  }
+}
+
+// K-major SWIZZLE_32B operand descriptor: rows of 32 B, 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) |
+         (6ull << 61);
+}
+
+template <int SEGA>
+struct Conv1Cfg {
+  static constexpr int kSliceA = 128 * 32;             // one kh slice of A: 128 rows x 32 B
+  static constexpr int kSliceB = 64 * 32;              // one kh slice of B: 64 rows x 32 B
+  static constexpr int kStageBytes = SEGA * 4 * kSliceA;
+  static constexpr int kBBytes = SEGA * 4 * kSliceB;
+  static constexpr int kStages = (SEGA == 2) ? 2 : 4;
+  static constexpr int kTmemCols = 128;                // 2 accumulators x 64 columns
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 256 + 1024;
+  static constexpr int kThreads = 192;
+};
+
+template <int SEGA>
+__global__ void __launch_bounds__(192, 2)
+conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  __nv_bfloat16* __restrict__ act1, int total_tiles, int* err) {
+  using Cfg = Conv1Cfg<SEGA>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + S * Cfg::kStageBytes;
+  const uint32_t bar0 = b_base + Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kBBytes);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: SEGA x 4 slices of [64 x 16]
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int sg_ = 0; sg_ < SEGA; ++sg_)
+        for (int kh = 0; kh < 4; ++kh)
+          tma_load_2d(b_base + (sg_ * 4 + kh) * Cfg::kSliceB, &tmap_b, wbar, sg_ * 64 + kh * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile >> 3, oh0 = (tile & 7) << 2;
+        if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrProducer + 10)) break;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+        for (int sg_ = 0; sg_ < SEGA; ++sg_)
+          for (int kh = 0; kh < 4; ++kh)
+            tma_load_5d(sa + (sg_ * 4 + kh) * Cfg::kSliceA, &tmap_a, full_bar(stage), 0, 0, kh & 1, oh0 + (kh >> 1),
+                        n * SEGA + sg_);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrMma + 10);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrMmaAcc + 10)) break;
+        if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrMma + 10)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int kh = 0; kh < 4; ++kh) {
+          const uint64_t a_hi = umma_desc_sw32(sa + kh * Cfg::kSliceA);
+          const uint64_t b_hi = umma_desc_sw32(b_base + kh * Cfg::kSliceB);
+          umma_f16(tmem_d, a_hi, b_hi, idesc, (uint32_t)(kh != 0));
+          if (SEGA == 2) {
+            const uint64_t a_lo = umma_desc_sw32(sa + (4 + kh) * Cfg::kSliceA);
+            const uint64_t b_lo = umma_desc_sw32(b_base + (4 + kh) * Cfg::kSliceB);
+            umma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
+            umma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int ct = 64 * SEGA;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n = tile >> 3, oh = ((tile & 7) << 2) + (row >> 5), ow = row & 31;
+      __nv_bfloat16* dst = act1 + ((((size_t)n * 4 + ((oh & 1) * 2 + (ow & 1))) * 16 + (oh >> 1)) * 16 + (ow >> 1)) * ct;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrEpilogue + 10)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int cb = 0; cb < 64; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+          a = a > 0.f ? a : 0.2f * a;
+          b = b > 0.f ? b : 0.2f * b;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
+          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
+          if (SEGA == 2) {
+            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
+            lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+          }
+        }
+        uint4* d = reinterpret_cast<uint4*>(dst + cb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        if (SEGA == 2) {
+          uint4* dl = reinterpret_cast<uint4*>(dst + 64 + cb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // L5 head: logit = <act4[n], w5>, prob = sigmoid(logit), loss = -max(log prob, -100).
 // One warp per sample; fixed summation order (lane-strided partials, xor-shuffle tree).
 // ------------------------------------------------------------------------------------------
@@ -495,11 +704,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int encode(CUtensorMap* m, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(state().encode_tiled);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
@@ -564,6 +773,41 @@ static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, co
   return SG_OK;
 }
 
+
+template <int SEGA>
+static int launch_conv1(const float* x, __nv_bfloat16* act0, const __nv_bfloat16* w1t, __nv_bfloat16* act1,
+                        int64_t batch, int* err, cudaStream_t stream) {
+  using Cfg = Conv1Cfg<SEGA>;
+  {
+    int64_t blocks = ceil_div(batch * 4356, 256);
+    const int64_t cap = (int64_t)state().sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    prep_input_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, reinterpret_cast<uint2*>(act0), batch, SEGA);
+    SG_LAUNCH_CHECK();
+  }
+  CUtensorMap ta, tb;
+  {
+    // (k within window, ow [window stride 16 B], row parity, row pair, image*SEGA + seg)
+    cuuint64_t dims[5] = {16, 32, 2, 33, (cuuint64_t)batch * SEGA};
+    cuuint64_t strides[4] = {16, 66 * 4 * 2, 2 * 66 * 4 * 2, (cuuint64_t)kIn0Bytes};
+    cuuint32_t box[5] = {16, 32, 1, 4, 1};
+    int r = encode(&ta, 5, act0, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+  }
+  {
+    cuuint64_t dims[2] = {128, 64};
+    cuuint64_t strides[1] = {128 * 2};
+    cuuint32_t box[2] = {16, 64};
+    int r = encode(&tb, 2, w1t, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+  }
+  const int64_t tiles = batch * 8;
+  int grid = (int)(tiles < (int64_t)state().sm_count * 2 ? tiles : (int64_t)state().sm_count * 2);
+  conv1_umma_kernel<SEGA><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, act1, (int)tiles, err);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 }  // namespace d64
 }  // namespace sg
 
@@ -575,6 +819,10 @@ int sg_d64_init_attributes() {
                                ConvCfg<128>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<256>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Conv1Cfg<1>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Conv1Cfg<2>::kSmemBytes));
   return SG_OK;
 }
 
@@ -598,7 +846,8 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
   const PackedLayout L = packed_layout(conv_mode);
   cudaStream_t st = sg::as_stream(stream);
   uint8_t* pk = static_cast<uint8_t*>(packed);
-  pack_small_kernel<<<32, 256, 0, st>>>(w1, w5, reinterpret_cast<float*>(pk + L.w1), reinterpret_cast<float*>(pk + L.w5));
+  pack_small_kernel<<<32, 256, 0, st>>>(w1, w5, reinterpret_cast<float*>(pk + L.w1), reinterpret_cast<float*>(pk + L.w5),
+                                        reinterpret_cast<__nv_bfloat16*>(pk + L.w1t));
   SG_LAUNCH_CHECK();
   pack_conv_weight_kernel<<<256, 256, 0, st>>>(w2, reinterpret_cast<__nv_bfloat16*>(pk + L.w2), 128, 64, L.nseg);
   pack_conv_weight_kernel<<<512, 256, 0, st>>>(w3, reinterpret_cast<__nv_bfloat16*>(pk + L.w3), 256, 128, L.nseg);
@@ -637,9 +886,13 @@ int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* wo
   switch (layer) {
     case 1:
       SG_REQUIRE(x != nullptr && ((uintptr_t)x & 15) == 0, "x must be a 16-byte aligned device pointer");
-      conv1_kernel<<<(unsigned)(batch * 8), 128, 0, st>>>(x, fq(P.w1), act1, W.sega);
-      SG_LAUNCH_CHECK();
-      return SG_OK;
+      if (getenv("SG_CONV1_DIRECT")) {  // CUDA-core direct conv kept for A/B timing only
+        conv1_kernel<<<(unsigned)(batch * 8), 128, 0, st>>>(x, fq(P.w1), act1, W.sega);
+        SG_LAUNCH_CHECK();
+        return SG_OK;
+      }
+      return (W.sega == 2) ? launch_conv1<2>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st)
+                           : launch_conv1<1>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st);
     case 2:
       return launch_conv<128>(act1, wq(P.w2), fq(P.ss2), act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
     case 3:
