@@ -424,6 +424,145 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// L2 (64 -> 128 channels) with the operands swapped: D^T[cout][pixel] = W * X^T.
+// With only 128 output channels a 128(pixel) x 128(cout) tile makes every tcgen05.mma read as many
+// operand bytes as a 128x256 one for half the math (shared-memory bound, 36 % tensor-pipe active
+// in profiles/r1a).  Here M = the 128 output channels (weights are the A operand), N = the 256
+// pixels of ONE whole 16x16 output image (a single 5-D TMA box), so the instruction is the full
+// 128x256x16 shape.  The accumulator is channel-major: TMEM lane = channel, column = pixel; the
+// epilogue writes one bf16 per lane, a warp covering 64 contiguous bytes of a pixel's channel row.
+// ------------------------------------------------------------------------------------------
+struct Conv2Cfg {
+  static constexpr int kWBytes = 128 * 64 * 2;    // weights tile  [128 cout x 64 k]
+  static constexpr int kXBytes = 256 * 64 * 2;    // pixel tile    [256 px   x 64 k]
+  static constexpr int kStageBytes = kWBytes + kXBytes;
+  static constexpr int kStages = 4;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kThreads = 192;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const ConvParams p) {
+  using Cfg = Conv2Cfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  const uint32_t bar0 = base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_w);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
+        for (int ks = 0; ks < p.k_steps; ++ks) {
+          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer + 20)) { ok = false; break; }
+          const int seg = ks % p.nseg;
+          const int tap = ks / p.nseg;  // c_in == 64: one channel chunk per tap
+          const int kh = tap >> 2, kw = tap & 3;
+          const uint32_t sw = base + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(sw, &tmap_w, full_bar(stage), ks * 64, 0);
+          tma_load_5d(sw + Cfg::kWBytes, &tmap_x, full_bar(stage), seg == 1 ? 64 : 0, (kw - 1) >> 1, (kh - 1) >> 1,
+                      ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(256);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 20)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        for (int ks = 0; ks < p.k_steps; ++ks) {
+          if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma + 20)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sw = base + stage * Cfg::kStageBytes;
+          const uint64_t wdesc = umma_desc_sw128(sw);
+          const uint64_t xdesc = umma_desc_sw128(sw + Cfg::kWBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_d, wdesc + 2 * k, xdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int ch = lg * 32 + lane;          // this thread's output channel
+    const float sc = __ldg(p.scale + ch), sh = __ldg(p.shift + ch);
+    const int ct = 128 * p.out_sega;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int img = blockIdx.x; img < p.n_img; img += gridDim.x) {
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 20)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 256);
+      __nv_bfloat16* out_img = p.out + (size_t)img * 4 * 64 * ct + ch;
+#pragma unroll 1
+      for (int pb = 0; pb < 256; pb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + pb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int px = pb + j, oh = px >> 4, ow = px & 15;
+          float a = fmaf(__uint_as_float(v[j]), sc, sh);
+          a = a > 0.f ? a : 0.2f * a;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+          __nv_bfloat16* d = out_img + ((size_t)((oh & 1) * 2 + (ow & 1)) * 64 + (oh >> 1) * 8 + (ow >> 1)) * ct;
+          *d = ah;
+          if (p.out_sega == 2) d[128] = __float2bfloat16_rn(a - __bfloat162float(ah));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // L1 on the tensor cores.
 //  prep_input_kernel : fp32 NCHW -> zero-padded NHWC4 bf16 [n][sega][66][66][4] (hi | lo planes), so that
 //                      for a fixed kh the 16 K-values (kw, c) of an output pixel are 32 contiguous bytes.
@@ -774,6 +913,43 @@ static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, co
 }
 
 
+static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* ss, __nv_bfloat16* act2,
+                             int64_t batch, int nseg, int sega, int* err, cudaStream_t stream) {
+  CUtensorMap tx, tw;
+  const int ct_in = 64 * sega;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)ct_in, 16, 16, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)16 * ct_in * 2, (cuuint64_t)256 * ct_in * 2,
+                             (cuuint64_t)1024 * ct_in * 2};
+    cuuint32_t box[5] = {64, 16, 16, 1, 1};
+    int r = encode(&tx, 5, act1, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  const int k_steps = 16 * nseg;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, 128};
+    cuuint64_t strides[1] = {(cuuint64_t)k_steps * 64 * 2};
+    cuuint32_t box[2] = {64, 128};
+    int r = encode(&tw, 2, wpk, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  ConvParams p = {};
+  p.n_img = (int)batch;
+  p.nseg = nseg;
+  p.k_steps = k_steps;
+  p.c_in = 64;
+  p.c_out = 128;
+  p.out_sega = sega;
+  p.scale = ss;
+  p.shift = ss + 128;
+  p.out = act2;
+  p.err = err;
+  const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
+  conv2_swap_kernel<<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, p);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 template <int SEGA>
 static int launch_conv1(const float* x, __nv_bfloat16* act0, const __nv_bfloat16* w1t, __nv_bfloat16* act1,
                         int64_t batch, int* err, cudaStream_t stream) {
@@ -819,6 +995,7 @@ int sg_d64_init_attributes() {
                                ConvCfg<128>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<256>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1Cfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -894,7 +1071,9 @@ int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* wo
       return (W.sega == 2) ? launch_conv1<2>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st)
                            : launch_conv1<1>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st);
     case 2:
-      return launch_conv<128>(act1, wq(P.w2), fq(P.ss2), act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
+      if (getenv("SG_CONV2_PIXEL_MAJOR"))  // 128x128 pixel-major tiles kept for A/B timing only
+        return launch_conv<128>(act1, wq(P.w2), fq(P.ss2), act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
+      return launch_conv2_swap(act1, wq(P.w2), fq(P.ss2), act2, batch, P.nseg, W.sega, err, st);
     case 3:
       return launch_conv<256>(act2, wq(P.w3), fq(P.ss3), act3, batch, 16, 128, 256, P.nseg, W.sega, 1, err, st);
     case 4:
