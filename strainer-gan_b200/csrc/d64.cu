@@ -612,16 +612,17 @@ struct Conv1Cfg {
   static constexpr int kSliceB = 64 * 32;              // one kh slice of B: 64 rows x 32 B
   static constexpr int kStageBytes = SEGA * 4 * kSliceA;
   static constexpr int kBBytes = SEGA * 4 * kSliceB;
-  static constexpr int kStages = (SEGA == 2) ? 2 : 4;
+  static constexpr int kStages = (SEGA == 2) ? 3 : 4;
   static constexpr int kTmemCols = 128;                // 2 accumulators x 64 columns
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 256 + 1024;
+  static constexpr int kStageOut = SEGA * 128 * 128;   // epilogue staging: 128 pixels x 64 ch bf16 per seg
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 2 * kStageOut + 256 + 1024;
   static constexpr int kThreads = 192;
 };
 
 template <int SEGA>
 __global__ void __launch_bounds__(192, 2)
 conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  __nv_bfloat16* __restrict__ act1, int total_tiles, int* err) {
+                  const __grid_constant__ CUtensorMap tmap_o, int total_tiles, int* err) {
   using Cfg = Conv1Cfg<SEGA>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -629,8 +630,9 @@ conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t b_base = base + S * Cfg::kStageBytes;
-  const uint32_t bar0 = b_base + Cfg::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kBBytes);
+  const uint32_t o_base = b_base + Cfg::kBBytes;   // 2 output staging buffers (1024-B aligned)
+  const uint32_t bar0 = o_base + 2 * Cfg::kStageOut;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kBBytes + 2 * Cfg::kStageOut);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
@@ -644,6 +646,7 @@ conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_b);
+    prefetch_tensormap(&tmap_o);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
     mbar_init(wbar, 1);
@@ -708,16 +711,26 @@ conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
+    // Epilogue: TMEM -> registers -> LeakyReLU -> bf16 -> swizzled smem staging -> TMA store.
+    // The tile's 128 pixels (4 output rows x 32 cols) are 4 parity planes x (2 x 16) pixels of act1:
+    // one 4 KB TMA box per plane (and per hi/lo segment), so HBM sees full 128-B rows.
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
+    const int ohl = row >> 5, ow = row & 31;
+    const int prow = (((ohl & 1) * 2 + (ow & 1)) << 5) + ((ohl >> 1) << 4) + (ow >> 1);  // row in staging
+    const uint32_t swz = (uint32_t)(prow & 7);
+    const bool issuer = (threadIdx.x == 64);
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int ct = 64 * SEGA;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n = tile >> 3, oh = ((tile & 7) << 2) + (row >> 5), ow = row & 31;
-      __nv_bfloat16* dst = act1 + ((((size_t)n * 4 + ((oh & 1) * 2 + (ow & 1))) * 16 + (oh >> 1)) * 16 + (ow >> 1)) * ct;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n = tile >> 3, oh0 = (tile & 7) << 2;
+      const uint32_t stg = o_base + (uint32_t)(it & 1) * Cfg::kStageOut;
       if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrEpilogue + 10)) break;
       tc_fence_after();
+      // the staging buffer used two tiles ago must have been read by its TMA stores
+      if (issuer) tma_store_wait_read<1>();
+      named_bar_sync(1, 128);
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
 #pragma unroll
       for (int cb = 0; cb < 64; cb += 32) {
@@ -738,19 +751,30 @@ conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
           }
         }
-        uint4* d = reinterpret_cast<uint4*>(dst + cb);
+        const uint32_t rbase = stg + (uint32_t)prow * 128u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-        if (SEGA == 2) {
-          uint4* dl = reinterpret_cast<uint4*>(dst + 64 + cb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)((cb >> 3) + q) ^ swz;   // SWIZZLE_128B: 16-B chunk ^= row & 7
+          st_shared_v4(rbase + chunk * 16u, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (SEGA == 2)
+            st_shared_v4(rbase + 128u * 128u + chunk * 16u, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      mbar_arrive(tempty_bar(acc));      // accumulator is in registers/smem: release TMEM early
+      fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA store
+      named_bar_sync(1, 128);
+      if (issuer) {
+#pragma unroll
+        for (int sg_ = 0; sg_ < SEGA; ++sg_)
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl)
+            tma_store_5d(&tmap_o, stg + (uint32_t)(sg_ * 128 * 128 + pl * 4096), sg_ * 64, 0, oh0 >> 1, pl, n);
+        tma_store_commit();
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (issuer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -977,9 +1001,19 @@ static int launch_conv1(const float* x, __nv_bfloat16* act0, const __nv_bfloat16
     int r = encode(&tb, 2, w1t, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r != SG_OK) return r;
   }
+  CUtensorMap to;
+  {
+    const cuuint64_t ct = 64 * SEGA;
+    cuuint64_t dims[5] = {ct, 16, 16, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {ct * 2, 16 * ct * 2, 256 * ct * 2, 1024 * ct * 2};
+    cuuint32_t box[5] = {64, 16, 2, 1, 1};
+    int r = encode(&to, 5, act1, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
   const int64_t tiles = batch * 8;
-  int grid = (int)(tiles < (int64_t)state().sm_count * 2 ? tiles : (int64_t)state().sm_count * 2);
-  conv1_umma_kernel<SEGA><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, act1, (int)tiles, err);
+  const int64_t ctas = (int64_t)state().sm_count * (SEGA == 1 ? 2 : 1);
+  int grid = (int)(tiles < ctas ? tiles : ctas);
+  conv1_umma_kernel<SEGA><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, (int)tiles, err);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
