@@ -94,31 +94,57 @@ def _torch_quantile_plan(n: int, q: float):
     return int(below), int(np.ceil(rank)), np.float32(rank - below)
 
 
-def order_stats(values: torch.Tensor, k: int, group=None) -> torch.Tensor:
+class _SelectOps:
+    """The five radix-select phases of the C ABI on one device (tests substitute a numpy double to
+    exercise the multi-rank protocol on CPU/gloo)."""
+
+    def __init__(self, device):
+        self.lib = _lib_for(device)
+
+    def begin(self, ws, k):
+        L.check(self.lib.sg_select_begin(_p(ws), k, _stream()), "sg_select_begin")
+
+    def hist(self, values, ws, p):
+        L.check(self.lib.sg_select_hist(_p(values), values.numel(), _p(ws), p, _stream()), "sg_select_hist")
+
+    def step(self, ws, p):
+        L.check(self.lib.sg_select_step(_p(ws), p, _stream()), "sg_select_step")
+
+    def min_above(self, values, ws):
+        L.check(self.lib.sg_select_min_above(_p(values), values.numel(), _p(ws), _stream()), "sg_select_min_above")
+
+    def finish(self, ws, out2):
+        L.check(self.lib.sg_select_finish(_p(ws), _p(out2), _stream()), "sg_select_finish")
+
+
+def order_stats(values: torch.Tensor, k: int, group=None, ops=None) -> torch.Tensor:
     """Device tensor [x_(k), x_(k+1)] of a 1-D fp32 CUDA tensor (radix select, no sort).
-    With ``group`` (torch.distributed), ``values`` is this rank's shard and k the GLOBAL rank; the
-    integer histograms are all-reduced so every rank gets identical results."""
+    With ``group`` (torch.distributed), ``values`` is this rank's shard and k the GLOBAL rank: the
+    integer digit histograms (+ NaN count) are all-reduced with SUM after each of the 3 passes and the
+    smallest key above the selected one with MIN, so every rank derives bit-identical statistics."""
     device = values.device
-    lib = _lib_for(device)
     n = values.numel()
     ws = torch.empty(L.SG_SELECT_WS_WORDS, dtype=torch.int32, device=device)
     out2 = torch.empty(2, dtype=torch.float32, device=device)
-    st = _stream()
-    if group is None:
-        L.check(lib.sg_radix_select(_p(values), n, k, _p(ws), _p(out2), st), "sg_radix_select")
+    if group is None and ops is None:
+        lib = _lib_for(device)
+        L.check(lib.sg_radix_select(_p(values), n, k, _p(ws), _p(out2), _stream()), "sg_radix_select")
         return out2
     import torch.distributed as dist
-    L.check(lib.sg_select_begin(_p(ws), k, st), "sg_select_begin")
+    ops = ops or _SelectOps(device)
+    ops.begin(ws, k)
     for p in range(L.SG_SELECT_NUM_PASSES):
-        L.check(lib.sg_select_hist(_p(values), n, _p(ws), p, st), "sg_select_hist")
-        dist.all_reduce(ws[:L.SG_SELECT_WS_NANCOUNT + 1], op=dist.ReduceOp.SUM, group=group)
-        L.check(lib.sg_select_step(_p(ws), p, st), "sg_select_step")
-    L.check(lib.sg_select_min_above(_p(values), n, _p(ws), st), "sg_select_min_above")
-    m = ws[L.SG_SELECT_WS_MINABOVE:L.SG_SELECT_WS_MINABOVE + 1]
-    m ^= -2147483648  # unsigned order -> signed order
-    dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
-    m ^= -2147483648
-    L.check(lib.sg_select_finish(_p(ws), _p(out2), st), "sg_select_finish")
+        ops.hist(values, ws, p)
+        if group is not None:
+            dist.all_reduce(ws[:L.SG_SELECT_WS_NANCOUNT + 1], op=dist.ReduceOp.SUM, group=group)
+        ops.step(ws, p)
+    ops.min_above(values, ws)
+    if group is not None:
+        m = ws[L.SG_SELECT_WS_MINABOVE:L.SG_SELECT_WS_MINABOVE + 1]
+        m ^= -2147483648  # uint32 key order -> int32 order for the MIN reduction
+        dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
+        m ^= -2147483648
+    ops.finish(ws, out2)
     return out2
 
 
@@ -129,12 +155,12 @@ def _lerp_dev(stats2: torch.Tensor, weight, kind: int) -> torch.Tensor:
     return thr
 
 
-def percentile_device(values: torch.Tensor, q, group=None, n_global=None) -> torch.Tensor:
+def percentile_device(values: torch.Tensor, q, group=None, n_global=None, ops=None) -> torch.Tensor:
     """``np.percentile(values_f32, q)`` evaluated on the GPU; returns a 1-element fp32 device tensor
     holding bit-for-bit numpy's result for python-scalar q (numpy evaluates q and the lerp in fp32)."""
     n = values.numel() if n_global is None else int(n_global)
     k0, k1, gamma, gdt = _np_percentile_plan(n, q)
-    stats2 = order_stats(values, k0, group)
+    stats2 = order_stats(values, k0, group, ops)
     if gdt != np.float32:
         # np.float64 q: numpy interpolates in float64 -> host finish on the two order statistics
         a, b = stats2.cpu().numpy().astype(np.float64)
@@ -143,6 +169,8 @@ def percentile_device(values: torch.Tensor, q, group=None, n_global=None) -> tor
         return torch.tensor([r], dtype=torch.float64)
     if k1 == k0:
         stats2 = torch.stack([stats2[0], stats2[0]])
+    if ops is not None and hasattr(ops, "lerp"):
+        return ops.lerp(stats2, gamma, L.SG_LERP_NUMPY)
     return _lerp_dev(stats2, gamma, L.SG_LERP_NUMPY)
 
 
@@ -431,6 +459,20 @@ def select_below_percentile(losses: torch.Tensor, q, group=None, index_base: int
     thr_h = thr.cpu().numpy()[0]
     c = int(count.item())
     return idx[:c].cpu().numpy(), thr_h
+
+
+def strain_shard(images: torch.Tensor, discriminator, loss_ratio=0.2, *, group=None, index_base: int = 0,
+                 n_global=None, conv_mode: str = "fp32", device=None):
+    """Data-parallel ``refine_dataset_by_loss`` ("#strainer gan.py:364-392") for one rank of a
+    sharded dataset: this rank scores ``images`` (global indices index_base ...), the threshold is the
+    GLOBAL percentile (only histograms cross NVLink), and the returned kept indices are global.
+    Concatenating the per-rank index arrays in rank order reproduces the single-GPU / reference
+    ``np.where`` order.  Returns (np.int64 kept_global_indices, np.float32 threshold, losses_dev)."""
+    device = _dev(device if device is not None else (images.device if images.is_cuda else None))
+    discriminator.eval()
+    losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
+    idx, thr = select_below_percentile(losses, (1 - loss_ratio) * 100, group, index_base, n_global)
+    return idx, thr, losses
 
 
 def get_percentile_threshold(losses, percentile=75):

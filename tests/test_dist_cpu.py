@@ -1,0 +1,148 @@
+"""CPU, world_size 2 over gloo: the multi-rank selection protocol.  The CUDA phases are
+replaced by a numpy double with the kernels' exact semantics (radix keys, 11/11/10-bit digit
+histograms, min-above), so what is under test is the host orchestration in api.order_stats /
+percentile_device: which words are all-reduced, with which op, in which order -- and that every
+rank ends with bit-identical order statistics equal to the single-process result."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import strainer_oracle as O
+
+
+def f2key(v):
+    b = np.asarray(v, np.float32).view(np.uint32).copy()
+    nan = (b & 0x7FFFFFFF) > 0x7F800000
+    b[b == 0x80000000] = 0
+    k = np.where(b & 0x80000000, ~b, b | 0x80000000).astype(np.uint32)
+    k[nan] = 0xFFFFFFFF
+    return k
+
+
+def key2f(k):
+    k = np.uint32(k)
+    if k == 0xFFFFFFFF:
+        return np.float32(np.nan)
+    b = (k & np.uint32(0x7FFFFFFF)) if (k & np.uint32(0x80000000)) else ~k
+    return np.array([b], np.uint32).view(np.float32)[0]
+
+
+class FakeSelectOps:
+    """numpy restatement of sel::begin/hist/step/min_above/finish (csrc/select.cu)."""
+    PREFIX, KREM, SELKEY, NEEDNEXT = 2052, 2054, 2056, 2057
+
+    def _u(self, ws):
+        return ws.numpy().view(np.uint32)
+
+    def begin(self, ws, k):
+        u = self._u(ws)
+        u[:] = 0
+        u[2049] = 0xFFFFFFFF
+        u[self.KREM:self.KREM + 2].view(np.uint64)[0] = k
+
+    def hist(self, values, ws, p):
+        u = self._u(ws)
+        key = f2key(values.numpy())
+        prefix = u[self.PREFIX]
+        if p == 0:
+            sel, dig = np.ones(key.shape, bool), key >> 21
+            u[2048] += np.uint32((key == 0xFFFFFFFF).sum())
+        elif p == 1:
+            sel, dig = (key >> 21) == prefix, (key >> 10) & 0x7FF
+        else:
+            sel, dig = (key >> 10) == prefix, key & 0x3FF
+        u[:2048] += np.bincount(dig[sel], minlength=2048).astype(np.uint32)
+
+    def step(self, ws, p):
+        u = self._u(ws)
+        k = int(u[self.KREM:self.KREM + 2].view(np.uint64)[0])
+        h = u[:2048].astype(np.uint64)
+        c = np.cumsum(h)
+        b = int(np.searchsorted(c, k, side="right"))
+        before = int(c[b - 1]) if b else 0
+        bits = 10 if p == 2 else 11
+        u[self.PREFIX] = b if p == 0 else ((int(u[self.PREFIX]) << bits) | b) & 0xFFFFFFFF
+        u[self.KREM:self.KREM + 2].view(np.uint64)[0] = k - before
+        if p == 2:
+            u[self.SELKEY] = u[self.PREFIX]
+            u[self.NEEDNEXT] = 1 if (k - before + 1 >= int(h[b])) else 0
+        u[:2048] = 0
+
+    def min_above(self, values, ws):
+        u = self._u(ws)
+        key = f2key(values.numpy())
+        above = key[key > u[self.SELKEY]]
+        if above.size:
+            u[2049] = min(u[2049], above.min())
+
+    def finish(self, ws, out2):
+        u = self._u(ws)
+        if u[2048]:
+            out2[:] = float("nan")
+            return
+        a = key2f(u[self.SELKEY])
+        b = a
+        if u[self.NEEDNEXT] and u[2049] != 0xFFFFFFFF:
+            b = key2f(u[2049])
+        out2[0], out2[1] = float(a), float(b)
+
+    def lerp(self, stats2, gamma, kind):
+        a, b = np.float32(stats2[0].item()), np.float32(stats2[1].item())
+        return torch.tensor([O.np_lerp(a, b, np.float32(gamma))], dtype=torch.float32)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import strainer_b200 as sb
+    rng = np.random.default_rng(123)
+    n = 20000
+    v = O.synth_losses(n, seed=77)
+    m = rng.random(n)
+    v[m < 0.3] = np.float32(0.25)
+    v[(m > 0.3) & (m < 0.33)] = np.float32(-0.0)
+    bounds = [0, 8192, n]                         # chunk-aligned, unequal shards
+    shard = torch.from_numpy(v[bounds[rank]:bounds[rank + 1]].copy())
+    s = np.sort(v)
+    ok = True
+    for k in (0, 1234, 5999, 6000, n - 2, n - 1):
+        got = sb.order_stats(shard, k, dist.group.WORLD, FakeSelectOps()).numpy()
+        want = np.array([s[k], s[min(k + 1, n - 1)]], np.float32)
+        ok &= bool(np.array_equal(got, want))
+    for q in (90.0, (1 - 0.8) * 100, 30.0, 100.0, 0.0):
+        thr = sb.percentile_device(shard, q, dist.group.WORLD, n, FakeSelectOps()).numpy()[0]
+        ok &= bool(thr == np.percentile(v, q))
+        # kept indices: local compaction + global base; concatenation by rank == np.where order
+        local = np.where(shard.numpy() < thr)[0] + bounds[rank]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        ok &= bool(np.array_equal(np.concatenate(gathered), np.where(v < thr)[0]))
+    vn = shard.clone()
+    if rank == 1:
+        vn[5] = float("nan")                       # a NaN on ONE rank poisons the global threshold on ALL ranks
+    ok &= bool(np.isnan(sb.percentile_device(vn, 90.0, dist.group.WORLD, n, FakeSelectOps()).numpy()[0]))
+    open(os.path.join(tmp, f"ok{rank}"), "w").write(str(ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_select_protocol_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["True", "True"]
+
+
+def test_fake_ops_match_single_process():
+    """the numpy double itself against np.sort (so the gloo test checks the protocol, not the double)"""
+    import strainer_b200 as sb
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(5000).astype(np.float32)
+    v[::7] = 0.5
+    s = np.sort(v)
+    for k in (0, 17, 2500, 4998, 4999):
+        got = sb.order_stats(torch.from_numpy(v), k, None, FakeSelectOps()).numpy()
+        assert np.array_equal(got, [s[k], s[min(k + 1, 4999)]])

@@ -1,0 +1,48 @@
+"""torchrun --nproc-per-node N tools/multi_gpu_check.py
+Every rank strains its shard over NCCL; rank 0 also strains the whole dataset alone and checks that the
+global threshold and the concatenated kept-index list are BIT-IDENTICAL to the single-GPU result
+(BASELINE.json north_star: 'identical to single-GPU results')."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import strainer_b200 as sb  # noqa: E402
+from oracle import strainer_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    per = 12288
+    n = per * world
+    netD = O.make_discriminator(O.SEED)
+    results = {}
+    for mode in ("fp32", "bf16"):
+        imgs = sb.synth_images(rank * per, per, O.SEED, device)
+        idx, thr, losses = sb.strain_shard(imgs, netD, 0.1, group=dist.group.WORLD, index_base=rank * per,
+                                           n_global=n, conv_mode=mode, device=device)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (idx, thr))
+        if rank == 0:
+            all_idx = np.concatenate([g[0] for g in gathered])
+            thrs = [g[1] for g in gathered]
+            assert all(t == thrs[0] for t in thrs), thrs
+            full = sb.synth_images(0, n, O.SEED, device)
+            idx1, thr1, _ = sb.strain_shard(full, netD, 0.1, conv_mode=mode, device=device)
+            assert thr1 == thrs[0], (thr1, thrs[0])
+            assert np.array_equal(all_idx, idx1)
+            results[mode] = (float(thr1), len(idx1), n)
+    if rank == 0:
+        print("multi_gpu_check OK", world, "ranks", results, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
