@@ -79,6 +79,15 @@ size_t sg_d64_workspace_bytes(int64_t max_batch, int conv_mode);
  * loss[batch] = -max(log prob, -100) (any of the three may be NULL). */
 int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
                  float* logit, float* prob, float* loss, void* stream);
+/* Train-mode-BatchNorm scoring: what `netD(real)` computes when netD was never put in eval mode
+ * ("# 상위 10% 제거해서 fake image에 concate.py:244-245"): layers 2..4 normalise with
+ * the batch statistics of THIS call and update the running statistics in place
+ * (running = (1-momentum)*running + momentum*batch_stat, unbiased variance); NULL running pointers
+ * skip the update.  gamma/beta come from `packed`. */
+int sg_d64_score_train(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
+                       float* bn2_running_mean, float* bn2_running_var, float* bn3_running_mean,
+                       float* bn3_running_var, float* bn4_running_mean, float* bn4_running_var, float momentum,
+                       float bn_eps, float* logit, float* prob, float* loss, void* stream);
 /* One stage of sg_d64_score on the same workspace (1: conv1 ... 4: conv4, 5: head); used by the
  * benchmark to time each kernel with events on the launching stream, and by the tests. */
 int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,

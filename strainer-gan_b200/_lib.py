@@ -30,6 +30,7 @@ _SIGS = {
     "sg_d64_pack": (c_int, [P] * 17 + [c_float, c_int, P, P]),
     "sg_d64_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "sg_d64_score": (c_int, [P, c_int64, P, P, c_int, P, P, P, P]),
+    "sg_d64_score_train": (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, c_float, c_float, P, P, P, P]),
     "sg_d64_run_layer": (c_int, [P, c_int64, P, P, c_int, c_int, P, P, P, P]),
     "sg_d64_check": (c_int, [P, P]),
     "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),

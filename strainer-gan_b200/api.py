@@ -317,6 +317,41 @@ class D64Scorer:
         L.check(self.lib.sg_d64_score(_p(x), b, _p(self.packed), _p(self.ws), self.mode, _p(logit), _p(prob), _p(loss),
                                       _stream()), "sg_d64_score")
 
+    def score_train_into(self, discriminator: nn.Module, x: torch.Tensor, logit=None, prob=None, loss=None):
+        """``netD(x)`` for a netD in TRAIN mode (under no_grad): BatchNorm uses the statistics of this batch
+        and its running_mean / running_var / num_batches_tracked are updated exactly as
+        nn.BatchNorm2d does."""
+        b = x.shape[0]
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        self.repack(discriminator)
+        _, bns = _d64_modules(discriminator)
+        stats, back = [], []
+        for bn in bns:
+            if not bn.track_running_stats or bn.running_mean is None:
+                stats += [None, None]
+                continue
+            for t in (bn.running_mean, bn.running_var):
+                if t.is_cuda and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous():
+                    stats.append(t)
+                else:
+                    d = t.detach().to(self.device, torch.float32).contiguous()
+                    stats.append(d)
+                    back.append((t, d))
+        moms = {bn.momentum for bn in bns}
+        if len(moms) != 1 or None in moms:
+            raise NotImplementedError("BatchNorm layers with different / cumulative momentum")
+        L.check(self.lib.sg_d64_score_train(_p(x), b, _p(self.packed), _p(self.ws), self.mode, *[_p(t) for t in stats],
+                                            float(moms.pop()), float(bns[0].eps), _p(logit), _p(prob), _p(loss), _stream()),
+                "sg_d64_score_train")
+        with torch.no_grad():
+            for t, d in back:
+                t.copy_(d)
+            for bn in bns:
+                if bn.track_running_stats and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+        self._sig = None  # running stats changed under the packed eval-mode fold
+
     def run_layer(self, x, layer: int, logit=None, prob=None, loss=None):
         """One stage (1..5) of score_into on this scorer's workspace (benchmark / tests)."""
         L.check(self.lib.sg_d64_run_layer(_p(x), x.shape[0], _p(self.packed), _p(self.ws), self.mode, layer, _p(logit),
@@ -635,17 +670,20 @@ def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1,
 
 
 def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "fp32"):
-    """The in-batch strain block ("# 상위 10% 제거해서 fake image에 concate.py:243-251") for a netD in EVAL
-    mode (after any dataset-scale strain the reference's D is in eval mode for good).
+    """The in-batch strain block ("# 상위 10% 제거해서 fake image에 concate.py:243-251"):
+    real_scores = netD(real) under no_grad, threshold = torch.quantile(scores, q), mask = scores >= thr.
+    netD is used AS IS: in train mode BatchNorm normalises with the batch statistics and its running
+    statistics are updated; in eval mode (the state every script that ran a
+    dataset-scale strain is in, quirk 1) the folded running statistics are used.
     Returns (filtered_real, filtered_fake, mask, threshold)."""
-    if netD.training and any(isinstance(m, nn.BatchNorm2d) for m in netD.modules()):
-        raise NotImplementedError("strain_batch: train-mode BatchNorm scoring (batch statistics + running-stat "
-                                  "update) is not built yet; call netD.eval() or score with torch and use strain_scores")
     device = _dev(real.device)
     sc = get_scorer(netD, device, conv_mode, max_batch=max(real.shape[0], 512))
     b = real.shape[0]
     prob = torch.empty(b, dtype=torch.float32, device=device)
-    sc.score_into(real.contiguous(), None, prob, None)
+    if netD.training:
+        sc.score_train_into(netD, real.contiguous(), None, prob, None)
+    else:
+        sc.score_into(real.contiguous(), None, prob, None)
     return strain_scores(real, prob, q)
 
 

@@ -30,13 +30,14 @@ namespace d64 {
 using namespace ptx;
 
 constexpr int kErrProducer = 1, kErrMma = 2, kErrMmaAcc = 3, kErrEpilogue = 4;
+constexpr int kBnBlocks = 256;              // fixed row partition of the train-mode BN reduction
 constexpr int kIn0Bytes = 66 * 66 * 4 * 2;  // one padded 66x66x4 bf16 image (34848 B)
 
 // ------------------------------------------------------------------------------------------
 // Packed parameter block layout (bytes), shared by sg_d64_pack / sg_d64_score
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
-  size_t w1, w1t, w2, w3, w4, w5, ss2, ss3, ss4, total;
+  size_t w1, w1t, w2, w3, w4, w5, ss2, ss3, ss4, ident, gb2, gb3, gb4, total;
   int nseg;
 };
 static PackedLayout packed_layout(int mode) {
@@ -52,12 +53,16 @@ static PackedLayout packed_layout(int mode) {
   L.ss2 = o; o += align_up(2 * 128 * 4, 1024);
   L.ss3 = o; o += align_up(2 * 256 * 4, 1024);
   L.ss4 = o; o += align_up(2 * 512 * 4, 1024);
+  L.ident = o; o += align_up(2 * 512 * 4, 1024);  // scale 1 | shift 0 (raw conv output for train-mode BN)
+  L.gb2 = o; o += align_up(2 * 128 * 4, 1024);    // gamma | beta
+  L.gb3 = o; o += align_up(2 * 256 * 4, 1024);
+  L.gb4 = o; o += align_up(2 * 512 * 4, 1024);
   L.total = o;
   return L;
 }
 
 struct WorkspaceLayout {
-  size_t flag, act0, act1, act2, act3, act4, total;
+  size_t flag, act0, act1, act2, act3, act4, bnpart, bnss, total;
   int sega;
 };
 static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
@@ -70,6 +75,8 @@ static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
   L.act3 = o; o += align_up((size_t)batch * 8 * 8 * 256 * L.sega * 2, 1024);
   L.act4 = o; o += align_up((size_t)batch * 16 * 512 * L.sega * 2, 1024);
   L.act0 = o; o += align_up((size_t)batch * kIn0Bytes * L.sega, 1024);  // zero-padded NHWC4 bf16 input
+  L.bnpart = o; o += align_up((size_t)kBnBlocks * 512 * 2 * sizeof(double), 1024);  // train-mode BN partial sums
+  L.bnss = o; o += align_up(2 * 512 * 4, 1024);                                      // batch-stat scale | shift
   L.total = o;
   return L;
 }
@@ -122,12 +129,15 @@ __global__ void pack_small_kernel(const float* __restrict__ w1, const float* __r
 // eval-mode BatchNorm2d folded to y = x * scale + shift
 __global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps, int c,
-                               float* __restrict__ ss) {
+                               float* __restrict__ ss, float* __restrict__ gb, float* __restrict__ ident) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < c) {
     const float s = gamma[i] / sqrtf(var[i] + eps);
     ss[i] = s;
     ss[c + i] = beta[i] - mean[i] * s;
+    gb[i] = gamma[i];
+    gb[c + i] = beta[i];
+    if (ident) { ident[i] = 1.f; ident[512 + i] = 0.f; }
   }
 }
 
@@ -224,6 +234,7 @@ struct ConvParams {
   int c_out;                  // output channels per segment
   int out_sega;               // 1: hi only, 2: hi|lo
   int out_planes;             // 1: parity-plane layout for the next conv, 0: plain [n][oh*OW+ow][C]
+  float slope;                // negative-side slope: 0.2 = LeakyReLU, 1.0 = identity (raw conv output)
   const float* scale;         // [c_out]
   const float* shift;         // [c_out]
   __nv_bfloat16* out;
@@ -391,8 +402,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int j = 0; j < 16; ++j) {
           float a = fmaf(__uint_as_float(v[2 * j]), __ldg(sc + 2 * j), __ldg(sh + 2 * j));
           float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(sc + 2 * j + 1), __ldg(sh + 2 * j + 1));
-          a = a > 0.f ? a : 0.2f * a;
-          b = b > 0.f ? b : 0.2f * b;
+          a = a > 0.f ? a : p.slope * a;
+          b = b > 0.f ? b : p.slope * b;
           const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
           hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
           const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
@@ -542,7 +553,7 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int j = 0; j < 32; ++j) {
           const int px = pb + j, oh = px >> 4, ow = px & 15;
           float a = fmaf(__uint_as_float(v[j]), sc, sh);
-          a = a > 0.f ? a : 0.2f * a;
+          a = a > 0.f ? a : p.slope * a;
           const __nv_bfloat16 ah = __float2bfloat16_rn(a);
           __nv_bfloat16* d = out_img + ((size_t)((oh & 1) * 2 + (ow & 1)) * 64 + (oh >> 1) * 8 + (ow >> 1)) * ct;
           *d = ah;
@@ -785,6 +796,91 @@ conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
+// Train-mode BatchNorm (in-batch strain, "# 상위 10% 제거해서 fake image에 concate.py:244-245": the
+// reference scores with netD in TRAIN mode under no_grad, so BN normalises with batch statistics
+// and updates running_mean / running_var).  The conv kernels write the raw conv
+// output (identity epilogue); these three kernels then reduce per-channel moments over all
+// rows in a fixed order (fp64), fold them into scale/shift (+ running-stat update, momentum,
+// unbiased variance) and apply scale/shift + LeakyReLU in place.  All layouts are channel-innermost,
+// so the kernels are layout agnostic: rows x (C*sega).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ act, int64_t rows, int c,
+                                                       int sega, double* __restrict__ part) {
+  const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * per, r1 = min(r0 + per, rows);
+  const int ct = c * sega;
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    double s = 0.0, q = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      float v = __bfloat162float(act[r * ct + ch]);
+      if (sega == 2) v += __bfloat162float(act[r * ct + c + ch]);
+      s += (double)v;
+      q = fma((double)v, (double)v, q);
+    }
+    part[((size_t)blockIdx.x * c + ch) * 2] = s;
+    part[((size_t)blockIdx.x * c + ch) * 2 + 1] = q;
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ part, int blocks, int64_t rows, int c,
+                                   const float* __restrict__ gb, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ ss) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    s += part[((size_t)b * c + ch) * 2];
+    q += part[((size_t)b * c + ch) * 2 + 1];
+  }
+  const double mean = s / (double)rows;
+  double var = q / (double)rows - mean * mean;   // biased (normalisation)
+  if (var < 0.0) var = 0.0;
+  const float scale = gb[ch] / sqrtf((float)var + eps);
+  ss[ch] = scale;
+  ss[512 + ch] = gb[c + ch] - (float)mean * scale;
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict__ act, int64_t rows, int c, int sega,
+                                                       const float* __restrict__ ss) {
+  const int groups = c >> 3;                                  // 8 channels (16 B) per thread
+  const int64_t total = rows * groups;
+  const int ct = c * sega;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / groups;
+    const int ch = (int)(i - r * groups) << 3;
+    uint4* ph = reinterpret_cast<uint4*>(act + r * ct + ch);
+    uint4* pl = reinterpret_cast<uint4*>(act + r * ct + c + ch);
+    const uint4 h = *ph;
+    uint4 l = make_uint4(0, 0, 0, 0);
+    if (sega == 2) l = *pl;
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+      float b = __uint_as_float(hw[k] & 0xFFFF0000u) + __uint_as_float(lw[k] & 0xFFFF0000u);
+      a = fmaf(a, ss[ch + 2 * k], ss[512 + ch + 2 * k]);
+      b = fmaf(b, ss[ch + 2 * k + 1], ss[512 + ch + 2 * k + 1]);
+      a = a > 0.f ? a : 0.2f * a;
+      b = b > 0.f ? b : 0.2f * b;
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      oh[k] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+      const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+      const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+      ol[k] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    }
+    *ph = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    if (sega == 2) *pl = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // L5 head: logit = <act4[n], w5>, prob = sigmoid(logit), loss = -max(log prob, -100).
 // One warp per sample; fixed summation order (lane-strided partials, xor-shuffle tree).
 // ------------------------------------------------------------------------------------------
@@ -882,9 +978,10 @@ static int encode(CUtensorMap* m, int rank, const void* ptr, const cuuint64_t* d
 
 // One conv layer L (2..4): input activation S_in x S_in x c_in (planes), output (S_in/2)^2 x c_out.
 template <int BLOCK_N>
-static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* ss, __nv_bfloat16* act_out,
-                       int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega, int out_planes, int* err,
-                       cudaStream_t stream) {
+static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
+                       __nv_bfloat16* act_out,
+                       int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega, int out_planes, float slope,
+                       int* err, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N>;
   const int ow = s_in / 2;
   int bh = 128 / ow;
@@ -926,8 +1023,9 @@ static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, co
   p.c_out = c_out;
   p.out_sega = sega;
   p.out_planes = out_planes;
-  p.scale = ss;
-  p.shift = ss + c_out;
+  p.slope = slope;
+  p.scale = scale;
+  p.shift = shift;
   p.out = act_out;
   p.err = err;
   int grid = p.total_tiles < state().sm_count ? p.total_tiles : state().sm_count;
@@ -937,8 +1035,9 @@ static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, co
 }
 
 
-static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* ss, __nv_bfloat16* act2,
-                             int64_t batch, int nseg, int sega, int* err, cudaStream_t stream) {
+static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* scale, const float* shift,
+                             __nv_bfloat16* act2,
+                             int64_t batch, int nseg, int sega, float slope, int* err, cudaStream_t stream) {
   CUtensorMap tx, tw;
   const int ct_in = 64 * sega;
   {
@@ -964,8 +1063,9 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
   p.c_in = 64;
   p.c_out = 128;
   p.out_sega = sega;
-  p.scale = ss;
-  p.shift = ss + 128;
+  p.slope = slope;
+  p.scale = scale;
+  p.shift = shift;
   p.out = act2;
   p.err = err;
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
@@ -1064,15 +1164,18 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
   pack_conv_weight_kernel<<<512, 256, 0, st>>>(w3, reinterpret_cast<__nv_bfloat16*>(pk + L.w3), 256, 128, L.nseg);
   pack_conv_weight_kernel<<<1024, 256, 0, st>>>(w4, reinterpret_cast<__nv_bfloat16*>(pk + L.w4), 512, 256, L.nseg);
   SG_LAUNCH_CHECK();
-  fold_bn_kernel<<<1, 128, 0, st>>>(bn2_gamma, bn2_beta, bn2_mean, bn2_var, bn_eps, 128, reinterpret_cast<float*>(pk + L.ss2));
-  fold_bn_kernel<<<1, 256, 0, st>>>(bn3_gamma, bn3_beta, bn3_mean, bn3_var, bn_eps, 256, reinterpret_cast<float*>(pk + L.ss3));
-  fold_bn_kernel<<<1, 512, 0, st>>>(bn4_gamma, bn4_beta, bn4_mean, bn4_var, bn_eps, 512, reinterpret_cast<float*>(pk + L.ss4));
+  fold_bn_kernel<<<1, 128, 0, st>>>(bn2_gamma, bn2_beta, bn2_mean, bn2_var, bn_eps, 128, reinterpret_cast<float*>(pk + L.ss2), reinterpret_cast<float*>(pk + L.gb2), nullptr);
+  fold_bn_kernel<<<1, 256, 0, st>>>(bn3_gamma, bn3_beta, bn3_mean, bn3_var, bn_eps, 256, reinterpret_cast<float*>(pk + L.ss3), reinterpret_cast<float*>(pk + L.gb3), nullptr);
+  fold_bn_kernel<<<1, 512, 0, st>>>(bn4_gamma, bn4_beta, bn4_mean, bn4_var, bn_eps, 512, reinterpret_cast<float*>(pk + L.ss4), reinterpret_cast<float*>(pk + L.gb4), reinterpret_cast<float*>(pk + L.ident));
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 
-int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
-                     float* logit, float* prob, float* loss, void* stream) {
+// layer 1..5 of the scoring pipeline.  bn_train != 0: layers 2..4 use batch statistics (train-mode BN),
+// updating running_stats[2*(layer-2)] / [2*(layer-2)+1] (may be NULL) with `momentum`.
+static int run_layer_impl(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
+                          float* logit, float* prob, float* loss, int bn_train, float* const* running_stats,
+                          float momentum, float eps, void* stream) {
   using namespace sg::d64;
   SG_READY();
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
@@ -1094,6 +1197,11 @@ int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* wo
   __nv_bfloat16* act4 = reinterpret_cast<__nv_bfloat16*>(ws + W.act4);
   auto wq = [&](size_t off) { return reinterpret_cast<const __nv_bfloat16*>(pk + off); };
   auto fq = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+  const float slope = bn_train ? 1.0f : 0.2f;
+  // eval: folded BN scale | shift; train: identity (ones | zeros at +512) so the raw conv output is stored
+  auto sc = [&](size_t off, int) { return fq(bn_train ? P.ident : off); };
+  auto sh = [&](size_t off, int c) { return bn_train ? fq(P.ident) + 512 : fq(off) + c; };
+  int r = SG_OK;
   switch (layer) {
     case 1:
       SG_REQUIRE(x != nullptr && ((uintptr_t)x & 15) == 0, "x must be a 16-byte aligned device pointer");
@@ -1106,17 +1214,66 @@ int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* wo
                            : launch_conv1<1>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st);
     case 2:
       if (getenv("SG_CONV2_PIXEL_MAJOR"))  // 128x128 pixel-major tiles kept for A/B timing only
-        return launch_conv<128>(act1, wq(P.w2), fq(P.ss2), act2, batch, 32, 64, 128, P.nseg, W.sega, 1, err, st);
-      return launch_conv2_swap(act1, wq(P.w2), fq(P.ss2), act2, batch, P.nseg, W.sega, err, st);
+        r = launch_conv<128>(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, 32, 64, 128, P.nseg, W.sega, 1,
+                             slope, err, st);
+      else
+        r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st);
+      break;
     case 3:
-      return launch_conv<256>(act2, wq(P.w3), fq(P.ss3), act3, batch, 16, 128, 256, P.nseg, W.sega, 1, err, st);
+      r = launch_conv<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
+                           slope, err, st);
+      break;
     case 4:
-      return launch_conv<256>(act3, wq(P.w4), fq(P.ss4), act4, batch, 8, 256, 512, P.nseg, W.sega, 0, err, st);
+      r = launch_conv<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
+                           slope, err, st);
+      break;
     default:
       head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, fq(P.w5), batch, W.sega, logit, prob, loss);
       SG_LAUNCH_CHECK();
       return SG_OK;
   }
+  if (r != SG_OK || !bn_train) return r;
+  // train-mode BN on the raw conv output of layer 2..4
+  const int c = layer == 2 ? 128 : layer == 3 ? 256 : 512;
+  const int64_t rows = batch * (layer == 2 ? 256 : layer == 3 ? 64 : 16);
+  __nv_bfloat16* act = layer == 2 ? act2 : layer == 3 ? act3 : act4;
+  const size_t gb = layer == 2 ? P.gb2 : layer == 3 ? P.gb3 : P.gb4;
+  double* part = reinterpret_cast<double*>(ws + W.bnpart);
+  float* ss = reinterpret_cast<float*>(ws + W.bnss);
+  int blocks = (int)(rows < kBnBlocks ? rows : kBnBlocks);
+  bn_stats_kernel<<<blocks, 256, 0, st>>>(act, rows, c, W.sega, part);
+  SG_LAUNCH_CHECK();
+  float* rm = running_stats ? running_stats[2 * (layer - 2)] : nullptr;
+  float* rv = running_stats ? running_stats[2 * (layer - 2) + 1] : nullptr;
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(part, blocks, rows, c, fq(gb), eps, momentum, rm, rv, ss);
+  SG_LAUNCH_CHECK();
+  int64_t ab = sg::ceil_div(rows * (c / 8), 256);
+  if (ab > (int64_t)sg::state().sm_count * 16) ab = (int64_t)sg::state().sm_count * 16;
+  bn_apply_kernel<<<(unsigned)ab, 256, 0, st>>>(act, rows, c, W.sega, ss);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
+                     float* logit, float* prob, float* loss, void* stream) {
+  return run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 0, nullptr, 0.f, 0.f, stream);
+}
+
+int sg_d64_score_train(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
+                       float* bn2_running_mean, float* bn2_running_var, float* bn3_running_mean,
+                       float* bn3_running_var, float* bn4_running_mean, float* bn4_running_var, float momentum,
+                       float bn_eps, float* logit, float* prob, float* loss, void* stream) {
+  SG_READY();
+  SG_REQUIRE(x && packed && workspace, "null pointer");
+  SG_REQUIRE(batch >= 1, "train-mode BatchNorm needs at least one sample");
+  SG_CUDA(cudaMemsetAsync(workspace, 0, 4, sg::as_stream(stream)));
+  float* rs[6] = {bn2_running_mean, bn2_running_var, bn3_running_mean, bn3_running_var, bn4_running_mean, bn4_running_var};
+  for (int layer = 1; layer <= 5; ++layer) {
+    const int r = run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 1, rs, momentum, bn_eps,
+                                 stream);
+    if (r != SG_OK) return r;
+  }
+  return SG_OK;
 }
 
 int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, float* logit,

@@ -174,3 +174,35 @@ def test_gmm_divide_golden(sb, golden):
     np.random.seed(1234)
     clean, _ = sb.divide_dataset_ensemble(lo.copy(), torch.utils.data.TensorDataset(torch.zeros(5000, 1)))
     assert np.array_equal(np.asarray(clean.indices), golden["g3_clean_idx"])
+
+
+@pytest.mark.parametrize("B", [64, 128])
+@pytest.mark.parametrize("on_cuda", [False, True])
+def test_strain_batch_train_mode_bn(sb, golden, B, on_cuda):
+    """the reference's in-batch block with netD in TRAIN mode: batch-stat BN + running-stat side effect"""
+    x = torch.from_numpy(O.synth_images(0, B))
+    d = O.make_discriminator(O.SEED)          # train mode, as every script that never calls .eval()
+    if on_cuda:
+        d = d.cuda()
+    fr, ff, mask, thr = sb.strain_batch(d, x.cuda())
+    scores_w = torch.from_numpy(golden[f"g8_{B}_scores"])
+    thr_w = float(golden[f"g8_{B}_threshold"])
+    near = (scores_w - thr_w).abs() <= 1e-3 * abs(thr_w)
+    assert not ((mask.cpu().numpy() != golden[f"g8_{B}_mask"]) & ~near.numpy()).any()
+    assert abs(thr.item() - thr_w) <= 1e-3 * abs(thr_w)
+    assert abs(ff.shape[0] - int(golden[f"g8_{B}_nfake"])) <= 1 and fr.shape[0] + ff.shape[0] == B
+    assert d.training
+    for key, t in ((f"g8_{B}_bn1_mean", d.main[3].running_mean), (f"g8_{B}_bn1_var", d.main[3].running_var),
+                   (f"g8_{B}_bn3_mean", d.main[9].running_mean), (f"g8_{B}_bn3_var", d.main[9].running_var)):
+        w = golden[key]
+        assert np.allclose(t.cpu().numpy(), w, rtol=1e-3, atol=1e-5), (key, np.abs(t.cpu().numpy() - w).max())
+    assert int(d.main[3].num_batches_tracked) == 1 and int(d.main[9].num_batches_tracked) == 1
+    # a following eval-mode score sees the UPDATED running statistics (packed fold is refreshed)
+    d.eval()
+    got = sb.get_scorer(d, "cuda", "fp32", max_batch=max(B, 512))
+    p = torch.empty(B, device="cuda")
+    got.repack(d)
+    got.score_into(x.cuda(), None, p, None)
+    with torch.no_grad():
+        want = d.cpu()(x).reshape(-1)
+    assert (p.cpu() - want).abs().max().item() <= 1e-3
