@@ -99,6 +99,16 @@ int sg_d64_check(const void* workspace, void* stream);
 int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, int layer, float* out,
                            void* stream);
 
+/* ---- auto-encoder reconstruction-error scoring -------------------------------------------
+ * replaces AutoEncoder.forward "#autoencoder.py:269-291" and the per-sample
+ * F.mse_loss(out, img, 'none').view(B,-1).mean(1) of ":315-316".
+ * h_params: HOST array of 12 DEVICE pointers {w,b} x {enc.0, enc.2, enc.4, dec.0, dec.2, dec.4} in the
+ * PyTorch layouts (Conv2d [out,in,k,k], ConvTranspose2d [in,out,k,k]).  x fp32 NCHW [batch,3,64,64];
+ * err_out[batch]; recon_out (optional, [batch,3,64,64]) receives the reconstruction. */
+size_t sg_ae_workspace_bytes(int64_t max_batch);
+int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
+                float* recon_out, void* stream);
+
 /* ---- selection: order statistics, thresholds ------------------------------------------
  * replaces np.percentile "#strainer gan.py:381", "# 종합 loss.py:288-292" and torch.quantile
  * "# 상위 10% 제거해서 fake image에 concate.py:246", "# z_score + DBSCAN.py:323".

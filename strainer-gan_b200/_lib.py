@@ -34,6 +34,8 @@ _SIGS = {
     "sg_d64_run_layer": (c_int, [P, c_int64, P, P, c_int, c_int, P, P, P, P]),
     "sg_d64_check": (c_int, [P, P]),
     "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),
+    "sg_ae_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_ae_score": (c_int, [P, c_int64, P, P, P, P, P]),
     "sg_select_begin": (c_int, [P, c_int64, P]),
     "sg_select_hist": (c_int, [P, c_int64, P, c_int, P]),
     "sg_select_step": (c_int, [P, c_int, P]),

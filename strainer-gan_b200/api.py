@@ -653,6 +653,61 @@ def compute_z_scores(dataset, feature_extractor):
     return zscore_max(_features_of(dataset, feature_extractor, device), ddof=0, eps_add=1e-7).cpu().numpy()
 
 
+# ---- auto-encoder straining ---------------------------------------------------------------------
+def _ae_params(autoencoder: nn.Module, device):
+    mods = [m for m in autoencoder.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))]
+    want = [(nn.Conv2d, (16, 3, 3, 3)), (nn.Conv2d, (32, 16, 3, 3)), (nn.Conv2d, (64, 32, 7, 7)),
+            (nn.ConvTranspose2d, (64, 32, 7, 7)), (nn.ConvTranspose2d, (32, 16, 3, 3)), (nn.ConvTranspose2d, (16, 3, 3, 3))]
+    ok = len(mods) == 6 and all(type(m) is t and tuple(m.weight.shape) == sh and m.bias is not None
+                                for m, (t, sh) in zip(mods, want))
+    if not ok:
+        raise NotImplementedError("strainer_b200 scores the reference AutoEncoder (\"#autoencoder.py:269-291\") only")
+    ps = []
+    for m in mods:
+        ps += [_f32c(m.weight.detach(), device), _f32c(m.bias.detach(), device)]
+    return ps
+
+
+def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: int = 2048) -> torch.Tensor:
+    """Per-sample reconstruction MSE of the reference AutoEncoder on the GPU; fp32 device tensor [N]."""
+    device = _dev(device)
+    lib = _lib_for(device)
+    params = _ae_params(autoencoder, device)
+    arr = (L.P * 12)(*[t.data_ptr() for t in params])
+    n = images.shape[0]
+    err = torch.empty(n, dtype=torch.float32, device=device)
+    ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(min(chunk, max(n, 1))))
+    for i in range(0, n, chunk):
+        x = _f32c(images[i:i + chunk], device)
+        L.check(lib.sg_ae_score(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()), "sg_ae_score")
+    return err
+
+
+def mean_plus_k_std(values: torch.Tensor, k: float) -> torch.Tensor:
+    """1-element fp32 device tensor mean + k * std (unbiased), "#autoencoder.py:320"; fixed-order fp64 sums."""
+    device = values.device
+    lib = _lib_for(device)
+    n = values.numel()
+    chunks = (n + L.SG_MOMENT_CHUNK - 1) // L.SG_MOMENT_CHUNK
+    part = torch.empty(2 * max(chunks, 1), dtype=torch.float64, device=device)
+    thr = torch.empty(1, dtype=torch.float32, device=device)
+    L.check(lib.sg_chunk_moments(_p(values), n, _p(part), _stream()), "sg_chunk_moments")
+    L.check(lib.sg_moments_finish(_p(part), chunks, n, float(k), L.P(0), _p(thr), _stream()), "sg_moments_finish")
+    return thr
+
+
+def detect_outliers_autoencoder(autoencoder, dataset, device, threshold=2.0):
+    """``detect_outliers_autoencoder`` ("#autoencoder.py:307-322"): per-sample reconstruction MSE,
+    inlier = error < mean + threshold * std (unbiased).  Returns a CPU torch.BoolTensor [N] like the
+    reference (whose errors are ``.cpu()``'d)."""
+    device = _dev(device)
+    autoencoder.eval()
+    err = ae_errors(autoencoder, _dataset_images(dataset), device)
+    thr = mean_plus_k_std(err, threshold)
+    _, _, mask = compact_indices(err, thr, L.SG_LT, 0, want_mask=True)
+    return mask.bool().cpu()
+
+
 # ---- in-batch strain + concat --------------------------------------------------------------------
 def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1, fake: torch.Tensor | None = None):
     """Selection half of the in-batch block ("# 상위 10% 제거해서 fake image에 concate.py:246-249"):

@@ -9,6 +9,7 @@
 #include "../../include/strainer_b200.h"
 
 extern "C" int sg_d64_init_attributes();  // internal: raises the conv kernels' dynamic smem limit
+extern "C" int sg_ae_init_attributes();
 
 namespace sg {
 

@@ -98,3 +98,21 @@ def test_moments_threshold(sb):
             L.check(lib.sg_chunk_moments(L.P(d.data_ptr()), half, L.P(p2.data_ptr()), st))
             L.check(lib.sg_chunk_moments(L.P(d[half:].data_ptr()), n - half, L.P(p2[2 * (chunks // 2):].data_ptr()), st))
             assert torch.equal(part, p2)
+
+
+def test_autoencoder_straining_golden(sb, golden):
+    """AE reconstruction straining vs the reference's own detect_outliers_autoencoder outputs"""
+    x = torch.from_numpy(O.synth_images(0, 160))
+    torch.manual_seed(O.SEED)
+    ae = O.AutoEncoder()
+    err = sb.ae_errors(ae, x, "cuda").cpu().numpy()
+    want = golden["g6_errors"]
+    assert (np.abs(err - want) / np.maximum(want, 1e-6)).max() <= 1e-3, np.abs(err - want).max()   # fp32: 1e-3 rel (measured ~1e-6)
+    ds = torch.utils.data.TensorDataset(x, torch.zeros(160, dtype=torch.long))
+    for thr_k, key in ((2.0, "g6_inlier"), (0.5, "g6_inlier_t05")):
+        got = sb.detect_outliers_autoencoder(ae, ds, "cuda", thr_k) if thr_k != 2.0 else sb.detect_outliers_autoencoder(ae, ds, "cuda")
+        assert isinstance(got, torch.Tensor) and got.dtype == torch.bool and got.device.type == "cpu"
+        te = torch.from_numpy(want)
+        t = (te.mean() + thr_k * te.std()).item()
+        near = np.abs(want - t) <= 1e-3 * abs(t)
+        assert not ((got.numpy() != golden[key]) & ~near).any()
