@@ -109,6 +109,13 @@ size_t sg_ae_workspace_bytes(int64_t max_batch);
 int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
                 float* recon_out, void* stream);
 
+/* ---- MLP discriminator scoring (28x28 path) --------------------------------------------------
+ * replaces Discriminator.forward of "Untitled-2.py:79-94" / "# 1,2,8.py:110-128" (eval mode) + BCE vs 1.
+ * h_params: HOST array of 8 DEVICE pointers {weight [out,in], bias} x 4 Linear layers.  x fp32 [batch,784]. */
+size_t sg_mlp_workspace_bytes(int64_t max_batch);
+int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* logit,
+                 float* prob, float* loss, void* stream);
+
 /* ---- selection: order statistics, thresholds ------------------------------------------
  * replaces np.percentile "#strainer gan.py:381", "# 종합 loss.py:288-292" and torch.quantile
  * "# 상위 10% 제거해서 fake image에 concate.py:246", "# z_score + DBSCAN.py:323".
@@ -180,6 +187,18 @@ int sg_minmax(const float* v, int64_t n, float* minmax, void* stream);
 /* np.histogram's uniform-bin fast path: edges[bins+1] fp32 (as np.linspace made them),
  * counts[bins] int64 accumulated (caller zeroes). */
 int sg_hist_uniform(const float* v, int64_t n, const float* edges, int bins, long long* counts, void* stream);
+
+/* ---- device sort + 1-D DBSCAN clean ratio --------------------------------------------------
+ * BASELINE.json north_star: "1-D DBSCAN thresholds on a device sort".  The reference's
+ * estimate_ratio_dbscan ("# z_score + DBSCAN.py:272-301") consumes only the fraction of
+ * non-noise points; this is sklearn.cluster.DBSCAN(eps, min_samples) applied to an (N,1) array:
+ * counts_out[0] = number of non-noise points, noise_out (optional) = 0/1 per point in input order. */
+size_t sg_sort_workspace_bytes(int64_t n);
+/* ascending stable LSD radix sort (NaN last, -0 == +0); order_out = source index of each sorted element */
+int sg_sort_f32(const float* v, int64_t n, float* sorted_out, int32_t* order_out, void* workspace, void* stream);
+size_t sg_dbscan1d_workspace_bytes(int64_t n);
+int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t* counts_out, uint8_t* noise_out,
+                void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

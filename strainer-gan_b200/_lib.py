@@ -36,6 +36,8 @@ _SIGS = {
     "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),
     "sg_ae_workspace_bytes": (c_size_t, [c_int64]),
     "sg_ae_score": (c_int, [P, c_int64, P, P, P, P, P]),
+    "sg_mlp_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_mlp_score": (c_int, [P, c_int64, P, P, P, P, P, P]),
     "sg_select_begin": (c_int, [P, c_int64, P]),
     "sg_select_hist": (c_int, [P, c_int64, P, c_int, P]),
     "sg_select_step": (c_int, [P, c_int, P]),
@@ -48,6 +50,10 @@ _SIGS = {
     "sg_compact_indices": (c_int, [P, c_int64, P, c_int, c_int64, P, P, P, P, P]),
     "sg_compact_rows": (c_int, [P, c_int64, c_int64, P, P, P, P, P, P]),
     "sg_gather_rows": (c_int, [P, c_int64, P, c_int64, P, P, P]),
+    "sg_sort_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_sort_f32": (c_int, [P, c_int64, P, P, P, P]),
+    "sg_dbscan1d_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_dbscan1d": (c_int, [P, c_int64, c_double, c_int, P, P, P, P]),
     "sg_chunk_moments": (c_int, [P, c_int64, P, P]),
     "sg_moments_finish": (c_int, [P, c_int64, c_int64, c_float, P, P, P]),
     "sg_col_moments_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -416,6 +416,42 @@ class D64Scorer:
         return outs
 
 
+class MLPScorer:
+    """Scores the reference's 28x28 MLP Discriminator ("Untitled-2.py:79-94", "# 1,2,8.py:110-128")."""
+
+    def __init__(self, discriminator: nn.Module, device=None, max_batch: int = 4096):
+        self.device = _dev(device)
+        self.lib = _lib_for(self.device)
+        self.max_batch = int(max_batch)
+        self.ws = torch.empty(self.lib.sg_mlp_workspace_bytes(self.max_batch), dtype=torch.uint8, device=self.device)
+        self.refresh(discriminator)
+
+    @staticmethod
+    def linears(discriminator):
+        lins = [m for m in discriminator.modules() if isinstance(m, nn.Linear)]
+        shapes = [tuple(m.weight.shape) for m in lins]
+        if shapes != [(1024, 784), (512, 1024), (256, 512), (1, 256)] or any(m.bias is None for m in lins):
+            raise NotImplementedError(f"strainer_b200 scores the reference 784-1024-512-256-1 MLP only; got {shapes}")
+        return lins
+
+    def refresh(self, discriminator):
+        self.params = []
+        for m in self.linears(discriminator):
+            self.params += [_f32c(m.weight.detach(), self.device), _f32c(m.bias.detach(), self.device)]
+        self.arr = (L.P * 8)(*[t.data_ptr() for t in self.params])
+
+    def score_into(self, x, logit=None, prob=None, loss=None):
+        b = x.shape[0]
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        L.check(self.lib.sg_mlp_score(_p(x), b, self.arr, _p(self.ws), _p(logit), _p(prob), _p(loss), _stream()),
+                "sg_mlp_score")
+
+
+def _is_mlp(netD) -> bool:
+    return any(isinstance(m, nn.Linear) for m in netD.modules()) and not any(isinstance(m, nn.Conv2d) for m in netD.modules())
+
+
 _COPY_STREAMS: dict = {}
 
 
@@ -653,6 +689,54 @@ def compute_z_scores(dataset, feature_extractor):
     return zscore_max(_features_of(dataset, feature_extractor, device), ddof=0, eps_add=1e-7).cpu().numpy()
 
 
+# ---- device sort / 1-D DBSCAN ----------------------------------------------------------------
+def sort_values(values, return_order: bool = False):
+    """Ascending stable device radix sort of a 1-D fp32 vector (NaN last)."""
+    device = _dev()
+    lib = _lib_for(device)
+    v = _f32c(values, device).reshape(-1)
+    n = v.numel()
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    order = torch.empty(n, dtype=torch.int32, device=device) if return_order else None
+    ws = _Scratch.get(device, "sort", lib.sg_sort_workspace_bytes(n))
+    L.check(lib.sg_sort_f32(_p(v), n, _p(out), _p(order), _p(ws), _stream()), "sg_sort_f32")
+    return (out, order) if return_order else out
+
+
+def dbscan1d_clean_ratio(values, eps, min_samples=3, return_noise: bool = False):
+    """Fraction of non-noise points of ``sklearn.cluster.DBSCAN(eps, min_samples)`` applied to a 1-D
+    value vector (the north_star's 1-D variant of ``estimate_ratio_dbscan``,
+    "# z_score + DBSCAN.py:291-299"); exact: sort + neighbour counts, no O(N^2) neighbour search."""
+    device = _dev()
+    lib = _lib_for(device)
+    v = _f32c(values, device).reshape(-1)
+    n = v.numel()
+    counts = torch.zeros(1, dtype=torch.int64, device=device)
+    noise = torch.empty(n, dtype=torch.uint8, device=device) if return_noise else None
+    ws = _Scratch.get(device, "dbscan", lib.sg_dbscan1d_workspace_bytes(n))
+    L.check(lib.sg_dbscan1d(_p(v), n, float(eps), int(min_samples), _p(counts), _p(noise), _p(ws), _stream()), "sg_dbscan1d")
+    ratio = counts.item() / n
+    return (ratio, noise.bool()) if return_noise else ratio
+
+
+def estimate_ratio_dbscan(dataset, eps=20, min_samples=3, feature_extractor=None):
+    """``estimate_ratio_dbscan`` ("# z_score + DBSCAN.py:272-301").  The reference clusters the
+    standardised 512-d ResNet18 features with scikit-learn; that neighbour search
+    stays scikit-learn on the host.  When the features are one-dimensional (a score / loss /
+    max-z vector) the device sort path ``dbscan1d_clean_ratio`` is used instead."""
+    device = _dev()
+    feats = _features_of(dataset, feature_extractor, device)
+    if feats.dim() == 1 or feats.shape[1] == 1:
+        f = feats.reshape(-1)
+        mean = f.double().mean()
+        std = f.double().std(unbiased=False)
+        return dbscan1d_clean_ratio(((f.double() - mean) / std).float(), eps, min_samples)
+    from sklearn.cluster import DBSCAN
+    from sklearn.preprocessing import StandardScaler
+    labels = DBSCAN(eps=eps, min_samples=min_samples).fit_predict(StandardScaler().fit_transform(feats.cpu().numpy()))
+    return np.sum(labels != -1) / len(labels)
+
+
 # ---- auto-encoder straining ---------------------------------------------------------------------
 def _ae_params(autoencoder: nn.Module, device):
     mods = [m for m in autoencoder.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))]
@@ -732,9 +816,17 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
     dataset-scale strain is in, quirk 1) the folded running statistics are used.
     Returns (filtered_real, filtered_fake, mask, threshold)."""
     device = _dev(real.device)
-    sc = get_scorer(netD, device, conv_mode, max_batch=max(real.shape[0], 512))
     b = real.shape[0]
     prob = torch.empty(b, dtype=torch.float32, device=device)
+    if _is_mlp(netD):
+        # 28x28 path: MLP discriminator on flattened images ("# 1,2,8.py:110-128", "Untitled-2.py:79-94")
+        if netD.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in netD.modules()):
+            raise NotImplementedError("train-mode Dropout draws from torch's RNG stream and cannot be mirrored; "
+                                      "score with netD.eval() (Dropout = identity)")
+        sc = MLPScorer(netD, device, max_batch=max(b, 512))
+        sc.score_into(_f32c(real.reshape(b, -1), device), None, prob, None)
+        return strain_scores(real, prob, q)
+    sc = get_scorer(netD, device, conv_mode, max_batch=max(real.shape[0], 512))
     if netD.training:
         sc.score_train_into(netD, real.contiguous(), None, prob, None)
     else:

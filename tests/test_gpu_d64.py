@@ -206,3 +206,28 @@ def test_strain_batch_train_mode_bn(sb, golden, B, on_cuda):
     with torch.no_grad():
         want = d.cpu()(x).reshape(-1)
     assert (p.cpu() - want).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_mlp_discriminator_config1(sb, dropout):
+    """config 1 (28x28 grayscale, batch 64, top-10 % in-batch removal) with the reference's MLP D"""
+    torch.manual_seed(3)
+    d = O.MLPDiscriminator(dropout=dropout).eval()
+    rng = np.random.default_rng(31)
+    x = torch.from_numpy(np.tanh(rng.standard_normal((64, 784))).astype(np.float32))
+    with torch.no_grad():
+        want = d(x).reshape(-1)
+    sc = sb.MLPScorer(d, "cuda", max_batch=64)
+    logit = torch.empty(64, device="cuda"); prob = torch.empty(64, device="cuda"); loss = torch.empty(64, device="cuda")
+    sc.score_into(x.cuda(), logit, prob, loss)
+    assert (prob.cpu() - want).abs().max().item() <= 1e-5          # fp32 GEMM chain: 1e-5 absolute on the scores
+    wl = O.bce_vs_ones(want).numpy()
+    assert (np.abs(loss.cpu().numpy() - wl) / np.maximum(wl, 1e-6)).max() <= 1e-3
+    fr_w, ff_w, mask_w, thr_w = O.strain_scores(x, want)
+    fr, ff, mask, thr = sb.strain_batch(d, x.cuda())
+    near = (want - thr_w).abs() <= 1e-4 * thr_w.abs()
+    assert not ((mask.cpu() != mask_w) & ~near).any()
+    assert ff.shape[0] == 7 and fr.shape[0] == 57                    # SURVEY §3.3: 7 of 64 removed
+    if dropout:
+        with pytest.raises(NotImplementedError):
+            sb.strain_batch(d.train(), x.cuda())

@@ -172,3 +172,38 @@ def test_sharded_select_emulated(sb):
     s = np.sort(v)
     for o in outs:
         assert np.array_equal(o, s[k:k + 2])
+
+
+def test_device_sort(sb):
+    rng = np.random.default_rng(41)
+    for n in (1, 2, 33, 2048, 2049, 100_003, 1 << 20):
+        v = adversarial(n, rng) if n > 2 else rng.standard_normal(n).astype(np.float32)
+        if n > 100:
+            v[11] = np.nan
+        out, order = sb.sort_values(v, return_order=True)
+        want_order = np.argsort(v, kind="stable")
+        got = out.cpu().numpy()
+        assert np.array_equal(got, np.sort(v), equal_nan=True)
+        # stable: equal keys (incl. -0.0 / +0.0, which share a key) keep their input order
+        o = order.cpu().numpy()
+        assert np.array_equal(np.sort(o), np.arange(n))
+        assert np.array_equal(v[o], v[want_order], equal_nan=True)
+        same = v[o][1:] == v[o][:-1]
+        assert np.all(o[1:][same] > o[:-1][same])
+
+
+def test_dbscan1d_vs_sklearn(sb):
+    rng = np.random.default_rng(42)
+    for n, eps, ms in ((50, 0.05, 3), (2000, 0.01, 3), (2000, 0.002, 5), (300, 0.5, 3), (5, 0.1, 3), (20000, 0.0005, 4)):
+        v = O.synth_losses(n, seed=int(rng.integers(1 << 30)))
+        ratio, noise = sb.dbscan1d_clean_ratio(v, eps, ms, return_noise=True)
+        want = O.dbscan1d_noise_sklearn(v, eps, ms)
+        assert np.array_equal(noise.cpu().numpy(), want), (n, eps, ms)
+        assert ratio == np.sum(~want) / n
+    v = np.round(O.synth_losses(3000, seed=3), 2)      # heavy ties, distances exactly == eps
+    ratio, noise = sb.dbscan1d_clean_ratio(v, 0.01, 3, return_noise=True)
+    assert np.array_equal(noise.cpu().numpy(), O.dbscan1d_noise_sklearn(v, 0.01, 3))
+    # z-score + 1-D DBSCAN straining (config 3): clean_ratio -> torch.quantile(max_z, ratio), <=
+    mz = O.zscore_max_torch(torch.from_numpy(O.synth_features(4096)))
+    r = sb.dbscan1d_clean_ratio(mz, 0.05, 3)
+    assert r == O.dbscan1d_clean_ratio(mz.numpy(), 0.05, 3)
