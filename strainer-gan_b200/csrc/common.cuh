@@ -10,6 +10,7 @@
 
 extern "C" int sg_d64_init_attributes();  // internal: raises the conv kernels' dynamic smem limit
 extern "C" int sg_ae_init_attributes();
+extern "C" int sg_select_init_attributes();
 
 namespace sg {
 
@@ -101,6 +102,38 @@ __device__ __forceinline__ int4 ldg_stream_i4(const int4* p) {
 __device__ __forceinline__ void stg_stream_i4(int4* p, const int4& v) {
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Streams a fp32 vector through `f(value, index)` with 128-bit loads, U independent loads in flight per
+// thread and consecutive threads on consecutive 16-B chunks (HBM-bound kernels: enough bytes in flight
+// to cover the DRAM latency).  Visit ORDER is unspecified: only for order-independent reductions.
+template <int U, typename F>
+__device__ __forceinline__ void stream_f32(const float* __restrict__ v, int64_t n, F&& f) {
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+    const int64_t n4 = n >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    int64_t i = gtid;
+    for (; i + (U - 1) * gsz < n4; i += U * gsz) {
+      float4 q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) q[u] = ldg_stream4(v4 + i + u * gsz);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t e = (i + u * gsz) << 2;
+        f(q[u].x, e); f(q[u].y, e + 1); f(q[u].z, e + 2); f(q[u].w, e + 3);
+      }
+    }
+    for (; i < n4; i += gsz) {
+      const float4 q = ldg_stream4(v4 + i);
+      const int64_t e = i << 2;
+      f(q.x, e); f(q.y, e + 1); f(q.z, e + 2); f(q.w, e + 3);
+    }
+    for (int64_t e = (n4 << 2) + gtid; e < n; e += gsz) f(v[e], e);
+  } else {
+    for (int64_t e = gtid; e < n; e += gsz) f(v[e], e);
+  }
 }
 
 template <typename T>

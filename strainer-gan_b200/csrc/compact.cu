@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* 
   __shared__ int s_tile;
   __shared__ int s_warp[kThreads / 32];
   __shared__ unsigned long long s_excl;
+  __shared__ int64_t s_idx[kTile];  // kept indices of the tile in order -> coalesced 8-byte stores
   unsigned long long* status = reinterpret_cast<unsigned long long*>(ws + 1);
   const float thr = *thr_p;
   while (true) {
@@ -129,12 +130,14 @@ __global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* 
     const int c = __popc(flags);
     int total;
     const int toff = block_excl_scan(c, s_warp, &total);
-    const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);
-    int64_t* dst = idx_out + excl + toff;
-    int w = 0;
+    {
+      int w = toff;
 #pragma unroll
-    for (int j = 0; j < kItems; ++j)
-      if (flags & (1u << j)) dst[w++] = index_base + base + j;
+      for (int j = 0; j < kItems; ++j)
+        if (flags & (1u << j)) s_idx[w++] = index_base + base + j;
+    }
+    const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);  // ends with a barrier
+    for (int i = threadIdx.x; i < total; i += kThreads) idx_out[excl + i] = s_idx[i];
     if (mask_out) {
       if (base + kItems <= n && (reinterpret_cast<uintptr_t>(mask_out) & 15) == 0) {
         uint32_t m[4];

@@ -8,19 +8,32 @@
 namespace sg {
 namespace mom {
 
+// One CTA per chunk of SG_MOMENT_CHUNK values.  Thread t accumulates elements {1024*q + 4*t + j}
+// (q = 0..3, j = 0..3) in that order -- 128-bit coalesced loads -- then a fixed shared-memory tree.
 __global__ void __launch_bounds__(256) chunk_moments_kernel(const float* __restrict__ v, int64_t n,
                                                             double* __restrict__ partial) {
   __shared__ double s_s[256], s_q[256];
-  const int64_t base = (int64_t)blockIdx.x * SG_MOMENT_CHUNK + threadIdx.x * 16;
+  const int64_t base = (int64_t)blockIdx.x * SG_MOMENT_CHUNK;
   double s = 0.0, q = 0.0;
+  const bool fast = (base + SG_MOMENT_CHUNK <= n) && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+  if (fast) {
+    float4 x[4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int64_t i = base + j;
-    if (i < n) {
-      const double x = (double)v[i];
-      s += x;
-      q = fma(x, x, q);
+    for (int k = 0; k < 4; ++k) x[k] = ldg_stream4(reinterpret_cast<const float4*>(v + base) + k * 256 + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const double d = (double)e[j]; s += d; q = fma(d, d, q); }
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t i = base + k * 1024 + threadIdx.x * 4 + j;
+        if (i < n) { const double d = (double)v[i]; s += d; q = fma(d, d, q); }
+      }
   }
   s_s[threadIdx.x] = s;
   s_q[threadIdx.x] = q;
@@ -60,6 +73,36 @@ __global__ void __launch_bounds__(256) col_partial_kernel(const float* __restric
                                                           double* __restrict__ part) {
   const int64_t r0 = (int64_t)blockIdx.x * kRowsPerBlock;
   const int64_t r1 = min(r0 + kRowsPerBlock, n);
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // thread owns 4 adjacent columns (one float4 per row), 4 rows in flight; rows in index order
+    for (int c = threadIdx.x * 4; c < d; c += 1024) {
+      double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+      int64_t r = r0;
+      for (; r + 4 <= r1; r += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = ldg_stream4(reinterpret_cast<const float4*>(x + (r + u) * d + c));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float e[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const double v = (double)e[j]; s[j] += v; q[j] = fma(v, v, q[j]); }
+        }
+      }
+      for (; r < r1; ++r) {
+        const float4 a = ldg_stream4(reinterpret_cast<const float4*>(x + r * d + c));
+        const float e[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double v = (double)e[j]; s[j] += v; q[j] = fma(v, v, q[j]); }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        part[((int64_t)blockIdx.x * d + c + j) * 2] = s[j];
+        part[((int64_t)blockIdx.x * d + c + j) * 2 + 1] = q[j];
+      }
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < d; c += 256) {
     double s = 0.0, q = 0.0;
     for (int64_t r = r0; r < r1; ++r) {
@@ -99,7 +142,23 @@ __global__ void __launch_bounds__(256) row_max_absz_kernel(const float* __restri
   float best = 0.f;
   bool has_nan = false;
   const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  if (vec) {
+  if (vec && d == 512) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = ldg_stream4(reinterpret_cast<const float4*>(xr + lane * 4 + u * 128));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = lane * 4 + u * 128;
+      const float4 m = *reinterpret_cast<const float4*>(mean + c);
+      const float4 s = *reinterpret_cast<const float4*>(denom + c);
+      const float z0 = fabsf(__fdiv_rn(__fsub_rn(a[u].x, m.x), s.x));
+      const float z1 = fabsf(__fdiv_rn(__fsub_rn(a[u].y, m.y), s.y));
+      const float z2 = fabsf(__fdiv_rn(__fsub_rn(a[u].z, m.z), s.z));
+      const float z3 = fabsf(__fdiv_rn(__fsub_rn(a[u].w, m.w), s.w));
+      has_nan |= (z0 != z0) | (z1 != z1) | (z2 != z2) | (z3 != z3);
+      best = fmaxf(best, fmaxf(fmaxf(z0, z1), fmaxf(z2, z3)));
+    }
+  } else if (vec) {
     for (int c = lane * 4; c < d; c += 128) {
       const float4 a = ldg_stream4(reinterpret_cast<const float4*>(xr + c));
       const float4 m = *reinterpret_cast<const float4*>(mean + c);
@@ -130,14 +189,12 @@ __global__ void __launch_bounds__(256) row_max_absz_kernel(const float* __restri
 __global__ void minmax_init_kernel(uint32_t* kk) { kk[0] = 0xFFFFFFFFu; kk[1] = 0u; kk[2] = 0u; }
 __global__ void __launch_bounds__(512) minmax_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ kk) {
   uint32_t lo = 0xFFFFFFFFu, hi = 0u, nan = 0u;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float f = v[i];
-    if (f != f) { nan = 1u; continue; }
+  stream_f32<4>(v, n, [&](float f, int64_t) {
+    if (f != f) { nan = 1u; return; }
     const uint32_t key = __float_as_uint(f) & 0x80000000u ? ~__float_as_uint(f) : (__float_as_uint(f) | 0x80000000u);
     lo = min(lo, key);
     hi = max(hi, key);
-  }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -158,30 +215,34 @@ __global__ void minmax_finish_kernel(const uint32_t* kk, float* out) {
 }
 
 // numpy's uniform-bin fast path (lib/_histograms_impl.py): fp32 index arithmetic + edge correction.
+// `copies` interleaved private histograms (bin*copies + lane%copies) remove the same-address atomic
+// serialisation a skewed distribution causes.
 __global__ void __launch_bounds__(512) hist_uniform_kernel(const float* __restrict__ v, int64_t n,
-                                                           const float* __restrict__ edges, int bins,
+                                                           const float* __restrict__ edges, int bins, int copies,
                                                            unsigned long long* __restrict__ counts) {
-  extern __shared__ uint32_t s_cnt[];
-  float* s_edges = reinterpret_cast<float*>(s_cnt + bins);
-  for (int i = threadIdx.x; i < bins; i += blockDim.x) s_cnt[i] = 0u;
+  extern __shared__ uint32_t s_cnt[];  // [bins][copies] then edges[bins + 1]
+  float* s_edges = reinterpret_cast<float*>(s_cnt + bins * copies);
+  for (int i = threadIdx.x; i < bins * copies; i += blockDim.x) s_cnt[i] = 0u;
   for (int i = threadIdx.x; i <= bins; i += blockDim.x) s_edges[i] = edges[i];
   __syncthreads();
   const float first = s_edges[0], last = s_edges[bins];
   const float denom = __fsub_rn(last, first);
   const float fb = (float)bins;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float x = v[i];
-    if (!(x >= first && x <= last)) continue;
+  const int copy = threadIdx.x & (copies - 1);
+  stream_f32<4>(v, n, [&](float x, int64_t) {
+    if (!(x >= first && x <= last)) return;
     int idx = (int)__fmul_rn(__fdiv_rn(__fsub_rn(x, first), denom), fb);
     if (idx == bins) --idx;
     if (x < s_edges[idx]) --idx;
     else if (x >= s_edges[idx + 1] && idx != bins - 1) ++idx;
-    atomicAdd(&s_cnt[idx], 1u);
-  }
+    atomicAdd(&s_cnt[idx * copies + copy], 1u);
+  });
   __syncthreads();
-  for (int i = threadIdx.x; i < bins; i += blockDim.x)
-    if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+    unsigned long long c = 0;
+    for (int k = 0; k < copies; ++k) c += s_cnt[i * copies + k];
+    if (c) atomicAdd(&counts[i], c);
+  }
 }
 
 }  // namespace mom
@@ -267,9 +328,11 @@ int sg_hist_uniform(const float* v, int64_t n, const float* edges, int bins, lon
   int64_t b = sg::ceil_div(n, 512 * 8);
   const int64_t cap = (int64_t)sg::state().sm_count * 4;
   if (b > cap) b = cap;
-  const size_t smem = (size_t)bins * 4 + (size_t)(bins + 1) * 4;
+  int copies = 32;
+  while (copies > 1 && (size_t)bins * copies * 4 > 40 * 1024) copies >>= 1;
+  const size_t smem = (size_t)bins * copies * 4 + (size_t)(bins + 1) * 4;
   sg::mom::hist_uniform_kernel<<<(unsigned)b, 512, smem, sg::as_stream(stream)>>>(
-      v, n, edges, bins, reinterpret_cast<unsigned long long*>(counts));
+      v, n, edges, bins, copies, reinterpret_cast<unsigned long long*>(counts));
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

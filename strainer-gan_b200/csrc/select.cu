@@ -36,36 +36,31 @@ __global__ void begin_kernel(uint32_t* ws, unsigned long long k) {
   }
 }
 
+// Digit histogram of one pass.  Loss vectors are badly skewed in the top digit (a handful of
+// exponents), so a single shared histogram serialises on same-address atomics: keep kCopies
+// interleaved copies (bin*kCopies + lane%kCopies -> distinct banks for one bin) and sum them on flush.
+constexpr int kCopies = 8;
 __global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws,
                                                    int pass) {
-  __shared__ uint32_t s_hist[2048];
+  extern __shared__ uint32_t s_hist[];  // [2048][kCopies]
   __shared__ uint32_t s_nan;
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = 0u;
+  for (int i = threadIdx.x; i < 2048 * kCopies; i += blockDim.x) s_hist[i] = 0u;
   if (threadIdx.x == 0) s_nan = 0u;
   __syncthreads();
   const uint32_t prefix = ws[W_PREFIX];
-  const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+  const uint32_t copy = threadIdx.x & (kCopies - 1);
   uint32_t nan_local = 0;
-  auto visit = [&](float f) {
+  stream_f32<4>(v, n, [&](float f, int64_t) {
     const uint32_t key = float_to_key(f);
     if (pass == 0 && key == 0xFFFFFFFFu) ++nan_local;
-    if (in_prefix(key, prefix, pass)) atomicAdd(&s_hist[digit_of(key, pass)], 1u);
-  };
-  if (aligned) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const float4 q = ldg_stream4(reinterpret_cast<const float4*>(v) + i);
-      visit(q.x); visit(q.y); visit(q.z); visit(q.w);
-    }
-    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) visit(v[i]);
-  } else {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) visit(v[i]);
-  }
+    if (in_prefix(key, prefix, pass)) atomicAdd(&s_hist[digit_of(key, pass) * kCopies + copy], 1u);
+  });
   if (nan_local) atomicAdd(&s_nan, nan_local);
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
-    const uint32_t c = s_hist[i];
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < kCopies; ++k) c += s_hist[i * kCopies + k];
     if (c) atomicAdd(&ws[SG_SELECT_WS_HIST + i], c);
   }
   if (threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
@@ -134,11 +129,10 @@ __global__ void __launch_bounds__(1024) step_kernel(uint32_t* ws, int pass) {
 __global__ void __launch_bounds__(512) min_above_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws) {
   const uint32_t sel = ws[W_SELKEY];
   uint32_t best = 0xFFFFFFFFu;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t key = float_to_key(v[i]);
+  stream_f32<4>(v, n, [&](float f, int64_t) {
+    const uint32_t key = float_to_key(f);
     if (key > sel && key < best) best = key;
-  }
+  });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
   if ((threadIdx.x & 31) == 0 && best != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], best);
@@ -213,7 +207,7 @@ __global__ void __launch_bounds__(1024) segment_stats_kernel(const float* __rest
 
 static int grid_for(int64_t n, int threads, int per_thread) {
   int64_t b = ceil_div(n, (int64_t)threads * per_thread);
-  const int64_t cap = (int64_t)state().sm_count * 4;
+  const int64_t cap = (int64_t)state().sm_count * 3;  // 3 x 64 KB histogram CTAs / 1536 threads per SM
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -223,6 +217,12 @@ static int grid_for(int64_t n, int threads, int per_thread) {
 }  // namespace sg
 
 extern "C" {
+
+int sg_select_init_attributes() {
+  SG_CUDA(cudaFuncSetAttribute(sg::sel::hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               2048 * sg::sel::kCopies * 4));
+  return SG_OK;
+}
 
 int sg_select_begin(uint32_t* ws, int64_t k, void* stream) {
   SG_READY();
@@ -237,7 +237,7 @@ int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stre
   SG_REQUIRE(ws != nullptr && n >= 0 && pass >= 0 && pass < SG_SELECT_NUM_PASSES, "arguments");
   SG_REQUIRE(n == 0 || v != nullptr, "v");
   if (n == 0) return SG_OK;
-  sg::sel::hist_kernel<<<sg::sel::grid_for(n, 512, 16), 512, 0, sg::as_stream(stream)>>>(v, n, ws, pass);
+  sg::sel::hist_kernel<<<sg::sel::grid_for(n, 512, 16), 512, 2048 * sg::sel::kCopies * 4, sg::as_stream(stream)>>>(v, n, ws, pass);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
