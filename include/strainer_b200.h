@@ -119,20 +119,21 @@ int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, vo
 /* ---- selection: order statistics, thresholds ------------------------------------------
  * replaces np.percentile "#strainer gan.py:381", "# 종합 loss.py:288-292" and torch.quantile
  * "# 상위 10% 제거해서 fake image에 concate.py:246", "# z_score + DBSCAN.py:323".
- * Radix select of the order statistics x_(k) and x_(k+1) (NaNs sort last, -0 == +0), split in
- * phases so that a multi-GPU caller can all-reduce ws[0..2049) (uint32 histogram + NaN count, SUM)
- * after each sg_select_hist and ws[SG_SELECT_WS_MINABOVE] (as int32 of key ^ 0x80000000 it is
- * order preserving; the Python layer reduces it with MIN on the biased value) after
- * sg_select_min_above.  */
-#define SG_SELECT_WS_WORDS 4096      /* uint32 words of workspace */
-#define SG_SELECT_WS_HIST 0          /* [2048] digit histogram of the current pass */
-#define SG_SELECT_WS_NANCOUNT 2048   /* number of NaNs seen (pass 0); SUM-reduced with the histogram */
-#define SG_SELECT_WS_MINABOVE 2049   /* smallest radix key above the selected one (MIN-reduced) */
-#define SG_SELECT_NUM_PASSES 3
+ * Radix select of the order statistics x_(k) and x_(k+1) (NaNs sort last, -0 == +0): four streaming
+ * passes over 8 key bits each (256-bin histograms in 32 lane-private shared-memory copies: conflict
+ * free even for skewed data); the last pass also tracks the smallest key above the selected 24-bit
+ * bucket, so x_(k+1) costs no extra read.  Split in phases so that a multi-GPU caller can all-reduce
+ * ws[0..257) (uint32 digit histogram + NaN count, SUM) after every sg_select_hist and
+ * ws[SG_SELECT_WS_MINABOVE] (MIN; as int32 of key ^ 0x80000000 it is order preserving) after the
+ * last one, before the matching sg_select_step.  */
+#define SG_SELECT_WS_WORDS 512       /* uint32 words of workspace */
+#define SG_SELECT_WS_HIST 0          /* [256] digit histogram of the current pass */
+#define SG_SELECT_WS_NANCOUNT 256    /* number of NaNs seen (pass 0); SUM-reduced with the histogram */
+#define SG_SELECT_WS_MINABOVE 257    /* smallest radix key above the selected bucket (MIN-reduced) */
+#define SG_SELECT_NUM_PASSES 4
 int sg_select_begin(uint32_t* ws, int64_t k, void* stream);
 int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stream);
 int sg_select_step(uint32_t* ws, int pass, void* stream);
-int sg_select_min_above(const float* v, int64_t n, uint32_t* ws, void* stream);
 /* out2[0] = x_(k), out2[1] = x_(k+1) (== x_(k) when k is the last index); NaN if any NaN. */
 int sg_select_finish(const uint32_t* ws, float* out2, void* stream);
 /* single-device convenience: all phases back to back */

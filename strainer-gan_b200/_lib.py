@@ -13,10 +13,10 @@ SG_LT, SG_LE, SG_GE, SG_GT = 0, 1, 2, 3
 SG_NOT = 4  # OR-ed into a comparison: logical negation (NaN-correct complement)
 SG_LERP_NUMPY, SG_LERP_TORCH = 0, 1
 SG_CONV_BF16, SG_CONV_BF16X3 = 0, 1
-SG_SELECT_WS_WORDS = 4096
-SG_SELECT_WS_NANCOUNT = 2048
-SG_SELECT_WS_MINABOVE = 2049
-SG_SELECT_NUM_PASSES = 3
+SG_SELECT_WS_WORDS = 512
+SG_SELECT_WS_NANCOUNT = 256
+SG_SELECT_WS_MINABOVE = 257
+SG_SELECT_NUM_PASSES = 4
 SG_MOMENT_CHUNK = 4096
 
 P = c_void_p
@@ -41,7 +41,6 @@ _SIGS = {
     "sg_select_begin": (c_int, [P, c_int64, P]),
     "sg_select_hist": (c_int, [P, c_int64, P, c_int, P]),
     "sg_select_step": (c_int, [P, c_int, P]),
-    "sg_select_min_above": (c_int, [P, c_int64, P, P]),
     "sg_select_finish": (c_int, [P, P, P]),
     "sg_radix_select": (c_int, [P, c_int64, c_int64, P, P, P]),
     "sg_lerp_threshold": (c_int, [P, c_float, c_int, P, P]),

@@ -110,9 +110,6 @@ class _SelectOps:
     def step(self, ws, p):
         L.check(self.lib.sg_select_step(_p(ws), p, _stream()), "sg_select_step")
 
-    def min_above(self, values, ws):
-        L.check(self.lib.sg_select_min_above(_p(values), values.numel(), _p(ws), _stream()), "sg_select_min_above")
-
     def finish(self, ws, out2):
         L.check(self.lib.sg_select_finish(_p(ws), _p(out2), _stream()), "sg_select_finish")
 
@@ -121,7 +118,7 @@ def order_stats(values: torch.Tensor, k: int, group=None, ops=None) -> torch.Ten
     """Device tensor [x_(k), x_(k+1)] of a 1-D fp32 CUDA tensor (radix select, no sort).
     With ``group`` (torch.distributed), ``values`` is this rank's shard and k the GLOBAL rank: the
     integer digit histograms (+ NaN count) are all-reduced with SUM after each of the 3 passes and the
-    smallest key above the selected one with MIN, so every rank derives bit-identical statistics."""
+    smallest key above the selected bucket with MIN, so every rank derives bit-identical statistics."""
     device = values.device
     n = values.numel()
     ws = torch.empty(L.SG_SELECT_WS_WORDS, dtype=torch.int32, device=device)
@@ -137,13 +134,12 @@ def order_stats(values: torch.Tensor, k: int, group=None, ops=None) -> torch.Ten
         ops.hist(values, ws, p)
         if group is not None:
             dist.all_reduce(ws[:L.SG_SELECT_WS_NANCOUNT + 1], op=dist.ReduceOp.SUM, group=group)
+            if p == L.SG_SELECT_NUM_PASSES - 1:
+                m = ws[L.SG_SELECT_WS_MINABOVE:L.SG_SELECT_WS_MINABOVE + 1]
+                m ^= -2147483648  # uint32 key order -> int32 order for the MIN reduction
+                dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
+                m ^= -2147483648
         ops.step(ws, p)
-    ops.min_above(values, ws)
-    if group is not None:
-        m = ws[L.SG_SELECT_WS_MINABOVE:L.SG_SELECT_WS_MINABOVE + 1]
-        m ^= -2147483648  # uint32 key order -> int32 order for the MIN reduction
-        dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
-        m ^= -2147483648
     ops.finish(ws, out2)
     return out2
 

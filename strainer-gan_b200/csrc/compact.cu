@@ -93,6 +93,14 @@ __device__ __forceinline__ int block_excl_scan(int c, int* s_warp, int* total) {
 }
 
 // v[i] CMP thr -> ascending global indices (int64) + optional byte mask.
+// One CTA per tile, tile ids claimed from an atomic counter in launch order (so every predecessor of a
+// tile is running or done -> the look-back spin cannot deadlock, and CTAs start staggered, which keeps
+// the look-back short: a persistent lock-step schedule was measured 2x slower because a whole wave
+// then walks back through hundreds of not-yet-resolved aggregates).  Inside a tile the layout is
+// STRIPED per warp: warp w owns 512 consecutive elements, slot j of lane l is element
+// w*512 + j*32 + l.  One __ballot_sync per slot gives the keep-mask of 32 consecutive elements, so a
+// lane's output position is popc(mask & lanes-below) past a running base and the kept lanes of a slot
+// write one contiguous run of int64: no shared-memory staging, no per-thread serial loop.
 __global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* __restrict__ v, int64_t n,
                                                                    const float* __restrict__ thr_p, int cmp,
                                                                    int64_t index_base, int64_t* __restrict__ idx_out,
@@ -100,59 +108,61 @@ __global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* 
                                                                    uint8_t* __restrict__ mask_out, ScanWs* ws,
                                                                    int num_tiles) {
   __shared__ int s_tile;
-  __shared__ int s_warp[kThreads / 32];
+  __shared__ int s_wtot[kThreads / 32];
   __shared__ unsigned long long s_excl;
-  __shared__ int64_t s_idx[kTile];  // kept indices of the tile in order -> coalesced 8-byte stores
   unsigned long long* status = reinterpret_cast<unsigned long long*>(ws + 1);
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
   const float thr = *thr_p;
-  while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile >= num_tiles) break;
-    const int64_t base = (int64_t)tile * kTile + (int64_t)threadIdx.x * kItems;
-    float x[kItems];
-    if (base + kItems <= n && (reinterpret_cast<uintptr_t>(v) & 15) == 0) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t wbase = (int64_t)tile * kTile + w * (kItems * 32);
+  float x[kItems];
+  if (wbase + kItems * 32 <= n) {
 #pragma unroll
-      for (int q = 0; q < kItems / 4; ++q) {
-        const float4 f = ldg_stream4(reinterpret_cast<const float4*>(v + base) + q);
-        x[4 * q] = f.x; x[4 * q + 1] = f.y; x[4 * q + 2] = f.z; x[4 * q + 3] = f.w;
-      }
-    } else {
+    for (int j = 0; j < kItems; ++j) x[j] = __ldg(v + wbase + j * 32 + lane);
+  } else {
 #pragma unroll
-      for (int j = 0; j < kItems; ++j) x[j] = (base + j < n) ? v[base + j] : 0.f;
+    for (int j = 0; j < kItems; ++j) {
+      const int64_t i = wbase + j * 32 + lane;
+      x[j] = (i < n) ? v[i] : 0.f;
     }
-    unsigned flags = 0;
-#pragma unroll
-    for (int j = 0; j < kItems; ++j)
-      if (base + j < n && cmp_apply(x[j], thr, cmp)) flags |= 1u << j;
-    const int c = __popc(flags);
-    int total;
-    const int toff = block_excl_scan(c, s_warp, &total);
-    {
-      int w = toff;
-#pragma unroll
-      for (int j = 0; j < kItems; ++j)
-        if (flags & (1u << j)) s_idx[w++] = index_base + base + j;
-    }
-    const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);  // ends with a barrier
-    for (int i = threadIdx.x; i < total; i += kThreads) idx_out[excl + i] = s_idx[i];
-    if (mask_out) {
-      if (base + kItems <= n && (reinterpret_cast<uintptr_t>(mask_out) & 15) == 0) {
-        uint32_t m[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          m[q] = ((flags >> (4 * q)) & 1u) | (((flags >> (4 * q + 1)) & 1u) << 8) |
-                 (((flags >> (4 * q + 2)) & 1u) << 16) | (((flags >> (4 * q + 3)) & 1u) << 24);
-        *reinterpret_cast<uint4*>(mask_out + base) = make_uint4(m[0], m[1], m[2], m[3]);
-      } else {
-        for (int j = 0; j < kItems; ++j)
-          if (base + j < n) mask_out[base + j] = (flags >> j) & 1u;
-      }
-    }
-    if (tile == num_tiles - 1 && threadIdx.x == 0) *count_out = (int64_t)(excl + total);
   }
+  unsigned masks[kItems];
+  int wtotal = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const bool keep = (wbase + j * 32 + lane < n) && cmp_apply(x[j], thr, cmp);
+    masks[j] = __ballot_sync(0xffffffffu, keep);
+    wtotal += __popc(masks[j]);
+  }
+  if (lane == 0) s_wtot[w] = wtotal;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < kThreads / 32; ++ww) {
+    const int c = s_wtot[ww];
+    if (ww < w) woff += c;
+    total += c;
+  }
+  const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);
+  int64_t* dst = idx_out + excl + woff;
+  const int64_t gidx = index_base + wbase + lane;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const unsigned m = masks[j];
+    if (m & (1u << lane)) dst[__popc(m & lt)] = gidx + j * 32;
+    dst += __popc(m);
+  }
+  if (mask_out) {
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int64_t i = wbase + j * 32 + lane;
+      if (i < n) mask_out[i] = (masks[j] >> lane) & 1u;
+    }
+  }
+  if (tile == num_tiles - 1 && threadIdx.x == 0) *count_out = (int64_t)(excl + total);
 }
 
 // Stable two-way partition destinations from a byte mask: dest[i] = rank among kept rows (mask != 0)
@@ -165,12 +175,10 @@ __global__ void __launch_bounds__(kThreads) partition_dest_kernel(const uint8_t*
   __shared__ int s_warp[kThreads / 32];
   __shared__ unsigned long long s_excl;
   unsigned long long* status = reinterpret_cast<unsigned long long*>(ws + 1);
-  while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
-    __syncthreads();
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
+  __syncthreads();
+  {
     const int tile = s_tile;
-    if (tile >= num_tiles) break;
     const int64_t base = (int64_t)tile * kTile + (int64_t)threadIdx.x * kItems;
     unsigned flags = 0;
 #pragma unroll
@@ -265,9 +273,7 @@ int sg_compact_indices(const float* v, int64_t n, const float* thr, int cmp, int
   }
   const int num_tiles = (int)sg::ceil_div(n, kTile);
   SG_CUDA(cudaMemsetAsync(workspace, 0, scan_ws_bytes(n), st));
-  int grid = num_tiles;
-  const int cap = sg::state().sm_count * 8;
-  if (grid > cap) grid = cap;
+  const int grid = num_tiles;  // one CTA per tile; ids come from the atomic counter in launch order
   compact_indices_kernel<<<grid, kThreads, 0, st>>>(v, n, thr, cmp, index_base, idx_out, count_out, mask_out,
                                                     static_cast<ScanWs*>(workspace), num_tiles);
   SG_LAUNCH_CHECK();
@@ -293,9 +299,7 @@ int sg_compact_rows(const void* rows, int64_t n, int64_t row_bytes, const uint8_
   const size_t sbytes = scan_ws_bytes(n);
   SG_CUDA(cudaMemsetAsync(workspace, 0, sbytes, st));
   int64_t* dest = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(workspace) + sbytes);
-  int grid = num_tiles;
-  const int cap = sg::state().sm_count * 8;
-  if (grid > cap) grid = cap;
+  const int grid = num_tiles;
   partition_dest_kernel<<<grid, kThreads, 0, st>>>(mask, n, dest, counts_out, static_cast<ScanWs*>(workspace), num_tiles);
   SG_LAUNCH_CHECK();
   move_rows_kernel<<<(unsigned)n, 256, 0, st>>>(static_cast<const int4*>(rows), row_bytes / 16, dest,

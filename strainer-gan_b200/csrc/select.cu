@@ -11,72 +11,73 @@ namespace sg {
 namespace sel {
 
 // internal workspace words (after the public ones)
-constexpr int W_PREFIX = 2052;     // selected key bits so far
-constexpr int W_KREM_LO = 2054;    // remaining rank inside the current bucket (u64)
-constexpr int W_SELKEY = 2056;     // final key of x_(k)
-constexpr int W_NEEDNEXT = 2057;   // 1: x_(k+1) is the smallest key above x_(k)
+constexpr int W_PREFIX = 260;      // selected key bits so far (8, 16, 24, 32 bits)
+constexpr int W_KREM_LO = 262;     // remaining rank inside the current bucket (u64)
+constexpr int W_SELKEY = 264;      // final key of x_(k)
+constexpr int W_NEEDNEXT = 265;    // 1: x_(k+1) has a larger key than x_(k)
+constexpr int W_NEXTIN = 266;     // smallest populated last-pass digit above the selected one (or ~0)
 
-__device__ __forceinline__ bool in_prefix(uint32_t key, uint32_t prefix, int pass) {
-  if (pass == 0) return true;
-  if (pass == 1) return (key >> 21) == prefix;
-  return (key >> 10) == prefix;
-}
-__device__ __forceinline__ uint32_t digit_of(uint32_t key, int pass) {
-  if (pass == 0) return key >> 21;
-  if (pass == 1) return (key >> 10) & 0x7FFu;
-  return key & 0x3FFu;
-}
-
+// Pass plan: 4 x 8 bits.  Loss vectors are heavily skewed in their top bits (a handful of exponents),
+// so a shared histogram serialises on same-address atomics.  With 256 bins the histogram fits in 32
+// lane-private copies (bin*32 + lane: every lane owns a bank), which makes every shared atomic
+// conflict-free in EVERY pass; passes 1..3 only count the elements inside the selected bucket.
+// The last pass also tracks the smallest key ABOVE the 24-bit bucket, so x_(k+1) needs no extra read.
 __global__ void begin_kernel(uint32_t* ws, unsigned long long k) {
   for (int i = threadIdx.x; i < SG_SELECT_WS_WORDS; i += blockDim.x) ws[i] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
     ws[SG_SELECT_WS_MINABOVE] = 0xFFFFFFFFu;
+    ws[W_NEXTIN] = 0xFFFFFFFFu;
     *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO) = k;
   }
 }
 
-// Digit histogram of one pass.  Loss vectors are badly skewed in the top digit (a handful of
-// exponents), so a single shared histogram serialises on same-address atomics: keep kCopies
-// interleaved copies (bin*kCopies + lane%kCopies -> distinct banks for one bin) and sum them on flush.
-constexpr int kCopies = 8;
-__global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws,
-                                                   int pass) {
-  extern __shared__ uint32_t s_hist[];  // [2048][kCopies]
-  __shared__ uint32_t s_nan;
-  for (int i = threadIdx.x; i < 2048 * kCopies; i += blockDim.x) s_hist[i] = 0u;
-  if (threadIdx.x == 0) s_nan = 0u;
+template <int PASS>
+__global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws) {
+  __shared__ uint32_t s_hist[256 * 32];
+  __shared__ uint32_t s_nan, s_min;
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_hist[i] = 0u;
+  if (threadIdx.x == 0) { s_nan = 0u; s_min = 0xFFFFFFFFu; }
   __syncthreads();
   const uint32_t prefix = ws[W_PREFIX];
-  const uint32_t copy = threadIdx.x & (kCopies - 1);
-  uint32_t nan_local = 0;
+  const uint32_t lane = threadIdx.x & 31;
+  constexpr int kShift = 24 - 8 * PASS;   // digit position
+  uint32_t nan_local = 0, min_local = 0xFFFFFFFFu;
   stream_f32<4>(v, n, [&](float f, int64_t) {
     const uint32_t key = float_to_key(f);
-    if (pass == 0 && key == 0xFFFFFFFFu) ++nan_local;
-    if (in_prefix(key, prefix, pass)) atomicAdd(&s_hist[digit_of(key, pass) * kCopies + copy], 1u);
+    if constexpr (PASS == 0) {
+      nan_local += (key == 0xFFFFFFFFu);
+      atomicAdd(&s_hist[((key >> 24) << 5) + lane], 1u);
+    } else {
+      const uint32_t hi = key >> (kShift + 8);
+      if (hi == prefix) atomicAdd(&s_hist[(((key >> kShift) & 255u) << 5) + lane], 1u);
+      if (PASS == 3 && hi > prefix) min_local = min(min_local, key);
+    }
   });
-  if (nan_local) atomicAdd(&s_nan, nan_local);
+  if (PASS == 0 && nan_local) atomicAdd(&s_nan, nan_local);
+  if (PASS == 3 && min_local != 0xFFFFFFFFu) atomicMin(&s_min, min_local);
   __syncthreads();
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < kCopies; ++k) c += s_hist[i * kCopies + k];
+    for (int k = 0; k < 32; ++k) c += s_hist[i * 32 + ((k + i) & 31)];
     if (c) atomicAdd(&ws[SG_SELECT_WS_HIST + i], c);
   }
-  if (threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
+  if (PASS == 0 && threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
+  if (PASS == 3 && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], s_min);
 }
 
-// Finds the bucket holding rank k_rem, narrows the prefix, clears the histogram for the next pass.
-__global__ void __launch_bounds__(1024) step_kernel(uint32_t* ws, int pass) {
-  __shared__ unsigned long long s_warp[32];
-  __shared__ unsigned long long s_before;
+// Finds the bin holding rank k_rem among the 256 bins, narrows the prefix, clears the histogram for the
+// next pass.  One thread per bin.
+__global__ void __launch_bounds__(256) step_kernel(uint32_t* ws, int pass) {
+  __shared__ unsigned long long s_warp[8];
+  __shared__ unsigned long long s_before, s_cnt;
   __shared__ int s_bucket;
+  __shared__ uint32_t s_next;
   const int t = threadIdx.x;
-  const unsigned long long c0 = ws[SG_SELECT_WS_HIST + 2 * t];
-  const unsigned long long c1 = ws[SG_SELECT_WS_HIST + 2 * t + 1];
+  const unsigned long long c = ws[SG_SELECT_WS_HIST + t];
   const unsigned long long k = *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO);
-  // inclusive scan of the per-thread pair sums
-  unsigned long long x = c0 + c1;
+  unsigned long long x = c;
   const int lane = t & 31, w = t >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -84,58 +85,29 @@ __global__ void __launch_bounds__(1024) step_kernel(uint32_t* ws, int pass) {
     if (lane >= o) x += y;
   }
   if (lane == 31) s_warp[w] = x;
-  if (t == 0) s_bucket = -1;
+  if (t == 0) { s_bucket = -1; s_next = 0xFFFFFFFFu; }
   __syncthreads();
-  if (w == 0) {
-    unsigned long long s = s_warp[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long y = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += y;
-    }
-    s_warp[lane] = s;
-  }
+  unsigned long long run = x - c;
+  for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
+  if (k >= run && k < run + c) { s_bucket = t; s_before = run; s_cnt = c; }
   __syncthreads();
-  const unsigned long long incl = x + (w ? s_warp[w - 1] : 0ull);
-  const unsigned long long excl = incl - (c0 + c1);
-  if (k >= excl && k < excl + c0) { s_bucket = 2 * t; s_before = excl; }
-  else if (k >= excl + c0 && k < incl) { s_bucket = 2 * t + 1; s_before = excl + c0; }
+  ws[SG_SELECT_WS_HIST + t] = 0u;
+  int b = s_bucket;
+  if (pass == 3 && b >= 0 && t > b && c != 0ull) atomicMin(&s_next, (uint32_t)t);  // next populated digit in the bucket
   __syncthreads();
-  ws[SG_SELECT_WS_HIST + 2 * t] = 0u;
-  ws[SG_SELECT_WS_HIST + 2 * t + 1] = 0u;
   if (t == 0) {
-    int b = s_bucket;
-    unsigned long long before = s_before;
-    if (b < 0) { b = (pass == 2) ? 1023 : 2047; before = 0; }  // k >= n: clamp (caller validates k < n)
-    const int bits = (pass == 2) ? 10 : 11;
-    const uint32_t prefix = (pass == 0) ? (uint32_t)b : ((ws[W_PREFIX] << bits) | (uint32_t)b);
+    unsigned long long before = s_before, cnt = s_cnt;
+    if (b < 0) { b = 255; before = 0; cnt = 0; }  // k >= n: clamp (callers validate k < n)
+    const uint32_t prefix = (pass == 0) ? (uint32_t)b : ((ws[W_PREFIX] << 8) | (uint32_t)b);
     ws[W_PREFIX] = prefix;
     const unsigned long long krem = k - before;
     *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO) = krem;
-    if (pass == 2) ws[W_SELKEY] = prefix;
-  }
-  // the owning thread knows the bucket population: decide whether x_(k+1) shares the key
-  if (pass == 2) {
-    __syncthreads();
-    const int b = s_bucket;
-    if (b >= 0 && (b >> 1) == t) {
-      const unsigned long long cnt = (b & 1) ? c1 : c0;
-      const unsigned long long krem = k - s_before;
+    if (pass == 3) {
+      ws[W_SELKEY] = prefix;
       ws[W_NEEDNEXT] = (krem + 1 >= cnt) ? 1u : 0u;
+      ws[W_NEXTIN] = (s_next == 0xFFFFFFFFu) ? 0xFFFFFFFFu : ((prefix & ~0xFFu) | s_next);
     }
   }
-}
-
-__global__ void __launch_bounds__(512) min_above_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws) {
-  const uint32_t sel = ws[W_SELKEY];
-  uint32_t best = 0xFFFFFFFFu;
-  stream_f32<4>(v, n, [&](float f, int64_t) {
-    const uint32_t key = float_to_key(f);
-    if (key > sel && key < best) best = key;
-  });
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((threadIdx.x & 31) == 0 && best != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], best);
 }
 
 __global__ void finish_kernel(const uint32_t* ws, float* out2) {
@@ -145,8 +117,9 @@ __global__ void finish_kernel(const uint32_t* ws, float* out2) {
   const float a = key_to_float(ws[W_SELKEY]);
   float b = a;
   if (ws[W_NEEDNEXT]) {
-    const uint32_t m = ws[SG_SELECT_WS_MINABOVE];
-    if (m != 0xFFFFFFFFu) b = key_to_float(m);
+    const uint32_t in_bucket = ws[W_NEXTIN], above = ws[SG_SELECT_WS_MINABOVE];
+    if (in_bucket != 0xFFFFFFFFu) b = key_to_float(in_bucket);
+    else if (above != 0xFFFFFFFFu) b = key_to_float(above);
   }
   out2[0] = a;
   out2[1] = b;
@@ -207,7 +180,7 @@ __global__ void __launch_bounds__(1024) segment_stats_kernel(const float* __rest
 
 static int grid_for(int64_t n, int threads, int per_thread) {
   int64_t b = ceil_div(n, (int64_t)threads * per_thread);
-  const int64_t cap = (int64_t)state().sm_count * 3;  // 3 x 64 KB histogram CTAs / 1536 threads per SM
+  const int64_t cap = (int64_t)state().sm_count * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -218,16 +191,12 @@ static int grid_for(int64_t n, int threads, int per_thread) {
 
 extern "C" {
 
-int sg_select_init_attributes() {
-  SG_CUDA(cudaFuncSetAttribute(sg::sel::hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               2048 * sg::sel::kCopies * 4));
-  return SG_OK;
-}
+int sg_select_init_attributes() { return SG_OK; }
 
 int sg_select_begin(uint32_t* ws, int64_t k, void* stream) {
   SG_READY();
   SG_REQUIRE(ws != nullptr && k >= 0, "ws/k");
-  sg::sel::begin_kernel<<<1, 1024, 0, sg::as_stream(stream)>>>(ws, (unsigned long long)k);
+  sg::sel::begin_kernel<<<1, 512, 0, sg::as_stream(stream)>>>(ws, (unsigned long long)k);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -237,7 +206,14 @@ int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stre
   SG_REQUIRE(ws != nullptr && n >= 0 && pass >= 0 && pass < SG_SELECT_NUM_PASSES, "arguments");
   SG_REQUIRE(n == 0 || v != nullptr, "v");
   if (n == 0) return SG_OK;
-  sg::sel::hist_kernel<<<sg::sel::grid_for(n, 512, 16), 512, 2048 * sg::sel::kCopies * 4, sg::as_stream(stream)>>>(v, n, ws, pass);
+  const int grid = sg::sel::grid_for(n, 512, 16);
+  cudaStream_t st = sg::as_stream(stream);
+  switch (pass) {
+    case 0: sg::sel::hist_kernel<0><<<grid, 512, 0, st>>>(v, n, ws); break;
+    case 1: sg::sel::hist_kernel<1><<<grid, 512, 0, st>>>(v, n, ws); break;
+    case 2: sg::sel::hist_kernel<2><<<grid, 512, 0, st>>>(v, n, ws); break;
+    default: sg::sel::hist_kernel<3><<<grid, 512, 0, st>>>(v, n, ws); break;
+  }
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -245,16 +221,7 @@ int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stre
 int sg_select_step(uint32_t* ws, int pass, void* stream) {
   SG_READY();
   SG_REQUIRE(ws != nullptr && pass >= 0 && pass < SG_SELECT_NUM_PASSES, "arguments");
-  sg::sel::step_kernel<<<1, 1024, 0, sg::as_stream(stream)>>>(ws, pass);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
-}
-
-int sg_select_min_above(const float* v, int64_t n, uint32_t* ws, void* stream) {
-  SG_READY();
-  SG_REQUIRE(ws != nullptr && n >= 0, "arguments");
-  if (n == 0) return SG_OK;
-  sg::sel::min_above_kernel<<<sg::sel::grid_for(n, 512, 8), 512, 0, sg::as_stream(stream)>>>(v, n, ws);
+  sg::sel::step_kernel<<<1, 256, 0, sg::as_stream(stream)>>>(ws, pass);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -274,7 +241,6 @@ int sg_radix_select(const float* v, int64_t n, int64_t k, uint32_t* ws, float* o
     r = sg_select_hist(v, n, ws, pass, stream);
     if (r == SG_OK) r = sg_select_step(ws, pass, stream);
   }
-  if (r == SG_OK) r = sg_select_min_above(v, n, ws, stream);
   if (r == SG_OK) r = sg_select_finish(ws, out2, stream);
   return r;
 }

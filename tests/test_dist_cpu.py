@@ -32,8 +32,9 @@ def key2f(k):
 
 
 class FakeSelectOps:
-    """numpy restatement of sel::begin/hist/step/min_above/finish (csrc/select.cu)."""
-    PREFIX, KREM, SELKEY, NEEDNEXT = 2052, 2054, 2056, 2057
+    """numpy restatement of sel::begin/hist<PASS>/step/finish (csrc/select.cu): four 8-bit passes, the
+    last one also tracks the smallest key above the selected 24-bit bucket."""
+    NAN, MINABOVE, PREFIX, KREM, SELKEY, NEEDNEXT, NEXTIN = 256, 257, 260, 262, 264, 265, 266
 
     def _u(self, ws):
         return ws.numpy().view(np.uint32)
@@ -41,53 +42,56 @@ class FakeSelectOps:
     def begin(self, ws, k):
         u = self._u(ws)
         u[:] = 0
-        u[2049] = 0xFFFFFFFF
+        u[self.MINABOVE] = 0xFFFFFFFF
+        u[self.NEXTIN] = 0xFFFFFFFF
         u[self.KREM:self.KREM + 2].view(np.uint64)[0] = k
 
     def hist(self, values, ws, p):
         u = self._u(ws)
         key = f2key(values.numpy())
         prefix = u[self.PREFIX]
+        shift = 24 - 8 * p
         if p == 0:
-            sel, dig = np.ones(key.shape, bool), key >> 21
-            u[2048] += np.uint32((key == 0xFFFFFFFF).sum())
-        elif p == 1:
-            sel, dig = (key >> 21) == prefix, (key >> 10) & 0x7FF
+            sel = np.ones(key.shape, bool)
+            u[self.NAN] += np.uint32((key == 0xFFFFFFFF).sum())
         else:
-            sel, dig = (key >> 10) == prefix, key & 0x3FF
-        u[:2048] += np.bincount(dig[sel], minlength=2048).astype(np.uint32)
+            hi = key >> np.uint32(shift + 8)
+            sel = hi == prefix
+            if p == 3:
+                above = key[hi > prefix]
+                if above.size:
+                    u[self.MINABOVE] = min(u[self.MINABOVE], above.min())
+        dig = (key >> np.uint32(shift)) & 0xFF
+        u[:256] += np.bincount(dig[sel], minlength=256).astype(np.uint32)
 
     def step(self, ws, p):
         u = self._u(ws)
         k = int(u[self.KREM:self.KREM + 2].view(np.uint64)[0])
-        h = u[:2048].astype(np.uint64)
+        h = u[:256].astype(np.uint64)
         c = np.cumsum(h)
         b = int(np.searchsorted(c, k, side="right"))
         before = int(c[b - 1]) if b else 0
-        bits = 10 if p == 2 else 11
-        u[self.PREFIX] = b if p == 0 else ((int(u[self.PREFIX]) << bits) | b) & 0xFFFFFFFF
+        u[self.PREFIX] = b if p == 0 else ((int(u[self.PREFIX]) << 8) | b) & 0xFFFFFFFF
         u[self.KREM:self.KREM + 2].view(np.uint64)[0] = k - before
-        if p == 2:
+        if p == 3:
             u[self.SELKEY] = u[self.PREFIX]
             u[self.NEEDNEXT] = 1 if (k - before + 1 >= int(h[b])) else 0
-        u[:2048] = 0
-
-    def min_above(self, values, ws):
-        u = self._u(ws)
-        key = f2key(values.numpy())
-        above = key[key > u[self.SELKEY]]
-        if above.size:
-            u[2049] = min(u[2049], above.min())
+            nz = np.nonzero(h[b + 1:])[0]
+            u[self.NEXTIN] = ((int(u[self.PREFIX]) & ~0xFF) | (b + 1 + int(nz[0]))) if nz.size else 0xFFFFFFFF
+        u[:256] = 0
 
     def finish(self, ws, out2):
         u = self._u(ws)
-        if u[2048]:
+        if u[self.NAN]:
             out2[:] = float("nan")
             return
         a = key2f(u[self.SELKEY])
         b = a
-        if u[self.NEEDNEXT] and u[2049] != 0xFFFFFFFF:
-            b = key2f(u[2049])
+        if u[self.NEEDNEXT]:
+            if u[self.NEXTIN] != 0xFFFFFFFF:
+                b = key2f(u[self.NEXTIN])
+            elif u[self.MINABOVE] != 0xFFFFFFFF:
+                b = key2f(u[self.MINABOVE])
         out2[0], out2[1] = float(a), float(b)
 
     def lerp(self, stats2, gamma, kind):

@@ -153,19 +153,21 @@ def test_sharded_select_emulated(sb):
     p = lambda t: L.P(t.data_ptr())
     for ws in wss:
         L.check(lib.sg_select_begin(p(ws), k, st))
-    for ps in range(3):
+    NW = L.SG_SELECT_WS_NANCOUNT + 1
+    MA = L.SG_SELECT_WS_MINABOVE
+    for ps in range(L.SG_SELECT_NUM_PASSES):
         for ws, sh in zip(wss, shards):
             L.check(lib.sg_select_hist(p(sh), sh.numel(), p(ws), ps, st))
-        tot = sum(ws[:2049].clone() for ws in wss)
+        tot = sum(ws[:NW].clone() for ws in wss)
+        if ps == L.SG_SELECT_NUM_PASSES - 1:
+            mins = torch.stack([ws[MA] ^ -2147483648 for ws in wss]).min() ^ -2147483648
         for ws in wss:
-            ws[:2049] = tot
+            ws[:NW] = tot
+            if ps == L.SG_SELECT_NUM_PASSES - 1:
+                ws[MA] = mins
             L.check(lib.sg_select_step(p(ws), ps, st))
-    for ws, sh in zip(wss, shards):
-        L.check(lib.sg_select_min_above(p(sh), sh.numel(), p(ws), st))
-    mins = torch.stack([ws[2049] ^ -2147483648 for ws in wss]).min() ^ -2147483648
     outs = []
     for ws in wss:
-        ws[2049] = mins
         o = torch.empty(2, device="cuda")
         L.check(lib.sg_select_finish(p(ws), p(o), st))
         outs.append(o.cpu().numpy())

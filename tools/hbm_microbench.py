@@ -60,7 +60,7 @@ def main():
     L.check(lib.sg_select_begin(p(ws), n // 2, st))
     rec("select_hist_pass0", timeit(lambda: lib.sg_select_hist(p(v), n, p(ws), 0, st)), 4 * n, "one radix-histogram pass: 4 B/elem read")
     rec("radix_select_total", timeit(lambda: lib.sg_radix_select(p(v), n, (9 * n) // 10, p(ws), p(out2), st)), 16 * n,
-        "3 histogram passes + min-above pass = 4 reads of 4 B/elem")
+        "x_(k) and x_(k+1): 4 streaming passes of 4 B/elem (8 key bits each)")
     thr = torch.tensor([float(np.percentile(v[:1 << 20].cpu().numpy(), 90))], device=dev)
     idx = torch.empty(n, dtype=torch.int64, device=dev)
     cnt = torch.empty(1, dtype=torch.int64, device=dev)
