@@ -93,22 +93,27 @@ __device__ __forceinline__ int block_excl_scan(int c, int* s_warp, int* total) {
 }
 
 // v[i] CMP thr -> ascending global indices (int64) + optional byte mask.
-// One CTA per tile, tile ids claimed from an atomic counter in launch order (so every predecessor of a
-// tile is running or done -> the look-back spin cannot deadlock, and CTAs start staggered, which keeps
-// the look-back short: a persistent lock-step schedule was measured 2x slower because a whole wave
-// then walks back through hundreds of not-yet-resolved aggregates).  Inside a tile the layout is
-// STRIPED per warp: warp w owns 512 consecutive elements, slot j of lane l is element
-// w*512 + j*32 + l.  One __ballot_sync per slot gives the keep-mask of 32 consecutive elements, so a
-// lane's output position is popc(mask & lanes-below) past a running base and the kept lanes of a slot
-// write one contiguous run of int64: no shared-memory staging, no per-thread serial loop.
-__global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* __restrict__ v, int64_t n,
+// One CTA per tile of kBigTile = 16384 elements; tile ids are claimed from an atomic counter in launch
+// order (every predecessor is running or done -> the look-back spin cannot deadlock).  The tile is
+// large on purpose: a look-back window resolves at most 32 tiles per L2 round trip, which with
+// 4096-element tiles capped the kernel at ~45 % of HBM peak (ncu: 23 of 29 stall cycles on the
+// barrier behind the look-back).
+// Layout inside a tile is STRIPED per warp: warp w owns 2048 consecutive elements, slot j of lane l is
+// element w*2048 + j*32 + l.  One __ballot_sync per slot gives the keep-mask of 32 consecutive
+// elements, so a lane's output position is popc(mask & lanes-below) past a running base and the kept
+// lanes of a slot write one contiguous run of int64: no shared-memory staging, no serial loop.
+// Each lane keeps only its own 64 keep-bits; the ballots are re-formed in the store phase.
+constexpr int kBigItems = 64;
+constexpr int kCiThreads = 256;
+constexpr int kBigTile = kCiThreads * kBigItems;  // 16384
+__global__ void __launch_bounds__(kCiThreads) compact_indices_kernel(const float* __restrict__ v, int64_t n,
                                                                    const float* __restrict__ thr_p, int cmp,
                                                                    int64_t index_base, int64_t* __restrict__ idx_out,
                                                                    int64_t* __restrict__ count_out,
                                                                    uint8_t* __restrict__ mask_out, ScanWs* ws,
                                                                    int num_tiles) {
   __shared__ int s_tile;
-  __shared__ int s_wtot[kThreads / 32];
+  __shared__ int s_wtot[kCiThreads / 32];
   __shared__ unsigned long long s_excl;
   unsigned long long* status = reinterpret_cast<unsigned long long*>(ws + 1);
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws->tile_counter, 1u);
@@ -117,31 +122,30 @@ __global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* 
   const unsigned lt = (1u << lane) - 1u;
   __syncthreads();
   const int tile = s_tile;
-  const int64_t wbase = (int64_t)tile * kTile + w * (kItems * 32);
-  float x[kItems];
-  if (wbase + kItems * 32 <= n) {
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) x[j] = __ldg(v + wbase + j * 32 + lane);
-  } else {
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
-      const int64_t i = wbase + j * 32 + lane;
-      x[j] = (i < n) ? v[i] : 0.f;
-    }
-  }
-  unsigned masks[kItems];
+  const int64_t wbase = (int64_t)tile * kBigTile + w * (kBigItems * 32);
+  unsigned long long bits = 0ull;
   int wtotal = 0;
+  const bool full = wbase + kBigItems * 32 <= n;
 #pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const bool keep = (wbase + j * 32 + lane < n) && cmp_apply(x[j], thr, cmp);
-    masks[j] = __ballot_sync(0xffffffffu, keep);
-    wtotal += __popc(masks[j]);
+  for (int g = 0; g < kBigItems / 16; ++g) {
+    float x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int64_t i = wbase + (g * 16 + j) * 32 + lane;
+      x[j] = (full || i < n) ? __ldg(v + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const bool keep = (full || wbase + (g * 16 + j) * 32 + lane < n) && cmp_apply(x[j], thr, cmp);
+      wtotal += __popc(__ballot_sync(0xffffffffu, keep));
+      bits |= (unsigned long long)keep << (g * 16 + j);
+    }
   }
   if (lane == 0) s_wtot[w] = wtotal;
   __syncthreads();
   int woff = 0, total = 0;
 #pragma unroll
-  for (int ww = 0; ww < kThreads / 32; ++ww) {
+  for (int ww = 0; ww < kCiThreads / 32; ++ww) {
     const int c = s_wtot[ww];
     if (ww < w) woff += c;
     total += c;
@@ -149,17 +153,18 @@ __global__ void __launch_bounds__(kThreads) compact_indices_kernel(const float* 
   const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);
   int64_t* dst = idx_out + excl + woff;
   const int64_t gidx = index_base + wbase + lane;
-#pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const unsigned m = masks[j];
-    if (m & (1u << lane)) dst[__popc(m & lt)] = gidx + j * 32;
+#pragma unroll 16
+  for (int j = 0; j < kBigItems; ++j) {
+    const bool keep = (bits >> j) & 1ull;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) dst[__popc(m & lt)] = gidx + j * 32;
     dst += __popc(m);
   }
   if (mask_out) {
-#pragma unroll
-    for (int j = 0; j < kItems; ++j) {
+#pragma unroll 16
+    for (int j = 0; j < kBigItems; ++j) {
       const int64_t i = wbase + j * 32 + lane;
-      if (i < n) mask_out[i] = (masks[j] >> lane) & 1u;
+      if (full || i < n) mask_out[i] = (uint8_t)((bits >> j) & 1ull);
     }
   }
   if (tile == num_tiles - 1 && threadIdx.x == 0) *count_out = (int64_t)(excl + total);
@@ -271,10 +276,10 @@ int sg_compact_indices(const float* v, int64_t n, const float* thr, int cmp, int
     SG_CUDA(cudaMemsetAsync(count_out, 0, 8, st));
     return SG_OK;
   }
-  const int num_tiles = (int)sg::ceil_div(n, kTile);
-  SG_CUDA(cudaMemsetAsync(workspace, 0, scan_ws_bytes(n), st));
+  const int num_tiles = (int)sg::ceil_div(n, kBigTile);
+  SG_CUDA(cudaMemsetAsync(workspace, 0, sizeof(ScanWs) + (size_t)num_tiles * 8, st));
   const int grid = num_tiles;  // one CTA per tile; ids come from the atomic counter in launch order
-  compact_indices_kernel<<<grid, kThreads, 0, st>>>(v, n, thr, cmp, index_base, idx_out, count_out, mask_out,
+  compact_indices_kernel<<<grid, kCiThreads, 0, st>>>(v, n, thr, cmp, index_base, idx_out, count_out, mask_out,
                                                     static_cast<ScanWs*>(workspace), num_tiles);
   SG_LAUNCH_CHECK();
   return SG_OK;
