@@ -231,3 +231,32 @@ def test_mlp_discriminator_config1(sb, dropout):
     if dropout:
         with pytest.raises(NotImplementedError):
             sb.strain_batch(d.train(), x.cuda())
+
+
+def test_integration_md_ctypes_stub(golden, netD):
+    """The reference-side ctypes binding shown in INTEGRATION.md §2 is executed verbatim (raw C ABI,
+    without the strainer_b200 Python package) and must reproduce the reference's result."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "ctypes.CDLL" in b]
+    assert len(blocks) == 1
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        exec(compile(blocks[0], "INTEGRATION.md", "exec"), ns)
+        x = torch.from_numpy(O.synth_images(0, 160))
+        ds = torch.utils.data.TensorDataset(x, torch.zeros(160, dtype=torch.long))
+        sub, thr = ns["refine_dataset_by_loss"](ds, netD, "cuda:0", 0.2)
+    finally:
+        os.chdir(cwd)
+    wthr = golden["g1a_threshold"]
+    assert abs(thr - wthr) <= 1e-3 * abs(wthr)
+    got = np.zeros(160, bool)
+    got[np.asarray(sub.indices)] = True
+    want = np.zeros(160, bool)
+    want[golden["g1a_indices"]] = True
+    near = np.abs(golden["g1_losses"] - wthr) <= 1e-3 * abs(wthr)
+    assert not ((got != want) & ~near).any()
