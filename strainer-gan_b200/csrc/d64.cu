@@ -796,6 +796,247 @@ conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
+// L1 fused with the input conversion: the fp32 NCHW image is the only HBM read (49 152 B/sample), no
+// bf16 staging copy.  One tile = 4 output rows x 32 cols of one image:
+//   warp 0    : TMA producer, fp32 box [3 ch][10 input rows][64 cols] (rows -1 / 64 zero-filled by TMA)
+//   warps 6-9 : converters, one output pixel per thread: 4 x (LDS.64 + 2 shuffles) per channel give the
+//               4x4x3 patch, packed to the K-major SWIZZLE_32B bf16 operand (K = kh | kw, c4) of the 4 kh slices
+//   warp 1    : tcgen05.mma issuer (M = 128, N = 64, 4 x K = 16; 12 MMAs in fp32-parity mode)
+//   warps 2-5 : epilogue, TMEM -> LeakyReLU -> bf16 -> swizzled staging -> TMA store into act1 planes
+// ------------------------------------------------------------------------------------------
+template <int SEGA>
+struct Conv1FCfg {
+  static constexpr int kRawBytes = 3 * 10 * 64 * 4;   // one fp32 input box
+  static constexpr int kRawStride = 8192;
+  static constexpr int kRawStages = 3;
+  static constexpr int kSliceA = 128 * 32;
+  static constexpr int kSliceB = 64 * 32;
+  static constexpr int kAStage = SEGA * 4 * kSliceA;
+  static constexpr int kAStages = 2;
+  static constexpr int kBBytes = SEGA * 4 * kSliceB;
+  static constexpr int kTmemCols = 128;
+  static constexpr int kStageOut = SEGA * 128 * 128;
+  static constexpr int kSmemBytes = kAStages * kAStage + kBBytes + 2 * kStageOut + kRawStages * kRawStride + 256 + 1024;
+  static constexpr int kThreads = 320;
+};
+
+template <int SEGA>
+__global__ void __launch_bounds__(320, SEGA == 1 ? 2 : 1)
+conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_o, int total_tiles, int* err) {
+  using Cfg = Conv1FCfg<SEGA>;
+  constexpr int SA = Cfg::kAStages, SR = Cfg::kRawStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + SA * Cfg::kAStage;
+  const uint32_t o_base = b_base + Cfg::kBBytes;
+  const uint32_t r_base = o_base + 2 * Cfg::kStageOut;
+  const uint32_t bar0 = r_base + SR * Cfg::kRawStride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto rfull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto rempty_bar = [&](int s) { return bar0 + 8u * (SR + s); };
+  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * SR + s); };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * SR + SA + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SR + 2 * SA + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SR + 2 * SA + 2 + a); };
+  constexpr int kNb = 2 * SR + 2 * SA + 4;
+  const uint32_t wbar = bar0 + 8u * kNb;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb + 1);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_b);
+    prefetch_tensormap(&tmap_o);
+    for (int s = 0; s < SR; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 128); }
+    for (int s = 0; s < SA; ++s) { mbar_init(afull_bar(s), 128); mbar_init(aempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int sg_ = 0; sg_ < SEGA; ++sg_)
+        for (int kh = 0; kh < 4; ++kh)
+          tma_load_2d(b_base + (sg_ * 4 + kh) * Cfg::kSliceB, &tmap_b, wbar, sg_ * 64 + kh * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile >> 3, oh0 = (tile & 7) << 2;
+        if (!mbar_wait(rempty_bar(stage), phase ^ 1u, s_abort, err, kErrProducer + 10)) break;
+        mbar_arrive_expect_tx(rfull_bar(stage), Cfg::kRawBytes);
+        tma_load_4d(r_base + stage * Cfg::kRawStride, &tmap_x, rfull_bar(stage), 0, 2 * oh0 - 1, 0, n);
+        if (++stage == SR) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrMma + 10);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrMmaAcc + 10)) break;
+        if (!mbar_wait(afull_bar(stage), phase, s_abort, err, kErrMma + 10)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+        const uint32_t sa = base + stage * Cfg::kAStage;
+#pragma unroll
+        for (int kh = 0; kh < 4; ++kh) {
+          const uint64_t a_hi = umma_desc_sw32(sa + kh * Cfg::kSliceA);
+          const uint64_t b_hi = umma_desc_sw32(b_base + kh * Cfg::kSliceB);
+          umma_f16(tmem_d, a_hi, b_hi, idesc, (uint32_t)(kh != 0));
+          if (SEGA == 2) {
+            const uint64_t a_lo = umma_desc_sw32(sa + (4 + kh) * Cfg::kSliceA);
+            const uint64_t b_lo = umma_desc_sw32(b_base + (4 + kh) * Cfg::kSliceB);
+            umma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
+            umma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
+          }
+        }
+        umma_commit(aempty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == SA) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 6) {
+    // ================= converters: fp32 patch -> bf16 K-major SW32 operand rows =================
+    const int ohl = warp - 6, ow = lane;
+    const int m = ohl * 32 + ow;
+    const uint32_t row_off = (uint32_t)m * 32u;
+    const uint32_t c0off = (uint32_t)(((m >> 2) & 1) << 4);   // SWIZZLE_32B: 16-B chunk ^= address bit 7
+    int rs = 0, as = 0;
+    uint32_t rphase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (!mbar_wait(rfull_bar(rs), rphase, s_abort, err, kErrProducer + 30)) break;
+      if (!mbar_wait(aempty_bar(as), aphase ^ 1u, s_abort, err, kErrProducer + 31)) break;
+      const uint32_t raw = r_base + rs * Cfg::kRawStride + (uint32_t)(ow * 8);
+      const uint32_t dst = base + as * Cfg::kAStage + row_off;
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh) {
+        float px[4][3];   // [kw][c]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float2 v = ld_shared_f2(raw + (uint32_t)(((c * 10 + 2 * ohl + kh) * 64) * 4));
+          float l = __shfl_up_sync(0xffffffffu, v.y, 1);
+          float r = __shfl_down_sync(0xffffffffu, v.x, 1);
+          if (ow == 0) l = 0.f;     // input column -1
+          if (ow == 31) r = 0.f;    // input column 64
+          px[0][c] = l; px[1][c] = v.x; px[2][c] = v.y; px[3][c] = r;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(px[kw][0]), h1 = __float2bfloat16_rn(px[kw][1]),
+                              h2 = __float2bfloat16_rn(px[kw][2]);
+          hi[2 * kw] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          hi[2 * kw + 1] = (uint32_t)__bfloat16_as_ushort(h2);
+          if (SEGA == 2) {
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(px[kw][0] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(px[kw][1] - __bfloat162float(h1));
+            const __nv_bfloat16 l2 = __float2bfloat16_rn(px[kw][2] - __bfloat162float(h2));
+            lo[2 * kw] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            lo[2 * kw + 1] = (uint32_t)__bfloat16_as_ushort(l2);
+          }
+        }
+        const uint32_t d = dst + (uint32_t)(kh * Cfg::kSliceA);
+        st_shared_v4(d + c0off, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(d + (c0off ^ 16u), hi[4], hi[5], hi[6], hi[7]);
+        if (SEGA == 2) {
+          st_shared_v4(d + 4 * Cfg::kSliceA + c0off, lo[0], lo[1], lo[2], lo[3]);
+          st_shared_v4(d + 4 * Cfg::kSliceA + (c0off ^ 16u), lo[4], lo[5], lo[6], lo[7]);
+        }
+      }
+      mbar_arrive(rempty_bar(rs));       // every LDS of this box has been consumed by the stores above
+      fence_proxy_async_smem();          // generic-proxy operand writes -> visible to tcgen05.mma
+      mbar_arrive(afull_bar(as));
+      if (++rs == SR) { rs = 0; rphase ^= 1u; }
+      if (++as == SA) { as = 0; aphase ^= 1u; }
+    }
+  } else {
+    // ================= epilogue (warps 2..5): as conv1_umma_kernel =================
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int ohl = row >> 5, ow = row & 31;
+    const int prow = (((ohl & 1) * 2 + (ow & 1)) << 5) + ((ohl >> 1) << 4) + (ow >> 1);
+    const uint32_t swz = (uint32_t)(prow & 7);
+    const bool issuer = (threadIdx.x == 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n = tile >> 3, oh0 = (tile & 7) << 2;
+      const uint32_t stg = o_base + (uint32_t)(it & 1) * Cfg::kStageOut;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrEpilogue + 10)) break;
+      tc_fence_after();
+      if (issuer) tma_store_wait_read<1>();
+      named_bar_sync(1, 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int cb = 0; cb < 64; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+          a = a > 0.f ? a : 0.2f * a;
+          b = b > 0.f ? b : 0.2f * b;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
+          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
+          if (SEGA == 2) {
+            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
+            lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+          }
+        }
+        const uint32_t rbase = stg + (uint32_t)prow * 128u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)((cb >> 3) + q) ^ swz;
+          st_shared_v4(rbase + chunk * 16u, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (SEGA == 2)
+            st_shared_v4(rbase + 128u * 128u + chunk * 16u, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer) {
+#pragma unroll
+        for (int sg_ = 0; sg_ < SEGA; ++sg_)
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl)
+            tma_store_5d(&tmap_o, stg + (uint32_t)(sg_ * 128 * 128 + pl * 4096), sg_ * 64, 0, oh0 >> 1, pl, n);
+        tma_store_commit();
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Train-mode BatchNorm (in-batch strain, "# 상위 10% 제거해서 fake image에 concate.py:244-245": the
 // reference scores with netD in TRAIN mode under no_grad, so BN normalises with batch statistics
 // and updates running_mean / running_var).  The conv kernels write the raw conv
@@ -963,10 +1204,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int encode(CUtensorMap* m, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                  const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(state().encode_tiled);
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1075,6 +1317,42 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
 }
 
 template <int SEGA>
+static int launch_conv1_fused(const float* x, const __nv_bfloat16* w1t, __nv_bfloat16* act1, int64_t batch, int* err,
+                              cudaStream_t stream) {
+  using Cfg = Conv1FCfg<SEGA>;
+  CUtensorMap tx, tb, to;
+  {
+    // fp32 NCHW input: (w, h, c, n); box = all 64 columns x 10 rows x 3 channels of one image
+    cuuint64_t dims[4] = {64, 64, 3, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {64 * 4, 64 * 64 * 4, 3 * 64 * 64 * 4};
+    cuuint32_t box[4] = {64, 10, 3, 1};
+    int r = encode(&tx, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    if (r != SG_OK) return r;
+  }
+  {
+    cuuint64_t dims[2] = {128, 64};
+    cuuint64_t strides[1] = {128 * 2};
+    cuuint32_t box[2] = {16, 64};
+    int r = encode(&tb, 2, w1t, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+  }
+  {
+    const cuuint64_t ct = 64 * SEGA;
+    cuuint64_t dims[5] = {ct, 16, 16, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {ct * 2, 16 * ct * 2, 256 * ct * 2, 1024 * ct * 2};
+    cuuint32_t box[5] = {64, 16, 2, 1, 1};
+    int r = encode(&to, 5, act1, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  const int64_t tiles = batch * 8;
+  const int64_t ctas = (int64_t)state().sm_count * (SEGA == 1 ? 2 : 1);
+  int grid = (int)(tiles < ctas ? tiles : ctas);
+  conv1_fused_kernel<SEGA><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tx, tb, to, (int)tiles, err);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+template <int SEGA>
 static int launch_conv1(const float* x, __nv_bfloat16* act0, const __nv_bfloat16* w1t, __nv_bfloat16* act1,
                         int64_t batch, int* err, cudaStream_t stream) {
   using Cfg = Conv1Cfg<SEGA>;
@@ -1134,6 +1412,10 @@ int sg_d64_init_attributes() {
                                Conv1Cfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1Cfg<2>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Conv1FCfg<1>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Conv1FCfg<2>::kSmemBytes));
   return SG_OK;
 }
 
@@ -1210,6 +1492,9 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
         SG_LAUNCH_CHECK();
         return SG_OK;
       }
+      if (!getenv("SG_CONV1_STAGED"))  // default: fp32 input converted inside the kernel
+        return (W.sega == 2) ? launch_conv1_fused<2>(x, wq(P.w1t), act1, batch, err, st)
+                             : launch_conv1_fused<1>(x, wq(P.w1t), act1, batch, err, st);
       return (W.sega == 2) ? launch_conv1<2>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st)
                            : launch_conv1<1>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st);
     case 2:
