@@ -106,8 +106,50 @@ __device__ __forceinline__ int block_excl_scan(int c, int* s_warp, int* total) {
 constexpr int kBigItems = 64;
 constexpr int kCiThreads = 256;
 constexpr int kBigTile = kCiThreads * kBigItems;  // 16384
+
+template <int CMP>
+__device__ __forceinline__ bool cmp_static(float v, float thr) {
+  bool r;
+  if ((CMP & 3) == SG_LT) r = v < thr;
+  else if ((CMP & 3) == SG_LE) r = v <= thr;
+  else if ((CMP & 3) == SG_GE) r = v >= thr;
+  else r = v > thr;
+  return (CMP & SG_NOT) ? !r : r;
+}
+// predicated 64-bit store (no branch around it: the SASS is one @P STG instead of BSSY/BRA/STG/BSYNC)
+__device__ __forceinline__ void st_if_u64(int64_t* p, int64_t v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u64 [%0], %1;\n\t}"
+               :: "l"(p), "l"(v), "r"((uint32_t)pred) : "memory");
+}
+
+// keep-bits of the 64 slots of one lane (slot j = element wbase + j*32 + lane)
+template <int CMP, bool FULL>
+__device__ __forceinline__ unsigned long long ci_keep_bits(const float* __restrict__ v, int64_t wbase, int64_t n,
+                                                           float thr, int lane) {
+  const float* p = v + wbase + lane;
+  uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+  for (int g = 0; g < kBigItems / 16; ++g) {
+    float x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int s = g * 16 + j;
+      x[j] = (FULL || wbase + s * 32 + lane < n) ? __ldg(p + s * 32) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int s = g * 16 + j;
+      const bool keep = (FULL || wbase + s * 32 + lane < n) && cmp_static<CMP>(x[j], thr);
+      if (s < 32) lo |= (uint32_t)keep << s;
+      else hi |= (uint32_t)keep << (s - 32);
+    }
+  }
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int CMP, bool MASK>
 __global__ void __launch_bounds__(kCiThreads) compact_indices_kernel(const float* __restrict__ v, int64_t n,
-                                                                   const float* __restrict__ thr_p, int cmp,
+                                                                   const float* __restrict__ thr_p,
                                                                    int64_t index_base, int64_t* __restrict__ idx_out,
                                                                    int64_t* __restrict__ count_out,
                                                                    uint8_t* __restrict__ mask_out, ScanWs* ws,
@@ -123,24 +165,12 @@ __global__ void __launch_bounds__(kCiThreads) compact_indices_kernel(const float
   __syncthreads();
   const int tile = s_tile;
   const int64_t wbase = (int64_t)tile * kBigTile + w * (kBigItems * 32);
-  unsigned long long bits = 0ull;
-  int wtotal = 0;
   const bool full = wbase + kBigItems * 32 <= n;
+  const unsigned long long bits = full ? ci_keep_bits<CMP, true>(v, wbase, n, thr, lane)
+                                       : ci_keep_bits<CMP, false>(v, wbase, n, thr, lane);
+  int wtotal = __popcll(bits);
 #pragma unroll
-  for (int g = 0; g < kBigItems / 16; ++g) {
-    float x[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int64_t i = wbase + (g * 16 + j) * 32 + lane;
-      x[j] = (full || i < n) ? __ldg(v + i) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const bool keep = (full || wbase + (g * 16 + j) * 32 + lane < n) && cmp_apply(x[j], thr, cmp);
-      wtotal += __popc(__ballot_sync(0xffffffffu, keep));
-      bits |= (unsigned long long)keep << (g * 16 + j);
-    }
-  }
+  for (int o = 16; o > 0; o >>= 1) wtotal += __shfl_xor_sync(0xffffffffu, wtotal, o);
   if (lane == 0) s_wtot[w] = wtotal;
   __syncthreads();
   int woff = 0, total = 0;
@@ -153,14 +183,16 @@ __global__ void __launch_bounds__(kCiThreads) compact_indices_kernel(const float
   const unsigned long long excl = lookback(status, tile, (unsigned long long)total, &s_excl);
   int64_t* dst = idx_out + excl + woff;
   const int64_t gidx = index_base + wbase + lane;
-#pragma unroll 16
+  const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
+  int o = 0;
+#pragma unroll
   for (int j = 0; j < kBigItems; ++j) {
-    const bool keep = (bits >> j) & 1ull;
+    const bool keep = (((j < 32) ? blo : bhi) >> (j & 31)) & 1u;
     const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (keep) dst[__popc(m & lt)] = gidx + j * 32;
-    dst += __popc(m);
+    st_if_u64(dst + (o + __popc(m & lt)), gidx + j * 32, keep);
+    o += __popc(m);
   }
-  if (mask_out) {
+  if (MASK) {
 #pragma unroll 16
     for (int j = 0; j < kBigItems; ++j) {
       const int64_t i = wbase + j * 32 + lane;
@@ -168,6 +200,18 @@ __global__ void __launch_bounds__(kCiThreads) compact_indices_kernel(const float
     }
   }
   if (tile == num_tiles - 1 && threadIdx.x == 0) *count_out = (int64_t)(excl + total);
+}
+
+template <int CMP>
+static void launch_compact_indices(int grid, cudaStream_t st, const float* v, int64_t n, const float* thr,
+                                   int64_t index_base, int64_t* idx_out, int64_t* count_out, uint8_t* mask_out,
+                                   ScanWs* ws, int num_tiles) {
+  if (mask_out)
+    compact_indices_kernel<CMP, true><<<grid, kCiThreads, 0, st>>>(v, n, thr, index_base, idx_out, count_out, mask_out, ws,
+                                                                 num_tiles);
+  else
+    compact_indices_kernel<CMP, false><<<grid, kCiThreads, 0, st>>>(v, n, thr, index_base, idx_out, count_out, mask_out, ws,
+                                                                  num_tiles);
 }
 
 // Stable two-way partition destinations from a byte mask: dest[i] = rank among kept rows (mask != 0)
@@ -279,8 +323,13 @@ int sg_compact_indices(const float* v, int64_t n, const float* thr, int cmp, int
   const int num_tiles = (int)sg::ceil_div(n, kBigTile);
   SG_CUDA(cudaMemsetAsync(workspace, 0, sizeof(ScanWs) + (size_t)num_tiles * 8, st));
   const int grid = num_tiles;  // one CTA per tile; ids come from the atomic counter in launch order
-  compact_indices_kernel<<<grid, kCiThreads, 0, st>>>(v, n, thr, cmp, index_base, idx_out, count_out, mask_out,
-                                                    static_cast<ScanWs*>(workspace), num_tiles);
+  ScanWs* sws = static_cast<ScanWs*>(workspace);
+  switch (cmp) {
+#define SG_CI_CASE(C) case C: launch_compact_indices<C>(grid, st, v, n, thr, index_base, idx_out, count_out, mask_out, sws, num_tiles); break;
+    SG_CI_CASE(0) SG_CI_CASE(1) SG_CI_CASE(2) SG_CI_CASE(3) SG_CI_CASE(4) SG_CI_CASE(5) SG_CI_CASE(6) SG_CI_CASE(7)
+#undef SG_CI_CASE
+    default: break;
+  }
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -16,7 +16,9 @@ METRICS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
     "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-    "smsp__cycles_active.avg", "sm__cycles_active.avg",
+    "smsp__cycles_active.avg", "sm__cycles_active.avg", "smsp__inst_executed.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
 ]
 
 
@@ -37,17 +39,27 @@ def launches(path):
         print(f"{v[1]:12.1f} {v[0]:8d} {100*v[1]/tot:6.1f}% {v[1]/v[0]:10.1f}  {k[:110]}")
 
 
-def full(path):
+def full(path, every=False):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ni = hdr.index("Kernel Name")
+    seen = set()
     for r in rows[2:]:
+        if r[ni] in seen and not every:   # one instance per kernel name (repeats of a timing loop are identical)
+            continue
+        seen.add(r[ni])
         print("kernel:", r[ni])
         for m in METRICS:
             if m in hdr:
                 i = hdr.index(m)
                 print(f"  {m:75s} {r[i]:>18s} {units[i]}")
+        stalls = []
+        for i, h in enumerate(hdr):
+            if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h and r[i]:
+                stalls.append((float(r[i].replace(",", "")), h.split("issue_stalled_")[1].split("_per_issue")[0]))
+        print("  warp stall reasons (warps per issue-active cycle):",
+              ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:6]))
         print()
 
 
