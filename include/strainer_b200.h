@@ -136,8 +136,18 @@ int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stre
 int sg_select_step(uint32_t* ws, int pass, void* stream);
 /* out2[0] = x_(k), out2[1] = x_(k+1) (== x_(k) when k is the last index); NaN if any NaN. */
 int sg_select_finish(const uint32_t* ws, float* out2, void* stream);
-/* single-device convenience: all phases back to back */
+/* single-device convenience: all phases back to back (each histogram pass ends with its own bucket step,
+ * run by the last CTA to finish: 4 + 2 launches) */
 int sg_radix_select(const float* v, int64_t n, int64_t k, uint32_t* ws, float* out2, void* stream);
+/* One-pass selection for large n (>= SG_SELECT_ONEPASS_MIN): two pivots from a 32768-element sample, ONE
+ * streaming read of v that counts the elements below the lower pivot and collects the ~3 % between the pivots,
+ * then the radix passes over that small buffer.  Always exact: if the pivots miss x_(k)/x_(k+1) or the buffer
+ * overflows (heavy ties) the radix passes run over v itself.  workspace: sg_select_workspace_bytes(n) bytes,
+ * 16-byte aligned; with a smaller workspace (>= 2 KB) it degrades to sg_radix_select. */
+#define SG_SELECT_ONEPASS_MIN (1 << 21)
+size_t sg_select_workspace_bytes(int64_t n);
+int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t workspace_bytes, float* out2,
+                  void* stream);
 /* thr[0] = lerp(stats2[0], stats2[1], weight) with the named rounding rule */
 int sg_lerp_threshold(const float* stats2, float weight, int lerp_kind, float* thr, void* stream);
 /* Segmented in-block quantile: `segments` consecutive segments of `seg_len` (<= 2048) values each;

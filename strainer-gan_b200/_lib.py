@@ -43,6 +43,8 @@ _SIGS = {
     "sg_select_step": (c_int, [P, c_int, P]),
     "sg_select_finish": (c_int, [P, P, P]),
     "sg_radix_select": (c_int, [P, c_int64, c_int64, P, P, P]),
+    "sg_select_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_select_kth": (c_int, [P, c_int64, c_int64, P, c_size_t, P, P]),
     "sg_lerp_threshold": (c_int, [P, c_float, c_int, P, P]),
     "sg_segment_order_stats": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "sg_compact_workspace_bytes": (c_size_t, [c_int64]),

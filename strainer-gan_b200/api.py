@@ -121,12 +121,15 @@ def order_stats(values: torch.Tensor, k: int, group=None, ops=None) -> torch.Ten
     smallest key above the selected bucket with MIN, so every rank derives bit-identical statistics."""
     device = values.device
     n = values.numel()
-    ws = torch.empty(L.SG_SELECT_WS_WORDS, dtype=torch.int32, device=device)
     out2 = torch.empty(2, dtype=torch.float32, device=device)
     if group is None and ops is None:
+        # single device: one streaming read for large n (sampled pivots), fused radix passes otherwise
         lib = _lib_for(device)
-        L.check(lib.sg_radix_select(_p(values), n, k, _p(ws), _p(out2), _stream()), "sg_radix_select")
+        nbytes = int(lib.sg_select_workspace_bytes(n))
+        ws = _Scratch.get(device, "select", nbytes)
+        L.check(lib.sg_select_kth(_p(values), n, k, _p(ws), nbytes, _p(out2), _stream()), "sg_select_kth")
         return out2
+    ws = torch.empty(L.SG_SELECT_WS_WORDS, dtype=torch.int32, device=device)
     import torch.distributed as dist
     ops = ops or _SelectOps(device)
     ops.begin(ws, k)

@@ -108,9 +108,7 @@ __device__ __forceinline__ void stg_stream_i4(int4* p, const int4& v) {
 // thread and consecutive threads on consecutive 16-B chunks (HBM-bound kernels: enough bytes in flight
 // to cover the DRAM latency).  Visit ORDER is unspecified: only for order-independent reductions.
 template <int U, typename F>
-__device__ __forceinline__ void stream_f32(const float* __restrict__ v, int64_t n, F&& f) {
-  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void stream_f32_grid(const float* __restrict__ v, int64_t n, int64_t gtid, int64_t gsz, F&& f) {
   if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
     const int64_t n4 = n >> 2;
     const float4* v4 = reinterpret_cast<const float4*>(v);
@@ -134,6 +132,10 @@ __device__ __forceinline__ void stream_f32(const float* __restrict__ v, int64_t 
   } else {
     for (int64_t e = gtid; e < n; e += gsz) f(v[e], e);
   }
+}
+template <int U, typename F>
+__device__ __forceinline__ void stream_f32(const float* __restrict__ v, int64_t n, F&& f) {
+  stream_f32_grid<U>(v, n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, f);
 }
 
 template <typename T>

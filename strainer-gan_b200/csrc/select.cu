@@ -5,6 +5,8 @@
 // one more pass finds x_(k+1) as the smallest key above it, and a one-thread kernel applies the
 // library's interpolation rule with the same rounding steps.  Integer histograms make the result
 // independent of summation order, hence bit-identical under any sharding.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace sg {
@@ -16,6 +18,20 @@ constexpr int W_KREM_LO = 262;     // remaining rank inside the current bucket (
 constexpr int W_SELKEY = 264;      // final key of x_(k)
 constexpr int W_NEEDNEXT = 265;    // 1: x_(k+1) has a larger key than x_(k)
 constexpr int W_NEXTIN = 266;     // smallest populated last-pass digit above the selected one (or ~0)
+// one-pass (sampled) selection state
+constexpr int W_LO_F = 270;        // float bits of the lower pivot (canonical, -inf when open)
+constexpr int W_HI_F = 271;        // float bits of the upper pivot (+inf when open)
+constexpr int W_BELOW = 272;       // u64: elements < lower pivot
+constexpr int W_CAND = 274;        // u64: elements in [lower, upper] = append cursor of the candidate buffer
+constexpr int W_NANF = 276;        // NaNs seen by the filter pass
+constexpr int W_OVERFLOW = 277;    // candidate buffer overflowed
+constexpr int W_TICKET = 278;      // CTAs of the filter pass that are done
+constexpr int W_USECAND = 279;     // 1: the radix passes run over the candidate buffer with the reduced rank
+constexpr int W_TICKET_PASS = 280; // [4] CTAs done per fused histogram pass
+constexpr int W_TICKET_SAMPLE = 284; // CTAs of the sampling kernel that are done
+constexpr int kSampleCount = 32768;
+constexpr int kSampleThreads = 1024;
+constexpr int kSampleSmem = (kSampleCount + 2 * 256 * 32) * 4;   // keys + lane-private histograms of both pivots
 
 // Pass plan: 4 x 8 bits.  Loss vectors are heavily skewed in their top bits (a handful of exponents),
 // so a shared histogram serialises on same-address atomics.  With 256 bins the histogram fits in 32
@@ -32,51 +48,284 @@ __global__ void begin_kernel(uint32_t* ws, unsigned long long k) {
   }
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws) {
+__device__ __forceinline__ void step_body(uint32_t* ws, int pass);
+
+__device__ __forceinline__ void finish_body(const uint32_t* ws, float* out2);
+
+// FUSED: single-device form.  The source may be redirected to the candidate buffer of the one-pass filter
+// (ws[W_USECAND]; only as many CTAs as that buffer needs do any work), the LAST CTA to finish runs the bucket
+// step itself (no separate step launch) and, after the last pass, writes the two order statistics.
+template <int PASS, bool FUSED>
+__global__ void __launch_bounds__(512, 4) hist_kernel(const float* __restrict__ v, int64_t n, const float* __restrict__ cand,
+                                                   uint32_t* __restrict__ ws, float* __restrict__ out2) {
   __shared__ uint32_t s_hist[256 * 32];
   __shared__ uint32_t s_nan, s_min;
-  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_hist[i] = 0u;
-  if (threadIdx.x == 0) { s_nan = 0u; s_min = 0xFFFFFFFFu; }
-  __syncthreads();
-  const uint32_t prefix = ws[W_PREFIX];
-  const uint32_t lane = threadIdx.x & 31;
-  constexpr int kShift = 24 - 8 * PASS;   // digit position
-  uint32_t nan_local = 0, min_local = 0xFFFFFFFFu;
-  stream_f32<4>(v, n, [&](float f, int64_t) {
-    const uint32_t key = float_to_key(f);
-    if constexpr (PASS == 0) {
-      nan_local += (key == 0xFFFFFFFFu);
-      atomicAdd(&s_hist[((key >> 24) << 5) + lane], 1u);
-    } else {
-      const uint32_t hi = key >> (kShift + 8);
-      if (hi == prefix) atomicAdd(&s_hist[(((key >> kShift) & 255u) << 5) + lane], 1u);
-      if (PASS == 3 && hi > prefix) min_local = min(min_local, key);
-    }
-  });
-  if (PASS == 0 && nan_local) atomicAdd(&s_nan, nan_local);
-  if (PASS == 3 && min_local != 0xFFFFFFFFu) atomicMin(&s_min, min_local);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) c += s_hist[i * 32 + ((k + i) & 31)];
-    if (c) atomicAdd(&ws[SG_SELECT_WS_HIST + i], c);
+  __shared__ int s_last;
+  int64_t eff_grid = gridDim.x;
+  if (FUSED && cand != nullptr && ws[W_USECAND] != 0u) {
+    v = cand;
+    n = (int64_t)*reinterpret_cast<const unsigned long long*>(ws + W_CAND);
+    eff_grid = min((int64_t)gridDim.x, max((int64_t)1, (n + 16383) >> 14));
   }
-  if (PASS == 0 && threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
-  if (PASS == 3 && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], s_min);
+  if (blockIdx.x < eff_grid) {
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_hist[i] = 0u;
+    if (threadIdx.x == 0) { s_nan = 0u; s_min = 0xFFFFFFFFu; }
+    __syncthreads();
+    const uint32_t prefix = ws[W_PREFIX];
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int kShift = 24 - 8 * PASS;   // digit position
+    uint32_t nan_local = 0, min_local = 0xFFFFFFFFu;
+    stream_f32_grid<4>(v, n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, eff_grid * blockDim.x, [&](float f, int64_t) {
+      const uint32_t key = float_to_key(f);
+      if constexpr (PASS == 0) {
+        nan_local += (key == 0xFFFFFFFFu);
+        atomicAdd(&s_hist[((key >> 24) << 5) + lane], 1u);
+      } else {
+        const uint32_t hi = key >> (kShift + 8);
+        if (hi == prefix) atomicAdd(&s_hist[(((key >> kShift) & 255u) << 5) + lane], 1u);
+        if (PASS == 3 && hi > prefix) min_local = min(min_local, key);
+      }
+    });
+    if (PASS == 0 && nan_local) atomicAdd(&s_nan, nan_local);
+    if (PASS == 3 && min_local != 0xFFFFFFFFu) atomicMin(&s_min, min_local);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) c += s_hist[i * 32 + ((k + i) & 31)];
+      if (c) atomicAdd(&ws[SG_SELECT_WS_HIST + i], c);
+    }
+    if (PASS == 0 && threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
+    if (PASS == 3 && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], s_min);
+  }
+  if (FUSED) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ws[W_TICKET_PASS + PASS], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      step_body(ws, PASS);
+      if (PASS == 3) {
+        __syncthreads();
+        if (threadIdx.x == 0) finish_body(ws, out2);
+      }
+    }
+  }
+}
+
+// ---- one-pass selection ---------------------------------------------------------------------------
+// SURVEY §8(d) counts ONE 4-byte read per element for the global select.  A radix select needs the bucket of
+// pass p before it can run pass p+1, i.e. four full reads.  Instead: (1) one CTA draws kSampleCount samples
+// at pseudo-random offsets of equal strides and radix-selects two pivots lo <= x_(k) <= x_(k+1) <= hi from them
+// (ranks k*S/n -+ 5 sigma of the binomial spread), (2) ONE streaming pass counts the elements below lo and
+// appends the elements of [lo, hi] (~3 % of n) to a candidate buffer (warp-private shared staging, one global
+// atomic per 128 candidates), (3) the last CTA verifies that both order statistics lie inside the candidates
+// and switches the four radix passes to that (L2-resident) buffer with the reduced rank.  If the check fails
+// (pivots missed, heavy ties overflowing the buffer) the radix passes run over the full input: always exact.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_pivot_kernel(const float* __restrict__ v, int64_t n,
+                                                                      uint32_t* __restrict__ ws, uint32_t* __restrict__ skeys,
+                                                                      uint32_t* __restrict__ ticket, unsigned long long k,
+                                                                      int r_lo, int r_hi) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_keys = s_dyn;                        // kSampleCount keys
+  uint32_t* s_h = s_dyn + kSampleCount;            // [2 targets][256 bins][32 lane-private copies]
+  __shared__ uint32_t s_c[2][256];
+  __shared__ uint32_t s_prefix[2], s_krem[2];
+  __shared__ int s_last;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // every CTA draws kSampleThreads samples (one DRAM sector each: spread over many SMs, a single SM cannot keep
+  // 32768 sector misses in flight); the last CTA to finish selects the pivots
+  const int64_t stride = n / kSampleCount;        // >= 64 (callers use this path for n >= 2^21 only)
+  {
+    const int s = blockIdx.x * kSampleThreads + t;
+    skeys[s] = float_to_key(__ldg(v + (int64_t)s * stride + (int64_t)(mix32((uint32_t)s) % (uint32_t)stride)));
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = t; i < SG_SELECT_WS_WORDS; i += kSampleThreads) ws[i] = 0u;   // also resets the ticket
+#pragma unroll 8
+  for (int j = 0; j < kSampleCount / kSampleThreads; ++j) s_keys[j * kSampleThreads + t] = __ldcg(skeys + j * kSampleThreads + t);
+  if (t < 2) { s_prefix[t] = 0u; s_krem[t] = (uint32_t)(t == 0 ? max(r_lo, 0) : min(r_hi, kSampleCount - 1)); }
+  __syncthreads();
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const uint32_t p0 = s_prefix[0], p1 = s_prefix[1];
+    const bool same = (p0 == p1);                  // both targets still in the same bucket: one histogram serves both
+    for (int i = t; i < (same ? 1 : 2) * 256 * 32; i += kSampleThreads) s_h[i] = 0u;
+    __syncthreads();
+    const int shift = 24 - 8 * pass;
+#pragma unroll 4
+    for (int s = t; s < kSampleCount; s += kSampleThreads) {
+      const uint32_t key = s_keys[s];
+      const uint32_t hi = (pass == 0) ? 0u : (key >> (shift + 8));
+      const uint32_t d = ((key >> shift) & 255u) * 32u + lane;
+      if (hi == p0) atomicAdd(&s_h[d], 1u);
+      if (!same && hi == p1) atomicAdd(&s_h[256 * 32 + d], 1u);
+    }
+    __syncthreads();
+    if (t < (same ? 256 : 512)) {
+      const uint32_t* h = s_h + (t >> 8) * 256 * 32 + (t & 255) * 32;
+      uint32_t c = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) c += h[(j + t) & 31];
+      s_c[t >> 8][t & 255] = c;
+    }
+    __syncthreads();
+    if (w < 2) {   // warp q narrows target q: 8 bins per lane
+      const uint32_t* cc = s_c[same ? 0 : w];
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = cc[lane * 8 + j]; sum += c[j]; }
+      uint32_t x = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      uint32_t run = x - sum;
+      const uint32_t kr = s_krem[w];
+      if (kr >= run && kr < run + sum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kr >= run && kr < run + c[j]) { s_prefix[w] = (s_prefix[w] << 8) | (uint32_t)(lane * 8 + j); s_krem[w] = kr - run; }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    ws[SG_SELECT_WS_MINABOVE] = 0xFFFFFFFFu;
+    ws[W_NEXTIN] = 0xFFFFFFFFu;
+    *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO) = k;
+    // NaN keys in the sample sort last: a NaN pivot opens that side
+    const uint32_t klo = s_prefix[0], khi = s_prefix[1];
+    ws[W_LO_F] = (r_lo < 0 || klo == 0xFFFFFFFFu) ? 0xFF800000u : __float_as_uint(key_to_float(klo));
+    ws[W_HI_F] = (r_hi >= kSampleCount || khi == 0xFFFFFFFFu) ? 0x7F800000u : __float_as_uint(key_to_float(khi));
+  }
+}
+
+constexpr int kFilterThreads = 512;
+constexpr int kStage = 256;   // staged candidates per warp (flush at >= 128: one global atomic per >= 128 candidates)
+__global__ void __launch_bounds__(kFilterThreads) filter_kernel(const float* __restrict__ v, int64_t n,
+                                                                float* __restrict__ cand, unsigned long long cap,
+                                                                uint32_t* __restrict__ ws, unsigned long long k) {
+  __shared__ float s_stage[kFilterThreads / 32][kStage];
+  __shared__ unsigned long long s_below;
+  __shared__ uint32_t s_nan;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const float lo = __uint_as_float(ws[W_LO_F]), hi = __uint_as_float(ws[W_HI_F]);
+  if (threadIdx.x == 0) { s_below = 0ull; s_nan = 0u; }
+  __syncthreads();
+  float* stage = s_stage[w];
+  int cnt = 0;                       // warp-uniform
+  uint32_t below = 0, nan = 0;
+  auto flush = [&]() {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned long long*>(ws + W_CAND), (unsigned long long)cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    if (base + (unsigned long long)cnt <= cap) {
+      for (int i = lane; i < cnt; i += 32) cand[base + i] = stage[i];
+    } else if (lane == 0) {
+      ws[W_OVERFLOW] = 1u;
+    }
+    __syncwarp();
+    cnt = 0;
+  };
+  auto visit = [&](float f, bool valid) {
+    below += (valid && f < lo);
+    nan += (valid && f != f);
+    const bool c = valid && f >= lo && f <= hi;
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    if (m) {
+      if (c) stage[cnt + __popc(m & lt)] = f;
+      cnt += __popc(m);
+    }
+  };
+  // warp-uniform trip counts: every lane of a warp runs the same iterations (tail lanes masked by `valid`)
+  const int64_t gwarp = (blockIdx.x * (int64_t)kFilterThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kFilterThreads) >> 5;
+  const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+  const int64_t n4 = aligned ? (n >> 2) : 0;
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  constexpr int U = 4;
+  int64_t i = gwarp * 32;            // float4 index of lane 0
+  for (; i + (U - 1) * nwarps * 32 + 32 <= n4; i += U * nwarps * 32) {
+    float4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = ldg_stream4(v4 + i + u * nwarps * 32 + lane);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      visit(q[u].x, true); visit(q[u].y, true); visit(q[u].z, true); visit(q[u].w, true);
+      if (cnt >= kStage / 2) flush();
+    }
+  }
+  for (; i < n4; i += nwarps * 32) {
+    const bool ok = i + lane < n4;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) q = ldg_stream4(v4 + i + lane);
+    visit(q.x, ok); visit(q.y, ok); visit(q.z, ok); visit(q.w, ok);
+    if (cnt >= kStage / 2) flush();
+  }
+  for (int64_t e = (n4 << 2) + gwarp * 32; e < n; e += nwarps * 32) {
+    const bool ok = e + lane < n;
+    visit(ok ? v[e + lane] : 0.f, ok);
+    if (cnt >= kStage / 2) flush();
+  }
+  if (cnt) flush();
+  below = warp_sum(below);
+  nan = warp_sum(nan);
+  if (lane == 0) {
+    if (below) atomicAdd(&s_below, (unsigned long long)below);
+    if (nan) atomicAdd(&s_nan, nan);
+  }
+  __syncthreads();
+  __shared__ int s_lastf;
+  if (threadIdx.x == 0) {
+    if (s_below) atomicAdd(reinterpret_cast<unsigned long long*>(ws + W_BELOW), s_below);
+    if (s_nan) atomicAdd(&ws[W_NANF], s_nan);
+    __threadfence();
+    s_lastf = (atomicAdd(&ws[W_TICKET], 1u) == gridDim.x - 1);
+    if (s_lastf) {
+      __threadfence();
+      const unsigned long long b = __ldcg(reinterpret_cast<unsigned long long*>(ws + W_BELOW));
+      const unsigned long long c = __ldcg(reinterpret_cast<unsigned long long*>(ws + W_CAND));
+      const uint32_t nn = __ldcg(ws + W_NANF);
+      const bool over = __ldcg(ws + W_OVERFLOW) != 0u;
+      const unsigned long long nv = (unsigned long long)n - nn;      // non-NaN elements
+      bool ok = !over && b <= k && (k + 1 < b + c || (k + 1 >= nv && k < b + c));
+      if (nn != 0u) { ok = !over; ws[SG_SELECT_WS_NANCOUNT] = nn; }    // any NaN: the result is NaN either way
+      if (ok) {
+        ws[W_USECAND] = 1u;
+        *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO) = (nn != 0u) ? 0ull : (k - b);
+      }
+    }
+  }
 }
 
 // Finds the bin holding rank k_rem among the 256 bins, narrows the prefix, clears the histogram for the
-// next pass.  One thread per bin.
-__global__ void __launch_bounds__(256) step_kernel(uint32_t* ws, int pass) {
+// next pass.  Executed by a whole CTA of >= 256 threads (thread t < 256 owns bin t).
+__device__ __forceinline__ void step_body(uint32_t* ws, int pass) {
   __shared__ unsigned long long s_warp[8];
   __shared__ unsigned long long s_before, s_cnt;
   __shared__ int s_bucket;
   __shared__ uint32_t s_next;
   const int t = threadIdx.x;
-  const unsigned long long c = ws[SG_SELECT_WS_HIST + t];
-  const unsigned long long k = *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO);
+  const bool on = t < 256;
+  const unsigned long long c = on ? __ldcg(ws + SG_SELECT_WS_HIST + t) : 0ull;
+  const unsigned long long k = __ldcg(reinterpret_cast<unsigned long long*>(ws + W_KREM_LO));
   unsigned long long x = c;
   const int lane = t & 31, w = t >> 5;
 #pragma unroll
@@ -84,21 +333,21 @@ __global__ void __launch_bounds__(256) step_kernel(uint32_t* ws, int pass) {
     const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
     if (lane >= o) x += y;
   }
-  if (lane == 31) s_warp[w] = x;
+  if (on && lane == 31) s_warp[w] = x;
   if (t == 0) { s_bucket = -1; s_next = 0xFFFFFFFFu; }
   __syncthreads();
   unsigned long long run = x - c;
-  for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
-  if (k >= run && k < run + c) { s_bucket = t; s_before = run; s_cnt = c; }
+  if (on) for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
+  if (on && k >= run && k < run + c) { s_bucket = t; s_before = run; s_cnt = c; }
   __syncthreads();
-  ws[SG_SELECT_WS_HIST + t] = 0u;
+  if (on) ws[SG_SELECT_WS_HIST + t] = 0u;
   int b = s_bucket;
-  if (pass == 3 && b >= 0 && t > b && c != 0ull) atomicMin(&s_next, (uint32_t)t);  // next populated digit in the bucket
+  if (on && pass == 3 && b >= 0 && t > b && c != 0ull) atomicMin(&s_next, (uint32_t)t);  // next populated digit in the bucket
   __syncthreads();
   if (t == 0) {
     unsigned long long before = s_before, cnt = s_cnt;
     if (b < 0) { b = 255; before = 0; cnt = 0; }  // k >= n: clamp (callers validate k < n)
-    const uint32_t prefix = (pass == 0) ? (uint32_t)b : ((ws[W_PREFIX] << 8) | (uint32_t)b);
+    const uint32_t prefix = (pass == 0) ? (uint32_t)b : ((__ldcg(ws + W_PREFIX) << 8) | (uint32_t)b);
     ws[W_PREFIX] = prefix;
     const unsigned long long krem = k - before;
     *reinterpret_cast<unsigned long long*>(ws + W_KREM_LO) = krem;
@@ -110,19 +359,23 @@ __global__ void __launch_bounds__(256) step_kernel(uint32_t* ws, int pass) {
   }
 }
 
-__global__ void finish_kernel(const uint32_t* ws, float* out2) {
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(256) step_kernel(uint32_t* ws, int pass) { step_body(ws, pass); }
+
+__device__ __forceinline__ void finish_body(const uint32_t* ws, float* out2) {
   const float nanv = __uint_as_float(0x7FC00000u);
-  if (ws[SG_SELECT_WS_NANCOUNT] != 0u) { out2[0] = nanv; out2[1] = nanv; return; }
-  const float a = key_to_float(ws[W_SELKEY]);
+  if (__ldcg(ws + SG_SELECT_WS_NANCOUNT) != 0u) { out2[0] = nanv; out2[1] = nanv; return; }
+  const float a = key_to_float(__ldcg(ws + W_SELKEY));
   float b = a;
-  if (ws[W_NEEDNEXT]) {
-    const uint32_t in_bucket = ws[W_NEXTIN], above = ws[SG_SELECT_WS_MINABOVE];
+  if (__ldcg(ws + W_NEEDNEXT)) {
+    const uint32_t in_bucket = __ldcg(ws + W_NEXTIN), above = __ldcg(ws + SG_SELECT_WS_MINABOVE);
     if (in_bucket != 0xFFFFFFFFu) b = key_to_float(in_bucket);
     else if (above != 0xFFFFFFFFu) b = key_to_float(above);
   }
   out2[0] = a;
   out2[1] = b;
+}
+__global__ void finish_kernel(const uint32_t* ws, float* out2) {
+  if (threadIdx.x == 0) finish_body(ws, out2);
 }
 
 __global__ void lerp_kernel(const float* stats2, float w, int kind, float* thr) {
@@ -191,7 +444,11 @@ static int grid_for(int64_t n, int threads, int per_thread) {
 
 extern "C" {
 
-int sg_select_init_attributes() { return SG_OK; }
+int sg_select_init_attributes() {
+  SG_CUDA(cudaFuncSetAttribute(sg::sel::sample_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               sg::sel::kSampleSmem));
+  return SG_OK;
+}
 
 int sg_select_begin(uint32_t* ws, int64_t k, void* stream) {
   SG_READY();
@@ -209,10 +466,10 @@ int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stre
   const int grid = sg::sel::grid_for(n, 512, 16);
   cudaStream_t st = sg::as_stream(stream);
   switch (pass) {
-    case 0: sg::sel::hist_kernel<0><<<grid, 512, 0, st>>>(v, n, ws); break;
-    case 1: sg::sel::hist_kernel<1><<<grid, 512, 0, st>>>(v, n, ws); break;
-    case 2: sg::sel::hist_kernel<2><<<grid, 512, 0, st>>>(v, n, ws); break;
-    default: sg::sel::hist_kernel<3><<<grid, 512, 0, st>>>(v, n, ws); break;
+    case 0: sg::sel::hist_kernel<0, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
+    case 1: sg::sel::hist_kernel<1, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
+    case 2: sg::sel::hist_kernel<2, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
+    default: sg::sel::hist_kernel<3, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
   }
   SG_LAUNCH_CHECK();
   return SG_OK;
@@ -234,15 +491,63 @@ int sg_select_finish(const uint32_t* ws, float* out2, void* stream) {
   return SG_OK;
 }
 
+// four fused histogram+step passes over v (or over the candidate buffer when the filter pass validated it)
+static int fused_passes(const float* v, int64_t n, const float* cand, uint32_t* ws, float* out2, cudaStream_t st) {
+  const int grid = sg::sel::grid_for(n, 512, 16);
+  sg::sel::hist_kernel<0, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
+  sg::sel::hist_kernel<1, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
+  sg::sel::hist_kernel<2, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
+  sg::sel::hist_kernel<3, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 int sg_radix_select(const float* v, int64_t n, int64_t k, uint32_t* ws, float* out2, void* stream) {
+  SG_READY();
   SG_REQUIRE(n > 0 && k >= 0 && k < n, "need 0 <= k < n");
+  SG_REQUIRE(v && ws && out2, "null pointer");
   int r = sg_select_begin(ws, k, stream);
-  for (int pass = 0; pass < SG_SELECT_NUM_PASSES && r == SG_OK; ++pass) {
-    r = sg_select_hist(v, n, ws, pass, stream);
-    if (r == SG_OK) r = sg_select_step(ws, pass, stream);
-  }
-  if (r == SG_OK) r = sg_select_finish(ws, out2, stream);
-  return r;
+  if (r != SG_OK) return r;
+  return fused_passes(v, n, nullptr, ws, out2, sg::as_stream(stream));
+}
+
+size_t sg_select_workspace_bytes(int64_t n) {
+  size_t b = SG_SELECT_WS_WORDS * 4;
+  if (n >= SG_SELECT_ONEPASS_MIN) b += sg::sel::kSampleCount * 4 + sg::align_up((size_t)(n / 16) * 4, 256);
+  return b;
+}
+
+int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t workspace_bytes, float* out2,
+                  void* stream) {
+  using namespace sg::sel;
+  SG_READY();
+  SG_REQUIRE(n > 0 && k >= 0 && k < n, "need 0 <= k < n");
+  SG_REQUIRE(v && workspace && out2, "null pointer");
+  SG_REQUIRE(workspace_bytes >= SG_SELECT_WS_WORDS * 4 && ((uintptr_t)workspace & 15) == 0, "workspace");
+  uint32_t* ws = static_cast<uint32_t*>(workspace);
+  cudaStream_t st = sg::as_stream(stream);
+  const size_t fixed = SG_SELECT_WS_WORDS * 4 + kSampleCount * 4;
+  if (n < SG_SELECT_ONEPASS_MIN || workspace_bytes < fixed + (size_t)(n / 16) * 4)
+    return sg_radix_select(v, n, k, ws, out2, stream);
+  uint32_t* skeys = ws + SG_SELECT_WS_WORDS;
+  float* cand = reinterpret_cast<float*>(skeys + kSampleCount);
+  const unsigned long long cap = (workspace_bytes - fixed) / 4;
+  // the sampling ticket lives in ws itself: every call leaves ws[W_TICKET_SAMPLE] == 0 (the last CTA clears ws),
+  // but a fresh workspace holds garbage -> clear it once per call, stream ordered
+  SG_CUDA(cudaMemsetAsync(ws + W_TICKET_SAMPLE, 0, 4, st));
+  // pivot ranks inside the sample: the ranks of x_(k), x_(k+1) scaled to the sample -+ 5.5 sigma (+ slack)
+  const double S = kSampleCount, p = (double)k / (double)n;
+  const double sigma = sqrt(S * p * (1.0 - p));
+  const int delta = (int)ceil(5.0 * sigma) + 24;
+  const int r_lo = (int)floor(p * S) - delta;
+  const int r_hi = (int)ceil((double)(k + 1) / (double)n * S) + delta;
+  sample_pivot_kernel<<<kSampleCount / kSampleThreads, kSampleThreads, kSampleSmem, st>>>(
+      v, n, ws, skeys, ws + W_TICKET_SAMPLE, (unsigned long long)k, r_lo, r_hi);
+  SG_LAUNCH_CHECK();
+  const int grid = sg::state().sm_count * 4;
+  filter_kernel<<<grid, kFilterThreads, 0, st>>>(v, n, cand, cap, ws, (unsigned long long)k);
+  SG_LAUNCH_CHECK();
+  return fused_passes(v, n, cand, ws, out2, st);
 }
 
 int sg_lerp_threshold(const float* stats2, float weight, int lerp_kind, float* thr, void* stream) {

@@ -44,6 +44,38 @@ def test_radix_select_order_stats(sb):
                 assert np.array_equal(got, want), (n, k, got, want)  # -0.0 == 0.0 under array_equal
 
 
+def test_onepass_select_large(sb):
+    """n >= 2^21 takes the sampled one-pass path (sg_select_kth): pivots from a sample, one streaming
+    read, radix passes over the candidates; the fallbacks (ties overflowing the candidate buffer, sorted
+    input, extreme ranks, NaN) must stay exact."""
+    rng = np.random.default_rng(21)
+    n = (1 << 22) + 12345
+    cases = {
+        "lognormal": O.synth_losses(n, seed=3),
+        "normal": rng.standard_normal(n).astype(np.float32),
+        "adversarial_ties": adversarial(n, rng),
+        "all_equal": np.full(n, 0.75, np.float32),
+        "sorted": np.sort(rng.standard_normal(n).astype(np.float32)),
+        "reverse_sorted": np.sort(rng.standard_normal(n).astype(np.float32))[::-1].copy(),
+        "two_values": (rng.random(n) < 0.5).astype(np.float32),
+    }
+    for name, v in cases.items():
+        s = np.sort(v)
+        d = dev(v)
+        for k in (0, 1, n // 10, n // 2, (9 * n) // 10, n - 2, n - 1, int(rng.integers(0, n))):
+            got = sb.order_stats(d, k).cpu().numpy()
+            want = np.array([s[k], s[min(k + 1, n - 1)]], np.float32)
+            assert np.array_equal(got, want), (name, k, got, want)
+    # unaligned view, percentile on top
+    v = O.synth_losses(n + 1, seed=4)
+    d = dev(v)[1:]
+    assert sb.percentile_device(d, 90.0).cpu().numpy()[0] == np.percentile(v[1:], 90.0)
+    # NaN anywhere -> NaN
+    v = O.synth_losses(n, seed=5)
+    v[n // 3] = np.nan
+    assert np.isnan(sb.order_stats(dev(v), n // 2).cpu().numpy()).all()
+
+
 def test_radix_select_nan(sb):
     v = np.arange(100, dtype=np.float32)
     v[17] = np.nan

@@ -61,6 +61,15 @@ def main():
     rec("select_hist_pass0", timeit(lambda: lib.sg_select_hist(p(v), n, p(ws), 0, st)), 4 * n, "one radix-histogram pass: 4 B/elem read")
     rec("radix_select_total", timeit(lambda: lib.sg_radix_select(p(v), n, (9 * n) // 10, p(ws), p(out2), st)), 16 * n,
         "x_(k) and x_(k+1): 4 streaming passes of 4 B/elem (8 key bits each)")
+    sws_bytes = int(lib.sg_select_workspace_bytes(n))
+    sws = torch.empty(sws_bytes, dtype=torch.uint8, device=dev)
+    t = timeit(lambda: lib.sg_select_kth(p(v), n, (9 * n) // 10, p(sws), sws_bytes, p(out2), st))
+    ref2 = out2.clone()
+    L.check(lib.sg_radix_select(p(v), n, (9 * n) // 10, p(ws), p(out2), st))
+    assert torch.equal(ref2, out2), (ref2, out2)
+    rec("select_onepass_total", t, 4 * n,
+        "x_(k), x_(k+1) by sampled pivots + ONE streaming read (SURVEY 8d: 4 B/elem) + radix passes over ~3 % candidates")
+    del sws
     thr = torch.tensor([float(np.percentile(v[:1 << 20].cpu().numpy(), 90))], device=dev)
     idx = torch.empty(n, dtype=torch.int64, device=dev)
     cnt = torch.empty(1, dtype=torch.int64, device=dev)
