@@ -126,7 +126,7 @@ int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, vo
  * ws[0..257) (uint32 digit histogram + NaN count, SUM) after every sg_select_hist and
  * ws[SG_SELECT_WS_MINABOVE] (MIN; as int32 of key ^ 0x80000000 it is order preserving) after the
  * last one, before the matching sg_select_step.  */
-#define SG_SELECT_WS_WORDS 512       /* uint32 words of workspace */
+#define SG_SELECT_WS_WORDS 2048      /* uint32 words of workspace */
 #define SG_SELECT_WS_HIST 0          /* [256] digit histogram of the current pass */
 #define SG_SELECT_WS_NANCOUNT 256    /* number of NaNs seen (pass 0); SUM-reduced with the histogram */
 #define SG_SELECT_WS_MINABOVE 257    /* smallest radix key above the selected bucket (MIN-reduced) */

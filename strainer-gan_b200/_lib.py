@@ -13,7 +13,7 @@ SG_LT, SG_LE, SG_GE, SG_GT = 0, 1, 2, 3
 SG_NOT = 4  # OR-ed into a comparison: logical negation (NaN-correct complement)
 SG_LERP_NUMPY, SG_LERP_TORCH = 0, 1
 SG_CONV_BF16, SG_CONV_BF16X3 = 0, 1
-SG_SELECT_WS_WORDS = 512
+SG_SELECT_WS_WORDS = 2048
 SG_SELECT_WS_NANCOUNT = 256
 SG_SELECT_WS_MINABOVE = 257
 SG_SELECT_NUM_PASSES = 4

@@ -27,7 +27,6 @@ constexpr int W_NANF = 276;        // NaNs seen by the filter pass
 constexpr int W_OVERFLOW = 277;    // candidate buffer overflowed
 constexpr int W_TICKET = 278;      // CTAs of the filter pass that are done
 constexpr int W_USECAND = 279;     // 1: the radix passes run over the candidate buffer with the reduced rank
-constexpr int W_TICKET_PASS = 280; // [4] CTAs done per fused histogram pass
 constexpr int W_TICKET_SAMPLE = 284; // CTAs of the sampling kernel that are done
 constexpr int kSampleCount = 32768;
 constexpr int kSampleThreads = 1024;
@@ -48,71 +47,187 @@ __global__ void begin_kernel(uint32_t* ws, unsigned long long k) {
   }
 }
 
-__device__ __forceinline__ void step_body(uint32_t* ws, int pass);
-
-__device__ __forceinline__ void finish_body(const uint32_t* ws, float* out2);
-
-// FUSED: single-device form.  The source may be redirected to the candidate buffer of the one-pass filter
-// (ws[W_USECAND]; only as many CTAs as that buffer needs do any work), the LAST CTA to finish runs the bucket
-// step itself (no separate step launch) and, after the last pass, writes the two order statistics.
-template <int PASS, bool FUSED>
-__global__ void __launch_bounds__(512, 4) hist_kernel(const float* __restrict__ v, int64_t n, const float* __restrict__ cand,
-                                                   uint32_t* __restrict__ ws, float* __restrict__ out2) {
+template <int PASS>
+__global__ void __launch_bounds__(512, 4) hist_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ws) {
   __shared__ uint32_t s_hist[256 * 32];
   __shared__ uint32_t s_nan, s_min;
-  __shared__ int s_last;
-  int64_t eff_grid = gridDim.x;
-  if (FUSED && cand != nullptr && ws[W_USECAND] != 0u) {
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_hist[i] = 0u;
+  if (threadIdx.x == 0) { s_nan = 0u; s_min = 0xFFFFFFFFu; }
+  __syncthreads();
+  const uint32_t prefix = ws[W_PREFIX];
+  const uint32_t lane = threadIdx.x & 31;
+  constexpr int kShift = 24 - 8 * PASS;   // digit position
+  uint32_t nan_local = 0, min_local = 0xFFFFFFFFu;
+  stream_f32<4>(v, n, [&](float f, int64_t) {
+    const uint32_t key = float_to_key(f);
+    if constexpr (PASS == 0) {
+      nan_local += (key == 0xFFFFFFFFu);
+      atomicAdd(&s_hist[((key >> 24) << 5) + lane], 1u);
+    } else {
+      const uint32_t hi = key >> (kShift + 8);
+      if (hi == prefix) atomicAdd(&s_hist[(((key >> kShift) & 255u) << 5) + lane], 1u);
+      if (PASS == 3 && hi > prefix) min_local = min(min_local, key);
+    }
+  });
+  if (PASS == 0 && nan_local) atomicAdd(&s_nan, nan_local);
+  if (PASS == 3 && min_local != 0xFFFFFFFFu) atomicMin(&s_min, min_local);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) c += s_hist[i * 32 + ((k + i) & 31)];
+    if (c) atomicAdd(&ws[SG_SELECT_WS_HIST + i], c);
+  }
+  if (PASS == 0 && threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
+  if (PASS == 3 && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], s_min);
+}
+
+// ---- single-device radix phases: ONE cooperative kernel ---------------------------------------------
+// All four 8-bit passes in one launch (cudaLaunchCooperativeKernel: every CTA is resident, so a grid barrier
+// may spin).  CTA b owns a contiguous slice of the source; the first kCacheKeys keys of the slice are kept in
+// shared memory, so a source that fits (the candidate buffer of the one-pass filter, or any n <= grid * 40960)
+// is read ONCE and passes 1..3 never touch global memory.  Per pass: lane-private histogram -> RED into the
+// pass's own 256 global bins -> grid barrier -> every CTA derives the bucket redundantly from those bins.
+constexpr int kTailThreads = 1024;
+constexpr int kCacheKeys = 40960;                                  // 160 KB
+constexpr int kTailSmem = (kCacheKeys + 256 * 32) * 4;             // + 32 KB lane-private histogram
+constexpr int W_BAR = 288;         // grid-barrier arrivals
+constexpr int W_ERR = 289;         // 1: a grid barrier timed out (protocol bug guard)
+constexpr int W_HIST4 = 512;       // [4][256] per-pass digit histograms of the cooperative kernel
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t gtimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void grid_barrier(uint32_t* ws, uint32_t target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ws + W_BAR, 1u);
+    const uint64_t t0 = gtimer_ns();
+    while (ld_acquire_u32(ws + W_BAR) < target) {
+      if (gtimer_ns() - t0 > 2000000000ull) { ws[W_ERR] = 1u; break; }   // never hang the GPU
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) radix_phases_kernel(const float* __restrict__ v, int64_t n,
+                                                                       const float* __restrict__ cand,
+                                                                       uint32_t* __restrict__ ws, float* __restrict__ out2) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_keys = s_dyn;
+  uint32_t* s_hist = s_dyn + kCacheKeys;
+  __shared__ unsigned long long s_warp[8];
+  __shared__ unsigned long long s_before, s_cnt;
+  __shared__ int s_bucket;
+  __shared__ uint32_t s_nan, s_min, s_next;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // candidate mode: every key lies in [klo, khi]; a pass whose digit (and everything above it) is the same in
+  // both bounds has a single populated bin and is skipped (typically the exponent byte, often two passes)
+  uint32_t klo = 0u, khi = 0xFFFFFFFFu;
+  if (cand != nullptr && ws[W_USECAND] != 0u) {
     v = cand;
     n = (int64_t)*reinterpret_cast<const unsigned long long*>(ws + W_CAND);
-    eff_grid = min((int64_t)gridDim.x, max((int64_t)1, (n + 16383) >> 14));
+    klo = float_to_key(__uint_as_float(ws[W_LO_F]));
+    khi = float_to_key(__uint_as_float(ws[W_HI_F]));
   }
-  if (blockIdx.x < eff_grid) {
-    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_hist[i] = 0u;
-    if (threadIdx.x == 0) { s_nan = 0u; s_min = 0xFFFFFFFFu; }
+  const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
+  const int64_t beg = min((int64_t)blockIdx.x * per, n), end = min(beg + per, n);
+  const int ncache = (int)min((int64_t)kCacheKeys, end - beg);
+  for (int i = t; i < ncache; i += kTailThreads) s_keys[i] = float_to_key(__ldg(v + beg + i));
+  const float* rest = v + beg + ncache;          // streamed again in every pass (only when the slice exceeds the cache)
+  const int64_t nrest = end - beg - ncache;
+  unsigned long long krem = *reinterpret_cast<const unsigned long long*>(ws + W_KREM_LO);
+  uint32_t prefix = 0u, arrivals = 0u;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {   // skippable passes (the last one always runs: it resolves x_(k+1))
+    if ((klo >> (24 - 8 * pass)) != (khi >> (24 - 8 * pass))) break;
+    prefix = klo >> (24 - 8 * pass);
+  }
+#pragma unroll 1
+  for (int pass = (prefix == 0u && (klo >> 24) != (khi >> 24)) ? 0 : ((klo >> 16) != (khi >> 16)) ? 1 : ((klo >> 8) != (khi >> 8)) ? 2 : 3;
+       pass < 4; ++pass) {
+    for (int i = t; i < 256 * 32; i += kTailThreads) s_hist[i] = 0u;
+    if (t == 0) { s_nan = 0u; s_min = 0xFFFFFFFFu; s_bucket = -1; s_next = 0xFFFFFFFFu; }
     __syncthreads();
-    const uint32_t prefix = ws[W_PREFIX];
-    const uint32_t lane = threadIdx.x & 31;
-    constexpr int kShift = 24 - 8 * PASS;   // digit position
+    const int shift = 24 - 8 * pass;
     uint32_t nan_local = 0, min_local = 0xFFFFFFFFu;
-    stream_f32_grid<4>(v, n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, eff_grid * blockDim.x, [&](float f, int64_t) {
-      const uint32_t key = float_to_key(f);
-      if constexpr (PASS == 0) {
-        nan_local += (key == 0xFFFFFFFFu);
-        atomicAdd(&s_hist[((key >> 24) << 5) + lane], 1u);
-      } else {
-        const uint32_t hi = key >> (kShift + 8);
-        if (hi == prefix) atomicAdd(&s_hist[(((key >> kShift) & 255u) << 5) + lane], 1u);
-        if (PASS == 3 && hi > prefix) min_local = min(min_local, key);
-      }
-    });
-    if (PASS == 0 && nan_local) atomicAdd(&s_nan, nan_local);
-    if (PASS == 3 && min_local != 0xFFFFFFFFu) atomicMin(&s_min, min_local);
+    auto visit = [&](uint32_t key) {
+      const uint32_t hi = (pass == 0) ? 0u : (key >> (shift + 8));
+      if (hi == prefix) atomicAdd(&s_hist[(((key >> shift) & 255u) << 5) + lane], 1u);
+      if (pass == 0) nan_local += (key == 0xFFFFFFFFu);
+      if (pass == 3 && hi > prefix) min_local = min(min_local, key);
+    };
+#pragma unroll 4
+    for (int i = t; i < ncache; i += kTailThreads) visit(s_keys[i]);
+    if (nrest > 0)
+      stream_f32_grid<4>(rest, nrest, (int64_t)t, (int64_t)kTailThreads, [&](float f, int64_t) { visit(float_to_key(f)); });
+    if (nan_local) atomicAdd(&s_nan, nan_local);
+    if (min_local != 0xFFFFFFFFu) atomicMin(&s_min, min_local);
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    uint32_t* gh = ws + W_HIST4 + pass * 256;
+    if (t < 256) {
       uint32_t c = 0;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) c += s_hist[i * 32 + ((k + i) & 31)];
-      if (c) atomicAdd(&ws[SG_SELECT_WS_HIST + i], c);
+      for (int k = 0; k < 32; ++k) c += s_hist[t * 32 + ((k + t) & 31)];
+      if (c) atomicAdd(gh + t, c);
     }
-    if (PASS == 0 && threadIdx.x == 0 && s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
-    if (PASS == 3 && threadIdx.x == 0 && s_min != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], s_min);
-  }
-  if (FUSED) {
-    __threadfence();
+    if (t == 0) {
+      if (s_nan) atomicAdd(&ws[SG_SELECT_WS_NANCOUNT], s_nan);
+      if (s_min != 0xFFFFFFFFu) atomicMin(&ws[SG_SELECT_WS_MINABOVE], s_min);
+    }
+    arrivals += gridDim.x;
+    grid_barrier(ws, arrivals);
+    // every CTA: bucket of rank krem among the 256 bins (thread t < 256 owns bin t)
+    const bool on = t < 256;
+    const unsigned long long c = on ? (unsigned long long)__ldcg(gh + t) : 0ull;
+    unsigned long long x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (on && lane == 31) s_warp[w] = x;
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&ws[W_TICKET_PASS + PASS], 1u) == gridDim.x - 1);
+    unsigned long long run = x - c;
+    if (on) for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
+    if (on && krem >= run && krem < run + c) { s_bucket = t; s_before = run; s_cnt = c; }
     __syncthreads();
-    if (s_last) {
-      __threadfence();
-      step_body(ws, PASS);
-      if (PASS == 3) {
-        __syncthreads();
-        if (threadIdx.x == 0) finish_body(ws, out2);
+    int b = s_bucket;
+    if (pass == 3 && on && b >= 0 && t > b && c != 0ull) atomicMin(&s_next, (uint32_t)t);
+    __syncthreads();
+    unsigned long long before = s_before, cnt = s_cnt;
+    if (b < 0) { b = 255; before = 0; cnt = 0; }
+    prefix = (prefix << 8) | (uint32_t)b;
+    krem -= before;
+    if (pass == 3 && blockIdx.x == 0 && t == 0) {
+      const float nanv = __uint_as_float(0x7FC00000u);
+      if (__ldcg(ws + SG_SELECT_WS_NANCOUNT) != 0u) {
+        out2[0] = nanv; out2[1] = nanv;
+      } else {
+        const float a = key_to_float(prefix);
+        float bb = a;
+        if (krem + 1 >= cnt) {   // x_(k+1) has a larger key
+          const uint32_t above = __ldcg(ws + SG_SELECT_WS_MINABOVE);
+          if (s_next != 0xFFFFFFFFu) bb = key_to_float((prefix & ~0xFFu) | s_next);
+          else if (above != 0xFFFFFFFFu) bb = key_to_float(above);
+        }
+        out2[0] = a; out2[1] = bb;
       }
     }
+    __syncthreads();
   }
 }
+
+__device__ __forceinline__ void step_body(uint32_t* ws, int pass);
+__device__ __forceinline__ void finish_body(const uint32_t* ws, float* out2);
 
 // ---- one-pass selection ---------------------------------------------------------------------------
 // SURVEY §8(d) counts ONE 4-byte read per element for the global select.  A radix select needs the bucket of
@@ -216,45 +331,55 @@ __global__ void __launch_bounds__(kSampleThreads) sample_pivot_kernel(const floa
 }
 
 constexpr int kFilterThreads = 512;
-constexpr int kStage = 256;   // staged candidates per warp (flush at >= 128: one global atomic per >= 128 candidates)
-__global__ void __launch_bounds__(kFilterThreads) filter_kernel(const float* __restrict__ v, int64_t n,
-                                                                float* __restrict__ cand, unsigned long long cap,
-                                                                uint32_t* __restrict__ ws, unsigned long long k) {
-  __shared__ float s_stage[kFilterThreads / 32][kStage];
+constexpr int kSlots = 20;    // staged candidates per THREAD; flushed by the warp when any lane holds > kSlots - 8
+
+__device__ __forceinline__ void count_if_lt(uint32_t& c, float f, float lo) {
+  asm("{\n\t.reg .pred q;\n\tsetp.lt.f32 q, %1, %2;\n\t@q add.u32 %0, %0, 1;\n\t}" : "+r"(c) : "f"(f), "f"(lo));
+}
+
+__global__ void __launch_bounds__(kFilterThreads, 4) filter_kernel(const float* __restrict__ v, int64_t n,
+                                                                   float* __restrict__ cand, unsigned long long cap,
+                                                                   uint32_t* __restrict__ ws, unsigned long long k) {
+  __shared__ float s_stage[kSlots * kFilterThreads];   // [slot][thread]: a thread's column is bank-conflict free
   __shared__ unsigned long long s_below;
   __shared__ uint32_t s_nan;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
+  __shared__ int s_lastf;
+  const int lane = threadIdx.x & 31;
   const float lo = __uint_as_float(ws[W_LO_F]), hi = __uint_as_float(ws[W_HI_F]);
   if (threadIdx.x == 0) { s_below = 0ull; s_nan = 0u; }
   __syncthreads();
-  float* stage = s_stage[w];
-  int cnt = 0;                       // warp-uniform
+  float* stage = s_stage + threadIdx.x;
+  int cnt = 0;                       // this thread's staged candidates
   uint32_t below = 0, nan = 0;
-  auto flush = [&]() {
+  auto flush = [&]() {               // whole warp
+    int x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, x, 31);
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned long long*>(ws + W_CAND), (unsigned long long)cnt);
+    if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned long long*>(ws + W_CAND), (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    __syncwarp();
-    if (base + (unsigned long long)cnt <= cap) {
-      for (int i = lane; i < cnt; i += 32) cand[base + i] = stage[i];
+    if (base + (unsigned long long)total <= cap) {
+      float* dst = cand + base + (x - cnt);
+      for (int j = 0; j < cnt; ++j) dst[j] = stage[j * kFilterThreads];
     } else if (lane == 0) {
       ws[W_OVERFLOW] = 1u;
     }
-    __syncwarp();
     cnt = 0;
   };
-  auto visit = [&](float f, bool valid) {
-    below += (valid && f < lo);
-    nan += (valid && f != f);
-    const bool c = valid && f >= lo && f <= hi;
-    const unsigned m = __ballot_sync(0xffffffffu, c);
-    if (m) {
-      if (c) stage[cnt + __popc(m & lt)] = f;
-      cnt += __popc(m);
-    }
+  auto push = [&](float f) {
+    count_if_lt(below, f, lo);
+    if (f >= lo && f <= hi) { stage[cnt * kFilterThreads] = f; ++cnt; }
   };
-  // warp-uniform trip counts: every lane of a warp runs the same iterations (tail lanes masked by `valid`)
+  auto visit4 = [&](const float4& q) {
+    push(q.x); push(q.y); push(q.z); push(q.w);
+    const float tsum = (q.x + q.y) + (q.z + q.w);      // NaN if any element is NaN (or inf - inf: checked exactly)
+    if (tsum != tsum) nan += (q.x != q.x) + (q.y != q.y) + (q.z != q.z) + (q.w != q.w);
+  };
+  // warp-uniform trip counts: every lane of a warp runs the same iterations
   const int64_t gwarp = (blockIdx.x * (int64_t)kFilterThreads + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * kFilterThreads) >> 5;
   const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
@@ -267,24 +392,20 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const float* __r
 #pragma unroll
     for (int u = 0; u < U; ++u) q[u] = ldg_stream4(v4 + i + u * nwarps * 32 + lane);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      visit(q[u].x, true); visit(q[u].y, true); visit(q[u].z, true); visit(q[u].w, true);
-      if (cnt >= kStage / 2) flush();
+    for (int u = 0; u < U; u += 2) {
+      visit4(q[u]); visit4(q[u + 1]);
+      if (__any_sync(0xffffffffu, cnt > kSlots - 8)) flush();
     }
   }
   for (; i < n4; i += nwarps * 32) {
-    const bool ok = i + lane < n4;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) q = ldg_stream4(v4 + i + lane);
-    visit(q.x, ok); visit(q.y, ok); visit(q.z, ok); visit(q.w, ok);
-    if (cnt >= kStage / 2) flush();
+    if (i + lane < n4) visit4(ldg_stream4(v4 + i + lane));
+    if (__any_sync(0xffffffffu, cnt > kSlots - 8)) flush();
   }
   for (int64_t e = (n4 << 2) + gwarp * 32; e < n; e += nwarps * 32) {
-    const bool ok = e + lane < n;
-    visit(ok ? v[e + lane] : 0.f, ok);
-    if (cnt >= kStage / 2) flush();
+    if (e + lane < n) { const float f = v[e + lane]; push(f); nan += (f != f); }
+    if (__any_sync(0xffffffffu, cnt > kSlots - 8)) flush();
   }
-  if (cnt) flush();
+  if (__any_sync(0xffffffffu, cnt > 0)) flush();
   below = warp_sum(below);
   nan = warp_sum(nan);
   if (lane == 0) {
@@ -292,7 +413,6 @@ __global__ void __launch_bounds__(kFilterThreads) filter_kernel(const float* __r
     if (nan) atomicAdd(&s_nan, nan);
   }
   __syncthreads();
-  __shared__ int s_lastf;
   if (threadIdx.x == 0) {
     if (s_below) atomicAdd(reinterpret_cast<unsigned long long*>(ws + W_BELOW), s_below);
     if (s_nan) atomicAdd(&ws[W_NANF], s_nan);
@@ -447,6 +567,8 @@ extern "C" {
 int sg_select_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(sg::sel::sample_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                sg::sel::kSampleSmem));
+  SG_CUDA(cudaFuncSetAttribute(sg::sel::radix_phases_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               sg::sel::kTailSmem));
   return SG_OK;
 }
 
@@ -466,10 +588,10 @@ int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stre
   const int grid = sg::sel::grid_for(n, 512, 16);
   cudaStream_t st = sg::as_stream(stream);
   switch (pass) {
-    case 0: sg::sel::hist_kernel<0, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
-    case 1: sg::sel::hist_kernel<1, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
-    case 2: sg::sel::hist_kernel<2, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
-    default: sg::sel::hist_kernel<3, false><<<grid, 512, 0, st>>>(v, n, nullptr, ws, nullptr); break;
+    case 0: sg::sel::hist_kernel<0><<<grid, 512, 0, st>>>(v, n, ws); break;
+    case 1: sg::sel::hist_kernel<1><<<grid, 512, 0, st>>>(v, n, ws); break;
+    case 2: sg::sel::hist_kernel<2><<<grid, 512, 0, st>>>(v, n, ws); break;
+    default: sg::sel::hist_kernel<3><<<grid, 512, 0, st>>>(v, n, ws); break;
   }
   SG_LAUNCH_CHECK();
   return SG_OK;
@@ -491,14 +613,16 @@ int sg_select_finish(const uint32_t* ws, float* out2, void* stream) {
   return SG_OK;
 }
 
-// four fused histogram+step passes over v (or over the candidate buffer when the filter pass validated it)
-static int fused_passes(const float* v, int64_t n, const float* cand, uint32_t* ws, float* out2, cudaStream_t st) {
-  const int grid = sg::sel::grid_for(n, 512, 16);
-  sg::sel::hist_kernel<0, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
-  sg::sel::hist_kernel<1, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
-  sg::sel::hist_kernel<2, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
-  sg::sel::hist_kernel<3, true><<<grid, 512, 0, st>>>(v, n, cand, ws, out2);
-  SG_LAUNCH_CHECK();
+// all four radix passes in one cooperative launch over v (or over the candidate buffer when the filter pass
+// validated it); `n_work` sizes the grid
+static int radix_phases(const float* v, int64_t n, const float* cand, int64_t n_work, uint32_t* ws, float* out2,
+                        cudaStream_t st) {
+  int64_t g = sg::ceil_div(n_work, 8192);
+  if (g > sg::state().sm_count) g = sg::state().sm_count;
+  if (g < 1) g = 1;
+  void* args[] = {(void*)&v, (void*)&n, (void*)&cand, (void*)&ws, (void*)&out2};
+  SG_CUDA(cudaLaunchCooperativeKernel((const void*)sg::sel::radix_phases_kernel, dim3((unsigned)g), dim3(sg::sel::kTailThreads),
+                                      args, sg::sel::kTailSmem, st));
   return SG_OK;
 }
 
@@ -508,7 +632,7 @@ int sg_radix_select(const float* v, int64_t n, int64_t k, uint32_t* ws, float* o
   SG_REQUIRE(v && ws && out2, "null pointer");
   int r = sg_select_begin(ws, k, stream);
   if (r != SG_OK) return r;
-  return fused_passes(v, n, nullptr, ws, out2, sg::as_stream(stream));
+  return radix_phases(v, n, nullptr, n, ws, out2, sg::as_stream(stream));
 }
 
 size_t sg_select_workspace_bytes(int64_t n) {
@@ -547,7 +671,7 @@ int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t 
   const int grid = sg::state().sm_count * 4;
   filter_kernel<<<grid, kFilterThreads, 0, st>>>(v, n, cand, cap, ws, (unsigned long long)k);
   SG_LAUNCH_CHECK();
-  return fused_passes(v, n, cand, ws, out2, st);
+  return radix_phases(v, n, cand, n / 32, ws, out2, st);
 }
 
 int sg_lerp_threshold(const float* stats2, float weight, int lerp_kind, float* thr, void* stream) {
