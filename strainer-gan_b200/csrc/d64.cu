@@ -435,6 +435,203 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// L3 / L4 on CTA PAIRS (tcgen05 cta_group::2): one 256(pixel) x 256(cout) tile per pair of SMs.
+// A single-CTA 128x256 tile makes every tcgen05.mma read 12 KB of operands from shared memory per 128
+// tensor cycles while TMA writes the next 48 KB stage: the pipe stalls on shared-memory bandwidth
+// (67-74 % tensor-pipe active in profiles/r1a).  In a pair each CTA stages its own 128 pixels (A, 16 KB)
+// and HALF of the 256 output channels (B, 16 KB); the hardware shares the B halves across the two SMs,
+// so each SM reads 8 KB and receives 32 KB per 512 tensor cycles.
+//   both CTAs : warp 0 TMA producer (loads signal the LEADER's full barrier), warps 2-5 epilogue
+//   leader    : warp 1 issues tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs
+// ------------------------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = 128 * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kThreads = 192;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvParams p) {
+  using Cfg = PairCfg;
+  constexpr int S = Cfg::kStages;
+  constexpr int BLOCK_N = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;   // identical in both CTAs (same kernel, same layout)
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  const uint32_t bar0 = base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);     // leader's copy is the live one: its producer's arrive.expect_tx (both CTAs' bytes)
+      mbar_init(empty_bar(s), 1);    // multicast tcgen05.commit of the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);    // multicast tcgen05.commit of the leader
+      mbar_init(tempty_bar(a), 8);   // leader's copy: one elected lane of each of the 2 x 4 epilogue warps
+    }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  cluster_sync_all();                // peer barriers initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ow_n = 1 << p.ow_log2;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
+        const int nt = tile % p.n_tiles;
+        const int mt = 2 * (tile / p.n_tiles) + (int)rank;
+        const int img0 = mt * p.bimg;
+        for (int ks = 0; ks < p.k_steps; ++ks) {
+          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer + 20)) { ok = false; break; }
+          const int seg = ks % p.nseg;
+          const int t2 = ks / p.nseg;
+          const int chunk = t2 % p.nchunk;
+          const int tap = t2 / p.nchunk;
+          const int kh = tap >> 2, kw = tap & 3;
+          const int cc = chunk * 64 + (seg == 1 ? p.c_in : 0);
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          tma_load_5d_pair(sa, &tmap_a, lead_full, cc, (kw - 1) >> 1, (kh - 1) >> 1,
+                           ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img0);
+          tma_load_2d_pair(sb, &tmap_b, lead_full, ks * 64, nt * BLOCK_N + (int)rank * 128);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
+        if (!mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 20)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ks = 0; ks < p.k_steps; ++ks) {
+          if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma + 20)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
+          umma_commit_pair(empty_bar(stage), 3);   // frees this stage in BOTH CTAs
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit_pair(tfull_bar(acc), 3);       // accumulator ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5 of both CTAs): own 128 pixels x 256 channels =================
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ct = p.c_out * p.out_sega;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      const int nt = tile % p.n_tiles;
+      const int mt = 2 * (tile / p.n_tiles) + (int)rank;
+      const int img = mt * p.bimg + (row >> (2 * p.ow_log2));
+      const int rem = row & ((1 << (2 * p.ow_log2)) - 1);
+      const int oh = rem >> p.ow_log2;
+      const int ow = rem & (ow_n - 1);
+      const bool valid = img < p.n_img;
+      size_t off;
+      if (p.out_planes) {
+        const int half = ow_n >> 1;
+        off = ((((size_t)img * 4 + ((oh & 1) * 2 + (ow & 1))) * half + (oh >> 1)) * half + (ow >> 1)) * ct;
+      } else {
+        off = (((size_t)img * ow_n + oh) * ow_n + ow) * ct;
+      }
+      __nv_bfloat16* dst = p.out + off + (size_t)nt * BLOCK_N;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 20)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int cb = 0; cb < BLOCK_N; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        const float* sc = p.scale + nt * BLOCK_N + cb;
+        const float* sh = p.shift + nt * BLOCK_N + cb;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = fmaf(__uint_as_float(v[2 * j]), __ldg(sc + 2 * j), __ldg(sh + 2 * j));
+          float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(sc + 2 * j + 1), __ldg(sh + 2 * j + 1));
+          a = a > 0.f ? a : p.slope * a;
+          b = b > 0.f ? b : p.slope * b;
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
+          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
+          const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+          const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
+          lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+        }
+        if (valid) {
+          uint4* d = reinterpret_cast<uint4*>(dst + cb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (p.out_sega == 2) {
+            uint4* dl = reinterpret_cast<uint4*>(dst + p.c_out + cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's barrier, from either CTA
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may leave while the peer can still touch its shared memory / barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // L2 (64 -> 128 channels) with the operands swapped: D^T[cout][pixel] = W * X^T.
 // With only 128 output channels a 128(pixel) x 128(cout) tile makes every tcgen05.mma read as many
 // operand bytes as a 128x256 one for half the math (shared-memory bound, 36 % tensor-pipe active
@@ -1277,6 +1474,60 @@ static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, co
 }
 
 
+// L3 / L4 on CTA pairs; same arguments as launch_conv<256> (tiles never split an image: s_in <= 16)
+static int launch_conv_pair(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
+                            __nv_bfloat16* act_out, int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega,
+                            int out_planes, float slope, int* err, cudaStream_t stream) {
+  using Cfg = PairCfg;
+  const int ow = s_in / 2;
+  const int bimg = 128 / (ow * ow);
+  const int ct_in = c_in * sega;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)ct_in, (cuuint64_t)ow, (cuuint64_t)ow, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)ow * ct_in * 2, (cuuint64_t)ow * ow * ct_in * 2,
+                             (cuuint64_t)4 * ow * ow * ct_in * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)ow, (cuuint32_t)ow, 1, (cuuint32_t)bimg};
+    int r = encode(&ta, 5, act_in, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  const int nchunk = c_in / 64;
+  const int k_steps = 16 * nchunk * nseg;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, (cuuint64_t)c_out};
+    cuuint64_t strides[1] = {(cuuint64_t)k_steps * 64 * 2};
+    cuuint32_t box[2] = {64, 128};   // each CTA of a pair stages half of the 256 output channels
+    int r = encode(&tb, 2, wpk, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  ConvParams p = {};
+  p.n_tiles = c_out / 256;
+  const int64_t m_tiles = ceil_div(batch, bimg);
+  p.total_tiles = (int)(ceil_div(m_tiles, 2) * p.n_tiles);   // PAIR tiles
+  p.n_img = (int)batch;
+  p.ow_log2 = __builtin_ctz(ow);
+  p.bh_log2 = p.ow_log2;
+  p.bimg = bimg;
+  p.tiles_per_img = 1;
+  p.c_in = c_in;
+  p.nchunk = nchunk;
+  p.nseg = nseg;
+  p.k_steps = k_steps;
+  p.c_out = c_out;
+  p.out_sega = sega;
+  p.out_planes = out_planes;
+  p.slope = slope;
+  p.scale = scale;
+  p.shift = shift;
+  p.out = act_out;
+  p.err = err;
+  int pairs = state().sm_count / 2;
+  if (p.total_tiles < pairs) pairs = p.total_tiles;
+  conv_pair_kernel<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* scale, const float* shift,
                              __nv_bfloat16* act2,
                              int64_t batch, int nseg, int sega, float slope, int* err, cudaStream_t stream) {
@@ -1408,6 +1659,7 @@ int sg_d64_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1Cfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1505,10 +1757,18 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
         r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st);
       break;
     case 3:
+      if (!getenv("SG_CONV_SINGLE_CTA"))  // default: CTA pairs (cta_group::2); single-CTA tiles kept for A/B timing
+        r = launch_conv_pair(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
+                             slope, err, st);
+      else
       r = launch_conv<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
                            slope, err, st);
       break;
     case 4:
+      if (!getenv("SG_CONV_SINGLE_CTA"))
+        r = launch_conv_pair(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
+                             slope, err, st);
+      else
       r = launch_conv<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
                            slope, err, st);
       break;

@@ -43,6 +43,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   return done != 0;
 }
+// acquire at cluster scope: for barriers that receive mbarrier.arrive.release.cluster from the peer CTA
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
 // Bounded wait: gives up after ~2 s of wall time, records `code` in *err (global) and raises the
 // CTA-wide abort flag, so a protocol bug can never hang the GPU box.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* s_abort, int* err, int code) {
@@ -50,6 +60,20 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
   const uint64_t t0 = globaltimer_ns();
   while (true) {
     if (mbar_try_wait(bar, parity)) return true;
+    if (*s_abort) return false;
+    if (globaltimer_ns() - t0 > 2000000000ull) {
+      *s_abort = 1;
+      atomicCAS(err, 0, code);
+      return false;
+    }
+  }
+}
+
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, volatile int* s_abort, int* err, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  while (true) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
     if (*s_abort) return false;
     if (globaltimer_ns() - t0 > 2000000000ull) {
       *s_abort = 1;
