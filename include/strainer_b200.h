@@ -109,6 +109,15 @@ size_t sg_ae_workspace_bytes(int64_t max_batch);
 int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
                 float* recon_out, void* stream);
 
+/* bf16 conv mode of the same auto-encoder (BASELINE.json config 4): the two 7x7 layers (86 % of the FLOPs) as
+ * implicit GEMMs on tcgen05 with bf16 operands / fp32 accumulation, bf16 NHWC activations, the small stride-2
+ * layers on the CUDA cores.  Same arguments as sg_ae_score; workspace from sg_ae_bf16_workspace_bytes, 1024-byte
+ * aligned.  sg_ae_bf16_check reports a timed-out pipeline (synchronises the stream). */
+size_t sg_ae_bf16_workspace_bytes(int64_t max_batch);
+int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
+                     float* recon_out, void* stream);
+int sg_ae_bf16_check(const void* workspace, void* stream);
+
 /* ---- MLP discriminator scoring (28x28 path) --------------------------------------------------
  * replaces Discriminator.forward of "Untitled-2.py:79-94" / "# 1,2,8.py:110-128" (eval mode) + BCE vs 1.
  * h_params: HOST array of 8 DEVICE pointers {weight [out,in], bias} x 4 Linear layers.  x fp32 [batch,784]. */
@@ -169,6 +178,15 @@ int sg_compact_indices(const float* v, int64_t n, const float* thr, int cmp, int
  * row_bytes must be a multiple of 16. */
 int sg_compact_rows(const void* rows, int64_t n, int64_t row_bytes, const uint8_t* mask, void* kept,
                     void* dropped, int64_t* counts_out, void* workspace, void* stream);
+/* The selection half of the in-batch strain block in two launches, for one batch of n <= 2048 scores
+ * ("# 상위 10% 제거해서 fake image에 concate.py:246-249"): thr = lerp(x_(k0), x_(k1), weight) by the named rule
+ * (torch.quantile), mask[i] = scores[i] CMP thr, then the stable partition rows[mask] -> kept, rows[~mask] ->
+ * dropped (rows may be NULL: threshold, mask and counts only).  workspace: n int64 (8*n bytes).
+ * counts_out = {#kept, #dropped}. */
+int sg_strain_rows(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp,
+                   const void* rows, int64_t row_bytes, void* kept, void* dropped, uint8_t* mask_out, float* thr_out,
+                   int64_t* counts_out, void* workspace, void* stream);
+
 /* out[i] = rows[idx[i]] for i < count (count read from *count_dev if non-NULL, else `count`). */
 int sg_gather_rows(const void* rows, int64_t row_bytes, const int64_t* idx, int64_t count,
                    const int64_t* count_dev, void* out, void* stream);

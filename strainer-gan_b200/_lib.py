@@ -36,6 +36,9 @@ _SIGS = {
     "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),
     "sg_ae_workspace_bytes": (c_size_t, [c_int64]),
     "sg_ae_score": (c_int, [P, c_int64, P, P, P, P, P]),
+    "sg_ae_bf16_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_ae_score_bf16": (c_int, [P, c_int64, P, P, P, P, P]),
+    "sg_ae_bf16_check": (c_int, [P, P]),
     "sg_mlp_workspace_bytes": (c_size_t, [c_int64]),
     "sg_mlp_score": (c_int, [P, c_int64, P, P, P, P, P, P]),
     "sg_select_begin": (c_int, [P, c_int64, P]),
@@ -50,6 +53,7 @@ _SIGS = {
     "sg_compact_workspace_bytes": (c_size_t, [c_int64]),
     "sg_compact_indices": (c_int, [P, c_int64, P, c_int, c_int64, P, P, P, P, P]),
     "sg_compact_rows": (c_int, [P, c_int64, c_int64, P, P, P, P, P, P]),
+    "sg_strain_rows": (c_int, [P, c_int64, c_int, c_int, c_float, c_int, c_int, P, c_int64, P, P, P, P, P, P, P]),
     "sg_gather_rows": (c_int, [P, c_int64, P, c_int64, P, P, P]),
     "sg_sort_workspace_bytes": (c_size_t, [c_int64]),
     "sg_sort_f32": (c_int, [P, c_int64, P, P, P, P]),

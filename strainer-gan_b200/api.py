@@ -292,7 +292,13 @@ class D64Scorer:
         return tuple((t.data_ptr(), t._version) for t in ts)
 
     def repack(self, discriminator: nn.Module, force: bool = False):
-        convs, bns = _d64_modules(discriminator)
+        # fast path: same module object, same parameter / buffer tensors, same versions -> nothing to do
+        cached = getattr(self, "_mods", None)
+        if cached is not None and cached[0] is discriminator and not force:
+            convs, bns = cached[1], cached[2]
+        else:
+            convs, bns = _d64_modules(discriminator)
+            self._mods = (discriminator, convs, bns)
         sig = self._signature(convs, bns)
         if sig == self._sig and not force:
             return
@@ -433,9 +439,14 @@ class MLPScorer:
             raise NotImplementedError(f"strainer_b200 scores the reference 784-1024-512-256-1 MLP only; got {shapes}")
         return lins
 
-    def refresh(self, discriminator):
+    def refresh(self, discriminator, force: bool = False):
+        lins = self.linears(discriminator)
+        sig = tuple((t.data_ptr(), t._version) for m in lins for t in (m.weight, m.bias))
+        if sig == getattr(self, "_sig", None) and not force:
+            return
+        self._sig = sig
         self.params = []
-        for m in self.linears(discriminator):
+        for m in lins:
             self.params += [_f32c(m.weight.detach(), self.device), _f32c(m.bias.detach(), self.device)]
         self.arr = (L.P * 8)(*[t.data_ptr() for t in self.params])
 
@@ -445,6 +456,22 @@ class MLPScorer:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
         L.check(self.lib.sg_mlp_score(_p(x), b, self.arr, _p(self.ws), _p(logit), _p(prob), _p(loss), _stream()),
                 "sg_mlp_score")
+
+
+_MLP_SCORERS: dict = {}
+
+
+def get_mlp_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096) -> "MLPScorer":
+    """Per-module cache: the weights are uploaded again only when a parameter tensor changed."""
+    device = _dev(device)
+    key = (id(discriminator), device.index, max_batch)
+    sc = _MLP_SCORERS.get(key)
+    if sc is None:
+        sc = MLPScorer(discriminator, device, max_batch)
+        _MLP_SCORERS[key] = sc
+    else:
+        sc.refresh(discriminator)
+    return sc
 
 
 def _is_mlp(netD) -> bool:
@@ -751,15 +778,29 @@ def _ae_params(autoencoder: nn.Module, device):
     return ps
 
 
-def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: int = 2048) -> torch.Tensor:
-    """Per-sample reconstruction MSE of the reference AutoEncoder on the GPU; fp32 device tensor [N]."""
+def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: int = 2048, *,
+              conv_mode: str = "fp32") -> torch.Tensor:
+    """Per-sample reconstruction MSE of the reference AutoEncoder on the GPU; fp32 device tensor [N].
+    conv_mode 'fp32': every layer in fp32 on the CUDA cores (reference parity, 1e-3 relative);
+    'bf16' (BASELINE config 4): the two 7x7 layers on tcgen05 with bf16 operands, bf16 activations."""
     device = _dev(device)
     lib = _lib_for(device)
+    if conv_mode not in ("fp32", "bf16"):
+        raise ValueError("conv_mode must be 'fp32' or 'bf16'")
     params = _ae_params(autoencoder, device)
     arr = (L.P * 12)(*[t.data_ptr() for t in params])
     n = images.shape[0]
     err = torch.empty(n, dtype=torch.float32, device=device)
-    ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(min(chunk, max(n, 1))))
+    cb = min(chunk, max(n, 1))
+    if conv_mode == "bf16":
+        ws = _Scratch.get(device, "ae_bf16", lib.sg_ae_bf16_workspace_bytes(cb))
+        for i in range(0, n, chunk):
+            x = _f32c(images[i:i + chunk], device)
+            L.check(lib.sg_ae_score_bf16(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()),
+                    "sg_ae_score_bf16")
+        L.check(lib.sg_ae_bf16_check(_p(ws), _stream()), "sg_ae_bf16_check")
+        return err
+    ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(cb))
     for i in range(0, n, chunk):
         x = _f32c(images[i:i + chunk], device)
         L.check(lib.sg_ae_score(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()), "sg_ae_score")
@@ -779,13 +820,13 @@ def mean_plus_k_std(values: torch.Tensor, k: float) -> torch.Tensor:
     return thr
 
 
-def detect_outliers_autoencoder(autoencoder, dataset, device, threshold=2.0):
+def detect_outliers_autoencoder(autoencoder, dataset, device, threshold=2.0, *, conv_mode: str = "fp32"):
     """``detect_outliers_autoencoder`` ("#autoencoder.py:307-322"): per-sample reconstruction MSE,
     inlier = error < mean + threshold * std (unbiased).  Returns a CPU torch.BoolTensor [N] like the
     reference (whose errors are ``.cpu()``'d)."""
     device = _dev(device)
     autoencoder.eval()
-    err = ae_errors(autoencoder, _dataset_images(dataset), device)
+    err = ae_errors(autoencoder, _dataset_images(dataset), device, conv_mode=conv_mode)
     thr = mean_plus_k_std(err, threshold)
     _, _, mask = compact_indices(err, thr, L.SG_LT, 0, want_mask=True)
     return mask.bool().cpu()
@@ -799,12 +840,46 @@ def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1,
     pre-sized buffer (the ``torch.cat`` of ":268" fused away); use ``concat_fake`` for autograd."""
     device = real.device
     scores = real_scores.reshape(-1).to(torch.float32).contiguous()
+    n = scores.numel()
+    if 1 <= n <= 2048 and n == real.shape[0]:
+        # one batch: sort + torch.quantile's lerp + mask + stable partition ranks in ONE CTA, then the row mover
+        lib = _lib_for(device)
+        k0, k1, w = _torch_quantile_plan(n, float(q))
+        rows = real.contiguous()
+        row_bytes = rows[0].numel() * rows.element_size()
+        if row_bytes % 16:
+            raise ValueError("row size must be a multiple of 16 bytes")
+        kept, dropped = torch.empty_like(rows), torch.empty_like(rows)
+        mask = torch.empty(n, dtype=torch.uint8, device=device)
+        thr = torch.empty(1, dtype=torch.float32, device=device)
+        counts = torch.empty(2, dtype=torch.int64, device=device)
+        ws = _Scratch.get(device, "strain", 8 * n)
+        L.check(lib.sg_strain_rows(_p(scores), n, k0, k1, float(w), L.SG_LERP_TORCH, L.SG_GE, _p(rows), row_bytes,
+                                   _p(kept), _p(dropped), _p(mask), _p(thr), _p(counts), _p(ws), _stream()),
+                "sg_strain_rows")
+        nk, nd = _read_counts(counts)
+        return kept[:nk], dropped[:nd], mask.view(torch.bool), thr[0]
     thr = quantile_device(scores, q)
     _, _, mask = compact_indices(scores, thr, L.SG_GE, 0, want_mask=True)
     kept, dropped, counts = partition_rows(real, mask)
-    c = counts.cpu()
-    nk, nd = int(c[0]), int(c[1])
+    nk, nd = _read_counts(counts)
     return kept[:nk], dropped[:nd], mask.bool(), thr[0]
+
+
+_PINNED: dict = {}
+
+
+def _read_counts(counts: torch.Tensor):
+    """The one synchronisation of the strain block (the reference's boolean indexing has two): the output
+    shapes depend on the counts.  Pinned staging + a stream sync instead of a pageable ``.cpu()``."""
+    key = counts.device.index
+    h = _PINNED.get(key)
+    if h is None:
+        h = torch.empty(2, dtype=torch.int64).pin_memory()
+        _PINNED[key] = h
+    h.copy_(counts, non_blocking=True)
+    torch.cuda.current_stream(counts.device).synchronize()
+    return int(h[0]), int(h[1])
 
 
 def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "fp32"):
@@ -822,7 +897,7 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
         if netD.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in netD.modules()):
             raise NotImplementedError("train-mode Dropout draws from torch's RNG stream and cannot be mirrored; "
                                       "score with netD.eval() (Dropout = identity)")
-        sc = MLPScorer(netD, device, max_batch=max(b, 512))
+        sc = get_mlp_scorer(netD, device, max_batch=max(b, 512))
         sc.score_into(_f32c(real.reshape(b, -1), device), None, prob, None)
         return strain_scores(real, prob, q)
     sc = get_scorer(netD, device, conv_mode, max_batch=max(real.shape[0], 512))
@@ -833,24 +908,10 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
     return strain_scores(real, prob, q)
 
 
-class _ConcatFake(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, fake, strained):
-        ctx.nf = fake.shape[0]
-        out = torch.empty((fake.shape[0] + strained.shape[0],) + tuple(fake.shape[1:]), dtype=fake.dtype,
-                          device=fake.device)
-        out[:ctx.nf].copy_(fake)
-        out[ctx.nf:].copy_(strained)
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        return g[:ctx.nf], g[ctx.nf:]
-
-
 def concat_fake(fake: torch.Tensor, strained: torch.Tensor) -> torch.Tensor:
-    """``torch.cat([fake, filtered_fake], dim=0)`` (":268"); gradient flows to the generator rows."""
-    return _ConcatFake.apply(fake, strained)
+    """``torch.cat([fake, filtered_fake], dim=0)`` (":268"); gradient flows to the generator rows.  The rows
+    come out of ``strain_batch`` already compacted, so this is the reference's own single copy kernel."""
+    return torch.cat([fake, strained], dim=0)
 
 
 def sample_pool(pool: torch.Tensor, b: int, indices: torch.Tensor | None = None) -> torch.Tensor:

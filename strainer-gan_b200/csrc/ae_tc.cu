@@ -1,0 +1,575 @@
+// Auto-encoder reconstruction-error scoring in bf16 conv mode (BASELINE.json config 4: "autoencoder
+// reconstruction-loss straining, 64x64 RGB, batch 512, bf16 conv mode"; reference "#autoencoder.py:269-291"
+// forward + ":315-316" per-sample MSE).
+//
+// 86 % of the auto-encoder's 46.6 MFLOP/sample sit in its two 7x7 layers; they run as implicit GEMMs on
+// tcgen05 (bf16 operands, fp32 accumulators in TMEM), the four small stride-2 layers (channels 3/16/32) stay
+// on the CUDA cores.  All activations are bf16 NHWC so that a filter tap of a pixel tile is one TMA box:
+//
+//   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> bf16 [32][32][16]            CUDA cores
+//   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> bf16 [16][16][32]                         CUDA cores
+//   L3 enc Conv 32->64 k7                -> bf16 [10][10][64]     tcgen05: M = the 100 output pixels of one image
+//        (rows 100..127 of the 128-row tile are dead), N = 64, K-step = two horizontally adjacent taps x 32
+//        channels = 64 contiguous bf16 of the NHWC input (an overlapping-stride TMA view), 7 x 4 K-steps
+//        (the 8th tap of a row has zero weights)
+//   L4 dec ConvT 64->32 k7 + ReLU        -> bf16 [16][16][32]     tcgen05, gather form: M = 128 output pixels
+//        (half an image), N = 32, K-step = one tap x 64 channels, 49 K-steps; input coordinates outside the
+//        10x10 map (negative too) are TMA zero fill
+//   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> bf16 [32][32][16]  CUDA cores, one 2x2 output quad per thread
+//   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace sg {
+namespace aetc {
+
+using namespace ptx;
+
+constexpr int kErrBase = 40;
+constexpr int kKs3 = 28, kKs4 = 49;                      // K-steps of 64 of the two 7x7 layers
+constexpr size_t kW3Bytes = (size_t)64 * kKs3 * 64 * 2;  // packed bf16 weights
+constexpr size_t kW4Bytes = (size_t)32 * kKs4 * 64 * 2;
+constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100 * 64 * 2, kAct4 = 256 * 32 * 2,
+                 kAct5 = 32 * 32 * 16 * 2;              // bytes per sample
+
+struct Layout {
+  size_t flag, w3, w4, a1, a2, a3, a4, a5, total;
+};
+static Layout layout(int64_t batch) {
+  Layout L;
+  size_t o = 0;
+  L.flag = o; o += 1024;
+  L.w3 = o; o += align_up(kW3Bytes, 1024);
+  L.w4 = o; o += align_up(kW4Bytes, 1024);
+  L.a1 = o; o += align_up(kAct1 * batch, 1024);
+  L.a2 = o; o += align_up(kAct2 * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
+  L.a3 = o; o += align_up(kAct3 * batch, 1024);
+  L.a4 = o; o += align_up(kAct4 * batch, 1024);
+  L.a5 = o; o += align_up(kAct5 * batch, 1024);
+  L.total = o;
+  return L;
+}
+
+// w3 [64][32][7][7] (Conv2d: out, in, kh, kw)  -> bf16 [oc][ks = kh*4 + kwp][j = px*32 + c], kw = 2*kwp + px (kw == 7 -> 0)
+// w4 [64][32][7][7] (ConvTranspose2d: in, out, kh, kw) -> bf16 [oc][ks = ky*7 + kx][ic]
+__global__ void pack_k7_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
+                               __nv_bfloat16* __restrict__ p4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * kKs3 * 64) {
+    const int j = i & 63, ks = (i >> 6) % kKs3, oc = i / (64 * kKs3);
+    const int kh = ks >> 2, kw = 2 * (ks & 3) + (j >> 5), c = j & 31;
+    p3[i] = __float2bfloat16_rn(kw < 7 ? w3[((oc * 32 + c) * 7 + kh) * 7 + kw] : 0.f);
+  }
+  if (i < 32 * kKs4 * 64) {
+    const int ic = i & 63, ks = (i >> 6) % kKs4, oc = i / (64 * kKs4);
+    const int ky = ks / 7, kx = ks % 7;
+    p4[i] = __float2bfloat16_rn(w4[((ic * 32 + oc) * 7 + ky) * 7 + kx]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The two 7x7 layers on tcgen05 (structure of d64.cu's conv_umma_kernel: warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-5 epilogue, mbarrier ring, two ping-pong accumulators in TMEM).
+// ------------------------------------------------------------------------------------------
+template <int N, bool CONVT>
+struct K7Cfg {
+  static constexpr int kABytes = 128 * 128;                        // 128 rows x 64 bf16 (SWIZZLE_128B)
+  static constexpr int kALoad = CONVT ? kABytes : 100 * 128;       // bytes TMA actually writes (10 x 10 box for L3)
+  static constexpr int kBBytes = N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = 2 * N;
+  static constexpr int kKSteps = CONVT ? kKs4 : kKs3;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+};
+
+template <int N, bool CONVT>
+__global__ void __launch_bounds__(192, 1)
+ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
+  using Cfg = K7Cfg<N, CONVT>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  const uint32_t bar0 = base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int img = CONVT ? (tile >> 1) : tile;
+        const int y0 = CONVT ? (tile & 1) * 8 : 0;
+        for (int ks = 0; ks < Cfg::kKSteps; ++ks) {
+          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 1)) { ok = false; break; }
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kALoad + Cfg::kBBytes);
+          if (CONVT) tma_load_4d(sa, &tmap_a, full_bar(stage), 0, -(ks % 7), y0 - ks / 7, img);   // in(y - ky, x - kx)
+          else tma_load_4d(sa, &tmap_a, full_bar(stage), 0, 2 * (ks & 3), ks >> 2, img);            // in(y + kh, x + kw)
+          tma_load_2d(sa + Cfg::kABytes, &tmap_b, full_bar(stage), ks * 64, 0);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 3)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+        for (int ks = 0; ks < Cfg::kKSteps; ++ks) {
+          if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 2)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sa = base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int img = CONVT ? (tile >> 1) : tile;
+      const bool valid = img < n_img && (CONVT || row < 100);
+      const size_t px = CONVT ? ((size_t)img * 256 + (tile & 1) * 128 + row) : ((size_t)img * 100 + row);
+      __nv_bfloat16* dst = out + px * N;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 4)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll
+      for (int cb = 0; cb < N; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(v[2 * j]) + __ldg(bias + cb + 2 * j);
+          float b = __uint_as_float(v[2 * j + 1]) + __ldg(bias + cb + 2 * j + 1);
+          if (CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }   // ReLU after the decoder's first layer only
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if (valid) {
+          uint4* d = reinterpret_cast<uint4*>(dst + cb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The four small layers (CUDA cores, fp32 math on bf16 activations)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// L1: x fp32 [n][3][64][64] -> a1 bf16 [n][32][32][16], one output pixel per thread
+__global__ void __launch_bounds__(256) enc1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ a1,
+                                                   int64_t n_img) {
+  __shared__ float s_w[27 * 16];
+  __shared__ float s_b[16];
+  for (int i = threadIdx.x; i < 27 * 16; i += 256) {
+    const int oc = i & 15, k = i >> 4;               // k = c*9 + ky*3 + kx
+    s_w[i] = w[oc * 27 + k];
+  }
+  if (threadIdx.x < 16) s_b[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t total = n_img * 1024;
+  for (int64_t p = blockIdx.x * 256ll + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
+    const int64_t n = p >> 10;
+    const int oy = (int)(p >> 5) & 31, ox = (int)p & 31;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = s_b[o];
+    const float* xin = x + n * 12288;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy - 1 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = 2 * ox - 1 + kx;
+          float v = 0.f;
+          if (iy >= 0 && iy < 64 && ix >= 0 && ix < 64) v = __ldg(xin + (c * 64 + iy) * 64 + ix);
+          const float* wr = s_w + (c * 9 + ky * 3 + kx) * 16;
+#pragma unroll
+          for (int o = 0; o < 16; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
+        }
+      }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack2(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+    uint4* d = reinterpret_cast<uint4*>(a1 + p * 16);
+    d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// L2: a1 bf16 [n][32][32][16] -> a2 bf16 [n][16][16][32], one output pixel per thread
+__global__ void __launch_bounds__(256) enc2_kernel(const __nv_bfloat16* __restrict__ a1, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ a2,
+                                                   int64_t n_img) {
+  __shared__ __align__(16) float s_w[9 * 16 * 32];   // [tap][ic][oc]
+  __shared__ float s_b[32];
+  for (int i = threadIdx.x; i < 9 * 16 * 32; i += 256) {
+    const int oc = i & 31, ic = (i >> 5) & 15, tap = i >> 9;
+    s_w[i] = w[(oc * 16 + ic) * 9 + tap];
+  }
+  if (threadIdx.x < 32) s_b[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t total = n_img * 256;
+  for (int64_t p = blockIdx.x * 256ll + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
+    const int64_t n = p >> 8;
+    const int oy = (int)(p >> 4) & 15, ox = (int)p & 15;
+    float acc[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) acc[o] = s_b[o];
+    const __nv_bfloat16* in = a1 + n * (32 * 32 * 16);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy - 1 + ky;
+      if (iy < 0 || iy >= 32) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox - 1 + kx;
+        if (ix < 0 || ix >= 32) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(in + (iy * 32 + ix) * 16);
+        float v[16];
+        unpack8(__ldg(src), v);
+        unpack8(__ldg(src + 1), v + 8);
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * 512);
+#pragma unroll
+        for (int ic = 0; ic < 16; ++ic)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w4 = wr[ic * 8 + q];
+            acc[4 * q] = fmaf(v[ic], w4.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v[ic], w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v[ic], w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v[ic], w4.w, acc[4 * q + 3]);
+          }
+      }
+    }
+    uint4* d = reinterpret_cast<uint4*>(a2 + p * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      d[q] = make_uint4(pack2(fmaxf(acc[8 * q], 0.f), fmaxf(acc[8 * q + 1], 0.f)),
+                        pack2(fmaxf(acc[8 * q + 2], 0.f), fmaxf(acc[8 * q + 3], 0.f)),
+                        pack2(fmaxf(acc[8 * q + 4], 0.f), fmaxf(acc[8 * q + 5], 0.f)),
+                        pack2(fmaxf(acc[8 * q + 6], 0.f), fmaxf(acc[8 * q + 7], 0.f)));
+  }
+}
+
+// ConvTranspose2d k3 s2 p1 op1 in gather form: out(y, x) += in((y + 1 - ky) / 2, (x + 1 - kx) / 2) * w[ic][oc][ky][kx]
+// for even (y + 1 - ky), (x + 1 - kx).  One thread owns the 2x2 output quad (2qy + py, 2qx + px): it reads the
+// four inputs (qy + dy, qx + dx) and every thread does the same 9 taps (no divergence):
+//   py = 0: dy = 0, ky = 1          py = 1: dy = 0 -> ky = 2, dy = 1 -> ky = 0        (same in x)
+__device__ __forceinline__ int tap_k(int parity, int d) { return parity == 0 ? 1 : (d ? 0 : 2); }
+
+// L5: a4 bf16 [n][16][16][32] -> a5 bf16 [n][32][32][16] (+ReLU)
+__global__ void __launch_bounds__(256) dec2_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ a5,
+                                                   int64_t n_img) {
+  __shared__ __align__(16) float s_w[9 * 32 * 16];   // [tap = ky*3+kx][ic][oc]
+  __shared__ float s_b[16];
+  for (int i = threadIdx.x; i < 9 * 32 * 16; i += 256) {
+    const int oc = i & 15, ic = (i >> 4) & 31, tap = i >> 9;
+    s_w[i] = w[(ic * 16 + oc) * 9 + tap];
+  }
+  if (threadIdx.x < 16) s_b[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t total = n_img * 256;
+  for (int64_t p = blockIdx.x * 256ll + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
+    const int64_t n = p >> 8;
+    const int qy = (int)(p >> 4) & 15, qx = (int)p & 15;
+    const __nv_bfloat16* in = a4 + n * (16 * 16 * 32);
+    float acc[4][16];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[o][c] = s_b[c];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = qy + dy, ix = qx + dx;
+        if (iy >= 16 || ix >= 16) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(in + (iy * 16 + ix) * 32);
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) unpack8(__ldg(src + q), v + 8 * q);
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          if (py == 0 && dy == 1) continue;
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            if (px == 0 && dx == 1) continue;
+            const float4* wr = reinterpret_cast<const float4*>(s_w + (tap_k(py, dy) * 3 + tap_k(px, dx)) * 512);
+            float* a = acc[py * 2 + px];
+#pragma unroll
+            for (int ic = 0; ic < 32; ++ic)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w4 = wr[ic * 4 + q];
+                a[4 * q] = fmaf(v[ic], w4.x, a[4 * q]);
+                a[4 * q + 1] = fmaf(v[ic], w4.y, a[4 * q + 1]);
+                a[4 * q + 2] = fmaf(v[ic], w4.z, a[4 * q + 2]);
+                a[4 * q + 3] = fmaf(v[ic], w4.w, a[4 * q + 3]);
+              }
+          }
+        }
+      }
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const float* a = acc[py * 2 + px];
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack2(fmaxf(a[2 * j], 0.f), fmaxf(a[2 * j + 1], 0.f));
+        uint4* d = reinterpret_cast<uint4*>(a5 + ((n * 32 + 2 * qy + py) * 32 + 2 * qx + px) * 16);
+        d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+  }
+}
+
+// L6: a5 bf16 [n][32][32][16] -> tanh(ConvT 16->3) fp32, squared error against x, per-sample mean.
+// One CTA per sample: 256 threads x 4 quads; fixed-order double reduction (reproducible).
+__global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __restrict__ a5, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* __restrict__ x,
+                                                       float* __restrict__ recon, float* __restrict__ err) {
+  __shared__ float s_w[9 * 16 * 3];   // [tap][ic][oc]
+  __shared__ float s_b[3];
+  __shared__ double s_red[256];
+  for (int i = threadIdx.x; i < 9 * 16 * 3; i += 256) {
+    const int oc = i % 3, ic = (i / 3) & 15, tap = i / 48;
+    s_w[i] = w[(ic * 3 + oc) * 9 + tap];
+  }
+  if (threadIdx.x < 3) s_b[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t n = blockIdx.x;
+  const __nv_bfloat16* in = a5 + n * (32 * 32 * 16);
+  const float* xin = x + n * 12288;
+  double sq = 0.0;
+  for (int qi = threadIdx.x; qi < 1024; qi += 256) {
+    const int qy = qi >> 5, qx = qi & 31;
+    float acc[4][3];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[o][c] = s_b[c];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = qy + dy, ix = qx + dx;
+        if (iy >= 32 || ix >= 32) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(in + (iy * 32 + ix) * 16);
+        float v[16];
+        unpack8(__ldg(src), v);
+        unpack8(__ldg(src + 1), v + 8);
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          if (py == 0 && dy == 1) continue;
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            if (px == 0 && dx == 1) continue;
+            const float* wr = s_w + (tap_k(py, dy) * 3 + tap_k(px, dx)) * 48;
+            float* a = acc[py * 2 + px];
+#pragma unroll
+            for (int ic = 0; ic < 16; ++ic) {
+              a[0] = fmaf(v[ic], wr[ic * 3], a[0]);
+              a[1] = fmaf(v[ic], wr[ic * 3 + 1], a[1]);
+              a[2] = fmaf(v[ic], wr[ic * 3 + 2], a[2]);
+            }
+          }
+        }
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const int off = (c * 64 + 2 * qy + py) * 64 + 2 * qx;
+        const float r0 = tanhf(acc[py * 2][c]), r1 = tanhf(acc[py * 2 + 1][c]);
+        const float2 t = __ldg(reinterpret_cast<const float2*>(xin + off));
+        const float d0 = r0 - t.x, d1 = r1 - t.y;
+        sq += (double)(d0 * d0) + (double)(d1 * d1);
+        if (recon) *reinterpret_cast<float2*>(recon + n * 12288 + off) = make_float2(r0, r1);
+      }
+  }
+  s_red[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) err[n] = (float)(s_red[0] / 12288.0);
+}
+
+template <int N, bool CONVT>
+static int launch_k7(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
+                     int64_t batch, int* err, cudaStream_t st) {
+  using Cfg = K7Cfg<N, CONVT>;
+  CUtensorMap ta, tb;
+  if (CONVT) {
+    // a3 [n][10][10][64]: box = 64 ch x 16 cols x 8 rows of one image, start (-kx, y0 - ky): outside -> zeros
+    cuuint64_t dims[4] = {64, 10, 10, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {128, 1280, 12800};
+    cuuint32_t box[4] = {64, 16, 8, 1};
+    int r = encode_tmap(&ta, 4, act_in, dims, strides, box);
+    if (r != SG_OK) return r;
+  } else {
+    // a2 [n][16][16][32] seen as rows of TWO adjacent pixels (64 bf16) at a one-pixel (64 B) stride
+    cuuint64_t dims[4] = {64, 16, 16, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {64, 1024, 16384};
+    cuuint32_t box[4] = {64, 10, 10, 1};
+    int r = encode_tmap(&ta, 4, act_in, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cfg::kKSteps * 64, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)Cfg::kKSteps * 64 * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)N};
+    int r = encode_tmap(&tb, 2, wpk, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  const int64_t tiles = CONVT ? 2 * batch : batch;
+  const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
+  ae_k7_kernel<N, CONVT><<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, (int)tiles, err);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+}  // namespace aetc
+}  // namespace sg
+
+extern "C" {
+
+int sg_ae_tc_init_attributes() {
+  using namespace sg::aetc;
+  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               K7Cfg<64, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               K7Cfg<32, true>::kSmemBytes));
+  return SG_OK;
+}
+
+size_t sg_ae_bf16_workspace_bytes(int64_t max_batch) { return sg::aetc::layout(max_batch < 1 ? 1 : max_batch).total; }
+
+int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
+                     float* recon_out, void* stream) {
+  using namespace sg::aetc;
+  SG_READY();
+  SG_REQUIRE(x && h_params && workspace && err_out, "null pointer");
+  SG_REQUIRE(batch >= 0 && batch <= (1 << 20), "batch out of range");
+  SG_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  for (int i = 0; i < 12; ++i) SG_REQUIRE(h_params[i] != nullptr, "h_params must hold 12 device pointers (w, b) x 6");
+  if (batch == 0) return SG_OK;
+  cudaStream_t st = sg::as_stream(stream);
+  const Layout L = layout(batch);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* err = reinterpret_cast<int*>(ws + L.flag);
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
+  SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * batch, 0, 1024, st));
+  pack_k7_kernel<<<(64 * kKs3 * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
+  SG_LAUNCH_CHECK();
+  const int64_t cap = (int64_t)sg::state().sm_count * 8;
+  auto blocks = [&](int64_t items) { int64_t b = sg::ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
+  enc1_kernel<<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
+  SG_LAUNCH_CHECK();
+  enc2_kernel<<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
+  SG_LAUNCH_CHECK();
+  int r = launch_k7<64, false>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
+  if (r != SG_OK) return r;
+  r = launch_k7<32, true>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
+  if (r != SG_OK) return r;
+  dec2_kernel<<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
+  SG_LAUNCH_CHECK();
+  dec3_mse_kernel<<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_ae_bf16_check(const void* workspace, void* stream) {
+  SG_READY();
+  SG_REQUIRE(workspace != nullptr, "workspace");
+  int flag = 0;
+  SG_CUDA(cudaMemcpyAsync(&flag, workspace, 4, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
+  SG_CUDA(cudaStreamSynchronize(sg::as_stream(stream)));
+  if (flag != 0) {
+    sg::set_error("auto-encoder tcgen05 pipeline timed out waiting on an mbarrier (code %d)", flag);
+    return SG_ECUDA;
+  }
+  return SG_OK;
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@
 extern "C" int sg_d64_init_attributes();  // internal: raises the conv kernels' dynamic smem limit
 extern "C" int sg_ae_init_attributes();
 extern "C" int sg_select_init_attributes();
+extern "C" int sg_ae_tc_init_attributes();
 
 namespace sg {
 
@@ -85,6 +86,19 @@ __device__ __forceinline__ bool cmp_apply(float v, float thr, int cmp) {
     default: r = v > thr; break;
   }
   return (cmp & SG_NOT) ? !r : r;
+}
+
+// The two interpolation rules of the reference's quantile calls, with their exact rounding steps.
+__device__ __forceinline__ float lerp_rule(float a, float b, float w, int kind) {
+  const float d = __fsub_rn(b, a);
+  if (kind == SG_LERP_NUMPY) {
+    // numpy _lerp with fp32 operands: separate roundings, no contraction
+    float r = __fadd_rn(a, __fmul_rn(d, w));
+    if (w >= 0.5f) r = __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, w)));
+    return r;
+  }
+  // torch.lerp: fused forms
+  return (fabsf(w) < 0.5f) ? __fmaf_rn(w, d, a) : __fmaf_rn(-d, __fsub_rn(1.0f, w), b);
 }
 
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {

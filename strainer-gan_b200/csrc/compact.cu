@@ -292,6 +292,90 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int4* __restrict
   for (; j < row_vec; j += 256) stg_stream_i4(dst + j, ldg_stream_i4(src + j));
 }
 
+// ------------------------------------------------------------------------------------------
+// The whole selection half of the in-batch strain block in ONE CTA
+// ("# 상위 10% 제거해서 fake image에 concate.py:246-249": thr = torch.quantile(scores, q); mask = scores >= thr;
+// real[mask], real[~mask]) for B <= 2048 scores: bitonic sort of the radix keys in shared memory, the
+// library's interpolation rule, the mask, and the stable two-way partition ranks -- the reference spends
+// a sort kernel, a lerp, a compare, two nonzero() (each a device sync) and two index_select launches here.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) strain_small_kernel(const float* __restrict__ v, int n, int pow2, int k0, int k1,
+                                                            float w, int lerp_kind, int cmp, float* __restrict__ thr_out,
+                                                            uint8_t* __restrict__ mask_out, int64_t* __restrict__ dest,
+                                                            int64_t* __restrict__ counts_out) {
+  extern __shared__ uint32_t s_keys[];   // pow2 keys
+  __shared__ int s_nan;
+  __shared__ float s_thr;
+  __shared__ int s_wsum[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) s_nan = 0;
+  __syncthreads();
+  for (int i = t; i < pow2; i += blockDim.x) {
+    uint32_t key = 0xFFFFFFFFu;
+    if (i < n) {
+      key = float_to_key(v[i]);
+      if (key == 0xFFFFFFFFu) s_nan = 1;
+    }
+    s_keys[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = t; i < (pow2 >> 1); i += blockDim.x) {
+        const int lo = ((i / stride) * stride * 2) + (i % stride);
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const uint32_t a = s_keys[lo], b = s_keys[hi];
+        if ((a > b) == up) { s_keys[lo] = b; s_keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (t == 0) {
+    float r = __uint_as_float(0x7FC00000u);
+    if (!s_nan) r = lerp_rule(key_to_float(s_keys[k0]), key_to_float(s_keys[k1]), w, lerp_kind);
+    s_thr = r;
+    thr_out[0] = r;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  // two consecutive elements per thread (n <= 2048), block exclusive scan of the keep flags
+  const int i0 = 2 * t, i1 = 2 * t + 1;
+  const bool k0f = i0 < n && cmp_apply(v[i0], thr, cmp);
+  const bool k1f = i1 < n && cmp_apply(v[i1], thr, cmp);
+  const int c = (int)k0f + (int)k1f;
+  int x = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_wsum[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int sacc = (lane < (int)(blockDim.x >> 5)) ? s_wsum[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, sacc, o);
+      if (lane >= o) sacc += y;
+    }
+    s_wsum[lane] = sacc;
+  }
+  __syncthreads();
+  const int kept_before = x - c + (wid ? s_wsum[wid - 1] : 0);
+  const int total = s_wsum[(blockDim.x >> 5) - 1];
+  if (i0 < n) {
+    if (mask_out) mask_out[i0] = (uint8_t)k0f;
+    dest[i0] = k0f ? (int64_t)kept_before : -(int64_t)(i0 - kept_before) - 1;
+  }
+  if (i1 < n) {
+    const int kb = kept_before + (int)k0f;
+    if (mask_out) mask_out[i1] = (uint8_t)k1f;
+    dest[i1] = k1f ? (int64_t)kb : -(int64_t)(i1 - kb) - 1;
+  }
+  if (t == 0) { counts_out[0] = total; counts_out[1] = n - total; }
+}
+
 static size_t scan_ws_bytes(int64_t n) {
   const int64_t tiles = ceil_div(n > 0 ? n : 1, kTile);
   return align_up(sizeof(ScanWs) + (size_t)tiles * 8, 256);
@@ -359,6 +443,36 @@ int sg_compact_rows(const void* rows, int64_t n, int64_t row_bytes, const uint8_
   move_rows_kernel<<<(unsigned)n, 256, 0, st>>>(static_cast<const int4*>(rows), row_bytes / 16, dest,
                                                 static_cast<int4*>(kept), static_cast<int4*>(dropped));
   SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_strain_rows(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp, const void* rows,
+                   int64_t row_bytes, void* kept, void* dropped, uint8_t* mask_out, float* thr_out, int64_t* counts_out,
+                   void* workspace, void* stream) {
+  using namespace sg::cmp;
+  SG_READY();
+  SG_REQUIRE(scores && thr_out && counts_out && workspace, "null pointer");
+  SG_REQUIRE(n >= 1 && n <= 2048, "n must be in [1, 2048] (one batch)");
+  SG_REQUIRE(k0 >= 0 && k0 < n && k1 >= k0 && k1 < n, "need 0 <= k0 <= k1 < n");
+  SG_REQUIRE(lerp_kind == SG_LERP_NUMPY || lerp_kind == SG_LERP_TORCH, "lerp_kind");
+  SG_REQUIRE(cmp >= 0 && cmp <= (SG_GT | SG_NOT), "cmp");
+  SG_REQUIRE(rows == nullptr || (row_bytes > 0 && (row_bytes & 15) == 0), "row_bytes must be a positive multiple of 16");
+  SG_REQUIRE(((uintptr_t)rows & 15) == 0 && ((uintptr_t)kept & 15) == 0 && ((uintptr_t)dropped & 15) == 0,
+             "row buffers must be 16-byte aligned");
+  cudaStream_t st = sg::as_stream(stream);
+  int pow2 = 2;
+  while (pow2 < n) pow2 <<= 1;
+  int threads = pow2 / 2;
+  if (threads < 32) threads = 32;
+  int64_t* dest = static_cast<int64_t*>(workspace);
+  strain_small_kernel<<<1, threads, pow2 * sizeof(uint32_t), st>>>(scores, (int)n, pow2, k0, k1, weight, lerp_kind, cmp,
+                                                                  thr_out, mask_out, dest, counts_out);
+  SG_LAUNCH_CHECK();
+  if (rows != nullptr) {
+    move_rows_kernel<<<(unsigned)n, 256, 0, st>>>(static_cast<const int4*>(rows), row_bytes / 16, dest,
+                                                  static_cast<int4*>(kept), static_cast<int4*>(dropped));
+    SG_LAUNCH_CHECK();
+  }
   return SG_OK;
 }
 

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace sg {
 namespace d64 {
@@ -1396,26 +1397,12 @@ __global__ void read_activation_kernel(const __nv_bfloat16* __restrict__ act, in
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int encode(CUtensorMap* m, int rank, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides,
                   const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
                   CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(state().encode_tiled);
-  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
-    return SG_ECUDA;
-  }
-  return SG_OK;
+  return encode_tmap(m, rank, ptr, dims, strides, box, swz, dtype);
 }
 
-// One conv layer L (2..4): input activation S_in x S_in x c_in (planes), output (S_in/2)^2 x c_out.
 template <int BLOCK_N>
 static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
                        __nv_bfloat16* act_out,

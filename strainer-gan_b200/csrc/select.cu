@@ -500,18 +500,7 @@ __global__ void finish_kernel(const uint32_t* ws, float* out2) {
 
 __global__ void lerp_kernel(const float* stats2, float w, int kind, float* thr) {
   if (threadIdx.x != 0) return;
-  const float a = stats2[0], b = stats2[1];
-  float r;
-  if (kind == SG_LERP_NUMPY) {
-    // numpy _lerp with fp32 operands: separate roundings, no contraction
-    const float d = __fsub_rn(b, a);
-    r = __fadd_rn(a, __fmul_rn(d, w));
-    if (w >= 0.5f) r = __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, w)));
-  } else {
-    // torch.lerp: fused forms
-    const float d = __fsub_rn(b, a);
-    r = (fabsf(w) < 0.5f) ? __fmaf_rn(w, d, a) : __fmaf_rn(-d, __fsub_rn(1.0f, w), b);
-  }
+  const float r = lerp_rule(stats2[0], stats2[1], w, kind);
   thr[0] = r;
 }
 

@@ -116,3 +116,36 @@ def test_autoencoder_straining_golden(sb, golden):
         t = (te.mean() + thr_k * te.std()).item()
         near = np.abs(want - t) <= 1e-3 * abs(t)
         assert not ((got.numpy() != golden[key]) & ~near).any()
+
+
+def test_autoencoder_bf16_conv_mode(sb, golden):
+    """bf16 conv mode (BASELINE config 4, stated separately from the fp32 bar): 7x7 layers on tcgen05 with bf16
+    operands and bf16 activations.  Reconstruction errors within 2e-2 relative of the reference's fp32 values;
+    inlier masks may differ only for samples within that tolerance of the threshold.  Batch sizes around the
+    tile sizes (1 image = 1 tile of L3 = 2 tiles of L4) incl. a ragged last chunk."""
+    torch.manual_seed(O.SEED)
+    ae = O.AutoEncoder()
+    x = torch.from_numpy(O.synth_images(0, 160))
+    want = golden["g6_errors"]
+    err = sb.ae_errors(ae, x, "cuda", conv_mode="bf16").cpu().numpy()
+    rel = np.abs(err - want) / np.maximum(want, 1e-6)
+    assert rel.max() <= 2e-2, rel.max()
+    for n, chunk in ((1, 2048), (3, 2), (149, 64), (160, 2048)):
+        e2 = sb.ae_errors(ae, x[:n], "cuda", chunk=chunk, conv_mode="bf16").cpu().numpy()
+        assert np.array_equal(e2, err[:n]), (n, chunk)     # independent of batch size / chunking (fixed-order sums)
+    ds = torch.utils.data.TensorDataset(x, torch.zeros(160, dtype=torch.long))
+    got = sb.detect_outliers_autoencoder(ae, ds, "cuda", 2.0, conv_mode="bf16")
+    te = torch.from_numpy(want)
+    t = (te.mean() + 2.0 * te.std()).item()
+    near = np.abs(want - t) <= 2e-2 * abs(t)
+    assert not ((got.numpy() != golden["g6_inlier"]) & ~near).any()
+    # trained-looking weights: larger, non-default parameters exercise every tap of the 7x7 layers
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for p in ae.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.5 / np.sqrt(max(p[0].numel(), 1))))
+    ref = O.ae_errors(ae, x[:48]).numpy()
+    e3 = sb.ae_errors(ae, x[:48], "cuda", conv_mode="bf16").cpu().numpy()
+    assert (np.abs(e3 - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2
+    e4 = sb.ae_errors(ae, x[:48], "cuda").cpu().numpy()
+    assert (np.abs(e4 - ref) / np.maximum(ref, 1e-6)).max() <= 1e-3
