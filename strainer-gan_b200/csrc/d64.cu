@@ -240,6 +240,7 @@ struct ConvParams {
   const float* shift;         // [c_out]
   __nv_bfloat16* out;
   int* err;
+  int debug;                  // timing experiments only (results invalid): 1 = weight tile loaded once per stage slot, 2 = same for activations
 };
 
 template <int BLOCK_N>
@@ -451,10 +452,12 @@ struct PairCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = 6;
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kSsBytes = 2 * 512 * 4;   // folded-BN scale | shift of every output channel, staged once
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kSsBytes + 1024;
   static constexpr int kThreads = 192;
 };
 
+template <int SEGA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const ConvParams p) {
@@ -494,6 +497,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  float* s_ss = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
+  for (int i = threadIdx.x; i < p.c_out; i += Cfg::kThreads) { s_ss[i] = p.scale[i]; s_ss[512 + i] = p.shift[i]; }
   tc_fence_before();
   cluster_sync_all();                // peer barriers initialised before any remote arrive / TMA signal
   tc_fence_after();
@@ -523,9 +528,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          const bool first_use = (tile == pair && ks < S);
+          const bool load_a = first_use || !(p.debug & 2), load_b = first_use || !(p.debug & 1);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * ((load_a ? Cfg::kABytes : 0) + (load_b ? Cfg::kBBytes : 0)));
+          if (load_a)
           tma_load_5d_pair(sa, &tmap_a, lead_full, cc, (kw - 1) >> 1, (kh - 1) >> 1,
                            ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img0);
+          if (load_b)
           tma_load_2d_pair(sb, &tmap_b, lead_full, ks * 64, nt * BLOCK_N + (int)rank * 128);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -563,11 +572,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ================= epilogue (warps 2..5 of both CTAs): own 128 pixels x 256 channels =================
+    // One warp per scheduler and nothing to hide latency behind: keep the instruction count per column low
+    // (scale/shift as 128-bit shared-memory broadcasts, max-form LeakyReLU, packed conversion, SEGA resolved
+    // at compile time: the lo half only exists in fp32-parity mode).
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int ct = p.c_out * p.out_sega;
+    const int ct = p.c_out * SEGA;
+    const float slope = p.slope;
     for (int tile = pair; tile < p.total_tiles; tile += npairs) {
       const int nt = tile % p.n_tiles;
       const int mt = 2 * (tile / p.n_tiles) + (int)rank;
@@ -584,34 +597,40 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         off = (((size_t)img * ow_n + oh) * ow_n + ow) * ct;
       }
       __nv_bfloat16* dst = p.out + off + (size_t)nt * BLOCK_N;
+      const float4* sc4 = reinterpret_cast<const float4*>(s_ss + nt * BLOCK_N);
+      const float4* sh4 = reinterpret_cast<const float4*>(s_ss + 512 + nt * BLOCK_N);
       if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 20)) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#pragma unroll 1
+#pragma unroll 2
       for (int cb = 0; cb < BLOCK_N; cb += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + cb, v);
         tmem_ld_wait();
-        const float* sc = p.scale + nt * BLOCK_N + cb;
-        const float* sh = p.shift + nt * BLOCK_N + cb;
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = fmaf(__uint_as_float(v[2 * j]), __ldg(sc + 2 * j), __ldg(sh + 2 * j));
-          float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(sc + 2 * j + 1), __ldg(sh + 2 * j + 1));
-          a = a > 0.f ? a : p.slope * a;
-          b = b > 0.f ? b : p.slope * b;
-          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
-          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
-          const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-          const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
-          lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = sc4[(cb >> 2) + q], h4 = sh4[(cb >> 2) + q];
+          float a0 = fmaf(__uint_as_float(v[4 * q]), s4.x, h4.x), a1 = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y);
+          float a2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z), a3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w);
+          a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);   // LeakyReLU (0 < slope <= 1; slope 1 = identity)
+          a2 = fmaxf(a2, slope * a2); a3 = fmaxf(a3, slope * a3);
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+          hi[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
+          hi[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+          if (SEGA == 2) {
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(a0 - f01.x, a1 - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(a2 - f23.x, a3 - f23.y);
+            lo[2 * q] = *reinterpret_cast<const uint32_t*>(&l01);
+            lo[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+          }
         }
         if (valid) {
           uint4* d = reinterpret_cast<uint4*>(dst + cb);
 #pragma unroll
           for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          if (p.out_sega == 2) {
+          if (SEGA == 2) {
             uint4* dl = reinterpret_cast<uint4*>(dst + p.c_out + cb);
 #pragma unroll
             for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
@@ -1508,9 +1527,11 @@ static int launch_conv_pair(const __nv_bfloat16* act_in, const __nv_bfloat16* wp
   p.shift = shift;
   p.out = act_out;
   p.err = err;
+  p.debug = getenv("SG_DEBUG_SKIP") ? atoi(getenv("SG_DEBUG_SKIP")) : 0;
   int pairs = state().sm_count / 2;
   if (p.total_tiles < pairs) pairs = p.total_tiles;
-  conv_pair_kernel<<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  if (sega == 2) conv_pair_kernel<2><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  else conv_pair_kernel<1><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1646,7 +1667,8 @@ int sg_d64_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1Cfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
