@@ -191,7 +191,9 @@ def main():
     value = n_global / (ms_step * 1e-3)
     kept = int(count.item())
     nchunks = (shard + CHUNK - 1) // CHUNK
-    launches_per_step = nchunks * 5 + 1 + 3 * 2 + 1 + 1 + 1 + 1     # score | select begin,3x(hist,step),min,finish | lerp | compact
+    # kernels per step: 5 per scoring chunk | select: begin + cooperative radix phases (N = 1) or begin + 4 x (hist, step)
+    # + finish (N > 1, all-reduce between) | lerp | index compaction
+    launches_per_step = nchunks * 5 + (2 if world == 1 else 10) + 1 + 1
 
     # ---- per-kernel timing of the conv kernels inside a long loop (sustained clocks) ----------------------
     def layer_times(sc, reps):
@@ -216,7 +218,11 @@ def main():
     achieved_tf = FLOP_CONV * CHUNK / (conv_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (L2+L3+L4 implicit-GEMM launches of one chunk)",
                 "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sust"],
-                "peak_source": f"bf16_tflops_sustained of {pk['src']}", "traffic": None,
+                "peak_source": f"bf16_tflops_sustained of {pk['src']}",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the three launches at 8192 samples, bf16 mode, from the
+                # ncu --set full capture profiles/r1c_conv_kernels_full.txt (L2 1.074+0.507, L3 0.538+0.235, L4 0.273+0.104 GB)
+                "traffic": 2.731e9 if (args.mode == "bf16" and CHUNK == 8192) else None,
+                "traffic_unit": "bytes per launch group (ncu, profiles/r1c_conv_kernels_full.txt)",
                 "algorithmic_flops_per_sample": FLOP_CONV, "samples_per_launch_group": CHUNK,
                 "issued_tensor_flops_factor": nseg}
     kernels = {"chunk": CHUNK, "ms": {k: float(v) for k, v in zip(["conv1", "conv2", "conv3", "conv4", "head"], lt)},
