@@ -44,6 +44,17 @@ def test_find_elbow_threshold_bit_exact(sb, golden):
         assert t1 == t2 and np.array_equal(c1, c2) and np.array_equal(h1, h2, equal_nan=True)
     with pytest.raises(ValueError):
         sb.find_elbow_threshold(np.array([1.0, np.nan], np.float32))
+    # values on / one ulp around the fp32 linspace edges, and a range far from zero (coarse ulps): the
+    # edge-corrected binning must still agree with np.histogram count for count
+    for lo, hi in ((0.0, 7.3), (-3.0, 11.0), (1000.0, 1001.0), (-2.5e4, -2.4e4), (1e-3, 1.5e-3)):
+        edges = np.linspace(np.float32(lo), np.float32(hi), 101, dtype=np.float32)
+        pts = np.concatenate([edges, np.nextafter(edges, np.float32(np.inf)), np.nextafter(edges, np.float32(-np.inf)),
+                              rng.uniform(lo, hi, 200_000).astype(np.float32)])
+        pts = pts[(pts >= np.float32(lo)) & (pts <= np.float32(hi))].astype(np.float32)
+        rng.shuffle(pts)
+        t2, c2, h2 = sb.find_elbow_threshold(pts)
+        t1, c1, h1 = O.find_elbow_threshold(pts)
+        assert np.array_equal(h1, h2) and t1 == t2 and np.array_equal(c1, c2), (lo, hi)
 
 
 def test_detect_outliers_variants(sb, feats, golden):
