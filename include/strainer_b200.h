@@ -217,6 +217,19 @@ int sg_minmax(const float* v, int64_t n, float* minmax, void* stream);
  * counts[bins] int64 accumulated (caller zeroes). */
 int sg_hist_uniform(const float* v, int64_t n, const float* edges, int bins, long long* counts, void* stream);
 
+/* ---- two-component 1-D Gaussian-mixture EM ----------------------------------------------------
+ * replaces GaussianMixture(n_components=2, max_iter=10, tol=1e-2, reg_covar=5e-4).fit(losses) of
+ * "#clean 분포와 noisy 분포가 만나는 지점의 loss보다 작은 데.py:290-292", "# 종합 loss.py:271-273" (SURVEY 8f item 2).
+ * scikit-learn's EM equations; deterministic start (Lloyd iterations from two given centres) instead of the
+ * RNG-seeded k-means.  Protocol: sg_gmm1d_begin, then (kmeans_iters + max_iter) rounds of
+ * sg_gmm1d_accumulate -> [multi-GPU: all-reduce SUM of the 8 doubles at workspace + 128] -> sg_gmm1d_update;
+ * rounds after convergence are no-ops, nothing is read back in between.  Result: doubles at workspace + 0:
+ * weights[2], means[2], variances[2], lower bound, n_iter, converged. */
+size_t sg_gmm1d_workspace_bytes(void);
+int sg_gmm1d_begin(const float* init_centers2, int kmeans_iters, void* workspace, void* stream);
+int sg_gmm1d_accumulate(const float* v, int64_t n, void* workspace, void* stream);
+int sg_gmm1d_update(int64_t n_total, double reg_covar, double tol, int max_iter, void* workspace, void* stream);
+
 /* ---- device sort + 1-D DBSCAN clean ratio --------------------------------------------------
  * BASELINE.json north_star: "1-D DBSCAN thresholds on a device sort".  The reference's
  * estimate_ratio_dbscan ("# z_score + DBSCAN.py:272-301") consumes only the fraction of

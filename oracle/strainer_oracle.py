@@ -592,3 +592,46 @@ def sample_pool(pool: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
     """``potential_fake_data[indices]`` "# strainer gan + concate.py:623-624" for given indices
     (the reference draws ``torch.randperm(P)[:b]`` on the host)."""
     return pool[indices]
+
+
+def gmm_fit_deterministic(losses: np.ndarray, max_iter: int = 10, tol: float = 1e-2, reg_covar: float = 5e-4,
+                          kmeans_iters: int = 30):
+    """float64 restatement of the device EM (csrc/gmm.cu): scikit-learn's GaussianMixture equations
+    (mixture/_gaussian_mixture.py: _estimate_gaussian_parameters, _estimate_log_prob_resp, the tol test on the
+    mean log-likelihood) with Lloyd iterations from the 25 % / 75 % order statistics as the start -- the
+    documented deviation from "#clean ... .py:290-292", whose k-means start draws from the global numpy RNG."""
+    x = np.asarray(losses, np.float32).reshape(-1).astype(np.float64)
+    n = x.size
+    s = np.sort(np.asarray(losses, np.float32).reshape(-1))
+    mu = np.array([s[(n - 1) // 4], s[(3 * (n - 1)) // 4]], np.float64)
+    eps10 = 10 * np.finfo(np.float64).eps
+    for left in range(kmeans_iters - 1, -1, -1):
+        c1 = np.abs(x - mu[1]) < np.abs(x - mu[0])
+        n0, n1 = float((~c1).sum()), float(c1.sum())
+        m = np.array([x[~c1].sum() / n0 if n0 > 0 else mu[0], x[c1].sum() / n1 if n1 > 0 else mu[1]])
+        moved = not np.array_equal(m, mu)
+        if moved and left > 0:
+            mu = m
+            continue
+        break
+    r = np.stack([(~c1).astype(np.float64), c1.astype(np.float64)], 1)
+
+    def m_step(r):
+        nk = r.sum(0) + eps10
+        mu = (r * x[:, None]).sum(0) / nk
+        var = np.maximum((r * (x * x)[:, None]).sum(0) / nk - mu * mu, 0.0) + reg_covar
+        return nk / n, mu, var
+    w, mu, var = m_step(r)
+    lb, n_iter, converged = -np.inf, 0, False
+    for n_iter in range(1, max_iter + 1):
+        lp = np.log(w) - 0.5 * (np.log(2 * np.pi) + np.log(var)) - (x[:, None] - mu) ** 2 * (0.5 / var)
+        mx = lp.max(1)
+        lse = mx + np.log(np.exp(lp - mx[:, None]).sum(1))
+        r = np.exp(lp - lse[:, None])
+        w, mu, var = m_step(r)
+        new_lb = lse.mean()
+        change, lb = new_lb - lb, new_lb
+        if abs(change) < tol:
+            converged = True
+            break
+    return {"weights": w, "means": mu, "stds": np.sqrt(var), "n_iter": n_iter, "converged": converged}

@@ -59,6 +59,10 @@ _SIGS = {
     "sg_sort_f32": (c_int, [P, c_int64, P, P, P, P]),
     "sg_dbscan1d_workspace_bytes": (c_size_t, [c_int64]),
     "sg_dbscan1d": (c_int, [P, c_int64, c_double, c_int, P, P, P, P]),
+    "sg_gmm1d_workspace_bytes": (c_size_t, []),
+    "sg_gmm1d_begin": (c_int, [P, c_int, P, P]),
+    "sg_gmm1d_accumulate": (c_int, [P, c_int64, P, P]),
+    "sg_gmm1d_update": (c_int, [c_int64, c_double, c_double, c_int, P, P]),
     "sg_chunk_moments": (c_int, [P, c_int64, P, P]),
     "sg_moments_finish": (c_int, [P, c_int64, c_int64, c_float, P, P, P]),
     "sg_col_moments_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -572,6 +572,62 @@ def strain_shard(images: torch.Tensor, discriminator, loss_ratio=0.2, *, group=N
     return idx, thr, losses
 
 
+class ResidentSubset:
+    """Device-resident replacement for ``Subset`` + a fresh ``DataLoader`` per epoch ("# final.py:444",
+    SURVEY 8f item 1): the strain result stays a kept-index tensor on the GPU and every batch is one
+    vectorised row gather from the resident image tensor -- no host index list, no per-sample
+    ``__getitem__``, no H2D copies.
+
+        sub = ResidentSubset.refine(images_dev, netD, loss_ratio=0.2)     # = refine_dataset_by_loss, on device
+        for epoch in ...:
+            for real in sub.batches(128, shuffle=True, generator=g):       # [b,3,64,64] device tensors
+                ...
+
+    ``indices`` are ascending (the reference's ``np.where`` order); ``batches(shuffle=False)`` therefore yields
+    exactly ``DataLoader(Subset(dataset, clean_indices), batch_size, shuffle=False)``'s image batches."""
+
+    def __init__(self, images: torch.Tensor, indices: torch.Tensor, threshold=None):
+        if not images.is_cuda:
+            raise ValueError("ResidentSubset keeps the dataset in HBM: pass a CUDA tensor")
+        self.images = images.contiguous()
+        self.indices = indices.to(device=images.device, dtype=torch.int64).contiguous()
+        self.threshold = threshold
+
+    def __len__(self):
+        return int(self.indices.numel())
+
+    @classmethod
+    def refine(cls, images: torch.Tensor, discriminator, loss_ratio=0.2, *, conv_mode: str = "fp32"):
+        """``refine_dataset_by_loss`` ("#strainer gan.py:364-392") without leaving the device."""
+        device = _dev(images.device)
+        discriminator.eval()
+        losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
+        thr = percentile_device(losses, (1 - loss_ratio) * 100)
+        idx, count, _ = compact_indices(losses, thr, L.SG_LT, 0)
+        c = int(count.item())
+        if c == 0:   # the reference's degenerate fallback keeps index 0, n // 2 times
+            return cls(images, torch.zeros(max(images.shape[0] // 2, 1), dtype=torch.int64, device=device), thr)
+        return cls(images, idx[:c], thr)
+
+    def batches(self, batch_size: int, shuffle: bool = True, generator=None, drop_last: bool = False):
+        device = self.images.device
+        lib = _lib_for(device)
+        n = len(self)
+        order = self.indices
+        if shuffle:
+            perm = torch.randperm(n, device=device, generator=generator)
+            order = self.indices.index_select(0, perm)
+        row_bytes = self.images[0].numel() * self.images.element_size()
+        for i in range(0, n, batch_size):
+            idx = order[i:i + batch_size]
+            if drop_last and idx.numel() < batch_size:
+                break
+            out = torch.empty((idx.numel(),) + tuple(self.images.shape[1:]), dtype=self.images.dtype, device=device)
+            L.check(lib.sg_gather_rows(_p(self.images), row_bytes, _p(idx), idx.numel(), L.P(0), _p(out), _stream()),
+                    "sg_gather_rows")
+            yield out
+
+
 def get_percentile_threshold(losses, percentile=75):
     """"# 종합 loss.py:287-288" on a device (or host) loss vector."""
     lt = _f32c(losses, _dev()).reshape(-1)
@@ -595,9 +651,41 @@ def _gmm_intersection(means, stds):
     return (-b + np.sqrt(b ** 2 - 4 * a * c)) / (2 * a)
 
 
-def get_gmm_threshold(losses):
-    """"# 종합 loss.py:270-285".  The 2-component EM fit stays scikit-learn on the host (SURVEY §2.2
-    K18); it is seeded by the global np.random state exactly like the reference."""
+def gmm_fit_device(losses, max_iter: int = 10, tol: float = 1e-2, reg_covar: float = 5e-4, *, group=None,
+                   n_global=None, kmeans_iters: int = 30):
+    """2-component 1-D Gaussian-mixture EM on the GPU: sklearn's EM equations
+    (``GaussianMixture(n_components=2, max_iter, tol, reg_covar)``) with a DETERMINISTIC initialisation -- Lloyd
+    iterations from the 25 % / 75 % order statistics instead of a k-means run seeded by the global numpy RNG.
+    With ``group`` the losses are this rank's shard: 8 partial sums are all-reduced per iteration, every rank
+    obtains the identical fit.  Returns dict(weights, means, stds, n_iter, converged) (float64 numpy)."""
+    device = _dev()
+    lib = _lib_for(device)
+    v = _f32c(losses, device).reshape(-1)
+    n = v.numel()
+    n_tot = int(n_global) if n_global is not None else n
+    c0 = order_stats(v, (n_tot - 1) // 4, group)[0:1]
+    c1 = order_stats(v, (3 * (n_tot - 1)) // 4, group)[0:1]
+    centers = torch.cat([c0, c1])
+    ws = torch.empty(lib.sg_gmm1d_workspace_bytes(), dtype=torch.uint8, device=device)
+    L.check(lib.sg_gmm1d_begin(_p(centers), kmeans_iters, _p(ws), _stream()), "sg_gmm1d_begin")
+    sums = ws[16 * 8:24 * 8].view(torch.float64)
+    for _ in range(kmeans_iters + max_iter):
+        L.check(lib.sg_gmm1d_accumulate(_p(v), n, _p(ws), _stream()), "sg_gmm1d_accumulate")
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        L.check(lib.sg_gmm1d_update(n_tot, float(reg_covar), float(tol), int(max_iter), _p(ws), _stream()), "sg_gmm1d_update")
+    st = ws[:16 * 8].view(torch.float64).cpu().numpy()
+    return {"weights": st[0:2].copy(), "means": st[2:4].copy(), "stds": np.sqrt(st[4:6]), "n_iter": int(st[7]),
+            "converged": bool(st[8]), "lower_bound": float(st[6])}
+
+
+def get_gmm_threshold(losses, *, fit: str = "sklearn"):
+    """"# 종합 loss.py:270-285".  fit='sklearn' (default, the reference's own call: the EM fit is seeded by the
+    global np.random state exactly like upstream); fit='device': the deterministic GPU EM of ``gmm_fit_device``."""
+    if fit == "device":
+        g = gmm_fit_device(losses)
+        return _gmm_intersection(g["means"], g["stds"])
     from sklearn.mixture import GaussianMixture
     lo = losses.cpu().numpy() if isinstance(losses, torch.Tensor) else np.asarray(losses)
     gmm = GaussianMixture(n_components=2, max_iter=10, tol=1e-2, reg_covar=5e-4)
@@ -621,9 +709,9 @@ def _divide(losses, dataset, threshold):
     return sub(dataset, idx[:c].cpu().numpy()), sub(dataset, nidx[:nc_].cpu().numpy())
 
 
-def divide_dataset(losses, dataset):
+def divide_dataset(losses, dataset, *, fit: str = "sklearn"):
     """GMM form, "#clean 분포와 ... .py:289-316": clean = losses < intersection threshold."""
-    return _divide(losses, dataset, get_gmm_threshold(losses))
+    return _divide(losses, dataset, get_gmm_threshold(losses, fit=fit))
 
 
 def divide_dataset_ensemble(losses, dataset):

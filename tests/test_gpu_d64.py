@@ -260,3 +260,29 @@ def test_integration_md_ctypes_stub(golden, netD):
     want[golden["g1a_indices"]] = True
     near = np.abs(golden["g1_losses"] - wthr) <= 1e-3 * abs(wthr)
     assert not ((got != want) & ~near).any()
+
+
+def test_resident_subset_epoch_pipeline(sb):
+    """the strain result as a device index tensor driving on-device batch gathers; unshuffled
+    batches equal DataLoader(Subset(dataset, clean_indices), shuffle=False) of the reference flow."""
+    n = 300
+    x = torch.from_numpy(O.synth_images(0, n))
+    netD = O.make_discriminator(O.SEED)
+    ds = torch.utils.data.TensorDataset(x, torch.zeros(n, dtype=torch.long))
+    sub_ref, thr_ref = sb.refine_dataset_by_loss(ds, netD, "cuda", 0.2)
+    sub = sb.ResidentSubset.refine(x.cuda(), netD, 0.2)
+    assert np.array_equal(sub.indices.cpu().numpy(), np.asarray(sub_ref.indices))
+    assert float(sub.threshold.cpu()[0]) == float(thr_ref)
+    loader = torch.utils.data.DataLoader(sub_ref, batch_size=64, shuffle=False)
+    got = list(sub.batches(64, shuffle=False))
+    want = [b[0] for b in loader]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g.cpu(), w)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    seen = torch.cat([b for b in sb.ResidentSubset(x.cuda(), sub.indices).batches(50, shuffle=True, generator=gen)])
+    assert seen.shape[0] == len(sub)
+    # a permutation of the kept rows: same multiset of per-row checksums
+    a = np.sort(seen.double().sum(dim=(1, 2, 3)).cpu().numpy())
+    b = np.sort(x[np.asarray(sub_ref.indices)].double().sum(dim=(1, 2, 3)).numpy())
+    assert np.array_equal(a, b)

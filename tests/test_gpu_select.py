@@ -241,3 +241,31 @@ def test_dbscan1d_vs_sklearn(sb):
     mz = O.zscore_max_torch(torch.from_numpy(O.synth_features(4096)))
     r = sb.dbscan1d_clean_ratio(mz, 0.05, 3)
     assert r == O.dbscan1d_clean_ratio(mz.numpy(), 0.05, 3)
+
+
+def test_gmm_em_device(sb):
+    """deterministic 2-component EM on the device vs its float64 restatement (tight) and vs a
+    seeded scikit-learn fit of the reference call (same optimum on a bimodal loss vector)."""
+    from sklearn.mixture import GaussianMixture
+    for seed, n in ((1, 20000), (2, 65536), (3, 1000)):
+        v = O.synth_losses(n, seed=seed)
+        got = sb.gmm_fit_device(v)
+        want = O.gmm_fit_deterministic(v)
+        assert got["n_iter"] == want["n_iter"] and got["converged"] == want["converged"]
+        for k in ("weights", "means", "stds"):
+            assert np.allclose(got[k], want[k], rtol=1e-9, atol=1e-12), (k, got[k], want[k])
+        np.random.seed(0)
+        g = GaussianMixture(n_components=2, max_iter=10, tol=1e-2, reg_covar=5e-4).fit(v.reshape(-1, 1))
+        sm, ss = g.means_.flatten().astype(np.float64), np.sqrt(g.covariances_.flatten()).astype(np.float64)
+        o = np.argsort(sm)
+        o2 = np.argsort(got["means"])
+        assert np.allclose(got["means"][o2], sm[o], rtol=5e-2), (got["means"], sm)
+        assert np.allclose(got["stds"][o2], ss[o], rtol=1e-1), (got["stds"], ss)
+        t_dev = sb.get_gmm_threshold(v, fit="device")
+        t_ref = O.gmm_intersection(sm.astype(np.float32), ss.astype(np.float32))
+        assert abs(t_dev - t_ref) <= 5e-2 * abs(t_ref), (t_dev, t_ref)
+    ds = torch.utils.data.TensorDataset(torch.zeros(1000, 1))
+    clean, noisy = sb.divide_dataset(v, ds, fit="device")
+    thr = sb.get_gmm_threshold(v, fit="device")
+    wc, wn = O.divide_by_threshold(v, thr)
+    assert np.array_equal(np.asarray(clean.indices), wc) and np.array_equal(np.asarray(noisy.indices), wn)
