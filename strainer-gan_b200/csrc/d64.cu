@@ -652,6 +652,246 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// L3 / L4 on CTA pairs with PLANE REUSE.  conv_pair_kernel streams one activation box per filter tap: every input
+// pixel is fetched from L2 four times (once per tap that touches it), and the L2 -> SM fabric, not the tensor pipe,
+// sets the pace.  Here the K loop is reordered by parity plane: the four taps (2 row shifts x 2
+// column shifts) that read plane (ph, pw) share TWO shared-memory copies of that plane, one per column shift
+// (loaded with the TMA start column at dw, so the shift costs nothing), each holding W+1 plane rows (one halo
+// row, TMA zero fill).  Tile rows are ordered (oh, image, ow): a row shift is then a whole number of 8-row core
+// groups, i.e. just a 1024-byte-aligned descriptor offset.  Activation bytes from L2 halve; the per-tap weight
+// tiles keep their own (deeper) ring.
+//   unit  = (plane, 64-channel chunk, activation segment): 2 copies, 4 taps x {1, 2} weight tiles
+// ------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct Pair2Cfg {
+  static constexpr int kCopyBytes = 20 * 1024;                 // (H+1) x IMG x W rows of 128 B: 18 KB (L2, L3), 20 KB (L4)
+  static constexpr int kUnitBytes = 2 * kCopyBytes;
+  static constexpr int kUnits = 3;                             // activation ring
+  static constexpr int kBBytes = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of the weight tile
+  static constexpr int kBStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSsBytes = 2 * 512 * 4;
+  static constexpr int kSmemBytes = kUnits * kUnitBytes + kBStages * kBBytes + 256 + kSsBytes + 1024;
+  static constexpr int kThreads = 192;
+};
+
+template <int SEGA, int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const ConvParams p) {
+  using Cfg = Pair2Cfg<BLOCK_N>;
+  constexpr int UA = Cfg::kUnits, SB = Cfg::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + UA * Cfg::kUnitBytes;
+  const uint32_t bar0 = b_base + SB * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto afull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
+  auto bfull_bar = [&](int s) { return bar0 + 8u * (2 * UA + s); };
+  auto bempty_bar = [&](int s) { return bar0 + 8u * (2 * UA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + 2 + a); };
+  constexpr int kNb = 2 * UA + 2 * SB + 4;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
+  float* s_ss = reinterpret_cast<float*>(smem + (bar0 - base) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int W = 1 << p.ow_log2;             // output (= plane) width: 16 (L2), 8 (L3), 4 (L4)
+  const int H = 1 << p.bh_log2;             // output rows per CTA tile: 8 (L2: the pair splits an image), W otherwise
+  const int IMG = p.bimg;                   // images per CTA tile: 1 (L2), 2 (L3), 8 (L4)
+  const int oh0 = (p.tiles_per_img > 1) ? (int)rank * H : 0;
+  const uint32_t copy_bytes = (uint32_t)((H + 1) * IMG * W * 128);
+  const uint32_t shift_bytes = (uint32_t)(IMG * W * 128);   // one plane row of every image = W*IMG/8 core groups
+  const int units = 4 * p.nchunk * SEGA;    // (plane, chunk, activation segment)
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  for (int i = threadIdx.x; i < p.c_out; i += Cfg::kThreads) { s_ss[i] = p.scale[i]; s_ss[512 + i] = p.shift[i]; }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  // unit u -> (plane, chunk, aseg); tap t in 0..3 of a plane -> (kh, kw); weight K-step of (tap, chunk, seg)
+  //   plane (ph, pw): kh in {1 - ph + 2*i... }: ph = 1 -> kh = 0 (dh -1), 2 (dh 0); ph = 0 -> kh = 1 (dh 0), 3 (dh +1)
+  //   the first of the two has row offset 0 inside the copy, the second one plane row further (see header)
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      int aslot = 0, bstage = 0;
+      uint32_t aphase = 0, bphase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
+        const int nt = tile % p.n_tiles;
+        const int img0 = (p.tiles_per_img > 1) ? tile / p.n_tiles : (2 * (tile / p.n_tiles) + (int)rank) * IMG;
+        for (int u = 0; u < units && ok; ++u) {
+          const int aseg = u % SEGA;
+          const int chunk = (u / SEGA) % p.nchunk;
+          const int plane = u / (SEGA * p.nchunk);
+          const int ph = plane >> 1, pw = plane & 1;
+          if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, p.err, kErrProducer + 30)) { ok = false; break; }
+          const uint32_t lead_afull = mapa_shared(afull_bar(aslot), 0);
+          if (leader) mbar_arrive_expect_tx(afull_bar(aslot), 4 * copy_bytes);   // 2 copies x 2 CTAs
+          const int cc = chunk * 64 + aseg * p.c_in;
+          const uint32_t ua = base + aslot * Cfg::kUnitBytes;
+          // copy 0: the tap with the smaller kw of this plane; copy 1: the larger.  pw = 1: dw = -1, 0; pw = 0: dw = 0, +1
+          tma_load_5d_pair(ua, &tmap_a, lead_afull, cc, pw ? -1 : 0, img0, oh0 + (ph ? -1 : 0), plane);
+          tma_load_5d_pair(ua + Cfg::kCopyBytes, &tmap_a, lead_afull, cc, pw ? 0 : 1, img0, oh0 + (ph ? -1 : 0), plane);
+          if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+          const int nb = (SEGA == 2 && aseg == 0) ? 2 : 1;   // A_hi pairs with B_hi and B_lo, A_lo with B_hi only
+          for (int t = 0; t < 4 && ok; ++t) {
+            const int kh = (t >> 1) * 2 + (1 - ph), kw = (t & 1) * 2 + (1 - pw);
+            const int tap = kh * 4 + kw;
+            for (int b = 0; b < nb; ++b) {
+              const int seg = (SEGA == 1) ? 0 : (aseg == 1 ? 1 : (b == 0 ? 0 : 2));
+              const int ks = (tap * p.nchunk + chunk) * p.nseg + seg;
+              if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, p.err, kErrProducer + 31)) { ok = false; break; }
+              const uint32_t lead_bfull = mapa_shared(bfull_bar(bstage), 0);
+              if (leader) mbar_arrive_expect_tx(bfull_bar(bstage), 2 * Cfg::kBBytes);
+              tma_load_2d_pair(b_base + bstage * Cfg::kBBytes, &tmap_b, lead_bfull, ks * 64, nt * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      int aslot = 0, bstage = 0, acc = 0;
+      uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
+        if (!mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 30)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        uint32_t first = 0;
+        for (int u = 0; u < units && ok; ++u) {
+          const int aseg = u % SEGA;
+          if (!mbar_wait(afull_bar(aslot), aphase, s_abort, p.err, kErrMma + 30)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t ua = base + aslot * Cfg::kUnitBytes;
+          const int nb = (SEGA == 2 && aseg == 0) ? 2 : 1;
+          for (int t = 0; t < 4 && ok; ++t) {
+            // t >> 1: second row tap of the plane (one plane row further), t & 1: second column tap (copy 1)
+            const uint64_t adesc = umma_desc_sw128(ua + (t & 1) * Cfg::kCopyBytes + (t >> 1) * shift_bytes);
+            for (int b = 0; b < nb; ++b) {
+              if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, p.err, kErrMma + 31)) { ok = false; break; }
+              tc_fence_after();
+              const uint64_t bdesc = umma_desc_sw128(b_base + bstage * Cfg::kBBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first);
+                first = 1u;
+              }
+              umma_commit_pair(bempty_bar(bstage), 3);
+              if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+            }
+          }
+          if (!ok) break;
+          umma_commit_pair(aempty_bar(aslot), 3);
+          if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit_pair(tfull_bar(acc), 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5 of both CTAs); tile row = (oh, image, ow) =================
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ct = p.c_out * SEGA;
+    const float slope = p.slope;
+    const int ow = row & (W - 1);
+    const int img_l = (row >> p.ow_log2) % IMG;
+    const int oh = oh0 + (row >> p.ow_log2) / IMG;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      const int nt = tile % p.n_tiles;
+      const int img = ((p.tiles_per_img > 1) ? tile / p.n_tiles : (2 * (tile / p.n_tiles) + (int)rank) * IMG) + img_l;
+      const bool valid = img < p.n_img;
+      size_t off;
+      if (p.out_planes) {
+        const int half = W >> 1;
+        off = ((((size_t)img * 4 + ((oh & 1) * 2 + (ow & 1))) * half + (oh >> 1)) * half + (ow >> 1)) * ct;
+      } else {
+        off = (((size_t)img * W + oh) * W + ow) * ct;
+      }
+      __nv_bfloat16* dst = p.out + off + (size_t)nt * BLOCK_N;
+      const float4* sc4 = reinterpret_cast<const float4*>(s_ss + nt * BLOCK_N);
+      const float4* sh4 = reinterpret_cast<const float4*>(s_ss + 512 + nt * BLOCK_N);
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 30)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 2
+      for (int cb = 0; cb < BLOCK_N; cb += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb, v);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 s4 = sc4[(cb >> 2) + q], h4 = sh4[(cb >> 2) + q];
+          float a0 = fmaf(__uint_as_float(v[4 * q]), s4.x, h4.x), a1 = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y);
+          float a2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z), a3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w);
+          a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);
+          a2 = fmaxf(a2, slope * a2); a3 = fmaxf(a3, slope * a3);
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+          hi[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
+          hi[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+          if (SEGA == 2) {
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(a0 - f01.x, a1 - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(a2 - f23.x, a3 - f23.y);
+            lo[2 * q] = *reinterpret_cast<const uint32_t*>(&l01);
+            lo[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+          }
+        }
+        if (valid) {
+          uint4* d = reinterpret_cast<uint4*>(dst + cb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (SEGA == 2) {
+            uint4* dl = reinterpret_cast<uint4*>(dst + p.c_out + cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // L2 (64 -> 128 channels) with the operands swapped: D^T[cout][pixel] = W * X^T.
 // With only 128 output channels a 128(pixel) x 128(cout) tile makes every tcgen05.mma read as many
 // operand bytes as a 128x256 one for half the math (shared-memory bound, 36 % tensor-pipe active
@@ -1536,6 +1776,66 @@ static int launch_conv_pair(const __nv_bfloat16* act_in, const __nv_bfloat16* wp
   return SG_OK;
 }
 
+// plane-reuse pair kernel for L2 (BLOCK_N = 128: the pair splits one image by rows), L3, L4 (BLOCK_N = 256)
+template <int BLOCK_N>
+static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
+                             __nv_bfloat16* act_out, int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega,
+                             int out_planes, float slope, int* err, cudaStream_t stream) {
+  using Cfg = Pair2Cfg<BLOCK_N>;
+  const int ow = s_in / 2;                 // output width = parity-plane width
+  const bool split = ow * ow > 128;        // L2: 256 output pixels per image -> one image per CTA pair
+  const int h_tile = split ? 128 / ow : ow;
+  const int bimg = split ? 1 : 128 / (ow * ow);
+  const int ct_in = c_in * sega;
+  CUtensorMap ta, tb;
+  {
+    // parity planes [img][plane][h][w][c] addressed as (c, w, img, h, plane): a copy is w fastest, then image, then
+    // plane row, so that a row shift of the window is a whole number of 8-row core groups
+    cuuint64_t dims[5] = {(cuuint64_t)ct_in, (cuuint64_t)ow, (cuuint64_t)batch, (cuuint64_t)ow, 4};
+    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)4 * ow * ow * ct_in * 2, (cuuint64_t)ow * ct_in * 2,
+                             (cuuint64_t)ow * ow * ct_in * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)ow, (cuuint32_t)bimg, (cuuint32_t)(h_tile + 1), 1};
+    int r = encode(&ta, 5, act_in, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  const int nchunk = c_in / 64;
+  const int k_steps = 16 * nchunk * nseg;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, (cuuint64_t)c_out};
+    cuuint64_t strides[1] = {(cuuint64_t)k_steps * 64 * 2};
+    cuuint32_t box[2] = {64, BLOCK_N / 2};
+    int r = encode(&tb, 2, wpk, dims, strides, box);
+    if (r != SG_OK) return r;
+  }
+  ConvParams p = {};
+  p.n_tiles = c_out / BLOCK_N;
+  const int64_t pair_m_tiles = split ? batch : ceil_div(ceil_div(batch, bimg), 2);
+  p.total_tiles = (int)(pair_m_tiles * p.n_tiles);
+  p.n_img = (int)batch;
+  p.ow_log2 = __builtin_ctz(ow);
+  p.bh_log2 = __builtin_ctz(h_tile);
+  p.bimg = bimg;
+  p.tiles_per_img = split ? 2 : 1;
+  p.c_in = c_in;
+  p.nchunk = nchunk;
+  p.nseg = nseg;
+  p.k_steps = k_steps;
+  p.c_out = c_out;
+  p.out_sega = sega;
+  p.out_planes = out_planes;
+  p.slope = slope;
+  p.scale = scale;
+  p.shift = shift;
+  p.out = act_out;
+  p.err = err;
+  int pairs = state().sm_count / 2;
+  if (p.total_tiles < pairs) pairs = p.total_tiles;
+  if (sega == 2) conv_pair2_kernel<2, BLOCK_N><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  else conv_pair2_kernel<1, BLOCK_N><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* scale, const float* shift,
                              __nv_bfloat16* act2,
                              int64_t batch, int nseg, int sega, float slope, int* err, cudaStream_t stream) {
@@ -1669,6 +1969,10 @@ int sg_d64_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<128>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<128>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1Cfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1759,14 +2063,20 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
       return (W.sega == 2) ? launch_conv1<2>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st)
                            : launch_conv1<1>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st);
     case 2:
-      if (getenv("SG_CONV2_PIXEL_MAJOR"))  // 128x128 pixel-major tiles kept for A/B timing only
+      if (getenv("SG_CONV2_PLANE_REUSE"))
+        r = launch_conv_pair2<128>(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, 32, 64, 128, P.nseg, W.sega, 1,
+                                   slope, err, st);
+      else if (getenv("SG_CONV2_PIXEL_MAJOR"))  // 128x128 pixel-major tiles kept for A/B timing only
         r = launch_conv<128>(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, 32, 64, 128, P.nseg, W.sega, 1,
                              slope, err, st);
       else
         r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st);
       break;
     case 3:
-      if (!getenv("SG_CONV_SINGLE_CTA"))  // default: CTA pairs (cta_group::2); single-CTA tiles kept for A/B timing
+      if (!getenv("SG_CONV_TAP_STREAM"))  // default: plane reuse; per-tap streaming kernels kept for A/B timing
+        r = launch_conv_pair2<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
+                              slope, err, st);
+      else if (!getenv("SG_CONV_SINGLE_CTA"))  // default: CTA pairs (cta_group::2); single-CTA tiles kept for A/B timing
         r = launch_conv_pair(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
                              slope, err, st);
       else
@@ -1774,7 +2084,10 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
                            slope, err, st);
       break;
     case 4:
-      if (!getenv("SG_CONV_SINGLE_CTA"))
+      if (!getenv("SG_CONV_TAP_STREAM"))
+        r = launch_conv_pair2<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
+                              slope, err, st);
+      else if (!getenv("SG_CONV_SINGLE_CTA"))
         r = launch_conv_pair(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
                              slope, err, st);
       else
