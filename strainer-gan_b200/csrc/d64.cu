@@ -747,12 +747,15 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int ph = plane >> 1, pw = plane & 1;
           if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, p.err, kErrProducer + 30)) { ok = false; break; }
           const uint32_t lead_afull = mapa_shared(afull_bar(aslot), 0);
-          if (leader) mbar_arrive_expect_tx(afull_bar(aslot), 4 * copy_bytes);   // 2 copies x 2 CTAs
+          const bool load_a = !(p.debug & 2) || (tile == pair && u < UA);        // timing experiment
+          if (leader) mbar_arrive_expect_tx(afull_bar(aslot), load_a ? 4 * copy_bytes : 0);   // 2 copies x 2 CTAs
           const int cc = chunk * 64 + aseg * p.c_in;
           const uint32_t ua = base + aslot * Cfg::kUnitBytes;
+          if (load_a) {
           // copy 0: the tap with the smaller kw of this plane; copy 1: the larger.  pw = 1: dw = -1, 0; pw = 0: dw = 0, +1
           tma_load_5d_pair(ua, &tmap_a, lead_afull, cc, pw ? -1 : 0, img0, oh0 + (ph ? -1 : 0), plane);
           tma_load_5d_pair(ua + Cfg::kCopyBytes, &tmap_a, lead_afull, cc, pw ? 0 : 1, img0, oh0 + (ph ? -1 : 0), plane);
+          }
           if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
           const int nb = (SEGA == 2 && aseg == 0) ? 2 : 1;   // A_hi pairs with B_hi and B_lo, A_lo with B_hi only
           for (int t = 0; t < 4 && ok; ++t) {
@@ -763,7 +766,9 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const int ks = (tap * p.nchunk + chunk) * p.nseg + seg;
               if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, p.err, kErrProducer + 31)) { ok = false; break; }
               const uint32_t lead_bfull = mapa_shared(bfull_bar(bstage), 0);
-              if (leader) mbar_arrive_expect_tx(bfull_bar(bstage), 2 * Cfg::kBBytes);
+              const bool load_b = !(p.debug & 1) || (tile == pair && u == 0);   // timing experiment: weights loaded once
+              if (leader) mbar_arrive_expect_tx(bfull_bar(bstage), load_b ? 2 * Cfg::kBBytes : 0);
+              if (load_b)
               tma_load_2d_pair(b_base + bstage * Cfg::kBBytes, &tmap_b, lead_bfull, ks * 64, nt * BLOCK_N + (int)rank * (BLOCK_N / 2));
               if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
             }
@@ -906,21 +911,28 @@ struct Conv2Cfg {
   static constexpr int kStageBytes = kWBytes + kXBytes;
   static constexpr int kStages = 4;
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kStageOut = 128 * 128 * 2;   // half an output image [128 px][128 ch] bf16, transposed for the TMA store
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 256 + 1024;
   static constexpr int kThreads = 192;
 };
 
+// SEGA == 1 (bf16 mode): the channel-major accumulator is transposed through shared memory ([pixel][channel],
+// 2-byte stores, a warp = 64 contiguous bytes) and leaves as two 5-D TMA stores per image; the direct form
+// (one 2-byte global store per element, 14 % of the kernel in profiles/r1c) is kept for the fp32-parity mode,
+// whose 3x longer main loop hides it.
+template <int SEGA>
 __global__ void __launch_bounds__(192, 1)
 conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
   using Cfg = Conv2Cfg;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-  const uint32_t bar0 = base + S * Cfg::kStageBytes;
+  const uint32_t stg = base + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kStageOut);
+  const uint32_t bar0 = stg + Cfg::kStageOut;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
@@ -932,6 +944,7 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_x);
     prefetch_tensormap(&tmap_w);
+    if (SEGA == 1) prefetch_tensormap(&tmap_o);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
     *s_abort = 0;
@@ -955,8 +968,11 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           const int tap = ks / p.nseg;  // c_in == 64: one channel chunk per tap
           const int kh = tap >> 2, kw = tap & 3;
           const uint32_t sw = base + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(sw, &tmap_w, full_bar(stage), ks * 64, 0);
+          const bool first_use = (img == (int)blockIdx.x && ks < S);
+          const bool load_w = first_use || !(p.debug & 1), load_x = first_use || !(p.debug & 2);   // timing experiments
+          mbar_arrive_expect_tx(full_bar(stage), (load_w ? Cfg::kWBytes : 0) + (load_x ? Cfg::kXBytes : 0));
+          if (load_w) tma_load_2d(sw, &tmap_w, full_bar(stage), ks * 64, 0);
+          if (load_x)
           tma_load_5d(sw + Cfg::kWBytes, &tmap_x, full_bar(stage), seg == 1 ? 64 : 0, (kw - 1) >> 1, (kh - 1) >> 1,
                       ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img);
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -1001,26 +1017,58 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 256);
       __nv_bfloat16* out_img = p.out + (size_t)img * 4 * 64 * ct + ch;
+      if (SEGA == 1) {
+        const bool issuer = (threadIdx.x == 64);
+        const float slope = p.slope;
 #pragma unroll 1
-      for (int pb = 0; pb < 256; pb += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + pb, v);
-        tmem_ld_wait();
+        for (int half = 0; half < 2; ++half) {
+          if (issuer) tma_store_wait_read<0>();       // the previous store has finished reading the staging tile
+          named_bar_sync(1, 128);
+#pragma unroll 1
+          for (int pq = 0; pq < 4; ++pq) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + half * 128 + pq * 32, v);
+            tmem_ld_wait();
+            // pixel (oh_l = 2*pq + (j >> 4), ow = j & 15) of this half -> staging row (plane, oh_l >> 1, ow >> 1)
+            const uint32_t rbase = stg + (uint32_t)(pq * 8 * 256 + ch * 2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int px = pb + j, oh = px >> 4, ow = px & 15;
-          float a = fmaf(__uint_as_float(v[j]), sc, sh);
-          a = a > 0.f ? a : p.slope * a;
-          const __nv_bfloat16 ah = __float2bfloat16_rn(a);
-          __nv_bfloat16* d = out_img + ((size_t)((oh & 1) * 2 + (ow & 1)) * 64 + (oh >> 1) * 8 + (ow >> 1)) * ct;
-          *d = ah;
-          if (p.out_sega == 2) d[128] = __float2bfloat16_rn(a - __bfloat162float(ah));
+            for (int j = 0; j < 32; ++j) {
+              float a = fmaf(__uint_as_float(v[j]), sc, sh);
+              a = fmaxf(a, slope * a);
+              const int row = (((j >> 4) & 1) * 2 + (j & 1)) * 32 + ((j & 15) >> 1);
+              st_shared_u16(rbase + (uint32_t)(row * 256), __bfloat16_as_ushort(__float2bfloat16_rn(a)));
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_5d(&tmap_o, stg, 0, 0, half * 4, 0, img);
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int pb = 0; pb < ((p.debug & 4) ? 32 : 256); pb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + pb, v);
+          tmem_ld_wait();
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int px = pb + j, oh = px >> 4, ow = px & 15;
+            float a = fmaf(__uint_as_float(v[j]), sc, sh);
+            a = a > 0.f ? a : p.slope * a;
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+            __nv_bfloat16* d = out_img + ((size_t)((oh & 1) * 2 + (ow & 1)) * 64 + (oh >> 1) * 8 + (ow >> 1)) * ct;
+            *d = ah;
+            if (p.out_sega == 2) d[128] = __float2bfloat16_rn(a - __bfloat162float(ah));
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (SEGA == 1 && threadIdx.x == 64) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -1828,6 +1876,7 @@ static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* w
   p.shift = shift;
   p.out = act_out;
   p.err = err;
+  p.debug = getenv("SG_DEBUG_SKIP") ? atoi(getenv("SG_DEBUG_SKIP")) : 0;
   int pairs = state().sm_count / 2;
   if (p.total_tiles < pairs) pairs = p.total_tiles;
   if (sega == 2) conv_pair2_kernel<2, BLOCK_N><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
@@ -1869,8 +1918,20 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
   p.shift = shift;
   p.out = act2;
   p.err = err;
+  p.debug = getenv("SG_DEBUG_SKIP") ? atoi(getenv("SG_DEBUG_SKIP")) : 0;
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-  conv2_swap_kernel<<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, p);
+  CUtensorMap to;
+  {
+    // act2 parity planes [img][4][8][8][128*sega]; one store = 4 plane rows of all 4 planes of one image (128 px x 128 ch)
+    const cuuint64_t ct = 128 * sega;
+    cuuint64_t dims[5] = {ct, 8, 8, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {ct * 2, 8 * ct * 2, 64 * ct * 2, 256 * ct * 2};
+    cuuint32_t box[5] = {128, 8, 4, 4, 1};
+    int r = encode(&to, 5, act2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (r != SG_OK) return r;
+  }
+  if (sega == 2) conv2_swap_kernel<2><<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, to, p);
+  else conv2_swap_kernel<1><<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, to, p);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1966,7 +2027,8 @@ int sg_d64_init_attributes() {
                                ConvCfg<128>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<256>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
