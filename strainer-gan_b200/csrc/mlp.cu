@@ -52,6 +52,53 @@ __global__ void __launch_bounds__(256) linear_lrelu_kernel(const float* __restri
   }
 }
 
+// Small-batch form (the reference's B = 64): weight-stationary.  One warp per output feature keeps its weight row in
+// registers (in_f / 32 values per lane), streams the <= 128 batch rows (shared by the 8 warps of the CTA through L1)
+// and reduces each dot product with shuffles.  out_f / 8 CTAs instead of out_f / 64: the chain is latency bound and
+// this form has 8x the CTAs and no shared-memory barriers in its K loop.
+template <int KPL>   // ceil(in_f / 32) values per lane
+__global__ void __launch_bounds__(256) linear_lrelu_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ y,
+                                                                 int batch, int in_f, int out_f, float slope) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= out_f) return;
+  float wr[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int k = lane + 32 * i;
+    wr[i] = k < in_f ? __ldg(w + (size_t)o * in_f + k) : 0.f;
+  }
+  const float bo = __ldg(bias + o);
+  for (int b = 0; b < batch; b += 2) {
+    const float* x0 = x + (size_t)b * in_f;
+    const bool two = b + 1 < batch;
+    const float* x1 = two ? x0 + in_f : x0;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < in_f) {
+        a0 = fmaf(x0[k], wr[i], a0);
+        a1 = fmaf(x1[k], wr[i], a1);
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    }
+    if (lane == 0) {
+      float v = a0 + bo;
+      y[(size_t)b * out_f + o] = v > 0.f ? v : slope * v;
+      if (two) {
+        v = a1 + bo;
+        y[(size_t)(b + 1) * out_f + o] = v > 0.f ? v : slope * v;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) mlp_head_kernel(const float* __restrict__ h, const float* __restrict__ w,
                                                        const float* __restrict__ bias, int batch, int in_f,
                                                        float* __restrict__ logit, float* __restrict__ prob,
@@ -96,6 +143,15 @@ int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, vo
   const float* in = x;
   float* outs[3] = {h1, h2, h3};
   for (int l = 0; l < 3; ++l) {
+    if (batch <= 128) {
+      const unsigned g = (unsigned)sg::ceil_div(dims[l + 1], 8);
+      if (l == 0) linear_lrelu_small_kernel<25><<<g, 256, 0, st>>>(in, h_params[0], h_params[1], outs[0], (int)batch, 784, 1024, 0.2f);
+      else if (l == 1) linear_lrelu_small_kernel<32><<<g, 256, 0, st>>>(in, h_params[2], h_params[3], outs[1], (int)batch, 1024, 512, 0.2f);
+      else linear_lrelu_small_kernel<16><<<g, 256, 0, st>>>(in, h_params[4], h_params[5], outs[2], (int)batch, 512, 256, 0.2f);
+      SG_LAUNCH_CHECK();
+      in = outs[l];
+      continue;
+    }
     const dim3 grid((unsigned)sg::ceil_div(dims[l + 1], 64), (unsigned)sg::ceil_div(batch, 64));
     linear_lrelu_kernel<<<grid, 256, 0, st>>>(in, h_params[2 * l], h_params[2 * l + 1], outs[l], (int)batch, dims[l],
                                               dims[l + 1], 0.2f);

@@ -231,6 +231,16 @@ def test_mlp_discriminator_config1(sb, dropout):
     if dropout:
         with pytest.raises(NotImplementedError):
             sb.strain_batch(d.train(), x.cuda())
+    # odd small batch (weight-stationary kernels) and a large batch (tiled SGEMM kernels)
+    d.eval()
+    for b in (1, 63, 129, 300):
+        xb = torch.from_numpy(np.tanh(rng.standard_normal((b, 784))).astype(np.float32))
+        with torch.no_grad():
+            wb = d(xb).reshape(-1)
+        scb = sb.MLPScorer(d, "cuda", max_batch=b)
+        pb = torch.empty(b, device="cuda")
+        scb.score_into(xb.cuda(), None, pb, None)
+        assert (pb.cpu() - wb).abs().max().item() <= 1e-5, b
 
 
 def test_integration_md_ctypes_stub(golden, netD):
