@@ -668,7 +668,7 @@ struct Pair2Cfg {
   static constexpr int kUnitBytes = 2 * kCopyBytes;
   static constexpr int kUnits = 3;                             // activation ring
   static constexpr int kBBytes = (BLOCK_N / 2) * 64 * 2;       // this CTA's half of the weight tile
-  static constexpr int kBStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kBStages = 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kSsBytes = 2 * 512 * 4;
   static constexpr int kSmemBytes = kUnits * kUnitBytes + kBStages * kBBytes + 256 + kSsBytes + 1024;
@@ -1049,6 +1049,206 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       } else {
 #pragma unroll 1
         for (int pb = 0; pb < ((p.debug & 4) ? 32 : 256); pb += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + pb, v);
+          tmem_ld_wait();
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int px = pb + j, oh = px >> 4, ow = px & 15;
+            float a = fmaf(__uint_as_float(v[j]), sc, sh);
+            a = a > 0.f ? a : p.slope * a;
+            const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+            __nv_bfloat16* d = out_img + ((size_t)((oh & 1) * 2 + (ow & 1)) * 64 + (oh >> 1) * 8 + (ow >> 1)) * ct;
+            *d = ah;
+            if (p.out_sega == 2) d[128] = __float2bfloat16_rn(a - __bfloat162float(ah));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (SEGA == 1 && threadIdx.x == 64) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+struct Conv2RCfg {
+  static constexpr int kWBytes = 128 * 64 * 2;            // weights of one tap [128 cout x 64 k]
+  static constexpr int kCopyBytes = 17 * 16 * 128;        // one shifted copy of a parity plane: 17 rows x 16 px x 64 ch
+  static constexpr int kUnitBytes = kCopyBytes;            // ring slot = ONE copy, shared by the two row taps of its column shift
+  static constexpr int kUnits = 3;
+  static constexpr int kWStages = 5;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kStageOut = 128 * 128 * 2;
+  static constexpr int kSmemBytes = kUnits * kUnitBytes + kWStages * kWBytes + kStageOut + 256 + 1024;
+  static constexpr int kThreads = 192;
+};
+
+// conv2_swap_kernel with PLANE REUSE of the pixel operand (see conv_pair2_kernel): the four taps of a parity plane
+// read two shared-memory copies of it (one per column shift, 17 plane rows x 16 columns each); a row shift is a
+// 2048-byte offset of the B descriptor.  Pixel bytes from L2 halve; the 16 KB weight tiles keep a ring of their own.
+template <int SEGA>
+__global__ void __launch_bounds__(192, 1)
+conv2_swap2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
+  using Cfg = Conv2RCfg;
+  constexpr int S = Cfg::kWStages, UA = Cfg::kUnits;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t w_base = base + UA * Cfg::kUnitBytes;
+  const uint32_t stg = w_base + S * Cfg::kWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (stg - base) + Cfg::kStageOut);
+  const uint32_t bar0 = stg + Cfg::kStageOut;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };              // weight ring
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto xfull_bar = [&](int s) { return bar0 + 8u * (2 * S + s); };    // plane-unit ring
+  auto xempty_bar = [&](int s) { return bar0 + 8u * (2 * S + UA + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 * UA + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 * UA + 2 + a); };
+  constexpr int kNb = 2 * S + 2 * UA + 4;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_w);
+    if (SEGA == 1) prefetch_tensormap(&tmap_o);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < UA; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, xslot = 0;
+      uint32_t phase = 0, xphase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
+        for (int u = 0; u < 8 * SEGA && ok; ++u) {
+          const int xseg = u % SEGA, cp = (u / SEGA) & 1, plane = u / (2 * SEGA), ph = plane >> 1, pw = plane & 1;
+          if (!mbar_wait(xempty_bar(xslot), xphase ^ 1u, s_abort, p.err, kErrProducer + 40)) { ok = false; break; }
+          const uint32_t ux = base + xslot * Cfg::kUnitBytes;
+          mbar_arrive_expect_tx(xfull_bar(xslot), Cfg::kCopyBytes);
+          // copy cp of plane (ph, pw): column shift dw = cp - pw, first plane row -ph
+          tma_load_5d(ux, &tmap_x, xfull_bar(xslot), xseg * 64, cp - pw, ph ? -1 : 0, plane, img);
+          if (++xslot == UA) { xslot = 0; xphase ^= 1u; }
+          const int nb = (SEGA == 2 && xseg == 0) ? 2 : 1;   // x_hi pairs with w_hi and w_lo, x_lo with w_hi only
+          for (int t = 0; t < 2 && ok; ++t) {
+            const int kh = t * 2 + (1 - ph), kw = cp * 2 + (1 - pw);
+            for (int b = 0; b < nb; ++b) {
+              const int seg = (SEGA == 1) ? 0 : (xseg == 1 ? 1 : (b == 0 ? 0 : 2));
+              const int ks = (kh * 4 + kw) * p.nseg + seg;
+              if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer + 41)) { ok = false; break; }
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::kWBytes);
+              tma_load_2d(w_base + stage * Cfg::kWBytes, &tmap_w, full_bar(stage), ks * 64, 0);
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(256);
+      int stage = 0, xslot = 0, acc = 0;
+      uint32_t phase = 0, xphase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 40)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        uint32_t first = 0;
+        for (int u = 0; u < 8 * SEGA && ok; ++u) {
+          const int xseg = u % SEGA;
+          if (!mbar_wait(xfull_bar(xslot), xphase, s_abort, p.err, kErrMma + 40)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t ux = base + xslot * Cfg::kUnitBytes;
+          const int nb = (SEGA == 2 && xseg == 0) ? 2 : 1;
+          for (int t = 0; t < 2 && ok; ++t) {
+            // t: second row tap of this copy (one plane row = 16 pixels x 128 B further)
+            const uint64_t xdesc = umma_desc_sw128(ux + t * 2048);
+            for (int b = 0; b < nb; ++b) {
+              if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma + 41)) { ok = false; break; }
+              tc_fence_after();
+              const uint64_t wdesc = umma_desc_sw128(w_base + stage * Cfg::kWBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(tmem_d, wdesc + 2 * k, xdesc + 2 * k, idesc, first);
+                first = 1u;
+              }
+              umma_commit(empty_bar(stage));
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+          }
+          if (!ok) break;
+          umma_commit(xempty_bar(xslot));
+          if (++xslot == UA) { xslot = 0; xphase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int ch = lg * 32 + lane;          // this thread's output channel
+    const float sc = __ldg(p.scale + ch), sh = __ldg(p.shift + ch);
+    const int ct = 128 * p.out_sega;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int img = blockIdx.x; img < p.n_img; img += gridDim.x) {
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 20)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 256);
+      __nv_bfloat16* out_img = p.out + (size_t)img * 4 * 64 * ct + ch;
+      if (SEGA == 1) {
+        const bool issuer = (threadIdx.x == 64);
+        const float slope = p.slope;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          if (issuer) tma_store_wait_read<0>();       // the previous store has finished reading the staging tile
+          named_bar_sync(1, 128);
+#pragma unroll 1
+          for (int pq = 0; pq < 4; ++pq) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + half * 128 + pq * 32, v);
+            tmem_ld_wait();
+            // pixel (oh_l = 2*pq + (j >> 4), ow = j & 15) of this half -> staging row (plane, oh_l >> 1, ow >> 1)
+            const uint32_t rbase = stg + (uint32_t)(pq * 8 * 256 + ch * 2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = fmaf(__uint_as_float(v[j]), sc, sh);
+              a = fmaxf(a, slope * a);
+              const int row = (((j >> 4) & 1) * 2 + (j & 1)) * 32 + ((j & 15) >> 1);
+              st_shared_u16(rbase + (uint32_t)(row * 256), __bfloat16_as_ushort(__float2bfloat16_rn(a)));
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_5d(&tmap_o, stg, 0, 0, half * 4, 0, img);
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int pb = 0; pb < 256; pb += 32) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + pb, v);
           tmem_ld_wait();
@@ -1930,6 +2130,19 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
     int r = encode(&to, 5, act2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r != SG_OK) return r;
   }
+  if (!getenv("SG_CONV_TAP_STREAM")) {   // default: plane reuse
+    CUtensorMap txr;
+    cuuint64_t dims[5] = {(cuuint64_t)ct_in, 16, 16, 4, (cuuint64_t)batch};
+    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)16 * ct_in * 2, (cuuint64_t)256 * ct_in * 2,
+                             (cuuint64_t)1024 * ct_in * 2};
+    cuuint32_t box[5] = {64, 16, 17, 1, 1};
+    int r = encode(&txr, 5, act1, dims, strides, box);
+    if (r != SG_OK) return r;
+    if (sega == 2) conv2_swap2_kernel<2><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
+    else conv2_swap2_kernel<1><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+  }
   if (sega == 2) conv2_swap_kernel<2><<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, to, p);
   else conv2_swap_kernel<1><<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, to, p);
   SG_LAUNCH_CHECK();
@@ -2029,6 +2242,8 @@ int sg_d64_init_attributes() {
                                ConvCfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv2_swap2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2RCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv2_swap2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2RCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
