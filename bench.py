@@ -234,7 +234,18 @@ def main():
     def sel_only():
         t = sb.percentile_device(losses, q, group, n_global)
         return sb.compact_indices(losses, t, 0, base)
-    ms_sel, _ = timed(sel_only, 20, 3)
+    for _ in range(5):
+        sel_only()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(30):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        sel_only()
+        b_.record()
+        evs.append((a_, b_))
+    torch.cuda.synchronize()
+    ms_sel = float(np.median([a_.elapsed_time(b_) for a_, b_ in evs]))   # median: robust to a host hiccup in the enqueue loop
 
     # ---- secondary: the fp32-parity conv mode (or bf16 when the headline is fp32) --------------------------
     other = "fp32" if args.mode == "bf16" else "bf16"
