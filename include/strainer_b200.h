@@ -128,13 +128,16 @@ int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, vo
 /* ---- selection: order statistics, thresholds ------------------------------------------
  * replaces np.percentile "#strainer gan.py:381", "# 종합 loss.py:288-292" and torch.quantile
  * "# 상위 10% 제거해서 fake image에 concate.py:246", "# z_score + DBSCAN.py:323".
- * Radix select of the order statistics x_(k) and x_(k+1) (NaNs sort last, -0 == +0): four streaming
- * passes over 8 key bits each (256-bin histograms in 32 lane-private shared-memory copies: conflict
- * free even for skewed data); the last pass also tracks the smallest key above the selected 24-bit
- * bucket, so x_(k+1) costs no extra read.  Split in phases so that a multi-GPU caller can all-reduce
- * ws[0..257) (uint32 digit histogram + NaN count, SUM) after every sg_select_hist and
- * ws[SG_SELECT_WS_MINABOVE] (MIN; as int32 of key ^ 0x80000000 it is order preserving) after the
- * last one, before the matching sg_select_step.  */
+ * Radix select of the order statistics x_(k) and x_(k+1) (NaNs sort last, -0 == +0) over 4 x 8 key bits
+ * (256-bin histograms in 32 lane-private shared-memory copies: conflict free even for skewed data); the last
+ * pass also tracks the smallest key above the selected 24-bit bucket, so x_(k+1) costs no extra read.
+ *  - single device: sg_select_kth / sg_radix_select.  All four passes run in ONE cooperative kernel (grid barrier
+ *    between passes, the CTA's slice of the input cached in shared memory); for n >= SG_SELECT_ONEPASS_MIN the
+ *    input itself is read ONCE (sampled pivots + a streaming filter pass) and the passes run over the ~2 % of
+ *    candidates between the pivots.
+ *  - multi-GPU: the phase entry points below, so that the caller can all-reduce ws[0..257) (uint32 digit
+ *    histogram + NaN count, SUM) after every sg_select_hist and ws[SG_SELECT_WS_MINABOVE] (MIN; as int32 of
+ *    key ^ 0x80000000 it is order preserving) after the last one, before the matching sg_select_step.  */
 #define SG_SELECT_WS_WORDS 2048      /* uint32 words of workspace */
 #define SG_SELECT_WS_HIST 0          /* [256] digit histogram of the current pass */
 #define SG_SELECT_WS_NANCOUNT 256    /* number of NaNs seen (pass 0); SUM-reduced with the histogram */
