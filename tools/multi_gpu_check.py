@@ -38,6 +38,20 @@ def main():
             assert thr1 == thrs[0], (thr1, thrs[0])
             assert np.array_equal(all_idx, idx1)
             results[mode] = (float(thr1), len(idx1), n)
+    # sharded deterministic GMM EM (8-double all-reduce per iteration): every rank holds the identical fit, and it
+    # agrees with the single-GPU fit of the whole vector to fp64 summation-order accuracy
+    v = O.synth_losses(40000 * world, seed=7)
+    shard = torch.from_numpy(v[rank * 40000:(rank + 1) * 40000]).to(device)
+    g = sb.gmm_fit_device(shard, group=dist.group.WORLD, n_global=v.size)
+    allg = [None] * world
+    dist.all_gather_object(allg, {k: np.asarray(g[k]).tolist() for k in ("weights", "means", "stds")})
+    if rank == 0:
+        assert all(a == allg[0] for a in allg), allg
+        g1 = sb.gmm_fit_device(torch.from_numpy(v).to(device))
+        for k in ("weights", "means", "stds"):
+            assert np.allclose(g[k], g1[k], rtol=1e-9), (k, g[k], g1[k])
+        assert g["n_iter"] == g1["n_iter"]
+        results["gmm"] = (g["means"].tolist(), g["n_iter"])
     if rank == 0:
         print("multi_gpu_check OK", world, "ranks", results, flush=True)
     dist.barrier()
