@@ -220,6 +220,17 @@ int sg_minmax(const float* v, int64_t n, float* minmax, void* stream);
  * counts[bins] int64 accumulated (caller zeroes). */
 int sg_hist_uniform(const float* v, int64_t n, const float* edges, int bins, long long* counts, void* stream);
 
+/* ---- DBSCAN clean ratio of [n, d] features on the tensor cores -----------------------------------
+ * replaces StandardScaler -> DBSCAN(eps, min_samples) -> mean(labels != -1) of estimate_ratio_dbscan
+ * "# z_score + DBSCAN.py:291-299" (SURVEY 8f item 2).  z = (x - mean) / denom (column moments from sg_col_moments,
+ * ddof 0), pairwise squared distances as a tcgen05 GEMM (bf16 hi/lo split, fp32-grade) with the eps threshold in
+ * the epilogue: pass 0 neighbour counts -> core points, pass 1 points within eps of a core point.
+ * counts_out = {#core, #non-noise} (device int64[2]); d multiple of 64; workspace 1024-byte aligned. */
+size_t sg_dbscan_nd_workspace_bytes(int64_t n, int d);
+int sg_dbscan_nd(const float* x, int64_t n, int d, const float* mean, const float* denom, double eps, int min_samples,
+                 int64_t* counts_out, void* workspace, void* stream);
+int sg_dbscan_nd_check(const void* workspace, void* stream);
+
 /* ---- two-component 1-D Gaussian-mixture EM ----------------------------------------------------
  * replaces GaussianMixture(n_components=2, max_iter=10, tol=1e-2, reg_covar=5e-4).fit(losses) of
  * "#clean 분포와 noisy 분포가 만나는 지점의 loss보다 작은 데.py:290-292", "# 종합 loss.py:271-273" (SURVEY 8f item 2).

@@ -59,6 +59,9 @@ _SIGS = {
     "sg_sort_f32": (c_int, [P, c_int64, P, P, P, P]),
     "sg_dbscan1d_workspace_bytes": (c_size_t, [c_int64]),
     "sg_dbscan1d": (c_int, [P, c_int64, c_double, c_int, P, P, P, P]),
+    "sg_dbscan_nd_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "sg_dbscan_nd": (c_int, [P, c_int64, c_int, P, P, c_double, c_int, P, P, P]),
+    "sg_dbscan_nd_check": (c_int, [P, P]),
     "sg_gmm1d_workspace_bytes": (c_size_t, []),
     "sg_gmm1d_begin": (c_int, [P, c_int, P, P]),
     "sg_gmm1d_accumulate": (c_int, [P, c_int64, P, P]),

@@ -833,11 +833,35 @@ def dbscan1d_clean_ratio(values, eps, min_samples=3, return_noise: bool = False)
     return (ratio, noise.bool()) if return_noise else ratio
 
 
-def estimate_ratio_dbscan(dataset, eps=20, min_samples=3, feature_extractor=None):
-    """``estimate_ratio_dbscan`` ("# z_score + DBSCAN.py:272-301").  The reference clusters the
-    standardised 512-d ResNet18 features with scikit-learn; that neighbour search
-    stays scikit-learn on the host.  When the features are one-dimensional (a score / loss /
-    max-z vector) the device sort path ``dbscan1d_clean_ratio`` is used instead."""
+def dbscan_clean_ratio(features, eps, min_samples=3, return_counts: bool = False):
+    """``mean(DBSCAN(eps, min_samples).fit_predict(StandardScaler().fit_transform(features)) != -1)``
+    ("# z_score + DBSCAN.py:291-299") for an [N, d] feature matrix, d a multiple of 64, on the GPU: column
+    standardisation + two thresholded pairwise-distance GEMMs on tcgen05 (core points, then points within eps of
+    a core point).  Nothing of size N^2 is stored."""
+    device = _dev()
+    lib = _lib_for(device)
+    f = _f32c(features, device)
+    n, d = f.shape
+    mean = torch.empty(d, dtype=torch.float32, device=device)
+    den = torch.empty(d, dtype=torch.float32, device=device)
+    zws = _Scratch.get(device, "colmom", lib.sg_col_moments_workspace_bytes(n, d))
+    L.check(lib.sg_col_moments(_p(f), n, d, 0, 0.0, _p(mean), _p(den), _p(zws), _stream()), "sg_col_moments")
+    den = torch.where(den == 0, torch.ones_like(den), den)     # StandardScaler: zero-variance columns are left unscaled
+    counts = torch.empty(2, dtype=torch.int64, device=device)
+    ws = _Scratch.get(device, "dbscan_nd", lib.sg_dbscan_nd_workspace_bytes(n, d))
+    L.check(lib.sg_dbscan_nd(_p(f), n, d, _p(mean), _p(den), float(eps), int(min_samples), _p(counts), _p(ws), _stream()),
+            "sg_dbscan_nd")
+    L.check(lib.sg_dbscan_nd_check(_p(ws), _stream()), "sg_dbscan_nd_check")
+    c = counts.cpu().numpy()
+    ratio = int(c[1]) / n
+    return (ratio, int(c[0]), int(c[1])) if return_counts else ratio
+
+
+def estimate_ratio_dbscan(dataset, eps=20, min_samples=3, feature_extractor=None, *, neighbors: str = "device"):
+    """``estimate_ratio_dbscan`` ("# z_score + DBSCAN.py:272-301"): StandardScaler -> DBSCAN -> fraction of
+    non-noise points of the (512-d ResNet18) features.  neighbors='device' (default when the feature width is a
+    multiple of 64): ``dbscan_clean_ratio`` on the tensor cores; 'sklearn': the reference's own host call.
+    One-dimensional inputs (a score / loss / max-z vector) use the device sort path ``dbscan1d_clean_ratio``."""
     device = _dev()
     feats = _features_of(dataset, feature_extractor, device)
     if feats.dim() == 1 or feats.shape[1] == 1:
@@ -845,6 +869,8 @@ def estimate_ratio_dbscan(dataset, eps=20, min_samples=3, feature_extractor=None
         mean = f.double().mean()
         std = f.double().std(unbiased=False)
         return dbscan1d_clean_ratio(((f.double() - mean) / std).float(), eps, min_samples)
+    if neighbors == "device" and feats.shape[1] % 64 == 0:
+        return dbscan_clean_ratio(feats, eps, min_samples)
     from sklearn.cluster import DBSCAN
     from sklearn.preprocessing import StandardScaler
     labels = DBSCAN(eps=eps, min_samples=min_samples).fit_predict(StandardScaler().fit_transform(feats.cpu().numpy()))

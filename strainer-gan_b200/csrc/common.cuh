@@ -12,6 +12,7 @@ extern "C" int sg_d64_init_attributes();  // internal: raises the conv kernels' 
 extern "C" int sg_ae_init_attributes();
 extern "C" int sg_select_init_attributes();
 extern "C" int sg_ae_tc_init_attributes();
+extern "C" int sg_dbscan_init_attributes();
 
 namespace sg {
 

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) col_partial_kernel(const float* __restric
     // keep 8 x 128-bit loads in flight each; the two row phases are combined in a fixed order.
     __shared__ double s_part[2][128][8];
     const int groups = d >> 2;                      // float4 column groups per row
-    const int phases = groups >= 256 ? 1 : 256 / groups;
+    const int phases = (groups == 128) ? 2 : 1;   // two row phases only in the tuned d = 512 case (their partials are combined below)
     const int cg = threadIdx.x % groups, ph = threadIdx.x / groups;
     for (int c0 = 0; c0 < groups; c0 += 256) {
       const int g = c0 + cg;

@@ -29,6 +29,13 @@ def test_zscore_max(sb, feats, golden):
     f2 = feats.copy()
     f2[:, 5] = 1.0  # constant column -> 0/0 = NaN -> every row NaN
     assert np.isnan(sb.zscore_max(torch.from_numpy(f2)).cpu().numpy()).all()
+    # feature widths other than the reference's 512 (vectorised and scalar column paths, ragged row counts)
+    rng = np.random.default_rng(5)
+    for n, d in ((1000, 64), (777, 100), (300, 128), (513, 1024), (129, 2048), (64, 7)):
+        f = (rng.standard_normal((n, d)) * rng.uniform(0.5, 3, d) + rng.uniform(-2, 2, d)).astype(np.float32)
+        got = sb.zscore_max(torch.from_numpy(f)).cpu().numpy()
+        want = O.zscore_max_torch(torch.from_numpy(f)).numpy()
+        assert np.allclose(got, want, rtol=2e-5, atol=1e-6), (n, d, np.abs(got - want).max())
 
 
 def test_find_elbow_threshold_bit_exact(sb, golden):
@@ -160,3 +167,31 @@ def test_autoencoder_bf16_conv_mode(sb, golden):
     assert (np.abs(e3 - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2
     e4 = sb.ae_errors(ae, x[:48], "cuda").cpu().numpy()
     assert (np.abs(e4 - ref) / np.maximum(ref, 1e-6)).max() <= 1e-3
+
+
+def test_dbscan_nd_clean_ratio_vs_sklearn(sb):
+    """StandardScaler -> DBSCAN -> mean(labels != -1) on [N, 512] features via thresholded
+    pairwise-distance GEMMs on tcgen05; counts of core / non-noise points equal scikit-learn's."""
+    from sklearn.cluster import DBSCAN
+    from sklearn.preprocessing import StandardScaler
+    rng = np.random.default_rng(17)
+    for n, d in ((700, 512), (3000, 512), (1025, 64), (2500, 128)):
+        # a few tight clusters + scattered points: core, border and noise points all occur
+        centers = rng.standard_normal((6, d)).astype(np.float32) * 3
+        lab = rng.integers(0, 6, n)
+        f = centers[lab] + rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.2, 1.2, (n, 1)).astype(np.float32)
+        f[: n // 10] = rng.standard_normal((n // 10, d)).astype(np.float32) * 6          # outliers
+        z = StandardScaler().fit_transform(f)
+        dist = np.sqrt(np.maximum((z * z).sum(1)[:, None] + (z * z).sum(1)[None, :] - 2 * z.astype(np.float64) @ z.T.astype(np.float64), 0))
+        for frac in (0.02, 0.1, 0.4):
+            eps = float(np.quantile(dist[np.triu_indices(n, 1)], frac))
+            if np.abs(dist - eps).min() < 1e-4 * eps:
+                eps *= 1.0003                                             # keep every pair off the decision boundary
+            m = DBSCAN(eps=eps, min_samples=3).fit(z)
+            want_core, want_clean = len(m.core_sample_indices_), int((m.labels_ != -1).sum())
+            ratio, core, clean = sb.dbscan_clean_ratio(torch.from_numpy(f), eps, 3, return_counts=True)
+            assert (core, clean) == (want_core, want_clean), (n, d, frac, core, clean, want_core, want_clean)
+            assert ratio == want_clean / n
+    ds = torch.utils.data.TensorDataset(torch.from_numpy(f), torch.zeros(n))
+    r_dev = sb.estimate_ratio_dbscan(ds, eps=eps, min_samples=3, feature_extractor=torch.nn.Identity())
+    assert r_dev == O.estimate_ratio_dbscan_features(f, eps, 3)

@@ -191,6 +191,16 @@ def main():
         c.update(cpu_ms=tc * 1e3, cpu_rows_per_s=nfeat / tc)
     out["configs"]["C3_zscore_dbscan1d_65536x512"] = c
 
+    # 512-d DBSCAN clean ratio (the reference's estimate_ratio_dbscan) on the tensor cores
+    for nd in (8192, 65536):
+        fdd = fd[:nd].contiguous()
+        t = gpu_time(lambda: sb.dbscan_clean_ratio(fdd, 28.0, 3), 3, 1)
+        c = {"rows": nd, "d": 512, "gpu_ms": t * 1e3, "pair_gemm_tflops": 2 * 3 * 2.0 * nd * nd * 512 / t / 1e12}
+        if not a.no_cpu and nd == 8192:
+            tc = cpu_time(lambda: O.estimate_ratio_dbscan_features(feats[:nd].numpy(), 28.0, 3), 1, 0)
+            c.update(cpu_ms=tc * 1e3)
+        out["configs"][f"C3_dbscan512_clean_ratio_{nd}"] = c
+
     # ---- C4: auto-encoder reconstruction straining, batch 512 ---------------------------------------------------
     torch.manual_seed(3)
     ae = O.AutoEncoder().eval()
