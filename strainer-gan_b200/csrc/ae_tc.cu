@@ -18,6 +18,7 @@
 //   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> bf16 [32][32][16]  CUDA cores, one 2x2 output quad per thread
 //   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -54,7 +55,8 @@ static Layout layout(int64_t batch) {
 }
 
 // w3 [64][32][7][7] (Conv2d: out, in, kh, kw)  -> bf16 [oc][ks = kh*4 + kwp][j = px*32 + c], kw = 2*kwp + px (kw == 7 -> 0)
-// w4 [64][32][7][7] (ConvTranspose2d: in, out, kh, kw) -> bf16 [oc][ks = ky*7 + kx][ic]
+// w4 [64][32][7][7] (ConvTranspose2d: in, out, kh, kw) -> bf16 [oc][ks = kx*7 + ky][ic] (the 7 row taps of a column shift
+// are contiguous: one weight stage of ae_dec1_kernel)
 __global__ void pack_k7_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
                                __nv_bfloat16* __restrict__ p4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,7 +67,7 @@ __global__ void pack_k7_kernel(const float* __restrict__ w3, const float* __rest
   }
   if (i < 32 * kKs4 * 64) {
     const int ic = i & 63, ks = (i >> 6) % kKs4, oc = i / (64 * kKs4);
-    const int ky = ks / 7, kx = ks % 7;
+    const int kx = ks / 7, ky = ks % 7;
     p4[i] = __float2bfloat16_rn(w4[((ic * 32 + oc) * 7 + ky) * 7 + kx]);
   }
 }
@@ -132,7 +134,7 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 1)) { ok = false; break; }
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kALoad + Cfg::kBBytes);
-          if (CONVT) tma_load_4d(sa, &tmap_a, full_bar(stage), 0, -(ks % 7), y0 - ks / 7, img);   // in(y - ky, x - kx)
+          if (CONVT) tma_load_4d(sa, &tmap_a, full_bar(stage), 0, -(ks / 7), y0 - ks % 7, img);   // in(y - ky, x - kx), ks = kx*7 + ky
           else tma_load_4d(sa, &tmap_a, full_bar(stage), 0, 2 * (ks & 3), ks >> 2, img);            // in(y + kh, x + kw)
           tma_load_2d(sa + Cfg::kABytes, &tmap_b, full_bar(stage), ks * 64, 0);
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -198,6 +200,168 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// L4 (ConvT 64->32 k7) with INPUT REUSE.  The per-tap kernel above fetches a 16 KB zero-padded window per tap and
+// tile: 2 x 49 x 20 KB = 1.96 MB of TMA traffic per image for a 12.8 KB input -- TMA-service bound (1.39 ms per 8192
+// images).  Here one shared-memory copy per COLUMN shift kx holds the whole zero-padded input (input rows -6..15 x
+// 16 columns starting at -kx, 64 ch = 44 KB, of which only 12.8 KB come from L2; the rest is TMA zero fill); the
+// 7 row taps ky and both 8-row output tiles of the image read it through descriptor offsets of whole rows
+// (16 pixels x 128 B = 2048 B).  Both tiles accumulate side by side in TMEM (2 x 32 columns per image).
+// ------------------------------------------------------------------------------------------
+struct Dec1Cfg {
+  static constexpr int kCopyBytes = 22 * 16 * 128;   // 44 KB slot: 6 zero rows | 10 input rows | 6 zero rows, 16 columns each
+  static constexpr int kLoadBytes = 10 * 16 * 128;   // only the 10 input rows are (re)loaded; the zero rows are written once
+  static constexpr int kCopies = 3;
+  static constexpr int kTapBytes = 32 * 128;         // one tap: 32 oc x 64 ic
+  static constexpr int kBBytes = 7 * kTapBytes;      // a weight stage = the 7 row taps of one column shift
+  static constexpr int kBStages = 2;
+  static constexpr int kTmemCols = 128;              // 2 images x (2 tiles x 32 columns)
+  static constexpr int kSmemBytes = kCopies * kCopyBytes + kBStages * kBBytes + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
+  using Cfg = Dec1Cfg;
+  constexpr int UA = Cfg::kCopies, SB = Cfg::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + UA * Cfg::kCopyBytes;
+  const uint32_t bar0 = b_base + SB * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto afull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
+  auto bfull_bar = [&](int s) { return bar0 + 8u * (2 * UA + s); };
+  auto bempty_bar = [&](int s) { return bar0 + 8u * (2 * UA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + 2 + a); };
+  constexpr int kNb = 2 * UA + 2 * SB + 4;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  for (int i = threadIdx.x; i < UA * 12 * 2048 / 16; i += 192) {   // rows 0-5 and 16-21 of every slot
+    const int slot = i / (12 * 128), r = (i / 128) % 12, c = i % 128;
+    const int rowi = r < 6 ? r : r + 10;
+    *reinterpret_cast<uint4*>(smem + slot * Cfg::kCopyBytes + rowi * 2048 + c * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int aslot = 0, bstage = 0;
+      uint32_t aphase = 0, bphase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
+        for (int kx = 0; kx < 7 && ok; ++kx) {
+          if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 11)) { ok = false; break; }
+          mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kLoadBytes);
+          tma_load_4d(base + aslot * Cfg::kCopyBytes + 6 * 2048, &tmap_a, afull_bar(aslot), 0, -kx, 0, img);
+          if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+          if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 12)) { ok = false; break; }
+          mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
+          for (int ky = 0; ky < 7; ++ky)
+            tma_load_2d(b_base + bstage * Cfg::kBBytes + ky * Cfg::kTapBytes, &tmap_b, bfull_bar(bstage), (kx * 7 + ky) * 64, 0);
+          if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(32);
+      int aslot = 0, bstage = 0, acc = 0;
+      uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 13)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+        uint32_t first = 0;
+        for (int kx = 0; kx < 7 && ok; ++kx) {
+          if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 14)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t ca = base + aslot * Cfg::kCopyBytes;
+          if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 15)) { ok = false; break; }
+          tc_fence_after();
+#pragma unroll 1
+          for (int ky = 0; ky < 7; ++ky) {
+            const uint64_t bdesc = umma_desc_sw128(b_base + bstage * Cfg::kBBytes + ky * Cfg::kTapBytes);
+            // output rows y0..y0+7 read input rows y0 - ky .. = copy rows (y0 + 6 - ky) ..; one copy row = 2048 B
+            const uint64_t a0 = umma_desc_sw128(ca + (uint32_t)(6 - ky) * 2048u);
+            const uint64_t a1 = umma_desc_sw128(ca + (uint32_t)(14 - ky) * 2048u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(tmem_d, a0 + 2 * k, bdesc + 2 * k, idesc, first);
+              umma_f16(tmem_d + 32, a1 + 2 * k, bdesc + 2 * k, idesc, first);
+              first = 1u;
+            }
+          }
+          umma_commit(bempty_bar(bstage));
+          if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+          if (!ok) break;
+          umma_commit(aempty_bar(aslot));
+          if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 16)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + t * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j), 0.f);
+          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1), 0.f);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        uint4* d = reinterpret_cast<uint4*>(out + ((size_t)img * 256 + t * 128 + row) * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -519,6 +683,7 @@ int sg_ae_tc_init_attributes() {
                                K7Cfg<64, false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<32, true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   return SG_OK;
 }
 
@@ -550,8 +715,25 @@ int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params
   SG_LAUNCH_CHECK();
   int r = launch_k7<64, false>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
   if (r != SG_OK) return r;
-  r = launch_k7<32, true>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
-  if (r != SG_OK) return r;
+  if (getenv("SG_AE_TAP_STREAM")) {   // per-tap streaming form kept for A/B timing
+    r = launch_k7<32, true>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
+    if (r != SG_OK) return r;
+  } else {
+    CUtensorMap ta, tb;
+    cuuint64_t adims[4] = {64, 10, 10, (cuuint64_t)batch};
+    cuuint64_t astr[3] = {128, 1280, 12800};
+    cuuint32_t abox[4] = {64, 16, 10, 1};   // the 10 input rows, 16 columns from -kx (columns outside the map: zero fill)
+    r = sg::encode_tmap(&ta, 4, bf(L.a3), adims, astr, abox);
+    if (r != SG_OK) return r;
+    cuuint64_t bdims[2] = {(cuuint64_t)kKs4 * 64, 32};
+    cuuint64_t bstr[1] = {(cuuint64_t)kKs4 * 64 * 2};
+    cuuint32_t bbox[2] = {64, 32};
+    r = sg::encode_tmap(&tb, 2, bf(L.w4), bdims, bstr, bbox);
+    if (r != SG_OK) return r;
+    const int grid = (int)(batch < sg::state().sm_count ? batch : sg::state().sm_count);
+    ae_dec1_kernel<<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
+    SG_LAUNCH_CHECK();
+  }
   dec2_kernel<<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
   SG_LAUNCH_CHECK();
   dec3_mse_kernel<<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
