@@ -1,11 +1,13 @@
 // D64 scoring path: Discriminator.forward (eval-mode BN) + sigmoid + BCE vs label 1.
 // Replaces "#strainer gan.py:230-256" + ":369-375" (K1..K6 of SURVEY.md §2.3).
 //
-//   L1  conv 3->64 k4s2p1 + LeakyReLU        fp32 NCHW in, CUDA-core direct conv, bf16 out
-//   L2  conv 64->128  + BN + LeakyReLU  \
-//   L3  conv 128->256 + BN + LeakyReLU   }   implicit GEMM on tcgen05: TMA-staged 128x64 activation
-//   L4  conv 256->512 + BN + LeakyReLU  /    tiles and Nx64 weight tiles (SWIZZLE_128B), fp32
-//                                            accumulators in TMEM, fused scale/shift/LeakyReLU epilogue
+//   L1  conv 3->64 k4s2p1 + LeakyReLU        conv1_fused_kernel: fp32 NCHW box by TMA, bf16 operand built in the kernel,
+//                                            tcgen05 M=128 N=64 K=4x16, TMA-store epilogue
+//   L2  conv 64->128  + BN + LeakyReLU       conv2_swap2_kernel: channel-major accumulator (weights = A), plane reuse
+//   L3  conv 128->256 + BN + LeakyReLU  \    conv_pair2_kernel: CTA pairs (cta_group::2, 256x256 tiles), plane reuse;
+//   L4  conv 256->512 + BN + LeakyReLU  /    fp32 accumulators in TMEM, fused scale/shift/LeakyReLU epilogue
+//       (conv_umma_kernel / conv_pair_kernel / conv2_swap_kernel: the per-tap-streaming forms, kept behind
+//        SG_CONV_SINGLE_CTA / SG_CONV_TAP_STREAM for A/B timing)
 //   L5  conv 512->1 k4s1p0 (8192-dot) + sigmoid + BCE: one warp per sample
 //
 // Activation layout between layers ("parity planes"): a 4x4/stride-2/pad-1 conv reads input pixel
@@ -32,7 +34,6 @@ using namespace ptx;
 
 constexpr int kErrProducer = 1, kErrMma = 2, kErrMmaAcc = 3, kErrEpilogue = 4;
 constexpr int kBnBlocks = 256;              // fixed row partition of the train-mode BN reduction
-constexpr int kIn0Bytes = 66 * 66 * 4 * 2;  // one padded 66x66x4 bf16 image (34848 B)
 
 // ------------------------------------------------------------------------------------------
 // Packed parameter block layout (bytes), shared by sg_d64_pack / sg_d64_score
@@ -63,7 +64,7 @@ static PackedLayout packed_layout(int mode) {
 }
 
 struct WorkspaceLayout {
-  size_t flag, act0, act1, act2, act3, act4, bnpart, bnss, total;
+  size_t flag, act1, act2, act3, act4, bnpart, bnss, total;
   int sega;
 };
 static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
@@ -75,7 +76,6 @@ static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
   L.act2 = o; o += align_up((size_t)batch * 16 * 16 * 128 * L.sega * 2, 1024);
   L.act3 = o; o += align_up((size_t)batch * 8 * 8 * 256 * L.sega * 2, 1024);
   L.act4 = o; o += align_up((size_t)batch * 16 * 512 * L.sega * 2, 1024);
-  L.act0 = o; o += align_up((size_t)batch * kIn0Bytes * L.sega, 1024);  // zero-padded NHWC4 bf16 input
   L.bnpart = o; o += align_up((size_t)kBnBlocks * 512 * 2 * sizeof(double), 1024);  // train-mode BN partial sums
   L.bnss = o; o += align_up(2 * 512 * 4, 1024);                                      // batch-stat scale | shift
   L.total = o;
@@ -139,82 +139,6 @@ __global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __r
     gb[i] = gamma[i];
     gb[c + i] = beta[i];
     if (ident) { ident[i] = 1.f; ident[512 + i] = 0.f; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// L1: direct conv 3->64, k4 s2 p1, LeakyReLU, fp32 math on CUDA cores.
-// One CTA = 4 output rows x 32 cols of one image (128 threads, one output pixel each, all 64
-// channels in registers).  Output: parity-plane bf16 [n][4][16][16][64*sega].
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) conv1_kernel(const float* __restrict__ x, const float* __restrict__ w1p,
-                                                    __nv_bfloat16* __restrict__ act1, int sega) {
-  __shared__ __align__(16) float s_w[48 * 64];
-  __shared__ float s_in[3][10][68];
-  const int n = blockIdx.x >> 3;
-  const int oh0 = (blockIdx.x & 7) << 2;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 48 * 64 / 4; i += 128)
-    reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(w1p)[i];
-  const float* xin = x + (size_t)n * 3 * 64 * 64;
-  // patch rows ih = 2*oh0-1 .. 2*oh0+8, cols iw = -1 .. 64 stored at [.][.][iw+1]
-  for (int i = tid; i < 3 * 10 * 66; i += 128) {
-    const int c = i / 660, r = (i / 66) % 10, col = i % 66;
-    const int ih = 2 * oh0 - 1 + r, iw = col - 1;
-    float v = 0.f;
-    if (ih >= 0 && ih < 64 && iw >= 0 && iw < 64) v = xin[(c * 64 + ih) * 64 + iw];
-    s_in[c][r][col] = v;
-  }
-  __syncthreads();
-  const int orow = tid >> 5, ow = tid & 31;
-  float in[48];
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int kh = 0; kh < 4; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 4; ++kw) in[c * 16 + kh * 4 + kw] = s_in[c][2 * orow + kh][2 * ow + kw];
-  const int oh = oh0 + orow;
-  const int ct = 64 * sega;
-  const size_t off = ((((size_t)n * 4 + ((oh & 1) * 2 + (ow & 1))) * 16 + (oh >> 1)) * 16 + (ow >> 1)) * ct;
-  __nv_bfloat16* dst = act1 + off;
-#pragma unroll 1
-  for (int cb = 0; cb < 64; cb += 16) {
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 48; ++k) {
-      const float4* wr = reinterpret_cast<const float4*>(s_w + k * 64 + cb);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w4 = wr[q];
-        acc[q * 4 + 0] = fmaf(in[k], w4.x, acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(in[k], w4.y, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(in[k], w4.z, acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(in[k], w4.w, acc[q * 4 + 3]);
-      }
-    }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = acc[2 * j], b = acc[2 * j + 1];
-      a = a > 0.f ? a : 0.2f * a;
-      b = b > 0.f ? b : 0.2f * b;
-      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-      hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-      const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-      const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-      lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-    }
-    uint4* d = reinterpret_cast<uint4*>(dst + cb);
-    d[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    d[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    if (sega == 2) {
-      uint4* dl = reinterpret_cast<uint4*>(dst + 64 + cb);
-      dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-    }
   }
 }
 
@@ -1279,228 +1203,6 @@ conv2_swap2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
-// L1 on the tensor cores.
-//  prep_input_kernel : fp32 NCHW -> zero-padded NHWC4 bf16 [n][sega][66][66][4] (hi | lo planes), so that
-//                      for a fixed kh the 16 K-values (kw, c) of an output pixel are 32 contiguous bytes.
-//  conv1_umma_kernel : implicit GEMM M = 128 pixels (4 output rows x 32), N = 64, K = 4 x 16.  The A
-//                      slice of one kh is ONE 5-D TMA box over an overlapping-stride view of the padded
-//                      image (window stride 16 B along ow), landing as a K-major SWIZZLE_32B operand;
-//                      the 8/16 KB of weights stay resident in shared memory for the whole kernel.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_input_kernel(const float* __restrict__ x, uint2* __restrict__ out,
-                                                         int64_t batch, int sega) {
-  const int64_t total = batch * 4356;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = i / 4356;
-    const int r2 = (int)(i - n * 4356);
-    const int r = r2 / 66, c = r2 - r * 66;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (r >= 1 && r <= 64 && c >= 1 && c <= 64) {
-      const float* px = x + (size_t)n * 12288 + (r - 1) * 64 + (c - 1);
-      v0 = px[0]; v1 = px[4096]; v2 = px[8192];
-    }
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1), h2 = __float2bfloat16_rn(v2);
-    uint2 hi;
-    hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    hi.y = (uint32_t)__bfloat16_as_ushort(h2);
-    out[(size_t)n * sega * 4356 + r2] = hi;
-    if (sega == 2) {
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-      const __nv_bfloat16 l2 = __float2bfloat16_rn(v2 - __bfloat162float(h2));
-      uint2 lo;
-      lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-      lo.y = (uint32_t)__bfloat16_as_ushort(l2);
-      out[((size_t)n * 2 + 1) * 4356 + r2] = lo;
-    }
-  }
-}
-
-// K-major SWIZZLE_32B operand descriptor: rows of 32 B, 8-row groups 256 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) |
-         (6ull << 61);
-}
-
-template <int SEGA>
-struct Conv1Cfg {
-  static constexpr int kSliceA = 128 * 32;             // one kh slice of A: 128 rows x 32 B
-  static constexpr int kSliceB = 64 * 32;              // one kh slice of B: 64 rows x 32 B
-  static constexpr int kStageBytes = SEGA * 4 * kSliceA;
-  static constexpr int kBBytes = SEGA * 4 * kSliceB;
-  static constexpr int kStages = (SEGA == 2) ? 3 : 4;
-  static constexpr int kTmemCols = 128;                // 2 accumulators x 64 columns
-  static constexpr int kStageOut = SEGA * 128 * 128;   // epilogue staging: 128 pixels x 64 ch bf16 per seg
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 2 * kStageOut + 256 + 1024;
-  static constexpr int kThreads = 192;
-};
-
-template <int SEGA>
-__global__ void __launch_bounds__(192, 2)
-conv1_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_o, int total_tiles, int* err) {
-  using Cfg = Conv1Cfg<SEGA>;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t b_base = base + S * Cfg::kStageBytes;
-  const uint32_t o_base = b_base + Cfg::kBBytes;   // 2 output staging buffers (1024-B aligned)
-  const uint32_t bar0 = o_base + 2 * Cfg::kStageOut;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kBBytes + 2 * Cfg::kStageOut);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    prefetch_tensormap(&tmap_o);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
-    mbar_init(wbar, 1);
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // resident weights: SEGA x 4 slices of [64 x 16]
-      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
-      for (int sg_ = 0; sg_ < SEGA; ++sg_)
-        for (int kh = 0; kh < 4; ++kh)
-          tma_load_2d(b_base + (sg_ * 4 + kh) * Cfg::kSliceB, &tmap_b, wbar, sg_ * 64 + kh * 16, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n = tile >> 3, oh0 = (tile & 7) << 2;
-        if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrProducer + 10)) break;
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        const uint32_t sa = base + stage * Cfg::kStageBytes;
-        for (int sg_ = 0; sg_ < SEGA; ++sg_)
-          for (int kh = 0; kh < 4; ++kh)
-            tma_load_5d(sa + (sg_ * 4 + kh) * Cfg::kSliceA, &tmap_a, full_bar(stage), 0, 0, kh & 1, oh0 + (kh >> 1),
-                        n * SEGA + sg_);
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrMma + 10);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrMmaAcc + 10)) break;
-        if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrMma + 10)) break;
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
-        const uint32_t sa = base + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int kh = 0; kh < 4; ++kh) {
-          const uint64_t a_hi = umma_desc_sw32(sa + kh * Cfg::kSliceA);
-          const uint64_t b_hi = umma_desc_sw32(b_base + kh * Cfg::kSliceB);
-          umma_f16(tmem_d, a_hi, b_hi, idesc, (uint32_t)(kh != 0));
-          if (SEGA == 2) {
-            const uint64_t a_lo = umma_desc_sw32(sa + (4 + kh) * Cfg::kSliceA);
-            const uint64_t b_lo = umma_desc_sw32(b_base + (4 + kh) * Cfg::kSliceB);
-            umma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
-            umma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
-          }
-        }
-        umma_commit(empty_bar(stage));
-        umma_commit(tfull_bar(acc));
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    // Epilogue: TMEM -> registers -> LeakyReLU -> bf16 -> swizzled smem staging -> TMA store.
-    // The tile's 128 pixels (4 output rows x 32 cols) are 4 parity planes x (2 x 16) pixels of act1:
-    // one 4 KB TMA box per plane (and per hi/lo segment), so HBM sees full 128-B rows.
-    const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    const int ohl = row >> 5, ow = row & 31;
-    const int prow = (((ohl & 1) * 2 + (ow & 1)) << 5) + ((ohl >> 1) << 4) + (ow >> 1);  // row in staging
-    const uint32_t swz = (uint32_t)(prow & 7);
-    const bool issuer = (threadIdx.x == 64);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n = tile >> 3, oh0 = (tile & 7) << 2;
-      const uint32_t stg = o_base + (uint32_t)(it & 1) * Cfg::kStageOut;
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrEpilogue + 10)) break;
-      tc_fence_after();
-      // the staging buffer used two tiles ago must have been read by its TMA stores
-      if (issuer) tma_store_wait_read<1>();
-      named_bar_sync(1, 128);
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
-#pragma unroll
-      for (int cb = 0; cb < 64; cb += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + cb, v);
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
-          a = a > 0.f ? a : 0.2f * a;
-          b = b > 0.f ? b : 0.2f * b;
-          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
-          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
-          if (SEGA == 2) {
-            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
-            lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-          }
-        }
-        const uint32_t rbase = stg + (uint32_t)prow * 128u;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = (uint32_t)((cb >> 3) + q) ^ swz;   // SWIZZLE_128B: 16-B chunk ^= row & 7
-          st_shared_v4(rbase + chunk * 16u, hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          if (SEGA == 2)
-            st_shared_v4(rbase + 128u * 128u + chunk * 16u, lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));      // accumulator is in registers/smem: release TMEM early
-      fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA store
-      named_bar_sync(1, 128);
-      if (issuer) {
-#pragma unroll
-        for (int sg_ = 0; sg_ < SEGA; ++sg_)
-#pragma unroll
-          for (int pl = 0; pl < 4; ++pl)
-            tma_store_5d(&tmap_o, stg + (uint32_t)(sg_ * 128 * 128 + pl * 4096), sg_ * 64, 0, oh0 >> 1, pl, n);
-        tma_store_commit();
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-    if (issuer) tma_store_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // L1 fused with the input conversion: the fp32 NCHW image is the only HBM read (49 152 B/sample), no
 // bf16 staging copy.  One tile = 4 output rows x 32 cols of one image:
 //   warp 0    : TMA producer, fp32 box [3 ch][10 input rows][64 cols] (rows -1 / 64 zero-filled by TMA)
@@ -2185,50 +1887,6 @@ static int launch_conv1_fused(const float* x, const __nv_bfloat16* w1t, __nv_bfl
   return SG_OK;
 }
 
-template <int SEGA>
-static int launch_conv1(const float* x, __nv_bfloat16* act0, const __nv_bfloat16* w1t, __nv_bfloat16* act1,
-                        int64_t batch, int* err, cudaStream_t stream) {
-  using Cfg = Conv1Cfg<SEGA>;
-  {
-    int64_t blocks = ceil_div(batch * 4356, 256);
-    const int64_t cap = (int64_t)state().sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    prep_input_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, reinterpret_cast<uint2*>(act0), batch, SEGA);
-    SG_LAUNCH_CHECK();
-  }
-  CUtensorMap ta, tb;
-  {
-    // (k within window, ow [window stride 16 B], row parity, row pair, image*SEGA + seg)
-    cuuint64_t dims[5] = {16, 32, 2, 33, (cuuint64_t)batch * SEGA};
-    cuuint64_t strides[4] = {16, 66 * 4 * 2, 2 * 66 * 4 * 2, (cuuint64_t)kIn0Bytes};
-    cuuint32_t box[5] = {16, 32, 1, 4, 1};
-    int r = encode(&ta, 5, act0, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (r != SG_OK) return r;
-  }
-  {
-    cuuint64_t dims[2] = {128, 64};
-    cuuint64_t strides[1] = {128 * 2};
-    cuuint32_t box[2] = {16, 64};
-    int r = encode(&tb, 2, w1t, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (r != SG_OK) return r;
-  }
-  CUtensorMap to;
-  {
-    const cuuint64_t ct = 64 * SEGA;
-    cuuint64_t dims[5] = {ct, 16, 16, 4, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {ct * 2, 16 * ct * 2, 256 * ct * 2, 1024 * ct * 2};
-    cuuint32_t box[5] = {64, 16, 2, 1, 1};
-    int r = encode(&to, 5, act1, dims, strides, box);
-    if (r != SG_OK) return r;
-  }
-  const int64_t tiles = batch * 8;
-  const int64_t ctas = (int64_t)state().sm_count * (SEGA == 1 ? 2 : 1);
-  int grid = (int)(tiles < ctas ? tiles : ctas);
-  conv1_umma_kernel<SEGA><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, to, (int)tiles, err);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
-}
-
 }  // namespace d64
 }  // namespace sg
 
@@ -2236,8 +1894,6 @@ extern "C" {
 
 int sg_d64_init_attributes() {
   using namespace sg::d64;
-  SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<128>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                ConvCfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
@@ -2248,12 +1904,6 @@ int sg_d64_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<128>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<128>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               Conv1Cfg<1>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv1_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               Conv1Cfg<2>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1FCfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2329,25 +1979,10 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   switch (layer) {
     case 1:
       SG_REQUIRE(x != nullptr && ((uintptr_t)x & 15) == 0, "x must be a 16-byte aligned device pointer");
-      if (getenv("SG_CONV1_DIRECT")) {  // CUDA-core direct conv kept for A/B timing only
-        conv1_kernel<<<(unsigned)(batch * 8), 128, 0, st>>>(x, fq(P.w1), act1, W.sega);
-        SG_LAUNCH_CHECK();
-        return SG_OK;
-      }
-      if (!getenv("SG_CONV1_STAGED"))  // default: fp32 input converted inside the kernel
-        return (W.sega == 2) ? launch_conv1_fused<2>(x, wq(P.w1t), act1, batch, err, st)
-                             : launch_conv1_fused<1>(x, wq(P.w1t), act1, batch, err, st);
-      return (W.sega == 2) ? launch_conv1<2>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st)
-                           : launch_conv1<1>(x, reinterpret_cast<__nv_bfloat16*>(ws + W.act0), wq(P.w1t), act1, batch, err, st);
+      return (W.sega == 2) ? launch_conv1_fused<2>(x, wq(P.w1t), act1, batch, err, st)
+                           : launch_conv1_fused<1>(x, wq(P.w1t), act1, batch, err, st);
     case 2:
-      if (getenv("SG_CONV2_PLANE_REUSE"))
-        r = launch_conv_pair2<128>(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, 32, 64, 128, P.nseg, W.sega, 1,
-                                   slope, err, st);
-      else if (getenv("SG_CONV2_PIXEL_MAJOR"))  // 128x128 pixel-major tiles kept for A/B timing only
-        r = launch_conv<128>(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, 32, 64, 128, P.nseg, W.sega, 1,
-                             slope, err, st);
-      else
-        r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st);
+      r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st);
       break;
     case 3:
       if (!getenv("SG_CONV_TAP_STREAM"))  // default: plane reuse; per-tap streaming kernels kept for A/B timing

@@ -178,6 +178,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
+// Same for 32-byte-swizzled operands (K = 16 bf16 per row): SBO = 8 rows * 32 B, layout SWIZZLE_32B = 6.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) |
+         (6ull << 61);
+}
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
