@@ -116,6 +116,12 @@ int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, voi
 size_t sg_ae_bf16_workspace_bytes(int64_t max_batch);
 int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
                      float* recon_out, void* stream);
+/* The same tensor-core pipeline with the conv mode as an argument: SG_CONV_BF16 as above; SG_CONV_BF16X3 = fp32-parity
+ * arithmetic (activations and 7x7 weights as bf16 hi | lo, three GEMM segments, ~1e-5 relative on the errors).
+ * workspace from sg_ae_tc_workspace_bytes(max_batch, conv_mode). */
+size_t sg_ae_tc_workspace_bytes(int64_t max_batch, int conv_mode);
+int sg_ae_score_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
+                   float* err_out, float* recon_out, void* stream);
 int sg_ae_bf16_check(const void* workspace, void* stream);
 
 /* ---- MLP discriminator scoring (28x28 path) --------------------------------------------------

@@ -895,23 +895,25 @@ def _ae_params(autoencoder: nn.Module, device):
 def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: int = 2048, *,
               conv_mode: str = "fp32") -> torch.Tensor:
     """Per-sample reconstruction MSE of the reference AutoEncoder on the GPU; fp32 device tensor [N].
-    conv_mode 'fp32': every layer in fp32 on the CUDA cores (reference parity, 1e-3 relative);
-    'bf16' (BASELINE config 4): the two 7x7 layers on tcgen05 with bf16 operands, bf16 activations."""
+    conv_mode 'fp32' (default): fp32-parity arithmetic on the tensor cores (bf16 hi/lo split of activations and 7x7
+    weights, three GEMM segments; ~1e-5 relative); 'bf16' (BASELINE config 4): bf16 operands and activations;
+    'fp32_cuda': every layer in plain fp32 on the CUDA cores (the first implementation, kept as a cross-check)."""
     device = _dev(device)
     lib = _lib_for(device)
-    if conv_mode not in ("fp32", "bf16"):
-        raise ValueError("conv_mode must be 'fp32' or 'bf16'")
+    if conv_mode not in ("fp32", "bf16", "fp32_cuda"):
+        raise ValueError("conv_mode must be 'fp32', 'bf16' or 'fp32_cuda'")
     params = _ae_params(autoencoder, device)
     arr = (L.P * 12)(*[t.data_ptr() for t in params])
     n = images.shape[0]
     err = torch.empty(n, dtype=torch.float32, device=device)
     cb = min(chunk, max(n, 1))
-    if conv_mode == "bf16":
-        ws = _Scratch.get(device, "ae_bf16", lib.sg_ae_bf16_workspace_bytes(cb))
+    if conv_mode != "fp32_cuda":
+        mode = L.SG_CONV_BF16 if conv_mode == "bf16" else L.SG_CONV_BF16X3
+        ws = _Scratch.get(device, "ae_tc", lib.sg_ae_tc_workspace_bytes(cb, mode))
         for i in range(0, n, chunk):
             x = _f32c(images[i:i + chunk], device)
-            L.check(lib.sg_ae_score_bf16(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()),
-                    "sg_ae_score_bf16")
+            L.check(lib.sg_ae_score_tc(_p(x), x.shape[0], arr, _p(ws), mode, _p(err[i:i + chunk]), L.P(0), _stream()),
+                    "sg_ae_score_tc")
         L.check(lib.sg_ae_bf16_check(_p(ws), _stream()), "sg_ae_bf16_check")
         return err
     ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(cb))

@@ -30,26 +30,28 @@ namespace aetc {
 using namespace ptx;
 
 constexpr int kErrBase = 40;
-constexpr int kKs3 = 28, kKs4 = 49;                      // K-steps of 64 of the two 7x7 layers
-constexpr size_t kW3Bytes = (size_t)64 * kKs3 * 64 * 2;  // packed bf16 weights
-constexpr size_t kW4Bytes = (size_t)32 * kKs4 * 64 * 2;
+constexpr int kKs3 = 28, kKs4 = 49;                      // K-steps of 64 of the two 7x7 layers (bf16 mode)
+constexpr int kKs3Split = 98;                            // split mode: 49 taps x {[x_hi|x_lo].[w_hi|w_hi], [x_hi|x_lo].[w_lo|0]}
 constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100 * 64 * 2, kAct4 = 256 * 32 * 2,
-                 kAct5 = 32 * 32 * 16 * 2;              // bytes per sample
+                 kAct5 = 32 * 32 * 16 * 2;              // bytes per sample and segment
 
+// SEG = 1: bf16 conv mode.  SEG = 2: fp32-parity mode on the same kernels -- every activation is stored as bf16
+// hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
+// on load and split on store.
 struct Layout {
   size_t flag, w3, w4, a1, a2, a3, a4, a5, total;
 };
-static Layout layout(int64_t batch) {
+static Layout layout(int64_t batch, int seg) {
   Layout L;
   size_t o = 0;
   L.flag = o; o += 1024;
-  L.w3 = o; o += align_up(kW3Bytes, 1024);
-  L.w4 = o; o += align_up(kW4Bytes, 1024);
-  L.a1 = o; o += align_up(kAct1 * batch, 1024);
-  L.a2 = o; o += align_up(kAct2 * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
-  L.a3 = o; o += align_up(kAct3 * batch, 1024);
-  L.a4 = o; o += align_up(kAct4 * batch, 1024);
-  L.a5 = o; o += align_up(kAct5 * batch, 1024);
+  L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
+  L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
+  L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
+  L.a2 = o; o += align_up(kAct2 * seg * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
+  L.a3 = o; o += align_up(kAct3 * seg * batch, 1024);
+  L.a4 = o; o += align_up(kAct4 * seg * batch, 1024);
+  L.a5 = o; o += align_up(kAct5 * seg * batch, 1024);
   L.total = o;
   return L;
 }
@@ -57,18 +59,34 @@ static Layout layout(int64_t batch) {
 // w3 [64][32][7][7] (Conv2d: out, in, kh, kw)  -> bf16 [oc][ks = kh*4 + kwp][j = px*32 + c], kw = 2*kwp + px (kw == 7 -> 0)
 // w4 [64][32][7][7] (ConvTranspose2d: in, out, kh, kw) -> bf16 [oc][ks = kx*7 + ky][ic] (the 7 row taps of a column shift
 // are contiguous: one weight stage of ae_dec1_kernel)
+template <int SEG>
 __global__ void pack_k7_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
                                __nv_bfloat16* __restrict__ p4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 64 * kKs3 * 64) {
-    const int j = i & 63, ks = (i >> 6) % kKs3, oc = i / (64 * kKs3);
-    const int kh = ks >> 2, kw = 2 * (ks & 3) + (j >> 5), c = j & 31;
-    p3[i] = __float2bfloat16_rn(kw < 7 ? w3[((oc * 32 + c) * 7 + kh) * 7 + kw] : 0.f);
+  auto hi_of = [](float v) { return __float2bfloat16_rn(v); };
+  auto lo_of = [](float v) { return __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v))); };
+  if (SEG == 1) {
+    if (i < 64 * kKs3 * 64) {
+      const int j = i & 63, ks = (i >> 6) % kKs3, oc = i / (64 * kKs3);
+      const int kh = ks >> 2, kw = 2 * (ks & 3) + (j >> 5), c = j & 31;
+      p3[i] = hi_of(kw < 7 ? w3[((oc * 32 + c) * 7 + kh) * 7 + kw] : 0.f);
+    }
+  } else {
+    // [oc][ks = tap*2 + s][j]: the A row is [x_hi(32) | x_lo(32)] of one pixel; s = 0: [w_hi | w_hi], s = 1: [w_lo | 0]
+    if (i < 64 * kKs3Split * 64) {
+      const int j = i & 63, ks = (i >> 6) % kKs3Split, oc = i / (64 * kKs3Split);
+      const int tap = ks >> 1, sgm = ks & 1, c = j & 31;
+      const float v = w3[((oc * 32 + c) * 7 + tap / 7) * 7 + tap % 7];
+      p3[i] = sgm == 0 ? hi_of(v) : (j < 32 ? lo_of(v) : __float2bfloat16_rn(0.f));
+    }
   }
-  if (i < 32 * kKs4 * 64) {
-    const int ic = i & 63, ks = (i >> 6) % kKs4, oc = i / (64 * kKs4);
+  if (i < 32 * kKs4 * SEG * 64) {
+    // [oc][(wseg*49 + kx*7 + ky)][ic]: the 7 row taps of a column shift are contiguous (one weight stage of ae_dec1_kernel)
+    const int ic = i & 63, kk = (i >> 6) % (kKs4 * SEG), oc = i / (64 * kKs4 * SEG);
+    const int wseg = kk / kKs4, ks = kk % kKs4;
     const int kx = ks / 7, ky = ks % 7;
-    p4[i] = __float2bfloat16_rn(w4[((ic * 32 + oc) * 7 + ky) * 7 + kx]);
+    const float v = w4[((ic * 32 + oc) * 7 + ky) * 7 + kx];
+    p4[i] = wseg == 0 ? hi_of(v) : lo_of(v);
   }
 }
 
@@ -76,7 +94,7 @@ __global__ void pack_k7_kernel(const float* __restrict__ w3, const float* __rest
 // The two 7x7 layers on tcgen05 (structure of d64.cu's conv_umma_kernel: warp 0 TMA producer, warp 1 MMA issuer,
 // warps 2-5 epilogue, mbarrier ring, two ping-pong accumulators in TMEM).
 // ------------------------------------------------------------------------------------------
-template <int N, bool CONVT>
+template <int N, bool CONVT, bool SPLIT = false>
 struct K7Cfg {
   static constexpr int kABytes = 128 * 128;                        // 128 rows x 64 bf16 (SWIZZLE_128B)
   static constexpr int kALoad = CONVT ? kABytes : 100 * 128;       // bytes TMA actually writes (10 x 10 box for L3)
@@ -84,15 +102,16 @@ struct K7Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = 6;
   static constexpr int kTmemCols = 2 * N;
-  static constexpr int kKSteps = CONVT ? kKs4 : kKs3;
+  static constexpr int kKSteps = CONVT ? kKs4 : (SPLIT ? kKs3Split : kKs3);
   static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 };
 
-template <int N, bool CONVT>
+// SPLIT (fp32-parity mode, L3 only): the input pixel row is [x_hi(32) | x_lo(32)], one tap per two K-steps
+template <int N, bool CONVT, bool SPLIT>
 __global__ void __launch_bounds__(192, 1)
 ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
-  using Cfg = K7Cfg<N, CONVT>;
+  using Cfg = K7Cfg<N, CONVT, SPLIT>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -135,6 +154,7 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const uint32_t sa = base + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kALoad + Cfg::kBBytes);
           if (CONVT) tma_load_4d(sa, &tmap_a, full_bar(stage), 0, -(ks / 7), y0 - ks % 7, img);   // in(y - ky, x - kx), ks = kx*7 + ky
+          else if (SPLIT) tma_load_4d(sa, &tmap_a, full_bar(stage), 0, (ks >> 1) % 7, (ks >> 1) / 7, img);   // one tap, [hi|lo]
           else tma_load_4d(sa, &tmap_a, full_bar(stage), 0, 2 * (ks & 3), ks >> 2, img);            // in(y + kh, x + kw)
           tma_load_2d(sa + Cfg::kABytes, &tmap_b, full_bar(stage), ks * 64, 0);
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -177,7 +197,7 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const int img = CONVT ? (tile >> 1) : tile;
       const bool valid = img < n_img && (CONVT || row < 100);
       const size_t px = CONVT ? ((size_t)img * 256 + (tile & 1) * 128 + row) : ((size_t)img * 100 + row);
-      __nv_bfloat16* dst = out + px * N;
+      __nv_bfloat16* dst = out + px * N * (SPLIT ? 2 : 1);
       if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 4)) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * N);
@@ -186,7 +206,7 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         uint32_t v[32];
         tmem_ld_32x32(taddr + cb, v);
         tmem_ld_wait();
-        uint32_t pk[16];
+        uint32_t pk[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float a = __uint_as_float(v[2 * j]) + __ldg(bias + cb + 2 * j);
@@ -194,11 +214,21 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           if (CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }   // ReLU after the decoder's first layer only
           const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+          if (SPLIT) {
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            pl[j] = *reinterpret_cast<const uint32_t*>(&l);
+          }
         }
         if (valid) {
           uint4* d = reinterpret_cast<uint4*>(dst + cb);
 #pragma unroll
           for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          if (SPLIT) {
+            uint4* dl = reinterpret_cast<uint4*>(dst + N + cb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -233,9 +263,13 @@ struct Dec1Cfg {
   static constexpr int kSmemBytes = kCopies * kCopyBytes + kBStages * kBBytes + 256 + 1024;
 };
 
+// SEG == 2 (fp32-parity mode): per column shift three sub-steps -- x_hi copy with w_hi, the same copy with w_lo,
+// x_lo copy with w_hi; input channels [hi 64 | lo 64], output [hi 32 | lo 32].
+template <int SEG>
 __global__ void __launch_bounds__(192, 1)
 ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
+  constexpr int kSub = (SEG == 2) ? 3 : 1;
   using Cfg = Dec1Cfg;
   constexpr int UA = Cfg::kCopies, SB = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -284,15 +318,21 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       bool ok = true;
       for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
         for (int kx = 0; kx < 7 && ok; ++kx) {
-          if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 11)) { ok = false; break; }
-          mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kLoadBytes);
-          tma_load_4d(base + aslot * Cfg::kCopyBytes + 6 * 2048, &tmap_a, afull_bar(aslot), 0, -kx, 0, img);
-          if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
-          if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 12)) { ok = false; break; }
-          mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
-          for (int ky = 0; ky < 7; ++ky)
-            tma_load_2d(b_base + bstage * Cfg::kBBytes + ky * Cfg::kTapBytes, &tmap_b, bfull_bar(bstage), (kx * 7 + ky) * 64, 0);
-          if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+          for (int sub = 0; sub < kSub && ok; ++sub) {
+            if (sub != 1) {   // sub 1 reuses the x_hi copy of sub 0
+              if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 11)) { ok = false; break; }
+              mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kLoadBytes);
+              tma_load_4d(base + aslot * Cfg::kCopyBytes + 6 * 2048, &tmap_a, afull_bar(aslot), sub == 2 ? 64 : 0, -kx, 0, img);
+              if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+            }
+            const int wseg = (sub == 1) ? 1 : 0;
+            if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 12)) { ok = false; break; }
+            mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
+            for (int ky = 0; ky < 7; ++ky)
+              tma_load_2d(b_base + bstage * Cfg::kBBytes + ky * Cfg::kTapBytes, &tmap_b, bfull_bar(bstage),
+                          (wseg * kKs4 + kx * 7 + ky) * 64, 0);
+            if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+          }
         }
       }
     }
@@ -308,29 +348,36 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
         uint32_t first = 0;
         for (int kx = 0; kx < 7 && ok; ++kx) {
-          if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 14)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t ca = base + aslot * Cfg::kCopyBytes;
-          if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 15)) { ok = false; break; }
-          tc_fence_after();
+          uint32_t ca = 0;
+          for (int sub = 0; sub < kSub && ok; ++sub) {
+            if (sub != 1) {
+              if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 14)) { ok = false; break; }
+              tc_fence_after();
+              ca = base + aslot * Cfg::kCopyBytes;
+            }
+            if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 15)) { ok = false; break; }
+            tc_fence_after();
 #pragma unroll 1
-          for (int ky = 0; ky < 7; ++ky) {
-            const uint64_t bdesc = umma_desc_sw128(b_base + bstage * Cfg::kBBytes + ky * Cfg::kTapBytes);
-            // output rows y0..y0+7 read input rows y0 - ky .. = copy rows (y0 + 6 - ky) ..; one copy row = 2048 B
-            const uint64_t a0 = umma_desc_sw128(ca + (uint32_t)(6 - ky) * 2048u);
-            const uint64_t a1 = umma_desc_sw128(ca + (uint32_t)(14 - ky) * 2048u);
+            for (int ky = 0; ky < 7; ++ky) {
+              const uint64_t bdesc = umma_desc_sw128(b_base + bstage * Cfg::kBBytes + ky * Cfg::kTapBytes);
+              // output rows y0..y0+7 read input rows y0 - ky .. = copy rows (y0 + 6 - ky) ..; one copy row = 2048 B
+              const uint64_t a0 = umma_desc_sw128(ca + (uint32_t)(6 - ky) * 2048u);
+              const uint64_t a1 = umma_desc_sw128(ca + (uint32_t)(14 - ky) * 2048u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tmem_d, a0 + 2 * k, bdesc + 2 * k, idesc, first);
-              umma_f16(tmem_d + 32, a1 + 2 * k, bdesc + 2 * k, idesc, first);
-              first = 1u;
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(tmem_d, a0 + 2 * k, bdesc + 2 * k, idesc, first);
+                umma_f16(tmem_d + 32, a1 + 2 * k, bdesc + 2 * k, idesc, first);
+                first = 1u;
+              }
+            }
+            umma_commit(bempty_bar(bstage));
+            if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+            // the x_hi copy is released after its second use (sub 1), the x_lo copy (or the only copy) right away
+            if ((SEG == 1) || sub >= 1) {
+              umma_commit(aempty_bar(aslot));
+              if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
             }
           }
-          umma_commit(bempty_bar(bstage));
-          if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
-          if (!ok) break;
-          umma_commit(aempty_bar(aslot));
-          if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
         }
         if (!ok) break;
         umma_commit(tfull_bar(acc));
@@ -351,17 +398,26 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(taddr + t * 32, v);
         tmem_ld_wait();
-        uint32_t pk[16];
+        uint32_t pk[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float a = fmaxf(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j), 0.f);
           const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1), 0.f);
           const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+          if (SEG == 2) {
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            pl[j] = *reinterpret_cast<const uint32_t*>(&l);
+          }
         }
-        uint4* d = reinterpret_cast<uint4*>(out + ((size_t)img * 256 + t * 128 + row) * 32);
+        uint4* d = reinterpret_cast<uint4*>(out + ((size_t)img * 256 + t * 128 + row) * 32 * SEG);
 #pragma unroll
         for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        if (SEG == 2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[4 + q] = make_uint4(pl[4 * q], pl[4 * q + 1], pl[4 * q + 2], pl[4 * q + 3]);
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -391,8 +447,44 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// C channels of one pixel: SEG = 1 -> C bf16; SEG = 2 -> [hi C | lo C], value = hi + lo
+template <int SEG, int C>
+__device__ __forceinline__ void load_px(const __nv_bfloat16* p, float* v) {
+  const uint4* src = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int q = 0; q < C / 8; ++q) unpack8(__ldg(src + q), v + 8 * q);
+  if (SEG == 2) {
+    float l[C];
+#pragma unroll
+    for (int q = 0; q < C / 8; ++q) unpack8(__ldg(src + C / 8 + q), l + 8 * q);
+#pragma unroll
+    for (int i = 0; i < C; ++i) v[i] += l[i];
+  }
+}
+template <int SEG, int C, bool RELU>
+__device__ __forceinline__ void store_px(__nv_bfloat16* p, const float* a) {
+  uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int q = 0; q < C / 8; ++q) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = a[8 * q + 2 * j], x1 = a[8 * q + 2 * j + 1];
+      if (RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+      if (SEG == 2) {
+        const float2 hf = __bfloat1622float2(hh);
+        l[j] = pack2(x0 - hf.x, x1 - hf.y);
+      }
+    }
+    d[q] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (SEG == 2) d[C / 8 + q] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
 
 // L1: x fp32 [n][3][64][64] -> a1 bf16 [n][32][32][16], one output pixel per thread
+template <int SEG>
 __global__ void __launch_bounds__(256) enc1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ a1,
                                                    int64_t n_img) {
@@ -427,16 +519,12 @@ __global__ void __launch_bounds__(256) enc1_kernel(const float* __restrict__ x, 
           for (int o = 0; o < 16; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
         }
       }
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack2(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-    uint4* d = reinterpret_cast<uint4*>(a1 + p * 16);
-    d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    store_px<SEG, 16, true>(a1 + p * 16 * SEG, acc);
   }
 }
 
 // L2: a1 bf16 [n][32][32][16] -> a2 bf16 [n][16][16][32], one output pixel per thread
+template <int SEG>
 __global__ void __launch_bounds__(256) enc2_kernel(const __nv_bfloat16* __restrict__ a1, const float* __restrict__ w,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ a2,
                                                    int64_t n_img) {
@@ -455,7 +543,7 @@ __global__ void __launch_bounds__(256) enc2_kernel(const __nv_bfloat16* __restri
     float acc[32];
 #pragma unroll
     for (int o = 0; o < 32; ++o) acc[o] = s_b[o];
-    const __nv_bfloat16* in = a1 + n * (32 * 32 * 16);
+    const __nv_bfloat16* in = a1 + n * (32 * 32 * 16 * SEG);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy - 1 + ky;
@@ -464,10 +552,8 @@ __global__ void __launch_bounds__(256) enc2_kernel(const __nv_bfloat16* __restri
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = 2 * ox - 1 + kx;
         if (ix < 0 || ix >= 32) continue;
-        const uint4* src = reinterpret_cast<const uint4*>(in + (iy * 32 + ix) * 16);
         float v[16];
-        unpack8(__ldg(src), v);
-        unpack8(__ldg(src + 1), v + 8);
+        load_px<SEG, 16>(in + (iy * 32 + ix) * 16 * SEG, v);
         const float4* wr = reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * 512);
 #pragma unroll
         for (int ic = 0; ic < 16; ++ic)
@@ -481,13 +567,7 @@ __global__ void __launch_bounds__(256) enc2_kernel(const __nv_bfloat16* __restri
           }
       }
     }
-    uint4* d = reinterpret_cast<uint4*>(a2 + p * 32);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      d[q] = make_uint4(pack2(fmaxf(acc[8 * q], 0.f), fmaxf(acc[8 * q + 1], 0.f)),
-                        pack2(fmaxf(acc[8 * q + 2], 0.f), fmaxf(acc[8 * q + 3], 0.f)),
-                        pack2(fmaxf(acc[8 * q + 4], 0.f), fmaxf(acc[8 * q + 5], 0.f)),
-                        pack2(fmaxf(acc[8 * q + 6], 0.f), fmaxf(acc[8 * q + 7], 0.f)));
+    store_px<SEG, 32, true>(a2 + p * 32 * SEG, acc);
   }
 }
 
@@ -498,6 +578,7 @@ __global__ void __launch_bounds__(256) enc2_kernel(const __nv_bfloat16* __restri
 __device__ __forceinline__ int tap_k(int parity, int d) { return parity == 0 ? 1 : (d ? 0 : 2); }
 
 // L5: a4 bf16 [n][16][16][32] -> a5 bf16 [n][32][32][16] (+ReLU)
+template <int SEG>
 __global__ void __launch_bounds__(256) dec2_kernel(const __nv_bfloat16* __restrict__ a4, const float* __restrict__ w,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ a5,
                                                    int64_t n_img) {
@@ -513,7 +594,7 @@ __global__ void __launch_bounds__(256) dec2_kernel(const __nv_bfloat16* __restri
   for (int64_t p = blockIdx.x * 256ll + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
     const int64_t n = p >> 8;
     const int qy = (int)(p >> 4) & 15, qx = (int)p & 15;
-    const __nv_bfloat16* in = a4 + n * (16 * 16 * 32);
+    const __nv_bfloat16* in = a4 + n * (16 * 16 * 32 * SEG);
     float acc[4][16];
 #pragma unroll
     for (int o = 0; o < 4; ++o)
@@ -525,10 +606,8 @@ __global__ void __launch_bounds__(256) dec2_kernel(const __nv_bfloat16* __restri
       for (int dx = 0; dx < 2; ++dx) {
         const int iy = qy + dy, ix = qx + dx;
         if (iy >= 16 || ix >= 16) continue;
-        const uint4* src = reinterpret_cast<const uint4*>(in + (iy * 16 + ix) * 32);
         float v[32];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) unpack8(__ldg(src + q), v + 8 * q);
+        load_px<SEG, 32>(in + (iy * 16 + ix) * 32 * SEG, v);
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
           if (py == 0 && dy == 1) continue;
@@ -554,19 +633,14 @@ __global__ void __launch_bounds__(256) dec2_kernel(const __nv_bfloat16* __restri
     for (int py = 0; py < 2; ++py)
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
-        const float* a = acc[py * 2 + px];
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack2(fmaxf(a[2 * j], 0.f), fmaxf(a[2 * j + 1], 0.f));
-        uint4* d = reinterpret_cast<uint4*>(a5 + ((n * 32 + 2 * qy + py) * 32 + 2 * qx + px) * 16);
-        d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        store_px<SEG, 16, true>(a5 + ((n * 32 + 2 * qy + py) * 32 + 2 * qx + px) * 16 * SEG, acc[py * 2 + px]);
       }
   }
 }
 
 // L6: a5 bf16 [n][32][32][16] -> tanh(ConvT 16->3) fp32, squared error against x, per-sample mean.
 // One CTA per sample: 256 threads x 4 quads; fixed-order double reduction (reproducible).
+template <int SEG>
 __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __restrict__ a5, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* __restrict__ x,
                                                        float* __restrict__ recon, float* __restrict__ err) {
@@ -580,7 +654,7 @@ __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __re
   if (threadIdx.x < 3) s_b[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int64_t n = blockIdx.x;
-  const __nv_bfloat16* in = a5 + n * (32 * 32 * 16);
+  const __nv_bfloat16* in = a5 + n * (32 * 32 * 16 * SEG);
   const float* xin = x + n * 12288;
   double sq = 0.0;
   for (int qi = threadIdx.x; qi < 1024; qi += 256) {
@@ -596,10 +670,8 @@ __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __re
       for (int dx = 0; dx < 2; ++dx) {
         const int iy = qy + dy, ix = qx + dx;
         if (iy >= 32 || ix >= 32) continue;
-        const uint4* src = reinterpret_cast<const uint4*>(in + (iy * 32 + ix) * 16);
         float v[16];
-        unpack8(__ldg(src), v);
-        unpack8(__ldg(src + 1), v + 8);
+        load_px<SEG, 16>(in + (iy * 32 + ix) * 16 * SEG, v);
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
           if (py == 0 && dy == 1) continue;
@@ -638,16 +710,23 @@ __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __re
   if (threadIdx.x == 0) err[n] = (float)(s_red[0] / 12288.0);
 }
 
-template <int N, bool CONVT>
+template <int N, bool CONVT, bool SPLIT>
 static int launch_k7(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
                      int64_t batch, int* err, cudaStream_t st) {
-  using Cfg = K7Cfg<N, CONVT>;
+  using Cfg = K7Cfg<N, CONVT, SPLIT>;
   CUtensorMap ta, tb;
   if (CONVT) {
     // a3 [n][10][10][64]: box = 64 ch x 16 cols x 8 rows of one image, start (-kx, y0 - ky): outside -> zeros
     cuuint64_t dims[4] = {64, 10, 10, (cuuint64_t)batch};
     cuuint64_t strides[3] = {128, 1280, 12800};
     cuuint32_t box[4] = {64, 16, 8, 1};
+    int r = encode_tmap(&ta, 4, act_in, dims, strides, box);
+    if (r != SG_OK) return r;
+  } else if (SPLIT) {
+    // a2 [n][16][16][hi 32 | lo 32]: one pixel = one 128-byte operand row
+    cuuint64_t dims[4] = {64, 16, 16, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {128, 2048, 32768};
+    cuuint32_t box[4] = {64, 10, 10, 1};
     int r = encode_tmap(&ta, 4, act_in, dims, strides, box);
     if (r != SG_OK) return r;
   } else {
@@ -667,7 +746,52 @@ static int launch_k7(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, cons
   }
   const int64_t tiles = CONVT ? 2 * batch : batch;
   const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
-  ae_k7_kernel<N, CONVT><<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, (int)tiles, err);
+  ae_k7_kernel<N, CONVT, SPLIT><<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, (int)tiles, err);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+template <int SEG>
+static int score_impl(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
+                      float* recon_out, cudaStream_t st) {
+  const Layout L = layout(batch, SEG);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* err = reinterpret_cast<int*>(ws + L.flag);
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
+  SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));
+  pack_k7_kernel<SEG><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
+  SG_LAUNCH_CHECK();
+  const int64_t cap = (int64_t)state().sm_count * 8;
+  auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
+  enc1_kernel<SEG><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
+  SG_LAUNCH_CHECK();
+  enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
+  SG_LAUNCH_CHECK();
+  int r = launch_k7<64, false, SEG == 2>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
+  if (r != SG_OK) return r;
+  if (SEG == 1 && getenv("SG_AE_TAP_STREAM")) {   // per-tap streaming form kept for A/B timing (bf16 mode)
+    r = launch_k7<32, true, false>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
+    if (r != SG_OK) return r;
+  } else {
+    CUtensorMap ta, tb;
+    cuuint64_t adims[4] = {(cuuint64_t)64 * SEG, 10, 10, (cuuint64_t)batch};
+    cuuint64_t astr[3] = {(cuuint64_t)128 * SEG, (cuuint64_t)1280 * SEG, (cuuint64_t)12800 * SEG};
+    cuuint32_t abox[4] = {64, 16, 10, 1};   // the 10 input rows, 16 columns from -kx (columns outside the map: zero fill)
+    r = encode_tmap(&ta, 4, bf(L.a3), adims, astr, abox);
+    if (r != SG_OK) return r;
+    cuuint64_t bdims[2] = {(cuuint64_t)kKs4 * SEG * 64, 32};
+    cuuint64_t bstr[1] = {(cuuint64_t)kKs4 * SEG * 64 * 2};
+    cuuint32_t bbox[2] = {64, 32};
+    r = encode_tmap(&tb, 2, bf(L.w4), bdims, bstr, bbox);
+    if (r != SG_OK) return r;
+    const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
+    ae_dec1_kernel<SEG><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
+    SG_LAUNCH_CHECK();
+  }
+  dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
+  SG_LAUNCH_CHECK();
+  dec3_mse_kernel<SEG><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -679,66 +803,46 @@ extern "C" {
 
 int sg_ae_tc_init_attributes() {
   using namespace sg::aetc;
-  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               K7Cfg<64, false>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               K7Cfg<32, true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               K7Cfg<64, false, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               K7Cfg<64, false, true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               K7Cfg<32, true, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   return SG_OK;
 }
 
-size_t sg_ae_bf16_workspace_bytes(int64_t max_batch) { return sg::aetc::layout(max_batch < 1 ? 1 : max_batch).total; }
+size_t sg_ae_bf16_workspace_bytes(int64_t max_batch) { return sg::aetc::layout(max_batch < 1 ? 1 : max_batch, 1).total; }
+size_t sg_ae_tc_workspace_bytes(int64_t max_batch, int conv_mode) {
+  return sg::aetc::layout(max_batch < 1 ? 1 : max_batch, conv_mode == SG_CONV_BF16X3 ? 2 : 1).total;
+}
 
-int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
-                     float* recon_out, void* stream) {
-  using namespace sg::aetc;
+static int ae_tc_args(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out) {
   SG_READY();
   SG_REQUIRE(x && h_params && workspace && err_out, "null pointer");
   SG_REQUIRE(batch >= 0 && batch <= (1 << 20), "batch out of range");
   SG_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
   for (int i = 0; i < 12; ++i) SG_REQUIRE(h_params[i] != nullptr, "h_params must hold 12 device pointers (w, b) x 6");
-  if (batch == 0) return SG_OK;
-  cudaStream_t st = sg::as_stream(stream);
-  const Layout L = layout(batch);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  int* err = reinterpret_cast<int*>(ws + L.flag);
-  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
-  SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
-  SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * batch, 0, 1024, st));
-  pack_k7_kernel<<<(64 * kKs3 * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
-  SG_LAUNCH_CHECK();
-  const int64_t cap = (int64_t)sg::state().sm_count * 8;
-  auto blocks = [&](int64_t items) { int64_t b = sg::ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
-  enc1_kernel<<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
-  SG_LAUNCH_CHECK();
-  enc2_kernel<<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
-  SG_LAUNCH_CHECK();
-  int r = launch_k7<64, false>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
-  if (r != SG_OK) return r;
-  if (getenv("SG_AE_TAP_STREAM")) {   // per-tap streaming form kept for A/B timing
-    r = launch_k7<32, true>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
-    if (r != SG_OK) return r;
-  } else {
-    CUtensorMap ta, tb;
-    cuuint64_t adims[4] = {64, 10, 10, (cuuint64_t)batch};
-    cuuint64_t astr[3] = {128, 1280, 12800};
-    cuuint32_t abox[4] = {64, 16, 10, 1};   // the 10 input rows, 16 columns from -kx (columns outside the map: zero fill)
-    r = sg::encode_tmap(&ta, 4, bf(L.a3), adims, astr, abox);
-    if (r != SG_OK) return r;
-    cuuint64_t bdims[2] = {(cuuint64_t)kKs4 * 64, 32};
-    cuuint64_t bstr[1] = {(cuuint64_t)kKs4 * 64 * 2};
-    cuuint32_t bbox[2] = {64, 32};
-    r = sg::encode_tmap(&tb, 2, bf(L.w4), bdims, bstr, bbox);
-    if (r != SG_OK) return r;
-    const int grid = (int)(batch < sg::state().sm_count ? batch : sg::state().sm_count);
-    ae_dec1_kernel<<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
-    SG_LAUNCH_CHECK();
-  }
-  dec2_kernel<<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
-  SG_LAUNCH_CHECK();
-  dec3_mse_kernel<<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
-  SG_LAUNCH_CHECK();
   return SG_OK;
+}
+
+int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
+                     float* recon_out, void* stream) {
+  int r = ae_tc_args(x, batch, h_params, workspace, err_out);
+  if (r != SG_OK || batch == 0) return r;
+  return sg::aetc::score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
+}
+
+int sg_ae_score_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
+                   float* err_out, float* recon_out, void* stream) {
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
+  int r = ae_tc_args(x, batch, h_params, workspace, err_out);
+  if (r != SG_OK || batch == 0) return r;
+  if (conv_mode == SG_CONV_BF16X3)
+    return sg::aetc::score_impl<2>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
+  return sg::aetc::score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
 }
 
 int sg_ae_bf16_check(const void* workspace, void* stream) {

@@ -214,8 +214,15 @@ def main():
     big = sb.synth_images(0, 32768, O.SEED, dev)
     tb = gpu_time(lambda: sb.ae_errors(ae, big, dev, chunk=8192, conv_mode="bf16"), 5, 2)
     c["gpu_samples_per_s_32768_resident"] = 32768 / tb
-    t32 = gpu_time(lambda: sb.ae_errors(ae, imgs, dev), 3, 1)
-    c["gpu_samples_per_s_fp32_mode"] = 4096 / t32
+    t32 = gpu_time(lambda: sb.ae_errors(ae, big, dev, chunk=8192), 3, 1)
+    c["gpu_samples_per_s_fp32_parity_mode_tensor_cores"] = 32768 / t32
+    t32c = gpu_time(lambda: sb.ae_errors(ae, imgs, dev, conv_mode="fp32_cuda"), 3, 1)
+    c["gpu_samples_per_s_fp32_cuda_cores"] = 4096 / t32c
+    e_tc = sb.ae_errors(ae, imgs, dev).double()
+    e_cc = sb.ae_errors(ae, imgs, dev, conv_mode="fp32_cuda").double()
+    e_bf = sb.ae_errors(ae, imgs, dev, conv_mode="bf16").double()
+    c["max_rel_diff_fp32tc_vs_fp32cuda"] = float(((e_tc - e_cc).abs() / e_cc).max())
+    c["max_rel_diff_bf16_vs_fp32cuda"] = float(((e_bf - e_cc).abs() / e_cc).max())
     del big
     if not a.no_cpu:
         ic = imgs[:512].cpu()
