@@ -1320,50 +1320,58 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
   } else if (warp >= 6) {
     // ================= converters: fp32 patch -> bf16 K-major SW32 operand rows =================
-    const int ohl = warp - 6, ow = lane;
-    const int m = ohl * 32 + ow;
-    const uint32_t row_off = (uint32_t)m * 32u;
-    const uint32_t c0off = (uint32_t)(((m >> 2) & 1) << 4);   // SWIZZLE_32B: 16-B chunk ^= address bit 7
+    // thread = (output row ohl, pixel PAIR 2p / 2p+1, filter-row half): one 128-bit load per channel covers the
+    // input columns 4p .. 4p+3, the two outer columns come from the neighbouring pairs by shuffle -- 41 % fewer
+    // shared-memory / shuffle instructions than one pixel per thread (the kernel was MIO bound, profiles/r1d).
+    const int ohl = warp - 6, pr = lane & 15, khh = lane >> 4;
+    const int m0 = ohl * 32 + 2 * pr;                         // operand rows m0, m0 + 1 (same swizzle phase)
+    const uint32_t row_off = (uint32_t)m0 * 32u;
+    const uint32_t c0off = (uint32_t)(((m0 >> 2) & 1) << 4);   // SWIZZLE_32B: 16-B chunk ^= address bit 7
     int rs = 0, as = 0;
     uint32_t rphase = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       if (!mbar_wait(rfull_bar(rs), rphase, s_abort, err, kErrProducer + 30)) break;
       if (!mbar_wait(aempty_bar(as), aphase ^ 1u, s_abort, err, kErrProducer + 31)) break;
-      const uint32_t raw = r_base + rs * Cfg::kRawStride + (uint32_t)(ow * 8);
+      const uint32_t raw = r_base + rs * Cfg::kRawStride + (uint32_t)(pr * 16);
       const uint32_t dst = base + as * Cfg::kAStage + row_off;
 #pragma unroll
-      for (int kh = 0; kh < 4; ++kh) {
-        float px[4][3];   // [kw][c]
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int kh = 2 * khh + k2;
+        float px[2][4][3];   // [pixel][kw][c]
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float2 v = ld_shared_f2(raw + (uint32_t)(((c * 10 + 2 * ohl + kh) * 64) * 4));
-          float l = __shfl_up_sync(0xffffffffu, v.y, 1);
-          float r = __shfl_down_sync(0xffffffffu, v.x, 1);
-          if (ow == 0) l = 0.f;     // input column -1
-          if (ow == 31) r = 0.f;    // input column 64
-          px[0][c] = l; px[1][c] = v.x; px[2][c] = v.y; px[3][c] = r;
+          const float4 v = ld_shared_f4(raw + (uint32_t)(((c * 10 + 2 * ohl + kh) * 64) * 4));
+          float l = __shfl_up_sync(0xffffffffu, v.w, 1, 16);
+          float r = __shfl_down_sync(0xffffffffu, v.x, 1, 16);
+          if (pr == 0) l = 0.f;      // input column -1
+          if (pr == 15) r = 0.f;     // input column 64
+          px[0][0][c] = l;   px[0][1][c] = v.x; px[0][2][c] = v.y; px[0][3][c] = v.z;
+          px[1][0][c] = v.y; px[1][1][c] = v.z; px[1][2][c] = v.w; px[1][3][c] = r;
         }
-        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int kw = 0; kw < 4; ++kw) {
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(px[kw][0]), h1 = __float2bfloat16_rn(px[kw][1]),
-                              h2 = __float2bfloat16_rn(px[kw][2]);
-          hi[2 * kw] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          hi[2 * kw + 1] = (uint32_t)__bfloat16_as_ushort(h2);
-          if (SEGA == 2) {
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(px[kw][0] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(px[kw][1] - __bfloat162float(h1));
-            const __nv_bfloat16 l2 = __float2bfloat16_rn(px[kw][2] - __bfloat162float(h2));
-            lo[2 * kw] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            lo[2 * kw + 1] = (uint32_t)__bfloat16_as_ushort(l2);
+        for (int q = 0; q < 2; ++q) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int kw = 0; kw < 4; ++kw) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(px[q][kw][0]), h1 = __float2bfloat16_rn(px[q][kw][1]),
+                                h2 = __float2bfloat16_rn(px[q][kw][2]);
+            hi[2 * kw] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            hi[2 * kw + 1] = (uint32_t)__bfloat16_as_ushort(h2);
+            if (SEGA == 2) {
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(px[q][kw][0] - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(px[q][kw][1] - __bfloat162float(h1));
+              const __nv_bfloat16 l2 = __float2bfloat16_rn(px[q][kw][2] - __bfloat162float(h2));
+              lo[2 * kw] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              lo[2 * kw + 1] = (uint32_t)__bfloat16_as_ushort(l2);
+            }
           }
-        }
-        const uint32_t d = dst + (uint32_t)(kh * Cfg::kSliceA);
-        st_shared_v4(d + c0off, hi[0], hi[1], hi[2], hi[3]);
-        st_shared_v4(d + (c0off ^ 16u), hi[4], hi[5], hi[6], hi[7]);
-        if (SEGA == 2) {
-          st_shared_v4(d + 4 * Cfg::kSliceA + c0off, lo[0], lo[1], lo[2], lo[3]);
-          st_shared_v4(d + 4 * Cfg::kSliceA + (c0off ^ 16u), lo[4], lo[5], lo[6], lo[7]);
+          const uint32_t d = dst + (uint32_t)(kh * Cfg::kSliceA + q * 32);
+          st_shared_v4(d + c0off, hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(d + (c0off ^ 16u), hi[4], hi[5], hi[6], hi[7]);
+          if (SEGA == 2) {
+            st_shared_v4(d + 4 * Cfg::kSliceA + c0off, lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(d + 4 * Cfg::kSliceA + (c0off ^ 16u), lo[4], lo[5], lo[6], lo[7]);
+          }
         }
       }
       mbar_arrive(rempty_bar(rs));       // every LDS of this box has been consumed by the stores above

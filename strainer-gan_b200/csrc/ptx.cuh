@@ -122,6 +122,11 @@ __device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr) : "memory");
   return r;
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) {
   asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"(v) : "memory");
 }
