@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--shard", type=int, default=SHARD)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the DCGAN train iters/sec leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -298,6 +299,21 @@ def main():
         cpu = {"value": ns / dt, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64)"}
 
+    # ---- second headline metric of BASELINE.json: DCGAN 64x64 train iters/sec (rank 0, N = 1) ------------------------
+    # The G/D update is outside the straining path and stays torch autograd in every arm; the arms
+    # differ in the in-batch strain block only ("# 상위 10% 제거해서 fake image에 concate.py:243-273").
+    train = None
+    if rank == 0 and world == 1 and not args.no_train:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import config_bench
+        del images, losses
+        torch.cuda.empty_cache()
+        train = {"batch": 128, "unit": "iters/s",
+                 "plain_dcgan_no_strain": config_bench.train_iters(device, 40, "none"),
+                 "reference_eager_strain_block_on_gpu": config_bench.train_iters(device, 40, "torch"),
+                 "b200_strain_batch_concat_fake": config_bench.train_iters(device, 40, "b200"),
+                 "note": "G/D forward + backward + Adam = torch autograd in all arms; only the strain block differs"}
+
     if rank == 0:
         line = {"metric": "strained_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -310,7 +326,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "frac_of_conv_roofline": value / world / (pk["tf_sust"] * 1e12 / FLOP_ALL),
-                "kernels": kernels, "select_compact_ms": ms_sel,
+                "kernels": kernels, "select_compact_ms": ms_sel, "train_iters_per_sec": train,
                 "other_mode": {"conv_mode": other, "value": n_global / (ms2 * 1e-3), "ms_per_step": ms2}}
         print(json.dumps(line), flush=True)
     if group is not None:
