@@ -330,7 +330,7 @@ class D64Scorer:
         if b > self.max_batch:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
         self.repack(discriminator)
-        _, bns = _d64_modules(discriminator)
+        bns = self._mods[2]          # cached by repack()
         stats, back = [], []
         for bn in bns:
             if not bn.track_running_stats or bn.running_mean is None:
@@ -352,9 +352,9 @@ class D64Scorer:
         with torch.no_grad():
             for t, d in back:
                 t.copy_(d)
-            for bn in bns:
-                if bn.track_running_stats and bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked += 1
+            nbt = [bn.num_batches_tracked for bn in bns if bn.track_running_stats and bn.num_batches_tracked is not None]
+            if nbt:
+                torch._foreach_add_(nbt, 1)      # one launch for the three counters
         self._sig = None  # running stats changed under the packed eval-mode fold
 
     def run_layer(self, x, layer: int, logit=None, prob=None, loss=None):
