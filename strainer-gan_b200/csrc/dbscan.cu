@@ -46,6 +46,19 @@ __global__ void __launch_bounds__(256) standardize_split_kernel(const float* __r
   if (lane == 0) norms[row] = row < n ? (float)acc : __int_as_float(0x7f800000);
 }
 
+// |z_i - z_j|^2 from the stored hi/lo halves (z = hi + lo to 2^-17), accumulated in double: the tie breaker for pairs
+// whose GEMM distance lies within the error bound of the threshold (exact duplicates at tiny eps, borderline pairs)
+__device__ __noinline__ float exact_d2(const __nv_bfloat16* __restrict__ zs, int64_t i, int64_t j, int d) {
+  const __nv_bfloat16* a = zs + i * 2 * d;
+  const __nv_bfloat16* b = zs + j * 2 * d;
+  double acc = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const float x = (__bfloat162float(a[k]) + __bfloat162float(a[d + k])) - (__bfloat162float(b[k]) + __bfloat162float(b[d + k]));
+    acc += (double)x * (double)x;
+  }
+  return (float)acc;
+}
+
 struct Cfg {
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = 256 * 64 * 2;
@@ -59,7 +72,8 @@ struct Cfg {
 // PASS 0: counts[i] += neighbours in this column tile; PASS 1: reach[i] |= a core neighbour in this column tile.
 template <int PASS>
 __global__ void __launch_bounds__(192, 1)
-pairdist_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms, int d, float eps2,
+pairdist_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ zs,
+                const float* __restrict__ norms, int d, float eps2,
                 const uint8_t* __restrict__ core, unsigned int* __restrict__ counts, uint8_t* __restrict__ reach,
                 int m_tiles, int n_tiles, int* err) {
   constexpr int S = Cfg::kStages;
@@ -168,7 +182,12 @@ pairdist_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float d2 = (ni + nj[cb + j]) - 2.f * __uint_as_float(v[j]);
+          const float sn = ni + nj[cb + j];
+          float d2 = sn - 2.f * __uint_as_float(v[j]);
+          // split-product error bound ~2^-15 |z_i||z_j| <= 2^-16 (|z_i|^2 + |z_j|^2) (+ fp32 rounding of the norms):
+          // inside it, decide exactly (+inf norms mark padding / non-core columns: never rechecked)
+          if (fabsf(d2 - eps2) <= 3.2e-5f * sn && sn < __int_as_float(0x7f800000))
+            d2 = exact_d2(zs, i, (int64_t)nt * 256 + cb + j, d);
           cnt += (d2 <= eps2);
         }
       }
@@ -283,12 +302,12 @@ int sg_dbscan_nd(const float* x, int64_t n, int d, const float* mean, const floa
   const int64_t total = (int64_t)m_tiles * n_tiles;
   const int grid = (int)(total < sg::state().sm_count ? total : sg::state().sm_count);
   const float eps2 = (float)(eps * eps);
-  pairdist_kernel<0><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, norms, d, eps2, nullptr, counts, nullptr, m_tiles,
+  pairdist_kernel<0><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, zs, norms, d, eps2, nullptr, counts, nullptr, m_tiles,
                                                                  n_tiles, err);
   SG_LAUNCH_CHECK();
   core_kernel<<<(unsigned)sg::ceil_div(L.n_pad, 256), 256, 0, st>>>(counts, L.n_pad, n, min_samples, core);
   SG_LAUNCH_CHECK();
-  pairdist_kernel<1><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, norms, d, eps2, core, nullptr, reach, m_tiles,
+  pairdist_kernel<1><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, zs, norms, d, eps2, core, nullptr, reach, m_tiles,
                                                                  n_tiles, err);
   SG_LAUNCH_CHECK();
   tally_kernel<<<sg::state().sm_count, 256, 0, st>>>(core, reach, n, tally);

@@ -200,3 +200,18 @@ def test_dbscan_nd_clean_ratio_vs_sklearn(sb):
     ds = torch.utils.data.TensorDataset(torch.from_numpy(f), torch.zeros(n))
     r_dev = sb.estimate_ratio_dbscan(ds, eps=eps, min_samples=3, feature_extractor=torch.nn.Identity())
     assert r_dev == O.estimate_ratio_dbscan_features(f, eps, 3)
+
+
+def test_dbscan_nd_edges(sb):
+    """degenerate neighbourhoods and tiny inputs of the tensor-core DBSCAN"""
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal((37, 64)).astype(np.float32)
+    assert sb.dbscan_clean_ratio(torch.from_numpy(f), 1e-3, 3, return_counts=True) == (0.0, 0, 0)          # everyone alone
+    assert sb.dbscan_clean_ratio(torch.from_numpy(f), 1e3, 3, return_counts=True) == (1.0, 37, 37)        # one big cluster
+    assert sb.dbscan_clean_ratio(torch.from_numpy(f), 1e-3, 1, return_counts=True) == (1.0, 37, 37)       # min_samples 1: self
+    g = np.repeat(rng.standard_normal((5, 128)).astype(np.float32), 3, axis=0)                              # 5 exact triplets
+    g = np.concatenate([g, rng.standard_normal((4, 128)).astype(np.float32) * 5])
+    ratio, core, clean = sb.dbscan_clean_ratio(torch.from_numpy(g), 1e-2, 3, return_counts=True)
+    assert (core, clean) == (15, 15) and ratio == 15 / 19
+    with pytest.raises(RuntimeError):
+        sb.dbscan_clean_ratio(torch.from_numpy(rng.standard_normal((10, 100)).astype(np.float32)), 1.0, 3)   # d % 64 != 0

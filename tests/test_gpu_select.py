@@ -269,3 +269,23 @@ def test_gmm_em_device(sb):
     thr = sb.get_gmm_threshold(v, fit="device")
     wc, wn = O.divide_by_threshold(v, thr)
     assert np.array_equal(np.asarray(clean.indices), wc) and np.array_equal(np.asarray(noisy.indices), wn)
+
+
+def test_strain_rows_edges(sb):
+    """fused in-batch selection (sg_strain_rows): smallest / largest batch, ties at the threshold, NaN score"""
+    rng = np.random.default_rng(9)
+    for n in (1, 2, 3, 64, 777, 2048):
+        rows = torch.from_numpy(rng.standard_normal((n, 3, 4, 4)).astype(np.float32)).cuda()
+        s = rng.standard_normal(n).astype(np.float32)
+        if n >= 64:
+            s[: n // 3] = np.float32(0.25)                     # ties
+        for q in (0.1, 0.5, 0.0, 1.0):
+            kept, dropped, mask, thr = sb.strain_scores(rows, torch.from_numpy(s).cuda(), q)
+            wk, wd, wm, wt = O.strain_scores(rows.cpu(), torch.from_numpy(s), q)
+            assert float(thr) == float(wt) and torch.equal(mask.cpu(), wm), (n, q)
+            assert torch.equal(kept.cpu(), wk) and torch.equal(dropped.cpu(), wd)
+    s = rng.standard_normal(100).astype(np.float32)
+    s[7] = np.nan
+    rows = torch.zeros(100, 4, device="cuda")
+    kept, dropped, mask, thr = sb.strain_scores(rows, torch.from_numpy(s).cuda(), 0.1)
+    assert np.isnan(float(thr)) and kept.shape[0] == 0 and dropped.shape[0] == 100      # s >= nan is False everywhere
