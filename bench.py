@@ -88,7 +88,7 @@ def run_reference(args, rank, world):
     from oracle import strainer_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 1024
+    sample = 4096
     x = torch.from_numpy(O.synth_images(0, sample))
     netD = O.make_discriminator(O.SEED)
     for _ in range(max(args.warmup, 1)):
@@ -290,14 +290,18 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        ns = 2048
+        ns = 16384
         xs = torch.from_numpy(O.synth_images(0, ns))
         O.refine_dataset_by_loss(xs[:256], netD, LOSS_RATIO)
-        t0 = time.perf_counter()
-        O.refine_dataset_by_loss(xs, netD, LOSS_RATIO)
-        dt = time.perf_counter() - t0
-        cpu = {"value": ns / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64)"}
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            O.refine_dataset_by_loss(xs, netD, LOSS_RATIO)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        cpu = {"value": ns / best, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64), "
+                         f"best of 3 passes ({3 * best:.1f} s of CPU work)"}
 
     # ---- second headline metric of BASELINE.json: DCGAN 64x64 train iters/sec (rank 0, N = 1) ------------------------
     # The G/D update is outside the straining path and stays torch autograd in every arm; the arms
