@@ -303,6 +303,30 @@ def main():
                "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64), "
                          f"best of 3 passes ({3 * best:.1f} s of CPU work)"}
 
+    # ---- "existing Blackwell kernels" bar: the reference's own torch ops on this GPU (eager, cuDNN) ----------
+    eager = None
+    if rank == 0 and world == 1 and not args.no_train:
+        import copy
+        netDg = copy.deepcopy(netD).to(device).eval()
+
+        def eager_scores(bs, nsamp):
+            with torch.no_grad():
+                out = []
+                for i in range(0, nsamp, bs):
+                    p_ = netDg(images[i:i + bs]).view(-1)
+                    out.append(torch.nn.functional.binary_cross_entropy(p_, torch.ones_like(p_), reduction="none"))
+                return torch.cat(out)
+        eager = {"unit": "samples/s", "note": "torch eager D forward + BCE on cuda (scoring only, no select/compact), fp32 weights, "
+                                              "torch defaults (cuDNN, TF32 convs allowed)"}
+        for bs, nsamp in ((64, 8192), (4096, 32768)):
+            eager_scores(bs, min(nsamp, 4 * bs))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eager_scores(bs, nsamp)
+            torch.cuda.synchronize()
+            eager[f"batch_{bs}"] = nsamp / (time.perf_counter() - t0)
+        del netDg
+
     # ---- second headline metric of BASELINE.json: DCGAN 64x64 train iters/sec (rank 0, N = 1) ------------------------
     # The G/D update is outside the straining path and stays torch autograd in every arm; the arms
     # differ in the in-batch strain block only ("# 상위 10% 제거해서 fake image에 concate.py:243-273").
@@ -330,7 +354,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "frac_of_conv_roofline": value / world / (pk["tf_sust"] * 1e12 / FLOP_ALL),
-                "kernels": kernels, "select_compact_ms": ms_sel, "train_iters_per_sec": train,
+                "kernels": kernels, "select_compact_ms": ms_sel, "train_iters_per_sec": train, "torch_eager_gpu": eager,
                 "other_mode": {"conv_mode": other, "value": n_global / (ms2 * 1e-3), "ms_per_step": ms2}}
         print(json.dumps(line), flush=True)
     if group is not None:
