@@ -651,31 +651,54 @@ def _gmm_intersection(means, stds):
     return (-b + np.sqrt(b ** 2 - 4 * a * c)) / (2 * a)
 
 
+class _GmmOps:
+    """The three phases of the device EM on one GPU (tests substitute a numpy double to exercise the multi-rank
+    protocol on CPU/gloo).  ``sums`` is the 8-double tensor that is all-reduced between accumulate and update."""
+
+    def __init__(self, device):
+        self.device = device
+        self.lib = _lib_for(device)
+        self.ws = torch.empty(self.lib.sg_gmm1d_workspace_bytes(), dtype=torch.uint8, device=device)
+        self.sums = self.ws[16 * 8:24 * 8].view(torch.float64)
+
+    def prepare(self, losses):
+        return _f32c(losses, self.device).reshape(-1)
+
+    def begin(self, centers, kmeans_iters):
+        L.check(self.lib.sg_gmm1d_begin(_p(centers), kmeans_iters, _p(self.ws), _stream()), "sg_gmm1d_begin")
+
+    def accumulate(self, v):
+        L.check(self.lib.sg_gmm1d_accumulate(_p(v), v.numel(), _p(self.ws), _stream()), "sg_gmm1d_accumulate")
+
+    def update(self, n_total, reg_covar, tol, max_iter):
+        L.check(self.lib.sg_gmm1d_update(n_total, float(reg_covar), float(tol), int(max_iter), _p(self.ws), _stream()),
+                "sg_gmm1d_update")
+
+    def state(self):
+        return self.ws[:16 * 8].view(torch.float64).cpu().numpy()
+
+
 def gmm_fit_device(losses, max_iter: int = 10, tol: float = 1e-2, reg_covar: float = 5e-4, *, group=None,
-                   n_global=None, kmeans_iters: int = 30):
+                   n_global=None, kmeans_iters: int = 30, ops=None, select_ops=None):
     """2-component 1-D Gaussian-mixture EM on the GPU: sklearn's EM equations
     (``GaussianMixture(n_components=2, max_iter, tol, reg_covar)``) with a DETERMINISTIC initialisation -- Lloyd
     iterations from the 25 % / 75 % order statistics instead of a k-means run seeded by the global numpy RNG.
     With ``group`` the losses are this rank's shard: 8 partial sums are all-reduced per iteration, every rank
     obtains the identical fit.  Returns dict(weights, means, stds, n_iter, converged) (float64 numpy)."""
-    device = _dev()
-    lib = _lib_for(device)
-    v = _f32c(losses, device).reshape(-1)
+    ops = ops or _GmmOps(_dev())
+    v = ops.prepare(losses)
     n = v.numel()
     n_tot = int(n_global) if n_global is not None else n
-    c0 = order_stats(v, (n_tot - 1) // 4, group)[0:1]
-    c1 = order_stats(v, (3 * (n_tot - 1)) // 4, group)[0:1]
-    centers = torch.cat([c0, c1])
-    ws = torch.empty(lib.sg_gmm1d_workspace_bytes(), dtype=torch.uint8, device=device)
-    L.check(lib.sg_gmm1d_begin(_p(centers), kmeans_iters, _p(ws), _stream()), "sg_gmm1d_begin")
-    sums = ws[16 * 8:24 * 8].view(torch.float64)
+    c0 = order_stats(v, (n_tot - 1) // 4, group, select_ops)[0:1]
+    c1 = order_stats(v, (3 * (n_tot - 1)) // 4, group, select_ops)[0:1]
+    ops.begin(torch.cat([c0, c1]), kmeans_iters)
     for _ in range(kmeans_iters + max_iter):
-        L.check(lib.sg_gmm1d_accumulate(_p(v), n, _p(ws), _stream()), "sg_gmm1d_accumulate")
+        ops.accumulate(v)
         if group is not None:
             import torch.distributed as dist
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        L.check(lib.sg_gmm1d_update(n_tot, float(reg_covar), float(tol), int(max_iter), _p(ws), _stream()), "sg_gmm1d_update")
-    st = ws[:16 * 8].view(torch.float64).cpu().numpy()
+            dist.all_reduce(ops.sums, op=dist.ReduceOp.SUM, group=group)
+        ops.update(n_tot, reg_covar, tol, max_iter)
+    st = ops.state()
     return {"weights": st[0:2].copy(), "means": st[2:4].copy(), "stds": np.sqrt(st[4:6]), "n_iter": int(st[7]),
             "converged": bool(st[8]), "lower_bound": float(st[6])}
 

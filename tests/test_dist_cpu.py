@@ -99,6 +99,80 @@ class FakeSelectOps:
         return torch.tensor([O.np_lerp(a, b, np.float32(gamma))], dtype=torch.float32)
 
 
+class FakeGmmOps:
+    """numpy restatement of csrc/gmm.cu (accumulate / update kernels) on one rank's shard: per-rank partial sums
+    in ``sums`` (all-reduced by api.gmm_fit_device), parameters in a 16-double state."""
+    W, MU, VAR, LB, ITER, CONV, PHASE, KLEFT = 0, 2, 4, 6, 7, 8, 9, 10
+
+    def __init__(self):
+        self.st = np.zeros(16)
+        self.sums = torch.zeros(8, dtype=torch.float64)
+
+    def prepare(self, losses):
+        return torch.as_tensor(np.asarray(losses, np.float32)).reshape(-1)
+
+    def begin(self, centers, kmeans_iters):
+        self.st[:] = 0
+        self.st[self.MU:self.MU + 2] = centers.numpy().astype(np.float64)
+        self.st[self.KLEFT] = kmeans_iters
+
+    def accumulate(self, v):
+        st, x = self.st, v.numpy().astype(np.float64)
+        out = np.zeros(8)
+        if st[self.PHASE] == 0:
+            c1 = np.abs(x - st[self.MU + 1]) < np.abs(x - st[self.MU])
+            out[0:3] = [(~c1).sum(), x[~c1].sum(), (x[~c1] ** 2).sum()]
+            out[3:6] = [c1.sum(), x[c1].sum(), (x[c1] ** 2).sum()]
+        elif st[self.PHASE] == 1:
+            w, mu, var = st[0:2], st[2:4], st[4:6]
+            lp = np.log(w) - 0.5 * (np.log(2 * np.pi) + np.log(var)) - (x[:, None] - mu) ** 2 * (0.5 / var)
+            mx = lp.max(1)
+            lse = mx + np.log(np.exp(lp - mx[:, None]).sum(1))
+            r = np.exp(lp - lse[:, None])
+            out[0:3] = [r[:, 0].sum(), (r[:, 0] * x).sum(), (r[:, 0] * x * x).sum()]
+            out[3:6] = [r[:, 1].sum(), (r[:, 1] * x).sum(), (r[:, 1] * x * x).sum()]
+            out[6] = lse.sum()
+        else:
+            return                                    # converged: the device kernel returns without touching sums
+        self.sums[:] = torch.from_numpy(out)
+
+    def update(self, n_total, reg_covar, tol, max_iter):
+        st, s = self.st, self.sums.numpy()
+        eps10 = 10 * np.finfo(np.float64).eps
+        if st[self.PHASE] == 2:
+            return
+
+        def params():
+            nk0, nk1 = s[0] + eps10, s[3] + eps10
+            mu0, mu1 = s[1] / nk0, s[4] / nk1
+            st[self.MU:self.MU + 2] = [mu0, mu1]
+            st[self.VAR:self.VAR + 2] = [max(s[2] / nk0 - mu0 * mu0, 0) + reg_covar, max(s[5] / nk1 - mu1 * mu1, 0) + reg_covar]
+            st[self.W:self.W + 2] = [nk0 / n_total, nk1 / n_total]
+        if st[self.PHASE] == 0:
+            m0 = s[1] / s[0] if s[0] > 0 else st[self.MU]
+            m1 = s[4] / s[3] if s[3] > 0 else st[self.MU + 1]
+            moved = (m0 != st[self.MU]) or (m1 != st[self.MU + 1])
+            st[self.KLEFT] -= 1
+            if moved and st[self.KLEFT] > 0:
+                st[self.MU:self.MU + 2] = [m0, m1]
+                return
+            params()
+            st[self.LB], st[self.ITER], st[self.PHASE] = -np.inf, 0, 1
+            return
+        lb = s[6] / n_total
+        params()
+        change = lb - st[self.LB]
+        st[self.LB] = lb
+        st[self.ITER] += 1
+        if abs(change) < tol:
+            st[self.CONV], st[self.PHASE] = 1, 2
+        elif st[self.ITER] >= max_iter:
+            st[self.PHASE] = 2
+
+    def state(self):
+        return self.st.copy()
+
+
 def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -130,6 +204,15 @@ def _worker(rank, world, port, tmp):
     if rank == 1:
         vn[5] = float("nan")                       # a NaN on ONE rank poisons the global threshold on ALL ranks
     ok &= bool(np.isnan(sb.percentile_device(vn, 90.0, dist.group.WORLD, n, FakeSelectOps()).numpy()[0]))
+    # sharded GMM EM: global order statistics for the start + an 8-double all-reduce per iteration; every rank must
+    # end with the fit of the whole vector (float64 restatement in the oracle)
+    vg = O.synth_losses(n, seed=78)
+    g = sb.gmm_fit_device(vg[bounds[rank]:bounds[rank + 1]].copy(), group=dist.group.WORLD, n_global=n, ops=FakeGmmOps(),
+                          select_ops=FakeSelectOps())
+    want = O.gmm_fit_deterministic(vg)
+    ok &= g["n_iter"] == want["n_iter"] and g["converged"] == want["converged"]
+    for key in ("weights", "means", "stds"):
+        ok &= bool(np.allclose(g[key], want[key], rtol=1e-10, atol=1e-13))
     open(os.path.join(tmp, f"ok{rank}"), "w").write(str(ok))
     dist.destroy_process_group()
 
