@@ -141,7 +141,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) radix_phases_kernel(const flo
   const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
   const int64_t beg = min((int64_t)blockIdx.x * per, n), end = min(beg + per, n);
   const int ncache = (int)min((int64_t)kCacheKeys, end - beg);
-  for (int i = t; i < ncache; i += kTailThreads) s_keys[i] = float_to_key(__ldg(v + beg + i));
+  if ((reinterpret_cast<uintptr_t>(v + beg) & 15) == 0) {   // beg is a multiple of 4: aligned whenever v is
+    const float4* v4 = reinterpret_cast<const float4*>(v + beg);
+    for (int i = t; i < (ncache >> 2); i += kTailThreads) {
+      const float4 q = ldg_stream4(v4 + i);
+      s_keys[4 * i] = float_to_key(q.x); s_keys[4 * i + 1] = float_to_key(q.y);
+      s_keys[4 * i + 2] = float_to_key(q.z); s_keys[4 * i + 3] = float_to_key(q.w);
+    }
+    for (int i = (ncache & ~3) + t; i < ncache; i += kTailThreads) s_keys[i] = float_to_key(__ldg(v + beg + i));
+  } else {
+    for (int i = t; i < ncache; i += kTailThreads) s_keys[i] = float_to_key(__ldg(v + beg + i));
+  }
   const float* rest = v + beg + ncache;          // streamed again in every pass (only when the slice exceeds the cache)
   const int64_t nrest = end - beg - ncache;
   unsigned long long krem = *reinterpret_cast<const unsigned long long*>(ws + W_KREM_LO);
@@ -233,7 +243,7 @@ __device__ __forceinline__ void finish_body(const uint32_t* ws, float* out2);
 // SURVEY §8(d) counts ONE 4-byte read per element for the global select.  A radix select needs the bucket of
 // pass p before it can run pass p+1, i.e. four full reads.  Instead: (1) one CTA draws kSampleCount samples
 // at pseudo-random offsets of equal strides and radix-selects two pivots lo <= x_(k) <= x_(k+1) <= hi from them
-// (ranks k*S/n -+ 5 sigma of the binomial spread), (2) ONE streaming pass counts the elements below lo and
+// (ranks k*S/n -+ 4.5 sigma of the binomial spread), (2) ONE streaming pass counts the elements below lo and
 // appends the elements of [lo, hi] (~3 % of n) to a candidate buffer (warp-private shared staging, one global
 // atomic per 128 candidates), (3) the last CTA verifies that both order statistics lie inside the candidates
 // and switches the four radix passes to that (L2-resident) buffer with the reduced rank.  If the check fails
@@ -254,6 +264,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_pivot_kernel(const floa
   __shared__ uint32_t s_prefix[2], s_krem[2];
   __shared__ int s_last;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the filter pass may become resident now (it waits)
   // every CTA draws kSampleThreads samples (one DRAM sector each: spread over many SMs, a single SM cannot keep
   // 32768 sector misses in flight); the last CTA to finish selects the pivots
   const int64_t stride = n / kSampleCount;        // >= 64 (callers use this path for n >= 2^21 only)
@@ -345,6 +356,9 @@ __global__ void __launch_bounds__(kFilterThreads, 4) filter_kernel(const float* 
   __shared__ uint32_t s_nan;
   __shared__ int s_lastf;
   const int lane = threadIdx.x & 31;
+  // launched with programmatic stream serialisation: the CTAs are resident while the pivot kernel still runs and
+  // wait here for its completion (its writes to ws are then visible)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const float lo = __uint_as_float(ws[W_LO_F]), hi = __uint_as_float(ws[W_HI_F]);
   if (threadIdx.x == 0) { s_below = 0ull; s_nan = 0u; }
   __syncthreads();
@@ -651,15 +665,26 @@ int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t 
   // pivot ranks inside the sample: the ranks of x_(k), x_(k+1) scaled to the sample -+ 5.5 sigma (+ slack)
   const double S = kSampleCount, p = (double)k / (double)n;
   const double sigma = sqrt(S * p * (1.0 - p));
-  const int delta = (int)ceil(5.0 * sigma) + 24;
+  const int delta = (int)ceil(4.5 * sigma) + 16;
   const int r_lo = (int)floor(p * S) - delta;
   const int r_hi = (int)ceil((double)(k + 1) / (double)n * S) + delta;
   sample_pivot_kernel<<<kSampleCount / kSampleThreads, kSampleThreads, kSampleSmem, st>>>(
       v, n, ws, skeys, ws + W_TICKET_SAMPLE, (unsigned long long)k, r_lo, r_hi);
   SG_LAUNCH_CHECK();
-  const int grid = sg::state().sm_count * 4;
-  filter_kernel<<<grid, kFilterThreads, 0, st>>>(v, n, cand, cap, ws, (unsigned long long)k);
-  SG_LAUNCH_CHECK();
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sg::state().sm_count * 4));
+    cfg.blockDim = dim3(kFilterThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const unsigned long long ku = (unsigned long long)k;
+    SG_CUDA(cudaLaunchKernelEx(&cfg, filter_kernel, v, n, cand, cap, ws, ku));
+  }
   return radix_phases(v, n, cand, n / 32, ws, out2, st);
 }
 
