@@ -83,62 +83,65 @@ static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Weight packing
-// ------------------------------------------------------------------------------------------
-// w [Cout][Cin][4][4] fp32 -> bf16 [Cout][((tap*nchunk + chunk)*nseg + seg)*64 + j], c = chunk*64 + j.
+// Weight packing.  w [Cout][Cin][4][4] fp32 -> bf16 [Cout][((tap*nchunk + chunk)*nseg + seg)*64 + j], c = chunk*64 + j;
 // seg 0: hi (pairs with A hi), seg 1: hi (pairs with A lo), seg 2: lo (pairs with A hi).
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
-                                        int cin, int nseg) {
+// w1 [64][3][4][4] -> fp32 [k = c*16 + kh*4 + kw][64] and bf16 [co][hi|lo][kh*16 + kw*4 + c];
+// w5 [1][512][4][4] -> fp32 [p = kh*4+kw][512];  eval-mode BatchNorm2d folded to y = x * scale + shift.
+// ------------------------------------------------------------------------------------------
+// All of sg_d64_pack in ONE launch (a training loop repacks after every optimiser step: 7 launches -> 1).
+// blockIdx ranges: [0, 1024) conv weights (grid-stride over w2 | w3 | w4), [1024, 1056) small tensors, 1056..1058 BN folds.
+struct PackAllArgs {
+  const float *w1, *w2, *w3, *w4, *w5;
+  const float *g[3], *b[3], *m[3], *v[3];
+  __nv_bfloat16 *p2, *p3, *p4, *o1t;
+  float *o1, *o5, *ss[3], *gb[3], *ident;
+  float eps;
+  int nseg;
+};
+__device__ __forceinline__ void pack_conv_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int nseg,
+                                               int64_t i) {
   const int nchunk = cin >> 6;
   const int64_t kprime = (int64_t)16 * nchunk * nseg * 64;
-  const int64_t total = (int64_t)cout * kprime;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i / kprime);
-    int64_t r = i - (int64_t)co * kprime;
-    const int j = (int)(r & 63); r >>= 6;
-    const int seg = (int)(r % nseg); r /= nseg;
-    const int chunk = (int)(r % nchunk);
-    const int tap = (int)(r / nchunk);
-    const int c = chunk * 64 + j;
-    const float v = w[((int64_t)co * cin + c) * 16 + tap];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    out[i] = (seg == 2) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
-  }
+  const int co = (int)(i / kprime);
+  int64_t r = i - (int64_t)co * kprime;
+  const int j = (int)(r & 63); r >>= 6;
+  const int seg = (int)(r % nseg); r /= nseg;
+  const int chunk = (int)(r % nchunk);
+  const int tap = (int)(r / nchunk);
+  const float v = w[((int64_t)co * cin + chunk * 64 + j) * 16 + tap];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[i] = (seg == 2) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
 }
-
-// w1 [64][3][4][4] -> fp32 [k = c*16 + kh*4 + kw][64];  w5 [1][512][4][4] -> fp32 [p = kh*4+kw][512]
-__global__ void pack_small_kernel(const float* __restrict__ w1, const float* __restrict__ w5, float* __restrict__ o1,
-                                  float* __restrict__ o5, __nv_bfloat16* __restrict__ o1t) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 64 * 128) {  // o1t [co][seg][kh*16 + kw*4 + c], c == 3 is the zero pad channel
-    const int co = i >> 7, seg = (i >> 6) & 1, k = i & 63;
-    const int kh = k >> 4, kw = (k >> 2) & 3, c = k & 3;
-    const float v = (c < 3) ? w1[co * 48 + c * 16 + kh * 4 + kw] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    o1t[i] = seg ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
-  }
-  if (i < 48 * 64) {
-    const int k = i >> 6, co = i & 63;
-    o1[i] = w1[co * 48 + k];
-  }
-  if (i < 16 * 512) {
-    const int p = i >> 9, c = i & 511;
-    o5[i] = w5[c * 16 + p];
-  }
-}
-
-// eval-mode BatchNorm2d folded to y = x * scale + shift
-__global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
-                               const float* __restrict__ mean, const float* __restrict__ var, float eps, int c,
-                               float* __restrict__ ss, float* __restrict__ gb, float* __restrict__ ident) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < c) {
-    const float s = gamma[i] / sqrtf(var[i] + eps);
-    ss[i] = s;
-    ss[c + i] = beta[i] - mean[i] * s;
-    gb[i] = gamma[i];
-    gb[c + i] = beta[i];
-    if (ident) { ident[i] = 1.f; ident[512 + i] = 0.f; }
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackAllArgs a) {
+  const int bid = blockIdx.x;
+  if (bid < 1024) {
+    const int64_t n2 = (int64_t)128 * 16 * 64 * a.nseg, n3 = (int64_t)256 * 16 * 128 * a.nseg, n4 = (int64_t)512 * 16 * 256 * a.nseg;
+    for (int64_t i = bid * 256ll + threadIdx.x; i < n2 + n3 + n4; i += 1024ll * 256) {
+      if (i < n2) pack_conv_elem(a.w2, a.p2, 64, a.nseg, i);
+      else if (i < n2 + n3) pack_conv_elem(a.w3, a.p3, 128, a.nseg, i - n2);
+      else pack_conv_elem(a.w4, a.p4, 256, a.nseg, i - n2 - n3);
+    }
+  } else if (bid < 1056) {
+    const int i = (bid - 1024) * 256 + threadIdx.x;
+    if (i < 64 * 128) {  // o1t [co][seg][kh*16 + kw*4 + c], c == 3 is the zero pad channel
+      const int co = i >> 7, seg = (i >> 6) & 1, k = i & 63;
+      const int kh = k >> 4, kw = (k >> 2) & 3, c = k & 3;
+      const float v = (c < 3) ? a.w1[co * 48 + c * 16 + kh * 4 + kw] : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      a.o1t[i] = seg ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+    }
+    if (i < 48 * 64) a.o1[i] = a.w1[(i & 63) * 48 + (i >> 6)];
+    if (i < 16 * 512) a.o5[i] = a.w5[(i & 511) * 16 + (i >> 9)];
+  } else {
+    const int l = bid - 1056, c = 128 << l;
+    for (int i = threadIdx.x; i < c; i += 256) {
+      const float sc = a.g[l][i] / sqrtf(a.v[l][i] + a.eps);
+      a.ss[l][i] = sc;
+      a.ss[l][c + i] = a.b[l][i] - a.m[l][i] * sc;
+      a.gb[l][i] = a.g[l][i];
+      a.gb[l][c + i] = a.b[l][i];
+      if (l == 2) { a.ident[i] = 1.f; a.ident[512 + i] = 0.f; }
+    }
   }
 }
 
@@ -1478,17 +1481,26 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ part, int blocks, int64_t rows, int c,
-                                   const float* __restrict__ gb, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ ss) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per channel: lane l adds the partials of blocks l, l+32, ... and the 32 lane sums are combined by a
+// fixed butterfly (deterministic; a single thread walking 256 strided doubles took 55 us per layer).
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int blocks, int64_t rows, int c,
+                                                          const float* __restrict__ gb, float eps, float momentum,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                          float* __restrict__ ss) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (ch >= c) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < blocks; ++b) {
+  for (int b = lane; b < blocks; b += 32) {
     s += part[((size_t)b * c + ch) * 2];
     q += part[((size_t)b * c + ch) * 2 + 1];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane != 0) return;
   const double mean = s / (double)rows;
   double var = q / (double)rows - mean * mean;   // biased (normalisation)
   if (var < 0.0) var = 0.0;
@@ -1939,16 +1951,29 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
   const PackedLayout L = packed_layout(conv_mode);
   cudaStream_t st = sg::as_stream(stream);
   uint8_t* pk = static_cast<uint8_t*>(packed);
-  pack_small_kernel<<<32, 256, 0, st>>>(w1, w5, reinterpret_cast<float*>(pk + L.w1), reinterpret_cast<float*>(pk + L.w5),
-                                        reinterpret_cast<__nv_bfloat16*>(pk + L.w1t));
-  SG_LAUNCH_CHECK();
-  pack_conv_weight_kernel<<<256, 256, 0, st>>>(w2, reinterpret_cast<__nv_bfloat16*>(pk + L.w2), 128, 64, L.nseg);
-  pack_conv_weight_kernel<<<512, 256, 0, st>>>(w3, reinterpret_cast<__nv_bfloat16*>(pk + L.w3), 256, 128, L.nseg);
-  pack_conv_weight_kernel<<<1024, 256, 0, st>>>(w4, reinterpret_cast<__nv_bfloat16*>(pk + L.w4), 512, 256, L.nseg);
-  SG_LAUNCH_CHECK();
-  fold_bn_kernel<<<1, 128, 0, st>>>(bn2_gamma, bn2_beta, bn2_mean, bn2_var, bn_eps, 128, reinterpret_cast<float*>(pk + L.ss2), reinterpret_cast<float*>(pk + L.gb2), nullptr);
-  fold_bn_kernel<<<1, 256, 0, st>>>(bn3_gamma, bn3_beta, bn3_mean, bn3_var, bn_eps, 256, reinterpret_cast<float*>(pk + L.ss3), reinterpret_cast<float*>(pk + L.gb3), nullptr);
-  fold_bn_kernel<<<1, 512, 0, st>>>(bn4_gamma, bn4_beta, bn4_mean, bn4_var, bn_eps, 512, reinterpret_cast<float*>(pk + L.ss4), reinterpret_cast<float*>(pk + L.gb4), reinterpret_cast<float*>(pk + L.ident));
+  PackAllArgs a;
+  a.w1 = w1; a.w2 = w2; a.w3 = w3; a.w4 = w4; a.w5 = w5;
+  const float* gs[3] = {bn2_gamma, bn3_gamma, bn4_gamma};
+  const float* bs[3] = {bn2_beta, bn3_beta, bn4_beta};
+  const float* ms[3] = {bn2_mean, bn3_mean, bn4_mean};
+  const float* vs[3] = {bn2_var, bn3_var, bn4_var};
+  const size_t sso[3] = {L.ss2, L.ss3, L.ss4}, gbo[3] = {L.gb2, L.gb3, L.gb4};
+  for (int l = 0; l < 3; ++l) {
+    SG_REQUIRE(gs[l] && bs[l] && ms[l] && vs[l], "null BatchNorm pointer");
+    a.g[l] = gs[l]; a.b[l] = bs[l]; a.m[l] = ms[l]; a.v[l] = vs[l];
+    a.ss[l] = reinterpret_cast<float*>(pk + sso[l]);
+    a.gb[l] = reinterpret_cast<float*>(pk + gbo[l]);
+  }
+  a.p2 = reinterpret_cast<__nv_bfloat16*>(pk + L.w2);
+  a.p3 = reinterpret_cast<__nv_bfloat16*>(pk + L.w3);
+  a.p4 = reinterpret_cast<__nv_bfloat16*>(pk + L.w4);
+  a.o1t = reinterpret_cast<__nv_bfloat16*>(pk + L.w1t);
+  a.o1 = reinterpret_cast<float*>(pk + L.w1);
+  a.o5 = reinterpret_cast<float*>(pk + L.w5);
+  a.ident = reinterpret_cast<float*>(pk + L.ident);
+  a.eps = bn_eps;
+  a.nseg = L.nseg;
+  pack_all_kernel<<<1059, 256, 0, st>>>(a);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -2032,7 +2057,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   SG_LAUNCH_CHECK();
   float* rm = running_stats ? running_stats[2 * (layer - 2)] : nullptr;
   float* rv = running_stats ? running_stats[2 * (layer - 2) + 1] : nullptr;
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(part, blocks, rows, c, fq(gb), eps, momentum, rm, rv, ss);
+  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(part, blocks, rows, c, fq(gb), eps, momentum, rm, rv, ss);
   SG_LAUNCH_CHECK();
   int64_t ab = sg::ceil_div(rows * (c / 8), 256);
   if (ab > (int64_t)sg::state().sm_count * 16) ab = (int64_t)sg::state().sm_count * 16;
