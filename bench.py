@@ -259,31 +259,48 @@ def main():
 
     # ---- end to end through the reference-facing call, host dataset -----------------------------------------
     e2e = None
+    e2e_u8 = None
     if not args.no_e2e:
+        def e2e_leg(ds, ne):
+            def e2e_step():
+                return sb.refine_dataset_by_loss(ds, netD, device, LOSS_RATIO, conv_mode=args.mode)
+            for _ in range(3):
+                sub, _t = e2e_step()
+            torch.cuda.synchronize()
+            if group is not None:
+                dist.barrier()
+            es = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(es):
+                sub, _t = e2e_step()
+            torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - t0) / es], device=device)
+            if group is not None:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return ne * world / dt.item(), int(len(sub.indices)) * 8 + 12
+
         ne = min(E2E_SAMPLES, shard)
         host = torch.empty((ne, 3, 64, 64), dtype=torch.float32).pin_memory()
         host.copy_(images[:ne])
-        ds = torch.utils.data.TensorDataset(host, torch.zeros(ne, dtype=torch.long))
-
-        def e2e_step():
-            return sb.refine_dataset_by_loss(ds, netD, device, LOSS_RATIO, conv_mode=args.mode)
-        for _ in range(3):
-            sub, _t = e2e_step()
-        torch.cuda.synchronize()
-        if group is not None:
-            dist.barrier()
-        es = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(es):
-            sub, _t = e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / es], device=device)
-        if group is not None:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": ne * world / dt.item(), "unit": "samples/s", "h2d_bytes_per_step": ne * 49152,
-               "d2h_bytes_per_step": int(len(sub.indices)) * 8 + 12, "samples_per_gpu": ne,
+        v, d2h = e2e_leg(torch.utils.data.TensorDataset(host, torch.zeros(ne, dtype=torch.long)), ne)
+        e2e = {"value": v, "unit": "samples/s", "h2d_bytes_per_step": ne * 49152,
+               "d2h_bytes_per_step": d2h, "samples_per_gpu": ne,
                "api": "refine_dataset_by_loss(TensorDataset(host pinned fp32), netD, device, 0.1)",
                "note": "each rank strains its own host dataset (replicas); PCIe H2D of 49152 B/sample is inside the timed region"}
+        del host
+        # the same call on a uint8 host dataset (the pixels the reference's ImageFolder decodes, ToTensor + Normalize
+        # applied on the device, bit-identical to the host transform): 12288 B/sample over PCIe
+        ne8 = shard
+        host8 = torch.empty((ne8, 3, 64, 64), dtype=torch.uint8).pin_memory()
+        for i in range(0, ne8, CHUNK):
+            host8[i:i + CHUNK].copy_(((images[i:i + CHUNK] + 1.0) * 127.5).round_().clamp_(0, 255).to(torch.uint8))
+        v8, d2h8 = e2e_leg(sb.U8ImageDataset(host8, None, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ne8)
+        e2e_u8 = {"value": v8, "unit": "samples/s", "h2d_bytes_per_step": ne8 * 12288, "d2h_bytes_per_step": d2h8,
+                  "samples_per_gpu": ne8,
+                  "api": "refine_dataset_by_loss(U8ImageDataset(host pinned uint8, Normalize(.5,.5)), netD, device, 0.1)",
+                  "note": "same strain on the uint8 pixels of the same images quantised to 8 bits; ToTensor + Normalize run on "
+                          "the device (sg_u8_normalize), 12288 B/sample over PCIe inside the timed region"}
+        del host8
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port of the reference on the host cores ----------------
     cpu = None
@@ -351,7 +368,7 @@ def main():
                            "samples_per_gpu": shard, "samples_total": n_global, "chunk": CHUNK, "loss_ratio": LOSS_RATIO,
                            "conv_mode": args.mode, "l2": "inputs (6.4 GB/GPU) larger than L2; no flush needed",
                            "kept": kept, "threshold": float(thr.item())},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "clocks": clocks, "e2e": e2e, "e2e_u8_dataset": e2e_u8, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "frac_of_conv_roofline": value / world / (pk["tf_sust"] * 1e12 / FLOP_ALL),
                 "kernels": kernels, "select_compact_ms": ms_sel, "train_iters_per_sec": train, "torch_eager_gpu": eager,

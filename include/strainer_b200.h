@@ -52,6 +52,12 @@ typedef enum SgConvMode {
   SG_CONV_BF16X3 = 1  /* fp32-parity mode: bf16 hi/lo split, 3 tcgen05 passes (hi*hi+lo*hi+hi*lo) */
 } SgConvMode;
 
+/* memory layout of a uint8 image batch */
+typedef enum SgLayout {
+  SG_LAYOUT_NCHW = 0, /* [N][C][H*W]: the layout ToTensor produces */
+  SG_LAYOUT_NHWC = 1  /* [N][H*W][C]: the PIL / np.asarray(image) layout ToTensor reads */
+} SgLayout;
+
 /* ---- library ------------------------------------------------------------------------- */
 int sg_version(void);
 const char* sg_last_error_string(void);
@@ -62,6 +68,14 @@ int sg_sm_count(void);
 
 /* ---- synthetic data (counter based, identical to oracle.synth_images) --- */
 int sg_synth_images(float* out, int64_t start, int64_t count, uint32_t seed, void* stream);
+
+/* ---- uint8 pixels -> the DataLoader's fp32 tensor --------------------------------------------
+ * replaces transforms.ToTensor() + transforms.Normalize(mean, std) of "#strainer gan.py:89-90, 115-116" for a
+ * dataset kept as uint8: out[n][c][p] = ((float)x / 255 - mean[c]) / std[c], every step a correctly rounded fp32
+ * operation = bit-identical to the host transform.  x: `count` images of `channels` (1..4) x `plane` (= H*W) bytes
+ * in `layout`; h_mean / h_std: HOST arrays of `channels` floats; out: fp32 NCHW.  HBM bound (1 B in, 4 B out). */
+int sg_u8_normalize(const uint8_t* x, int64_t count, int channels, int64_t plane, int layout, const float* h_mean,
+                    const float* h_std, float* out, void* stream);
 
 /* ---- D64 scoring: Discriminator.forward + BCE vs label 1 ------------------------------
  * replaces "#strainer gan.py:230-256" (5 convs, eval-mode BN, LeakyReLU .2, Sigmoid) and the

@@ -13,6 +13,7 @@ SG_LT, SG_LE, SG_GE, SG_GT = 0, 1, 2, 3
 SG_NOT = 4  # OR-ed into a comparison: logical negation (NaN-correct complement)
 SG_LERP_NUMPY, SG_LERP_TORCH = 0, 1
 SG_CONV_BF16, SG_CONV_BF16X3 = 0, 1
+SG_LAYOUT_NCHW, SG_LAYOUT_NHWC = 0, 1
 SG_SELECT_WS_WORDS = 2048
 SG_SELECT_WS_NANCOUNT = 256
 SG_SELECT_WS_MINABOVE = 257
@@ -26,6 +27,7 @@ _SIGS = {
     "sg_init": (c_int, [c_int]),
     "sg_sm_count": (c_int, []),
     "sg_synth_images": (c_int, [P, c_int64, c_int64, c_uint32, P]),
+    "sg_u8_normalize": (c_int, [P, c_int64, c_int, c_int64, c_int, P, P, P, P]),
     "sg_d64_packed_bytes": (c_size_t, [c_int]),
     "sg_d64_pack": (c_int, [P] * 17 + [c_float, c_int, P, P]),
     "sg_d64_workspace_bytes": (c_size_t, [c_int64, c_int]),

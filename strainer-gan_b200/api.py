@@ -383,31 +383,38 @@ class D64Scorer:
                 "sg_d64_read_activation")
         return out
 
-    def score(self, images: torch.Tensor, want=("loss",)):
-        """Scores N images (CUDA tensor, or a host tensor streamed through pinned double buffers with the
-        H2D copies overlapped with compute).  Returns a dict of fp32 device tensors [N]."""
+    def score(self, images, want=("loss",)):
+        """Scores N images: a fp32 tensor [N,3,64,64] or a ``U8Images`` (uint8 pixels + Normalize, converted on the
+        device), CUDA resident or on the host (streamed through double buffers with the H2D copies overlapped with
+        compute; pinned source tensors are copied from directly).  Returns a dict of fp32 device tensors [N]."""
         n = images.shape[0]
         outs = {k: torch.empty(n, dtype=torch.float32, device=self.device) for k in want}
-        if images.dtype != torch.float32 or tuple(images.shape[1:]) != (3, 64, 64):
-            raise ValueError("images must be float32 [N,3,64,64]")
+        u8 = images if isinstance(images, U8Images) else None
+        if tuple(images.shape[1:]) != (3, 64, 64) or (u8 is None and images.dtype != torch.float32):
+            raise ValueError("images must be float32 [N,3,64,64] or U8Images of 3x64x64 pixels")
 
         def sl(name, i, b):
             return outs[name][i:i + b] if name in outs else None
 
-        if images.is_cuda:
-            images = images.contiguous()
-            for i in range(0, n, self.max_batch):
-                b = min(self.max_batch, n - i)
-                self.score_into(images[i:i + b], sl("logit", i, b), sl("prob", i, b), sl("loss", i, b))
-            return outs
-        # host path: 2 pinned staging buffers + 2 device buffers, copy stream ahead of compute
+        def score_chunk(x, i, b):
+            self.score_into(x, sl("logit", i, b), sl("prob", i, b), sl("loss", i, b))
+
         cb = self.max_batch
-        images = images.contiguous()
-        pinned_src = images.is_pinned()
+        src = (u8.pixels if u8 is not None else images).contiguous()
+        if src.is_cuda:
+            f32 = torch.empty((min(cb, max(n, 1)), 3, 64, 64), dtype=torch.float32, device=self.device) if u8 is not None else None
+            for i in range(0, n, cb):
+                b = min(cb, n - i)
+                score_chunk(u8.normalize_into(src[i:i + b], f32[:b]) if u8 is not None else src[i:i + b], i, b)
+            return outs
+        # host path: 2 device buffers (+ 2 pinned staging buffers for a pageable source), copy stream ahead of compute
+        pinned_src = src.is_pinned()
         main = torch.cuda.current_stream()
         copy_stream = _copy_stream(self.device)
-        dev = [torch.empty((cb, 3, 64, 64), dtype=torch.float32, device=self.device) for _ in range(2)]
-        pin = None if pinned_src else [torch.empty((cb, 3, 64, 64), dtype=torch.float32).pin_memory() for _ in range(2)]
+        row = tuple(src.shape[1:])
+        dev = [torch.empty((cb,) + row, dtype=src.dtype, device=self.device) for _ in range(2)]
+        f32 = [torch.empty((cb, 3, 64, 64), dtype=torch.float32, device=self.device) for _ in range(2)] if u8 is not None else None
+        pin = None if pinned_src else [torch.empty((cb,) + row, dtype=src.dtype).pin_memory() for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
         nchunks = (n + cb - 1) // cb
@@ -420,15 +427,21 @@ class D64Scorer:
             with torch.cuda.stream(copy_stream):
                 if ci >= 2:
                     copy_stream.wait_event(consumed[s])
-                src = images[i:i + b]
+                part = src[i:i + b]
                 if not pinned_src:
-                    pin[s][:b].copy_(src)
-                    src = pin[s][:b]
-                dev[s][:b].copy_(src, non_blocking=True)
+                    pin[s][:b].copy_(part)
+                    part = pin[s][:b]
+                dev[s][:b].copy_(part, non_blocking=True)
                 copied[s].record(copy_stream)
             main.wait_event(copied[s])
-            self.score_into(dev[s][:b], sl("logit", i, b), sl("prob", i, b), sl("loss", i, b))
-            consumed[s].record(main)
+            if u8 is not None:
+                # the uint8 staging buffer is free again as soon as the conversion has run
+                x = u8.normalize_into(dev[s][:b], f32[s][:b])
+                consumed[s].record(main)
+                score_chunk(x, i, b)
+            else:
+                score_chunk(dev[s][:b], i, b)
+                consumed[s].record(main)
         return outs
 
 
@@ -515,18 +528,129 @@ def get_scorer(discriminator: nn.Module, device=None, mode: str = "fp32", max_ba
     return sc
 
 
+# ----------------------------------------------------------------------------------------------
+# uint8 datasets: ToTensor + Normalize on the device
+# ----------------------------------------------------------------------------------------------
+class U8Images:
+    """A batch of uint8 images plus the ``Normalize(mean, std)`` that follows ``ToTensor`` in the reference's
+    transform ("#strainer gan.py:89-90").  ``pixels``: uint8 ``[N,C,H,W]`` (layout 'NCHW') or ``[N,H,W,C]`` ('NHWC',
+    what ``np.asarray(PIL image)`` gives), host (pinned or not) or CUDA.  ``to_f32`` produces, on the device, exactly the
+    fp32 NCHW tensor the host transform would (``sg_u8_normalize``: correctly rounded fp32 division / subtraction)."""
+
+    def __init__(self, pixels: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), layout: str = "NCHW"):
+        if not isinstance(pixels, torch.Tensor):
+            pixels = torch.as_tensor(np.asarray(pixels))
+        if pixels.dtype != torch.uint8 or pixels.dim() != 4:
+            raise ValueError("pixels must be a uint8 tensor [N,C,H,W] or [N,H,W,C]")
+        if layout not in ("NCHW", "NHWC"):
+            raise ValueError("layout must be 'NCHW' or 'NHWC'")
+        self.pixels = pixels.contiguous()
+        self.layout = layout
+        n, a, b, c = self.pixels.shape
+        self.chw = (a, b, c) if layout == "NCHW" else (c, a, b)
+        ch = self.chw[0]
+        mean = [float(m) for m in (mean if hasattr(mean, "__len__") else [mean] * ch)]
+        std = [float(v) for v in (std if hasattr(std, "__len__") else [std] * ch)]
+        if not 1 <= ch <= 4 or len(mean) != ch or len(std) != ch:
+            raise ValueError("1..4 channels with one mean / std per channel")
+        self.mean, self.std = tuple(mean), tuple(std)
+        self._cmean = (L.c_float * ch)(*mean)
+        self._cstd = (L.c_float * ch)(*std)
+
+    @property
+    def shape(self):
+        return (self.pixels.shape[0],) + self.chw
+
+    @property
+    def is_cuda(self):
+        return self.pixels.is_cuda
+
+    def __len__(self):
+        return self.pixels.shape[0]
+
+    def _like(self, pixels):
+        return U8Images(pixels, self.mean, self.std, self.layout)
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            return self._like(self.pixels[key])
+        return self._like(self.pixels.index_select(0, torch.as_tensor(key, dtype=torch.long, device=self.pixels.device)))
+
+    def normalize_into(self, src_dev: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """src_dev: device uint8 rows in this object's layout -> out: fp32 [b,C,H,W] (stream ordered)."""
+        b = src_dev.shape[0]
+        c, h, w = self.chw
+        lay = L.SG_LAYOUT_NCHW if self.layout == "NCHW" else L.SG_LAYOUT_NHWC
+        L.check(_lib_for(out.device).sg_u8_normalize(_p(src_dev), b, c, h * w, lay, self._cmean, self._cstd, _p(out),
+                                                     _stream()), "sg_u8_normalize")
+        return out
+
+    def to_f32(self, device=None) -> torch.Tensor:
+        device = _dev(device if device is not None else (self.pixels.device if self.is_cuda else None))
+        out = torch.empty(self.shape, dtype=torch.float32, device=device)
+        return self.normalize_into(self.pixels.to(device), out)
+
+    def host_f32(self, i=None) -> torch.Tensor:
+        """The host transform itself (ToTensor + Normalize as torchvision computes them): what ``__getitem__`` of the
+        dataset yields, so that unmodified reference code sees the same values the device path computes."""
+        px = self.pixels if i is None else self.pixels[i]
+        px = px.cpu()
+        if self.layout == "NHWC":
+            px = px.permute(2, 0, 1) if px.dim() == 3 else px.permute(0, 3, 1, 2)
+        x = px.contiguous().to(torch.float32).div(255)
+        shape = (-1, 1, 1)
+        mean = torch.as_tensor(self.mean, dtype=torch.float32).view(shape)
+        std = torch.as_tensor(self.std, dtype=torch.float32).view(shape)
+        return x.sub_(mean).div_(std)
+
+
+class U8ImageDataset(torch.utils.data.Dataset):
+    """Map-style dataset over uint8 pixels whose ``__getitem__`` yields ``(ToTensor+Normalize(image), label)`` exactly as
+    the reference's ``ImageFolder(..., transform=Compose([..., ToTensor(), Normalize(mean, std)]))`` does
+    ("#strainer gan.py:85-91"): unmodified reference code can iterate it through a ``DataLoader``, while the functions of
+    this module recognise it, keep it uint8 over PCIe / in HBM and normalise on the device (bit-identical values)."""
+
+    def __init__(self, pixels, labels=None, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), layout: str = "NCHW"):
+        self.images = pixels if isinstance(pixels, U8Images) else U8Images(pixels, mean, std, layout)
+        self.labels = labels
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        label = 0 if self.labels is None else self.labels[i]
+        return self.images.host_f32(int(i)), label
+
+
+def _device_f32_chunks(images, device, chunk: int):
+    """Yields (start, fp32 device tensor [b,C,H,W]) over a float tensor or a U8Images (host or CUDA)."""
+    n = images.shape[0]
+    if isinstance(images, U8Images):
+        buf = torch.empty((min(chunk, max(n, 1)),) + images.chw, dtype=torch.float32, device=device)
+        for i in range(0, n, chunk):
+            src = images.pixels[i:i + chunk].to(device, non_blocking=True)
+            yield i, images.normalize_into(src, buf[:src.shape[0]])
+        return
+    for i in range(0, n, chunk):
+        yield i, _f32c(images[i:i + chunk], device)
+
+
 def _dataset_images(dataset):
     """Resident image tensor of a dataset if it exposes one (TensorDataset / Subset of it), else
     materialise it through the dataset's own __getitem__ (host side, as the reference's DataLoader)."""
     from torch.utils.data import Subset, TensorDataset
-    if isinstance(dataset, torch.Tensor):
+    if isinstance(dataset, (torch.Tensor, U8Images)):
         return dataset
+    if isinstance(dataset, U8ImageDataset):
+        return dataset.images
     if isinstance(dataset, TensorDataset):
         return dataset.tensors[0]
     if isinstance(dataset, Subset):
         base = _dataset_images(dataset.dataset)
-        idx = torch.as_tensor(np.asarray(dataset.indices).reshape(-1), dtype=torch.long, device=base.device)
-        return base.index_select(0, idx)
+        idx = np.asarray(dataset.indices).reshape(-1)
+        if isinstance(base, U8Images):
+            return base[idx]
+        return base.index_select(0, torch.as_tensor(idx, dtype=torch.long, device=base.device))
     return torch.stack([dataset[i][0] for i in range(len(dataset))])
 
 
@@ -802,11 +926,11 @@ def find_elbow_threshold(z_scores, bins=100):
 def _features_of(dataset, feature_extractor, device):
     imgs = _dataset_images(dataset)
     if feature_extractor is None or isinstance(feature_extractor, nn.Identity):
-        return _f32c(imgs, device)
+        return imgs.to_f32(device) if isinstance(imgs, U8Images) else _f32c(imgs, device)
     feats = []
     with torch.no_grad():
-        for i in range(0, imgs.shape[0], 64):
-            feats.append(feature_extractor(imgs[i:i + 64].to(device)).float())
+        for _, x in _device_f32_chunks(imgs, device, 64):
+            feats.append(feature_extractor(x).float())
     return torch.cat(feats, dim=0)
 
 
@@ -944,15 +1068,13 @@ def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: 
     if conv_mode != "fp32_cuda":
         mode = L.SG_CONV_BF16 if conv_mode == "bf16" else L.SG_CONV_BF16X3
         ws = _Scratch.get(device, "ae_tc", lib.sg_ae_tc_workspace_bytes(cb, mode))
-        for i in range(0, n, chunk):
-            x = _f32c(images[i:i + chunk], device)
+        for i, x in _device_f32_chunks(images, device, chunk):
             L.check(lib.sg_ae_score_tc(_p(x), x.shape[0], arr, _p(ws), mode, _p(err[i:i + chunk]), L.P(0), _stream()),
                     "sg_ae_score_tc")
         L.check(lib.sg_ae_bf16_check(_p(ws), _stream()), "sg_ae_bf16_check")
         return err
     ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(cb))
-    for i in range(0, n, chunk):
-        x = _f32c(images[i:i + chunk], device)
+    for i, x in _device_f32_chunks(images, device, chunk):
         L.check(lib.sg_ae_score(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()), "sg_ae_score")
     return err
 

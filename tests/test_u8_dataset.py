@@ -1,0 +1,125 @@
+"""uint8 datasets: the reference's transform chain ToTensor() + Normalize(mean, std) ("#strainer gan.py:85-91,
+113-116") computed on the device (sg_u8_normalize) must be bit-identical to the host transform, so that straining a
+U8ImageDataset gives the same thresholds and kept-index lists as straining the fp32 tensors a DataLoader yields."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import strainer_oracle as O
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import strainer_b200
+    return strainer_b200
+
+
+def host_transform(px_nchw_u8, mean, std):
+    """ToTensor + Normalize restated with numpy fp32 arithmetic (IEEE division / subtraction, one rounding each)."""
+    x = px_nchw_u8.astype(np.float32) / np.float32(255)
+    m = np.asarray(mean, np.float32).reshape(1, -1, 1, 1)
+    s = np.asarray(std, np.float32).reshape(1, -1, 1, 1)
+    return (x - m) / s
+
+
+def test_dataset_getitem_equals_torchvision(sb):
+    """CPU: what U8ImageDataset yields == torchvision's own ToTensor + Normalize on the PIL image (the reference's
+    transform), and == the numpy restatement used by the GPU tests."""
+    tv = pytest.importorskip("torchvision.transforms")
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    hwc = rng.integers(0, 256, size=(5, 64, 64, 3), dtype=np.uint8)
+    hwc[0, :4, :64, 0] = np.arange(256, dtype=np.uint8).reshape(4, 64)   # every pixel value at least once
+    for mean, std in (((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        tf = tv.Compose([tv.ToTensor(), tv.Normalize(mean, std)])
+        want = torch.stack([tf(Image.fromarray(im)) for im in hwc])
+        ds_hwc = sb.U8ImageDataset(torch.from_numpy(hwc), None, mean, std, layout="NHWC")
+        ds_chw = sb.U8ImageDataset(torch.from_numpy(hwc).permute(0, 3, 1, 2).contiguous(), torch.arange(5), mean, std)
+        for i in range(5):
+            assert torch.equal(ds_hwc[i][0], want[i])
+            assert torch.equal(ds_chw[i][0], want[i])
+            assert int(ds_chw[i][1]) == i
+        assert np.array_equal(host_transform(hwc.transpose(0, 3, 1, 2), mean, std), want.numpy())
+    # a DataLoader over it batches like any map-style dataset (what unmodified reference code would do)
+    xb, yb = next(iter(torch.utils.data.DataLoader(ds_chw, batch_size=4, shuffle=False)))
+    assert torch.equal(xb, want[:4]) and yb.tolist() == [0, 1, 2, 3]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(7, 3, 64, 64), (3, 1, 28, 28), (2, 4, 5, 3), (1, 3, 16, 16), (0, 3, 64, 64)])
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+def test_u8_normalize_bit_exact(sb, shape, layout):
+    rng = np.random.default_rng(11)
+    n, c, h, w = shape
+    px = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    k = min(256, px.size)
+    px.reshape(-1)[:k] = np.arange(k, dtype=np.uint8)   # every pixel value
+    mean = [0.5, 0.456, 0.0, 0.25][:c]
+    std = [0.5, 0.224, 1.0, 3.0][:c]
+    want = host_transform(px, mean, std)
+    src = px if layout == "NCHW" else np.ascontiguousarray(px.transpose(0, 2, 3, 1))
+    for dev in ("cpu", "cuda"):
+        imgs = sb.U8Images(torch.from_numpy(src).to(dev), mean, std, layout)
+        assert imgs.shape == shape
+        got = imgs.to_f32("cuda").cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want)
+    # unaligned views take the generic kernel
+    if n >= 2 and layout == "NCHW":
+        flat = torch.zeros(px.size + 1, dtype=torch.uint8, device="cuda")
+        flat[1:] = torch.from_numpy(px).reshape(-1).cuda()
+        imgs = sb.U8Images(flat[1:].view(shape), mean, std)
+        assert imgs.pixels.data_ptr() % 16 != 0
+        assert np.array_equal(imgs.to_f32().cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("where", ["pageable", "pinned", "cuda"])
+def test_refine_u8_dataset_equals_fp32_dataset(sb, where):
+    """Same thresholds / kept indices / losses (bit for bit) whether the dataset is fp32 or uint8 + device normalise; and
+    the oracle run on what the uint8 dataset's __getitem__ yields agrees within the fp32-mode tolerance."""
+    n = 300
+    netD = O.make_discriminator(O.SEED)
+    f = O.synth_images(0, n)
+    px = torch.from_numpy(np.clip(np.rint((f + 1.0) * 127.5), 0, 255).astype(np.uint8))
+    if where == "pinned":
+        px = px.pin_memory()
+    elif where == "cuda":
+        px = px.cuda()
+    ds8 = sb.U8ImageDataset(px, torch.zeros(n, dtype=torch.long))
+    x32 = torch.from_numpy(host_transform(px.cpu().numpy(), (0.5,) * 3, (0.5,) * 3))
+    assert torch.equal(ds8[5][0], x32[5])
+    ds32 = torch.utils.data.TensorDataset(x32, torch.zeros(n, dtype=torch.long))
+    sc = sb.get_scorer(netD, "cuda", "fp32", max_batch=128)   # several chunks + a ragged tail through the double buffers
+    l8 = sc.score(ds8.images, ("loss",))["loss"].cpu()
+    l32 = sc.score(x32, ("loss",))["loss"].cpu()
+    assert torch.equal(l8, l32)
+    sub8, thr8 = sb.refine_dataset_by_loss(ds8, netD, "cuda", 0.2)
+    sub32, thr32 = sb.refine_dataset_by_loss(ds32, netD, "cuda", 0.2)
+    assert thr8 == thr32 and np.array_equal(np.asarray(sub8.indices), np.asarray(sub32.indices))
+    assert sub8.dataset is ds8
+    widx, wthr, wloss = O.refine_dataset_by_loss(x32, netD, 0.2)
+    assert abs(thr8 - wthr) <= 1e-3 * abs(wthr)
+    got = np.zeros(n, bool)
+    got[np.asarray(sub8.indices)] = True
+    want = np.zeros(n, bool)
+    want[widx] = True
+    near = np.abs(wloss.reshape(-1) - wthr) <= 1e-3 * abs(wthr)
+    assert not ((got != want) & ~near).any()
+    # Subset of a uint8 dataset (the second straining pass of "# final.py:444") stays uint8
+    sub_again, _ = sb.refine_dataset_by_loss(sub8, netD, "cuda", 0.2)
+    ref_again, _ = sb.refine_dataset_by_loss(torch.utils.data.Subset(ds32, sub32.indices), netD, "cuda", 0.2)
+    assert np.array_equal(np.asarray(sub_again.indices), np.asarray(ref_again.indices))
+
+
+@pytest.mark.gpu
+def test_autoencoder_u8_dataset(sb):
+    n = 70
+    torch.manual_seed(O.SEED)
+    ae = O.AutoEncoder()
+    f = O.synth_images(1000, n)
+    px = torch.from_numpy(np.clip(np.rint((f + 1.0) * 127.5), 0, 255).astype(np.uint8))
+    ds8 = sb.U8ImageDataset(px)
+    x32 = torch.from_numpy(host_transform(px.numpy(), (0.5,) * 3, (0.5,) * 3))
+    m8 = sb.detect_outliers_autoencoder(ae, ds8, "cuda")
+    m32 = sb.detect_outliers_autoencoder(ae, torch.utils.data.TensorDataset(x32, torch.zeros(n)), "cuda")
+    assert torch.equal(m8, m32)

@@ -106,6 +106,14 @@ def main():
     rec("hist_uniform_100", timeit(lambda: lib.sg_hist_uniform(p(v), n, p(edges), 100, p(hc), st)), 4 * n)
     part = torch.empty(2 * (n // L.SG_MOMENT_CHUNK + 1), dtype=torch.float64, device=dev)
     rec("chunk_moments", timeit(lambda: lib.sg_chunk_moments(p(v), n, p(part), st)), 4 * n)
+    # uint8 pixels -> fp32 NCHW (ToTensor + Normalize): 65536 images, 1 B read + 4 B written per element
+    un = 65536
+    cm = (L.c_float * 3)(0.5, 0.5, 0.5)
+    f32 = torch.empty((un, 3, 64, 64), dtype=torch.float32, device=dev)
+    for name, lay, shape in (("u8_normalize_nchw", L.SG_LAYOUT_NCHW, (un, 3, 64, 64)), ("u8_normalize_nhwc", L.SG_LAYOUT_NHWC, (un, 64, 64, 3))):
+        u8 = torch.randint(0, 256, shape, dtype=torch.uint8, device=dev, generator=g)
+        t = timeit(lambda: lib.sg_u8_normalize(p(u8), un, 3, 4096, lay, cm, cm, p(f32), st))
+        rec(name, t, 5 * un * 12288, "1 B read + 4 B written per element (random pixels: worst case for the look-up table)")
     print(json.dumps(out))
 
 
