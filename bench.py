@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--shard", type=int, default=SHARD)
+    ap.add_argument("--chunk", type=int, default=CHUNK, help="samples per scoring launch group")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the DCGAN train iters/sec leg")
@@ -128,6 +129,8 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    global CHUNK
+    CHUNK = args.chunk
 
     import numpy as np
     import torch
