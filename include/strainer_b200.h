@@ -270,7 +270,9 @@ int sg_gmm1d_update(int64_t n_total, double reg_covar, double tol, int max_iter,
  * non-noise points; this is sklearn.cluster.DBSCAN(eps, min_samples) applied to an (N,1) array:
  * counts_out[0] = number of non-noise points, noise_out (optional) = 0/1 per point in input order. */
 size_t sg_sort_workspace_bytes(int64_t n);
-/* ascending stable LSD radix sort (NaN last, -0 == +0); order_out = source index of each sorted element */
+/* ascending stable LSD radix sort (NaN last, -0 == +0), n <= 2^30: one histogram kernel + 4 single-kernel passes
+ * (decoupled look-back).  sorted_out and / or order_out (source index of each sorted element) may be NULL: without
+ * order_out the passes move keys only (36 B / element instead of 64).  Outputs must not overlap the workspace. */
 int sg_sort_f32(const float* v, int64_t n, float* sorted_out, int32_t* order_out, void* workspace, void* stream);
 size_t sg_dbscan1d_workspace_bytes(int64_t n);
 int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t* counts_out, uint8_t* noise_out,

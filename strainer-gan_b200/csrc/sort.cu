@@ -4,134 +4,185 @@
 // points, which in one dimension is fully determined by the sorted order:
 //   core(i)   <=>  #{j : |x_j - x_i| <= eps} >= min_samples     (float64 distances, as scikit-learn)
 //   noise(i)  <=>  not core(i) and no core point within eps
-// LSD radix sort: 4 passes x 8 bits over the order-preserving key (NaN last), stable, with the
-// original index as payload.  Per pass: per-tile digit histograms -> exclusive scan in (digit, tile)
-// order -> stable scatter (warp-level match ranking, per-warp digit counters).
+// LSD radix sort, 4 passes x 8 bits over the order-preserving key (NaN last), stable, original index as optional
+// payload, in the "onesweep" form: ONE kernel reads the input once and builds the four global digit histograms, then
+// every pass is ONE kernel -- a tile ranks its keys (warp-level match ranking, stable), publishes its 256 digit counts
+// to a tile-state array, resolves the counts of all earlier tiles by decoupled look-back (one thread per digit),
+// reorders the tile in shared memory and writes digit-contiguous runs.  Traffic per element: 4 B (histogram read) +
+// per pass read + write of key (+ payload): 36 B keys only, 64 B with the payload (pass 0 reads the floats and
+// generates the index, the last pass writes floats).  The first version (per-tile histograms -> single-CTA scan ->
+// scatter, 3 launches per pass, uncoalesced 4-byte scatter) ran at 2 % of the HBM peak.
 #include "common.cuh"
 
 namespace sg {
 namespace srt {
 
-constexpr int kThreads = 256;
-constexpr int kItems = 8;
-constexpr int kTile = kThreads * kItems;  // 2048
+constexpr int kThreads = 256;          // element-wise kernels
+constexpr int kST = 512;               // sort CTA: 16 warps
+constexpr int kSWarps = kST / 32;
+constexpr int kSI = 8;                 // keys per thread
+constexpr int kSTile = kST * kSI;      // 4096 keys per tile
+constexpr uint32_t kStAgg = 1u << 30, kStIncl = 2u << 30, kStMask = (1u << 30) - 1;   // tile state: flag | count
 
-__global__ void __launch_bounds__(kThreads) keys_init_kernel(const float* __restrict__ v, int64_t n,
-                                                             uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    keys[i] = float_to_key(v[i]);
-    idx[i] = (int32_t)i;
-  }
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads) hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift,
-                                                        uint32_t* __restrict__ hist, int tiles) {
-  __shared__ uint32_t s_h[256];
-  s_h[threadIdx.x] = 0;
+// All four digit histograms in one read of the input.  Per-warp shared-memory histograms; each thread keeps the
+// (digit, count) run of its last key per pass and only touches shared memory when the digit changes, so clustered
+// inputs (constant exponent byte, all-equal vectors) do not serialise on one counter.
+__global__ void __launch_bounds__(kThreads) hist4_kernel(const float* __restrict__ v, int64_t n, uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t s_h[kThreads / 32][1024];
+  for (int i = threadIdx.x; i < (kThreads / 32) * 1024; i += kThreads) (&s_h[0][0])[i] = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * kTile;
+  uint32_t* h = s_h[threadIdx.x >> 5];
+  uint32_t cur[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+  stream_f32<4>(v, n, [&](float x, int64_t) {
+    const uint32_t k = float_to_key(x);
 #pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const int64_t i = base + j * kThreads + threadIdx.x;
-    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255u], 1u);
-  }
-  __syncthreads();
-  hist[(size_t)threadIdx.x * tiles + blockIdx.x] = s_h[threadIdx.x];
-}
-
-// exclusive scan of hist[256 * tiles] in place (single CTA, sequential 1024-wide sweeps)
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ hist, int64_t total) {
-  __shared__ uint32_t s_w[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int64_t b = 0; b < total; b += 1024) {
-    const int64_t i = b + threadIdx.x;
-    const uint32_t v = i < total ? hist[i] : 0u;
-    uint32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) s_w[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      uint32_t s = s_w[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += y;
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t d = (k >> (8 * p)) & 255u;
+      if (d != cur[p]) {
+        if (cnt[p]) atomicAdd(&h[p * 256 + cur[p]], cnt[p]);
+        cur[p] = d;
+        cnt[p] = 0;
       }
-      s_w[lane] = s;
+      ++cnt[p];
     }
-    __syncthreads();
-    const uint32_t incl = x + (w ? s_w[w - 1] : 0u) + s_carry;
-    if (i < total) hist[i] = incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = incl;
-    __syncthreads();
+  });
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    if (cnt[p]) atomicAdd(&h[p * 256 + cur[p]], cnt[p]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += kThreads) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += s_h[w][i];
+    if (t) atomicAdd(&ghist[i], t);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                           const int32_t* __restrict__ idx_in, int64_t n, int shift,
-                                                           const uint32_t* __restrict__ offs, int tiles,
-                                                           uint32_t* __restrict__ keys_out, int32_t* __restrict__ idx_out) {
-  __shared__ uint32_t s_cnt[kThreads / 32][256];  // per-warp digit counters -> per-warp offsets
+// exclusive scan of one value per thread over the first 256 threads (8 warps) of the CTA; s_w: 8 words of scratch
+__device__ __forceinline__ uint32_t scan256_excl(uint32_t v, uint32_t* s_w) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (kThreads / 32) * 256; i += kThreads) (&s_cnt[0][0])[i] = 0;
-  __syncthreads();
-  // warp w owns elements [w*256, (w+1)*256) of the tile, visited in 8 rounds of 32 (index order)
-  const int64_t wbase = (int64_t)blockIdx.x * kTile + w * (kItems * 32);
-  uint32_t key[kItems];
-  int32_t pay[kItems];
-  uint32_t rank[kItems];
+  uint32_t x = v;
 #pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const int64_t i = wbase + j * 32 + lane;
-    const bool valid = i < n;
-    key[j] = valid ? keys_in[i] : 0xFFFFFFFFu;
-    pay[j] = valid ? idx_in[i] : 0;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_w[w] = x;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  uint32_t base = 0;
+#pragma unroll
+  for (int ww = 0; ww < 8; ++ww) base += (ww < w) ? s_w[ww] : 0u;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  return base + x - v;
+}
+
+// One radix pass.  FIRST: keys_in are the caller's floats and the payload is the element index.  LAST: keys are written
+// back as floats.  Tiles are claimed from an atomic counter, so every predecessor of a tile is running or done and the
+// look-back spin cannot deadlock.
+template <bool FIRST, bool LAST, bool PAIRS>
+__global__ void __launch_bounds__(kST, 2)
+onesweep_kernel(const void* __restrict__ keys_in_, const int32_t* __restrict__ pay_in, uint32_t n, int shift,
+                const uint32_t* __restrict__ ghist, uint32_t* __restrict__ tile_state, uint32_t* __restrict__ tile_counter,
+                void* __restrict__ keys_out_, int32_t* __restrict__ pay_out) {
+  __shared__ uint16_t s_cnt[kSWarps][256];   // per-warp digit counts -> per-warp offsets inside the digit
+  __shared__ uint32_t s_keys[kSTile];
+  __shared__ int32_t s_pay[PAIRS ? kSTile : 1];
+  __shared__ uint32_t s_gbase[256];          // global position of the tile's digit run minus its local start
+  __shared__ uint16_t s_lstart[256];
+  __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_tile;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  for (int i = threadIdx.x; i < kSWarps * 256 / 2; i += kST) reinterpret_cast<uint32_t*>(&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  // warp w owns keys [w*256, (w+1)*256) of the tile, visited in 8 rounds of 32 in index order (stability)
+  const uint32_t wbase = tile * kSTile + w * (kSI * 32);
+  uint32_t key[kSI];
+  uint32_t rank[kSI];
+#pragma unroll
+  for (int j = 0; j < kSI; ++j) {
+    const uint32_t i = wbase + j * 32 + lane;
+    if (FIRST) key[j] = i < n ? float_to_key(static_cast<const float*>(keys_in_)[i]) : 0xFFFFFFFFu;
+    else key[j] = i < n ? static_cast<const uint32_t*>(keys_in_)[i] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int j = 0; j < kSI; ++j) {
+    const bool valid = wbase + j * 32 + lane < n;
     const uint32_t d = (key[j] >> shift) & 255u;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane) & vmask;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane) & vmask;
+    const unsigned below = peers & ((1u << lane) - 1u);
     const uint32_t before = valid ? s_cnt[w][d] : 0u;
-    rank[j] = before + __popc(peers & ((1u << lane) - 1u));
+    rank[j] = before + __popc(below);
     __syncwarp();
-    if (valid && (peers & ((1u << lane) - 1u)) == 0u) s_cnt[w][d] = before + __popc(peers);  // leader updates
+    if (valid && below == 0u) s_cnt[w][d] = (uint16_t)(before + __popc(peers));  // the lowest lane of each digit group
     __syncwarp();
   }
   __syncthreads();
-  // digit d: exclusive scan of the 8 warp counts
-  {
+  if (threadIdx.x < 256) {
     const int d = threadIdx.x;
     uint32_t run = 0;
 #pragma unroll
-    for (int ww = 0; ww < kThreads / 32; ++ww) {
+    for (int ww = 0; ww < kSWarps; ++ww) {
       const uint32_t c = s_cnt[ww][d];
-      s_cnt[ww][d] = run;
+      s_cnt[ww][d] = (uint16_t)run;
       run += c;
+    }
+    uint32_t* st = tile_state + (size_t)tile * 256 + d;
+    st_relaxed_u32(st, (tile == 0 ? kStIncl : kStAgg) | run);
+    const uint32_t lstart = scan256_excl(run, s_w);
+    const uint32_t gstart = scan256_excl(ghist[d], s_w);
+    uint32_t excl = 0;
+    for (uint32_t t = tile; t-- > 0;) {
+      const uint32_t* ps = tile_state + (size_t)t * 256 + d;
+      uint32_t wd;
+      do { wd = ld_relaxed_u32(ps); } while ((wd >> 30) == 0u);
+      excl += wd & kStMask;
+      if ((wd >> 30) == 2u) break;
+    }
+    if (tile != 0) st_relaxed_u32(st, kStIncl | (excl + run));
+    s_gbase[d] = gstart + excl - lstart;
+    s_lstart[d] = (uint16_t)lstart;
+  }
+  __syncthreads();
+  int32_t pay[PAIRS ? kSI : 1];
+  if (PAIRS && !FIRST) {
+#pragma unroll
+    for (int j = 0; j < kSI; ++j) {
+      const uint32_t i = wbase + j * 32 + lane;
+      pay[j] = i < n ? pay_in[i] : 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kSI; ++j) {
+    const uint32_t i = wbase + j * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (key[j] >> shift) & 255u;
+      const uint32_t pos = (uint32_t)s_lstart[d] + s_cnt[w][d] + rank[j];
+      s_keys[pos] = key[j];
+      if (PAIRS) s_pay[pos] = FIRST ? (int32_t)i : pay[j];
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < kItems; ++j) {
-    const int64_t i = wbase + j * 32 + lane;
-    if (i < n) {
-      const uint32_t d = (key[j] >> shift) & 255u;
-      const uint32_t pos = offs[(size_t)d * tiles + blockIdx.x] + s_cnt[w][d] + rank[j];
-      keys_out[pos] = key[j];
-      idx_out[pos] = pay[j];
-    }
+  const uint32_t tbase = tile * kSTile;
+  const uint32_t count = n - tbase < (uint32_t)kSTile ? n - tbase : (uint32_t)kSTile;
+  for (uint32_t p = threadIdx.x; p < count; p += kST) {
+    const uint32_t k = s_keys[p];
+    const uint32_t g = s_gbase[(k >> shift) & 255u] + p;
+    if (LAST) static_cast<float*>(keys_out_)[g] = key_to_float(k);
+    else static_cast<uint32_t*>(keys_out_)[g] = k;
+    if (PAIRS) pay_out[g] = s_pay[p];
   }
-}
-
-__global__ void __launch_bounds__(kThreads) keys_to_float_kernel(const uint32_t* __restrict__ keys, int64_t n,
-                                                                 float* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = key_to_float(keys[i]);
 }
 
 // neighbourhood [lo, hi] of sorted point i (|s_j - s_i| <= eps in float64) and the core flag
@@ -188,19 +239,28 @@ __global__ void __launch_bounds__(kThreads) dbscan_noise_kernel(const int32_t* _
 struct SortWs {
   uint32_t* keys[2];
   int32_t* idx[2];
-  uint32_t* hist;
+  uint32_t* zero_begin;   // [ghist 4 x 256 | tile counters 4 (+ pad) | tile state 4 x tiles x 256], cleared per sort
+  size_t zero_bytes;
+  uint32_t* ghist;
+  uint32_t* counters;
+  uint32_t* state;
   size_t total;
 };
 static SortWs carve(void* ws, int64_t n) {
   SortWs s;
   uint8_t* p = static_cast<uint8_t*>(ws);
   const size_t nb = align_up((size_t)(n > 0 ? n : 1) * 4, 256);
-  const int64_t tiles = ceil_div(n > 0 ? n : 1, kTile);
+  const int64_t tiles = ceil_div(n > 0 ? n : 1, kSTile);
   s.keys[0] = reinterpret_cast<uint32_t*>(p); p += nb;
   s.keys[1] = reinterpret_cast<uint32_t*>(p); p += nb;
   s.idx[0] = reinterpret_cast<int32_t*>(p); p += nb;
   s.idx[1] = reinterpret_cast<int32_t*>(p); p += nb;
-  s.hist = reinterpret_cast<uint32_t*>(p); p += align_up((size_t)tiles * 256 * 4, 256);
+  s.zero_begin = reinterpret_cast<uint32_t*>(p);
+  s.ghist = s.zero_begin;
+  s.counters = s.ghist + 1024;
+  s.state = s.counters + 64;
+  s.zero_bytes = (size_t)(1024 + 64 + 4 * tiles * 256) * 4;
+  p += align_up(s.zero_bytes, 256);
   s.total = (size_t)(p - static_cast<uint8_t*>(ws));
   return s;
 }
@@ -212,18 +272,34 @@ static int grid1d(int64_t n) {
   return (int)(b < 1 ? 1 : b);
 }
 
-// sorts into keys[0]/idx[0] (4 passes ping-pong back to buffer 0)
-static int sort_keys(const float* v, int64_t n, SortWs& s, cudaStream_t st) {
-  const int tiles = (int)ceil_div(n, kTile);
-  keys_init_kernel<<<grid1d(n), kThreads, 0, st>>>(v, n, s.keys[0], s.idx[0]);
+template <bool FIRST, bool LAST>
+static void launch_pass(bool pairs, int tiles, cudaStream_t st, const void* kin, const int32_t* pin, uint32_t n, int shift,
+                        const uint32_t* ghist, uint32_t* state, uint32_t* counter, void* kout, int32_t* pout) {
+  if (pairs) onesweep_kernel<FIRST, LAST, true><<<tiles, kST, 0, st>>>(kin, pin, n, shift, ghist, state, counter, kout, pout);
+  else onesweep_kernel<FIRST, LAST, false><<<tiles, kST, 0, st>>>(kin, pin, n, shift, ghist, state, counter, kout, pout);
+}
+
+// Sorts v ascending (NaN last, stable).  sorted_out (floats) and / or order_out (original indices) may be null; they
+// must not alias the workspace buffers keys[0] / idx[0] (the last pass reads those).
+static int sort_keys(const float* v, int64_t n, SortWs& s, cudaStream_t st, float* sorted_out, int32_t* order_out) {
+  const int tiles = (int)ceil_div(n, kSTile);
+  const bool pairs = order_out != nullptr;
+  SG_CUDA(cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st));
+  int hb = (int)ceil_div(n, kThreads * 16);
+  const int hcap = state().sm_count * 4;
+  if (hb > hcap) hb = hcap;
+  hist4_kernel<<<hb < 1 ? 1 : hb, kThreads, 0, st>>>(v, n, s.ghist);
   SG_LAUNCH_CHECK();
-  for (int pass = 0; pass < 4; ++pass) {
-    const int src = pass & 1, dst = src ^ 1;
-    hist_kernel<<<tiles, kThreads, 0, st>>>(s.keys[src], n, pass * 8, s.hist, tiles);
-    scan_kernel<<<1, 1024, 0, st>>>(s.hist, (int64_t)tiles * 256);
-    scatter_kernel<<<tiles, kThreads, 0, st>>>(s.keys[src], s.idx[src], n, pass * 8, s.hist, tiles, s.keys[dst], s.idx[dst]);
-    SG_LAUNCH_CHECK();
-  }
+  const uint32_t un = (uint32_t)n;
+  const size_t ts = (size_t)tiles * 256;
+  launch_pass<true, false>(pairs, tiles, st, v, nullptr, un, 0, s.ghist, s.state, s.counters, s.keys[0], s.idx[0]);
+  launch_pass<false, false>(pairs, tiles, st, s.keys[0], s.idx[0], un, 8, s.ghist + 256, s.state + ts, s.counters + 1, s.keys[1], s.idx[1]);
+  launch_pass<false, false>(pairs, tiles, st, s.keys[1], s.idx[1], un, 16, s.ghist + 512, s.state + 2 * ts, s.counters + 2, s.keys[0], s.idx[0]);
+  if (sorted_out)
+    launch_pass<false, true>(pairs, tiles, st, s.keys[0], s.idx[0], un, 24, s.ghist + 768, s.state + 3 * ts, s.counters + 3, sorted_out, order_out);
+  else
+    launch_pass<false, false>(pairs, tiles, st, s.keys[0], s.idx[0], un, 24, s.ghist + 768, s.state + 3 * ts, s.counters + 3, s.keys[1], order_out);
+  SG_LAUNCH_CHECK();
   return SG_OK;
 }
 
@@ -240,18 +316,12 @@ size_t sg_sort_workspace_bytes(int64_t n) {
 int sg_sort_f32(const float* v, int64_t n, float* sorted_out, int32_t* order_out, void* workspace, void* stream) {
   using namespace sg::srt;
   SG_READY();
-  SG_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && workspace, "arguments");
+  SG_REQUIRE(n >= 0 && n <= ((int64_t)1 << 30) && workspace, "arguments (n <= 2^30)");
   if (n == 0) return SG_OK;
   SG_REQUIRE(v != nullptr, "v");
   SG_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
-  cudaStream_t st = sg::as_stream(stream);
   SortWs s = carve(workspace, n);
-  int r = sort_keys(v, n, s, st);
-  if (r != SG_OK) return r;
-  if (sorted_out) keys_to_float_kernel<<<grid1d(n), kThreads, 0, st>>>(s.keys[0], n, sorted_out);
-  if (order_out) SG_CUDA(cudaMemcpyAsync(order_out, s.idx[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-  SG_LAUNCH_CHECK();
-  return SG_OK;
+  return sort_keys(v, n, s, sg::as_stream(stream), sorted_out, order_out);
 }
 
 size_t sg_dbscan1d_workspace_bytes(int64_t n) {
@@ -265,7 +335,7 @@ int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t*
   using namespace sg::srt;
   SG_READY();
   SG_REQUIRE(v && counts_out && workspace, "null pointer");
-  SG_REQUIRE(n >= 1 && n < ((int64_t)1 << 31), "n");
+  SG_REQUIRE(n >= 1 && n <= ((int64_t)1 << 30), "n (1 .. 2^30)");
   SG_REQUIRE(eps >= 0.0 && min_samples >= 1, "eps/min_samples");
   SG_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t st = sg::as_stream(stream);
@@ -282,9 +352,9 @@ int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t*
   unsigned long long* clean = reinterpret_cast<unsigned long long*>(p + 16);
   p += 256;
   void* cws = p;
-  int r = sort_keys(v, n, s, st);
+  int32_t* order = noise_out ? s.idx[1] : nullptr;   // per-sample noise flags need the original positions
+  int r = sort_keys(v, n, s, st, sorted, order);
   if (r != SG_OK) return r;
-  keys_to_float_kernel<<<grid1d(n), kThreads, 0, st>>>(s.keys[0], n, sorted);
   dbscan_core_kernel<<<grid1d(n), kThreads, 0, st>>>(sorted, n, eps, min_samples, lo, hi, core_f);
   SG_LAUNCH_CHECK();
   const float h = 0.5f;
@@ -292,7 +362,7 @@ int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t*
   SG_CUDA(cudaMemsetAsync(clean, 0, 8, st));
   r = sg_compact_indices(core_f, n, half, SG_GT, 0, core_pos, ncore, nullptr, cws, stream);
   if (r != SG_OK) return r;
-  dbscan_noise_kernel<<<grid1d(n), kThreads, 0, st>>>(lo, hi, core_f, core_pos, ncore, s.idx[0], n, noise_out, clean);
+  dbscan_noise_kernel<<<grid1d(n), kThreads, 0, st>>>(lo, hi, core_f, core_pos, ncore, order, n, noise_out, clean);
   SG_LAUNCH_CHECK();
   SG_CUDA(cudaMemcpyAsync(counts_out, clean, 8, cudaMemcpyDeviceToDevice, st));
   return SG_OK;

@@ -226,6 +226,42 @@ def test_device_sort(sb):
         assert np.all(o[1:][same] > o[:-1][same])
 
 
+def test_device_sort_variants(sb):
+    """keys only / order only, several waves of tiles (look-back across finished tiles), degenerate digit distributions."""
+    L = sb._lib
+    lib = L.init(0)
+    st = L.P(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(43)
+    n = (1 << 22) + 12345          # 1028 tiles: more than one wave of 296 CTAs
+    cases = {
+        "lognormal": np.exp(rng.standard_normal(n)).astype(np.float32),
+        "all_equal": np.full(n, 0.25, np.float32),
+        "ascending": np.arange(n, dtype=np.float32) - 1000.0,
+        "descending": -np.arange(n, dtype=np.float32),
+        "few_values": rng.choice(np.array([-1.5, 0.0, -0.0, 3.0, np.inf, -np.inf, np.nan], np.float32), n),
+    }
+    ws = torch.empty(lib.sg_sort_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    for name, v in cases.items():
+        vd = torch.from_numpy(v).cuda()
+        want_order = np.argsort(v, kind="stable")
+        keys = torch.empty(n, dtype=torch.float32, device="cuda")
+        L.check(lib.sg_sort_f32(L.P(vd.data_ptr()), n, L.P(keys.data_ptr()), L.P(0), L.P(ws.data_ptr()), st), name)
+        assert np.array_equal(keys.cpu().numpy(), np.sort(v), equal_nan=True), name
+        order = torch.empty(n, dtype=torch.int32, device="cuda")
+        L.check(lib.sg_sort_f32(L.P(vd.data_ptr()), n, L.P(0), L.P(order.data_ptr()), L.P(ws.data_ptr()), st), name)
+        o = order.cpu().numpy()
+        if name == "few_values":   # -0.0 and +0.0 share a key: compare through the values and check stability
+            assert np.array_equal(v[o], v[want_order], equal_nan=True)
+            same = (v[o][1:] == v[o][:-1]) | (np.isnan(v[o][1:]) & np.isnan(v[o][:-1]))
+            assert np.all(o[1:][same] > o[:-1][same])
+        else:
+            assert np.array_equal(o, want_order), name
+        both_k = torch.empty(n, dtype=torch.float32, device="cuda")
+        both_o = torch.empty(n, dtype=torch.int32, device="cuda")
+        L.check(lib.sg_sort_f32(L.P(vd.data_ptr()), n, L.P(both_k.data_ptr()), L.P(both_o.data_ptr()), L.P(ws.data_ptr()), st), name)
+        assert torch.equal(both_k.view(torch.int32), keys.view(torch.int32)) and torch.equal(both_o, order), name
+
+
 def test_dbscan1d_vs_sklearn(sb):
     rng = np.random.default_rng(42)
     for n, eps, ms in ((50, 0.05, 3), (2000, 0.01, 3), (2000, 0.002, 5), (300, 0.5, 3), (5, 0.1, 3), (20000, 0.0005, 4)):
