@@ -18,10 +18,9 @@ namespace sg {
 namespace srt {
 
 constexpr int kThreads = 256;          // element-wise kernels
-constexpr int kST = 512;               // sort CTA: 16 warps
-constexpr int kSWarps = kST / 32;
-constexpr int kSI = 8;                 // keys per thread
-constexpr int kSTile = kST * kSI;      // 4096 keys per tile
+// Tile = 4096 keys: 256 threads x 16 keys when a payload moves along (3 CTAs / SM at 80 registers), 512 threads x 8 keys
+// for keys alone -- the best of the shapes measured (profiles/r1e_sort_bench.json).
+constexpr int kSortTile = 4096;
 constexpr uint32_t kStAgg = 1u << 30, kStIncl = 2u << 30, kStMask = (1u << 30) - 1;   // tile state: flag | count
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
@@ -87,40 +86,62 @@ __device__ __forceinline__ uint32_t scan256_excl(uint32_t v, uint32_t* s_w) {
 
 // One radix pass.  FIRST: keys_in are the caller's floats and the payload is the element index.  LAST: keys are written
 // back as floats.  Tiles are claimed from an atomic counter, so every predecessor of a tile is running or done and the
-// look-back spin cannot deadlock.
-template <bool FIRST, bool LAST, bool PAIRS>
-__global__ void __launch_bounds__(kST, 2)
+// look-back spin cannot deadlock.  T threads x I keys per thread = one tile.
+constexpr int kLook = 8;   // predecessors read per look-back round trip
+
+template <int T, int I, bool PAIRS>
+struct SweepCfg {
+  static constexpr int kWarps = T / 32;
+  static constexpr int kTile = T * I;
+  static constexpr int kCntBytes = kWarps * 256 * 2;
+  static constexpr int kSmemBytes = kCntBytes + kTile * 4 * (PAIRS ? 2 : 1) + 256 * 4 + 256 * 2 + 64;
+  static constexpr int kRegs = I <= 8 ? 64 : 80;
+  static constexpr int kMinBlocks = 65536 / (T * kRegs);
+};
+
+template <int T, int I, bool FIRST, bool LAST, bool PAIRS>
+__global__ void __launch_bounds__(T, (SweepCfg<T, I, PAIRS>::kMinBlocks))
 onesweep_kernel(const void* __restrict__ keys_in_, const int32_t* __restrict__ pay_in, uint32_t n, int shift,
                 const uint32_t* __restrict__ ghist, uint32_t* __restrict__ tile_state, uint32_t* __restrict__ tile_counter,
                 void* __restrict__ keys_out_, int32_t* __restrict__ pay_out) {
-  __shared__ uint16_t s_cnt[kSWarps][256];   // per-warp digit counts -> per-warp offsets inside the digit
-  __shared__ uint32_t s_keys[kSTile];
-  __shared__ int32_t s_pay[PAIRS ? kSTile : 1];
-  __shared__ uint32_t s_gbase[256];          // global position of the tile's digit run minus its local start
-  __shared__ uint16_t s_lstart[256];
-  __shared__ uint32_t s_w[8];
-  __shared__ uint32_t s_tile;
+  using Cfg = SweepCfg<T, I, PAIRS>;
+  static_assert(T >= 256 && Cfg::kTile == kSortTile && Cfg::kTile <= 65535, "one thread per digit; 16-bit local positions");
+  extern __shared__ __align__(16) uint8_t smem_sort[];
+  uint16_t (*s_cnt)[256] = reinterpret_cast<uint16_t (*)[256]>(smem_sort);   // per-warp digit counts -> offsets in the digit
+  uint32_t* s_keys = reinterpret_cast<uint32_t*>(smem_sort + Cfg::kCntBytes);
+  int32_t* s_pay = reinterpret_cast<int32_t*>(s_keys + Cfg::kTile);
+  uint32_t* s_gbase = reinterpret_cast<uint32_t*>(s_keys + Cfg::kTile * (PAIRS ? 2 : 1));   // global run start - local start
+  uint16_t* s_lstart = reinterpret_cast<uint16_t*>(s_gbase + 256);
+  uint32_t* s_w = reinterpret_cast<uint32_t*>(s_lstart + 256);
+  uint32_t* s_tile = s_w + 8;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-  for (int i = threadIdx.x; i < kSWarps * 256 / 2; i += kST) reinterpret_cast<uint32_t*>(&s_cnt[0][0])[i] = 0;
+  if (threadIdx.x == 0) *s_tile = atomicAdd(tile_counter, 1u);
+  for (int i = threadIdx.x; i < Cfg::kCntBytes / 4; i += T) reinterpret_cast<uint32_t*>(smem_sort)[i] = 0;
   __syncthreads();
-  const uint32_t tile = s_tile;
-  // warp w owns keys [w*256, (w+1)*256) of the tile, visited in 8 rounds of 32 in index order (stability)
-  const uint32_t wbase = tile * kSTile + w * (kSI * 32);
-  uint32_t key[kSI];
-  uint32_t rank[kSI];
+  const uint32_t tile = *s_tile;
+  // warp w owns keys [w*32*I, (w+1)*32*I) of the tile, visited in I rounds of 32 in index order (stability)
+  const uint32_t wbase = tile * Cfg::kTile + w * (I * 32);
+  uint32_t key[I];
+  uint32_t rank[I];
 #pragma unroll
-  for (int j = 0; j < kSI; ++j) {
+  for (int j = 0; j < I; ++j) {
     const uint32_t i = wbase + j * 32 + lane;
     if (FIRST) key[j] = i < n ? float_to_key(static_cast<const float*>(keys_in_)[i]) : 0xFFFFFFFFu;
     else key[j] = i < n ? static_cast<const uint32_t*>(keys_in_)[i] : 0xFFFFFFFFu;
   }
 #pragma unroll
-  for (int j = 0; j < kSI; ++j) {
+  for (int j = 0; j < I; ++j) {
     const bool valid = wbase + j * 32 + lane < n;
     const uint32_t d = (key[j] >> shift) & 255u;
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane) & vmask;
+    // lanes holding the same digit, from 8 bit-plane votes (measured 10-15 % faster per sort than __match_any_sync)
+    unsigned peers = vmask;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
     const unsigned below = peers & ((1u << lane) - 1u);
     const uint32_t before = valid ? s_cnt[w][d] : 0u;
     rank[j] = before + __popc(below);
@@ -129,42 +150,39 @@ onesweep_kernel(const void* __restrict__ keys_in_, const int32_t* __restrict__ p
     __syncwarp();
   }
   __syncthreads();
+  // ---- digit threads: tile counts -> publish, local run starts, first look-back batch in flight ----
+  uint32_t run = 0, gstart = 0, lstart = 0, excl = 0;
+  uint32_t wd[kLook];
+  int64_t t = (int64_t)tile - 1;
+  uint32_t* st = tile_state + (size_t)tile * 256 + threadIdx.x;
   if (threadIdx.x < 256) {
     const int d = threadIdx.x;
-    uint32_t run = 0;
 #pragma unroll
-    for (int ww = 0; ww < kSWarps; ++ww) {
+    for (int ww = 0; ww < Cfg::kWarps; ++ww) {
       const uint32_t c = s_cnt[ww][d];
       s_cnt[ww][d] = (uint16_t)run;
       run += c;
     }
-    uint32_t* st = tile_state + (size_t)tile * 256 + d;
     st_relaxed_u32(st, (tile == 0 ? kStIncl : kStAgg) | run);
-    const uint32_t lstart = scan256_excl(run, s_w);
-    const uint32_t gstart = scan256_excl(ghist[d], s_w);
-    uint32_t excl = 0;
-    for (uint32_t t = tile; t-- > 0;) {
-      const uint32_t* ps = tile_state + (size_t)t * 256 + d;
-      uint32_t wd;
-      do { wd = ld_relaxed_u32(ps); } while ((wd >> 30) == 0u);
-      excl += wd & kStMask;
-      if ((wd >> 30) == 2u) break;
-    }
-    if (tile != 0) st_relaxed_u32(st, kStIncl | (excl + run));
-    s_gbase[d] = gstart + excl - lstart;
+#pragma unroll
+    for (int q = 0; q < kLook; ++q)
+      wd[q] = (t - q >= 0) ? ld_relaxed_u32(tile_state + (size_t)(t - q) * 256 + d) : kStIncl;
+    lstart = scan256_excl(run, s_w);
+    gstart = scan256_excl(ghist[d], s_w);
     s_lstart[d] = (uint16_t)lstart;
   }
   __syncthreads();
-  int32_t pay[PAIRS ? kSI : 1];
+  // ---- all threads: reorder the tile in shared memory (needs only the local starts) while the look-back loads fly ----
+  int32_t pay[PAIRS ? I : 1];
   if (PAIRS && !FIRST) {
 #pragma unroll
-    for (int j = 0; j < kSI; ++j) {
+    for (int j = 0; j < I; ++j) {
       const uint32_t i = wbase + j * 32 + lane;
       pay[j] = i < n ? pay_in[i] : 0;
     }
   }
 #pragma unroll
-  for (int j = 0; j < kSI; ++j) {
+  for (int j = 0; j < I; ++j) {
     const uint32_t i = wbase + j * 32 + lane;
     if (i < n) {
       const uint32_t d = (key[j] >> shift) & 255u;
@@ -173,10 +191,34 @@ onesweep_kernel(const void* __restrict__ keys_in_, const int32_t* __restrict__ p
       if (PAIRS) s_pay[pos] = FIRST ? (int32_t)i : pay[j];
     }
   }
+  // ---- digit threads: finish the look-back.  kLook predecessors per round trip: with ~300 tiles in flight the nearest
+  // tile that knows its inclusive prefix is typically 10-25 tiles back, and one dependent L2 access per tile made
+  // that walk the dominant cost of a pass (profiles/r1e_sort_full.txt: barrier + long-scoreboard stalls).
+  if (threadIdx.x < 256) {
+    const int d = threadIdx.x;
+    bool done = t < 0;
+    while (!done) {
+#pragma unroll
+      for (int q = 0; q < kLook; ++q) {
+        if (done) break;
+        const uint32_t f = wd[q] >> 30;
+        if (f == 0u) break;            // not published yet: re-read from this tile on
+        excl += wd[q] & kStMask;
+        --t;
+        done = (f == 2u);
+      }
+      if (done) break;
+#pragma unroll
+      for (int q = 0; q < kLook; ++q)
+        wd[q] = (t - q >= 0) ? ld_relaxed_u32(tile_state + (size_t)(t - q) * 256 + d) : kStIncl;
+    }
+    if (tile != 0) st_relaxed_u32(st, kStIncl | (excl + run));
+    s_gbase[d] = gstart + excl - lstart;
+  }
   __syncthreads();
-  const uint32_t tbase = tile * kSTile;
-  const uint32_t count = n - tbase < (uint32_t)kSTile ? n - tbase : (uint32_t)kSTile;
-  for (uint32_t p = threadIdx.x; p < count; p += kST) {
+  const uint32_t tbase = tile * Cfg::kTile;
+  const uint32_t count = n - tbase < (uint32_t)Cfg::kTile ? n - tbase : (uint32_t)Cfg::kTile;
+  for (uint32_t p = threadIdx.x; p < count; p += T) {
     const uint32_t k = s_keys[p];
     const uint32_t g = s_gbase[(k >> shift) & 255u] + p;
     if (LAST) static_cast<float*>(keys_out_)[g] = key_to_float(k);
@@ -250,7 +292,7 @@ static SortWs carve(void* ws, int64_t n) {
   SortWs s;
   uint8_t* p = static_cast<uint8_t*>(ws);
   const size_t nb = align_up((size_t)(n > 0 ? n : 1) * 4, 256);
-  const int64_t tiles = ceil_div(n > 0 ? n : 1, kSTile);
+  const int64_t tiles = ceil_div(n > 0 ? n : 1, kSortTile);
   s.keys[0] = reinterpret_cast<uint32_t*>(p); p += nb;
   s.keys[1] = reinterpret_cast<uint32_t*>(p); p += nb;
   s.idx[0] = reinterpret_cast<int32_t*>(p); p += nb;
@@ -272,17 +314,33 @@ static int grid1d(int64_t n) {
   return (int)(b < 1 ? 1 : b);
 }
 
+struct PassArgs {
+  const void* kin; const int32_t* pin; uint32_t n; int shift; const uint32_t* ghist; uint32_t* state; uint32_t* counter;
+  void* kout; int32_t* pout;
+};
 template <bool FIRST, bool LAST>
-static void launch_pass(bool pairs, int tiles, cudaStream_t st, const void* kin, const int32_t* pin, uint32_t n, int shift,
-                        const uint32_t* ghist, uint32_t* state, uint32_t* counter, void* kout, int32_t* pout) {
-  if (pairs) onesweep_kernel<FIRST, LAST, true><<<tiles, kST, 0, st>>>(kin, pin, n, shift, ghist, state, counter, kout, pout);
-  else onesweep_kernel<FIRST, LAST, false><<<tiles, kST, 0, st>>>(kin, pin, n, shift, ghist, state, counter, kout, pout);
+static void launch_pass(bool pairs, int tiles, cudaStream_t st, const PassArgs& a) {
+  if (pairs)
+    onesweep_kernel<256, 16, FIRST, LAST, true><<<tiles, 256, SweepCfg<256, 16, true>::kSmemBytes, st>>>(
+        a.kin, a.pin, a.n, a.shift, a.ghist, a.state, a.counter, a.kout, a.pout);
+  else
+    onesweep_kernel<512, 8, FIRST, LAST, false><<<tiles, 512, SweepCfg<512, 8, false>::kSmemBytes, st>>>(
+        a.kin, a.pin, a.n, a.shift, a.ghist, a.state, a.counter, a.kout, a.pout);
+}
+
+template <bool FIRST, bool LAST>
+static int set_attrs() {
+  SG_CUDA(cudaFuncSetAttribute(onesweep_kernel<256, 16, FIRST, LAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               SweepCfg<256, 16, true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(onesweep_kernel<512, 8, FIRST, LAST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               SweepCfg<512, 8, false>::kSmemBytes));
+  return SG_OK;
 }
 
 // Sorts v ascending (NaN last, stable).  sorted_out (floats) and / or order_out (original indices) may be null; they
 // must not alias the workspace buffers keys[0] / idx[0] (the last pass reads those).
 static int sort_keys(const float* v, int64_t n, SortWs& s, cudaStream_t st, float* sorted_out, int32_t* order_out) {
-  const int tiles = (int)ceil_div(n, kSTile);
+  const int tiles = (int)ceil_div(n, kSortTile);
   const bool pairs = order_out != nullptr;
   SG_CUDA(cudaMemsetAsync(s.zero_begin, 0, s.zero_bytes, st));
   int hb = (int)ceil_div(n, kThreads * 16);
@@ -292,13 +350,13 @@ static int sort_keys(const float* v, int64_t n, SortWs& s, cudaStream_t st, floa
   SG_LAUNCH_CHECK();
   const uint32_t un = (uint32_t)n;
   const size_t ts = (size_t)tiles * 256;
-  launch_pass<true, false>(pairs, tiles, st, v, nullptr, un, 0, s.ghist, s.state, s.counters, s.keys[0], s.idx[0]);
-  launch_pass<false, false>(pairs, tiles, st, s.keys[0], s.idx[0], un, 8, s.ghist + 256, s.state + ts, s.counters + 1, s.keys[1], s.idx[1]);
-  launch_pass<false, false>(pairs, tiles, st, s.keys[1], s.idx[1], un, 16, s.ghist + 512, s.state + 2 * ts, s.counters + 2, s.keys[0], s.idx[0]);
+  launch_pass<true, false>(pairs, tiles, st, PassArgs{v, nullptr, un, 0, s.ghist, s.state, s.counters, s.keys[0], s.idx[0]});
+  launch_pass<false, false>(pairs, tiles, st, PassArgs{s.keys[0], s.idx[0], un, 8, s.ghist + 256, s.state + ts, s.counters + 1, s.keys[1], s.idx[1]});
+  launch_pass<false, false>(pairs, tiles, st, PassArgs{s.keys[1], s.idx[1], un, 16, s.ghist + 512, s.state + 2 * ts, s.counters + 2, s.keys[0], s.idx[0]});
   if (sorted_out)
-    launch_pass<false, true>(pairs, tiles, st, s.keys[0], s.idx[0], un, 24, s.ghist + 768, s.state + 3 * ts, s.counters + 3, sorted_out, order_out);
+    launch_pass<false, true>(pairs, tiles, st, PassArgs{s.keys[0], s.idx[0], un, 24, s.ghist + 768, s.state + 3 * ts, s.counters + 3, sorted_out, order_out});
   else
-    launch_pass<false, false>(pairs, tiles, st, s.keys[0], s.idx[0], un, 24, s.ghist + 768, s.state + 3 * ts, s.counters + 3, s.keys[1], order_out);
+    launch_pass<false, false>(pairs, tiles, st, PassArgs{s.keys[0], s.idx[0], un, 24, s.ghist + 768, s.state + 3 * ts, s.counters + 3, s.keys[1], order_out});
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -307,6 +365,14 @@ static int sort_keys(const float* v, int64_t n, SortWs& s, cudaStream_t st, floa
 }  // namespace sg
 
 extern "C" {
+
+int sg_sort_init_attributes() {
+  using namespace sg::srt;
+  int r = set_attrs<true, false>();
+  if (r == SG_OK) r = set_attrs<false, false>();
+  if (r == SG_OK) r = set_attrs<false, true>();
+  return r;
+}
 
 size_t sg_sort_workspace_bytes(int64_t n) {
   sg::srt::SortWs s = sg::srt::carve(nullptr, n);
