@@ -227,49 +227,57 @@ onesweep_kernel(const void* __restrict__ keys_in_, const int32_t* __restrict__ p
   }
 }
 
-// neighbourhood [lo, hi] of sorted point i (|s_j - s_i| <= eps in float64) and the core flag
+// Neighbourhood [lo, hi] of sorted point i: |s_j - s_i| <= eps evaluated in float64 (as scikit-learn does).  The window
+// is found by galloping outwards from i (1, 2, 4, ... steps, then a binary search inside the last interval): O(log
+// window) neighbouring, cache-resident loads instead of 2 x log2(n) dependent loads across the whole array.
+__device__ __forceinline__ void dbscan_window(const float* __restrict__ s, int64_t n, int64_t i, double eps, int64_t& lo, int64_t& hi) {
+  const double x = (double)s[i];
+  int64_t a, b = i;                       // first j in [0, i] with x - s[j] <= eps (b: known inside, or i itself)
+  for (int64_t step = 1;; step <<= 1) {
+    a = b - step;
+    if (a < 0) { a = 0; break; }
+    if (x - (double)s[a] <= eps) b = a; else { a = a + 1; break; }
+  }
+  while (a < b) {
+    const int64_t m = (a + b) >> 1;
+    if (x - (double)s[m] <= eps) b = m; else a = m + 1;
+  }
+  lo = a;
+  a = i;                                  // last j in [i, n-1] with s[j] - x <= eps
+  for (int64_t step = 1;; step <<= 1) {
+    b = a + step;
+    if (b > n - 1) { b = n - 1; break; }
+    if ((double)s[b] - x <= eps) a = b; else { b = b - 1; break; }
+  }
+  while (a < b) {
+    const int64_t m = (a + b + 1) >> 1;
+    if ((double)s[m] - x <= eps) a = m; else b = m - 1;
+  }
+  hi = a;
+}
+
 __global__ void __launch_bounds__(kThreads) dbscan_core_kernel(const float* __restrict__ s, int64_t n, double eps,
-                                                               int min_samples, int32_t* __restrict__ lo_out,
-                                                               int32_t* __restrict__ hi_out, float* __restrict__ core_f) {
+                                                               int min_samples, uint8_t* __restrict__ core) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double x = (double)s[i];
-    int64_t a = 0, b = i;  // first j in [0, i] with x - s[j] <= eps
-    while (a < b) {
-      const int64_t m = (a + b) >> 1;
-      if (x - (double)s[m] <= eps) b = m; else a = m + 1;
-    }
-    const int64_t lo = a;
-    a = i; b = n - 1;      // last j in [i, n-1] with s[j] - x <= eps
-    while (a < b) {
-      const int64_t m = (a + b + 1) >> 1;
-      if ((double)s[m] - x <= eps) a = m; else b = m - 1;
-    }
-    const int64_t hi = a;
-    lo_out[i] = (int32_t)lo;
-    hi_out[i] = (int32_t)hi;
-    core_f[i] = (hi - lo + 1 >= min_samples) ? 1.0f : 0.0f;
+    int64_t lo, hi;
+    dbscan_window(s, n, i, eps, lo, hi);
+    core[i] = (hi - lo + 1 >= min_samples) ? 1 : 0;
   }
 }
 
-// noise(i) = not core and no core position within [lo, hi]; core_pos ascending (ncore entries)
-__global__ void __launch_bounds__(kThreads) dbscan_noise_kernel(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,
-                                                                const float* __restrict__ core_f,
-                                                                const int64_t* __restrict__ core_pos,
-                                                                const int64_t* __restrict__ ncore_p,
-                                                                const int32_t* __restrict__ order, int64_t n,
+// noise(i) = not core and no core point inside its window.  A non-core point has fewer than min_samples points in its
+// window, so the window is simply walked (no compaction of the core positions, no second search).
+__global__ void __launch_bounds__(kThreads) dbscan_noise_kernel(const float* __restrict__ s, const uint8_t* __restrict__ core,
+                                                                const int32_t* __restrict__ order, int64_t n, double eps,
                                                                 uint8_t* __restrict__ noise_out,
                                                                 unsigned long long* __restrict__ clean_count) {
-  const int64_t ncore = *ncore_p;
   unsigned local = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    bool clean = core_f[i] != 0.0f;
-    if (!clean && ncore > 0) {
-      int64_t a = 0, b = ncore;  // first core position >= lo[i]
-      while (a < b) {
-        const int64_t m = (a + b) >> 1;
-        if (core_pos[m] >= lo[i]) b = m; else a = m + 1;
-      }
-      clean = (a < ncore) && (core_pos[a] <= hi[i]);
+    bool clean = core[i] != 0;
+    if (!clean) {
+      int64_t lo, hi;
+      dbscan_window(s, n, i, eps, lo, hi);
+      for (int64_t j = lo; j <= hi && !clean; ++j) clean = core[j] != 0;
     }
     if (noise_out) noise_out[order[i]] = clean ? 0 : 1;
     local += clean ? 1u : 0u;
@@ -392,8 +400,7 @@ int sg_sort_f32(const float* v, int64_t n, float* sorted_out, int32_t* order_out
 
 size_t sg_dbscan1d_workspace_bytes(int64_t n) {
   const size_t nn = (size_t)(n > 0 ? n : 1);
-  return sg_sort_workspace_bytes(n) + sg::align_up(nn * 4, 256) * 4 + sg::align_up(nn * 8, 256) + 256 +
-         sg_compact_workspace_bytes(n);
+  return sg_sort_workspace_bytes(n) + sg::align_up(nn * 4, 256) + sg::align_up(nn, 256) + 256;
 }
 
 int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t* counts_out, uint8_t* noise_out,
@@ -407,28 +414,15 @@ int sg_dbscan1d(const float* v, int64_t n, double eps, int min_samples, int64_t*
   cudaStream_t st = sg::as_stream(stream);
   SortWs s = carve(workspace, n);
   uint8_t* p = static_cast<uint8_t*>(workspace) + sg::align_up(s.total, 256);
-  const size_t nb4 = sg::align_up((size_t)n * 4, 256);
-  float* sorted = reinterpret_cast<float*>(p); p += nb4;
-  int32_t* lo = reinterpret_cast<int32_t*>(p); p += nb4;
-  int32_t* hi = reinterpret_cast<int32_t*>(p); p += nb4;
-  float* core_f = reinterpret_cast<float*>(p); p += nb4;
-  int64_t* core_pos = reinterpret_cast<int64_t*>(p); p += sg::align_up((size_t)n * 8, 256);
-  int64_t* ncore = reinterpret_cast<int64_t*>(p);
-  float* half = reinterpret_cast<float*>(p + 8);
-  unsigned long long* clean = reinterpret_cast<unsigned long long*>(p + 16);
-  p += 256;
-  void* cws = p;
+  float* sorted = reinterpret_cast<float*>(p); p += sg::align_up((size_t)n * 4, 256);
+  uint8_t* core = p; p += sg::align_up((size_t)n, 256);
+  unsigned long long* clean = reinterpret_cast<unsigned long long*>(p);
   int32_t* order = noise_out ? s.idx[1] : nullptr;   // per-sample noise flags need the original positions
   int r = sort_keys(v, n, s, st, sorted, order);
   if (r != SG_OK) return r;
-  dbscan_core_kernel<<<grid1d(n), kThreads, 0, st>>>(sorted, n, eps, min_samples, lo, hi, core_f);
-  SG_LAUNCH_CHECK();
-  const float h = 0.5f;
-  SG_CUDA(cudaMemcpyAsync(half, &h, 4, cudaMemcpyHostToDevice, st));
   SG_CUDA(cudaMemsetAsync(clean, 0, 8, st));
-  r = sg_compact_indices(core_f, n, half, SG_GT, 0, core_pos, ncore, nullptr, cws, stream);
-  if (r != SG_OK) return r;
-  dbscan_noise_kernel<<<grid1d(n), kThreads, 0, st>>>(lo, hi, core_f, core_pos, ncore, order, n, noise_out, clean);
+  dbscan_core_kernel<<<grid1d(n), kThreads, 0, st>>>(sorted, n, eps, min_samples, core);
+  dbscan_noise_kernel<<<grid1d(n), kThreads, 0, st>>>(sorted, core, order, n, eps, noise_out, clean);
   SG_LAUNCH_CHECK();
   SG_CUDA(cudaMemcpyAsync(counts_out, clean, 8, cudaMemcpyDeviceToDevice, st));
   return SG_OK;

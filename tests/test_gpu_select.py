@@ -273,6 +273,17 @@ def test_dbscan1d_vs_sklearn(sb):
     v = np.round(O.synth_losses(3000, seed=3), 2)      # heavy ties, distances exactly == eps
     ratio, noise = sb.dbscan1d_clean_ratio(v, 0.01, 3, return_noise=True)
     assert np.array_equal(noise.cpu().numpy(), O.dbscan1d_noise_sklearn(v, 0.01, 3))
+    # many tiles, windows from 1 to tens of thousands of points, ties, huge magnitudes (scikit-learn rejects inf / NaN
+    # inputs); oracle: the sort-based numpy form, itself checked against scikit-learn in tests/test_oracle_golden.py
+    big = np.concatenate([O.synth_losses(300_000, seed=9), np.full(5000, 0.5, np.float32),
+                          np.array([3e38, 3e38, -3e38, 1e30, -1e30], np.float32)])
+    rng.shuffle(big)
+    for eps, ms in ((1e-6, 3), (1e-4, 50), (0.0, 2), (3.0, 100)):
+        ratio, noise = sb.dbscan1d_clean_ratio(big, eps, ms, return_noise=True)
+        want = O.dbscan1d_noise(big, eps, ms)
+        assert np.array_equal(noise.cpu().numpy(), want), (eps, ms)
+        assert ratio == np.sum(~want) / big.size
+        assert sb.dbscan1d_clean_ratio(big, eps, ms) == ratio      # keys-only sort path (no per-sample flags)
     # z-score + 1-D DBSCAN straining (config 3): clean_ratio -> torch.quantile(max_z, ratio), <=
     mz = O.zscore_max_torch(torch.from_numpy(O.synth_features(4096)))
     r = sb.dbscan1d_clean_ratio(mz, 0.05, 3)
