@@ -88,7 +88,7 @@ def run_reference(args, rank, world):
     from oracle import strainer_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 4096
+    sample = int(os.environ.get("SG_BENCH_REF_SAMPLES", "4096"))   # bounded sample of the workload per step
     x = torch.from_numpy(O.synth_images(0, sample))
     netD = O.make_discriminator(O.SEED)
     for _ in range(max(args.warmup, 1)):
@@ -110,6 +110,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    global CHUNK
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -129,7 +130,6 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
-    global CHUNK
     CHUNK = args.chunk
 
     import numpy as np

@@ -77,3 +77,30 @@ def test_f32_threshold_directed_rounding(sb):
         assert np.array_equal(v <= f(t, 1), v <= t)
         assert np.array_equal(v >= f(t, 2), v >= t)
         assert np.array_equal(v > f(t, 3), v > t)
+
+
+def test_entry_scripts_compile():
+    """bench.py, __graft_entry__.py and the tools byte-compile (a `global` after use is a SyntaxError only at compile time)."""
+    import glob
+    import os
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "tools", "*.py")):
+        py_compile.compile(path, doraise=True)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` is pure CPU (oracle port): one tiny step must print a JSON line with the contract keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SG_BENCH_REF_SAMPLES="128")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "strained_samples_per_sec"
+    for k in ("value", "unit", "cpu_baseline", "e2e", "config", "higher_is_better"):
+        assert k in line
