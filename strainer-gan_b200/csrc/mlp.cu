@@ -52,49 +52,59 @@ __global__ void __launch_bounds__(256) linear_lrelu_kernel(const float* __restri
   }
 }
 
-// Small-batch form (the reference's B = 64): weight-stationary.  One warp per output feature keeps its weight row in
-// registers (in_f / 32 values per lane), streams the <= 128 batch rows (shared by the 8 warps of the CTA through L1)
-// and reduces each dot product with shuffles.  out_f / 8 CTAs instead of out_f / 64: the chain is latency bound and
-// this form has 8x the CTAs and no shared-memory barriers in its K loop.
-template <int KPL>   // ceil(in_f / 32) values per lane
+// Small-batch form (the reference's B = 64; any B <= 128), latency bound: one CTA = 8 output features.  Their weight rows
+// (<= 32 KB) are loaded into shared memory once, in one round trip; warp w then takes batch rows w, w + 8, ...: the row
+// is read with 128-bit loads straight into registers (all loads of TWO rows in flight together), multiplied against the
+// 8 weight rows (conflict-free 128-bit shared-memory reads) and reduced with shuffles.  One dependent L2 round trip per
+// pair of rows and no barrier in the loop.  (Earlier forms: weight row in registers + batch rows one by one through L1,
+// 60 us per layer at B = 64; x staged through shared memory in 64-wide K chunks, 30 us per layer.)
+template <int KV>   // 128-bit words per lane and row: ceil(in_f / 128)
 __global__ void __launch_bounds__(256) linear_lrelu_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, float* __restrict__ y,
                                                                  int batch, int in_f, int out_f, float slope) {
-  const int lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (o >= out_f) return;
-  float wr[KPL];
-#pragma unroll
-  for (int i = 0; i < KPL; ++i) {
-    const int k = lane + 32 * i;
-    wr[i] = k < in_f ? __ldg(w + (size_t)o * in_f + k) : 0.f;
+  __shared__ float4 sw4[8 * KV * 32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int o0 = blockIdx.x * 8;
+  for (int idx = threadIdx.x; idx < 8 * KV * 32; idx += 256) {
+    const int ol = idx / (KV * 32), k = 4 * (idx - ol * (KV * 32));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < in_f && o0 + ol < out_f) v = __ldg(reinterpret_cast<const float4*>(w + (size_t)(o0 + ol) * in_f + k));
+    sw4[idx] = v;
   }
-  const float bo = __ldg(bias + o);
-  for (int b = 0; b < batch; b += 2) {
-    const float* x0 = x + (size_t)b * in_f;
-    const bool two = b + 1 < batch;
-    const float* x1 = two ? x0 + in_f : x0;
-    float a0 = 0.f, a1 = 0.f;
+  __syncthreads();
+  float bo[8];
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < in_f) {
-        a0 = fmaf(x0[k], wr[i], a0);
-        a1 = fmaf(x1[k], wr[i], a1);
-      }
-    }
+  for (int o = 0; o < 8; ++o) bo[o] = o0 + o < out_f ? __ldg(bias + o0 + o) : 0.f;
+  for (int b = wp; b < batch; b += 16) {
+    const int b1 = b + 8;
+    float4 xa[KV], xb[KV];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, s);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+    for (int i = 0; i < KV; ++i) {
+      const int k = 4 * (lane + 32 * i);
+      xa[i] = k < in_f ? __ldg(reinterpret_cast<const float4*>(x + (size_t)b * in_f + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[i] = (k < in_f && b1 < batch) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)b1 * in_f + k))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (lane == 0) {
-      float v = a0 + bo;
-      y[(size_t)b * out_f + o] = v > 0.f ? v : slope * v;
-      if (two) {
-        v = a1 + bo;
-        y[(size_t)(b + 1) * out_f + o] = v > 0.f ? v : slope * v;
+    float ra = 0.f, rb = 0.f;   // lane o keeps output o of both rows
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        const float4 wv = sw4[o * KV * 32 + lane + 32 * i];
+        a0 = fmaf(xa[i].x, wv.x, a0); a0 = fmaf(xa[i].y, wv.y, a0); a0 = fmaf(xa[i].z, wv.z, a0); a0 = fmaf(xa[i].w, wv.w, a0);
+        a1 = fmaf(xb[i].x, wv.x, a1); a1 = fmaf(xb[i].y, wv.y, a1); a1 = fmaf(xb[i].z, wv.z, a1); a1 = fmaf(xb[i].w, wv.w, a1);
       }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, sft);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, sft);
+      }
+      if (lane == o) { ra = a0 + bo[o]; rb = a1 + bo[o]; }
+    }
+    if (lane < 8 && o0 + lane < out_f) {
+      y[(size_t)b * out_f + o0 + lane] = ra > 0.f ? ra : slope * ra;
+      if (b1 < batch) y[(size_t)b1 * out_f + o0 + lane] = rb > 0.f ? rb : slope * rb;
     }
   }
 }
@@ -143,11 +153,11 @@ int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, vo
   const float* in = x;
   float* outs[3] = {h1, h2, h3};
   for (int l = 0; l < 3; ++l) {
-    if (batch <= 128) {
+    if (batch <= 128 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {   // 128-bit row loads
       const unsigned g = (unsigned)sg::ceil_div(dims[l + 1], 8);
-      if (l == 0) linear_lrelu_small_kernel<25><<<g, 256, 0, st>>>(in, h_params[0], h_params[1], outs[0], (int)batch, 784, 1024, 0.2f);
-      else if (l == 1) linear_lrelu_small_kernel<32><<<g, 256, 0, st>>>(in, h_params[2], h_params[3], outs[1], (int)batch, 1024, 512, 0.2f);
-      else linear_lrelu_small_kernel<16><<<g, 256, 0, st>>>(in, h_params[4], h_params[5], outs[2], (int)batch, 512, 256, 0.2f);
+      if (l == 0) linear_lrelu_small_kernel<7><<<g, 256, 0, st>>>(in, h_params[0], h_params[1], outs[0], (int)batch, 784, 1024, 0.2f);
+      else if (l == 1) linear_lrelu_small_kernel<8><<<g, 256, 0, st>>>(in, h_params[2], h_params[3], outs[1], (int)batch, 1024, 512, 0.2f);
+      else linear_lrelu_small_kernel<4><<<g, 256, 0, st>>>(in, h_params[4], h_params[5], outs[2], (int)batch, 512, 256, 0.2f);
       SG_LAUNCH_CHECK();
       in = outs[l];
       continue;

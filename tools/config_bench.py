@@ -133,6 +133,12 @@ def main():
     mlpd.load_state_dict(mlp.state_dict())
     t = gpu_time(lambda: sb.strain_batch(mlpd, x28d, 0.1), a.iters)
     c1 = {"batch": 64, "gpu_us_per_batch": t * 1e6, "gpu_samples_per_s": 64 / t}
+    msc = sb.get_mlp_scorer(mlpd, dev, max_batch=512)
+    pr = torch.empty(64, device=dev)
+    xf = x28d.reshape(64, -1)
+    c1["gpu_us_mlp_scoring_only"] = gpu_time(lambda: msc.score_into(xf, None, pr, None), 200, 20) * 1e6
+    c1["gpu_us_strain_scores_only"] = gpu_time(lambda: sb.strain_scores(x28d, pr, 0.1), 200, 20) * 1e6
+    c1["gpu_us_per_batch_200_iters"] = gpu_time(lambda: sb.strain_batch(mlpd, x28d, 0.1), 200, 20) * 1e6
     if not a.no_cpu:
         tc = cpu_time(lambda: O.strain_batch(mlp, x28.reshape(64, -1), 0.1), 20, 3)
         c1.update(cpu_us_per_batch=tc * 1e6, cpu_samples_per_s=64 / tc)
