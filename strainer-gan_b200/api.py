@@ -721,20 +721,23 @@ class ResidentSubset:
     ``indices`` are ascending (the reference's ``np.where`` order); ``batches(shuffle=False)`` therefore yields
     exactly ``DataLoader(Subset(dataset, clean_indices), batch_size, shuffle=False)``'s image batches."""
 
-    def __init__(self, images: torch.Tensor, indices: torch.Tensor, threshold=None):
-        if not images.is_cuda:
-            raise ValueError("ResidentSubset keeps the dataset in HBM: pass a CUDA tensor")
-        self.images = images.contiguous()
-        self.indices = indices.to(device=images.device, dtype=torch.int64).contiguous()
+    def __init__(self, images, indices: torch.Tensor, threshold=None):
+        # a U8Images keeps the resident rows uint8 (12 288 B per sample); batches are normalised after the gather
+        self.u8 = images if isinstance(images, U8Images) else None
+        rows = images.pixels if self.u8 is not None else images
+        if not rows.is_cuda:
+            raise ValueError("ResidentSubset keeps the dataset in HBM: pass a CUDA tensor (or a U8Images of one)")
+        self.images = rows.contiguous()
+        self.indices = indices.to(device=rows.device, dtype=torch.int64).contiguous()
         self.threshold = threshold
 
     def __len__(self):
         return int(self.indices.numel())
 
     @classmethod
-    def refine(cls, images: torch.Tensor, discriminator, loss_ratio=0.2, *, conv_mode: str = "fp32"):
+    def refine(cls, images, discriminator, loss_ratio=0.2, *, conv_mode: str = "fp32"):
         """``refine_dataset_by_loss`` ("#strainer gan.py:364-392") without leaving the device."""
-        device = _dev(images.device)
+        device = _dev(images.pixels.device if isinstance(images, U8Images) else images.device)
         discriminator.eval()
         losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
         thr = percentile_device(losses, (1 - loss_ratio) * 100)
@@ -760,6 +763,8 @@ class ResidentSubset:
             out = torch.empty((idx.numel(),) + tuple(self.images.shape[1:]), dtype=self.images.dtype, device=device)
             L.check(lib.sg_gather_rows(_p(self.images), row_bytes, _p(idx), idx.numel(), L.P(0), _p(out), _stream()),
                     "sg_gather_rows")
+            if self.u8 is not None:
+                out = self.u8.normalize_into(out, torch.empty((idx.numel(),) + self.u8.chw, dtype=torch.float32, device=device))
             yield out
 
 

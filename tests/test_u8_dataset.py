@@ -123,3 +123,24 @@ def test_autoencoder_u8_dataset(sb):
     m8 = sb.detect_outliers_autoencoder(ae, ds8, "cuda")
     m32 = sb.detect_outliers_autoencoder(ae, torch.utils.data.TensorDataset(x32, torch.zeros(n)), "cuda")
     assert torch.equal(m8, m32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+def test_resident_subset_u8(sb, layout):
+    """Device-resident epochs over uint8 rows: same kept set as the fp32 resident dataset, batches = gather + normalise."""
+    n = 200
+    netD = O.make_discriminator(O.SEED)
+    px = np.clip(np.rint((O.synth_images(50, n) + 1.0) * 127.5), 0, 255).astype(np.uint8)
+    x32 = torch.from_numpy(host_transform(px, (0.5,) * 3, (0.5,) * 3)).cuda()
+    src = px if layout == "NCHW" else np.ascontiguousarray(px.transpose(0, 2, 3, 1))
+    u8 = sb.U8Images(torch.from_numpy(src).cuda(), layout=layout)
+    s8 = sb.ResidentSubset.refine(u8, netD, 0.2)
+    s32 = sb.ResidentSubset.refine(x32, netD, 0.2)
+    assert torch.equal(s8.indices, s32.indices) and torch.equal(s8.threshold, s32.threshold)
+    b8 = list(s8.batches(64, shuffle=False))
+    b32 = list(s32.batches(64, shuffle=False))
+    assert len(b8) == len(b32) and all(torch.equal(a, b) for a, b in zip(b8, b32))
+    g8, g32 = torch.Generator(device="cuda").manual_seed(3), torch.Generator(device="cuda").manual_seed(3)
+    for a, b in zip(s8.batches(32, generator=g8), s32.batches(32, generator=g32)):
+        assert a.dtype == torch.float32 and torch.equal(a, b)
