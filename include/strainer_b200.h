@@ -49,7 +49,10 @@ typedef enum SgLerp {
 /* arithmetic of the discriminator convolutions */
 typedef enum SgConvMode {
   SG_CONV_BF16 = 0,   /* bf16 operands, fp32 accumulate (1 tcgen05 pass) */
-  SG_CONV_BF16X3 = 1  /* fp32-parity mode: bf16 hi/lo split, 3 tcgen05 passes (hi*hi+lo*hi+hi*lo) */
+  SG_CONV_BF16X3 = 1, /* fp32-parity mode: bf16 hi/lo split, 3 tcgen05 passes (hi*hi+lo*hi+hi*lo) */
+  SG_CONV_FP16 = 2    /* fp16 operands and activations, fp32 accumulate, 1 pass: 11-bit significands keep the losses within
+                         1e-3 of fp32 (the north_star's fp32 bar) at the bf16 mode's speed; needs |activation| < 65504.
+                         sg_d64_* only (the auto-encoder entry points take SG_CONV_BF16 / SG_CONV_BF16X3) */
 } SgConvMode;
 
 /* memory layout of a uint8 image batch */
@@ -108,7 +111,8 @@ int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* wo
                      float* logit, float* prob, float* loss, void* stream);
 /* debugging / tests: copies the activation of layer `layer` (1..4) of the last sg_d64_score call
  * on `workspace` into fp32 NCHW `out` ([batch,64,32,32], [batch,128,16,16], ...). */
-/* Synchronises `stream` and reports a pipeline time-out recorded by the conv kernels (tests). */
+/* Synchronises `stream` and reports a pipeline time-out recorded by the conv kernels (tests) or, in SG_CONV_FP16
+ * mode, a non-finite logit (an activation overflowed fp16; SG_EINVAL, sticky since the last check). */
 int sg_d64_check(const void* workspace, void* stream);
 int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, int layer, float* out,
                            void* stream);

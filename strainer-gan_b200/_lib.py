@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libstrainer_b200.so")
 SG_LT, SG_LE, SG_GE, SG_GT = 0, 1, 2, 3
 SG_NOT = 4  # OR-ed into a comparison: logical negation (NaN-correct complement)
 SG_LERP_NUMPY, SG_LERP_TORCH = 0, 1
-SG_CONV_BF16, SG_CONV_BF16X3 = 0, 1
+SG_CONV_BF16, SG_CONV_BF16X3, SG_CONV_FP16 = 0, 1, 2
 SG_LAYOUT_NCHW, SG_LAYOUT_NHWC = 0, 1
 SG_SELECT_WS_WORDS = 2048
 SG_SELECT_WS_NANCOUNT = 256

@@ -21,6 +21,7 @@
 // (hi = rn(x), lo = rn(x - hi)); the GEMM runs three K-segments per (tap, channel chunk):
 // A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, i.e. a 3x longer K loop through the same kernel.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -33,6 +34,25 @@ namespace d64 {
 using namespace ptx;
 
 constexpr int kErrProducer = 1, kErrMma = 2, kErrMmaAcc = 3, kErrEpilogue = 4;
+constexpr int kFp16OverflowMagic = 0x46503136;   // workspace word 1 (sticky until sg_d64_check reads it)
+
+// 16-bit operand format of the single-segment modes: bf16 (SG_CONV_BF16) or fp16 (SG_CONV_FP16: 11-bit significand,
+// losses within 1e-3 of fp32 in ONE tensor pass; activations must stay below 65504).  Same kernels, same shared
+// memory / TMA layouts; only the fp32 <-> 16-bit conversions and the MMA instruction descriptor differ.
+template <bool HALF> __device__ __forceinline__ uint16_t act_pack1(float a) {
+  return HALF ? __half_as_ushort(__float2half_rn(a)) : __bfloat16_as_ushort(__float2bfloat16_rn(a));
+}
+template <bool HALF> __device__ __forceinline__ uint32_t act_pack2(float a, float b) {   // a in the low half
+  if (HALF) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float act_unpack(uint16_t u, bool half) {
+  return half ? __half2float(__ushort_as_half(u)) : __uint_as_float((uint32_t)u << 16);
+}
+__device__ __forceinline__ uint16_t act_pack_rt(float a, bool half) {
+  return half ? __half_as_ushort(__float2half_rn(a)) : __bfloat16_as_ushort(__float2bfloat16_rn(a));
+}
 constexpr int kBnBlocks = 256;              // fixed row partition of the train-mode BN reduction
 
 // ------------------------------------------------------------------------------------------
@@ -97,9 +117,10 @@ struct PackAllArgs {
   float *o1, *o5, *ss[3], *gb[3], *ident;
   float eps;
   int nseg;
+  int half;   // SG_CONV_FP16: 16-bit weights are fp16 (nseg == 1)
 };
 __device__ __forceinline__ void pack_conv_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int nseg,
-                                               int64_t i) {
+                                               int64_t i, bool half) {
   const int nchunk = cin >> 6;
   const int64_t kprime = (int64_t)16 * nchunk * nseg * 64;
   const int co = (int)(i / kprime);
@@ -109,6 +130,7 @@ __device__ __forceinline__ void pack_conv_elem(const float* __restrict__ w, __nv
   const int chunk = (int)(r % nchunk);
   const int tap = (int)(r / nchunk);
   const float v = w[((int64_t)co * cin + chunk * 64 + j) * 16 + tap];
+  if (half) { reinterpret_cast<uint16_t*>(out)[i] = __half_as_ushort(__float2half_rn(v)); return; }
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   out[i] = (seg == 2) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
 }
@@ -117,9 +139,9 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackAllArgs a) {
   if (bid < 1024) {
     const int64_t n2 = (int64_t)128 * 16 * 64 * a.nseg, n3 = (int64_t)256 * 16 * 128 * a.nseg, n4 = (int64_t)512 * 16 * 256 * a.nseg;
     for (int64_t i = bid * 256ll + threadIdx.x; i < n2 + n3 + n4; i += 1024ll * 256) {
-      if (i < n2) pack_conv_elem(a.w2, a.p2, 64, a.nseg, i);
-      else if (i < n2 + n3) pack_conv_elem(a.w3, a.p3, 128, a.nseg, i - n2);
-      else pack_conv_elem(a.w4, a.p4, 256, a.nseg, i - n2 - n3);
+      if (i < n2) pack_conv_elem(a.w2, a.p2, 64, a.nseg, i, a.half);
+      else if (i < n2 + n3) pack_conv_elem(a.w3, a.p3, 128, a.nseg, i - n2, a.half);
+      else pack_conv_elem(a.w4, a.p4, 256, a.nseg, i - n2 - n3, a.half);
     }
   } else if (bid < 1056) {
     const int i = (bid - 1024) * 256 + threadIdx.x;
@@ -128,7 +150,8 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackAllArgs a) {
       const int kh = k >> 4, kw = (k >> 2) & 3, c = k & 3;
       const float v = (c < 3) ? a.w1[co * 48 + c * 16 + kh * 4 + kw] : 0.f;
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      a.o1t[i] = seg ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+      if (a.half) reinterpret_cast<uint16_t*>(a.o1t)[i] = seg ? (uint16_t)0 : __half_as_ushort(__float2half_rn(v));
+      else a.o1t[i] = seg ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
     }
     if (i < 48 * 64) a.o1[i] = a.w1[(i & 63) * 48 + (i >> 6)];
     if (i < 16 * 512) a.o5[i] = a.w5[(i & 511) * 16 + (i >> 9)];
@@ -602,7 +625,7 @@ struct Pair2Cfg {
   static constexpr int kThreads = 192;
 };
 
-template <int SEGA, int BLOCK_N>
+template <int SEGA, int BLOCK_N, bool HALF = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const ConvParams p) {
@@ -706,7 +729,7 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      constexpr uint32_t idesc = umma_idesc_16(256, BLOCK_N, HALF);
       int aslot = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, acc_phase = 0;
       bool ok = true;
@@ -787,6 +810,7 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           float a2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z), a3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w);
           a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);
           a2 = fmaxf(a2, slope * a2); a3 = fmaxf(a3, slope * a3);
+          if (HALF) { hi[2 * q] = act_pack2<true>(a0, a1); hi[2 * q + 1] = act_pack2<true>(a2, a3); continue; }
           const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
           hi[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
           hi[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
@@ -1020,7 +1044,7 @@ struct Conv2RCfg {
 // conv2_swap_kernel with PLANE REUSE of the pixel operand (see conv_pair2_kernel): the four taps of a parity plane
 // read two shared-memory copies of it (one per column shift, 17 plane rows x 16 columns each); a row shift is a
 // 2048-byte offset of the B descriptor.  Pixel bytes from L2 halve; the 16 KB weight tiles keep a ring of their own.
-template <int SEGA>
+template <int SEGA, bool HALF = false>
 __global__ void __launch_bounds__(192, 1)
 conv2_swap2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
@@ -1092,7 +1116,7 @@ conv2_swap2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(256);
+      constexpr uint32_t idesc = umma_idesc_16(128, 256, HALF);
       int stage = 0, xslot = 0, acc = 0;
       uint32_t phase = 0, xphase = 0, acc_phase = 0;
       bool ok = true;
@@ -1163,7 +1187,7 @@ conv2_swap2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
               float a = fmaf(__uint_as_float(v[j]), sc, sh);
               a = fmaxf(a, slope * a);
               const int row = (((j >> 4) & 1) * 2 + (j & 1)) * 32 + ((j & 15) >> 1);
-              st_shared_u16(rbase + (uint32_t)(row * 256), __bfloat16_as_ushort(__float2bfloat16_rn(a)));
+              st_shared_u16(rbase + (uint32_t)(row * 256), act_pack1<HALF>(a));
             }
           }
           fence_proxy_async_smem();
@@ -1230,7 +1254,7 @@ struct Conv1FCfg {
   static constexpr int kThreads = 320;
 };
 
-template <int SEGA>
+template <int SEGA, bool HALF = false>
 __global__ void __launch_bounds__(320, SEGA == 1 ? 2 : 1)
 conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ CUtensorMap tmap_o, int total_tiles, int* err) {
@@ -1293,7 +1317,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(64);
+      constexpr uint32_t idesc = umma_idesc_16(128, 64, HALF);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = mbar_wait(wbar, 0, s_abort, err, kErrMma + 10);
@@ -1356,6 +1380,11 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int kw = 0; kw < 4; ++kw) {
+            if (HALF) {
+              hi[2 * kw] = act_pack2<true>(px[q][kw][0], px[q][kw][1]);
+              hi[2 * kw + 1] = (uint32_t)act_pack1<true>(px[q][kw][2]);
+              continue;
+            }
             const __nv_bfloat16 h0 = __float2bfloat16_rn(px[q][kw][0]), h1 = __float2bfloat16_rn(px[q][kw][1]),
                                 h2 = __float2bfloat16_rn(px[q][kw][2]);
             hi[2 * kw] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
@@ -1413,6 +1442,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
           a = a > 0.f ? a : 0.2f * a;
           b = b > 0.f ? b : 0.2f * b;
+          if (HALF) { hi[j] = act_pack2<true>(a, b); continue; }
           const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
           hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
           if (SEGA == 2) {
@@ -1464,14 +1494,14 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 // so the kernels are layout agnostic: rows x (C*sega).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ act, int64_t rows, int c,
-                                                       int sega, double* __restrict__ part) {
+                                                       int sega, int half, double* __restrict__ part) {
   const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = blockIdx.x * per, r1 = min(r0 + per, rows);
   const int ct = c * sega;
   for (int ch = threadIdx.x; ch < c; ch += 256) {
     double s = 0.0, q = 0.0;
     for (int64_t r = r0; r < r1; ++r) {
-      float v = __bfloat162float(act[r * ct + ch]);
+      float v = act_unpack(reinterpret_cast<const uint16_t*>(act)[r * ct + ch], half != 0);
       if (sega == 2) v += __bfloat162float(act[r * ct + c + ch]);
       s += (double)v;
       q = fma((double)v, (double)v, q);
@@ -1515,7 +1545,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict__ act, int64_t rows, int c, int sega,
-                                                       const float* __restrict__ ss) {
+                                                       int half, const float* __restrict__ ss) {
   const int groups = c >> 3;                                  // 8 channels (16 B) per thread
   const int64_t total = rows * groups;
   const int ct = c * sega;
@@ -1531,12 +1561,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
     uint32_t oh[4], ol[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float a = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
-      float b = __uint_as_float(hw[k] & 0xFFFF0000u) + __uint_as_float(lw[k] & 0xFFFF0000u);
+      float a, b;
+      if (half) {
+        a = act_unpack((uint16_t)(hw[k] & 0xFFFFu), true);
+        b = act_unpack((uint16_t)(hw[k] >> 16), true);
+      } else {
+        a = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+        b = __uint_as_float(hw[k] & 0xFFFF0000u) + __uint_as_float(lw[k] & 0xFFFF0000u);
+      }
       a = fmaf(a, ss[ch + 2 * k], ss[512 + ch + 2 * k]);
       b = fmaf(b, ss[ch + 2 * k + 1], ss[512 + ch + 2 * k + 1]);
       a = a > 0.f ? a : 0.2f * a;
       b = b > 0.f ? b : 0.2f * b;
+      if (half) { oh[k] = act_pack2<true>(a, b); ol[k] = 0u; continue; }
       const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
       oh[k] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
       const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
@@ -1553,8 +1590,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
 // One warp per sample; fixed summation order (lane-strided partials, xor-shuffle tree).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restrict__ act4, const float* __restrict__ w5p,
-                                                   int64_t batch, int sega, float* __restrict__ logit,
-                                                   float* __restrict__ prob, float* __restrict__ loss) {
+                                                   int64_t batch, int sega, int half, float* __restrict__ logit,
+                                                   float* __restrict__ prob, float* __restrict__ loss, int* __restrict__ err) {
   const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= batch) return;
@@ -1574,8 +1611,14 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restri
       const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        xv[2 * q] = __uint_as_float(rw[q] << 16);
-        xv[2 * q + 1] = __uint_as_float(rw[q] & 0xFFFF0000u);
+        if (half) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
+          xv[2 * q] = f.x;
+          xv[2 * q + 1] = f.y;
+        } else {
+          xv[2 * q] = __uint_as_float(rw[q] << 16);
+          xv[2 * q + 1] = __uint_as_float(rw[q] & 0xFFFF0000u);
+        }
       }
       if (sega == 2) {
         const uint4 rl = *reinterpret_cast<const uint4*>(ap + 512 + c);
@@ -1594,6 +1637,8 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restri
   }
   accv = warp_sum(accv);
   if (lane == 0) {
+    // fp16 mode: an activation beyond 65504 became inf on the way (or the input was not finite) -> sg_d64_check reports it
+    if (half && !(fabsf(accv) <= 3.4e38f)) atomicExch(err + 1, kFp16OverflowMagic);
     const float pr = 1.0f / (1.0f + expf(-accv));
     if (logit) logit[n] = accv;
     if (prob) prob[n] = pr;
@@ -1604,7 +1649,7 @@ __global__ void __launch_bounds__(256) head_kernel(const __nv_bfloat16* __restri
 
 // debug/test: parity-plane (or plain) bf16 activation -> fp32 NCHW (hi + lo)
 __global__ void read_activation_kernel(const __nv_bfloat16* __restrict__ act, int64_t batch, int s, int c, int sega,
-                                       int planes, float* __restrict__ out) {
+                                       int half_fmt, int planes, float* __restrict__ out) {
   const int64_t total = batch * c * s * s;
   const int ct = c * sega;
   const int half = s >> 1;
@@ -1617,7 +1662,7 @@ __global__ void read_activation_kernel(const __nv_bfloat16* __restrict__ act, in
     size_t off;
     if (planes) off = ((((size_t)n * 4 + ((h & 1) * 2 + (w & 1))) * half + (h >> 1)) * half + (w >> 1)) * ct;
     else off = (((size_t)n * s + h) * s + w) * ct;
-    float v = __bfloat162float(act[off + ch]);
+    float v = act_unpack(reinterpret_cast<const uint16_t*>(act)[off + ch], half_fmt != 0);
     if (sega == 2) v += __bfloat162float(act[off + c + ch]);
     out[i] = v;
   }
@@ -1750,7 +1795,7 @@ static int launch_conv_pair(const __nv_bfloat16* act_in, const __nv_bfloat16* wp
 template <int BLOCK_N>
 static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
                              __nv_bfloat16* act_out, int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega,
-                             int out_planes, float slope, int* err, cudaStream_t stream) {
+                             int out_planes, float slope, int* err, cudaStream_t stream, bool half = false) {
   using Cfg = Pair2Cfg<BLOCK_N>;
   const int ow = s_in / 2;                 // output width = parity-plane width
   const bool split = ow * ow > 128;        // L2: 256 output pixels per image -> one image per CTA pair
@@ -1802,6 +1847,7 @@ static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* w
   int pairs = state().sm_count / 2;
   if (p.total_tiles < pairs) pairs = p.total_tiles;
   if (sega == 2) conv_pair2_kernel<2, BLOCK_N><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  else if (half) conv_pair2_kernel<1, BLOCK_N, true><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   else conv_pair2_kernel<1, BLOCK_N><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   SG_LAUNCH_CHECK();
   return SG_OK;
@@ -1809,7 +1855,7 @@ static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* w
 
 static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* scale, const float* shift,
                              __nv_bfloat16* act2,
-                             int64_t batch, int nseg, int sega, float slope, int* err, cudaStream_t stream) {
+                             int64_t batch, int nseg, int sega, float slope, int* err, cudaStream_t stream, bool half = false) {
   CUtensorMap tx, tw;
   const int ct_in = 64 * sega;
   {
@@ -1852,7 +1898,7 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
     int r = encode(&to, 5, act2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r != SG_OK) return r;
   }
-  if (!getenv("SG_CONV_TAP_STREAM")) {   // default: plane reuse
+  if (half || !getenv("SG_CONV_TAP_STREAM")) {   // default: plane reuse (the only form with an fp16 variant)
     CUtensorMap txr;
     cuuint64_t dims[5] = {(cuuint64_t)ct_in, 16, 16, 4, (cuuint64_t)batch};
     cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)16 * ct_in * 2, (cuuint64_t)256 * ct_in * 2,
@@ -1861,6 +1907,7 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
     int r = encode(&txr, 5, act1, dims, strides, box);
     if (r != SG_OK) return r;
     if (sega == 2) conv2_swap2_kernel<2><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
+    else if (half) conv2_swap2_kernel<1, true><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
     else conv2_swap2_kernel<1><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
     SG_LAUNCH_CHECK();
     return SG_OK;
@@ -1871,7 +1918,7 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
   return SG_OK;
 }
 
-template <int SEGA>
+template <int SEGA, bool HALF = false>
 static int launch_conv1_fused(const float* x, const __nv_bfloat16* w1t, __nv_bfloat16* act1, int64_t batch, int* err,
                               cudaStream_t stream) {
   using Cfg = Conv1FCfg<SEGA>;
@@ -1902,7 +1949,7 @@ static int launch_conv1_fused(const float* x, const __nv_bfloat16* w1t, __nv_bfl
   const int64_t tiles = batch * 8;
   const int64_t ctas = (int64_t)state().sm_count * (SEGA == 1 ? 2 : 1);
   int grid = (int)(tiles < ctas ? tiles : ctas);
-  conv1_fused_kernel<SEGA><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tx, tb, to, (int)tiles, err);
+  conv1_fused_kernel<SEGA, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tx, tb, to, (int)tiles, err);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1928,6 +1975,12 @@ int sg_d64_init_attributes() {
                                Conv1FCfg<1>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Conv1FCfg<2>::kSmemBytes));
+  // fp16 conv mode (SG_CONV_FP16): the default kernels with fp16 operands
+  SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Conv1FCfg<1>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv2_swap2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2RCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Pair2Cfg<256>::kSmemBytes));
   return SG_OK;
 }
 
@@ -1945,7 +1998,7 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
                 float bn_eps, int conv_mode, void* packed, void* stream) {
   using namespace sg::d64;
   SG_READY();
-  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
   SG_REQUIRE(w1 && w2 && w3 && w4 && w5 && packed, "null weight pointer");
   SG_REQUIRE(((uintptr_t)packed & 1023) == 0, "packed buffer must be 1024-byte aligned");
   const PackedLayout L = packed_layout(conv_mode);
@@ -1973,6 +2026,7 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
   a.ident = reinterpret_cast<float*>(pk + L.ident);
   a.eps = bn_eps;
   a.nseg = L.nseg;
+  a.half = conv_mode == SG_CONV_FP16;
   pack_all_kernel<<<1059, 256, 0, st>>>(a);
   SG_LAUNCH_CHECK();
   return SG_OK;
@@ -1985,7 +2039,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
                           float momentum, float eps, void* stream) {
   using namespace sg::d64;
   SG_READY();
-  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
   SG_REQUIRE(packed && workspace, "null pointer");
   SG_REQUIRE(layer >= 1 && layer <= 5, "layer must be 1..5");
   SG_REQUIRE(batch >= 0 && batch <= (1 << 22), "batch out of range");
@@ -2005,6 +2059,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   auto wq = [&](size_t off) { return reinterpret_cast<const __nv_bfloat16*>(pk + off); };
   auto fq = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
   const float slope = bn_train ? 1.0f : 0.2f;
+  const bool half = conv_mode == SG_CONV_FP16;
   // eval: folded BN scale | shift; train: identity (ones | zeros at +512) so the raw conv output is stored
   auto sc = [&](size_t off, int) { return fq(bn_train ? P.ident : off); };
   auto sh = [&](size_t off, int c) { return bn_train ? fq(P.ident) + 512 : fq(off) + c; };
@@ -2012,15 +2067,16 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   switch (layer) {
     case 1:
       SG_REQUIRE(x != nullptr && ((uintptr_t)x & 15) == 0, "x must be a 16-byte aligned device pointer");
+      if (half) return launch_conv1_fused<1, true>(x, wq(P.w1t), act1, batch, err, st);
       return (W.sega == 2) ? launch_conv1_fused<2>(x, wq(P.w1t), act1, batch, err, st)
                            : launch_conv1_fused<1>(x, wq(P.w1t), act1, batch, err, st);
     case 2:
-      r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st);
+      r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st, half);
       break;
     case 3:
-      if (!getenv("SG_CONV_TAP_STREAM"))  // default: plane reuse; per-tap streaming kernels kept for A/B timing
+      if (half || !getenv("SG_CONV_TAP_STREAM"))  // default: plane reuse; per-tap streaming kernels kept for A/B timing
         r = launch_conv_pair2<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
-                              slope, err, st);
+                              slope, err, st, half);
       else if (!getenv("SG_CONV_SINGLE_CTA"))  // default: CTA pairs (cta_group::2); single-CTA tiles kept for A/B timing
         r = launch_conv_pair(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
                              slope, err, st);
@@ -2029,9 +2085,9 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
                            slope, err, st);
       break;
     case 4:
-      if (!getenv("SG_CONV_TAP_STREAM"))
+      if (half || !getenv("SG_CONV_TAP_STREAM"))
         r = launch_conv_pair2<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
-                              slope, err, st);
+                              slope, err, st, half);
       else if (!getenv("SG_CONV_SINGLE_CTA"))
         r = launch_conv_pair(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
                              slope, err, st);
@@ -2040,7 +2096,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
                            slope, err, st);
       break;
     default:
-      head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, fq(P.w5), batch, W.sega, logit, prob, loss);
+      head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, fq(P.w5), batch, W.sega, half, logit, prob, loss, err);
       SG_LAUNCH_CHECK();
       return SG_OK;
   }
@@ -2053,7 +2109,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   double* part = reinterpret_cast<double*>(ws + W.bnpart);
   float* ss = reinterpret_cast<float*>(ws + W.bnss);
   int blocks = (int)(rows < kBnBlocks ? rows : kBnBlocks);
-  bn_stats_kernel<<<blocks, 256, 0, st>>>(act, rows, c, W.sega, part);
+  bn_stats_kernel<<<blocks, 256, 0, st>>>(act, rows, c, W.sega, half, part);
   SG_LAUNCH_CHECK();
   float* rm = running_stats ? running_stats[2 * (layer - 2)] : nullptr;
   float* rv = running_stats ? running_stats[2 * (layer - 2) + 1] : nullptr;
@@ -2061,7 +2117,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   SG_LAUNCH_CHECK();
   int64_t ab = sg::ceil_div(rows * (c / 8), 256);
   if (ab > (int64_t)sg::state().sm_count * 16) ab = (int64_t)sg::state().sm_count * 16;
-  bn_apply_kernel<<<(unsigned)ab, 256, 0, st>>>(act, rows, c, W.sega, ss);
+  bn_apply_kernel<<<(unsigned)ab, 256, 0, st>>>(act, rows, c, W.sega, half, ss);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -2104,12 +2160,18 @@ int sg_d64_score(const float* x, int64_t batch, const void* packed, void* worksp
 int sg_d64_check(const void* workspace, void* stream) {
   SG_READY();
   SG_REQUIRE(workspace != nullptr, "workspace");
-  int flag = 0;
-  SG_CUDA(cudaMemcpyAsync(&flag, workspace, 4, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
+  int flags[2] = {0, 0};
+  SG_CUDA(cudaMemcpyAsync(flags, workspace, 8, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
   SG_CUDA(cudaStreamSynchronize(sg::as_stream(stream)));
-  if (flag != 0) {
-    sg::set_error("conv pipeline timed out waiting on an mbarrier (role code %d: 1 producer, 2 mma, 3 mma-acc, 4 epilogue)", flag);
+  if (flags[0] != 0) {
+    sg::set_error("conv pipeline timed out waiting on an mbarrier (role code %d: 1 producer, 2 mma, 3 mma-acc, 4 epilogue)", flags[0]);
     return SG_ECUDA;
+  }
+  if (flags[1] == sg::d64::kFp16OverflowMagic) {
+    (void)cudaMemsetAsync(static_cast<uint8_t*>(const_cast<void*>(workspace)) + 4, 0, 4, sg::as_stream(stream));
+    sg::set_error("non-finite logit in the fp16 conv mode: an activation exceeded 65504 (or the input is not finite); "
+                  "score this discriminator with SG_CONV_BF16X3 ('fp32') or SG_CONV_BF16");
+    return SG_EINVAL;
   }
   return SG_OK;
 }
@@ -2127,7 +2189,7 @@ int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, 
   int blocks = (int)sg::ceil_div(total, 256);
   if (blocks > 65535) blocks = 65535;
   read_activation_kernel<<<blocks, 256, 0, sg::as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(ws + offs[layer]), batch, s[layer], c[layer], W.sega, layer != 4, out);
+      reinterpret_cast<const __nv_bfloat16*>(ws + offs[layer]), batch, s[layer], c[layer], W.sega, conv_mode == SG_CONV_FP16, layer != 4, out);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

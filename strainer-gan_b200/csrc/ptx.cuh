@@ -255,6 +255,10 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// kind::f16 with A = B = fp16 (format fields 0) or bf16 (1): the fp16 conv mode uses the same kernels and descriptors
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, bool half) {
+  return (1u << 4) | (half ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 }  // namespace ptx
 }  // namespace sg
