@@ -1380,9 +1380,9 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int kw = 0; kw < 4; ++kw) {
-            if (HALF) {
-              hi[2 * kw] = act_pack2<true>(px[q][kw][0], px[q][kw][1]);
-              hi[2 * kw + 1] = (uint32_t)act_pack1<true>(px[q][kw][2]);
+            if (HALF || SEGA == 1) {   // packed two-value conversions (the kernel is issue bound: 0.315 -> 0.27 ms)
+              hi[2 * kw] = act_pack2<HALF>(px[q][kw][0], px[q][kw][1]);
+              hi[2 * kw + 1] = (uint32_t)act_pack1<HALF>(px[q][kw][2]);
               continue;
             }
             const __nv_bfloat16 h0 = __float2bfloat16_rn(px[q][kw][0]), h1 = __float2bfloat16_rn(px[q][kw][1]),
@@ -1442,7 +1442,7 @@ conv1_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
           a = a > 0.f ? a : 0.2f * a;
           b = b > 0.f ? b : 0.2f * b;
-          if (HALF) { hi[j] = act_pack2<true>(a, b); continue; }
+          if (HALF || SEGA == 1) { hi[j] = act_pack2<HALF>(a, b); continue; }
           const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
           hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
           if (SEGA == 2) {
