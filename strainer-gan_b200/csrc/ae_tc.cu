@@ -39,12 +39,13 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
 // on load and split on store.
 struct Layout {
-  size_t flag, w3, w4, a1, a2, a3, a4, a5, total;
+  size_t flag, w2, w3, w4, a1, a2, a3, a4, a5, total;
 };
 static Layout layout(int64_t batch, int seg) {
   Layout L;
   size_t o = 0;
   L.flag = o; o += 1024;
+  L.w2 = o; o += align_up((size_t)32 * 144 * 2, 1024);   // enc2 weights, bf16 [oc][tap*16 + ic] (tensor-core form, SEG == 1)
   L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
   L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
   L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
@@ -433,6 +434,149 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// L2 (enc Conv 16->32 k3 s2 p1 + ReLU) on tcgen05 (bf16 conv mode).  One tile = 8 x 16 output pixels of one image
+// (M = 128), N = 32, one MMA (K = 16 input channels) per filter tap.  The A operand of tap (ky, kx) is the set of
+// input pixels (2 oy - 1 + ky, 2 ox - 1 + kx): ONE 4-D TMA box with traversal stride 2 in x and y (start coordinate
+// -1 = the zero padding), landing as 128 dense 32-byte rows (SWIZZLE_32B).  The nine 1 KB weight tiles stay in shared
+// memory for the whole kernel.  The CUDA-core form (one output pixel per thread, 4 FMAs per shared-memory load)
+// took 0.67 ms per 8 192 images = 29 TFLOP/s.
+// ------------------------------------------------------------------------------------------
+struct Enc2Cfg {
+  static constexpr int kABytes = 128 * 32;     // one tap of one tile
+  static constexpr int kStages = 18;           // two tiles of taps in flight
+  static constexpr int kBBytes = 9 * 32 * 32;  // [tap][32 oc x 16 ic]
+  static constexpr int kTmemCols = 64;         // 2 accumulators x 32 columns
+  static constexpr int kSmemBytes = kStages * kABytes + kBBytes + 512 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
+  using Cfg = Enc2Cfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + S * Cfg::kABytes;
+  const uint32_t bar0 = b_base + Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_base + tap * 1024, &tmap_b, wbar, tap * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int img = tile >> 1, oy0 = (tile & 1) * 8;
+        for (int tap = 0; tap < 9; ++tap) {
+          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 11)) { ok = false; break; }
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kABytes);
+          tma_load_4d(base + stage * Cfg::kABytes, &tmap_a, full_bar(stage), 0, tap % 3 - 1, 2 * oy0 - 1 + tap / 3, img);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(32);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 12);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 13)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
+        for (int tap = 0; tap < 9; ++tap) {
+          if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 12)) { ok = false; break; }
+          tc_fence_after();
+          umma_f16(tmem_d, umma_desc_sw32(base + stage * Cfg::kABytes), umma_desc_sw32(b_base + tap * 1024), idesc,
+                   (uint32_t)(tap != 0));
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    float bo[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bo[c] = __ldg(bias + c);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int img = tile >> 1;
+      __nv_bfloat16* dst = out + ((size_t)img * 256 + (tile & 1) * 128 + row) * 32;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 14)) break;
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[2 * j], 0.f);
+        const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[2 * j + 1], 0.f);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      if (img < n_img) {
+        uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// enc2 weights [32][16][3][3] (out, in, ky, kx) -> bf16 [oc][tap*16 + ic]
+__global__ void pack_enc2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 32 * 144) {
+    const int oc = i / 144, r = i - oc * 144, tap = r >> 4, ic = r & 15;
+    p[i] = __float2bfloat16_rn(w[(oc * 16 + ic) * 9 + tap]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // The four small layers (CUDA cores, fp32 math on bf16 activations)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
@@ -766,7 +910,27 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
   enc1_kernel<SEG><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
   SG_LAUNCH_CHECK();
-  enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
+  if (SEG == 1 && !getenv("SG_AE_ENC2_CUDA")) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
+    pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2));
+    CUtensorMap ta, tb;
+    // a1 [n][32][32][16]: box = 16 ch x (16 columns at stride 2) x (8 rows at stride 2) of one image
+    cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
+    cuuint64_t astr[3] = {32, 1024, 32768};
+    cuuint32_t abox[4] = {16, 32, 16, 1};
+    cuuint32_t aes[4] = {1, 2, 2, 1};
+    int r2 = encode_tmap(&ta, 4, bf(L.a1), adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, aes);
+    if (r2 != SG_OK) return r2;
+    cuuint64_t bdims[2] = {144, 32};
+    cuuint64_t bstr[1] = {288};
+    cuuint32_t bbox[2] = {16, 32};
+    r2 = encode_tmap(&tb, 2, bf(L.w2), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r2 != SG_OK) return r2;
+    const int64_t tiles = 2 * batch;
+    const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
+    ae_enc2_tc_kernel<<<grid, 192, Enc2Cfg::kSmemBytes, st>>>(ta, tb, h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
+  } else {
+    enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
+  }
   SG_LAUNCH_CHECK();
   int r = launch_k7<64, false, SEG == 2>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
   if (r != SG_OK) return r;
@@ -809,6 +973,7 @@ int sg_ae_tc_init_attributes() {
                                K7Cfg<64, false, true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<32, true, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   return SG_OK;
