@@ -39,13 +39,14 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
 // on load and split on store.
 struct Layout {
-  size_t flag, w2, w3, w4, a1, a2, a3, a4, a5, total;
+  size_t flag, w2, w5, w3, w4, a1, a2, a3, a4, a5, total;
 };
 static Layout layout(int64_t batch, int seg) {
   Layout L;
   size_t o = 0;
   L.flag = o; o += 1024;
   L.w2 = o; o += align_up((size_t)32 * 144 * 2, 1024);   // enc2 weights, bf16 [oc][tap*16 + ic] (tensor-core form, SEG == 1)
+  L.w5 = o; o += align_up((size_t)16 * 288 * 2, 1024);   // dec2 weights, bf16 [oc][(tap*2 + half)*16 + ic] (tensor-core form)
   L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
   L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
   L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
@@ -577,6 +578,172 @@ __global__ void pack_enc2_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// L5 (dec ConvT 32->16 k3 s2 p1 op1 + ReLU) on tcgen05 (bf16 conv mode), gather form by output parity class:
+// out(2qy + py, 2qx + px) = sum over the taps whose parity matches of in(qy + dy, qx + dx) * w (see tap_k below).
+// One tile = 8 x 16 quads of one image (M = 128); the four classes (py, px) have their own N = 16 accumulators
+// side by side in TMEM.  The A operands are the FOUR shifted windows in(qy + dy, qx + dx) (row / column 16 = TMA
+// zero fill), each as two 16-channel halves of dense 32-byte rows (SWIZZLE_32B): 8 TMA boxes = 32 KB per tile, read
+// by 18 MMAs (9 taps x 2 halves, K = 16).  The 18 weight tiles [16 oc x 16 ic] stay in shared memory.
+// ------------------------------------------------------------------------------------------
+struct Dec2Cfg {
+  static constexpr int kPart = 128 * 32;          // one (shift, half) window of a tile
+  static constexpr int kStageBytes = 8 * kPart;   // 32 KB per tile
+  static constexpr int kStages = 4;
+  static constexpr int kBBytes = 18 * 512;
+  static constexpr int kTmemCols = 128;           // 2 buffers x 4 classes x 16 columns
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 256 + 1024;
+};
+__host__ __device__ constexpr int dec2_tap_k(int parity, int d) { return parity == 0 ? 1 : (d ? 0 : 2); }
+
+__global__ void __launch_bounds__(192, 1)
+ae_dec2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
+  using Cfg = Dec2Cfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + S * Cfg::kStageBytes;
+  const uint32_t bar0 = b_base + Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int t = 0; t < 18; ++t) tma_load_2d(b_base + t * 512, &tmap_b, wbar, t * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int img = tile >> 1, qy0 = (tile & 1) * 8;
+        if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 21)) break;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int part = 0; part < 8; ++part) {   // part = (dy*2 + dx)*2 + half
+          const int half = part & 1, dx = (part >> 1) & 1, dy = part >> 2;
+          tma_load_4d(sa + part * Cfg::kPart, &tmap_a, full_bar(stage), half * 16, dx, qy0 + dy, img);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(16);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 22);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 23)) break;
+        if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 22)) break;
+        tc_fence_after();
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+          const int py = cls >> 1, px = cls & 1;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
+          bool first = true;
+#pragma unroll
+          for (int dy = 0; dy <= py; ++dy)
+#pragma unroll
+            for (int dx = 0; dx <= px; ++dx) {
+              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                umma_f16(tmem_d, umma_desc_sw32(sa + ((dy * 2 + dx) * 2 + half) * Cfg::kPart),
+                         umma_desc_sw32(b_base + (tap * 2 + half) * 512), idesc, first ? 0u : 1u);
+                first = false;
+              }
+            }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int qyl = row >> 4, qx = row & 15;
+    float bo[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) bo[c] = __ldg(bias + c);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int img = tile >> 1, qy = (tile & 1) * 8 + qyl;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 24)) break;
+      tc_fence_after();
+      uint32_t v0[32], v1[32];   // classes (0,0) (0,1) | (1,0) (1,1)
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+      tmem_ld_32x32(taddr, v0);
+      tmem_ld_32x32(taddr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (img < n_img) {
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          const uint32_t* v = py ? v1 : v0;
+          uint32_t pk[16];   // pixels (2qx, 2qx + 1) of output row 2qy + py: 2 x 16 channels = 64 contiguous bytes
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[(2 * j) & 15], 0.f);
+            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[(2 * j + 1) & 15], 0.f);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          uint4* d = reinterpret_cast<uint4*>(out + (((size_t)img * 32 + 2 * qy + py) * 32 + 2 * qx) * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// dec2 weights [32][16][3][3] (ConvTranspose2d: in, out, ky, kx) -> bf16 [oc][(tap*2 + half)*16 + icl], ic = half*16 + icl
+__global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16 * 288) {
+    const int oc = i / 288, r = i - oc * 288, t = r >> 4, icl = r & 15;
+    const int tap = t >> 1, ic = (t & 1) * 16 + icl;
+    p[i] = __float2bfloat16_rn(w[(ic * 16 + oc) * 9 + tap]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // The four small layers (CUDA cores, fp32 math on bf16 activations)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
@@ -953,7 +1120,26 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     ae_dec1_kernel<SEG><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
     SG_LAUNCH_CHECK();
   }
-  dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
+  if (SEG == 1 && !getenv("SG_AE_DEC2_CUDA")) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
+    pack_dec2_kernel<<<(16 * 288 + 255) / 256, 256, 0, st>>>(h_params[8], bf(L.w5));
+    CUtensorMap ta, tb;
+    // a4 [n][16][16][32]: box = 16 channels (one half) x 16 columns x 8 rows of one image, shifted by (dx, dy)
+    cuuint64_t adims[4] = {32, 16, 16, (cuuint64_t)batch};
+    cuuint64_t astr[3] = {64, 1024, 16384};
+    cuuint32_t abox[4] = {16, 16, 8, 1};
+    r = encode_tmap(&ta, 4, bf(L.a4), adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+    cuuint64_t bdims[2] = {288, 16};
+    cuuint64_t bstr[1] = {576};
+    cuuint32_t bbox[2] = {16, 16};
+    r = encode_tmap(&tb, 2, bf(L.w5), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+    const int64_t tiles = 2 * batch;
+    const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
+    ae_dec2_tc_kernel<<<grid, 192, Dec2Cfg::kSmemBytes, st>>>(ta, tb, h_params[9], bf(L.a5), (int)batch, (int)tiles, err);
+  } else {
+    dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
+  }
   SG_LAUNCH_CHECK();
   dec3_mse_kernel<SEG><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
   SG_LAUNCH_CHECK();
@@ -974,6 +1160,7 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<32, true, false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   return SG_OK;
