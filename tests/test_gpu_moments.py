@@ -215,3 +215,32 @@ def test_dbscan_nd_edges(sb):
     assert (core, clean) == (15, 15) and ratio == 15 / 19
     with pytest.raises(RuntimeError):
         sb.dbscan_clean_ratio(torch.from_numpy(rng.standard_normal((10, 100)).astype(np.float32)), 1.0, 3)   # d % 64 != 0
+
+
+def test_autoencoder_small_layers_tensor_core_vs_cuda_core(sb):
+    """enc2 / dec2 of the bf16 mode run on tcgen05 (stride-2 TMA boxes, parity-class accumulators); the CUDA-core forms
+    stay selectable (SG_AE_ENC2_CUDA / SG_AE_DEC2_CUDA).  With non-trivial weights every tap matters: both forms must
+    agree to bf16 weight rounding, and each with the oracle."""
+    import os
+    torch.manual_seed(11)
+    ae = O.AutoEncoder()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for p in ae.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.7 / np.sqrt(max(p[0].numel(), 1))))
+    x = torch.from_numpy(O.synth_images(300, 37))          # odd count: a ragged last tile pair
+    ref = O.ae_errors(ae, x).numpy()
+    got = {}
+    try:
+        for name, env in (("tc", {}), ("enc2_cuda", {"SG_AE_ENC2_CUDA": "1"}), ("dec2_cuda", {"SG_AE_DEC2_CUDA": "1"}),
+                          ("both_cuda", {"SG_AE_ENC2_CUDA": "1", "SG_AE_DEC2_CUDA": "1"})):
+            for k in ("SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            got[name] = sb.ae_errors(ae, x, "cuda", conv_mode="bf16").cpu().numpy()
+    finally:
+        for k in ("SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
+            os.environ.pop(k, None)
+    for name, e in got.items():
+        assert (np.abs(e - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2, name
+        assert (np.abs(e - got["both_cuda"]) / np.maximum(ref, 1e-6)).max() <= 5e-3, name
