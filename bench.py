@@ -222,16 +222,17 @@ def main():
     conv_ms = float(lt[1] + lt[2] + lt[3])
     nseg = 3 if args.mode == "fp32" else 1
     achieved_tf = FLOP_CONV * CHUNK / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv2_swap_kernel + 2 x conv_pair2_kernel (L2+L3+L4 implicit-GEMM launches of one chunk)",
+    roofline = {"bound": "tensor", "kernel": "conv2_swap2_kernel + 2 x conv_pair2_kernel (L2+L3+L4 implicit-GEMM launches of one chunk)",
                 "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sust"],
                 "peak_source": f"bf16_tflops_sustained of {pk['src']} (cuBLAS bf16 back to back for 4 s: the convs are timed inside a "
                                "long loop under the same sw_power_cap)",
                 "frac_of_burst_peak": achieved_tf / pk["tf_burst"], "burst_peak": pk["tf_burst"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of the three launches at 8192 samples, bf16 mode, from the
-                # ncu --set full capture profiles/r1d_conv_kernels_full.txt (L2 1.074+0.508, L3 0.538+0.234, L4 0.273+0.107 GB);
+                # ncu --set full captures profiles/r1d_conv_kernels_full.txt (bf16) / r1f_conv_kernels_fp16_full.txt (L2 1.074+0.506,
+                # L3 0.538+0.235, L4 0.273+0.107 GB);
                 # algorithmic: act1 1.074 + act2 0.537 read, act2 0.537 + act3 0.268 + act4 0.134 written = 2.55 GB
                 "traffic": 2.734e9 if (args.mode in ("bf16", "fp16") and CHUNK == 8192) else None,
-                "traffic_unit": "bytes per launch group (ncu, profiles/r1d_conv_kernels_full.txt)",
+                "traffic_unit": "bytes per launch group (ncu, profiles/r1d_conv_kernels_full.txt, r1f_conv_kernels_fp16_full.txt)",
                 "algorithmic_flops_per_sample": FLOP_CONV, "samples_per_launch_group": CHUNK,
                 "issued_tensor_flops_factor": nseg}
     kernels = {"chunk": CHUNK, "ms": {k: float(v) for k, v in zip(["conv1", "conv2", "conv3", "conv4", "head"], lt)},
