@@ -52,7 +52,7 @@ typedef enum SgConvMode {
   SG_CONV_BF16X3 = 1, /* fp32-parity mode: bf16 hi/lo split, 3 tcgen05 passes (hi*hi+lo*hi+hi*lo) */
   SG_CONV_FP16 = 2    /* fp16 operands and activations, fp32 accumulate, 1 pass: 11-bit significands keep the losses within
                          1e-3 of fp32 (the north_star's fp32 bar) at the bf16 mode's speed; needs |activation| < 65504.
-                         sg_d64_* only (the auto-encoder entry points take SG_CONV_BF16 / SG_CONV_BF16X3) */
+                         accepted by sg_d64_* and sg_ae_score_tc */
 } SgConvMode;
 
 /* memory layout of a uint8 image batch */

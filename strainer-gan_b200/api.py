@@ -1070,18 +1070,19 @@ def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: 
     """Per-sample reconstruction MSE of the reference AutoEncoder on the GPU; fp32 device tensor [N].
     conv_mode 'fp32' (default): fp32-parity arithmetic on the tensor cores (bf16 hi/lo split of activations and 7x7
     weights, three GEMM segments; ~1e-5 relative); 'bf16' (BASELINE config 4): bf16 operands and activations;
+    'fp16': fp16 operands and activations, one tensor pass, errors within the same 1e-3 bar as 'fp32' at the bf16 mode's speed;
     'fp32_cuda': every layer in plain fp32 on the CUDA cores (the first implementation, kept as a cross-check)."""
     device = _dev(device)
     lib = _lib_for(device)
-    if conv_mode not in ("fp32", "bf16", "fp32_cuda"):
-        raise ValueError("conv_mode must be 'fp32', 'bf16' or 'fp32_cuda'")
+    if conv_mode not in ("fp32", "fp16", "bf16", "fp32_cuda"):
+        raise ValueError("conv_mode must be 'fp32', 'fp16', 'bf16' or 'fp32_cuda'")
     params = _ae_params(autoencoder, device)
     arr = (L.P * 12)(*[t.data_ptr() for t in params])
     n = images.shape[0]
     err = torch.empty(n, dtype=torch.float32, device=device)
     cb = min(chunk, max(n, 1))
     if conv_mode != "fp32_cuda":
-        mode = L.SG_CONV_BF16 if conv_mode == "bf16" else L.SG_CONV_BF16X3
+        mode = {"bf16": L.SG_CONV_BF16, "fp16": L.SG_CONV_FP16}.get(conv_mode, L.SG_CONV_BF16X3)
         ws = _Scratch.get(device, "ae_tc", lib.sg_ae_tc_workspace_bytes(cb, mode))
         for i, x in _device_f32_chunks(images, device, chunk):
             L.check(lib.sg_ae_score_tc(_p(x), x.shape[0], arr, _p(ws), mode, _p(err[i:i + chunk]), L.P(0), _stream()),

@@ -18,6 +18,7 @@
 //   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> bf16 [32][32][16]  CUDA cores, one 2x2 output quad per thread
 //   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,6 +31,18 @@ namespace aetc {
 using namespace ptx;
 
 constexpr int kErrBase = 40;
+
+// fp16 conv mode (SG_CONV_FP16, HALF = true): the single-segment kernels with fp16 operands / activations -- reconstruction
+// errors within the 1e-3 fp32 bar in ONE tensor pass (the bf16 hi/lo parity mode needs three).  Only the 16-bit
+// conversions and the MMA operand-format bits differ.
+template <bool HALF> __device__ __forceinline__ uint32_t pk2(float a, float b) {   // a in the low half
+  if (HALF) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <bool HALF> __device__ __forceinline__ uint16_t pk1(float a) {
+  return HALF ? __half_as_ushort(__float2half_rn(a)) : __bfloat16_as_ushort(__float2bfloat16_rn(a));
+}
 constexpr int kKs3 = 28, kKs4 = 49;                      // K-steps of 64 of the two 7x7 layers (bf16 mode)
 constexpr int kKs3Split = 98;                            // split mode: 49 taps x {[x_hi|x_lo].[w_hi|w_hi], [x_hi|x_lo].[w_lo|0]}
 constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100 * 64 * 2, kAct4 = 256 * 32 * 2,
@@ -61,11 +74,11 @@ static Layout layout(int64_t batch, int seg) {
 // w3 [64][32][7][7] (Conv2d: out, in, kh, kw)  -> bf16 [oc][ks = kh*4 + kwp][j = px*32 + c], kw = 2*kwp + px (kw == 7 -> 0)
 // w4 [64][32][7][7] (ConvTranspose2d: in, out, kh, kw) -> bf16 [oc][ks = kx*7 + ky][ic] (the 7 row taps of a column shift
 // are contiguous: one weight stage of ae_dec1_kernel)
-template <int SEG>
+template <int SEG, bool HALF = false>
 __global__ void pack_k7_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
                                __nv_bfloat16* __restrict__ p4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  auto hi_of = [](float v) { return __float2bfloat16_rn(v); };
+  auto hi_of = [](float v) { return __ushort_as_bfloat16(pk1<HALF>(v)); };   // HALF: fp16 bits carried in the bf16 type
   auto lo_of = [](float v) { return __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v))); };
   if (SEG == 1) {
     if (i < 64 * kKs3 * 64) {
@@ -109,7 +122,7 @@ struct K7Cfg {
 };
 
 // SPLIT (fp32-parity mode, L3 only): the input pixel row is [x_hi(32) | x_lo(32)], one tap per two K-steps
-template <int N, bool CONVT, bool SPLIT>
+template <int N, bool CONVT, bool SPLIT, bool HALF = false>
 __global__ void __launch_bounds__(192, 1)
 ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
@@ -165,7 +178,7 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(N);
+      constexpr uint32_t idesc = umma_idesc_16(128, N, HALF);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = true;
@@ -214,6 +227,7 @@ ae_k7_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           float a = __uint_as_float(v[2 * j]) + __ldg(bias + cb + 2 * j);
           float b = __uint_as_float(v[2 * j + 1]) + __ldg(bias + cb + 2 * j + 1);
           if (CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }   // ReLU after the decoder's first layer only
+          if (HALF) { pk[j] = pk2<true>(a, b); continue; }
           const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
           if (SPLIT) {
@@ -267,7 +281,7 @@ struct Dec1Cfg {
 
 // SEG == 2 (fp32-parity mode): per column shift three sub-steps -- x_hi copy with w_hi, the same copy with w_lo,
 // x_lo copy with w_hi; input channels [hi 64 | lo 64], output [hi 32 | lo 32].
-template <int SEG>
+template <int SEG, bool HALF = false>
 __global__ void __launch_bounds__(192, 1)
 ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
@@ -340,7 +354,7 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(32);
+      constexpr uint32_t idesc = umma_idesc_16(128, 32, HALF);
       int aslot = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, acc_phase = 0;
       bool ok = true;
@@ -405,6 +419,7 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < 16; ++j) {
           const float a = fmaxf(__uint_as_float(v[2 * j]) + __ldg(bias + 2 * j), 0.f);
           const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + __ldg(bias + 2 * j + 1), 0.f);
+          if (HALF) { pk[j] = pk2<true>(a, b); continue; }
           const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
           pk[j] = *reinterpret_cast<const uint32_t*>(&h);
           if (SEG == 2) {
@@ -450,6 +465,7 @@ struct Enc2Cfg {
   static constexpr int kSmemBytes = kStages * kABytes + kBBytes + 512 + 1024;
 };
 
+template <bool HALF>
 __global__ void __launch_bounds__(192, 1)
 ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
@@ -505,7 +521,7 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(32);
+      constexpr uint32_t idesc = umma_idesc_16(128, 32, HALF);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 12);
@@ -549,8 +565,7 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int j = 0; j < 16; ++j) {
         const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[2 * j], 0.f);
         const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[2 * j + 1], 0.f);
-        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        pk[j] = pk2<HALF>(a, b);
       }
       if (img < n_img) {
         uint4* d = reinterpret_cast<uint4*>(dst);
@@ -569,11 +584,12 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // enc2 weights [32][16][3][3] (out, in, ky, kx) -> bf16 [oc][tap*16 + ic]
-__global__ void pack_enc2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p) {
+__global__ void pack_enc2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 32 * 144) {
     const int oc = i / 144, r = i - oc * 144, tap = r >> 4, ic = r & 15;
-    p[i] = __float2bfloat16_rn(w[(oc * 16 + ic) * 9 + tap]);
+    const float v = w[(oc * 16 + ic) * 9 + tap];
+    reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
   }
 }
 
@@ -595,6 +611,7 @@ struct Dec2Cfg {
 };
 __host__ __device__ constexpr int dec2_tap_k(int parity, int d) { return parity == 0 ? 1 : (d ? 0 : 2); }
 
+template <bool HALF>
 __global__ void __launch_bounds__(192, 1)
 ae_dec2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
@@ -652,7 +669,7 @@ ae_dec2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(16);
+      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 22);
@@ -714,8 +731,7 @@ ae_dec2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < 16; ++j) {
             const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[(2 * j) & 15], 0.f);
             const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[(2 * j + 1) & 15], 0.f);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+            pk[j] = pk2<HALF>(a, b);
           }
           uint4* d = reinterpret_cast<uint4*>(out + (((size_t)img * 32 + 2 * qy + py) * 32 + 2 * qx) * 16);
 #pragma unroll
@@ -734,24 +750,32 @@ ae_dec2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // dec2 weights [32][16][3][3] (ConvTranspose2d: in, out, ky, kx) -> bf16 [oc][(tap*2 + half)*16 + icl], ic = half*16 + icl
-__global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p) {
+__global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 16 * 288) {
     const int oc = i / 288, r = i - oc * 288, t = r >> 4, icl = r & 15;
     const int tap = t >> 1, ic = (t & 1) * 16 + icl;
-    p[i] = __float2bfloat16_rn(w[(ic * 16 + oc) * 9 + tap]);
+    const float v = w[(ic * 16 + oc) * 9 + tap];
+    reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // The four small layers (CUDA cores, fp32 math on bf16 activations)
 // ------------------------------------------------------------------------------------------
+template <bool HALF = false>
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    if (HALF) {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = v.x;
+      f[2 * i + 1] = v.y;
+    } else {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
   }
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -759,11 +783,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 // C channels of one pixel: SEG = 1 -> C bf16; SEG = 2 -> [hi C | lo C], value = hi + lo
-template <int SEG, int C>
+template <int SEG, int C, bool HALF = false>
 __device__ __forceinline__ void load_px(const __nv_bfloat16* p, float* v) {
   const uint4* src = reinterpret_cast<const uint4*>(p);
 #pragma unroll
-  for (int q = 0; q < C / 8; ++q) unpack8(__ldg(src + q), v + 8 * q);
+  for (int q = 0; q < C / 8; ++q) unpack8<HALF>(__ldg(src + q), v + 8 * q);
   if (SEG == 2) {
     float l[C];
 #pragma unroll
@@ -772,7 +796,7 @@ __device__ __forceinline__ void load_px(const __nv_bfloat16* p, float* v) {
     for (int i = 0; i < C; ++i) v[i] += l[i];
   }
 }
-template <int SEG, int C, bool RELU>
+template <int SEG, int C, bool RELU, bool HALF = false>
 __device__ __forceinline__ void store_px(__nv_bfloat16* p, const float* a) {
   uint4* d = reinterpret_cast<uint4*>(p);
 #pragma unroll
@@ -782,6 +806,7 @@ __device__ __forceinline__ void store_px(__nv_bfloat16* p, const float* a) {
     for (int j = 0; j < 4; ++j) {
       float x0 = a[8 * q + 2 * j], x1 = a[8 * q + 2 * j + 1];
       if (RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      if (HALF) { h[j] = pk2<true>(x0, x1); continue; }
       const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
       h[j] = *reinterpret_cast<const uint32_t*>(&hh);
       if (SEG == 2) {
@@ -795,7 +820,7 @@ __device__ __forceinline__ void store_px(__nv_bfloat16* p, const float* a) {
 }
 
 // L1: x fp32 [n][3][64][64] -> a1 bf16 [n][32][32][16], one output pixel per thread
-template <int SEG>
+template <int SEG, bool HALF = false>
 __global__ void __launch_bounds__(256) enc1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ a1,
                                                    int64_t n_img) {
@@ -830,7 +855,7 @@ __global__ void __launch_bounds__(256) enc1_kernel(const float* __restrict__ x, 
           for (int o = 0; o < 16; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
         }
       }
-    store_px<SEG, 16, true>(a1 + p * 16 * SEG, acc);
+    store_px<SEG, 16, true, HALF>(a1 + p * 16 * SEG, acc);
   }
 }
 
@@ -951,7 +976,7 @@ __global__ void __launch_bounds__(256) dec2_kernel(const __nv_bfloat16* __restri
 
 // L6: a5 bf16 [n][32][32][16] -> tanh(ConvT 16->3) fp32, squared error against x, per-sample mean.
 // One CTA per sample: 256 threads x 4 quads; fixed-order double reduction (reproducible).
-template <int SEG>
+template <int SEG, bool HALF = false>
 __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __restrict__ a5, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* __restrict__ x,
                                                        float* __restrict__ recon, float* __restrict__ err) {
@@ -982,7 +1007,7 @@ __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __re
         const int iy = qy + dy, ix = qx + dx;
         if (iy >= 32 || ix >= 32) continue;
         float v[16];
-        load_px<SEG, 16>(in + (iy * 32 + ix) * 16 * SEG, v);
+        load_px<SEG, 16, HALF>(in + (iy * 32 + ix) * 16 * SEG, v);
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
           if (py == 0 && dy == 1) continue;
@@ -1021,7 +1046,7 @@ __global__ void __launch_bounds__(256) dec3_mse_kernel(const __nv_bfloat16* __re
   if (threadIdx.x == 0) err[n] = (float)(s_red[0] / 12288.0);
 }
 
-template <int N, bool CONVT, bool SPLIT>
+template <int N, bool CONVT, bool SPLIT, bool HALF = false>
 static int launch_k7(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
                      int64_t batch, int* err, cudaStream_t st) {
   using Cfg = K7Cfg<N, CONVT, SPLIT>;
@@ -1057,12 +1082,12 @@ static int launch_k7(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, cons
   }
   const int64_t tiles = CONVT ? 2 * batch : batch;
   const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
-  ae_k7_kernel<N, CONVT, SPLIT><<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, (int)tiles, err);
+  ae_k7_kernel<N, CONVT, SPLIT, HALF><<<grid, 192, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, (int)tiles, err);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 
-template <int SEG>
+template <int SEG, bool HALF = false>
 static int score_impl(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
                       float* recon_out, cudaStream_t st) {
   const Layout L = layout(batch, SEG);
@@ -1071,14 +1096,14 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
   SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));
-  pack_k7_kernel<SEG><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
+  pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
   SG_LAUNCH_CHECK();
   const int64_t cap = (int64_t)state().sm_count * 8;
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
-  enc1_kernel<SEG><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
+  enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
   SG_LAUNCH_CHECK();
-  if (SEG == 1 && !getenv("SG_AE_ENC2_CUDA")) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
-    pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2));
+  if (HALF || (SEG == 1 && !getenv("SG_AE_ENC2_CUDA"))) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
+    pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2), HALF);
     CUtensorMap ta, tb;
     // a1 [n][32][32][16]: box = 16 ch x (16 columns at stride 2) x (8 rows at stride 2) of one image
     cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
@@ -1094,14 +1119,14 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     if (r2 != SG_OK) return r2;
     const int64_t tiles = 2 * batch;
     const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
-    ae_enc2_tc_kernel<<<grid, 192, Enc2Cfg::kSmemBytes, st>>>(ta, tb, h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
+    ae_enc2_tc_kernel<HALF><<<grid, 192, Enc2Cfg::kSmemBytes, st>>>(ta, tb, h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
   } else {
     enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
   }
   SG_LAUNCH_CHECK();
-  int r = launch_k7<64, false, SEG == 2>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
+  int r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
   if (r != SG_OK) return r;
-  if (SEG == 1 && getenv("SG_AE_TAP_STREAM")) {   // per-tap streaming form kept for A/B timing (bf16 mode)
+  if (SEG == 1 && !HALF && getenv("SG_AE_TAP_STREAM")) {   // per-tap streaming form kept for A/B timing (bf16 mode)
     r = launch_k7<32, true, false>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
     if (r != SG_OK) return r;
   } else {
@@ -1117,11 +1142,11 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     r = encode_tmap(&tb, 2, bf(L.w4), bdims, bstr, bbox);
     if (r != SG_OK) return r;
     const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-    ae_dec1_kernel<SEG><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
+    ae_dec1_kernel<SEG, HALF><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
     SG_LAUNCH_CHECK();
   }
-  if (SEG == 1 && !getenv("SG_AE_DEC2_CUDA")) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
-    pack_dec2_kernel<<<(16 * 288 + 255) / 256, 256, 0, st>>>(h_params[8], bf(L.w5));
+  if (HALF || (SEG == 1 && !getenv("SG_AE_DEC2_CUDA"))) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
+    pack_dec2_kernel<<<(16 * 288 + 255) / 256, 256, 0, st>>>(h_params[8], bf(L.w5), HALF);
     CUtensorMap ta, tb;
     // a4 [n][16][16][32]: box = 16 channels (one half) x 16 columns x 8 rows of one image, shifted by (dx, dy)
     cuuint64_t adims[4] = {32, 16, 16, (cuuint64_t)batch};
@@ -1136,12 +1161,12 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     if (r != SG_OK) return r;
     const int64_t tiles = 2 * batch;
     const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
-    ae_dec2_tc_kernel<<<grid, 192, Dec2Cfg::kSmemBytes, st>>>(ta, tb, h_params[9], bf(L.a5), (int)batch, (int)tiles, err);
+    ae_dec2_tc_kernel<HALF><<<grid, 192, Dec2Cfg::kSmemBytes, st>>>(ta, tb, h_params[9], bf(L.a5), (int)batch, (int)tiles, err);
   } else {
     dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
   }
   SG_LAUNCH_CHECK();
-  dec3_mse_kernel<SEG><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
+  dec3_mse_kernel<SEG, HALF><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1159,8 +1184,13 @@ int sg_ae_tc_init_attributes() {
                                K7Cfg<64, false, true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<32, true, false>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               K7Cfg<64, false, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   return SG_OK;
@@ -1189,9 +1219,11 @@ int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params
 
 int sg_ae_score_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
                    float* err_out, float* recon_out, void* stream) {
-  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3, "conv_mode");
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
   int r = ae_tc_args(x, batch, h_params, workspace, err_out);
   if (r != SG_OK || batch == 0) return r;
+  if (conv_mode == SG_CONV_FP16)
+    return sg::aetc::score_impl<1, true>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
   if (conv_mode == SG_CONV_BF16X3)
     return sg::aetc::score_impl<2>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
   return sg::aetc::score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));

@@ -167,6 +167,8 @@ def test_autoencoder_bf16_conv_mode(sb, golden):
     assert (np.abs(e3 - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2
     e4 = sb.ae_errors(ae, x[:48], "cuda").cpu().numpy()                      # fp32-parity mode on the tensor cores
     assert (np.abs(e4 - ref) / np.maximum(ref, 1e-6)).max() <= 1e-3, (np.abs(e4 - ref) / np.maximum(ref, 1e-6)).max()
+    e6 = sb.ae_errors(ae, x[:48], "cuda", conv_mode="fp16").cpu().numpy()    # fp16 mode: one tensor pass, the fp32 bar
+    assert (np.abs(e6 - ref) / np.maximum(ref, 1e-6)).max() <= 1e-3, (np.abs(e6 - ref) / np.maximum(ref, 1e-6)).max()
     e5 = sb.ae_errors(ae, x[:48], "cuda", conv_mode="fp32_cuda").cpu().numpy()  # plain fp32 on the CUDA cores
     assert (np.abs(e5 - ref) / np.maximum(ref, 1e-6)).max() <= 1e-3
     for n, chunk in ((1, 2048), (5, 2), (48, 17)):

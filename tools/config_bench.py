@@ -222,6 +222,11 @@ def main():
     c["gpu_samples_per_s_32768_resident"] = 32768 / tb
     t32 = gpu_time(lambda: sb.ae_errors(ae, big, dev, chunk=8192), 3, 1)
     c["gpu_samples_per_s_fp32_parity_mode_tensor_cores"] = 32768 / t32
+    t16 = gpu_time(lambda: sb.ae_errors(ae, big, dev, chunk=8192, conv_mode="fp16"), 5, 2)
+    c["gpu_samples_per_s_fp16_mode_32768_resident"] = 32768 / t16
+    e_16 = sb.ae_errors(ae, imgs, dev, conv_mode="fp16").double()
+    e_ref = sb.ae_errors(ae, imgs, dev, conv_mode="fp32_cuda").double()
+    c["max_rel_diff_fp16_vs_fp32cuda"] = float(((e_16 - e_ref).abs() / e_ref).max())
     t32c = gpu_time(lambda: sb.ae_errors(ae, imgs, dev, conv_mode="fp32_cuda"), 3, 1)
     c["gpu_samples_per_s_fp32_cuda_cores"] = 4096 / t32c
     e_tc = sb.ae_errors(ae, imgs, dev).double()
