@@ -52,12 +52,13 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
 // on load and split on store.
 struct Layout {
-  size_t flag, w2, w5, w3, w4, a1, a2, a3, a4, a5, total;
+  size_t flag, w1, w2, w5, w3, w4, a1, a2, a3, a4, a5, total;
 };
 static Layout layout(int64_t batch, int seg) {
   Layout L;
   size_t o = 0;
   L.flag = o; o += 1024;
+  L.w1 = o; o += align_up((size_t)16 * 48 * 2, 1024);    // enc1 weights, 16-bit [oc][kh*16 + kw*4 + c] (tensor-core form)
   L.w2 = o; o += align_up((size_t)32 * 144 * 2, 1024);   // enc2 weights, bf16 [oc][tap*16 + ic] (tensor-core form, SEG == 1)
   L.w5 = o; o += align_up((size_t)16 * 288 * 2, 1024);   // dec2 weights, bf16 [oc][(tap*2 + half)*16 + ic] (tensor-core form)
   L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
@@ -446,6 +447,200 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// L1 (enc Conv 3->16 k3 s2 p1 + ReLU) on tcgen05, fused with the fp32 -> 16-bit input conversion (the structure of
+// d64.cu's conv1_fused_kernel: a 3x3 stride-2 pad-1 filter is that kernel's 4x4 stride-2 pad-1 geometry with the
+// fourth filter row / column absent).  One tile = 4 output rows x 32 columns of one image (M = 128), N = 16:
+//   warp 0    : TMA producer, fp32 box [3 ch][10 input rows][64 cols] (row -1 zero-filled by TMA)
+//   warps 6-9 : converters, one output-pixel PAIR per thread and filter row: 128-bit shared-memory loads + two shuffles
+//               give the 3x3x3 patches, packed to the K-major SWIZZLE_32B operand (K = kw*4 + c, 16 per filter row)
+//   warp 1    : three tcgen05.mma (M = 128, N = 16, K = 16), one per filter row
+//   warps 2-5 : epilogue, TMEM -> bias + ReLU -> 16-bit -> 32 contiguous bytes per pixel of a1 [n][32][32][16]
+// The CUDA-core form (one output pixel per thread) took 0.32 ms per 8 192 images; the HBM floor is 0.10 ms.
+// ------------------------------------------------------------------------------------------
+struct Enc1Cfg {
+  static constexpr int kRawBytes = 3 * 10 * 64 * 4;
+  static constexpr int kRawStride = 8192;
+  static constexpr int kRawStages = 3;
+  static constexpr int kSliceA = 128 * 32;      // one filter row of a tile
+  static constexpr int kAStage = 3 * kSliceA;
+  static constexpr int kAStages = 2;
+  static constexpr int kBBytes = 3 * 16 * 32;   // [kh][16 oc x 16 k]
+  static constexpr int kTmemCols = 64;          // 2 accumulators x 16 columns (read 32 wide)
+  static constexpr int kSmemBytes = kAStages * kAStage + 2048 + kRawStages * kRawStride + 256 + 1024;
+  static constexpr int kThreads = 320;
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(320, 2)
+ae_enc1_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int total_tiles, int* err) {
+  using Cfg = Enc1Cfg;
+  constexpr int SA = Cfg::kAStages, SR = Cfg::kRawStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + SA * Cfg::kAStage;
+  const uint32_t r_base = b_base + 2048;
+  const uint32_t bar0 = r_base + SR * Cfg::kRawStride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto rfull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto rempty_bar = [&](int s) { return bar0 + 8u * (SR + s); };
+  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * SR + s); };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * SR + SA + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SR + 2 * SA + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SR + 2 * SA + 2 + a); };
+  constexpr int kNb = 2 * SR + 2 * SA + 4;
+  const uint32_t wbar = bar0 + 8u * kNb;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb + 1);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_x);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < SR; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 128); }
+    for (int s = 0; s < SA; ++s) { mbar_init(afull_bar(s), 128); mbar_init(aempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int kh = 0; kh < 3; ++kh) tma_load_2d(b_base + kh * 512, &tmap_b, wbar, kh * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = tile >> 3, oh0 = (tile & 7) << 2;
+        if (!mbar_wait(rempty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 31)) break;
+        mbar_arrive_expect_tx(rfull_bar(stage), Cfg::kRawBytes);
+        tma_load_4d(r_base + stage * Cfg::kRawStride, &tmap_x, rfull_bar(stage), 0, 2 * oh0 - 1, 0, n);
+        if (++stage == SR) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 32);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 33)) break;
+        if (!mbar_wait(afull_bar(stage), phase, s_abort, err, kErrBase + 32)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 16);
+        const uint32_t sa = base + stage * Cfg::kAStage;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+          umma_f16(tmem_d, umma_desc_sw32(sa + kh * Cfg::kSliceA), umma_desc_sw32(b_base + kh * 512), idesc, (uint32_t)(kh != 0));
+        umma_commit(aempty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == SA) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 6) {
+    // converters: thread = (output row ohl, pixel pair 2p / 2p + 1, lanes 0-15: filter rows 0 and 2, lanes 16-31: row 1)
+    const int ohl = warp - 6, pr = lane & 15, khh = lane >> 4;
+    const int m0 = ohl * 32 + 2 * pr;
+    const uint32_t row_off = (uint32_t)m0 * 32u;
+    const uint32_t c0off = (uint32_t)(((m0 >> 2) & 1) << 4);   // SWIZZLE_32B: 16-byte chunk ^= address bit 7
+    int rs = 0, as = 0;
+    uint32_t rphase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (!mbar_wait(rfull_bar(rs), rphase, s_abort, err, kErrBase + 34)) break;
+      if (!mbar_wait(aempty_bar(as), aphase ^ 1u, s_abort, err, kErrBase + 35)) break;
+      const uint32_t raw = r_base + rs * Cfg::kRawStride + (uint32_t)(pr * 16);
+      const uint32_t dst = base + as * Cfg::kAStage + row_off;
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int kh = khh + 2 * k2;     // lanes 0-15: 0, 2; lanes 16-31: 1, (3 = absent)
+        float px[2][3][3];               // [pixel][kw][c]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          // all lanes run the loads and shuffles (kh == 3 reads filter row 2 again and discards it)
+          const float4 v = ld_shared_f4(raw + (uint32_t)(((c * 10 + 2 * ohl + (kh < 3 ? kh : 2)) * 64) * 4));
+          float l = __shfl_up_sync(0xffffffffu, v.w, 1, 16);
+          if (pr == 0) l = 0.f;          // input column -1
+          px[0][0][c] = l;   px[0][1][c] = v.x; px[0][2][c] = v.y;
+          px[1][0][c] = v.y; px[1][1][c] = v.z; px[1][2][c] = v.w;
+        }
+        if (kh < 3) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t w[8];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              w[2 * kw] = pk2<HALF>(px[q][kw][0], px[q][kw][1]);
+              w[2 * kw + 1] = (uint32_t)pk1<HALF>(px[q][kw][2]);
+            }
+            w[6] = 0u; w[7] = 0u;        // kw = 3 does not exist
+            const uint32_t d = dst + (uint32_t)(kh * Cfg::kSliceA + q * 32);
+            st_shared_v4(d + c0off, w[0], w[1], w[2], w[3]);
+            st_shared_v4(d + (c0off ^ 16u), w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+      mbar_arrive(rempty_bar(rs));
+      fence_proxy_async_smem();
+      mbar_arrive(afull_bar(as));
+      if (++rs == SR) { rs = 0; rphase ^= 1u; }
+      if (++as == SA) { as = 0; aphase ^= 1u; }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;      // tile pixel: output row row >> 5, column row & 31
+    float bo[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) bo[c] = __ldg(bias + c);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n = tile >> 3, oh0 = (tile & 7) << 2;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 36)) break;
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 16), v);   // columns 16.. are not ours
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pk[j] = pk2<HALF>(fmaxf(__uint_as_float(v[2 * j]) + bo[2 * j], 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bo[2 * j + 1], 0.f));
+      uint4* d = reinterpret_cast<uint4*>(out + (((size_t)n * 32 + oh0 + (row >> 5)) * 32 + (row & 31)) * 16);
+      d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// enc1 weights [16][3][3][3] (out, in, ky, kx) -> 16-bit [oc][kh*16 + kw*4 + c] (kw = 3 and c = 3 are zero padding)
+__global__ void pack_enc1_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16 * 48) {
+    const int oc = i / 48, r = i - oc * 48, kh = r >> 4, kw = (r >> 2) & 3, c = r & 3;
+    const float v = (kw < 3 && c < 3) ? w[((oc * 3 + c) * 3 + kh) * 3 + kw] : 0.f;
+    reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
   }
 }
 
@@ -1100,7 +1295,26 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   SG_LAUNCH_CHECK();
   const int64_t cap = (int64_t)state().sm_count * 8;
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
-  enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
+  if ((HALF || (SEG == 1 && !getenv("SG_AE_ENC1_CUDA"))) && ((uintptr_t)x & 15) == 0) {   // tensor-core form
+    pack_enc1_kernel<<<3, 256, 0, st>>>(h_params[0], bf(L.w1), HALF);
+    CUtensorMap tx, tb;
+    cuuint64_t xdims[4] = {64, 64, 3, (cuuint64_t)batch};        // fp32 NCHW input: (w, h, c, n)
+    cuuint64_t xstr[3] = {64 * 4, 64 * 64 * 4, 3 * 64 * 64 * 4};
+    cuuint32_t xbox[4] = {64, 10, 3, 1};
+    int r1 = encode_tmap(&tx, 4, x, xdims, xstr, xbox, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    if (r1 != SG_OK) return r1;
+    cuuint64_t bdims[2] = {48, 16};
+    cuuint64_t bstr[1] = {96};
+    cuuint32_t bbox[2] = {16, 16};
+    r1 = encode_tmap(&tb, 2, bf(L.w1), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r1 != SG_OK) return r1;
+    const int64_t tiles = batch * 8;
+    const int64_t ctas = (int64_t)state().sm_count * 2;
+    ae_enc1_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), Enc1Cfg::kThreads, Enc1Cfg::kSmemBytes, st>>>(
+        tx, tb, h_params[1], bf(L.a1), (int)tiles, err);
+  } else {
+    enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
+  }
   SG_LAUNCH_CHECK();
   if (HALF || (SEG == 1 && !getenv("SG_AE_ENC2_CUDA"))) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
     pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2), HALF);
@@ -1184,6 +1398,8 @@ int sg_ae_tc_init_attributes() {
                                K7Cfg<64, false, true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<32, true, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));

@@ -220,8 +220,8 @@ def test_dbscan_nd_edges(sb):
 
 
 def test_autoencoder_small_layers_tensor_core_vs_cuda_core(sb):
-    """enc2 / dec2 of the bf16 mode run on tcgen05 (stride-2 TMA boxes, parity-class accumulators); the CUDA-core forms
-    stay selectable (SG_AE_ENC2_CUDA / SG_AE_DEC2_CUDA).  With non-trivial weights every tap matters: both forms must
+    """enc1 / enc2 / dec2 of the bf16 mode run on tcgen05 (stride-2 TMA boxes, parity-class accumulators); the CUDA-core forms
+    stay selectable (SG_AE_ENC1_CUDA / SG_AE_ENC2_CUDA / SG_AE_DEC2_CUDA).  With non-trivial weights every tap matters: both forms must
     agree to bf16 weight rounding, and each with the oracle."""
     import os
     torch.manual_seed(11)
@@ -234,14 +234,15 @@ def test_autoencoder_small_layers_tensor_core_vs_cuda_core(sb):
     ref = O.ae_errors(ae, x).numpy()
     got = {}
     try:
-        for name, env in (("tc", {}), ("enc2_cuda", {"SG_AE_ENC2_CUDA": "1"}), ("dec2_cuda", {"SG_AE_DEC2_CUDA": "1"}),
-                          ("both_cuda", {"SG_AE_ENC2_CUDA": "1", "SG_AE_DEC2_CUDA": "1"})):
-            for k in ("SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
+        for name, env in (("tc", {}), ("enc1_cuda", {"SG_AE_ENC1_CUDA": "1"}), ("enc2_cuda", {"SG_AE_ENC2_CUDA": "1"}),
+                          ("dec2_cuda", {"SG_AE_DEC2_CUDA": "1"}),
+                          ("both_cuda", {"SG_AE_ENC1_CUDA": "1", "SG_AE_ENC2_CUDA": "1", "SG_AE_DEC2_CUDA": "1"})):
+            for k in ("SG_AE_ENC1_CUDA", "SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             got[name] = sb.ae_errors(ae, x, "cuda", conv_mode="bf16").cpu().numpy()
     finally:
-        for k in ("SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
+        for k in ("SG_AE_ENC1_CUDA", "SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
             os.environ.pop(k, None)
     for name, e in got.items():
         assert (np.abs(e - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2, name
