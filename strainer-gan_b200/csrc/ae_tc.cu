@@ -52,7 +52,7 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
 // on load and split on store.
 struct Layout {
-  size_t flag, w1, w2, w5, w3, w4, a1, a2, a3, a4, a5, total;
+  size_t flag, w1, w2, w5, w6, w3, w4, a1, a2, a3, a4, a5, part, total;
 };
 static Layout layout(int64_t batch, int seg) {
   Layout L;
@@ -61,6 +61,7 @@ static Layout layout(int64_t batch, int seg) {
   L.w1 = o; o += align_up((size_t)16 * 48 * 2, 1024);    // enc1 weights, 16-bit [oc][kh*16 + kw*4 + c] (tensor-core form)
   L.w2 = o; o += align_up((size_t)32 * 144 * 2, 1024);   // enc2 weights, bf16 [oc][tap*16 + ic] (tensor-core form, SEG == 1)
   L.w5 = o; o += align_up((size_t)16 * 288 * 2, 1024);   // dec2 weights, bf16 [oc][(tap*2 + half)*16 + ic] (tensor-core form)
+  L.w6 = o; o += align_up((size_t)16 * 144 * 2, 1024);   // dec3 weights, 16-bit [oc (3 of 16)][tap*16 + ic] (tensor-core form)
   L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
   L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
   L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
@@ -68,6 +69,7 @@ static Layout layout(int64_t batch, int seg) {
   L.a3 = o; o += align_up(kAct3 * seg * batch, 1024);
   L.a4 = o; o += align_up(kAct4 * seg * batch, 1024);
   L.a5 = o; o += align_up(kAct5 * seg * batch, 1024);
+  L.part = o; o += align_up((size_t)batch * 8 * sizeof(double), 1024);   // per-tile squared-error sums (dec3 tensor-core form)
   L.total = o;
   return L;
 }
@@ -956,6 +958,182 @@ __global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// L6 (dec ConvT 16->3 k3 s2 p1 op1 + tanh) + squared error against the input, on tcgen05.  Same gather form as L5:
+// one tile = 4 x 32 quads of one image (M = 128, 8 tiles per image), four shifted 16-channel windows per tile (4 TMA
+// boxes of 4 KB), nine K = 16 MMAs into four N = 16 accumulators (3 of the 16 columns are real output channels).
+// The epilogue adds the bias, applies tanh, reads the matching 12 input values (coalesced float2 rows of the fp32
+// NCHW image), and reduces the squared differences in a fixed order: thread (double) -> warp butterfly -> the four
+// warps in order -> partial[image][tile]; ae_mse_finish_kernel adds the 8 tile sums of an image in order.
+// ------------------------------------------------------------------------------------------
+struct Dec3Cfg {
+  static constexpr int kPart = 128 * 32;
+  static constexpr int kStageBytes = 4 * kPart;   // 16 KB per tile
+  static constexpr int kStages = 3;
+  static constexpr int kBBytes = 9 * 512;
+  static constexpr int kTmemCols = 128;           // 2 buffers x 4 classes x 16 columns
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 512 + 256 + 1024;
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(192, 3)
+ae_dec3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ recon,
+                  double* __restrict__ partial, int total_tiles, int* err) {
+  using Cfg = Dec3Cfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + S * Cfg::kStageBytes;
+  const uint32_t bar0 = b_base + Cfg::kBBytes + 512;
+  double* s_part = reinterpret_cast<double*>(smem + (b_base + Cfg::kBBytes - base));   // [2][4] warp sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(b_base + t * 512, &tmap_b, wbar, t * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int img = tile >> 3, qy0 = (tile & 7) * 4;
+        if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 41)) break;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int part = 0; part < 4; ++part)     // part = dy*2 + dx
+          tma_load_4d(sa + part * Cfg::kPart, &tmap_a, full_bar(stage), 0, part & 1, qy0 + (part >> 1), img);
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 42);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 43)) break;
+        if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 42)) break;
+        tc_fence_after();
+        const uint32_t sa = base + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+          const int py = cls >> 1, px = cls & 1;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
+          bool first = true;
+#pragma unroll
+          for (int dy = 0; dy <= py; ++dy)
+#pragma unroll
+            for (int dx = 0; dx <= px; ++dx) {
+              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
+              umma_f16(tmem_d, umma_desc_sw32(sa + (dy * 2 + dx) * Cfg::kPart), umma_desc_sw32(b_base + tap * 512), idesc,
+                       first ? 0u : 1u);
+              first = false;
+            }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int qyl = row >> 5, qx = row & 31;
+    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+    int acc = 0, it = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int img = tile >> 3, qy = (tile & 7) * 4 + qyl;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 44)) break;
+      tc_fence_after();
+      uint32_t v0[32], v1[32];   // classes (0,0) (0,1) | (1,0) (1,1), 16 columns each, channels 0..2 real
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+      tmem_ld_32x32(taddr, v0);
+      tmem_ld_32x32(taddr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      const float* xin = x + (size_t)img * 12288;
+      double sq = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          const uint32_t* v = py ? v1 : v0;
+          const int off = (c * 64 + 2 * qy + py) * 64 + 2 * qx;
+          const float r0 = tanhf(__uint_as_float(v[c]) + bc), r1 = tanhf(__uint_as_float(v[16 + c]) + bc);
+          const float2 t = __ldg(reinterpret_cast<const float2*>(xin + off));
+          const float d0 = r0 - t.x, d1 = r1 - t.y;
+          sq += (double)(d0 * d0) + (double)(d1 * d1);
+          if (recon) *reinterpret_cast<float2*>(recon + (size_t)img * 12288 + off) = make_float2(r0, r1);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      double* sp = s_part + (it & 1) * 4;
+      if (lane == 0) sp[lg] = sq;
+      named_bar_sync(1, 128);
+      if (row == 0) partial[tile] = ((sp[0] + sp[1]) + sp[2]) + sp[3];
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+__global__ void ae_mse_finish_kernel(const double* __restrict__ partial, int64_t n_img, float* __restrict__ err) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n < n_img) {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += partial[n * 8 + t];
+    err[n] = (float)(s / 12288.0);
+  }
+}
+
+// dec3 weights [16][3][3][3] (ConvTranspose2d: in, out, ky, kx) -> 16-bit [oc][tap*16 + ic], rows oc >= 3 zero
+__global__ void pack_dec3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16 * 144) {
+    const int oc = i / 144, r = i - oc * 144, tap = r >> 4, ic = r & 15;
+    const float v = oc < 3 ? w[(ic * 3 + oc) * 9 + tap] : 0.f;
+    reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // The four small layers (CUDA cores, fp32 math on bf16 activations)
 // ------------------------------------------------------------------------------------------
 template <bool HALF = false>
@@ -1380,7 +1558,30 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
   }
   SG_LAUNCH_CHECK();
-  dec3_mse_kernel<SEG, HALF><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
+  if ((HALF || (SEG == 1 && !getenv("SG_AE_DEC3_CUDA"))) && ((uintptr_t)x & 7) == 0 && ((uintptr_t)recon_out & 7) == 0) {
+    pack_dec3_kernel<<<(16 * 144 + 255) / 256, 256, 0, st>>>(h_params[10], bf(L.w6), HALF);
+    CUtensorMap ta, tb;
+    // a5 [n][32][32][16]: box = 16 ch x 32 columns x 4 rows of one image, shifted by (dx, dy); row / column 32 -> zeros
+    cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
+    cuuint64_t astr[3] = {32, 1024, 32768};
+    cuuint32_t abox[4] = {16, 32, 4, 1};
+    r = encode_tmap(&ta, 4, bf(L.a5), adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+    cuuint64_t bdims[2] = {144, 16};
+    cuuint64_t bstr[1] = {288};
+    cuuint32_t bbox[2] = {16, 16};
+    r = encode_tmap(&tb, 2, bf(L.w6), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+    const int64_t tiles = 8 * batch;
+    const int64_t ctas = (int64_t)state().sm_count * 3;
+    double* part = reinterpret_cast<double*>(ws + L.part);
+    ae_dec3_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), 192, Dec3Cfg::kSmemBytes, st>>>(
+        ta, tb, h_params[11], x, recon_out, part, (int)tiles, err);
+    SG_LAUNCH_CHECK();
+    ae_mse_finish_kernel<<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
+  } else {
+    dec3_mse_kernel<SEG, HALF><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
+  }
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1398,6 +1599,8 @@ int sg_ae_tc_init_attributes() {
                                K7Cfg<64, false, true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<32, true, false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));

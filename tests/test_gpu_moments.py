@@ -235,14 +235,15 @@ def test_autoencoder_small_layers_tensor_core_vs_cuda_core(sb):
     got = {}
     try:
         for name, env in (("tc", {}), ("enc1_cuda", {"SG_AE_ENC1_CUDA": "1"}), ("enc2_cuda", {"SG_AE_ENC2_CUDA": "1"}),
-                          ("dec2_cuda", {"SG_AE_DEC2_CUDA": "1"}),
-                          ("both_cuda", {"SG_AE_ENC1_CUDA": "1", "SG_AE_ENC2_CUDA": "1", "SG_AE_DEC2_CUDA": "1"})):
-            for k in ("SG_AE_ENC1_CUDA", "SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
+                          ("dec2_cuda", {"SG_AE_DEC2_CUDA": "1"}), ("dec3_cuda", {"SG_AE_DEC3_CUDA": "1"}),
+                          ("both_cuda", {"SG_AE_ENC1_CUDA": "1", "SG_AE_ENC2_CUDA": "1", "SG_AE_DEC2_CUDA": "1",
+                                         "SG_AE_DEC3_CUDA": "1"})):
+            for k in ("SG_AE_ENC1_CUDA", "SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA", "SG_AE_DEC3_CUDA"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             got[name] = sb.ae_errors(ae, x, "cuda", conv_mode="bf16").cpu().numpy()
     finally:
-        for k in ("SG_AE_ENC1_CUDA", "SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA"):
+        for k in ("SG_AE_ENC1_CUDA", "SG_AE_ENC2_CUDA", "SG_AE_DEC2_CUDA", "SG_AE_DEC3_CUDA"):
             os.environ.pop(k, None)
     for name, e in got.items():
         assert (np.abs(e - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2, name
