@@ -23,7 +23,7 @@ def main():
     n = per * world
     netD = O.make_discriminator(O.SEED)
     results = {}
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32", "bf16", "fp16"):
         imgs = sb.synth_images(rank * per, per, O.SEED, device)
         idx, thr, losses = sb.strain_shard(imgs, netD, 0.1, group=dist.group.WORLD, index_base=rank * per,
                                            n_global=n, conv_mode=mode, device=device)
