@@ -45,6 +45,37 @@ def test_dataset_getitem_equals_torchvision(sb):
     assert torch.equal(xb, want[:4]) and yb.tolist() == [0, 1, 2, 3]
 
 
+def test_u8_images_host_logic(sb):
+    """CPU: slicing / fancy indexing / Subset resolution of a uint8 dataset keep pixels, layout and normalisation; the
+    resolver hands Subset-of-Subset chains of uint8 datasets to the scorer as uint8 rows in the right order."""
+    rng = np.random.default_rng(5)
+    px = torch.from_numpy(rng.integers(0, 256, size=(20, 64, 64, 3), dtype=np.uint8))
+    imgs = sb.U8Images(px, (0.4, 0.5, 0.6), (0.2, 0.3, 0.4), layout="NHWC")
+    assert imgs.shape == (20, 3, 64, 64) and len(imgs) == 20 and not imgs.is_cuda
+    part = imgs[3:9]
+    assert isinstance(part, sb.U8Images) and part.shape == (6, 3, 64, 64) and part.mean == imgs.mean and part.layout == "NHWC"
+    assert torch.equal(part.pixels, px[3:9])
+    pick = imgs[np.array([7, 2, 2, 19])]
+    assert torch.equal(pick.pixels, px[[7, 2, 2, 19]])
+    assert torch.equal(pick.host_f32(1), imgs.host_f32(2))
+    ds = sb.U8ImageDataset(imgs, torch.arange(20))
+    sub = torch.utils.data.Subset(torch.utils.data.Subset(ds, [1, 5, 9, 13]), [3, 0])
+    from strainer_gan_b200.api import _dataset_images
+    got = _dataset_images(sub)
+    assert isinstance(got, sb.U8Images) and torch.equal(got.pixels, px[[13, 1]])
+    assert torch.equal(sub[0][0], imgs.host_f32(13)) and int(sub[0][1]) == 13
+    with pytest.raises(ValueError):
+        sb.U8Images(px.float())
+    with pytest.raises(ValueError):
+        sb.U8Images(px, (0.5,), (0.5,), layout="NHWC")
+    with pytest.raises(ValueError):
+        sb.U8Images(px, layout="CHWN")
+    # without a GPU every compute entry point fails loudly (no CPU fallback), including the uint8 path
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            imgs.to_f32()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(7, 3, 64, 64), (3, 1, 28, 28), (2, 4, 5, 3), (1, 3, 16, 16), (0, 3, 64, 64)])
 @pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
