@@ -52,6 +52,15 @@ def _f32c(t: torch.Tensor, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+def _aligned_empty(nbytes: int, device, align: int = 1024) -> torch.Tensor:
+    """uint8 device buffer whose address is a multiple of ``align``: the caching allocator only guarantees 512 bytes (small
+    blocks), the C ABI asks for 1024 (TMA / swizzle atoms) on its workspaces."""
+    n = (int(nbytes) + align - 1) // align * align
+    raw = torch.empty(n + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + n]
+
+
 class _Scratch:
     """Per-device cache of workspaces (caller-owned buffers of the C ABI)."""
     _cache: dict = {}
@@ -62,7 +71,7 @@ class _Scratch:
         t = cls._cache.get(k)
         n = (int(nbytes) + 1023) // 1024 * 1024
         if t is None or t.numel() < n:
-            t = torch.empty(n, dtype=torch.uint8, device=device)
+            t = _aligned_empty(n, device)
             cls._cache[k] = t
         return t
 
@@ -280,9 +289,8 @@ class D64Scorer:
         self.mode_name = mode
         self.mode = _MODES[mode]
         self.max_batch = int(max_batch)
-        self.packed = torch.empty(self.lib.sg_d64_packed_bytes(self.mode), dtype=torch.uint8, device=self.device)
-        self.ws = torch.empty(self.lib.sg_d64_workspace_bytes(self.max_batch, self.mode), dtype=torch.uint8,
-                              device=self.device)
+        self.packed = _aligned_empty(self.lib.sg_d64_packed_bytes(self.mode), self.device)
+        self.ws = _aligned_empty(self.lib.sg_d64_workspace_bytes(self.max_batch, self.mode), self.device)
         self.ws[:1024].zero_()      # status words (pipeline time-out, fp16 overflow)
         self._sig = None
         self.repack(discriminator)

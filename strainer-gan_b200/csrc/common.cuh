@@ -154,6 +154,18 @@ __device__ __forceinline__ void stream_f32(const float* __restrict__ v, int64_t 
   stream_f32_grid<U>(v, n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, f);
 }
 
+// Shared-memory counters in issue-bound streaming loops: atomicAdd on a generic pointer makes the compiler re-derive the
+// shared window (S2UR SR_CgaCtaId / ULEA / IMAD, 4-5 instructions) at every call.  A 32-bit shared address laundered
+// through an asm stays in a register, and red.shared needs no generic -> shared conversion.
+__device__ __forceinline__ uint32_t smem_addr_reg(const void* p) {
+  uint32_t a;
+  asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return a;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

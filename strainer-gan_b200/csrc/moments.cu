@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(512) hist_uniform_kernel(const float* __restri
   // by tests against np.histogram), ~8 instructions less per element.
   const float scale = __fdiv_rn((float)bins, __fsub_rn(last, first));
   const int copy = threadIdx.x & (copies - 1);
+  const uint32_t cnt_base = smem_addr_reg(s_cnt) + (uint32_t)copy * 4u;
   // The edge look-ups (two shared-memory loads per element) are only needed when x sits within rounding
   // distance of an edge: the raw position t = (x - first) * scale carries at most ~3 ulp of relative error and
   // an fp32 linspace edge is within 1 ulp(max |edge|) of its ideal value, i.e. `delta` bins in total.  If the
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(512) hist_uniform_kernel(const float* __restri
       if (x < s_edges[idx]) --idx;
       else if (x >= s_edges[idx + 1] && idx != bins - 1) ++idx;
     }
-    atomicAdd(&s_cnt[idx * copies + copy], 1u);
+    red_shared_add(cnt_base + (uint32_t)(idx * copies) * 4u, 1u);   // see smem_addr_reg: the loop is issue bound
   });
   __syncthreads();
   for (int i = threadIdx.x; i < bins; i += blockDim.x) {

@@ -56,16 +56,17 @@ __global__ void __launch_bounds__(512, 4) hist_kernel(const float* __restrict__ 
   __syncthreads();
   const uint32_t prefix = ws[W_PREFIX];
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t hbase = smem_addr_reg(s_hist) + lane * 4u;   // lane-private column of the [256][32] histogram
   constexpr int kShift = 24 - 8 * PASS;   // digit position
   uint32_t nan_local = 0, min_local = 0xFFFFFFFFu;
   stream_f32<4>(v, n, [&](float f, int64_t) {
     const uint32_t key = float_to_key(f);
     if constexpr (PASS == 0) {
       nan_local += (key == 0xFFFFFFFFu);
-      atomicAdd(&s_hist[((key >> 24) << 5) + lane], 1u);
+      red_shared_add(hbase + ((key >> 24) << 7), 1u);
     } else {
       const uint32_t hi = key >> (kShift + 8);
-      if (hi == prefix) atomicAdd(&s_hist[(((key >> kShift) & 255u) << 5) + lane], 1u);
+      if (hi == prefix) red_shared_add(hbase + (((key >> kShift) & 255u) << 7), 1u);
       if (PASS == 3 && hi > prefix) min_local = min(min_local, key);
     }
   });

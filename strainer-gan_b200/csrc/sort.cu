@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kThreads) hist4_kernel(const float* __restrict
   __shared__ uint32_t s_h[kThreads / 32][1024];
   for (int i = threadIdx.x; i < (kThreads / 32) * 1024; i += kThreads) (&s_h[0][0])[i] = 0;
   __syncthreads();
-  uint32_t* h = s_h[threadIdx.x >> 5];
+  const uint32_t hb = smem_addr_reg(s_h[threadIdx.x >> 5]);
   uint32_t cur[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
   stream_f32<4>(v, n, [&](float x, int64_t) {
     const uint32_t k = float_to_key(x);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads) hist4_kernel(const float* __restrict
     for (int p = 0; p < 4; ++p) {
       const uint32_t d = (k >> (8 * p)) & 255u;
       if (d != cur[p]) {
-        if (cnt[p]) atomicAdd(&h[p * 256 + cur[p]], cnt[p]);
+        if (cnt[p]) red_shared_add(hb + (uint32_t)(p * 256 + cur[p]) * 4u, cnt[p]);
         cur[p] = d;
         cnt[p] = 0;
       }
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) hist4_kernel(const float* __restrict
   });
 #pragma unroll
   for (int p = 0; p < 4; ++p)
-    if (cnt[p]) atomicAdd(&h[p * 256 + cur[p]], cnt[p]);
+    if (cnt[p]) red_shared_add(hb + (uint32_t)(p * 256 + cur[p]) * 4u, cnt[p]);
   __syncthreads();
   for (int i = threadIdx.x; i < 1024; i += kThreads) {
     uint32_t t = 0;

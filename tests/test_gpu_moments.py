@@ -248,3 +248,22 @@ def test_autoencoder_small_layers_tensor_core_vs_cuda_core(sb):
     for name, e in got.items():
         assert (np.abs(e - ref) / np.maximum(ref, 1e-6)).max() <= 2e-2, name
         assert (np.abs(e - got["both_cuda"]) / np.maximum(ref, 1e-6)).max() <= 5e-3, name
+
+
+def test_workspaces_are_1024_aligned_whatever_the_allocator_returns(sb):
+    """torch's caching allocator aligns small blocks to 512 bytes only; the C ABI wants 1024 on its TMA workspaces.  Shift
+    the small pool by 512-byte blocks and request fresh scratch buffers: every one must come back 1024-aligned and the
+    small 512-d DBSCAN call (whose workspace is a small block) must work at any pool offset."""
+    from strainer_gan_b200 import api
+    rng = np.random.default_rng(3)
+    f = torch.from_numpy(rng.standard_normal((300, 64)).astype(np.float32))
+    keep = []
+    for i in range(6):
+        keep.append(torch.empty(512, dtype=torch.uint8, device="cuda"))      # moves the next small block by 512 bytes
+        api._Scratch._cache.clear()
+        t = api._aligned_empty(1000 + 512 * i, torch.device("cuda", 0))
+        assert t.data_ptr() % 1024 == 0 and t.numel() >= 1000 + 512 * i
+        r = sb.dbscan_clean_ratio(f, 9.0, 3)
+        assert 0.0 <= r <= 1.0
+        for (dev, key), buf in api._Scratch._cache.items():
+            assert buf.data_ptr() % 1024 == 0, key
