@@ -34,7 +34,7 @@ import torch.nn.functional as F
 
 # --------------------------------------------------------------------------------------
 # Counter-based synthetic data.  Mirrored bit-for-bit by the CUDA
-# generator ``sg_synth_images`` (strainer-gan_b200/csrc/synth.cu): integer hash only,
+# generator ``sg_synth_images`` (strainer-gan_b200/csrc/api.cu): integer hash only,
 # and the int->float map is exact in fp32, so CPU and GPU agree exactly.
 # --------------------------------------------------------------------------------------
 SEED = 999  # the reference's manualSeed, "#strainer gan.py:38"
@@ -83,6 +83,17 @@ def synth_images(start: int, count: int, seed: int = SEED, nc: int = 3, hw: int 
         vc = (np.uint32(3) * a.astype(np.uint64) + b.astype(np.uint64)) >> np.uint64(2)
     v = np.where(noisy, vn.astype(np.uint64), vc).astype(np.float32)
     return v * np.float32(2.0 ** -23) - np.float32(1.0)
+
+
+def to_tensor_normalize(pixels_u8_nchw: np.ndarray, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)) -> np.ndarray:
+    """The reference's dataset transform tail, ``transforms.ToTensor()`` + ``transforms.Normalize(mean, std)``
+    ("#strainer gan.py:89-90, 115-116"), restated on uint8 NCHW pixels with explicit fp32 steps: x / 255, then
+    (x - mean[c]) / std[c] (IEEE division / subtraction, one rounding each).  Pinned against torchvision itself in
+    tests/test_u8_dataset.py; mirrored bit for bit by ``sg_u8_normalize``."""
+    x = np.asarray(pixels_u8_nchw).astype(np.float32) / np.float32(255)
+    m = np.asarray(mean, np.float32).reshape(1, -1, 1, 1)
+    s = np.asarray(std, np.float32).reshape(1, -1, 1, 1)
+    return (x - m) / s
 
 
 def synth_features(n: int, d: int = 512, seed: int = SEED, outlier_frac: float = 0.1) -> np.ndarray:

@@ -15,11 +15,8 @@ def sb():
 
 
 def host_transform(px_nchw_u8, mean, std):
-    """ToTensor + Normalize restated with numpy fp32 arithmetic (IEEE division / subtraction, one rounding each)."""
-    x = px_nchw_u8.astype(np.float32) / np.float32(255)
-    m = np.asarray(mean, np.float32).reshape(1, -1, 1, 1)
-    s = np.asarray(std, np.float32).reshape(1, -1, 1, 1)
-    return (x - m) / s
+    """ToTensor + Normalize: the oracle's restatement (numpy fp32 arithmetic, one rounding per step)."""
+    return O.to_tensor_normalize(px_nchw_u8, mean, std)
 
 
 def test_dataset_getitem_equals_torchvision(sb):
