@@ -592,7 +592,8 @@ class U8Images:
     def __getitem__(self, key):
         if isinstance(key, slice):
             return self._like(self.pixels[key])
-        return self._like(self.pixels.index_select(0, torch.as_tensor(key, dtype=torch.long, device=self.pixels.device)))
+        idx = torch.as_tensor(key, dtype=torch.long, device=self.pixels.device).reshape(-1)   # an int selects one image
+        return self._like(self.pixels.index_select(0, idx))
 
     def normalize_into(self, src_dev: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         """src_dev: device uint8 rows in this object's layout -> out: fp32 [b,C,H,W] (stream ordered)."""

@@ -55,6 +55,7 @@ def test_u8_images_host_logic(sb):
     pick = imgs[np.array([7, 2, 2, 19])]
     assert torch.equal(pick.pixels, px[[7, 2, 2, 19]])
     assert torch.equal(pick.host_f32(1), imgs.host_f32(2))
+    assert imgs[4].shape == (1, 3, 64, 64) and torch.equal(imgs[4].pixels[0], px[4])
     ds = sb.U8ImageDataset(imgs, torch.arange(20))
     sub = torch.utils.data.Subset(torch.utils.data.Subset(ds, [1, 5, 9, 13]), [3, 0])
     from strainer_gan_b200.api import _dataset_images
