@@ -109,11 +109,24 @@ int sg_d64_score_train(const float* x, int64_t batch, const void* packed, void* 
  * benchmark to time each kernel with events on the launching stream, and by the tests. */
 int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
                      float* logit, float* prob, float* loss, void* stream);
+/* Status words.  The conv kernels bound every mbarrier wait (2 s) and record the role that gave up in word 0; in
+ * SG_CONV_FP16 mode the head records a non-finite logit (an activation beyond 65504) in word 1.  Both words are
+ * STICKY: they live in the first 8 bytes of `workspace` and stay set across calls until sg_d64_check reports and
+ * clears them.  The *_status variants write to a caller-owned, caller-zeroed device int32[2] instead (NULL = the
+ * workspace's words), so that a caller can keep one pair per chunk and re-score exactly the chunks that overflowed
+ * (api.py conv_mode="auto").  In SG_CONV_FP16 mode sg_d64_score_train_status commits the running statistics only if
+ * word 1 is still zero after the head: a batch that overflowed leaves them untouched. */
+int sg_d64_score_status(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
+                        float* logit, float* prob, float* loss, int32_t* status2, void* stream);
+int sg_d64_score_train_status(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
+                              float* bn2_running_mean, float* bn2_running_var, float* bn3_running_mean,
+                              float* bn3_running_var, float* bn4_running_mean, float* bn4_running_var, float momentum,
+                              float bn_eps, float* logit, float* prob, float* loss, int32_t* status2, void* stream);
+/* Synchronises `stream`, reports (SG_ECUDA: pipeline time-out, SG_EINVAL: fp16 overflow) and clears the workspace's
+ * own status words. */
+int sg_d64_check(const void* workspace, void* stream);
 /* debugging / tests: copies the activation of layer `layer` (1..4) of the last sg_d64_score call
  * on `workspace` into fp32 NCHW `out` ([batch,64,32,32], [batch,128,16,16], ...). */
-/* Synchronises `stream` and reports a pipeline time-out recorded by the conv kernels (tests) or, in SG_CONV_FP16
- * mode, a non-finite logit (an activation overflowed fp16; SG_EINVAL, sticky since the last check). */
-int sg_d64_check(const void* workspace, void* stream);
 int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, int layer, float* out,
                            void* stream);
 
@@ -184,6 +197,10 @@ int sg_radix_select(const float* v, int64_t n, int64_t k, uint32_t* ws, float* o
 size_t sg_select_workspace_bytes(int64_t n);
 int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t workspace_bytes, float* out2,
                   void* stream);
+/* Synchronises `stream` and reports (SG_ECUDA) a grid barrier of the cooperative select kernel that gave up after its
+ * 2 s bound -- possible only when the device is time-sliced (MPS, debugger) under the cooperative launch; the order
+ * statistics of that call were written as NaN, never as values from incomplete histograms. */
+int sg_select_check(const void* workspace, void* stream);
 /* thr[0] = lerp(stats2[0], stats2[1], weight) with the named rounding rule */
 int sg_lerp_threshold(const float* stats2, float weight, int lerp_kind, float* thr, void* stream);
 /* Segmented in-block quantile: `segments` consecutive segments of `seg_len` (<= 2048) values each;
@@ -214,6 +231,16 @@ int sg_strain_rows(const float* scores, int64_t n, int k0, int k1, float weight,
                    const void* rows, int64_t row_bytes, void* kept, void* dropped, uint8_t* mask_out, float* thr_out,
                    int64_t* counts_out, void* workspace, void* stream);
 
+/* The same with the torch.cat of ":268" fused away: `concat` is ONE buffer of n rows; the dropped rows (the strained
+ * reals that join the fake batch) are written to its rows [#kept, n) -- straight behind the #kept rows the generator
+ * output is then copied to by sg_concat_rows -- instead of to a buffer of their own. */
+int sg_strain_rows_concat(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp,
+                          const void* rows, int64_t row_bytes, void* kept, void* concat, uint8_t* mask_out, float* thr_out,
+                          int64_t* counts_out, void* workspace, void* stream);
+/* out[0..na) = a, out[na..na+nb) = b (rows of row_bytes, a multiple of 16): torch.cat([fake, filtered_fake], 0) of
+ * ":268" as one launch; rows of b that already sit at out + na*row_bytes (sg_strain_rows_concat) are not touched. */
+int sg_concat_rows(const void* a, int64_t na, const void* b, int64_t nb, int64_t row_bytes, void* out, void* stream);
+
 /* out[i] = rows[idx[i]] for i < count (count read from *count_dev if non-NULL, else `count`). */
 int sg_gather_rows(const void* rows, int64_t row_bytes, const int64_t* idx, int64_t count,
                    const int64_t* count_dev, void* out, void* stream);
@@ -230,6 +257,10 @@ int sg_chunk_moments(const float* v, int64_t n, double* partial, void* stream);
  * chunk order; thr[0] = (float)mean + k * (float)std as torch evaluates it in fp32. */
 int sg_moments_finish(const double* partial, int64_t chunks, int64_t n, float k, double* stats, float* thr,
                       void* stream);
+/* out[i] = (float)((v[i] - stats[0]) / std) evaluated in fp64: StandardScaler on a single column
+ * ("# z_score + DBSCAN.py:291") from the stats of sg_moments_finish (stats[1] = unbiased std; ddof 0 rescales it to the
+ * population std StandardScaler uses; a zero std leaves the values unscaled). */
+int sg_standardize(const float* v, int64_t n, const double* stats, int ddof, float* out, void* stream);
 size_t sg_col_moments_workspace_bytes(int64_t n, int d);
 /* mean[d], inv-or-std[d] of the columns of x[n,d]; ddof 1 (torch.std) or 0 (np.std);
  * denom[j] = std_j + eps_add. */

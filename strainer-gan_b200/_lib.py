@@ -33,6 +33,8 @@ _SIGS = {
     "sg_d64_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "sg_d64_score": (c_int, [P, c_int64, P, P, c_int, P, P, P, P]),
     "sg_d64_score_train": (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, c_float, c_float, P, P, P, P]),
+    "sg_d64_score_status": (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P]),
+    "sg_d64_score_train_status": (c_int, [P, c_int64, P, P, c_int, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P]),
     "sg_d64_run_layer": (c_int, [P, c_int64, P, P, c_int, c_int, P, P, P, P]),
     "sg_d64_check": (c_int, [P, P]),
     "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),
@@ -52,12 +54,15 @@ _SIGS = {
     "sg_radix_select": (c_int, [P, c_int64, c_int64, P, P, P]),
     "sg_select_workspace_bytes": (c_size_t, [c_int64]),
     "sg_select_kth": (c_int, [P, c_int64, c_int64, P, c_size_t, P, P]),
+    "sg_select_check": (c_int, [P, P]),
     "sg_lerp_threshold": (c_int, [P, c_float, c_int, P, P]),
     "sg_segment_order_stats": (c_int, [P, c_int64, c_int, c_int, c_int, P, P]),
     "sg_compact_workspace_bytes": (c_size_t, [c_int64]),
     "sg_compact_indices": (c_int, [P, c_int64, P, c_int, c_int64, P, P, P, P, P]),
     "sg_compact_rows": (c_int, [P, c_int64, c_int64, P, P, P, P, P, P]),
     "sg_strain_rows": (c_int, [P, c_int64, c_int, c_int, c_float, c_int, c_int, P, c_int64, P, P, P, P, P, P, P]),
+    "sg_strain_rows_concat": (c_int, [P, c_int64, c_int, c_int, c_float, c_int, c_int, P, c_int64, P, P, P, P, P, P, P]),
+    "sg_concat_rows": (c_int, [P, c_int64, P, c_int64, c_int64, P, P]),
     "sg_gather_rows": (c_int, [P, c_int64, P, c_int64, P, P, P]),
     "sg_sort_workspace_bytes": (c_size_t, [c_int64]),
     "sg_sort_f32": (c_int, [P, c_int64, P, P, P, P]),
@@ -72,6 +77,7 @@ _SIGS = {
     "sg_gmm1d_update": (c_int, [c_int64, c_double, c_double, c_int, P, P]),
     "sg_chunk_moments": (c_int, [P, c_int64, P, P]),
     "sg_moments_finish": (c_int, [P, c_int64, c_int64, c_float, P, P, P]),
+    "sg_standardize": (c_int, [P, c_int64, P, c_int, P, P]),
     "sg_col_moments_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "sg_col_moments": (c_int, [P, c_int64, c_int, c_int, c_float, P, P, P, P]),
     "sg_row_max_absz": (c_int, [P, c_int64, c_int, P, P, P, P]),
@@ -80,7 +86,7 @@ _SIGS = {
 }
 
 _lib = None
-_inited_device = None
+_inited_devices = set()
 
 
 def load():
@@ -110,12 +116,12 @@ def check(rc, what=""):
 
 
 def init(device_index):
-    """Bind the library to a CUDA device (once per process / device)."""
-    global _inited_device
+    """Prepare the library for a CUDA device (once per process and device; per-device state lives in the library,
+    the caller's current device is left untouched)."""
     lib = load()
-    if _inited_device != device_index:
+    if device_index not in _inited_devices:
         check(lib.sg_init(int(device_index)), "sg_init")
-        _inited_device = device_index
+        _inited_devices.add(device_index)
     return lib
 
 

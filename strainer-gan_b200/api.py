@@ -9,6 +9,7 @@ sm_100 GPU or without the built library every entry point raises.
 from __future__ import annotations
 
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -34,12 +35,52 @@ def _dev(device=None) -> torch.device:
     return device
 
 
+class _DevLib:
+    """The C ABI bound to ONE device: every call runs with that device current (the library launches on, and keeps its
+    state per, the current CUDA device), whatever torch's current device is; the caller's device is restored."""
+
+    def __init__(self, lib, index: int):
+        self._lib = lib
+        self._index = index
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        index = self._index
+
+        def call(*args):
+            if torch.cuda.current_device() == index:
+                return fn(*args)
+            with torch.cuda.device(index):
+                return fn(*args)
+        setattr(self, name, call)
+        return call
+
+
+_DEVLIBS: dict = {}
+_ACTIVE = [None]    # device index of the library calls being assembled (set by _lib_for, read by _stream)
+
+
+def _dev_of(x) -> torch.device:
+    """The device an input already lives on (CUDA tensors / U8Images), else torch's current CUDA device."""
+    px = getattr(x, "pixels", x)
+    if isinstance(px, torch.Tensor) and px.is_cuda:
+        return px.device
+    return _dev()
+
+
 def _lib_for(device: torch.device):
-    return L.init(device.index)
+    idx = device.index
+    d = _DEVLIBS.get(idx)
+    if d is None:
+        d = _DevLib(L.init(idx), idx)
+        _DEVLIBS[idx] = d
+    _ACTIVE[0] = idx
+    return d
 
 
 def _stream():
-    return L.P(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream ON THE DEVICE of the call being assembled (not of torch's current device)."""
+    return L.P(torch.cuda.current_stream(_ACTIVE[0]).cuda_stream)
 
 
 def _p(t):
@@ -108,7 +149,11 @@ class _SelectOps:
     exercise the multi-rank protocol on CPU/gloo)."""
 
     def __init__(self, device):
-        self.lib = _lib_for(device)
+        self.device = device
+
+    @property
+    def lib(self):
+        return _lib_for(self.device)
 
     def begin(self, ws, k):
         L.check(self.lib.sg_select_begin(_p(ws), k, _stream()), "sg_select_begin")
@@ -166,6 +211,8 @@ def _lerp_dev(stats2: torch.Tensor, weight, kind: int) -> torch.Tensor:
 def percentile_device(values: torch.Tensor, q, group=None, n_global=None, ops=None) -> torch.Tensor:
     """``np.percentile(values_f32, q)`` evaluated on the GPU; returns a 1-element fp32 device tensor
     holding bit-for-bit numpy's result for python-scalar q (numpy evaluates q and the lerp in fp32)."""
+    if group is not None and n_global is None:
+        n_global = _group_total(values.numel(), group, values.device)   # never rank the global vector by a shard length
     n = values.numel() if n_global is None else int(n_global)
     k0, k1, gamma, gdt = _np_percentile_plan(n, q)
     stats2 = order_stats(values, k0, group, ops)
@@ -252,7 +299,10 @@ def partition_rows(rows: torch.Tensor, mask: torch.Tensor, kept_out=None, droppe
 # ----------------------------------------------------------------------------------------------
 # D64 scoring
 # ----------------------------------------------------------------------------------------------
-_MODES = {"bf16": L.SG_CONV_BF16, "fp32": L.SG_CONV_BF16X3, "bf16x3": L.SG_CONV_BF16X3, "fp16": L.SG_CONV_FP16}
+_MODES = {"bf16": L.SG_CONV_BF16, "fp32": L.SG_CONV_BF16X3, "bf16x3": L.SG_CONV_BF16X3, "fp16": L.SG_CONV_FP16,
+          "auto": L.SG_CONV_FP16}
+_FP16_OVERFLOW = 0x46503136     # status word 1 of the head kernel (csrc/d64.cu: kFp16OverflowMagic)
+_FALLBACK_CHUNK = 1024          # samples per launch group of the fp32-parity re-score of an overflowed chunk
 
 
 def _d64_modules(discriminator: nn.Module):
@@ -272,28 +322,42 @@ def _d64_modules(discriminator: nn.Module):
     return convs, bns
 
 
+def _raise_status(st0: int):
+    raise RuntimeError(f"strainer_b200: the conv pipeline timed out waiting on an mbarrier (role code {st0}: 1x producer, "
+                       "2x mma, 3x accumulator, 4x epilogue); the losses of this call are invalid")
+
+
 class D64Scorer:
     """Packs a reference ``Discriminator``'s weights for the tcgen05 kernels and scores batches:
     eval-mode BN folded into the conv epilogues, sigmoid and BCE-vs-1 fused into the head.
 
-    mode 'bf16': bf16 operands / fp32 accumulate.  mode 'fp32': fp32-parity arithmetic (bf16 hi/lo
-    split, 3 tensor-core passes, ~1e-5 relative on the losses).  mode 'fp16': fp16 operands and activations, one
-    pass at the bf16 mode's speed, losses within 1e-3 of fp32 (measured 2e-4); activations must stay below 65504
-    (``check()`` reports an overflow)."""
+    mode 'auto' (the default of every entry point): fp16 operands and activations with fp32 accumulation -- one tensor
+    pass, losses within 1e-3 of fp32 (measured 2e-4) -- and, for exactly the chunks whose head reported a non-finite
+    logit (an activation beyond fp16's 65504), a second scoring of that chunk in the fp32-parity mode; nothing raises.
+    mode 'fp16': the same kernels without the recovery (an overflow raises).  mode 'fp32' / 'bf16x3': fp32-parity
+    arithmetic (bf16 hi/lo split, 3 tensor-core passes, ~1e-5 relative on the losses).  mode 'bf16': bf16 operands /
+    fp32 accumulate (2e-2 bar, stated separately)."""
 
-    def __init__(self, discriminator: nn.Module, device=None, mode: str = "fp32", max_batch: int = 4096):
+    def __init__(self, discriminator: nn.Module, device=None, mode: str = "auto", max_batch: int = 4096):
         self.device = _dev(device)
-        self.lib = _lib_for(self.device)
         if mode not in _MODES:
             raise ValueError(f"mode must be one of {sorted(_MODES)}")
         self.mode_name = mode
         self.mode = _MODES[mode]
         self.max_batch = int(max_batch)
-        self.packed = _aligned_empty(self.lib.sg_d64_packed_bytes(self.mode), self.device)
-        self.ws = _aligned_empty(self.lib.sg_d64_workspace_bytes(self.max_batch, self.mode), self.device)
-        self.ws[:1024].zero_()      # status words (pipeline time-out, fp16 overflow)
+        lib = self.lib
+        self.packed = _aligned_empty(lib.sg_d64_packed_bytes(self.mode), self.device)
+        self.ws = _aligned_empty(lib.sg_d64_workspace_bytes(self.max_batch, self.mode), self.device)
+        self.ws[:1024].zero_()      # sticky status words (pipeline time-out, fp16 overflow) of calls without a status slice
         self._sig = None
+        self._fallback = None       # 'auto': fp32-parity scorer, built when the first chunk overflows
+        self._stage = {}            # cached staging buffers of the host-streaming path
+        self.fallback_chunks = 0    # chunks (or batches) re-scored since construction
         self.repack(discriminator)
+
+    @property
+    def lib(self):
+        return _lib_for(self.device)
 
     @staticmethod
     def _signature(convs, bns):
@@ -305,11 +369,11 @@ class D64Scorer:
     def repack(self, discriminator: nn.Module, force: bool = False):
         # fast path: same module object, same parameter / buffer tensors, same versions -> nothing to do
         cached = getattr(self, "_mods", None)
-        if cached is not None and cached[0] is discriminator and not force:
+        if cached is not None and cached[0]() is discriminator and not force:
             convs, bns = cached[1], cached[2]
         else:
             convs, bns = _d64_modules(discriminator)
-            self._mods = (discriminator, convs, bns)
+            self._mods = (weakref.ref(discriminator), convs, bns)
         sig = self._signature(convs, bns)
         if sig == self._sig and not force:
             return
@@ -336,18 +400,34 @@ class D64Scorer:
         self._keep = args  # stream-ordered: keep alive until the pack kernels ran
         self._sig = sig
 
-    def score_into(self, x: torch.Tensor, logit=None, prob=None, loss=None):
-        """x: fp32 CUDA [b,3,64,64], b <= max_batch; writes into the given device slices."""
+    def _module(self):
+        m = self._mods[0]()
+        if m is None:
+            raise RuntimeError("the discriminator this scorer was built for no longer exists")
+        return m
+
+    def fallback(self) -> "D64Scorer":
+        """The fp32-parity scorer that re-scores what overflowed fp16 in 'auto' mode (built on first use)."""
+        if self._fallback is None:
+            self._fallback = D64Scorer(self._module(), self.device, "fp32", max_batch=min(self.max_batch, _FALLBACK_CHUNK))
+        else:
+            self._fallback.repack(self._module())
+        return self._fallback
+
+    def score_into(self, x: torch.Tensor, logit=None, prob=None, loss=None, status=None):
+        """x: fp32 CUDA [b,3,64,64], b <= max_batch; writes into the given device slices.  ``status``: a zeroed device
+        int32[2] that receives this launch group's sticky status words (None: the workspace's own, see ``check``)."""
         b = x.shape[0]
         if b > self.max_batch:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
-        L.check(self.lib.sg_d64_score(_p(x), b, _p(self.packed), _p(self.ws), self.mode, _p(logit), _p(prob), _p(loss),
-                                      _stream()), "sg_d64_score")
+        L.check(self.lib.sg_d64_score_status(_p(x), b, _p(self.packed), _p(self.ws), self.mode, _p(logit), _p(prob), _p(loss),
+                                             _p(status), _stream()), "sg_d64_score_status")
 
-    def score_train_into(self, discriminator: nn.Module, x: torch.Tensor, logit=None, prob=None, loss=None):
+    def score_train_into(self, discriminator: nn.Module, x: torch.Tensor, logit=None, prob=None, loss=None, status=None):
         """``netD(x)`` for a netD in TRAIN mode (under no_grad): BatchNorm uses the statistics of this batch
         and its running_mean / running_var / num_batches_tracked are updated exactly as
-        nn.BatchNorm2d does."""
+        nn.BatchNorm2d does.  In the fp16-operand modes the running statistics are committed on
+        the device only if no activation overflowed (the caller then scores the batch again in another mode)."""
         b = x.shape[0]
         if b > self.max_batch:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
@@ -368,16 +448,25 @@ class D64Scorer:
         moms = {bn.momentum for bn in bns}
         if len(moms) != 1 or None in moms:
             raise NotImplementedError("BatchNorm layers with different / cumulative momentum")
-        L.check(self.lib.sg_d64_score_train(_p(x), b, _p(self.packed), _p(self.ws), self.mode, *[_p(t) for t in stats],
-                                            float(moms.pop()), float(bns[0].eps), _p(logit), _p(prob), _p(loss), _stream()),
-                "sg_d64_score_train")
+        L.check(self.lib.sg_d64_score_train_status(_p(x), b, _p(self.packed), _p(self.ws), self.mode, *[_p(t) for t in stats],
+                                                   float(moms.pop()), float(bns[0].eps), _p(logit), _p(prob), _p(loss),
+                                                   _p(status), _stream()), "sg_d64_score_train_status")
+        self._train_back = back
+        self._sig = None  # running stats changed under the packed eval-mode fold
+
+    def commit_train_side_effects(self):
+        """The module-side effects of a train-mode forward that are not written by the kernels: copies back running
+        statistics that do not live on this device, bumps ``num_batches_tracked`` and the version counters of the
+        running statistics (so that every cached fold of this module is rebuilt).  Called once per scored batch."""
+        bns = self._mods[2]
         with torch.no_grad():
-            for t, d in back:
+            for t, d in getattr(self, "_train_back", ()):
                 t.copy_(d)
+            self._train_back = []
             nbt = [bn.num_batches_tracked for bn in bns if bn.track_running_stats and bn.num_batches_tracked is not None]
             if nbt:
                 torch._foreach_add_(nbt, 1)      # one launch for the three counters
-        self._sig = None  # running stats changed under the packed eval-mode fold
+        _bump_versions([t for bn in bns for t in (bn.running_mean, bn.running_var) if t is not None])
 
     def run_layer(self, x, layer: int, logit=None, prob=None, loss=None):
         """One stage (1..5) of score_into on this scorer's workspace (benchmark / tests)."""
@@ -385,6 +474,8 @@ class D64Scorer:
                                           _p(prob), _p(loss), _stream()), "sg_d64_run_layer")
 
     def check(self):
+        """Synchronises and raises if a launch WITHOUT a status slice recorded a pipeline time-out or an fp16 overflow
+        since the last check (the words are sticky; this clears them)."""
         L.check(self.lib.sg_d64_check(_p(self.ws), _stream()), "sg_d64_check")
 
     def read_activation(self, batch: int, layer: int) -> torch.Tensor:
@@ -394,73 +485,126 @@ class D64Scorer:
                 "sg_d64_read_activation")
         return out
 
+    # -- dataset-scale scoring ---------------------------------------------------------------------------------------
+    def _staging(self, key, shape, dtype, pinned=False):
+        t = self._stage.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype).pin_memory() if pinned else torch.empty(shape, dtype=dtype, device=self.device)
+            self._stage[key] = t
+        return t
+
     def score(self, images, want=("loss",)):
         """Scores N images: a fp32 tensor [N,3,64,64] or a ``U8Images`` (uint8 pixels + Normalize, converted on the
         device), CUDA resident or on the host (streamed through double buffers with the H2D copies overlapped with
-        compute; pinned source tensors are copied from directly).  Returns a dict of fp32 device tensors [N]."""
+        compute; pinned source tensors are copied from directly).  Returns a dict of fp32 device tensors [N].
+        Ends with ONE host read of the per-chunk status words: a pipeline time-out raises in every mode, an fp16
+        overflow raises in mode 'fp16' and re-scores the affected chunks in fp32-parity arithmetic in mode 'auto'."""
         n = images.shape[0]
         outs = {k: torch.empty(n, dtype=torch.float32, device=self.device) for k in want}
         u8 = images if isinstance(images, U8Images) else None
         if tuple(images.shape[1:]) != (3, 64, 64) or (u8 is None and images.dtype != torch.float32):
             raise ValueError("images must be float32 [N,3,64,64] or U8Images of 3x64x64 pixels")
+        cb = self.max_batch
+        nchunks = (n + cb - 1) // cb
+        if nchunks == 0:
+            return outs
+        lib = self.lib            # also makes this scorer's device the one _stream() refers to
+        status = torch.zeros((nchunks, 2), dtype=torch.int32, device=self.device)
 
         def sl(name, i, b):
             return outs[name][i:i + b] if name in outs else None
 
-        def score_chunk(x, i, b):
-            self.score_into(x, sl("logit", i, b), sl("prob", i, b), sl("loss", i, b))
+        def score_chunk(x, ci, i, b):
+            self.score_into(x, sl("logit", i, b), sl("prob", i, b), sl("loss", i, b), status[ci])
 
-        cb = self.max_batch
         src = (u8.pixels if u8 is not None else images).contiguous()
         if src.is_cuda:
-            f32 = torch.empty((min(cb, max(n, 1)), 3, 64, 64), dtype=torch.float32, device=self.device) if u8 is not None else None
-            for i in range(0, n, cb):
+            f32 = self._staging("f32_0", (cb, 3, 64, 64), torch.float32) if u8 is not None else None
+            for ci in range(nchunks):
+                i = ci * cb
                 b = min(cb, n - i)
-                score_chunk(u8.normalize_into(src[i:i + b], f32[:b]) if u8 is not None else src[i:i + b], i, b)
-            self._check_fp16()
-            return outs
-        # host path: 2 device buffers (+ 2 pinned staging buffers for a pageable source), copy stream ahead of compute
-        pinned_src = src.is_pinned()
-        main = torch.cuda.current_stream()
-        copy_stream = _copy_stream(self.device)
-        row = tuple(src.shape[1:])
-        dev = [torch.empty((cb,) + row, dtype=src.dtype, device=self.device) for _ in range(2)]
-        f32 = [torch.empty((cb, 3, 64, 64), dtype=torch.float32, device=self.device) for _ in range(2)] if u8 is not None else None
-        pin = None if pinned_src else [torch.empty((cb,) + row, dtype=src.dtype).pin_memory() for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        nchunks = (n + cb - 1) // cb
-        for ci in range(nchunks):
-            s = ci & 1
-            i = ci * cb
-            b = min(cb, n - i)
-            if ci >= 2 and not pinned_src:
-                copied[s].synchronize()  # the H2D copy that last read pin[s] has finished
-            with torch.cuda.stream(copy_stream):
-                if ci >= 2:
-                    copy_stream.wait_event(consumed[s])
-                part = src[i:i + b]
-                if not pinned_src:
-                    pin[s][:b].copy_(part)
-                    part = pin[s][:b]
-                dev[s][:b].copy_(part, non_blocking=True)
-                copied[s].record(copy_stream)
-            main.wait_event(copied[s])
-            if u8 is not None:
-                # the uint8 staging buffer is free again as soon as the conversion has run
-                x = u8.normalize_into(dev[s][:b], f32[s][:b])
-                consumed[s].record(main)
-                score_chunk(x, i, b)
-            else:
-                score_chunk(dev[s][:b], i, b)
-                consumed[s].record(main)
-        self._check_fp16()
+                score_chunk(u8.normalize_into(src[i:i + b], f32[:b]) if u8 is not None else src[i:i + b], ci, i, b)
+        else:
+            # host path: 2 device buffers (+ 2 pinned staging buffers for a pageable source), copy stream ahead of compute.
+            # The buffers are cached on the scorer and only ever touched in this order: the copy stream first waits for
+            # everything already queued on the main stream (an earlier call's kernels may still be reading them).
+            pinned_src = src.is_pinned()
+            main = torch.cuda.current_stream(self.device)
+            copy_stream = _copy_stream(self.device)
+            copy_stream.wait_stream(main)
+            row = tuple(src.shape[1:])
+            dev = [self._staging(f"dev_{k}", (cb,) + row, src.dtype) for k in range(2)]
+            f32 = [self._staging(f"f32_{k}", (cb, 3, 64, 64), torch.float32) for k in range(2)] if u8 is not None else None
+            pin = None if pinned_src else [self._staging(f"pin_{k}", (cb,) + row, src.dtype, pinned=True) for k in range(2)]
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            for ci in range(nchunks):
+                s_ = ci & 1
+                i = ci * cb
+                b = min(cb, n - i)
+                if ci >= 2 and not pinned_src:
+                    copied[s_].synchronize()  # the H2D copy that last read pin[s_] has finished
+                with torch.cuda.stream(copy_stream):
+                    if ci >= 2:
+                        copy_stream.wait_event(consumed[s_])
+                    part = src[i:i + b]
+                    if not pinned_src:
+                        pin[s_][:b].copy_(part)
+                        part = pin[s_][:b]
+                    dev[s_][:b].copy_(part, non_blocking=True)
+                    copied[s_].record(copy_stream)
+                main.wait_event(copied[s_])
+                if u8 is not None:
+                    # the uint8 staging buffer is free again as soon as the conversion has run
+                    x = u8.normalize_into(dev[s_][:b], f32[s_][:b])
+                    consumed[s_].record(main)
+                    score_chunk(x, ci, i, b)
+                else:
+                    score_chunk(dev[s_][:b], ci, i, b)
+                    consumed[s_].record(main)
+            if not pinned_src:
+                copied[(nchunks - 1) & 1].synchronize()   # the cached pinned buffers may be reused by the next call
+        del lib
+        self._resolve(status, images, outs, cb)
         return outs
 
-    def _check_fp16(self):
-        """fp16 mode only: raise if an activation overflowed (one stream sync; the callers read results back anyway)."""
-        if self.mode == L.SG_CONV_FP16:
-            self.check()
+    def _resolve(self, status: torch.Tensor, images, outs, cb: int):
+        """One host read of the status words of a ``score`` call (a stream synchronisation; every caller reads results
+        back right after)."""
+        st = status.cpu().numpy()
+        if st[:, 0].any():
+            _raise_status(int(st[:, 0][st[:, 0] != 0][0]))
+        bad = np.nonzero(st[:, 1] == _FP16_OVERFLOW)[0]
+        if bad.size == 0:
+            return
+        if self.mode_name != "auto":
+            raise RuntimeError("strainer_b200: non-finite logit in the fp16 conv mode: an activation exceeded 65504 (or the "
+                               "input is not finite); use conv_mode='auto' (re-scores such chunks in fp32-parity "
+                               "arithmetic), 'fp32' or 'bf16'")
+        fb = self.fallback()
+        n = images.shape[0]
+        for ci in bad:
+            i0, i1 = int(ci) * cb, min(n, (int(ci) + 1) * cb)
+            part = images[i0:i1]
+            if not isinstance(part, U8Images):
+                part = part.to(self.device)
+            sub = fb.score(part, tuple(outs.keys()))
+            for k, v in outs.items():
+                v[i0:i1].copy_(sub[k])
+            self.fallback_chunks += 1
+
+
+def _bump_versions(tensors):
+    """Tensors that a kernel wrote through raw pointers get their ``_version`` bumped, so that every cache keyed on it
+    (the BN folds of all scorers of this module) is rebuilt."""
+    ts = [t for t in tensors if isinstance(t, torch.Tensor)]
+    if not ts:
+        return
+    try:    # no kernel launch: the counters are host-side objects
+        torch._C._autograd._unsafe_set_version_counter(ts, [t._version + 1 for t in ts])
+    except Exception:
+        with torch.no_grad():
+            torch._foreach_mul_(ts, 1.0)
 
 
 class MLPScorer:
@@ -468,10 +612,13 @@ class MLPScorer:
 
     def __init__(self, discriminator: nn.Module, device=None, max_batch: int = 4096):
         self.device = _dev(device)
-        self.lib = _lib_for(self.device)
         self.max_batch = int(max_batch)
         self.ws = torch.empty(self.lib.sg_mlp_workspace_bytes(self.max_batch), dtype=torch.uint8, device=self.device)
         self.refresh(discriminator)
+
+    @property
+    def lib(self):
+        return _lib_for(self.device)
 
     @staticmethod
     def linears(discriminator):
@@ -503,6 +650,13 @@ class MLPScorer:
 _MLP_SCORERS: dict = {}
 
 
+def _cache_put(cache: dict, key, module: nn.Module, scorer):
+    """Scorer caches hold packed weights and multi-GB workspaces: an entry lives exactly as long as its module (the
+    scorer itself only keeps a weak reference to it)."""
+    cache[key] = scorer
+    weakref.finalize(module, cache.pop, key, None)
+
+
 def get_mlp_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096) -> "MLPScorer":
     """Per-module cache: the weights are uploaded again only when a parameter tensor changed."""
     device = _dev(device)
@@ -510,7 +664,7 @@ def get_mlp_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096)
     sc = _MLP_SCORERS.get(key)
     if sc is None:
         sc = MLPScorer(discriminator, device, max_batch)
-        _MLP_SCORERS[key] = sc
+        _cache_put(_MLP_SCORERS, key, discriminator, sc)
     else:
         sc.refresh(discriminator)
     return sc
@@ -534,16 +688,23 @@ def _copy_stream(device):
 _SCORERS: dict = {}
 
 
-def get_scorer(discriminator: nn.Module, device=None, mode: str = "fp32", max_batch: int = 4096) -> D64Scorer:
+def get_scorer(discriminator: nn.Module, device=None, mode: str = "auto", max_batch: int = 4096) -> D64Scorer:
     device = _dev(device)
     key = (id(discriminator), device.index, mode, max_batch)
     sc = _SCORERS.get(key)
     if sc is None:
         sc = D64Scorer(discriminator, device, mode, max_batch)
-        _SCORERS[key] = sc
+        _cache_put(_SCORERS, key, discriminator, sc)
     else:
         sc.repack(discriminator)
     return sc
+
+
+def clear_scorer_caches():
+    """Drops every cached scorer (packed weights, workspaces, staging buffers) and scratch workspace."""
+    _SCORERS.clear()
+    _MLP_SCORERS.clear()
+    _Scratch._cache.clear()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -654,9 +815,9 @@ def _device_f32_chunks(images, device, chunk: int):
         yield i, _f32c(images[i:i + chunk], device)
 
 
-def _dataset_images(dataset):
-    """Resident image tensor of a dataset if it exposes one (TensorDataset / Subset of it), else
-    materialise it through the dataset's own __getitem__ (host side, as the reference's DataLoader)."""
+def _resident_images(dataset):
+    """The image tensor behind a dataset that exposes one (tensor, U8Images, U8ImageDataset, TensorDataset, Subset of
+    those), else None."""
     from torch.utils.data import Subset, TensorDataset
     if isinstance(dataset, (torch.Tensor, U8Images)):
         return dataset
@@ -665,36 +826,72 @@ def _dataset_images(dataset):
     if isinstance(dataset, TensorDataset):
         return dataset.tensors[0]
     if isinstance(dataset, Subset):
-        base = _dataset_images(dataset.dataset)
+        base = _resident_images(dataset.dataset)
+        if base is None:
+            return None
         idx = np.asarray(dataset.indices).reshape(-1)
         if isinstance(base, U8Images):
             return base[idx]
         return base.index_select(0, torch.as_tensor(idx, dtype=torch.long, device=base.device))
-    return torch.stack([dataset[i][0] for i in range(len(dataset))])
+    return None
+
+
+STREAM_BATCH = 4096      # samples per DataLoader batch when a dataset has to be streamed through __getitem__
+STREAM_WORKERS = 2       # the reference's own loaders use workers=2 ("#strainer gan.py:50")
+
+
+def _iter_image_chunks(dataset, chunk: int = None):
+    """Image batches of a map-style dataset WITHOUT a resident tensor (e.g. an ImageFolder with transforms), through a
+    DataLoader like the reference's ("#strainer gan.py:366": batch_size 64, shuffle False), only with a larger batch:
+    never more than one batch of decoded images is held on the host."""
+    loader = torch.utils.data.DataLoader(dataset, batch_size=chunk or STREAM_BATCH, shuffle=False,
+                                         num_workers=STREAM_WORKERS if len(dataset) > 4 * (chunk or STREAM_BATCH) else 0)
+    for batch in loader:
+        yield batch[0] if isinstance(batch, (list, tuple)) else batch
+
+
+def _dataset_images(dataset):
+    """Resident image tensor of a dataset if it exposes one, else the dataset materialised through its own
+    ``__getitem__`` (small datasets / feature rows only: the scoring entry points stream instead, ``_score_dataset``)."""
+    imgs = _resident_images(dataset)
+    if imgs is not None:
+        return imgs
+    return torch.cat(list(_iter_image_chunks(dataset)), dim=0)
+
+
+def _score_dataset(scorer, dataset, want=("loss",)):
+    """``scorer.score`` over a dataset: in one call when it exposes a resident tensor, else streamed batch by batch
+    through a DataLoader (bounded host memory; the losses are assembled on the device)."""
+    imgs = _resident_images(dataset)
+    if imgs is not None:
+        return scorer.score(imgs, want)
+    parts = [scorer.score(x.contiguous().float(), want) for x in _iter_image_chunks(dataset)]
+    if not parts:
+        return {k: torch.empty(0, dtype=torch.float32, device=scorer.device) for k in want}
+    return {k: torch.cat([p_[k] for p_ in parts]) for k in want}
 
 
 # ----------------------------------------------------------------------------------------------
 # the reference's function boundary
 # ----------------------------------------------------------------------------------------------
-def evaluate_dataset(netD, dataset, device, *, conv_mode: str = "fp32", return_device: bool = False):
+def evaluate_dataset(netD, dataset, device, *, conv_mode: str = "auto", return_device: bool = False):
     """``evaluate_dataset`` ("#clean 분포와 ... .py:272-287", "# 종합 loss.py:315-330"): per-sample
     BCE(D(x), 1) with eval-mode BN (sticky ``netD.eval()``); returns np.ndarray (N,) float32."""
     device = _dev(device)
     netD.eval()
-    images = _dataset_images(dataset)
-    losses = get_scorer(netD, device, conv_mode).score(images, ("loss",))["loss"]
+    losses = _score_dataset(get_scorer(netD, device, conv_mode), dataset, ("loss",))["loss"]
     return losses if return_device else losses.cpu().numpy()
 
 
-def refine_dataset_by_loss(dataset, discriminator, device, loss_ratio=0.2, *, conv_mode: str = "fp32"):
+def refine_dataset_by_loss(dataset, discriminator, device, loss_ratio=0.2, *, conv_mode: str = "auto"):
     """``refine_dataset_by_loss`` ("#strainer gan.py:364-392"): score every sample, threshold at the
     (1-loss_ratio)*100 percentile, keep ``loss < threshold`` in ascending index order.
-    Returns (torch.utils.data.Subset, np.float32 threshold)."""
+    Returns (torch.utils.data.Subset, np.float32 threshold).  conv_mode 'auto' (default): one fp16 tensor pass held to
+    the fp32 bar (1e-3), chunks that overflow fp16 re-scored in fp32-parity arithmetic; 'fp32' / 'bf16' / 'fp16'."""
     device = _dev(device)
     discriminator.eval()  # sticky, as in the reference (SURVEY quirk 1)
-    images = _dataset_images(dataset)
-    n = images.shape[0]
-    losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
+    n = len(dataset)
+    losses = _score_dataset(get_scorer(discriminator, device, conv_mode), dataset, ("loss",))["loss"]
     clean_indices, threshold = select_below_percentile(losses, (1 - loss_ratio) * 100)
     if len(clean_indices) == 0:
         # reference fallback on its (N,1,1)-shaped loss array: argsort along the last axis (len 1) -> zeros
@@ -702,24 +899,45 @@ def refine_dataset_by_loss(dataset, discriminator, device, loss_ratio=0.2, *, co
     return torch.utils.data.Subset(dataset, clean_indices), threshold
 
 
+def _group_total(n_local: int, group, device) -> int:
+    """Global element count of a sharded vector: the sum of the shard lengths over ``group`` (one 8-byte all-reduce)."""
+    import torch.distributed as dist
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
+
+
+def _select_check(device):
+    """After a synchronisation point: raises if the cooperative select kernel of the last call on ``device`` gave up."""
+    ws = _Scratch._cache.get((device.index, "select"))
+    if ws is not None:
+        L.check(_lib_for(device).sg_select_check(_p(ws), _stream()), "sg_select_check")
+
+
 def select_below_percentile(losses: torch.Tensor, q, group=None, index_base: int = 0, n_global=None):
     """threshold = np.percentile(losses, q); indices = np.where(losses < threshold)[0] -- on device.
-    One host sync at the end (count + threshold).  Returns (np.int64 indices, np.float32 threshold)."""
+    One host sync at the end (count + threshold).  With ``group`` the losses are this rank's shard of a global vector
+    of ``n_global`` elements (summed over the group when not given).  Returns (np.int64 indices, np.float32 threshold)."""
+    if group is not None and n_global is None:
+        n_global = _group_total(losses.numel(), group, losses.device)
     thr = percentile_device(losses, q, group, n_global)
     idx, count, _ = compact_indices(losses, thr, L.SG_LT, index_base)
     thr_h = thr.cpu().numpy()[0]
     c = int(count.item())
+    if group is None:
+        _select_check(losses.device)
     return idx[:c].cpu().numpy(), thr_h
 
 
-def strain_shard(images: torch.Tensor, discriminator, loss_ratio=0.2, *, group=None, index_base: int = 0,
-                 n_global=None, conv_mode: str = "fp32", device=None):
+def strain_shard(images, discriminator, loss_ratio=0.2, *, group=None, index_base: int = 0,
+                 n_global=None, conv_mode: str = "auto", device=None):
     """Data-parallel ``refine_dataset_by_loss`` ("#strainer gan.py:364-392") for one rank of a
     sharded dataset: this rank scores ``images`` (global indices index_base ...), the threshold is the
     GLOBAL percentile (only histograms cross NVLink), and the returned kept indices are global.
     Concatenating the per-rank index arrays in rank order reproduces the single-GPU / reference
-    ``np.where`` order.  Returns (np.int64 kept_global_indices, np.float32 threshold, losses_dev)."""
-    device = _dev(device if device is not None else (images.device if images.is_cuda else None))
+    ``np.where`` order.  ``n_global``: total sample count over the group (all-reduced when not given).
+    Returns (np.int64 kept_global_indices, np.float32 threshold, losses_dev)."""
+    device = _dev(device if device is not None else _dev_of(images))
     discriminator.eval()
     losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
     idx, thr = select_below_percentile(losses, (1 - loss_ratio) * 100, group, index_base, n_global)
@@ -754,7 +972,7 @@ class ResidentSubset:
         return int(self.indices.numel())
 
     @classmethod
-    def refine(cls, images, discriminator, loss_ratio=0.2, *, conv_mode: str = "fp32"):
+    def refine(cls, images, discriminator, loss_ratio=0.2, *, conv_mode: str = "auto"):
         """``refine_dataset_by_loss`` ("#strainer gan.py:364-392") without leaving the device."""
         device = _dev(images.pixels.device if isinstance(images, U8Images) else images.device)
         discriminator.eval()
@@ -789,13 +1007,13 @@ class ResidentSubset:
 
 def get_percentile_threshold(losses, percentile=75):
     """"# 종합 loss.py:287-288" on a device (or host) loss vector."""
-    lt = _f32c(losses, _dev()).reshape(-1)
+    lt = _f32c(losses, _dev_of(losses)).reshape(-1)
     return percentile_device(lt, percentile).cpu().numpy()[0]
 
 
 def get_iqr_threshold(losses):
     """"# 종합 loss.py:290-294": Q3 + 1.5 * (Q3 - Q1)."""
-    lt = _f32c(losses, _dev()).reshape(-1)
+    lt = _f32c(losses, _dev_of(losses)).reshape(-1)
     q1 = percentile_device(lt, 25).cpu().numpy()[0]
     q3 = percentile_device(lt, 75).cpu().numpy()[0]
     return q3 + 1.5 * (q3 - q1)
@@ -816,9 +1034,12 @@ class _GmmOps:
 
     def __init__(self, device):
         self.device = device
-        self.lib = _lib_for(device)
         self.ws = torch.empty(self.lib.sg_gmm1d_workspace_bytes(), dtype=torch.uint8, device=device)
         self.sums = self.ws[16 * 8:24 * 8].view(torch.float64)
+
+    @property
+    def lib(self):
+        return _lib_for(self.device)
 
     def prepare(self, losses):
         return _f32c(losses, self.device).reshape(-1)
@@ -844,9 +1065,11 @@ def gmm_fit_device(losses, max_iter: int = 10, tol: float = 1e-2, reg_covar: flo
     iterations from the 25 % / 75 % order statistics instead of a k-means run seeded by the global numpy RNG.
     With ``group`` the losses are this rank's shard: 8 partial sums are all-reduced per iteration, every rank
     obtains the identical fit.  Returns dict(weights, means, stds, n_iter, converged) (float64 numpy)."""
-    ops = ops or _GmmOps(_dev())
+    ops = ops or _GmmOps(_dev_of(losses))
     v = ops.prepare(losses)
     n = v.numel()
+    if group is not None and n_global is None:
+        n_global = _group_total(n, group, v.device)
     n_tot = int(n_global) if n_global is not None else n
     c0 = order_stats(v, (n_tot - 1) // 4, group, select_ops)[0:1]
     c1 = order_stats(v, (3 * (n_tot - 1)) // 4, group, select_ops)[0:1]
@@ -881,7 +1104,7 @@ def get_ensemble_threshold(losses):
 
 
 def _divide(losses, dataset, threshold):
-    lt = _f32c(losses, _dev()).reshape(-1)
+    lt = _f32c(losses, _dev_of(losses)).reshape(-1)
     n = lt.numel()
     idx, count, _ = compact_indices(lt, threshold, L.SG_LT, 0)
     nidx, ncount, _ = compact_indices(lt, threshold, L.SG_LT | L.SG_NOT, 0)  # ~(loss < thr): NaNs are noisy
@@ -905,7 +1128,7 @@ def divide_dataset_ensemble(losses, dataset):
 def zscore_max(features, ddof: int = 1, eps_add: float = 0.0) -> torch.Tensor:
     """max_j |(x_ij - mean_j) / (std_j + eps_add)| per row of a [N, D] feature matrix
     ("#z_score.py:286-291" with ddof=1; "# 1,2,8.py:164-168" with ddof=0, eps_add=1e-7). Device tensor."""
-    device = _dev()
+    device = _dev_of(features)
     lib = _lib_for(device)
     x = _f32c(features, device)
     n, d = x.shape
@@ -922,7 +1145,7 @@ def zscore_max(features, ddof: int = 1, eps_add: float = 0.0) -> torch.Tensor:
 def find_elbow_threshold(z_scores, bins=100):
     """``find_elbow_threshold`` ("#strainer gan.py:291-309").  min/max and the 100-bin histogram run
     on the device with numpy's exact bin arithmetic; the 100-element tail is numpy on the host."""
-    device = _dev()
+    device = _dev_of(z_scores)
     lib = _lib_for(device)
     z = _f32c(z_scores, device).reshape(-1)
     n = z.numel()
@@ -959,12 +1182,20 @@ def _features_of(dataset, feature_extractor, device):
 
 
 def detect_outliers(dataset, feature_extractor, user_threshold=None, *, threshold=None, clean_ratio=None):
-    """The four ``detect_outliers`` variants of the reference, selected by keyword:
-      default / ``user_threshold``  -> "#strainer gan.py:331-360" (elbow or user value; numpy bool)
-      ``threshold=5.0``             -> "#z_score.py:276-294" (fixed, strict <; torch bool)
-      ``clean_ratio=r``             -> "# z_score + DBSCAN.py:305-326" (torch.quantile(max_z, r), <=)
+    """``detect_outliers`` of "#strainer gan.py:331-360" (the canonical script): inlier = max|z| < threshold with the
+    threshold given (``user_threshold``, third positional argument as upstream) or found by ``find_elbow_threshold``;
+    returns a numpy bool array.  The reference defines three MORE functions of this name in other scripts, whose third
+    positional argument means something else; they are exported under their own names so that an unmodified call site
+    can never be routed to the wrong rule silently:
+      ``detect_outliers_fixed(dataset, fe, threshold=5.0)``   "#z_score.py:276-294"  (strict <, torch bool)
+      ``detect_outliers_elbow(dataset, fe)``                  "#z_score + 엘보우 threshold.py:306-330"
+      ``detect_outliers_ratio(dataset, fe, clean_ratio)``     "# z_score + DBSCAN.py:305-326" (torch.quantile, <=)
+    (a script imports the one it defines: ``from strainer_b200 import detect_outliers_ratio as detect_outliers``).
+    The keywords ``threshold=`` / ``clean_ratio=`` select the same variants from this entry point.
     Feature extraction itself (pretrained ResNet18) is out of scope: pass the module, or nn.Identity()
     over a dataset of feature rows."""
+    if sum(v is not None for v in (user_threshold, threshold, clean_ratio)) > 1:
+        raise TypeError("detect_outliers: give at most one of user_threshold, threshold=, clean_ratio=")
     device = _dev()
     mz = zscore_max(_features_of(dataset, feature_extractor, device))
     if clean_ratio is not None:
@@ -979,6 +1210,23 @@ def detect_outliers(dataset, feature_extractor, user_threshold=None, *, threshol
     return mask.bool().cpu().numpy()
 
 
+def detect_outliers_fixed(dataset, feature_extractor, threshold=5.0):
+    """``detect_outliers(dataset, feature_extractor, threshold=5.0)`` of "#z_score.py:276-294": max|z| < threshold
+    (strict), CPU torch.BoolTensor."""
+    return detect_outliers(dataset, feature_extractor, threshold=float(threshold))
+
+
+def detect_outliers_elbow(dataset, feature_extractor):
+    """``detect_outliers(dataset, feature_extractor)`` of "#z_score + 엘보우 threshold.py:306-330": elbow threshold, numpy bool."""
+    return detect_outliers(dataset, feature_extractor)
+
+
+def detect_outliers_ratio(dataset, feature_extractor, clean_ratio):
+    """``detect_outliers(dataset, feature_extractor, clean_ratio)`` of "# z_score + DBSCAN.py:305-326":
+    threshold = torch.quantile(max|z|, clean_ratio), inlier = max|z| <= threshold, CPU torch.BoolTensor."""
+    return detect_outliers(dataset, feature_extractor, clean_ratio=float(clean_ratio))
+
+
 def compute_z_scores(dataset, feature_extractor):
     """``compute_z_scores`` ("# 1,2,8.py:154-170"): np.std (ddof 0) + 1e-7; returns np.ndarray (N,)."""
     device = _dev()
@@ -988,7 +1236,7 @@ def compute_z_scores(dataset, feature_extractor):
 # ---- device sort / 1-D DBSCAN ----------------------------------------------------------------
 def sort_values(values, return_order: bool = False):
     """Ascending stable device radix sort of a 1-D fp32 vector (NaN last)."""
-    device = _dev()
+    device = _dev_of(values)
     lib = _lib_for(device)
     v = _f32c(values, device).reshape(-1)
     n = v.numel()
@@ -1003,7 +1251,7 @@ def dbscan1d_clean_ratio(values, eps, min_samples=3, return_noise: bool = False)
     """Fraction of non-noise points of ``sklearn.cluster.DBSCAN(eps, min_samples)`` applied to a 1-D
     value vector (the north_star's 1-D variant of ``estimate_ratio_dbscan``,
     "# z_score + DBSCAN.py:291-299"); exact: sort + neighbour counts, no O(N^2) neighbour search."""
-    device = _dev()
+    device = _dev_of(values)
     lib = _lib_for(device)
     v = _f32c(values, device).reshape(-1)
     n = v.numel()
@@ -1020,7 +1268,7 @@ def dbscan_clean_ratio(features, eps, min_samples=3, return_counts: bool = False
     ("# z_score + DBSCAN.py:291-299") for an [N, d] feature matrix, d a multiple of 64, on the GPU: column
     standardisation + two thresholded pairwise-distance GEMMs on tcgen05 (core points, then points within eps of
     a core point).  Nothing of size N^2 is stored."""
-    device = _dev()
+    device = _dev_of(features)
     lib = _lib_for(device)
     f = _f32c(features, device)
     n, d = f.shape
@@ -1047,10 +1295,18 @@ def estimate_ratio_dbscan(dataset, eps=20, min_samples=3, feature_extractor=None
     device = _dev()
     feats = _features_of(dataset, feature_extractor, device)
     if feats.dim() == 1 or feats.shape[1] == 1:
-        f = feats.reshape(-1)
-        mean = f.double().mean()
-        std = f.double().std(unbiased=False)
-        return dbscan1d_clean_ratio(((f.double() - mean) / std).float(), eps, min_samples)
+        # StandardScaler on one column: (x - mean) / std (ddof 0) from the library's fixed-order fp64 chunk moments
+        f = feats.reshape(-1).contiguous()
+        lib = _lib_for(device)
+        n = f.numel()
+        chunks = (n + L.SG_MOMENT_CHUNK - 1) // L.SG_MOMENT_CHUNK
+        part = torch.empty(2 * max(chunks, 1), dtype=torch.float64, device=device)
+        stats = torch.empty(2, dtype=torch.float64, device=device)
+        L.check(lib.sg_chunk_moments(_p(f), n, _p(part), _stream()), "sg_chunk_moments")
+        L.check(lib.sg_moments_finish(_p(part), chunks, n, 0.0, _p(stats), L.P(0), _stream()), "sg_moments_finish")
+        z = torch.empty(n, dtype=torch.float32, device=device)
+        L.check(lib.sg_standardize(_p(f), n, _p(stats), 0, _p(z), _stream()), "sg_standardize")
+        return dbscan1d_clean_ratio(z, eps, min_samples)
     if neighbors == "device" and feats.shape[1] % 64 == 0:
         return dbscan_clean_ratio(feats, eps, min_samples)
     from sklearn.cluster import DBSCAN
@@ -1130,11 +1386,20 @@ def detect_outliers_autoencoder(autoencoder, dataset, device, threshold=2.0, *, 
 
 
 # ---- in-batch strain + concat --------------------------------------------------------------------
-def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1, fake: torch.Tensor | None = None):
+def _alias(buf: torch.Tensor, row0: int, rows: int) -> torch.Tensor:
+    """rows [row0, row0 + rows) of ``buf`` as a tensor of its own (same memory, no autograd / view relation)."""
+    out = torch.empty(0, dtype=buf.dtype, device=buf.device)
+    shape = (rows,) + tuple(buf.shape[1:])
+    return out.set_(buf.untyped_storage(), buf.storage_offset() + row0 * buf.stride(0), shape, buf.stride())
+
+
+def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1, *, _extra_status=None):
     """Selection half of the in-batch block ("# 상위 10% 제거해서 fake image에 concate.py:246-249"):
     threshold = torch.quantile(scores, q); mask = scores >= threshold; real[mask], real[~mask] in one
-    pass.  With ``fake`` given the strained rows are written straight behind the fake rows of a
-    pre-sized buffer (the ``torch.cat`` of ":268" fused away); use ``concat_fake`` for autograd."""
+    pass.  For one batch (<= 2048 rows) the strained rows ``real[~mask]`` are written straight to the TAIL of a
+    pre-sized ``[B, ...]`` buffer -- behind the ``B - s`` rows the generator output will occupy -- so that
+    ``concat_fake(fake, filtered_fake)`` (":268") only has to copy the generator rows.
+    Returns (filtered_real, filtered_fake, mask, threshold)."""
     device = real.device
     scores = real_scores.reshape(-1).to(torch.float32).contiguous()
     n = scores.numel()
@@ -1146,46 +1411,58 @@ def strain_scores(real: torch.Tensor, real_scores: torch.Tensor, q: float = 0.1,
         row_bytes = rows[0].numel() * rows.element_size()
         if row_bytes % 16:
             raise ValueError("row size must be a multiple of 16 bytes")
-        kept, dropped = torch.empty_like(rows), torch.empty_like(rows)
+        kept, concat = torch.empty_like(rows), torch.empty_like(rows)
         mask = torch.empty(n, dtype=torch.uint8, device=device)
         thr = torch.empty(1, dtype=torch.float32, device=device)
         counts = torch.empty(2, dtype=torch.int64, device=device)
         ws = _Scratch.get(device, "strain", 8 * n)
-        L.check(lib.sg_strain_rows(_p(scores), n, k0, k1, float(w), L.SG_LERP_TORCH, L.SG_GE, _p(rows), row_bytes,
-                                   _p(kept), _p(dropped), _p(mask), _p(thr), _p(counts), _p(ws), _stream()),
-                "sg_strain_rows")
-        nk, nd = _read_counts(counts)
-        return kept[:nk], dropped[:nd], mask.view(torch.bool), thr[0]
+        L.check(lib.sg_strain_rows_concat(_p(scores), n, k0, k1, float(w), L.SG_LERP_TORCH, L.SG_GE, _p(rows), row_bytes,
+                                          _p(kept), _p(concat), _p(mask), _p(thr), _p(counts), _p(ws), _stream()),
+                "sg_strain_rows_concat")
+        nk, nd = _read_counts(counts, _extra_status)
+        filtered_fake = _alias(concat, nk, nd)
+        filtered_fake._sg_concat_buffer = concat      # concat_fake recognises the pre-placed tail
+        return kept[:nk], filtered_fake, mask.view(torch.bool), thr[0]
     thr = quantile_device(scores, q)
     _, _, mask = compact_indices(scores, thr, L.SG_GE, 0, want_mask=True)
     kept, dropped, counts = partition_rows(real, mask)
-    nk, nd = _read_counts(counts)
+    nk, nd = _read_counts(counts, _extra_status)
     return kept[:nk], dropped[:nd], mask.bool(), thr[0]
 
 
 _PINNED: dict = {}
 
 
-def _read_counts(counts: torch.Tensor):
+def _read_counts(counts: torch.Tensor, extra_status=None):
     """The one synchronisation of the strain block (the reference's boolean indexing has two): the output
-    shapes depend on the counts.  Pinned staging + a stream sync instead of a pageable ``.cpu()``."""
+    shapes depend on the counts.  Pinned staging + a stream sync instead of a pageable ``.cpu()``.  ``extra_status``:
+    a device int32[2] (a scorer's status words) read back in the same synchronisation into ``_PINNED_STATUS``."""
     key = counts.device.index
     h = _PINNED.get(key)
     if h is None:
-        h = torch.empty(2, dtype=torch.int64).pin_memory()
+        h = (torch.empty(2, dtype=torch.int64).pin_memory(), torch.zeros(2, dtype=torch.int32).pin_memory())
         _PINNED[key] = h
-    h.copy_(counts, non_blocking=True)
+    h[0].copy_(counts, non_blocking=True)
+    if extra_status is not None:
+        h[1].copy_(extra_status, non_blocking=True)
     torch.cuda.current_stream(counts.device).synchronize()
+    return int(h[0][0]), int(h[0][1])
+
+
+def _last_status(device) -> tuple:
+    h = _PINNED[device.index][1]
     return int(h[0]), int(h[1])
 
 
-def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "fp32"):
+def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "auto"):
     """The in-batch strain block ("# 상위 10% 제거해서 fake image에 concate.py:243-251"):
     real_scores = netD(real) under no_grad, threshold = torch.quantile(scores, q), mask = scores >= thr.
     netD is used AS IS: in train mode BatchNorm normalises with the batch statistics and its running
     statistics are updated; in eval mode (the state every script that ran a
     dataset-scale strain is in, quirk 1) the folded running statistics are used.
-    Returns (filtered_real, filtered_fake, mask, threshold)."""
+    Returns (filtered_real, filtered_fake, mask, threshold); ``filtered_fake`` already sits behind the generator rows of
+    the batch ``concat_fake`` assembles (":268").  conv_mode as in ``refine_dataset_by_loss``: 'auto' scores in fp16
+    and, if the batch overflowed fp16, once more in fp32-parity arithmetic (the status words travel with the counts)."""
     device = _dev(real.device)
     b = real.shape[0]
     prob = torch.empty(b, dtype=torch.float32, device=device)
@@ -1197,20 +1474,83 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
         sc = get_mlp_scorer(netD, device, max_batch=max(b, 512))
         sc.score_into(_f32c(real.reshape(b, -1), device), None, prob, None)
         return strain_scores(real, prob, q)
-    sc = get_scorer(netD, device, conv_mode, max_batch=max(real.shape[0], 512))
-    if netD.training:
-        sc.score_train_into(netD, real.contiguous(), None, prob, None)
-    else:
-        sc.score_into(real.contiguous(), None, prob, None)
-    out = strain_scores(real, prob, q)
-    sc._check_fp16()
+    sc = get_scorer(netD, device, conv_mode, max_batch=max(b, 512))
+    x = real.contiguous()
+    train = netD.training
+
+    def run(scorer, status):
+        if train:
+            scorer.score_train_into(netD, x, None, prob, None, status)
+        else:
+            scorer.score_into(x, None, prob, None, status)
+        return strain_scores(real, prob, q, _extra_status=status)
+
+    status = torch.zeros(2, dtype=torch.int32, device=device)
+    out = run(sc, status)
+    st0, st1 = _last_status(device)
+    if st0:
+        _raise_status(st0)
+    if st1 == _FP16_OVERFLOW:
+        if sc.mode_name != "auto":
+            raise RuntimeError("strainer_b200: non-finite logit in the fp16 conv mode (an activation exceeded 65504); use "
+                               "conv_mode='auto', 'fp32' or 'bf16'")
+        # the fp16 pass left the running statistics untouched (bn_commit_kernel); score the batch again in fp32 parity
+        sc.fallback_chunks += 1
+        fb = sc.fallback()
+        if fb.max_batch < b:
+            fb = sc._fallback = D64Scorer(netD, device, "fp32", max_batch=b)
+        status.zero_()
+        out = run(fb, status)
+        st0, _ = _last_status(device)
+        if st0:
+            _raise_status(st0)
+        sc = fb
+    if train:
+        sc.commit_train_side_effects()
     return out
 
 
+class _ConcatFake(torch.autograd.Function):
+    """torch.cat([fake, strained], 0) of "# 상위 10% 제거해서 fake image에 concate.py:268" as ONE row-copy launch into a
+    pre-sized buffer; the gradient of the result flows to the generator rows only (the strained reals are data)."""
+
+    @staticmethod
+    def forward(ctx, fake, strained):
+        n1, n2 = fake.shape[0], strained.shape[0]
+        ctx.n1 = n1
+        device = fake.device
+        lib = _lib_for(device)
+        f = fake.contiguous()
+        row_bytes = (f[0].numel() if n1 else strained[0].numel()) * f.element_size()
+        buf = getattr(strained, "_sg_concat_buffer", None)
+        in_place = (buf is not None and buf.shape[0] == n1 + n2 and buf.dtype == f.dtype and buf.device == device
+                    and tuple(buf.shape[1:]) == tuple(f.shape[1:])
+                    and strained.data_ptr() == buf.data_ptr() + n1 * row_bytes)
+        if in_place:
+            out = _alias(buf, 0, n1 + n2)
+            src_b = strained
+        else:
+            out = torch.empty((n1 + n2,) + tuple(f.shape[1:]), dtype=f.dtype, device=device)
+            src_b = strained.contiguous()
+        if row_bytes % 16:
+            raise ValueError("row size must be a multiple of 16 bytes")
+        L.check(lib.sg_concat_rows(_p(f), n1, _p(src_b), n2, row_bytes, _p(out), _stream()), "sg_concat_rows")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad[:ctx.n1], None
+
+
 def concat_fake(fake: torch.Tensor, strained: torch.Tensor) -> torch.Tensor:
-    """``torch.cat([fake, filtered_fake], dim=0)`` (":268"); gradient flows to the generator rows.  The rows
-    come out of ``strain_batch`` already compacted, so this is the reference's own single copy kernel."""
-    return torch.cat([fake, strained], dim=0)
+    """``torch.cat([fake, filtered_fake], dim=0)`` (":268") for the ``filtered_fake`` of ``strain_batch`` /
+    ``strain_scores``: those rows were already written behind the ``fake.size(0)`` generator rows of a pre-sized
+    ``[B, ...]`` buffer, so only the generator rows are copied (one launch) and the buffer is returned; the backward
+    hands ``grad[:fake.size(0)]`` to the generator.  Any other ``strained`` tensor is concatenated by the same kernel
+    into a fresh buffer.  Note: the pre-sized buffer is consumed -- call this once per ``strain_batch`` result."""
+    if fake.dim() != strained.dim() or tuple(fake.shape[1:]) != tuple(strained.shape[1:]) or fake.dtype != strained.dtype:
+        raise ValueError(f"concat_fake: incompatible shapes {tuple(fake.shape)} / {tuple(strained.shape)} or dtypes")
+    return _ConcatFake.apply(fake, strained)
 
 
 def sample_pool(pool: torch.Tensor, b: int, indices: torch.Tensor | None = None) -> torch.Tensor:

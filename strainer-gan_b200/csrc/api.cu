@@ -6,9 +6,17 @@
 namespace sg {
 
 static thread_local char g_err[512] = "ok";
-static DeviceState g_state;
+// One state per CUDA device: every entry point works on the CURRENT device of the calling thread (the Python layer
+// makes the tensor's device current around each call), so a process may drive several GPUs.
+constexpr int kMaxDevices = 64;
+static DeviceState g_states[kMaxDevices];
+static DeviceState g_none;
 
-DeviceState& state() { return g_state; }
+DeviceState& state() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { (void)cudaGetLastError(); return g_none; }
+  return g_states[dev];
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,8 +26,8 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_ready() {
-  if (!g_state.ready) {
-    set_error("sg_init(device) has not succeeded on this process (no sm_100 device bound)");
+  if (!state().ready) {
+    set_error("sg_init(device) has not succeeded for the current CUDA device of this thread (no sm_100 device bound)");
     return SG_ENOINIT;
   }
   return SG_OK;
@@ -71,7 +79,7 @@ int sg_version(void) { return 100; }
 
 const char* sg_last_error_string(void) { return sg::g_err; }
 
-int sg_sm_count(void) { return sg::g_state.sm_count; }
+int sg_sm_count(void) { return sg::state().sm_count; }
 
 int sg_init(int device) {
   int count = 0;
@@ -90,6 +98,11 @@ int sg_init(int device) {
                   prop.minor);
     return SG_EARCH;
   }
+  SG_REQUIRE(device < sg::kMaxDevices, "device index out of range");
+  // the caller's current device is left as it was: attributes are set with `device` current, then it is restored
+  int prev = -1;
+  SG_CUDA(cudaGetDevice(&prev));
+  struct Restore { int d; ~Restore() { if (d >= 0) (void)cudaSetDevice(d); } } restore{prev == device ? -1 : prev};
   SG_CUDA(cudaSetDevice(device));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -98,17 +111,18 @@ int sg_init(int device) {
     sg::set_error("cuTensorMapEncodeTiled not available from the driver");
     return SG_ECUDA;
   }
-  sg::g_state.device = device;
-  sg::g_state.sm_count = prop.multiProcessorCount;
-  sg::g_state.encode_tiled = fn;
-  sg::g_state.ready = true;
+  sg::DeviceState& st = sg::g_states[device];
+  st.device = device;
+  st.sm_count = prop.multiProcessorCount;
+  st.encode_tiled = fn;
+  st.ready = true;
   int r = sg_d64_init_attributes();
   if (r == SG_OK) r = sg_ae_init_attributes();
   if (r == SG_OK) r = sg_select_init_attributes();
   if (r == SG_OK) r = sg_ae_tc_init_attributes();
   if (r == SG_OK) r = sg_dbscan_init_attributes();
   if (r == SG_OK) r = sg_sort_init_attributes();
-  if (r != SG_OK) { sg::g_state.ready = false; return r; }
+  if (r != SG_OK) { st.ready = false; return r; }
   return SG_OK;
 }
 

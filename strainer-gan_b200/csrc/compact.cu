@@ -274,6 +274,23 @@ __global__ void __launch_bounds__(256) move_rows_kernel(const int4* __restrict__
   for (; j < row_vec; j += 256) stg_stream_i4(dst + j, ldg_stream_i4(src + j));
 }
 
+// out[i] = a[i] for i < na, out[na + j] = b[j] behind them: one CTA per row (the concat of the strain block; when the
+// b rows were written in place by sg_strain_rows_concat only the first na CTAs are launched).
+__global__ void __launch_bounds__(256) concat_rows_kernel(const int4* __restrict__ a, int64_t na, const int4* __restrict__ b,
+                                                          int64_t row_vec, int4* __restrict__ out) {
+  const int64_t i = blockIdx.x;
+  const int4* src = (i < na) ? a + i * row_vec : b + (i - na) * row_vec;
+  int4* dst = out + i * row_vec;
+  int64_t j = threadIdx.x;
+  for (; j + 3 * 256 < row_vec; j += 4 * 256) {
+    const int4 p = ldg_stream_i4(src + j), q = ldg_stream_i4(src + j + 256);
+    const int4 r = ldg_stream_i4(src + j + 512), t = ldg_stream_i4(src + j + 768);
+    stg_stream_i4(dst + j, p); stg_stream_i4(dst + j + 256, q);
+    stg_stream_i4(dst + j + 512, r); stg_stream_i4(dst + j + 768, t);
+  }
+  for (; j < row_vec; j += 256) stg_stream_i4(dst + j, ldg_stream_i4(src + j));
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const int4* __restrict__ rows, int64_t row_vec,
                                                           const int64_t* __restrict__ idx,
                                                           const int64_t* __restrict__ count_dev,
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int4* __restrict
 __global__ void __launch_bounds__(1024) strain_small_kernel(const float* __restrict__ v, int n, int pow2, int k0, int k1,
                                                             float w, int lerp_kind, int cmp, float* __restrict__ thr_out,
                                                             uint8_t* __restrict__ mask_out, int64_t* __restrict__ dest,
-                                                            int64_t* __restrict__ counts_out) {
+                                                            int64_t* __restrict__ counts_out, int tail) {
   extern __shared__ uint32_t s_keys[];   // pow2 keys
   __shared__ int s_nan;
   __shared__ float s_thr;
@@ -364,14 +381,17 @@ __global__ void __launch_bounds__(1024) strain_small_kernel(const float* __restr
   __syncthreads();
   const int kept_before = x - c + (wid ? s_wsum[wid - 1] : 0);
   const int total = s_wsum[(blockDim.x >> 5) - 1];
+  // tail: the dropped rows go to rows [total, n) of ONE n-row buffer -- right behind the `total` rows the generator
+  // will write into it ("# 상위 10% 제거해서 fake image에 concate.py:268": cat([fake, filtered_fake]) without the copy)
+  const int dbase = tail ? total : 0;
   if (i0 < n) {
     if (mask_out) mask_out[i0] = (uint8_t)k0f;
-    dest[i0] = k0f ? (int64_t)kept_before : -(int64_t)(i0 - kept_before) - 1;
+    dest[i0] = k0f ? (int64_t)kept_before : -(int64_t)(dbase + i0 - kept_before) - 1;
   }
   if (i1 < n) {
     const int kb = kept_before + (int)k0f;
     if (mask_out) mask_out[i1] = (uint8_t)k1f;
-    dest[i1] = k1f ? (int64_t)kb : -(int64_t)(i1 - kb) - 1;
+    dest[i1] = k1f ? (int64_t)kb : -(int64_t)(dbase + i1 - kb) - 1;
   }
   if (t == 0) { counts_out[0] = total; counts_out[1] = n - total; }
 }
@@ -446,9 +466,9 @@ int sg_compact_rows(const void* rows, int64_t n, int64_t row_bytes, const uint8_
   return SG_OK;
 }
 
-int sg_strain_rows(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp, const void* rows,
-                   int64_t row_bytes, void* kept, void* dropped, uint8_t* mask_out, float* thr_out, int64_t* counts_out,
-                   void* workspace, void* stream) {
+static int strain_rows_impl(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp,
+                            const void* rows, int64_t row_bytes, void* kept, void* dropped, uint8_t* mask_out, float* thr_out,
+                            int64_t* counts_out, void* workspace, int tail, void* stream) {
   using namespace sg::cmp;
   SG_READY();
   SG_REQUIRE(scores && thr_out && counts_out && workspace, "null pointer");
@@ -466,13 +486,45 @@ int sg_strain_rows(const float* scores, int64_t n, int k0, int k1, float weight,
   if (threads < 32) threads = 32;
   int64_t* dest = static_cast<int64_t*>(workspace);
   strain_small_kernel<<<1, threads, pow2 * sizeof(uint32_t), st>>>(scores, (int)n, pow2, k0, k1, weight, lerp_kind, cmp,
-                                                                  thr_out, mask_out, dest, counts_out);
+                                                                  thr_out, mask_out, dest, counts_out, tail);
   SG_LAUNCH_CHECK();
   if (rows != nullptr) {
     move_rows_kernel<<<(unsigned)n, 256, 0, st>>>(static_cast<const int4*>(rows), row_bytes / 16, dest,
                                                   static_cast<int4*>(kept), static_cast<int4*>(dropped));
     SG_LAUNCH_CHECK();
   }
+  return SG_OK;
+}
+
+int sg_strain_rows(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp, const void* rows,
+                   int64_t row_bytes, void* kept, void* dropped, uint8_t* mask_out, float* thr_out, int64_t* counts_out,
+                   void* workspace, void* stream) {
+  return strain_rows_impl(scores, n, k0, k1, weight, lerp_kind, cmp, rows, row_bytes, kept, dropped, mask_out, thr_out,
+                          counts_out, workspace, 0, stream);
+}
+
+int sg_strain_rows_concat(const float* scores, int64_t n, int k0, int k1, float weight, int lerp_kind, int cmp,
+                          const void* rows, int64_t row_bytes, void* kept, void* concat, uint8_t* mask_out, float* thr_out,
+                          int64_t* counts_out, void* workspace, void* stream) {
+  SG_REQUIRE(rows != nullptr && concat != nullptr, "rows / concat buffer");
+  return strain_rows_impl(scores, n, k0, k1, weight, lerp_kind, cmp, rows, row_bytes, kept, concat, mask_out, thr_out,
+                          counts_out, workspace, 1, stream);
+}
+
+int sg_concat_rows(const void* a, int64_t na, const void* b, int64_t nb, int64_t row_bytes, void* out, void* stream) {
+  SG_READY();
+  SG_REQUIRE(na >= 0 && nb >= 0 && na + nb <= 0x7FFFFFFF, "row counts");
+  SG_REQUIRE(row_bytes > 0 && (row_bytes & 15) == 0, "row_bytes must be a positive multiple of 16");
+  if (na + nb == 0) return SG_OK;
+  SG_REQUIRE(out && (na == 0 || a) && (nb == 0 || b), "null pointer");
+  SG_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)out & 15) == 0,
+             "row buffers must be 16-byte aligned");
+  const bool b_in_place = nb == 0 || b == static_cast<const uint8_t*>(out) + (size_t)na * row_bytes;
+  const int64_t grid = na + (b_in_place ? 0 : nb);
+  if (grid == 0) return SG_OK;
+  sg::cmp::concat_rows_kernel<<<(unsigned)grid, 256, 0, sg::as_stream(stream)>>>(
+      static_cast<const int4*>(a), na, static_cast<const int4*>(b), row_bytes / 16, static_cast<int4*>(out));
+  SG_LAUNCH_CHECK();
   return SG_OK;
 }
 

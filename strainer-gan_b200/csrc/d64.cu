@@ -6,8 +6,8 @@
 //   L2  conv 64->128  + BN + LeakyReLU       conv2_swap2_kernel: channel-major accumulator (weights = A), plane reuse
 //   L3  conv 128->256 + BN + LeakyReLU  \    conv_pair2_kernel: CTA pairs (cta_group::2, 256x256 tiles), plane reuse;
 //   L4  conv 256->512 + BN + LeakyReLU  /    fp32 accumulators in TMEM, fused scale/shift/LeakyReLU epilogue
-//       (conv_umma_kernel / conv_pair_kernel / conv2_swap_kernel: the per-tap-streaming forms, kept behind
-//        SG_CONV_SINGLE_CTA / SG_CONV_TAP_STREAM for A/B timing)
+//       (the per-tap-streaming forms of round 1 -- conv_umma_kernel / conv_pair_kernel / conv2_swap_kernel -- are in
+//        the git history; DESIGN.md section 4 records what each step bought)
 //   L5  conv 512->1 k4s1p0 (8192-dot) + sigmoid + BCE: one warp per sample
 //
 // Activation layout between layers ("parity planes"): a 4x4/stride-2/pad-1 conv reads input pixel
@@ -22,7 +22,6 @@
 // A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, i.e. a 3x longer K loop through the same kernel.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -84,7 +83,7 @@ static PackedLayout packed_layout(int mode) {
 }
 
 struct WorkspaceLayout {
-  size_t flag, act1, act2, act3, act4, bnpart, bnss, total;
+  size_t flag, act1, act2, act3, act4, bnpart, bnss, bnrun, total;
   int sega;
 };
 static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
@@ -98,6 +97,8 @@ static WorkspaceLayout workspace_layout(int64_t batch, int mode) {
   L.act4 = o; o += align_up((size_t)batch * 16 * 512 * L.sega * 2, 1024);
   L.bnpart = o; o += align_up((size_t)kBnBlocks * 512 * 2 * sizeof(double), 1024);  // train-mode BN partial sums
   L.bnss = o; o += align_up(2 * 512 * 4, 1024);                                      // batch-stat scale | shift
+  L.bnrun = o; o += align_up(6 * 512 * 4, 1024);   // fp16 mode: pending running_mean | running_var of BN 2..4 (committed
+                                                   // by bn_commit_kernel only if no activation overflowed)
   L.total = o;
   return L;
 }
@@ -190,416 +191,7 @@ struct ConvParams {
   const float* shift;         // [c_out]
   __nv_bfloat16* out;
   int* err;
-  int debug;                  // timing experiments only (results invalid): 1 = weight tile loaded once per stage slot, 2 = same for activations
 };
-
-template <int BLOCK_N>
-struct ConvCfg {
-  static constexpr int kBlockM = 128;
-  static constexpr int kBlockK = 64;
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
-  static constexpr int kThreads = 192;
-};
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-  const uint32_t bar0 = base + S * Cfg::kStageBytes;
-  // barrier slots: full[S] | empty[S] | tmem_full[2] | tmem_empty[2] ; then tmem base slot, abort flag
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
-    }
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int ow_n = 1 << p.ow_log2;
-  const int bh = 1 << p.bh_log2;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
-        int img0, oh0;
-        if (p.tiles_per_img > 1) { img0 = mt / p.tiles_per_img; oh0 = (mt % p.tiles_per_img) * bh; }
-        else { img0 = mt * p.bimg; oh0 = 0; }
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer)) { ok = false; break; }
-          const int seg = ks % p.nseg;
-          const int t2 = ks / p.nseg;
-          const int chunk = t2 % p.nchunk;
-          const int tap = t2 / p.nchunk;
-          const int kh = tap >> 2, kw = tap & 3;
-          const int cc = chunk * 64 + (seg == 1 ? p.c_in : 0);
-          const uint32_t sa = base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_5d(sa, &tmap_a, full_bar(stage), cc, (kw - 1) >> 1, oh0 + ((kh - 1) >> 1),
-                      ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img0);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), ks * 64, nt * BLOCK_N);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles && ok; tile += gridDim.x) {
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc)) break;
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t sa = base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 16): +32 B inside the 128-B swizzle row
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
-          umma_commit(empty_bar(stage));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        if (!ok) break;
-        umma_commit(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    // ================= epilogue (warps 2..5) =================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
-    const int row = lg * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const int ct = p.c_out * p.out_sega;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
-      int img0, oh0;
-      if (p.tiles_per_img > 1) { img0 = mt / p.tiles_per_img; oh0 = (mt % p.tiles_per_img) * bh; }
-      else { img0 = mt * p.bimg; oh0 = 0; }
-      const int img = img0 + (row >> (p.ow_log2 + p.bh_log2));
-      const int rem = row & ((1 << (p.ow_log2 + p.bh_log2)) - 1);
-      const int oh = oh0 + (rem >> p.ow_log2);
-      const int ow = rem & (ow_n - 1);
-      const bool valid = img < p.n_img;
-      size_t off;
-      if (p.out_planes) {
-        const int half = ow_n >> 1;
-        off = ((((size_t)img * 4 + ((oh & 1) * 2 + (ow & 1))) * half + (oh >> 1)) * half + (ow >> 1)) * ct;
-      } else {
-        off = (((size_t)img * ow_n + oh) * ow_n + ow) * ct;
-      }
-      __nv_bfloat16* dst = p.out + off + (size_t)nt * BLOCK_N;
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue)) break;
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#pragma unroll 1
-      for (int cb = 0; cb < BLOCK_N; cb += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + cb, v);
-        tmem_ld_wait();
-        const float* sc = p.scale + nt * BLOCK_N + cb;
-        const float* sh = p.shift + nt * BLOCK_N + cb;
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float a = fmaf(__uint_as_float(v[2 * j]), __ldg(sc + 2 * j), __ldg(sh + 2 * j));
-          float b = fmaf(__uint_as_float(v[2 * j + 1]), __ldg(sc + 2 * j + 1), __ldg(sh + 2 * j + 1));
-          a = a > 0.f ? a : p.slope * a;
-          b = b > 0.f ? b : p.slope * b;
-          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh2 = __float2bfloat16_rn(b);
-          hi[j] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh2) << 16);
-          const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-          const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh2));
-          lo[j] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-        }
-        if (valid) {
-          uint4* d = reinterpret_cast<uint4*>(dst + cb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          if (p.out_sega == 2) {
-            uint4* dl = reinterpret_cast<uint4*>(dst + p.c_out + cb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// L3 / L4 on CTA PAIRS (tcgen05 cta_group::2): one 256(pixel) x 256(cout) tile per pair of SMs.
-// A single-CTA 128x256 tile makes every tcgen05.mma read 12 KB of operands from shared memory per 128
-// tensor cycles while TMA writes the next 48 KB stage: the pipe stalls on shared-memory bandwidth
-// (67-74 % tensor-pipe active in profiles/r1a).  In a pair each CTA stages its own 128 pixels (A, 16 KB)
-// and HALF of the 256 output channels (B, 16 KB); the hardware shares the B halves across the two SMs,
-// so each SM reads 8 KB and receives 32 KB per 512 tensor cycles.
-//   both CTAs : warp 0 TMA producer (loads signal the LEADER's full barrier), warps 2-5 epilogue
-//   leader    : warp 1 issues tcgen05.mma.cta_group::2 (M = 256) and multicasts its commits to both CTAs
-// ------------------------------------------------------------------------------------------
-struct PairCfg {
-  static constexpr int kABytes = 128 * 64 * 2;
-  static constexpr int kBBytes = 128 * 64 * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 6;
-  static constexpr int kTmemCols = 512;
-  static constexpr int kSsBytes = 2 * 512 * 4;   // folded-BN scale | shift of every output channel, staged once
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + kSsBytes + 1024;
-  static constexpr int kThreads = 192;
-};
-
-template <int SEGA>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const ConvParams p) {
-  using Cfg = PairCfg;
-  constexpr int S = Cfg::kStages;
-  constexpr int BLOCK_N = 256;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;   // identical in both CTAs (same kernel, same layout)
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-  const uint32_t bar0 = base + S * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = (rank == 0);
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);     // leader's copy is the live one: its producer's arrive.expect_tx (both CTAs' bytes)
-      mbar_init(empty_bar(s), 1);    // multicast tcgen05.commit of the leader
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);    // multicast tcgen05.commit of the leader
-      mbar_init(tempty_bar(a), 8);   // leader's copy: one elected lane of each of the 2 x 4 epilogue warps
-    }
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  float* s_ss = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);
-  for (int i = threadIdx.x; i < p.c_out; i += Cfg::kThreads) { s_ss[i] = p.scale[i]; s_ss[512 + i] = p.shift[i]; }
-  tc_fence_before();
-  cluster_sync_all();                // peer barriers initialised before any remote arrive / TMA signal
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int ow_n = 1 << p.ow_log2;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
-  if (warp == 0) {
-    // ================= TMA producer (both CTAs) =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
-        const int nt = tile % p.n_tiles;
-        const int mt = 2 * (tile / p.n_tiles) + (int)rank;
-        const int img0 = mt * p.bimg;
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer + 20)) { ok = false; break; }
-          const int seg = ks % p.nseg;
-          const int t2 = ks / p.nseg;
-          const int chunk = t2 % p.nchunk;
-          const int tap = t2 / p.nchunk;
-          const int kh = tap >> 2, kw = tap & 3;
-          const int cc = chunk * 64 + (seg == 1 ? p.c_in : 0);
-          const uint32_t sa = base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-          const bool first_use = (tile == pair && ks < S);
-          const bool load_a = first_use || !(p.debug & 2), load_b = first_use || !(p.debug & 1);
-          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * ((load_a ? Cfg::kABytes : 0) + (load_b ? Cfg::kBBytes : 0)));
-          if (load_a)
-          tma_load_5d_pair(sa, &tmap_a, lead_full, cc, (kw - 1) >> 1, (kh - 1) >> 1,
-                           ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img0);
-          if (load_b)
-          tma_load_2d_pair(sb, &tmap_b, lead_full, ks * 64, nt * BLOCK_N + (int)rank * 128);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      bool ok = true;
-      for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
-        if (!mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 20)) break;
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma + 20)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t sa = base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
-          umma_commit_pair(empty_bar(stage), 3);   // frees this stage in BOTH CTAs
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        if (!ok) break;
-        umma_commit_pair(tfull_bar(acc), 3);       // accumulator ready in BOTH CTAs
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    // ================= epilogue (warps 2..5 of both CTAs): own 128 pixels x 256 channels =================
-    // One warp per scheduler and nothing to hide latency behind: keep the instruction count per column low
-    // (scale/shift as 128-bit shared-memory broadcasts, max-form LeakyReLU, packed conversion, SEGA resolved
-    // at compile time: the lo half only exists in fp32-parity mode).
-    const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const int ct = p.c_out * SEGA;
-    const float slope = p.slope;
-    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
-      const int nt = tile % p.n_tiles;
-      const int mt = 2 * (tile / p.n_tiles) + (int)rank;
-      const int img = mt * p.bimg + (row >> (2 * p.ow_log2));
-      const int rem = row & ((1 << (2 * p.ow_log2)) - 1);
-      const int oh = rem >> p.ow_log2;
-      const int ow = rem & (ow_n - 1);
-      const bool valid = img < p.n_img;
-      size_t off;
-      if (p.out_planes) {
-        const int half = ow_n >> 1;
-        off = ((((size_t)img * 4 + ((oh & 1) * 2 + (ow & 1))) * half + (oh >> 1)) * half + (ow >> 1)) * ct;
-      } else {
-        off = (((size_t)img * ow_n + oh) * ow_n + ow) * ct;
-      }
-      __nv_bfloat16* dst = p.out + off + (size_t)nt * BLOCK_N;
-      const float4* sc4 = reinterpret_cast<const float4*>(s_ss + nt * BLOCK_N);
-      const float4* sh4 = reinterpret_cast<const float4*>(s_ss + 512 + nt * BLOCK_N);
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 20)) break;
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#pragma unroll 2
-      for (int cb = 0; cb < BLOCK_N; cb += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + cb, v);
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 s4 = sc4[(cb >> 2) + q], h4 = sh4[(cb >> 2) + q];
-          float a0 = fmaf(__uint_as_float(v[4 * q]), s4.x, h4.x), a1 = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y);
-          float a2 = fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z), a3 = fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w);
-          a0 = fmaxf(a0, slope * a0); a1 = fmaxf(a1, slope * a1);   // LeakyReLU (0 < slope <= 1; slope 1 = identity)
-          a2 = fmaxf(a2, slope * a2); a3 = fmaxf(a3, slope * a3);
-          const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
-          hi[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
-          hi[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-          if (SEGA == 2) {
-            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-            const __nv_bfloat162 l01 = __floats2bfloat162_rn(a0 - f01.x, a1 - f01.y);
-            const __nv_bfloat162 l23 = __floats2bfloat162_rn(a2 - f23.x, a3 - f23.y);
-            lo[2 * q] = *reinterpret_cast<const uint32_t*>(&l01);
-            lo[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&l23);
-          }
-        }
-        if (valid) {
-          uint4* d = reinterpret_cast<uint4*>(dst + cb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          if (SEGA == 2) {
-            uint4* dl = reinterpret_cast<uint4*>(dst + p.c_out + cb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's barrier, from either CTA
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();   // neither CTA may leave while the peer can still touch its shared memory / barriers / TMEM
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // L3 / L4 on CTA pairs with PLANE REUSE.  conv_pair_kernel streams one activation box per filter tap: every input
@@ -697,15 +289,12 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int ph = plane >> 1, pw = plane & 1;
           if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, p.err, kErrProducer + 30)) { ok = false; break; }
           const uint32_t lead_afull = mapa_shared(afull_bar(aslot), 0);
-          const bool load_a = !(p.debug & 2) || (tile == pair && u < UA);        // timing experiment
-          if (leader) mbar_arrive_expect_tx(afull_bar(aslot), load_a ? 4 * copy_bytes : 0);   // 2 copies x 2 CTAs
+          if (leader) mbar_arrive_expect_tx(afull_bar(aslot), 4 * copy_bytes);   // 2 copies x 2 CTAs
           const int cc = chunk * 64 + aseg * p.c_in;
           const uint32_t ua = base + aslot * Cfg::kUnitBytes;
-          if (load_a) {
           // copy 0: the tap with the smaller kw of this plane; copy 1: the larger.  pw = 1: dw = -1, 0; pw = 0: dw = 0, +1
           tma_load_5d_pair(ua, &tmap_a, lead_afull, cc, pw ? -1 : 0, img0, oh0 + (ph ? -1 : 0), plane);
           tma_load_5d_pair(ua + Cfg::kCopyBytes, &tmap_a, lead_afull, cc, pw ? 0 : 1, img0, oh0 + (ph ? -1 : 0), plane);
-          }
           if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
           const int nb = (SEGA == 2 && aseg == 0) ? 2 : 1;   // A_hi pairs with B_hi and B_lo, A_lo with B_hi only
           for (int t = 0; t < 4 && ok; ++t) {
@@ -716,9 +305,7 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               const int ks = (tap * p.nchunk + chunk) * p.nseg + seg;
               if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, p.err, kErrProducer + 31)) { ok = false; break; }
               const uint32_t lead_bfull = mapa_shared(bfull_bar(bstage), 0);
-              const bool load_b = !(p.debug & 1) || (tile == pair && u == 0);   // timing experiment: weights loaded once
-              if (leader) mbar_arrive_expect_tx(bfull_bar(bstage), load_b ? 2 * Cfg::kBBytes : 0);
-              if (load_b)
+              if (leader) mbar_arrive_expect_tx(bfull_bar(bstage), 2 * Cfg::kBBytes);
               tma_load_2d_pair(b_base + bstage * Cfg::kBBytes, &tmap_b, lead_bfull, ks * 64, nt * BLOCK_N + (int)rank * (BLOCK_N / 2));
               if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
             }
@@ -844,188 +431,6 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// L2 (64 -> 128 channels) with the operands swapped: D^T[cout][pixel] = W * X^T.
-// With only 128 output channels a 128(pixel) x 128(cout) tile makes every tcgen05.mma read as many
-// operand bytes as a 128x256 one for half the math (shared-memory bound, 36 % tensor-pipe active
-// in profiles/r1a).  Here M = the 128 output channels (weights are the A operand), N = the 256
-// pixels of ONE whole 16x16 output image (a single 5-D TMA box), so the instruction is the full
-// 128x256x16 shape.  The accumulator is channel-major: TMEM lane = channel, column = pixel; the
-// epilogue writes one bf16 per lane, a warp covering 64 contiguous bytes of a pixel's channel row.
-// ------------------------------------------------------------------------------------------
-struct Conv2Cfg {
-  static constexpr int kWBytes = 128 * 64 * 2;    // weights tile  [128 cout x 64 k]
-  static constexpr int kXBytes = 256 * 64 * 2;    // pixel tile    [256 px   x 64 k]
-  static constexpr int kStageBytes = kWBytes + kXBytes;
-  static constexpr int kStages = 4;
-  static constexpr int kTmemCols = 512;
-  static constexpr int kStageOut = 128 * 128 * 2;   // half an output image [128 px][128 ch] bf16, transposed for the TMA store
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOut + 256 + 1024;
-  static constexpr int kThreads = 192;
-};
-
-// SEGA == 1 (bf16 mode): the channel-major accumulator is transposed through shared memory ([pixel][channel],
-// 2-byte stores, a warp = 64 contiguous bytes) and leaves as two 5-D TMA stores per image; the direct form
-// (one 2-byte global store per element, 14 % of the kernel in profiles/r1c) is kept for the fp32-parity mode,
-// whose 3x longer main loop hides it.
-template <int SEGA>
-__global__ void __launch_bounds__(192, 1)
-conv2_swap_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                  const __grid_constant__ CUtensorMap tmap_o, const ConvParams p) {
-  using Cfg = Conv2Cfg;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t stg = base + S * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kStageOut);
-  const uint32_t bar0 = stg + Cfg::kStageOut;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 4);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 5);
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_x);
-    prefetch_tensormap(&tmap_w);
-    if (SEGA == 1) prefetch_tensormap(&tmap_o);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, p.err, kErrProducer + 20)) { ok = false; break; }
-          const int seg = ks % p.nseg;
-          const int tap = ks / p.nseg;  // c_in == 64: one channel chunk per tap
-          const int kh = tap >> 2, kw = tap & 3;
-          const uint32_t sw = base + stage * Cfg::kStageBytes;
-          const bool first_use = (img == (int)blockIdx.x && ks < S);
-          const bool load_w = first_use || !(p.debug & 1), load_x = first_use || !(p.debug & 2);   // timing experiments
-          mbar_arrive_expect_tx(full_bar(stage), (load_w ? Cfg::kWBytes : 0) + (load_x ? Cfg::kXBytes : 0));
-          if (load_w) tma_load_2d(sw, &tmap_w, full_bar(stage), ks * 64, 0);
-          if (load_x)
-          tma_load_5d(sw + Cfg::kWBytes, &tmap_x, full_bar(stage), seg == 1 ? 64 : 0, (kw - 1) >> 1, (kh - 1) >> 1,
-                      ((kh - 1) & 1) * 2 + ((kw - 1) & 1), img);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_m128(256);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      bool ok = true;
-      for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 20)) break;
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma + 20)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t sw = base + stage * Cfg::kStageBytes;
-          const uint64_t wdesc = umma_desc_sw128(sw);
-          const uint64_t xdesc = umma_desc_sw128(sw + Cfg::kWBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_d, wdesc + 2 * k, xdesc + 2 * k, idesc, (uint32_t)((ks | k) != 0));
-          umma_commit(empty_bar(stage));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        if (!ok) break;
-        umma_commit(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    const int lg = warp & 3;
-    const int ch = lg * 32 + lane;          // this thread's output channel
-    const float sc = __ldg(p.scale + ch), sh = __ldg(p.shift + ch);
-    const int ct = 128 * p.out_sega;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int img = blockIdx.x; img < p.n_img; img += gridDim.x) {
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, p.err, kErrEpilogue + 20)) break;
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 256);
-      __nv_bfloat16* out_img = p.out + (size_t)img * 4 * 64 * ct + ch;
-      if (SEGA == 1) {
-        const bool issuer = (threadIdx.x == 64);
-        const float slope = p.slope;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          if (issuer) tma_store_wait_read<0>();       // the previous store has finished reading the staging tile
-          named_bar_sync(1, 128);
-#pragma unroll 1
-          for (int pq = 0; pq < 4; ++pq) {
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + half * 128 + pq * 32, v);
-            tmem_ld_wait();
-            // pixel (oh_l = 2*pq + (j >> 4), ow = j & 15) of this half -> staging row (plane, oh_l >> 1, ow >> 1)
-            const uint32_t rbase = stg + (uint32_t)(pq * 8 * 256 + ch * 2);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float a = fmaf(__uint_as_float(v[j]), sc, sh);
-              a = fmaxf(a, slope * a);
-              const int row = (((j >> 4) & 1) * 2 + (j & 1)) * 32 + ((j & 15) >> 1);
-              st_shared_u16(rbase + (uint32_t)(row * 256), __bfloat16_as_ushort(__float2bfloat16_rn(a)));
-            }
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (issuer) {
-            tma_store_5d(&tmap_o, stg, 0, 0, half * 4, 0, img);
-            tma_store_commit();
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int pb = 0; pb < ((p.debug & 4) ? 32 : 256); pb += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + pb, v);
-          tmem_ld_wait();
-  #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int px = pb + j, oh = px >> 4, ow = px & 15;
-            float a = fmaf(__uint_as_float(v[j]), sc, sh);
-            a = a > 0.f ? a : p.slope * a;
-            const __nv_bfloat16 ah = __float2bfloat16_rn(a);
-            __nv_bfloat16* d = out_img + ((size_t)((oh & 1) * 2 + (ow & 1)) * 64 + (oh >> 1) * 8 + (ow >> 1)) * ct;
-            *d = ah;
-            if (p.out_sega == 2) d[128] = __float2bfloat16_rn(a - __bfloat162float(ah));
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-    if (SEGA == 1 && threadIdx.x == 64) tma_store_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -1515,7 +920,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
 // fixed butterfly (deterministic; a single thread walking 256 strided doubles took 55 us per layer).
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int blocks, int64_t rows, int c,
                                                           const float* __restrict__ gb, float eps, float momentum,
-                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                          const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                                          float* __restrict__ new_mean, float* __restrict__ new_var,
                                                           float* __restrict__ ss) {
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -1537,11 +943,22 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
   const float scale = gb[ch] / sqrtf((float)var + eps);
   ss[ch] = scale;
   ss[512 + ch] = gb[c + ch] - (float)mean * scale;
-  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+  if (running_mean) new_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
   if (running_var) {
     const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
-    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+    new_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
   }
+}
+
+// fp16 mode: the running statistics of the three BatchNorm layers become visible only if the whole batch stayed finite
+// (status[1] == 0 after the head): an overflowing batch is scored again in another conv mode by the caller and must
+// update the statistics exactly once.
+struct BnCommitArgs { float* dst[6]; };
+__global__ void __launch_bounds__(512) bn_commit_kernel(const float* __restrict__ pending, const BnCommitArgs a,
+                                                        const int* __restrict__ status) {
+  if (status[1] != 0) return;
+  const int t = blockIdx.x, c = 128 << (t >> 1);
+  if (a.dst[t] && threadIdx.x < c) a.dst[t][threadIdx.x] = pending[t * 512 + threadIdx.x];
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict__ act, int64_t rows, int c, int sega,
@@ -1677,120 +1094,6 @@ static int encode(CUtensorMap* m, int rank, const void* ptr, const cuuint64_t* d
   return encode_tmap(m, rank, ptr, dims, strides, box, swz, dtype);
 }
 
-template <int BLOCK_N>
-static int launch_conv(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
-                       __nv_bfloat16* act_out,
-                       int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega, int out_planes, float slope,
-                       int* err, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
-  const int ow = s_in / 2;
-  int bh = 128 / ow;
-  if (bh > ow) bh = ow;
-  const int bimg = 128 / (ow * bh);
-  const int tiles_per_img = ow / bh;
-  const int ct_in = c_in * sega;
-  CUtensorMap ta, tb;
-  {
-    cuuint64_t dims[5] = {(cuuint64_t)ct_in, (cuuint64_t)ow, (cuuint64_t)ow, 4, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)ow * ct_in * 2, (cuuint64_t)ow * ow * ct_in * 2,
-                             (cuuint64_t)4 * ow * ow * ct_in * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)ow, (cuuint32_t)bh, 1, (cuuint32_t)bimg};
-    int r = encode(&ta, 5, act_in, dims, strides, box);
-    if (r != SG_OK) return r;
-  }
-  const int nchunk = c_in / 64;
-  const int k_steps = 16 * nchunk * nseg;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, (cuuint64_t)c_out};
-    cuuint64_t strides[1] = {(cuuint64_t)k_steps * 64 * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BLOCK_N};
-    int r = encode(&tb, 2, wpk, dims, strides, box);
-    if (r != SG_OK) return r;
-  }
-  ConvParams p;
-  p.n_tiles = c_out / BLOCK_N;
-  const int64_t m_tiles = (tiles_per_img > 1) ? batch * tiles_per_img : ceil_div(batch, bimg);
-  p.total_tiles = (int)(m_tiles * p.n_tiles);
-  p.n_img = (int)batch;
-  p.ow_log2 = __builtin_ctz(ow);
-  p.bh_log2 = __builtin_ctz(bh);
-  p.bimg = bimg;
-  p.tiles_per_img = tiles_per_img;
-  p.c_in = c_in;
-  p.nchunk = nchunk;
-  p.nseg = nseg;
-  p.k_steps = k_steps;
-  p.c_out = c_out;
-  p.out_sega = sega;
-  p.out_planes = out_planes;
-  p.slope = slope;
-  p.scale = scale;
-  p.shift = shift;
-  p.out = act_out;
-  p.err = err;
-  int grid = p.total_tiles < state().sm_count ? p.total_tiles : state().sm_count;
-  conv_umma_kernel<BLOCK_N><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
-}
-
-
-// L3 / L4 on CTA pairs; same arguments as launch_conv<256> (tiles never split an image: s_in <= 16)
-static int launch_conv_pair(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
-                            __nv_bfloat16* act_out, int64_t batch, int s_in, int c_in, int c_out, int nseg, int sega,
-                            int out_planes, float slope, int* err, cudaStream_t stream) {
-  using Cfg = PairCfg;
-  const int ow = s_in / 2;
-  const int bimg = 128 / (ow * ow);
-  const int ct_in = c_in * sega;
-  CUtensorMap ta, tb;
-  {
-    cuuint64_t dims[5] = {(cuuint64_t)ct_in, (cuuint64_t)ow, (cuuint64_t)ow, 4, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)ow * ct_in * 2, (cuuint64_t)ow * ow * ct_in * 2,
-                             (cuuint64_t)4 * ow * ow * ct_in * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)ow, (cuuint32_t)ow, 1, (cuuint32_t)bimg};
-    int r = encode(&ta, 5, act_in, dims, strides, box);
-    if (r != SG_OK) return r;
-  }
-  const int nchunk = c_in / 64;
-  const int k_steps = 16 * nchunk * nseg;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, (cuuint64_t)c_out};
-    cuuint64_t strides[1] = {(cuuint64_t)k_steps * 64 * 2};
-    cuuint32_t box[2] = {64, 128};   // each CTA of a pair stages half of the 256 output channels
-    int r = encode(&tb, 2, wpk, dims, strides, box);
-    if (r != SG_OK) return r;
-  }
-  ConvParams p = {};
-  p.n_tiles = c_out / 256;
-  const int64_t m_tiles = ceil_div(batch, bimg);
-  p.total_tiles = (int)(ceil_div(m_tiles, 2) * p.n_tiles);   // PAIR tiles
-  p.n_img = (int)batch;
-  p.ow_log2 = __builtin_ctz(ow);
-  p.bh_log2 = p.ow_log2;
-  p.bimg = bimg;
-  p.tiles_per_img = 1;
-  p.c_in = c_in;
-  p.nchunk = nchunk;
-  p.nseg = nseg;
-  p.k_steps = k_steps;
-  p.c_out = c_out;
-  p.out_sega = sega;
-  p.out_planes = out_planes;
-  p.slope = slope;
-  p.scale = scale;
-  p.shift = shift;
-  p.out = act_out;
-  p.err = err;
-  p.debug = getenv("SG_DEBUG_SKIP") ? atoi(getenv("SG_DEBUG_SKIP")) : 0;
-  int pairs = state().sm_count / 2;
-  if (p.total_tiles < pairs) pairs = p.total_tiles;
-  if (sega == 2) conv_pair_kernel<2><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  else conv_pair_kernel<1><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
-}
-
 // plane-reuse pair kernel for L2 (BLOCK_N = 128: the pair splits one image by rows), L3, L4 (BLOCK_N = 256)
 template <int BLOCK_N>
 static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* scale, const float* shift,
@@ -1843,7 +1146,6 @@ static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* w
   p.shift = shift;
   p.out = act_out;
   p.err = err;
-  p.debug = getenv("SG_DEBUG_SKIP") ? atoi(getenv("SG_DEBUG_SKIP")) : 0;
   int pairs = state().sm_count / 2;
   if (p.total_tiles < pairs) pairs = p.total_tiles;
   if (sega == 2) conv_pair2_kernel<2, BLOCK_N><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
@@ -1856,16 +1158,8 @@ static int launch_conv_pair2(const __nv_bfloat16* act_in, const __nv_bfloat16* w
 static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk, const float* scale, const float* shift,
                              __nv_bfloat16* act2,
                              int64_t batch, int nseg, int sega, float slope, int* err, cudaStream_t stream, bool half = false) {
-  CUtensorMap tx, tw;
+  CUtensorMap tw;
   const int ct_in = 64 * sega;
-  {
-    cuuint64_t dims[5] = {(cuuint64_t)ct_in, 16, 16, 4, (cuuint64_t)batch};
-    cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)16 * ct_in * 2, (cuuint64_t)256 * ct_in * 2,
-                             (cuuint64_t)1024 * ct_in * 2};
-    cuuint32_t box[5] = {64, 16, 16, 1, 1};
-    int r = encode(&tx, 5, act1, dims, strides, box);
-    if (r != SG_OK) return r;
-  }
   const int k_steps = 16 * nseg;
   {
     cuuint64_t dims[2] = {(cuuint64_t)k_steps * 64, 128};
@@ -1886,7 +1180,6 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
   p.shift = shift;
   p.out = act2;
   p.err = err;
-  p.debug = getenv("SG_DEBUG_SKIP") ? atoi(getenv("SG_DEBUG_SKIP")) : 0;
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
   CUtensorMap to;
   {
@@ -1898,22 +1191,18 @@ static int launch_conv2_swap(const __nv_bfloat16* act1, const __nv_bfloat16* wpk
     int r = encode(&to, 5, act2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r != SG_OK) return r;
   }
-  if (half || !getenv("SG_CONV_TAP_STREAM")) {   // default: plane reuse (the only form with an fp16 variant)
-    CUtensorMap txr;
+  CUtensorMap txr;   // one shifted copy of a parity plane: 17 plane rows x 16 columns x 64 channels
+  {
     cuuint64_t dims[5] = {(cuuint64_t)ct_in, 16, 16, 4, (cuuint64_t)batch};
     cuuint64_t strides[4] = {(cuuint64_t)ct_in * 2, (cuuint64_t)16 * ct_in * 2, (cuuint64_t)256 * ct_in * 2,
                              (cuuint64_t)1024 * ct_in * 2};
     cuuint32_t box[5] = {64, 16, 17, 1, 1};
     int r = encode(&txr, 5, act1, dims, strides, box);
     if (r != SG_OK) return r;
-    if (sega == 2) conv2_swap2_kernel<2><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
-    else if (half) conv2_swap2_kernel<1, true><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
-    else conv2_swap2_kernel<1><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
-    SG_LAUNCH_CHECK();
-    return SG_OK;
   }
-  if (sega == 2) conv2_swap_kernel<2><<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, to, p);
-  else conv2_swap_kernel<1><<<grid, Conv2Cfg::kThreads, Conv2Cfg::kSmemBytes, stream>>>(tx, tw, to, p);
+  if (sega == 2) conv2_swap2_kernel<2><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
+  else if (half) conv2_swap2_kernel<1, true><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
+  else conv2_swap2_kernel<1><<<grid, Conv2RCfg::kThreads, Conv2RCfg::kSmemBytes, stream>>>(txr, tw, to, p);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1961,14 +1250,8 @@ extern "C" {
 
 int sg_d64_init_attributes() {
   using namespace sg::d64;
-  SG_CUDA(cudaFuncSetAttribute(conv_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               ConvCfg<256>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv2_swap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2RCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv2_swap2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2RCfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(conv_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv_pair2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair2Cfg<256>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(conv1_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2036,7 +1319,7 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
 // updating running_stats[2*(layer-2)] / [2*(layer-2)+1] (may be NULL) with `momentum`.
 static int run_layer_impl(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
                           float* logit, float* prob, float* loss, int bn_train, float* const* running_stats,
-                          float momentum, float eps, void* stream) {
+                          float momentum, float eps, int32_t* status, void* stream) {
   using namespace sg::d64;
   SG_READY();
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
@@ -2051,7 +1334,9 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   cudaStream_t st = sg::as_stream(stream);
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  int* err = reinterpret_cast<int*>(ws + W.flag);
+  // status words: [0] pipeline time-out role code, [1] fp16 overflow marker; the caller's (sticky, caller-cleared)
+  // or the workspace's own (cleared by sg_d64_check)
+  int* err = status ? reinterpret_cast<int*>(status) : reinterpret_cast<int*>(ws + W.flag);
   __nv_bfloat16* act1 = reinterpret_cast<__nv_bfloat16*>(ws + W.act1);
   __nv_bfloat16* act2 = reinterpret_cast<__nv_bfloat16*>(ws + W.act2);
   __nv_bfloat16* act3 = reinterpret_cast<__nv_bfloat16*>(ws + W.act3);
@@ -2074,26 +1359,12 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
       r = launch_conv2_swap(act1, wq(P.w2), sc(P.ss2, 128), sh(P.ss2, 128), act2, batch, P.nseg, W.sega, slope, err, st, half);
       break;
     case 3:
-      if (half || !getenv("SG_CONV_TAP_STREAM"))  // default: plane reuse; per-tap streaming kernels kept for A/B timing
-        r = launch_conv_pair2<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
-                              slope, err, st, half);
-      else if (!getenv("SG_CONV_SINGLE_CTA"))  // default: CTA pairs (cta_group::2); single-CTA tiles kept for A/B timing
-        r = launch_conv_pair(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
-                             slope, err, st);
-      else
-      r = launch_conv<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
-                           slope, err, st);
+      r = launch_conv_pair2<256>(act2, wq(P.w3), sc(P.ss3, 256), sh(P.ss3, 256), act3, batch, 16, 128, 256, P.nseg, W.sega, 1,
+                                 slope, err, st, half);
       break;
     case 4:
-      if (half || !getenv("SG_CONV_TAP_STREAM"))
-        r = launch_conv_pair2<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
-                              slope, err, st, half);
-      else if (!getenv("SG_CONV_SINGLE_CTA"))
-        r = launch_conv_pair(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
-                             slope, err, st);
-      else
-      r = launch_conv<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
-                           slope, err, st);
+      r = launch_conv_pair2<256>(act3, wq(P.w4), sc(P.ss4, 512), sh(P.ss4, 512), act4, batch, 8, 256, 512, P.nseg, W.sega, 0,
+                                 slope, err, st, half);
       break;
     default:
       head_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(act4, fq(P.w5), batch, W.sega, half, logit, prob, loss, err);
@@ -2113,7 +1384,10 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   SG_LAUNCH_CHECK();
   float* rm = running_stats ? running_stats[2 * (layer - 2)] : nullptr;
   float* rv = running_stats ? running_stats[2 * (layer - 2) + 1] : nullptr;
-  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(part, blocks, rows, c, fq(gb), eps, momentum, rm, rv, ss);
+  // fp16 mode: the new statistics are parked in the workspace until the head has shown that nothing overflowed
+  float* pend = reinterpret_cast<float*>(ws + W.bnrun) + (size_t)2 * (layer - 2) * 512;
+  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(part, blocks, rows, c, fq(gb), eps, momentum, rm, rv, half ? pend : rm,
+                                                  half ? pend + 512 : rv, ss);
   SG_LAUNCH_CHECK();
   int64_t ab = sg::ceil_div(rows * (c / 8), 256);
   if (ab > (int64_t)sg::state().sm_count * 16) ab = (int64_t)sg::state().sm_count * 16;
@@ -2124,21 +1398,52 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
 
 int sg_d64_run_layer(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
                      float* logit, float* prob, float* loss, void* stream) {
-  return run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 0, nullptr, 0.f, 0.f, stream);
+  return run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 0, nullptr, 0.f, 0.f, nullptr, stream);
+}
+
+int sg_d64_score_train_status(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
+                              float* bn2_running_mean, float* bn2_running_var, float* bn3_running_mean,
+                              float* bn3_running_var, float* bn4_running_mean, float* bn4_running_var, float momentum,
+                              float bn_eps, float* logit, float* prob, float* loss, int32_t* status2, void* stream) {
+  using namespace sg::d64;
+  SG_READY();
+  SG_REQUIRE(x && packed && workspace, "null pointer");
+  SG_REQUIRE(batch >= 1, "train-mode BatchNorm needs at least one sample");
+  float* rs[6] = {bn2_running_mean, bn2_running_var, bn3_running_mean, bn3_running_var, bn4_running_mean, bn4_running_var};
+  for (int layer = 1; layer <= 5; ++layer) {
+    const int r = run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 1, rs, momentum, bn_eps,
+                                 status2, stream);
+    if (r != SG_OK) return r;
+  }
+  if (conv_mode == SG_CONV_FP16) {
+    const WorkspaceLayout W = workspace_layout(batch, conv_mode);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    BnCommitArgs a;
+    for (int i = 0; i < 6; ++i) a.dst[i] = rs[i];
+    bn_commit_kernel<<<6, 512, 0, sg::as_stream(stream)>>>(reinterpret_cast<const float*>(ws + W.bnrun), a,
+                                                           status2 ? status2 : reinterpret_cast<const int*>(ws + W.flag));
+    SG_LAUNCH_CHECK();
+  }
+  return SG_OK;
 }
 
 int sg_d64_score_train(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode,
                        float* bn2_running_mean, float* bn2_running_var, float* bn3_running_mean,
                        float* bn3_running_var, float* bn4_running_mean, float* bn4_running_var, float momentum,
                        float bn_eps, float* logit, float* prob, float* loss, void* stream) {
+  return sg_d64_score_train_status(x, batch, packed, workspace, conv_mode, bn2_running_mean, bn2_running_var,
+                                   bn3_running_mean, bn3_running_var, bn4_running_mean, bn4_running_var, momentum, bn_eps,
+                                   logit, prob, loss, nullptr, stream);
+}
+
+int sg_d64_score_status(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, float* logit,
+                        float* prob, float* loss, int32_t* status2, void* stream) {
   SG_READY();
   SG_REQUIRE(x && packed && workspace, "null pointer");
-  SG_REQUIRE(batch >= 1, "train-mode BatchNorm needs at least one sample");
-  SG_CUDA(cudaMemsetAsync(workspace, 0, 4, sg::as_stream(stream)));
-  float* rs[6] = {bn2_running_mean, bn2_running_var, bn3_running_mean, bn3_running_var, bn4_running_mean, bn4_running_var};
+  if (batch == 0) return SG_OK;
   for (int layer = 1; layer <= 5; ++layer) {
-    const int r = run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 1, rs, momentum, bn_eps,
-                                 stream);
+    const int r = run_layer_impl(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, 0, nullptr, 0.f, 0.f,
+                                 status2, stream);
     if (r != SG_OK) return r;
   }
   return SG_OK;
@@ -2146,15 +1451,7 @@ int sg_d64_score_train(const float* x, int64_t batch, const void* packed, void* 
 
 int sg_d64_score(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, float* logit,
                  float* prob, float* loss, void* stream) {
-  SG_READY();
-  SG_REQUIRE(x && packed && workspace, "null pointer");
-  if (batch == 0) return SG_OK;
-  SG_CUDA(cudaMemsetAsync(workspace, 0, 4, sg::as_stream(stream)));  // pipeline time-out flag
-  for (int layer = 1; layer <= 5; ++layer) {
-    const int r = sg_d64_run_layer(x, batch, packed, workspace, conv_mode, layer, logit, prob, loss, stream);
-    if (r != SG_OK) return r;
-  }
-  return SG_OK;
+  return sg_d64_score_status(x, batch, packed, workspace, conv_mode, logit, prob, loss, nullptr, stream);
 }
 
 int sg_d64_check(const void* workspace, void* stream) {
@@ -2163,12 +1460,13 @@ int sg_d64_check(const void* workspace, void* stream) {
   int flags[2] = {0, 0};
   SG_CUDA(cudaMemcpyAsync(flags, workspace, 8, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
   SG_CUDA(cudaStreamSynchronize(sg::as_stream(stream)));
+  if (flags[0] != 0 || flags[1] != 0)   // both words are sticky until reported here
+    (void)cudaMemsetAsync(const_cast<void*>(workspace), 0, 8, sg::as_stream(stream));
   if (flags[0] != 0) {
     sg::set_error("conv pipeline timed out waiting on an mbarrier (role code %d: 1 producer, 2 mma, 3 mma-acc, 4 epilogue)", flags[0]);
     return SG_ECUDA;
   }
   if (flags[1] == sg::d64::kFp16OverflowMagic) {
-    (void)cudaMemsetAsync(static_cast<uint8_t*>(const_cast<void*>(workspace)) + 4, 0, 4, sg::as_stream(stream));
     sg::set_error("non-finite logit in the fp16 conv mode: an activation exceeded 65504 (or the input is not finite); "
                   "score this discriminator with SG_CONV_BF16X3 ('fp32') or SG_CONV_BF16");
     return SG_EINVAL;

@@ -298,6 +298,19 @@ __global__ void __launch_bounds__(512) hist_uniform_kernel(const float* __restri
   }
 }
 
+// out[i] = (float)((v[i] - mean) / std) in fp64, std from the unbiased one of sg_moments_finish (ddof 0: scaled by
+// sqrt((n-1)/n), StandardScaler's population std); a zero std leaves the column unscaled like StandardScaler.
+__global__ void __launch_bounds__(256) standardize_kernel(const float* __restrict__ v, int64_t n,
+                                                          const double* __restrict__ stats, int ddof,
+                                                          float* __restrict__ out) {
+  const double mean = stats[0];
+  double sd = stats[1];
+  if (ddof == 0 && n > 1) sd *= sqrt((double)(n - 1) / (double)n);
+  if (!(sd > 0.0)) sd = 1.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)(((double)v[i] - mean) / sd);
+}
+
 }  // namespace mom
 }  // namespace sg
 
@@ -320,6 +333,17 @@ int sg_moments_finish(const double* partial, int64_t chunks, int64_t n, float k,
   SG_READY();
   SG_REQUIRE(partial && chunks >= 1 && n >= 1, "arguments");
   sg::mom::moments_finish_kernel<<<1, 32, 0, sg::as_stream(stream)>>>(partial, chunks, n, k, stats, thr);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_standardize(const float* v, int64_t n, const double* stats, int ddof, float* out, void* stream) {
+  SG_READY();
+  SG_REQUIRE(v && stats && out && n >= 1 && (ddof == 0 || ddof == 1), "arguments");
+  int64_t blocks = sg::ceil_div(n, 1024);
+  const int64_t cap = (int64_t)sg::state().sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  sg::mom::standardize_kernel<<<(unsigned)blocks, 256, 0, sg::as_stream(stream)>>>(v, n, stats, ddof, out);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

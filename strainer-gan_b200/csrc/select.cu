@@ -222,6 +222,10 @@ __global__ void __launch_bounds__(kTailThreads, 1) radix_phases_kernel(const flo
       const float nanv = __uint_as_float(0x7FC00000u);
       if (__ldcg(ws + SG_SELECT_WS_NANCOUNT) != 0u) {
         out2[0] = nanv; out2[1] = nanv;
+      } else if (__ldcg(ws + W_ERR) != 0u) {
+        // a grid barrier gave up (possible only when the device is time-sliced under the cooperative launch): never
+        // hand out statistics built from incomplete histograms; sg_select_check reports the condition
+        out2[0] = out2[1] = __uint_as_float(0x7FC00000u);
       } else {
         const float a = key_to_float(prefix);
         float bb = a;
@@ -687,6 +691,21 @@ int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t 
     SG_CUDA(cudaLaunchKernelEx(&cfg, filter_kernel, v, n, cand, cap, ws, ku));
   }
   return radix_phases(v, n, cand, n / 32, ws, out2, st);
+}
+
+int sg_select_check(const void* workspace, void* stream) {
+  SG_READY();
+  SG_REQUIRE(workspace != nullptr, "workspace");
+  uint32_t flag = 0;
+  const uint32_t* ws = static_cast<const uint32_t*>(workspace);
+  SG_CUDA(cudaMemcpyAsync(&flag, ws + sg::sel::W_ERR, 4, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
+  SG_CUDA(cudaStreamSynchronize(sg::as_stream(stream)));
+  if (flag != 0) {
+    sg::set_error("radix select: a grid barrier of the cooperative kernel timed out (device time-sliced?); the order "
+                  "statistics of that call were returned as NaN");
+    return SG_ECUDA;
+  }
+  return SG_OK;
 }
 
 int sg_lerp_threshold(const float* stats2, float weight, int lerp_kind, float* thr, void* stream) {

@@ -17,3 +17,10 @@ def pytest_configure(config):
 def golden():
     path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def golden2():
+    """round-2 fixtures (tests/golden/make_golden_v2.py): in-batch block at B = 256 / 512, concat block + gradient"""
+    path = os.path.join(ROOT, "tests", "golden", "golden_v2.npz")
+    return dict(np.load(path, allow_pickle=False))

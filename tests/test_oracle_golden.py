@@ -113,6 +113,41 @@ def test_inbatch_strain_golden(golden, imgs, B):
     assert int(d.main[3].num_batches_tracked) == golden[f"g8_{B}_nbt"] == 1
 
 
+@pytest.mark.parametrize("B", [256, 512])
+def test_inbatch_strain_golden_configs_3_4(golden2, B):
+    """BASELINE configs 3 / 4 batch sizes: the oracle's in-batch block equals the reference's own code (train-mode BN)"""
+    d = O.make_discriminator(O.SEED)  # train mode
+    x = torch.from_numpy(O.synth_images(0, B))
+    fr, ff, mask, thr, scores = O.strain_batch(d, x)
+    assert np.array_equal(scores.numpy(), golden2[f"g8_{B}_scores"])
+    assert np.array_equal(thr.numpy(), golden2[f"g8_{B}_threshold"])
+    assert np.array_equal(mask.numpy(), golden2[f"g8_{B}_mask"])
+    assert ff.shape[0] == golden2[f"g8_{B}_nfake"] == {256: 26, 512: 52}[B]  # SURVEY 8a: s = 26 / 52
+    for li, name in ((3, "bn1"), (6, "bn2"), (9, "bn3")):
+        assert np.array_equal(d.main[li].running_mean.numpy(), golden2[f"g8_{B}_{name}_mean"])
+        assert np.array_equal(d.main[li].running_var.numpy(), golden2[f"g8_{B}_{name}_var"])
+
+
+def test_concat_block_golden(golden2):
+    """strained -> fake concat + generator-loss gradient ("# 상위 10% 제거해서 fake image에 concate.py:265-273, 282-284")"""
+    B = 64
+    d = O.make_discriminator(O.SEED).eval()
+    x = torch.from_numpy(O.synth_images(1000, B))
+    with torch.no_grad():
+        fr, ff, mask, thr, scores = O.strain_batch(d, x)
+    assert np.array_equal(mask.numpy(), golden2["g9_mask"]) and ff.shape[0] == golden2["g9_nfake"]
+    g = torch.Generator().manual_seed(1234)
+    gz = torch.tanh(torch.randn(B - ff.shape[0], 3, 64, 64, generator=g)).requires_grad_(True)
+    fake = O.concat_fake(gz, ff)
+    assert fake.shape[0] == golden2["g9_label_len"] == B
+    assert np.array_equal(fake.detach().double().sum(dim=(1, 2, 3)).numpy(), golden2["g9_fake_rowsum"])
+    out = d(fake).view(-1)
+    err = torch.nn.BCELoss()(out, torch.full((B,), 1.0))
+    err.backward()
+    assert np.array_equal(out.detach().numpy(), golden2["g9_output"])
+    assert np.array_equal(gz.grad[:, :, ::16, ::16].numpy(), golden2["g9_grad_sample"])
+
+
 # ---- bit-level restatements vs the library calls themselves --------------------------------
 def test_np_percentile_restatement():
     rng = np.random.default_rng(7)
