@@ -4,13 +4,14 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload (config 5 of BASELINE.json, weak scaling): every GPU holds a shard of SHARD = 131072 synthetic
-64x64x3 fp32 samples (2^20 samples at 8 GPUs); ONE STEP = one full dataset-scale strain =
-  D scoring of every sample (tcgen05 convs + fused sigmoid/BCE head)  ->  global top-10 % cutoff
+64x64x3 fp32 samples (2^20 samples at 8 GPUs); ONE STEP = one full dataset-scale strain through the repo's public call
+with its DEFAULTS (``strain_shard(images, netD, 0.1, group=...)`` = the data-parallel ``refine_dataset_by_loss``):
+  D scoring of every sample (tcgen05 convs + fused sigmoid/BCE head, conv_mode 'auto')  ->  global top-10 % cutoff
   (np.percentile(losses, 90) by radix select; integer histograms all-reduced over NCCL when N > 1)
-  ->  ascending kept-index compaction (np.where(loss < thr)).
-`value` is the whole-job samples/s with the shard resident in HBM; `e2e` is the same strain through the
-reference-facing call (refine_dataset_by_loss on a HOST dataset: H2D of every image and D2H of the kept
-indices inside the timed region).  Under torchrun one process per GPU; timing = CUDA events, max over ranks.
+  ->  ascending kept-index compaction (np.where(loss < thr)), kept indices read back to the host.
+`value` is the whole-job samples/s with the shard resident in HBM; `e2e` is the same call on a HOST dataset (H2D of
+every image and D2H of the kept indices inside the timed region; at N > 1 ONE host dataset split by rank, global
+threshold).  Under torchrun one process per GPU; timing = CUDA events, max over ranks.
 """
 import argparse
 import json
@@ -24,9 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SHARD = 131072          # samples per GPU (6.4 GB fp32): inputs are far larger than the 126 MB L2
-CHUNK = 8192            # samples per scoring launch group
-E2E_SAMPLES = 32768     # per-GPU host dataset for the end-to-end leg (1.6 GB pinned)
+CHUNK = 8192            # samples per scoring launch group (the library's DATASET_CHUNK)
 LOSS_RATIO = 0.1        # "remove top 10 % loss"
+PARITY_TOTAL = 98304    # samples of the multi-GPU parity check (single-GPU strain of the concatenated shards, rank 0)
 FLOP_CONV = 2 * (256 * 128 * 1024 + 64 * 256 * 2048 + 16 * 512 * 4096)   # L2..L4 = 201.3 MFLOP / sample
 FLOP_ALL = FLOP_CONV + 2 * (1024 * 64 * 48 + 8192)                      # 207.6 MFLOP / sample
 
@@ -80,10 +81,10 @@ class ClockSampler:
 
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle port of refine_dataset_by_loss,
-    "#strainer gan.py:364-392": torch-CPU D forward + np.percentile + np.where) on the host cores."""
+    "#strainer gan.py:364-392": torch-CPU D forward + np.percentile + np.where) on the host cores.  The reference is 21
+    flat scripts that cannot be installed or imported (they load datasets at import time), so the port is what runs."""
     if rank != 0:
         return
-    import numpy as np
     import torch
     from oracle import strainer_oracle as O
     cores = os.cpu_count() or 1
@@ -109,6 +110,39 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def numa_cpus_of_gpu(torch, index):
+    """(numa node, cpu set) of the host memory closest to GPU `index`, from sysfs; (None, None) if unknown."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return node, cpus
+    except Exception:
+        return None, None
+
+
+def conv_traffic_from_profile(mode_is_16bit, chunk):
+    """dram bytes (read + write) of the L2 + L3 + L4 launches of one 8192-sample chunk, read from the newest committed
+    ncu --set full summary (tools/ncu_traffic.py writes profiles/*_conv_traffic.json); None when there is none."""
+    import glob
+    if not mode_is_16bit or chunk != 8192:
+        return None, None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        return float(d["l2_l3_l4_dram_bytes"]), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 def main():
     global CHUNK
     ap = argparse.ArgumentParser()
@@ -116,14 +150,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="fp16", choices=["fp16", "bf16", "fp32"],
-                    help="conv arithmetic: fp16 (one tensor pass, meets the 1e-3 fp32 bar), bf16 (one pass, 2e-2 bar), "
-                         "fp32 (bf16 hi/lo split, three passes)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "fp16", "bf16", "fp32"],
+                    help="conv arithmetic of the headline; 'auto' = the library default (no conv_mode argument is passed)")
     ap.add_argument("--shard", type=int, default=SHARD)
-    ap.add_argument("--chunk", type=int, default=CHUNK, help="samples per scoring launch group")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the DCGAN train iters/sec leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind this rank to the NUMA node of its GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -132,16 +165,23 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
-    CHUNK = args.chunk
 
     import numpy as np
     import torch
     import torch.distributed as dist
     import strainer_b200 as sb
     from oracle import strainer_oracle as O
+    CHUNK = sb.DATASET_CHUNK
 
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # pinned host buffers are first-touched by this process: run it on the cores next to its GPU (NUMA-local memory)
+    numa_node, numa_cpus = (None, None) if args.no_numa else numa_cpus_of_gpu(torch, local)
+    if numa_cpus:
+        try:
+            os.sched_setaffinity(0, numa_cpus & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+        except Exception:
+            numa_node = None
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -151,21 +191,17 @@ def main():
     shard = args.shard
     n_global = shard * world
     base = rank * shard
+    kw = {} if args.mode == "auto" else {"conv_mode": args.mode}     # the headline passes NO conv_mode argument
+    lib = sb._lib.load()
 
     netD = O.make_discriminator(O.SEED)   # reference architecture, weights_init + perturbed BN stats
     netD.eval()
     images = sb.synth_images(base, shard, O.SEED, device)      # resident shard, generated on device
-    scorer = sb.D64Scorer(netD, device, args.mode, max_batch=CHUNK)
-    losses = torch.empty(shard, dtype=torch.float32, device=device)
     q = (1 - LOSS_RATIO) * 100
 
-    def strain_step(sc):
-        for i in range(0, shard, CHUNK):
-            b = min(CHUNK, shard - i)
-            sc.score_into(images[i:i + b], None, None, losses[i:i + b])
-        thr = sb.percentile_device(losses, q, group, n_global)
-        idx, count, _ = sb.compact_indices(losses, thr, 0, base)
-        return thr, idx, count
+    def strain_step(**mode_kw):
+        # the public data-parallel call, defaults only: D scoring -> global percentile -> global kept indices (host)
+        return sb.strain_shard(images, netD, LOSS_RATIO, group=group, index_base=base, n_global=n_global, **mode_kw)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -175,69 +211,108 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.sg_launch_count()
         e0.record()
         for _ in range(steps):
             out = fn()
         e1.record()
         torch.cuda.synchronize()
+        launches = lib.sg_launch_count() - l0
         if group is not None:
             dist.barrier()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if group is not None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / steps, out
+        return ms.item() / steps, out, launches
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_step, (thr, idx, count) = timed(lambda: strain_step(scorer), args.steps, args.warmup)
+    ms_step, (kept_idx, thr, losses), launches = timed(lambda: strain_step(**kw), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    scorer.check()
     value = n_global / (ms_step * 1e-3)
-    kept = int(count.item())
+    kept = int(len(kept_idx))
+    scorer = sb.get_scorer(netD, device, args.mode, CHUNK)
+    fallback_chunks = scorer.fallback_chunks
     nchunks = (shard + CHUNK - 1) // CHUNK
-    # kernels per step: 5 per scoring chunk | select: begin + cooperative radix phases (N = 1) or begin + 4 x (hist, step)
-    # + finish (N > 1, all-reduce between) | lerp | index compaction
-    launches_per_step = nchunks * 5 + (2 if world == 1 else 10) + 1 + 1
 
-    # ---- per-kernel timing of the conv kernels inside a long loop (sustained clocks) ----------------------
-    def layer_times(sc, reps):
-        xs = images[:CHUNK]
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(reps)]
-        for w in range(2):
-            for layer in range(1, 6):
-                sc.run_layer(xs, layer, None, None, losses[:CHUNK])
+    # ---- the same step in the three-pass fp32-parity arithmetic (bf16 hi/lo split), stated next to the headline ------
+    ms32, _, _ = timed(lambda: strain_step(conv_mode="fp32"), max(2, args.steps // 3), 3)
+    fp32_parity_value = n_global / (ms32 * 1e-3)
+    other_modes = {"fp32": {"value": fp32_parity_value, "ms_per_step": ms32}}
+    for other in ("bf16",):
+        ms2, _, _ = timed(lambda: strain_step(conv_mode=other), max(2, args.steps // 3), 3)
+        other_modes[other] = {"value": n_global / (ms2 * 1e-3), "ms_per_step": ms2}
+    sb.clear_scorer_caches()           # the fp32 workspaces (4 GB) are not needed below
+    scorer = sb.D64Scorer(netD, device, args.mode, max_batch=CHUNK)
+    loss_buf = torch.empty(shard, dtype=torch.float32, device=device)
+
+    # ---- per-kernel times INSIDE the real step: one full pass over the shard, an event after every launch; the first two
+    #      chunks (clock ramp) are dropped.  These are sustained-clock times: frac is taken against the sustained peak.
+    def in_step_layer_times():
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(nchunks)]
+        passes = max(3, int(round(600.0 / max(ms_step, 1.0))))   # ~0.6 s of the same launches: the board settles at its
+        for rep in range(passes):                                # power-capped clocks; the LAST pass is the one measured
+            for ci in range(nchunks):
+                xs = images[ci * CHUNK:(ci + 1) * CHUNK]
+                ev[ci][0].record()
+                for layer in range(1, 6):
+                    scorer.run_layer(xs, layer, None, None, loss_buf[ci * CHUNK:ci * CHUNK + xs.shape[0]])
+                    ev[ci][layer].record()
         torch.cuda.synchronize()
+        use = range(2, nchunks) if nchunks > 4 else range(nchunks)
+        t = np.array([[ev[ci][l].elapsed_time(ev[ci][l + 1]) for l in range(5)] for ci in use])
+        return t.mean(axis=0), float(np.mean([ev[ci][0].elapsed_time(ev[ci][5]) for ci in use]))
+
+    # ---- the same launches timed alone in a short loop (burst clocks): only comparable with the BURST peak
+    def short_loop_layer_times(reps):
+        xs = images[:CHUNK]
+        for _ in range(2):
+            for layer in range(1, 6):
+                scorer.run_layer(xs, layer, None, None, loss_buf[:CHUNK])
+        torch.cuda.synchronize()
+        time.sleep(0.5)                 # let the board cool off the previous leg
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(reps)]
         for r in range(reps):
             ev[r][0].record()
             for layer in range(1, 6):
-                sc.run_layer(images[(r % nchunks) * CHUNK:(r % nchunks) * CHUNK + CHUNK], layer, None, None, losses[:CHUNK])
+                scorer.run_layer(images[(r % nchunks) * CHUNK:(r % nchunks) * CHUNK + CHUNK], layer, None, None, loss_buf[:CHUNK])
                 ev[r][layer].record()
         torch.cuda.synchronize()
-        t = np.array([[ev[r][l].elapsed_time(ev[r][l + 1]) for l in range(5)] for r in range(reps)])
-        return t.mean(axis=0)   # ms per launch of [conv1, conv2, conv3, conv4, head] at CHUNK samples
+        return np.array([[ev[r][l].elapsed_time(ev[r][l + 1]) for l in range(5)] for r in range(reps)]).mean(axis=0)
 
-    lt = layer_times(scorer, 24)
+    lt, chunk_ms = in_step_layer_times()
+    lt_short = short_loop_layer_times(8)
+    scorer.check()
     conv_ms = float(lt[1] + lt[2] + lt[3])
+    conv_ms_short = float(lt_short[1] + lt_short[2] + lt_short[3])
     nseg = 3 if args.mode == "fp32" else 1
     achieved_tf = FLOP_CONV * CHUNK / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv2_swap2_kernel + 2 x conv_pair2_kernel (L2+L3+L4 implicit-GEMM launches of one chunk)",
+    achieved_tf_short = FLOP_CONV * CHUNK / (conv_ms_short * 1e-3) / 1e12
+    traffic, traffic_src = conv_traffic_from_profile(args.mode != "fp32", CHUNK)
+    roofline = {"bound": "tensor",
+                "kernel": "conv2_swap2_kernel + 2 x conv_pair2_kernel (the L2 + L3 + L4 implicit-GEMM launches of one 8192-sample chunk)",
                 "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sust"],
-                "peak_source": f"bf16_tflops_sustained of {pk['src']} (cuBLAS bf16 back to back for 4 s: the convs are timed inside a "
-                               "long loop under the same sw_power_cap)",
-                "frac_of_burst_peak": achieved_tf / pk["tf_burst"], "burst_peak": pk["tf_burst"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of the three launches at 8192 samples, bf16 mode, from the
-                # ncu --set full captures profiles/r1d_conv_kernels_full.txt (bf16) / r1f_conv_kernels_fp16_full.txt (L2 1.074+0.506,
-                # L3 0.538+0.235, L4 0.273+0.107 GB);
-                # algorithmic: act1 1.074 + act2 0.537 read, act2 0.537 + act3 0.268 + act4 0.134 written = 2.55 GB
-                "traffic": 2.734e9 if (args.mode in ("bf16", "fp16") and CHUNK == 8192) else None,
-                "traffic_unit": "bytes per launch group (ncu, profiles/r1d_conv_kernels_full.txt, r1f_conv_kernels_fp16_full.txt)",
+                "how": "CUDA events after every launch of a full pass over the shard (same launches and order as the timed "
+                       "step), mean over chunks 2.. : sustained clocks, hence the SUSTAINED cuBLAS bf16 peak",
+                "peak_source": f"bf16_tflops_sustained of {pk['src']}",
+                "short_loop": {"achieved": achieved_tf_short, "peak": pk["tf_burst"], "frac": achieved_tf_short / pk["tf_burst"],
+                               "how": "8 chunks timed right after a pause (burst clocks) against the BURST cuBLAS peak"},
+                "whole_step_frac_of_sustained_peak": value / world / (pk["tf_sust"] * 1e12 / FLOP_ALL),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_unit": "dram bytes read + written by the three launches of one chunk (ncu --set full)",
+                "algorithmic_bytes": {"act1_read": CHUNK * 131072, "act2_write_read": 2 * CHUNK * 65536,
+                                      "act3_write_read": 2 * CHUNK * 32768, "act4_write": CHUNK * 16384},
                 "algorithmic_flops_per_sample": FLOP_CONV, "samples_per_launch_group": CHUNK,
                 "issued_tensor_flops_factor": nseg}
-    kernels = {"chunk": CHUNK, "ms": {k: float(v) for k, v in zip(["conv1", "conv2", "conv3", "conv4", "head"], lt)},
-               "tflops": {k: float(f * CHUNK / (v * 1e-3) / 1e12) for k, f, v in zip(
-                   ["conv2", "conv3", "conv4"], [2 * 256 * 128 * 1024, 2 * 64 * 256 * 2048, 2 * 16 * 512 * 4096], lt[1:4])}}
+    names = ["conv1", "conv2", "conv3", "conv4", "head"]
+    kernels = {"chunk": CHUNK, "in_step_ms": {k: float(v) for k, v in zip(names, lt)},
+               "in_step_chunk_ms": chunk_ms, "in_step_sum_ms": float(lt.sum()),
+               "short_loop_ms": {k: float(v) for k, v in zip(names, lt_short)},
+               "in_step_tflops": {k: float(f * CHUNK / (v * 1e-3) / 1e12) for k, f, v in zip(
+                   ["conv2", "conv3", "conv4"], [2 * 256 * 128 * 1024, 2 * 64 * 256 * 2048, 2 * 16 * 512 * 4096], lt[1:4])},
+               "conv1_hbm_gbs": float(CHUNK * (49152 + 131072) / (lt[0] * 1e-3) / 1e9)}
 
     # selection + compaction kernels alone (HBM-bound in theory; 0.5 MB here => launch/L2 bound)
     def sel_only():
@@ -256,45 +331,100 @@ def main():
     torch.cuda.synchronize()
     ms_sel = float(np.median([a_.elapsed_time(b_) for a_, b_ in evs]))   # median: robust to a host hiccup in the enqueue loop
 
-    # ---- secondary: the other conv modes on the same step ---------------------------------------------------
-    other_modes = {}
-    for other in [m for m in ("fp16", "bf16", "fp32") if m != args.mode]:
-        sc2 = sb.D64Scorer(netD, device, other, max_batch=CHUNK)
-        ms2, _ = timed(lambda: strain_step(sc2), max(2, args.steps // 3), 3)
-        sc2.check()
-        other_modes[other] = {"value": n_global / (ms2 * 1e-3), "ms_per_step": ms2}
-        del sc2
+    # ---- multi-GPU parity (outside every timed region): the sharded strain of PARITY_TOTAL samples against rank 0's
+    #      single-GPU strain of the concatenated shards -- threshold bits and kept-index list must be identical ---------
+    parity = None
+    if world > 1:
+        per = (PARITY_TOTAL // world) // 4096 * 4096
+        pidx, pthr, _ = sb.strain_shard(images[:per], netD, LOSS_RATIO, group=group, index_base=rank * per,
+                                        n_global=per * world, **kw)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (np.asarray(pidx), np.float32(pthr).tobytes()))
+        if rank == 0:
+            whole = torch.cat([sb.synth_images(r * shard, per, O.SEED, device) for r in range(world)])
+            # global index of sample j of rank r in the parity run is r*per + j
+            sidx, sthr, _ = sb.strain_shard(whole, netD, LOSS_RATIO, **kw)
+            multi = np.concatenate([g[0] for g in gathered])
+            parity = {"n": per * world, "threshold_equal": all(g[1] == np.float32(sthr).tobytes() for g in gathered),
+                      "kept_indices_equal": bool(np.array_equal(multi, sidx)), "kept": int(len(sidx)),
+                      "threshold": float(sthr)}
+            del whole
+        dist.barrier()
+
+    # ---- H2D micro-benchmark: one cudaMemcpyAsync of a chunk from pinned memory, all ranks at once ----------------------
+    h2d = None
+    if not args.no_e2e:
+        hb = torch.empty((CHUNK, 3, 64, 64), dtype=torch.float32).pin_memory()
+        hb.normal_()
+        db = torch.empty_like(hb, device=device)
+        for _ in range(2):
+            db.copy_(hb, non_blocking=True)
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(12):
+            db.copy_(hb, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        gbs = torch.tensor([12 * hb.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9], device=device)
+        allg = [torch.zeros_like(gbs) for _ in range(world)]
+        if group is not None:
+            dist.all_gather(allg, gbs)
+        else:
+            allg = [gbs]
+        per_gpu = [float(t.item()) for t in allg]
+        h2d = {"gbs_per_gpu": per_gpu, "gbs_aggregate": float(sum(per_gpu)), "bytes_per_copy": hb.numel() * 4,
+               "numa_node": numa_node, "numa_bound": bool(numa_cpus),
+               "how": "12 x cudaMemcpyAsync of one 8192-image chunk (403 MB) from pinned host memory, every rank at the same "
+                      "time; the pinned buffer is first-touched on the cores of the GPU's NUMA node"}
+        del hb, db
 
     # ---- end to end through the reference-facing call, host dataset -----------------------------------------
     e2e = None
     e2e_u8 = None
     if not args.no_e2e:
-        def e2e_leg(ds, ne):
-            def e2e_step():
-                return sb.refine_dataset_by_loss(ds, netD, device, LOSS_RATIO, conv_mode=args.mode)
+        def e2e_leg(fn, ne):
             for _ in range(3):
-                sub, _t = e2e_step()
+                out = fn()
             torch.cuda.synchronize()
             if group is not None:
                 dist.barrier()
             es = max(3, min(args.steps, 10))
             t0 = time.perf_counter()
             for _ in range(es):
-                sub, _t = e2e_step()
+                out = fn()
             torch.cuda.synchronize()
             dt = torch.tensor([(time.perf_counter() - t0) / es], device=device)
             if group is not None:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            return ne * world / dt.item(), int(len(sub.indices)) * 8 + 12
+            return ne * world / dt.item(), out
 
-        ne = min(E2E_SAMPLES, shard)
+        import psutil
+        ne = shard
+        while ne > 8192 and ne * 49152 * max(world, 1) > 0.5 * psutil.virtual_memory().available:
+            ne //= 2
         host = torch.empty((ne, 3, 64, 64), dtype=torch.float32).pin_memory()
-        host.copy_(images[:ne])
-        v, d2h = e2e_leg(torch.utils.data.TensorDataset(host, torch.zeros(ne, dtype=torch.long)), ne)
-        e2e = {"value": v, "unit": "samples/s", "h2d_bytes_per_step": ne * 49152,
-               "d2h_bytes_per_step": d2h, "samples_per_gpu": ne,
-               "api": "refine_dataset_by_loss(TensorDataset(host pinned fp32), netD, device, 0.1)",
-               "note": "each rank strains its own host dataset (replicas); PCIe H2D of 49152 B/sample is inside the timed region"}
+        for i in range(0, ne, CHUNK):
+            host[i:i + CHUNK].copy_(images[i:i + CHUNK])
+        if world == 1:
+            ds = torch.utils.data.TensorDataset(host, torch.zeros(ne, dtype=torch.long))
+            v, (sub, _t) = e2e_leg(lambda: sb.refine_dataset_by_loss(ds, netD, device, LOSS_RATIO, **kw), ne)
+            d2h = int(len(sub.indices)) * 8 + 4
+            api = "refine_dataset_by_loss(TensorDataset(host pinned fp32), netD, device, 0.1)"
+            note = "PCIe H2D of 49152 B/sample is inside the timed region"
+        else:
+            # ONE host dataset of ne*world samples split by rank: rank r holds samples [r*ne, (r+1)*ne) of it; the
+            # threshold is the GLOBAL percentile, the kept indices are global (strain_shard = sharded refine_dataset_by_loss)
+            v, (idx_, _t, _l) = e2e_leg(lambda: sb.strain_shard(host, netD, LOSS_RATIO, group=group, index_base=rank * ne,
+                                                                n_global=ne * world, device=device, **kw), ne)
+            d2h = int(len(idx_)) * 8 + 4
+            api = "strain_shard(host pinned fp32 shard, netD, 0.1, group=WORLD, index_base=rank*n, n_global=N*n)"
+            note = ("one host dataset split by rank, global threshold (NCCL all-reduced histograms) and global kept indices; "
+                    "PCIe H2D of 49152 B/sample is inside the timed region")
+        e2e = {"value": v, "unit": "samples/s", "h2d_bytes_per_step": ne * 49152, "d2h_bytes_per_step": d2h,
+               "samples_per_gpu": ne, "api": api, "note": note, "h2d_gbs_per_gpu_implied": v / world * 49152 / 1e9}
         del host
         # the same call on a uint8 host dataset (the pixels the reference's ImageFolder decodes, ToTensor + Normalize
         # applied on the device, bit-identical to the host transform): 12288 B/sample over PCIe
@@ -302,17 +432,29 @@ def main():
         host8 = torch.empty((ne8, 3, 64, 64), dtype=torch.uint8).pin_memory()
         for i in range(0, ne8, CHUNK):
             host8[i:i + CHUNK].copy_(((images[i:i + CHUNK] + 1.0) * 127.5).round_().clamp_(0, 255).to(torch.uint8))
-        v8, d2h8 = e2e_leg(sb.U8ImageDataset(host8, None, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ne8)
+        u8 = sb.U8ImageDataset(host8, None, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
+        if world == 1:
+            v8, (sub8, _t) = e2e_leg(lambda: sb.refine_dataset_by_loss(u8, netD, device, LOSS_RATIO, **kw), ne8)
+            d2h8 = int(len(sub8.indices)) * 8 + 4
+        else:
+            v8, (idx8, _t, _l) = e2e_leg(lambda: sb.strain_shard(u8.images, netD, LOSS_RATIO, group=group, index_base=rank * ne8,
+                                                                 n_global=ne8 * world, device=device, **kw), ne8)
+            d2h8 = int(len(idx8)) * 8 + 4
         e2e_u8 = {"value": v8, "unit": "samples/s", "h2d_bytes_per_step": ne8 * 12288, "d2h_bytes_per_step": d2h8,
                   "samples_per_gpu": ne8,
-                  "api": "refine_dataset_by_loss(U8ImageDataset(host pinned uint8, Normalize(.5,.5)), netD, device, 0.1)",
+                  "api": "the same call on U8ImageDataset(host pinned uint8, Normalize(.5,.5))",
                   "note": "same strain on the uint8 pixels of the same images quantised to 8 bits; ToTensor + Normalize run on "
                           "the device (sg_u8_normalize), 12288 B/sample over PCIe inside the timed region"}
-        del host8
+        del host8, u8
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port of the reference on the host cores ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if numa_cpus:
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))     # the CPU leg may use every core again
+            except Exception:
+                pass
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         ns = 16384
@@ -325,28 +467,25 @@ def main():
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         cpu = {"value": ns / best, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64), "
-                         f"best of 3 passes ({3 * best:.1f} s of CPU work)"}
+               "sample": f"first {ns} samples of the same stream, oracle refine_dataset_by_loss (torch CPU fp32, bs 64, no "
+                         f"DataLoader), best of 3 passes ({3 * best:.1f} s of CPU work)"}
         # parity of every conv mode against the oracle's losses on those samples (the oracle as the checker)
         widx, wthr, wloss = O.refine_dataset_by_loss(xs, netD, LOSS_RATIO)
         wloss = wloss.reshape(-1)
-        parity = {"samples": ns, "oracle_threshold": float(wthr)}
-        for m in ("fp16", "bf16", "fp32"):
-            scm = scorer if m == args.mode else sb.D64Scorer(netD, device, m, max_batch=CHUNK)
-            lm = scm.score(images[:ns], ("loss",))["loss"]
-            tm = sb.percentile_device(lm, q)
-            im, cm, _ = sb.compact_indices(lm, tm, 0, 0)
+        parity_modes = {"samples": ns, "oracle_threshold": float(wthr)}
+        for m in ("auto", "bf16", "fp32"):
+            im, tm, lm = sb.strain_shard(images[:ns], netD, LOSS_RATIO, conv_mode=m)
             lm_h = lm.cpu().numpy()
             rel = np.abs(lm_h - wloss) / np.maximum(np.abs(wloss), 1e-6)
             got = np.zeros(ns, bool)
-            got[im[:int(cm.item())].cpu().numpy()] = True
+            got[im] = True
             want = np.zeros(ns, bool)
             want[widx] = True
             near = np.abs(wloss - wthr) <= 1e-3 * abs(wthr)
-            parity[m] = {"max_rel_loss_err": float(rel.max()), "threshold": float(tm.item()),
-                         "mask_disagreements": int((got != want).sum()),
-                         "mask_disagreements_outside_1e-3_of_threshold": int(((got != want) & ~near).sum())}
-        cpu["parity_vs_oracle"] = parity
+            parity_modes[m] = {"max_rel_loss_err": float(rel.max()), "threshold": float(tm),
+                               "mask_disagreements": int((got != want).sum()),
+                               "mask_disagreements_outside_1e-3_of_threshold": int(((got != want) & ~near).sum())}
+        cpu["parity_vs_oracle"] = parity_modes
 
     # ---- "existing Blackwell kernels" bar: the reference's own torch ops on this GPU (eager, cuDNN) ----------
     eager = None
@@ -379,7 +518,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_train:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import config_bench
-        del images, losses
+        del images, losses, loss_buf
+        sb.clear_scorer_caches()
         torch.cuda.empty_cache()
         train = {"batch": 128, "unit": "iters/s",
                  "plain_dcgan_no_strain": config_bench.train_iters(device, 40, "none"),
@@ -390,15 +530,19 @@ def main():
     if rank == 0:
         line = {"metric": "strained_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "fp16", "bf16": "bf16", "fp32": "bf16x3 (fp32-parity split)"}[args.mode],
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"auto": "fp16 (fp32 accumulate; overflowed chunks re-scored in bf16x3)", "fp16": "fp16", "bf16": "bf16",
+                          "fp32": "bf16x3 (fp32-parity split)"}[args.mode],
                 "data": "synthetic",
                 "config": {"workload": "C5 dataset-scale D64 scoring + global top-10% radix select + index compaction",
+                           "api": "strain_shard(images, netD, 0.1, group, index_base, n_global) -- library defaults, no conv_mode",
                            "samples_per_gpu": shard, "samples_total": n_global, "chunk": CHUNK, "loss_ratio": LOSS_RATIO,
                            "conv_mode": args.mode, "l2": "inputs (6.4 GB/GPU) larger than L2; no flush needed",
-                           "kept": kept, "threshold": float(thr.item())},
-                "clocks": clocks, "e2e": e2e, "e2e_u8_dataset": e2e_u8, "gpu_launches": launches_per_step * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu,
-                "frac_of_conv_roofline": value / world / (pk["tf_sust"] * 1e12 / FLOP_ALL),
+                           "kept": kept, "threshold": float(thr), "fp16_chunks_rescored": fallback_chunks},
+                "clocks": clocks, "e2e": e2e, "e2e_u8_dataset": e2e_u8, "gpu_launches": int(launches),
+                "gpu_launches_note": "sg_launch_count() difference over the timed region on rank 0 (every launch site of the library)",
+                "fp32_parity_value": fp32_parity_value,
+                "roofline": roofline, "cpu_baseline": cpu, "multi_gpu_parity": parity, "h2d_microbench": h2d,
                 "kernels": kernels, "select_compact_ms": ms_sel, "train_iters_per_sec": train, "torch_eager_gpu": eager,
                 "other_modes": other_modes}
         print(json.dumps(line), flush=True)

@@ -68,6 +68,9 @@ const char* sg_last_error_string(void);
  * cuTensorMapEncodeTiled through the runtime, raises the dynamic shared-memory limits. */
 int sg_init(int device);
 int sg_sm_count(void);
+/* Kernels this library has launched in this process so far (every launch site counts; bench.py reports the difference
+ * over its timed region as gpu_launches). */
+long long sg_launch_count(void);
 
 /* ---- synthetic data (counter based, identical to oracle.synth_images) --- */
 int sg_synth_images(float* out, int64_t start, int64_t count, uint32_t seed, void* stream);

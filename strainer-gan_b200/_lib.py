@@ -26,6 +26,7 @@ _SIGS = {
     "sg_last_error_string": (ctypes.c_char_p, []),
     "sg_init": (c_int, [c_int]),
     "sg_sm_count": (c_int, []),
+    "sg_launch_count": (ctypes.c_longlong, []),
     "sg_synth_images": (c_int, [P, c_int64, c_int64, c_uint32, P]),
     "sg_u8_normalize": (c_int, [P, c_int64, c_int, c_int64, c_int, P, P, P, P]),
     "sg_d64_packed_bytes": (c_size_t, [c_int]),

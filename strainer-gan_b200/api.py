@@ -686,6 +686,16 @@ def _copy_stream(device):
 
 
 _SCORERS: dict = {}
+DATASET_CHUNK = 8192     # samples per scoring launch group at dataset scale (tools/chunk_sweep.py; 2 GB of activations)
+
+
+def _chunk_for(n: int) -> int:
+    """Launch-group size for a dataset of n samples: DATASET_CHUNK at scale, the next power of two (>= 512) below it, so
+    that a small dataset does not allocate the 2 GB workspace of the large one."""
+    c = 512
+    while c < min(int(n), DATASET_CHUNK):
+        c *= 2
+    return c
 
 
 def get_scorer(discriminator: nn.Module, device=None, mode: str = "auto", max_batch: int = 4096) -> D64Scorer:
@@ -879,7 +889,7 @@ def evaluate_dataset(netD, dataset, device, *, conv_mode: str = "auto", return_d
     BCE(D(x), 1) with eval-mode BN (sticky ``netD.eval()``); returns np.ndarray (N,) float32."""
     device = _dev(device)
     netD.eval()
-    losses = _score_dataset(get_scorer(netD, device, conv_mode), dataset, ("loss",))["loss"]
+    losses = _score_dataset(get_scorer(netD, device, conv_mode, _chunk_for(len(dataset))), dataset, ("loss",))["loss"]
     return losses if return_device else losses.cpu().numpy()
 
 
@@ -891,7 +901,7 @@ def refine_dataset_by_loss(dataset, discriminator, device, loss_ratio=0.2, *, co
     device = _dev(device)
     discriminator.eval()  # sticky, as in the reference
     n = len(dataset)
-    losses = _score_dataset(get_scorer(discriminator, device, conv_mode), dataset, ("loss",))["loss"]
+    losses = _score_dataset(get_scorer(discriminator, device, conv_mode, _chunk_for(n)), dataset, ("loss",))["loss"]
     clean_indices, threshold = select_below_percentile(losses, (1 - loss_ratio) * 100)
     if len(clean_indices) == 0:
         # reference fallback on its (N,1,1)-shaped loss array: argsort along the last axis (len 1) -> zeros
@@ -939,7 +949,7 @@ def strain_shard(images, discriminator, loss_ratio=0.2, *, group=None, index_bas
     Returns (np.int64 kept_global_indices, np.float32 threshold, losses_dev)."""
     device = _dev(device if device is not None else _dev_of(images))
     discriminator.eval()
-    losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
+    losses = get_scorer(discriminator, device, conv_mode, _chunk_for(images.shape[0])).score(images, ("loss",))["loss"]
     idx, thr = select_below_percentile(losses, (1 - loss_ratio) * 100, group, index_base, n_global)
     return idx, thr, losses
 
@@ -976,7 +986,7 @@ class ResidentSubset:
         """``refine_dataset_by_loss`` ("#strainer gan.py:364-392") without leaving the device."""
         device = _dev(images.pixels.device if isinstance(images, U8Images) else images.device)
         discriminator.eval()
-        losses = get_scorer(discriminator, device, conv_mode).score(images, ("loss",))["loss"]
+        losses = get_scorer(discriminator, device, conv_mode, _chunk_for(images.shape[0])).score(images, ("loss",))["loss"]
         thr = percentile_device(losses, (1 - loss_ratio) * 100)
         idx, count, _ = compact_indices(losses, thr, L.SG_LT, 0)
         c = int(count.item())

@@ -18,6 +18,9 @@ DeviceState& state() {
   return g_states[dev];
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -78,6 +81,8 @@ extern "C" {
 int sg_version(void) { return 100; }
 
 const char* sg_last_error_string(void) { return sg::g_err; }
+
+long long sg_launch_count(void) { return (long long)__atomic_load_n(&sg::g_launches, __ATOMIC_RELAXED); }
 
 int sg_sm_count(void) { return sg::state().sm_count; }
 

@@ -26,6 +26,7 @@ struct DeviceState {
 };
 DeviceState& state();
 void set_error(const char* fmt, ...);
+void count_launch();  // bumps the process-wide kernel-launch counter read by sg_launch_count()
 int check_ready();  // SG_OK or SG_ENOINIT / SG_EARCH
 
 #define SG_CUDA(expr)                                                              \
@@ -53,6 +54,7 @@ int check_ready();  // SG_OK or SG_ENOINIT / SG_EARCH
 
 #define SG_LAUNCH_CHECK()                                                          \
   do {                                                                             \
+    sg::count_launch();                                                            \
     cudaError_t _e = cudaGetLastError();                                           \
     if (_e != cudaSuccess) {                                                       \
       sg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

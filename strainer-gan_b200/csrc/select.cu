@@ -631,6 +631,7 @@ static int radix_phases(const float* v, int64_t n, const float* cand, int64_t n_
   void* args[] = {(void*)&v, (void*)&n, (void*)&cand, (void*)&ws, (void*)&out2};
   SG_CUDA(cudaLaunchCooperativeKernel((const void*)sg::sel::radix_phases_kernel, dim3((unsigned)g), dim3(sg::sel::kTailThreads),
                                       args, sg::sel::kTailSmem, st));
+  sg::count_launch();
   return SG_OK;
 }
 
@@ -689,6 +690,7 @@ int sg_select_kth(const float* v, int64_t n, int64_t k, void* workspace, size_t 
     cfg.numAttrs = 1;
     const unsigned long long ku = (unsigned long long)k;
     SG_CUDA(cudaLaunchKernelEx(&cfg, filter_kernel, v, n, cand, cap, ws, ku));
+    sg::count_launch();
   }
   return radix_phases(v, n, cand, n / 32, ws, out2, st);
 }

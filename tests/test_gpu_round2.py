@@ -134,7 +134,8 @@ def test_strain_batch_train_mode_bn_configs_3_4(sb, golden2, B, mode):
     for li, name in ((3, "bn1"), (6, "bn2"), (9, "bn3")):
         for t, key in ((d.main[li].running_mean, "mean"), (d.main[li].running_var, "var")):
             w = golden2[f"g8_{B}_{name}_{key}"]
-            assert np.allclose(t.cpu().numpy(), w, rtol=1e-3, atol=1e-5), (name, key, np.abs(t.cpu().numpy() - w).max())
+            atol = 1e-5 if mode == "fp32" else 1e-4      # fp16 operands: statistics of fp16-rounded conv outputs
+            assert np.allclose(t.cpu().numpy(), w, rtol=1e-3, atol=atol), (name, key, np.abs(t.cpu().numpy() - w).max())
         assert int(d.main[li].num_batches_tracked) == 1
 
 

@@ -91,15 +91,19 @@ def train_iters(dev, iters, mode):
                 m = s >= thr
                 freal, ffake = real[m], real[~m]
         else:
-            freal, ffake, _, _ = sb.strain_batch(netD, real, 0.1, conv_mode="bf16")
+            freal, ffake, _, _ = sb.strain_batch(netD, real, 0.1)          # library defaults
         netD.zero_grad()
         out = netD(freal).view(-1)
         errD_real = crit(out, torch.ones_like(out))
         errD_real.backward()
         noise = torch.randn(freal.shape[0], nz, 1, 1, device=dev)
         fake = netG(noise)
-        cat = sb.concat_fake(fake.detach(), ffake) if mode == "b200" else torch.cat([fake.detach(), ffake], 0)
-        out = netD(cat).view(-1)
+        # ":268": fake = cat([fake, filtered_fake]); D sees fake.detach(), the G step the concatenated batch itself
+        if mode == "b200":
+            fake = sb.concat_fake(fake, ffake)
+        elif mode == "torch":
+            fake = torch.cat([fake, ffake], dim=0)
+        out = netD(fake.detach()).view(-1)
         errD_fake = crit(out, torch.zeros_like(out))
         errD_fake.backward()
         optD.step()
