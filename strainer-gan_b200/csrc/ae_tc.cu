@@ -19,7 +19,6 @@
 //   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -52,7 +51,7 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
 // on load and split on store.
 struct Layout {
-  size_t flag, w1, w2, w5, w6, w3, w4, a1, a2, a3, a4, a5, part, total;
+  size_t flag, w1, w2, w5, w6, w3, w4, w3t, w4t, a1, a2, a3, a4, a5, part, total;
 };
 static Layout layout(int64_t batch, int seg) {
   Layout L;
@@ -64,6 +63,8 @@ static Layout layout(int64_t batch, int seg) {
   L.w6 = o; o += align_up((size_t)16 * 144 * 2, 1024);   // dec3 weights, 16-bit [oc (3 of 16)][tap*16 + ic] (tensor-core form)
   L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
   L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
+  L.w3t = o; o += align_up((size_t)4 * 7 * 128 * 32 * 2, 1024);   // row-tap forms of the 7x7 weights (single-segment modes)
+  L.w4t = o; o += align_up((size_t)2 * 7 * 128 * 64 * 2, 1024);
   L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
   L.a2 = o; o += align_up(kAct2 * seg * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
   L.a3 = o; o += align_up(kAct3 * seg * batch, 1024);
@@ -450,6 +451,276 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// The two 7x7 layers in ROW-TAP form (single-segment modes).  The gather forms above pay either TMA service (enc3: the
+// 12.8 KB input window is fetched once per K-step, 28 x per image) or shared-memory operand bandwidth (dec1: N = 32
+// MMAs read 5 KB of operands for 16 cycles of tensor work).  Here the seven COLUMN taps kx move from the contraction
+// onto the N side of the GEMM and the column shift is undone in the epilogue:
+//
+//   enc3  T[(oy, ix), (kx, co)] = sum_{ky, ci} in[oy + ky][ix][ci] * w[co][ci][ky][kx]     out[oy][ox] = sum_kx T[(oy, ox + kx), kx]
+//   dec1  T[(oy, ix), (kx, co)] = sum_{ky, ci} in[oy - ky][ix][ci] * w[ci][co][ky][kx]     out[oy][ox] = sum_kx T[(oy, ox - kx), kx]
+//
+// M rows are (row oy, INPUT column ix) at a pitch of 16 columns, so the A operand of row tap ky is the image's ONE
+// shared-memory copy shifted by whole 16-pixel rows (a swizzle-atom-aligned descriptor offset): the input is loaded
+// once per image, nothing is re-fetched per tap.  N = (kx, co) is cut into chunks of 128 columns (2 kx x 64 co for
+// enc3, 4 kx x 32 co for dec1): M128 x N128 x K16 MMAs read 8 KB of operands for 64 tensor cycles, i.e. the tensor
+// pipe, not shared memory, is the bound; a weight stage (one chunk, one ky: 8 / 16 KB) serves both 128-row tiles of
+// the image.  The column shift is a width-16 warp shuffle (an output pixel and the seven input columns it sums over
+// sit in the same half warp), accumulated in registers across the chunks: no col2im pass, no atomics, fixed order.
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: epilogue of tile 0 (rows oy 0..7) | warps 6-9: tile 1
+// ------------------------------------------------------------------------------------------
+template <bool CONVT>
+struct K7TCfg {
+  static constexpr int kCin = CONVT ? 64 : 32, kCout = CONVT ? 32 : 64;
+  static constexpr int kRowB = kCin * 2;                       // operand row: one pixel's channels (SW128 / SW64)
+  static constexpr int kKxPerChunk = CONVT ? 4 : 2, kChunks = CONVT ? 2 : 4;
+  static constexpr int kK16 = kCin / 16;
+  static constexpr int kSlotRows = 22;                         // enc3: 16 input rows + 6 rows only dead outputs read;
+  static constexpr int kSlotBytes = kSlotRows * 16 * kRowB;    // dec1: 6 zero rows | 10 input rows | 6 zero rows
+  static constexpr int kLoadBytes = (CONVT ? 10 : 16) * 16 * kRowB;
+  static constexpr int kSlots = 2;
+  static constexpr int kBBytes = 128 * kRowB;                  // one (chunk, ky) weight stage
+  static constexpr int kBStages = 4;
+  static constexpr int kTmemCols = 512;                        // 2 accumulators x (2 tiles x 128 columns)
+  static constexpr int kThreads = 320;
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + kBStages * kBBytes + 256 + 256 + 1024;
+};
+
+template <bool CONVT, bool HALF>
+__global__ void __launch_bounds__(320, 1)
+ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
+  using Cfg = K7TCfg<CONVT>;
+  constexpr int UA = Cfg::kSlots, SB = Cfg::kBStages, COUT = Cfg::kCout;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base + UA * Cfg::kSlotBytes;
+  const uint32_t bar0 = b_base + SB * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto afull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
+  auto bfull_bar = [&](int s) { return bar0 + 8u * (2 * UA + s); };
+  auto bempty_bar = [&](int s) { return bar0 + 8u * (2 * UA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + 2 + a); };
+  constexpr int kNb = 2 * UA + 2 * SB + 4;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + (bar0 - base) + 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
+  // rows of the slots TMA never writes: the zero padding of the transposed conv / rows only dead outputs read
+  for (int i = threadIdx.x; i < UA * Cfg::kSlotBytes / 16; i += Cfg::kThreads)
+    *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int aslot = 0, bstage = 0;
+      uint32_t aphase = 0, bphase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
+        if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 21)) break;
+        mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kLoadBytes);
+        // enc3: the 16 x 16 input; dec1: the 10 input rows at slot rows 6..15, columns 10..15 zero-filled by TMA
+        tma_load_4d(base + aslot * Cfg::kSlotBytes + (CONVT ? 6 * 16 * Cfg::kRowB : 0), &tmap_a, afull_bar(aslot), 0, 0, 0, img);
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+        for (int s = 0; s < Cfg::kChunks * 7 && ok; ++s) {     // s = chunk * 7 + ky
+          if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 22)) { ok = false; break; }
+          mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
+          tma_load_2d(b_base + bstage * Cfg::kBBytes, &tmap_b, bfull_bar(bstage), 0, s * 128);
+          if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int aslot = 0, bstage = 0, acc = 0;
+      uint32_t aphase = 0, bphase = 0, acc_phase = 0;
+      bool ok = true;
+      for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
+        if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 23)) break;
+        tc_fence_after();
+        const uint32_t ca = base + aslot * Cfg::kSlotBytes;
+        for (int c = 0; c < Cfg::kChunks && ok; ++c) {
+          const int nkx = (7 - c * Cfg::kKxPerChunk) < Cfg::kKxPerChunk ? (7 - c * Cfg::kKxPerChunk) : Cfg::kKxPerChunk;
+          const uint32_t idesc = umma_idesc_16(128, nkx * COUT, HALF);
+          if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 24)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+          uint32_t first = 0;
+          for (int ky = 0; ky < 7 && ok; ++ky) {
+            if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 25)) { ok = false; break; }
+            tc_fence_after();
+            // tile t covers output rows 8t .. 8t+7: enc3 reads input rows oy + ky, dec1 padded rows oy - ky + 6
+            const uint32_t r0 = (uint32_t)(CONVT ? 6 - ky : ky), rowpx = 16u * Cfg::kRowB;
+            uint64_t a0, a1, bd;
+            if (CONVT) {
+              a0 = umma_desc_sw128(ca + r0 * rowpx); a1 = umma_desc_sw128(ca + (r0 + 8) * rowpx);
+              bd = umma_desc_sw128(b_base + bstage * Cfg::kBBytes);
+            } else {
+              a0 = umma_desc_sw64(ca + r0 * rowpx); a1 = umma_desc_sw64(ca + (r0 + 8) * rowpx);
+              bd = umma_desc_sw64(b_base + bstage * Cfg::kBBytes);
+            }
+#pragma unroll
+            for (int k = 0; k < Cfg::kK16; ++k) {
+              umma_f16(tmem_d, a0 + 2 * k, bd + 2 * k, idesc, first);
+              umma_f16(tmem_d + 128, a1 + 2 * k, bd + 2 * k, idesc, first);
+              first = 1u;
+            }
+            umma_commit(bempty_bar(bstage));
+            if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
+          }
+          if (!ok) break;
+          umma_commit(tfull_bar(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (!ok) break;
+        umma_commit(aempty_bar(aslot));
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue: column-tap sums by half-warp shuffles, bias (+ ReLU), 16-bit store =================
+    const int q = warp & 3;                      // TMEM lane quadrant of this warp
+    const int tile = (warp - 2) >> 2;            // warps 2..5: rows 0..7, warps 6..9: rows 8..15
+    const int oy = tile * 8 + 2 * q + (lane >> 4), ix = lane & 15;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
+      float o[COUT];
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) o[j] = s_bias[j];
+      bool ok = true;
+#pragma unroll 1
+      for (int c = 0; c < Cfg::kChunks; ++c) {
+        if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 26)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + tile * 128);
+#pragma unroll 1
+        for (int kl = 0; kl < Cfg::kKxPerChunk; ++kl) {
+          const int kx = c * Cfg::kKxPerChunk + kl;
+          if (kx >= 7) break;
+#pragma unroll
+          for (int cb = 0; cb < COUT; cb += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + (uint32_t)(kl * COUT + cb), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = __uint_as_float(v[j]);
+              if (CONVT) {      // out[oy][ox] += T[(oy, ox - kx)][kx]: from the lane kx to the left (none: zero)
+                const float u = __shfl_up_sync(0xffffffffu, t, (unsigned)kx, 16);
+                t = (ix >= kx) ? u : 0.f;
+              } else {          // out[oy][ox] += T[(oy, ox + kx)][kx]: from the lane kx to the right (dead lanes: own value)
+                t = __shfl_down_sync(0xffffffffu, t, (unsigned)kx, 16);
+              }
+              o[cb + j] += t;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (!ok) break;
+      const bool valid = CONVT ? true : (oy < 10 && ix < 10);
+      if (valid) {
+        const size_t px = CONVT ? ((size_t)img * 256 + oy * 16 + ix) : ((size_t)img * 100 + oy * 10 + ix);
+        uint4* d = reinterpret_cast<uint4*>(out + px * COUT);
+#pragma unroll
+        for (int g = 0; g < COUT / 8; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float a = o[8 * g + 2 * h], b = o[8 * g + 2 * h + 1];
+            if (CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }     // ReLU follows the decoder's first layer only
+            pk[h] = pk2<HALF>(a, b);
+          }
+          d[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// row-tap weight layouts: [chunk][ky][n = kxl * COUT + co][ci], kx = chunk * kKxPerChunk + kxl (kx >= 7: zero rows)
+//   enc3: w3 [co 64][ci 32][ky][kx] (Conv2d)            dec1: w4 [ci 64][co 32][ky][kx] (ConvTranspose2d)
+template <bool HALF>
+__global__ void pack_k7t_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
+                                __nv_bfloat16* __restrict__ p4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  auto cvt = [](float v) { return __ushort_as_bfloat16(pk1<HALF>(v)); };   // HALF: fp16 bits carried in the bf16 type
+  if (i < 4 * 7 * 128 * 32) {
+    const int ci = i & 31, n = (i >> 5) & 127, s = i >> 12;          // s = chunk * 7 + ky
+    const int ky = s % 7, kx = (s / 7) * 2 + (n >> 6), co = n & 63;
+    p3[i] = cvt(kx < 7 ? w3[((co * 32 + ci) * 7 + ky) * 7 + kx] : 0.f);
+  }
+  if (i < 2 * 7 * 128 * 64) {
+    const int ci = i & 63, n = (i >> 6) & 127, s = i >> 13;
+    const int ky = s % 7, kx = (s / 7) * 4 + (n >> 5), co = n & 31;
+    p4[i] = cvt(kx < 7 ? w4[((ci * 32 + co) * 7 + ky) * 7 + kx] : 0.f);
+  }
+}
+
+template <bool CONVT, bool HALF>
+static int launch_k7t(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
+                      int64_t batch, int* err, cudaStream_t st) {
+  using Cfg = K7TCfg<CONVT>;
+  CUtensorMap ta, tb;
+  int r;
+  if (CONVT) {
+    // a3 [n][10][10][64]: the 10 input rows, 16 columns from 0 (columns 10..15: TMA zero fill)
+    cuuint64_t dims[4] = {64, 10, 10, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {128, 1280, 12800};
+    cuuint32_t box[4] = {64, 16, 10, 1};
+    r = encode_tmap(&ta, 4, act_in, dims, strides, box);
+  } else {
+    // a2 [n][16][16][32]: one whole image, 64-byte operand rows
+    cuuint64_t dims[4] = {32, 16, 16, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {64, 1024, 16384};
+    cuuint32_t box[4] = {32, 16, 16, 1};
+    r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
+  if (r != SG_OK) return r;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cfg::kCin, (cuuint64_t)Cfg::kChunks * 7 * 128};
+    cuuint64_t strides[1] = {(cuuint64_t)Cfg::kRowB};
+    cuuint32_t box[2] = {(cuuint32_t)Cfg::kCin, 128};
+    r = encode_tmap(&tb, 2, wpk, dims, strides, box, CONVT ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r != SG_OK) return r;
+  }
+  const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
+  ae_k7t_kernel<CONVT, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1469,11 +1740,12 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
   SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));
-  pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
+  if (SEG == 1) pack_k7t_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
+  else pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
   SG_LAUNCH_CHECK();
   const int64_t cap = (int64_t)state().sm_count * 8;
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
-  if ((HALF || (SEG == 1 && !getenv("SG_AE_ENC1_CUDA"))) && ((uintptr_t)x & 15) == 0) {   // tensor-core form
+  if (SEG == 1 && ((uintptr_t)x & 15) == 0) {   // tensor-core form (single-segment modes)
     pack_enc1_kernel<<<3, 256, 0, st>>>(h_params[0], bf(L.w1), HALF);
     CUtensorMap tx, tb;
     cuuint64_t xdims[4] = {64, 64, 3, (cuuint64_t)batch};        // fp32 NCHW input: (w, h, c, n)
@@ -1494,7 +1766,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
   }
   SG_LAUNCH_CHECK();
-  if (HALF || (SEG == 1 && !getenv("SG_AE_ENC2_CUDA"))) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
+  if (SEG == 1) {   // tensor-core form (single-segment modes); the CUDA-core form serves the fp32-parity mode
     pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2), HALF);
     CUtensorMap ta, tb;
     // a1 [n][32][32][16]: box = 16 ch x (16 columns at stride 2) x (8 rows at stride 2) of one image
@@ -1516,12 +1788,16 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
   }
   SG_LAUNCH_CHECK();
-  int r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
-  if (r != SG_OK) return r;
-  if (SEG == 1 && !HALF && getenv("SG_AE_TAP_STREAM")) {   // per-tap streaming form kept for A/B timing (bf16 mode)
-    r = launch_k7<32, true, false>(bf(L.a3), bf(L.w4), h_params[7], bf(L.a4), batch, err, st);
+  int r;
+  if (SEG == 1) {
+    // single-segment modes: both 7x7 layers in row-tap form (input resident in shared memory, column taps on N)
+    r = launch_k7t<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
+    if (r != SG_OK) return r;
+    r = launch_k7t<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
     if (r != SG_OK) return r;
   } else {
+    r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
+    if (r != SG_OK) return r;
     CUtensorMap ta, tb;
     cuuint64_t adims[4] = {(cuuint64_t)64 * SEG, 10, 10, (cuuint64_t)batch};
     cuuint64_t astr[3] = {(cuuint64_t)128 * SEG, (cuuint64_t)1280 * SEG, (cuuint64_t)12800 * SEG};
@@ -1537,7 +1813,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     ae_dec1_kernel<SEG, HALF><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
     SG_LAUNCH_CHECK();
   }
-  if (HALF || (SEG == 1 && !getenv("SG_AE_DEC2_CUDA"))) {   // tensor-core form (bf16 conv mode); CUDA-core form kept for A/B timing
+  if (SEG == 1) {   // tensor-core form (single-segment modes)
     pack_dec2_kernel<<<(16 * 288 + 255) / 256, 256, 0, st>>>(h_params[8], bf(L.w5), HALF);
     CUtensorMap ta, tb;
     // a4 [n][16][16][32]: box = 16 channels (one half) x 16 columns x 8 rows of one image, shifted by (dx, dy)
@@ -1558,7 +1834,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
   }
   SG_LAUNCH_CHECK();
-  if ((HALF || (SEG == 1 && !getenv("SG_AE_DEC3_CUDA"))) && ((uintptr_t)x & 7) == 0 && ((uintptr_t)recon_out & 7) == 0) {
+  if (SEG == 1 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)recon_out & 7) == 0) {
     pack_dec3_kernel<<<(16 * 144 + 255) / 256, 256, 0, st>>>(h_params[10], bf(L.w6), HALF);
     CUtensorMap ta, tb;
     // a5 [n][32][32][16]: box = 16 ch x 32 columns x 4 rows of one image, shifted by (dx, dy); row / column 32 -> zeros
@@ -1612,6 +1888,10 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<true>::kSmemBytes));
   return SG_OK;
 }
 

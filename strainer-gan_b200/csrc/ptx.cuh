@@ -183,6 +183,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
+// Same for 64-byte-swizzled operands (K = 32 bf16 per row): SBO = 8 rows * 64 B, layout SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
 // Same for 32-byte-swizzled operands (K = 16 bf16 per row): SBO = 8 rows * 32 B, layout SWIZZLE_32B = 6.
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) |

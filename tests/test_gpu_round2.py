@@ -166,7 +166,7 @@ def test_concat_fake_literal_block(sb, golden2):
     label_g = torch.full((fake.size(0),), 1.0, dtype=torch.float, device="cuda")
     crit = nn.BCELoss()
     out_d = d(fake.detach()).view(-1)                       # D step on fake.detach() (":271")
-    assert out_d.shape[0] == B and not out_d.requires_grad
+    assert out_d.shape[0] == B and not fake.detach().requires_grad and fake.requires_grad
     errG = crit(d(fake).view(-1), label_g)
     errG.backward()
     crit(d(fake_ref).view(-1), label_g).backward()
