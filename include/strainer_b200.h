@@ -156,6 +156,12 @@ int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params
 size_t sg_ae_tc_workspace_bytes(int64_t max_batch, int conv_mode);
 int sg_ae_score_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
                    float* err_out, float* recon_out, void* stream);
+/* The two halves of sg_ae_score_tc: sg_ae_pack_tc converts the weights into the kernels' layouts once (and clears the
+ * workspace's status word); sg_ae_forward_tc scores a batch with already packed weights (h_params still supplies the
+ * fp32 biases) -- a dataset-scale caller packs once and runs one forward per chunk on the same workspace. */
+int sg_ae_pack_tc(const float* const* h_params, void* workspace, int conv_mode, void* stream);
+int sg_ae_forward_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
+                     float* err_out, float* recon_out, void* stream);
 int sg_ae_bf16_check(const void* workspace, void* stream);
 
 /* ---- MLP discriminator scoring (28x28 path) --------------------------------------------------

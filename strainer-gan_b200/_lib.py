@@ -46,6 +46,8 @@ _SIGS = {
     "sg_ae_bf16_check": (c_int, [P, P]),
     "sg_ae_tc_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "sg_ae_score_tc": (c_int, [P, c_int64, P, P, c_int, P, P, P]),
+    "sg_ae_pack_tc": (c_int, [P, P, c_int, P]),
+    "sg_ae_forward_tc": (c_int, [P, c_int64, P, P, c_int, P, P, P]),
     "sg_mlp_workspace_bytes": (c_size_t, [c_int64]),
     "sg_mlp_score": (c_int, [P, c_int64, P, P, P, P, P, P]),
     "sg_select_begin": (c_int, [P, c_int64, P]),

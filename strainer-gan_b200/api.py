@@ -1340,33 +1340,48 @@ def _ae_params(autoencoder: nn.Module, device):
     return ps
 
 
-def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: int = 2048, *,
-              conv_mode: str = "fp32") -> torch.Tensor:
+AE_CHUNK = 8192      # images per launch group of the auto-encoder pipeline (1.1 GB of 16-bit activations)
+
+
+def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: int = AE_CHUNK, *,
+              conv_mode: str = "auto") -> torch.Tensor:
     """Per-sample reconstruction MSE of the reference AutoEncoder on the GPU; fp32 device tensor [N].
-    conv_mode 'fp32' (default): fp32-parity arithmetic on the tensor cores (bf16 hi/lo split of activations and 7x7
-    weights, three GEMM segments; ~1e-5 relative); 'bf16' (BASELINE config 4): bf16 operands and activations;
-    'fp16': fp16 operands and activations, one tensor pass, errors within the same 1e-3 bar as 'fp32' at the bf16 mode's speed;
-    'fp32_cuda': every layer in plain fp32 on the CUDA cores (the first implementation, kept as a cross-check)."""
+    conv_mode 'auto' (default): fp16 operands and activations with fp32 accumulation -- one tensor pass, errors within
+    the 1e-3 fp32 bar (measured 2e-6) -- and chunks whose errors come out non-finite (an activation beyond fp16's range)
+    scored again in fp32-parity arithmetic; 'fp16': the same without the recovery; 'fp32': fp32-parity arithmetic on the
+    tensor cores (bf16 hi/lo split of activations and 7x7 weights, three GEMM segments; ~1e-7 relative); 'bf16' (BASELINE
+    config 4): bf16 operands and activations; 'fp32_cuda': every layer in plain fp32 on the CUDA cores (the first
+    implementation, kept as a cross-check)."""
     device = _dev(device)
     lib = _lib_for(device)
-    if conv_mode not in ("fp32", "fp16", "bf16", "fp32_cuda"):
-        raise ValueError("conv_mode must be 'fp32', 'fp16', 'bf16' or 'fp32_cuda'")
+    if conv_mode not in ("auto", "fp32", "fp16", "bf16", "fp32_cuda"):
+        raise ValueError("conv_mode must be 'auto', 'fp32', 'fp16', 'bf16' or 'fp32_cuda'")
     params = _ae_params(autoencoder, device)
     arr = (L.P * 12)(*[t.data_ptr() for t in params])
     n = images.shape[0]
     err = torch.empty(n, dtype=torch.float32, device=device)
     cb = min(chunk, max(n, 1))
-    if conv_mode != "fp32_cuda":
-        mode = {"bf16": L.SG_CONV_BF16, "fp16": L.SG_CONV_FP16}.get(conv_mode, L.SG_CONV_BF16X3)
-        ws = _Scratch.get(device, "ae_tc", lib.sg_ae_tc_workspace_bytes(cb, mode))
+    if conv_mode == "fp32_cuda":
+        ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(cb))
         for i, x in _device_f32_chunks(images, device, chunk):
-            L.check(lib.sg_ae_score_tc(_p(x), x.shape[0], arr, _p(ws), mode, _p(err[i:i + chunk]), L.P(0), _stream()),
-                    "sg_ae_score_tc")
-        L.check(lib.sg_ae_bf16_check(_p(ws), _stream()), "sg_ae_bf16_check")
+            L.check(lib.sg_ae_score(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()), "sg_ae_score")
         return err
-    ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(cb))
-    for i, x in _device_f32_chunks(images, device, chunk):
-        L.check(lib.sg_ae_score(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()), "sg_ae_score")
+    mode = {"bf16": L.SG_CONV_BF16, "fp16": L.SG_CONV_FP16, "auto": L.SG_CONV_FP16}.get(conv_mode, L.SG_CONV_BF16X3)
+    ws = _Scratch.get(device, ("ae_tc", mode), lib.sg_ae_tc_workspace_bytes(cb, mode))
+    L.check(lib.sg_ae_pack_tc(arr, _p(ws), mode, _stream()), "sg_ae_pack_tc")      # once; one forward per chunk below
+    nchunks = (n + chunk - 1) // chunk
+    mm = torch.empty((max(nchunks, 1), 8), dtype=torch.float32, device=device) if conv_mode == "auto" else None
+    for ci, (i, x) in enumerate(_device_f32_chunks(images, device, chunk)):
+        e = err[i:i + x.shape[0]]
+        L.check(lib.sg_ae_forward_tc(_p(x), x.shape[0], arr, _p(ws), mode, _p(e), L.P(0), _stream()), "sg_ae_forward_tc")
+        if mm is not None:     # min / max of the chunk's errors (NaN if any NaN): the overflow probe of the auto mode
+            L.check(lib.sg_minmax(_p(e), x.shape[0], _p(mm[ci]), _stream()), "sg_minmax")
+    L.check(lib.sg_ae_bf16_check(_p(ws), _stream()), "sg_ae_bf16_check")             # synchronises: pipeline time-outs
+    if mm is not None and n:
+        bad = np.nonzero(~np.isfinite(mm[:nchunks, :2].cpu().numpy()).all(axis=1))[0]
+        for ci in bad:
+            i0, i1 = int(ci) * chunk, min(n, (int(ci) + 1) * chunk)
+            err[i0:i1].copy_(ae_errors(autoencoder, images[i0:i1], device, min(chunk, 2048), conv_mode="fp32"))
     return err
 
 
@@ -1383,7 +1398,7 @@ def mean_plus_k_std(values: torch.Tensor, k: float) -> torch.Tensor:
     return thr
 
 
-def detect_outliers_autoencoder(autoencoder, dataset, device, threshold=2.0, *, conv_mode: str = "fp32"):
+def detect_outliers_autoencoder(autoencoder, dataset, device, threshold=2.0, *, conv_mode: str = "auto"):
     """``detect_outliers_autoencoder`` ("#autoencoder.py:307-322"): per-sample reconstruction MSE,
     inlier = error < mean + threshold * std (unbiased).  Returns a CPU torch.BoolTensor [N] like the
     reference (whose errors are ``.cpu()``'d)."""

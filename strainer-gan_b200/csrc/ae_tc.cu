@@ -482,10 +482,13 @@ struct K7TCfg {
   static constexpr int kLoadBytes = (CONVT ? 10 : 16) * 16 * kRowB;
   static constexpr int kSlots = 2;
   static constexpr int kBBytes = 128 * kRowB;                  // one (chunk, ky) weight stage
-  static constexpr int kBStages = 4;
+  // a stage is consumed in 256 (enc3) / 512 (dec1) tensor cycles, an L2 -> shared-memory TMA takes ~1.5 k cycles to land:
+  // 128 KB of weight stages in flight keep the issuer fed (4 stages left it latency bound: 0.45 ms per 8192 images)
+  static constexpr int kBStages = CONVT ? 8 : 16;
   static constexpr int kTmemCols = 512;                        // 2 accumulators x (2 tiles x 128 columns)
   static constexpr int kThreads = 320;
-  static constexpr int kSmemBytes = kSlots * kSlotBytes + kBStages * kBBytes + 256 + 256 + 1024;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + kBStages * kBBytes + kBarBytes + 256 + 1024;
 };
 
 template <bool CONVT, bool HALF>
@@ -510,7 +513,8 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   constexpr int kNb = 2 * UA + 2 * SB + 4;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
   volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
-  float* s_bias = reinterpret_cast<float*>(smem + (bar0 - base) + 256);
+  static_assert((kNb + 2) * 8 <= Cfg::kBarBytes, "barrier block too small");
+  float* s_bias = reinterpret_cast<float*>(smem + (bar0 - base) + Cfg::kBarBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -613,12 +617,15 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < COUT; ++j) o[j] = s_bias[j];
       bool ok = true;
-#pragma unroll 1
+      // fully unrolled over (chunk, kx): the shuffle distance is an immediate (a register distance made SHFL the
+      // bound of the whole kernel: 96 % XU utilisation, tensor pipe 49 % active)
+#pragma unroll
       for (int c = 0; c < Cfg::kChunks; ++c) {
+        if (!ok) break;
         if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 26)) { ok = false; break; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + tile * 128);
-#pragma unroll 1
+#pragma unroll
         for (int kl = 0; kl < Cfg::kKxPerChunk; ++kl) {
           const int kx = c * Cfg::kKxPerChunk + kl;
           if (kx >= 7) break;
@@ -630,11 +637,13 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float t = __uint_as_float(v[j]);
-              if (CONVT) {      // out[oy][ox] += T[(oy, ox - kx)][kx]: from the lane kx to the left (none: zero)
-                const float u = __shfl_up_sync(0xffffffffu, t, (unsigned)kx, 16);
-                t = (ix >= kx) ? u : 0.f;
-              } else {          // out[oy][ox] += T[(oy, ox + kx)][kx]: from the lane kx to the right (dead lanes: own value)
-                t = __shfl_down_sync(0xffffffffu, t, (unsigned)kx, 16);
+              if (kx > 0) {
+                if (CONVT) {      // out[oy][ox] += T[(oy, ox - kx)][kx]: from the lane kx to the left (none: zero)
+                  const float u = __shfl_up_sync(0xffffffffu, t, (unsigned)kx, 16);
+                  t = (ix >= kx) ? u : 0.f;
+                } else {          // out[oy][ox] += T[(oy, ox + kx)][kx]: from the lane kx to the right (dead lanes: own value)
+                  t = __shfl_down_sync(0xffffffffu, t, (unsigned)kx, 16);
+                }
               }
               o[cb + j] += t;
             }
@@ -1733,20 +1742,33 @@ static int launch_k7(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, cons
 
 template <int SEG, bool HALF = false>
 static int score_impl(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
-                      float* recon_out, cudaStream_t st) {
+                      float* recon_out, cudaStream_t st, bool do_pack = true, bool do_forward = true) {
   const Layout L = layout(batch, SEG);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* err = reinterpret_cast<int*>(ws + L.flag);
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
-  SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
-  SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));
-  if (SEG == 1) pack_k7t_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
-  else pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
-  SG_LAUNCH_CHECK();
+  if (do_pack) {
+    // the weight blocks sit in front of the activations: their offsets do not depend on the batch size
+    SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
+    if (SEG == 1) pack_k7t_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
+    else pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
+    SG_LAUNCH_CHECK();
+    if (SEG == 1) {
+      pack_enc1_kernel<<<3, 256, 0, st>>>(h_params[0], bf(L.w1), HALF);
+      SG_LAUNCH_CHECK();
+      pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2), HALF);
+      SG_LAUNCH_CHECK();
+      pack_dec2_kernel<<<(16 * 288 + 255) / 256, 256, 0, st>>>(h_params[8], bf(L.w5), HALF);
+      SG_LAUNCH_CHECK();
+      pack_dec3_kernel<<<(16 * 144 + 255) / 256, 256, 0, st>>>(h_params[10], bf(L.w6), HALF);
+      SG_LAUNCH_CHECK();
+    }
+  }
+  if (!do_forward) return SG_OK;
+  if (SEG == 2) SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));   // slack the paired-tap view reads
   const int64_t cap = (int64_t)state().sm_count * 8;
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
   if (SEG == 1 && ((uintptr_t)x & 15) == 0) {   // tensor-core form (single-segment modes)
-    pack_enc1_kernel<<<3, 256, 0, st>>>(h_params[0], bf(L.w1), HALF);
     CUtensorMap tx, tb;
     cuuint64_t xdims[4] = {64, 64, 3, (cuuint64_t)batch};        // fp32 NCHW input: (w, h, c, n)
     cuuint64_t xstr[3] = {64 * 4, 64 * 64 * 4, 3 * 64 * 64 * 4};
@@ -1767,7 +1789,6 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   }
   SG_LAUNCH_CHECK();
   if (SEG == 1) {   // tensor-core form (single-segment modes); the CUDA-core form serves the fp32-parity mode
-    pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2), HALF);
     CUtensorMap ta, tb;
     // a1 [n][32][32][16]: box = 16 ch x (16 columns at stride 2) x (8 rows at stride 2) of one image
     cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
@@ -1814,7 +1835,6 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     SG_LAUNCH_CHECK();
   }
   if (SEG == 1) {   // tensor-core form (single-segment modes)
-    pack_dec2_kernel<<<(16 * 288 + 255) / 256, 256, 0, st>>>(h_params[8], bf(L.w5), HALF);
     CUtensorMap ta, tb;
     // a4 [n][16][16][32]: box = 16 channels (one half) x 16 columns x 8 rows of one image, shifted by (dx, dy)
     cuuint64_t adims[4] = {32, 16, 16, (cuuint64_t)batch};
@@ -1835,7 +1855,6 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   }
   SG_LAUNCH_CHECK();
   if (SEG == 1 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)recon_out & 7) == 0) {
-    pack_dec3_kernel<<<(16 * 144 + 255) / 256, 256, 0, st>>>(h_params[10], bf(L.w6), HALF);
     CUtensorMap ta, tb;
     // a5 [n][32][32][16]: box = 16 ch x 32 columns x 4 rows of one image, shifted by (dx, dy); row / column 32 -> zeros
     cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
@@ -1916,16 +1935,37 @@ int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params
   return sg::aetc::score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
 }
 
+static int ae_tc_dispatch(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
+                          float* err_out, float* recon_out, void* stream, bool do_pack, bool do_forward) {
+  using namespace sg::aetc;
+  cudaStream_t st = sg::as_stream(stream);
+  if (conv_mode == SG_CONV_FP16) return score_impl<1, true>(x, batch, h_params, workspace, err_out, recon_out, st, do_pack, do_forward);
+  if (conv_mode == SG_CONV_BF16X3) return score_impl<2>(x, batch, h_params, workspace, err_out, recon_out, st, do_pack, do_forward);
+  return score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, st, do_pack, do_forward);
+}
+
 int sg_ae_score_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
                    float* err_out, float* recon_out, void* stream) {
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
   int r = ae_tc_args(x, batch, h_params, workspace, err_out);
   if (r != SG_OK || batch == 0) return r;
-  if (conv_mode == SG_CONV_FP16)
-    return sg::aetc::score_impl<1, true>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
-  if (conv_mode == SG_CONV_BF16X3)
-    return sg::aetc::score_impl<2>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
-  return sg::aetc::score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
+  return ae_tc_dispatch(x, batch, h_params, workspace, conv_mode, err_out, recon_out, stream, true, true);
+}
+
+int sg_ae_pack_tc(const float* const* h_params, void* workspace, int conv_mode, void* stream) {
+  SG_READY();
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
+  SG_REQUIRE(h_params && workspace && ((uintptr_t)workspace & 1023) == 0, "h_params / 1024-byte aligned workspace");
+  for (int i = 0; i < 12; ++i) SG_REQUIRE(h_params[i] != nullptr, "h_params must hold 12 device pointers (w, b) x 6");
+  return ae_tc_dispatch(nullptr, 1, h_params, workspace, conv_mode, nullptr, nullptr, stream, true, false);
+}
+
+int sg_ae_forward_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
+                     float* err_out, float* recon_out, void* stream) {
+  SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
+  int r = ae_tc_args(x, batch, h_params, workspace, err_out);
+  if (r != SG_OK || batch == 0) return r;
+  return ae_tc_dispatch(x, batch, h_params, workspace, conv_mode, err_out, recon_out, stream, false, true);
 }
 
 int sg_ae_bf16_check(const void* workspace, void* stream) {
