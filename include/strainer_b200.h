@@ -171,6 +171,32 @@ size_t sg_mlp_workspace_bytes(int64_t max_batch);
 int sg_mlp_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* logit,
                  float* prob, float* loss, void* stream);
 
+/* The same chain on the tensor cores for dataset-scale batches ("tcgen05 GEMM chain"): fp32 rows -> fp16,
+ * three tcgen05 GEMMs (fp16 operands, fp32 accumulation, fused bias + LeakyReLU epilogues), dot + sigmoid + BCE head.
+ * sg_mlp_tc_pack converts the three hidden-layer weights to fp16 once (packed: sg_mlp_tc_packed_bytes, 1024-aligned);
+ * h_params still supplies the fp32 biases and the last layer.  status2 (device int32[2], caller-zeroed, may be NULL = the
+ * first words of `workspace`): [0] pipeline time-out role code, [1] non-zero if a logit came out non-finite (an
+ * activation beyond fp16's range: score that batch with sg_mlp_score). */
+size_t sg_mlp_tc_packed_bytes(void);
+size_t sg_mlp_tc_workspace_bytes(int64_t max_batch);
+int sg_mlp_tc_pack(const float* const* h_params, void* packed, void* stream);
+int sg_mlp_score_tc(const float* x, int64_t batch, const float* const* h_params, const void* packed, void* workspace,
+                    float* logit, float* prob, float* loss, int32_t* status2, void* stream);
+
+/* ---- DCGAN-28 conv discriminator scoring (BASELINE.json config 1) -------------------------------
+ * The reference has no 28x28 DCGAN; SURVEY 8d C1 option (ii) defines one for config 1 and this is it:
+ * Conv(1->64, k4 s2 p1) LeakyReLU(.2) | Conv(64->128, k4 s2 p1) BatchNorm2d LeakyReLU(.2) | Conv(128->1, k7) Sigmoid,
+ * all convs without bias; eval-mode BN folded.  Layer 1 runs on the CUDA cores and writes the im2col rows of layer 2,
+ * which is one tcgen05 GEMM [batch*49, 1024] x [128, 1024]^T; layer 3 + sigmoid + BCE is a dot per image.
+ * w1 [64,1,4,4] fp32 is read as is; sg_d28_pack packs w2 [128,64,4,4], w3 [1,128,7,7] and the BN fold.
+ * x fp32 [batch,1,28,28].  status2 as for sg_mlp_score_tc. */
+size_t sg_d28_packed_bytes(void);
+size_t sg_d28_workspace_bytes(int64_t max_batch);
+int sg_d28_pack(const float* w2, const float* w3, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                const float* bn_var, float bn_eps, void* packed, void* stream);
+int sg_d28_score(const float* x, int64_t batch, const float* w1, const void* packed, void* workspace, float* logit,
+                 float* prob, float* loss, int32_t* status2, void* stream);
+
 /* ---- selection: order statistics, thresholds ------------------------------------------
  * replaces np.percentile "#strainer gan.py:381", "# 종합 loss.py:288-292" and torch.quantile
  * "# 상위 10% 제거해서 fake image에 concate.py:246", "# z_score + DBSCAN.py:323".

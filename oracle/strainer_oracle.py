@@ -201,6 +201,44 @@ class MLPDiscriminator(nn.Module):
         return self.model(x)
 
 
+class Discriminator28(nn.Module):
+    """DCGAN-28 conv discriminator for BASELINE config 1.  The reference has NO 28x28 DCGAN (its 28x28
+    scripts use the MLP above); SURVEY 8d C1 option (ii) defines this net for the config -- the 64x64 Discriminator's
+    recipe ("#strainer gan.py:230-256": k4 s2 p1 convs without bias, BatchNorm from the second layer on, LeakyReLU .2,
+    a final full-map conv + Sigmoid) cut down to 28x28 grayscale.  torch.nn on the CPU IS its oracle."""
+
+    def __init__(self, ndf: int = 64):
+        super().__init__()
+        self.main = nn.Sequential(
+            nn.Conv2d(1, ndf, 4, 2, 1, bias=False), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(ndf, ndf * 2, 4, 2, 1, bias=False), nn.BatchNorm2d(ndf * 2), nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(ndf * 2, 1, 7, 1, 0, bias=False), nn.Sigmoid())
+
+    def forward(self, x):
+        return self.main(x)
+
+
+def make_discriminator28(seed: int = SEED) -> Discriminator28:
+    """weights_init'ed DCGAN-28 D with non-trivial BN running statistics (as make_discriminator)."""
+    g = torch.Generator().manual_seed(seed)
+    d = Discriminator28()
+    for m in d.modules():
+        if isinstance(m, nn.Conv2d):
+            m.weight.data = torch.randn(m.weight.shape, generator=g) * 0.02
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data = 1.0 + torch.randn(m.weight.shape, generator=g) * 0.02
+            m.bias.data.zero_()
+            m.running_mean = torch.randn(m.running_mean.shape, generator=g) * 0.1
+            m.running_var = torch.rand(m.running_var.shape, generator=g) + 0.5
+    return d
+
+
+def synth_images28(start: int, count: int, seed: int = SEED) -> np.ndarray:
+    """Config-1 inputs: fp32 [count,1,28,28] in [-1,1], 80 % smooth "clean" images / 20 % iid noise --
+    the centre 28x28 crop of channel 0 of the 64x64 counter-based stream (same sample keys, same noisy flags)."""
+    return np.ascontiguousarray(synth_images(start, count, seed)[:, :1, 18:46, 18:46])
+
+
 # --------------------------------------------------------------------------------------
 # Scoring (a1+a2, a3, a4)
 # --------------------------------------------------------------------------------------

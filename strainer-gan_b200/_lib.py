@@ -50,6 +50,14 @@ _SIGS = {
     "sg_ae_forward_tc": (c_int, [P, c_int64, P, P, c_int, P, P, P]),
     "sg_mlp_workspace_bytes": (c_size_t, [c_int64]),
     "sg_mlp_score": (c_int, [P, c_int64, P, P, P, P, P, P]),
+    "sg_mlp_tc_packed_bytes": (c_size_t, []),
+    "sg_mlp_tc_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_mlp_tc_pack": (c_int, [P, P, P]),
+    "sg_mlp_score_tc": (c_int, [P, c_int64, P, P, P, P, P, P, P, P]),
+    "sg_d28_packed_bytes": (c_size_t, []),
+    "sg_d28_workspace_bytes": (c_size_t, [c_int64]),
+    "sg_d28_pack": (c_int, [P, P, P, P, P, P, c_float, P, P]),
+    "sg_d28_score": (c_int, [P, c_int64, P, P, P, P, P, P, P, P]),
     "sg_select_begin": (c_int, [P, c_int64, P]),
     "sg_select_hist": (c_int, [P, c_int64, P, c_int, P]),
     "sg_select_step": (c_int, [P, c_int, P]),

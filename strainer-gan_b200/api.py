@@ -607,13 +607,78 @@ def _bump_versions(tensors):
             torch._foreach_mul_(ts, 1.0)
 
 
-class MLPScorer:
-    """Scores the reference's 28x28 MLP Discriminator ("Untitled-2.py:79-94", "# 1,2,8.py:110-128")."""
+MLP_TC_MIN_BATCH = 1024      # below this the chain is launch bound and the fp32 small-batch kernels win
 
-    def __init__(self, discriminator: nn.Module, device=None, max_batch: int = 4096):
+
+class _SmallNetScorer:
+    """Shared ``score`` loop of the 28x28 scorers: chunks of ``max_batch`` rows, host rows copied per chunk, one status read
+    at the end; a chunk that produced a non-finite logit in the fp16 tensor-core form is scored again in fp32."""
+
+    def _score_chunk_tc(self, x, b, logit, prob, loss, status):
+        raise NotImplementedError
+
+    def _score_chunk_fp32(self, x, b, logit, prob, loss):
+        raise NotImplementedError
+
+    def score(self, images, want=("loss",)):
+        n = images.shape[0]
+        outs = {k: torch.empty(n, dtype=torch.float32, device=self.device) for k in want}
+        if n == 0:
+            return outs
+        if isinstance(images, U8Images):
+            images = images.to_f32(self.device)
+        rows = images.reshape(n, -1)
+        if rows.shape[1] != 784:
+            raise ValueError("the 28x28 scorers take [N,1,28,28] or [N,784] inputs")
+        cb = self.max_batch
+        nchunks = (n + cb - 1) // cb
+        status = torch.zeros((nchunks, 2), dtype=torch.int32, device=self.device)
+        tc = []
+        for ci in range(nchunks):
+            i = ci * cb
+            x = _f32c(rows[i:i + cb], self.device)
+            b = x.shape[0]
+            o = [outs[k][i:i + b] if k in outs else None for k in ("logit", "prob", "loss")]
+            if self.use_tc(b):
+                self._score_chunk_tc(x, b, *o, status[ci])
+                tc.append(ci)
+            else:
+                self._score_chunk_fp32(x, b, *o)
+        if tc:
+            st = status.cpu().numpy()
+            if st[:, 0].any():
+                _raise_status(int(st[:, 0][st[:, 0] != 0][0]))
+            for ci in np.nonzero(st[:, 1] != 0)[0]:
+                if self.mode_name == "fp16":
+                    raise RuntimeError("strainer_b200: non-finite logit in the fp16 tensor-core form; use conv_mode='auto' or 'fp32'")
+                i = int(ci) * cb
+                x = _f32c(rows[i:i + cb], self.device)
+                b = x.shape[0]
+                self._score_chunk_fp32(x, b, *[outs[k][i:i + b] if k in outs else None for k in ("logit", "prob", "loss")])
+                self.fallback_chunks += 1
+        return outs
+
+    def use_tc(self, b: int) -> bool:
+        return self.mode_name in ("fp16", "bf16") or (self.mode_name == "auto" and b >= MLP_TC_MIN_BATCH)
+
+
+class MLPScorer(_SmallNetScorer):
+    """Scores the reference's 28x28 MLP Discriminator ("Untitled-2.py:79-94", "# 1,2,8.py:110-128").
+    mode 'auto' (default): batches of >= MLP_TC_MIN_BATCH rows run as a tcgen05 GEMM chain (fp16 operands, fp32
+    accumulation, the 1e-3 bar) with an fp32 re-score of a chunk whose logits overflowed; smaller batches and mode 'fp32'
+    use the fp32 CUDA-core kernels (launch bound at the reference's B = 64); 'fp16': the tensor-core chain at any size."""
+
+    def __init__(self, discriminator: nn.Module, device=None, max_batch: int = 4096, mode: str = "auto"):
         self.device = _dev(device)
+        if mode not in ("auto", "fp32", "fp16"):
+            raise ValueError("MLP scorer modes: 'auto', 'fp32', 'fp16'")
+        self.mode_name = mode
         self.max_batch = int(max_batch)
+        self.fallback_chunks = 0
         self.ws = torch.empty(self.lib.sg_mlp_workspace_bytes(self.max_batch), dtype=torch.uint8, device=self.device)
+        self.ws_tc = None
+        self.packed = None
+        self._packed_sig = None
         self.refresh(discriminator)
 
     @property
@@ -639,12 +704,97 @@ class MLPScorer:
             self.params += [_f32c(m.weight.detach(), self.device), _f32c(m.bias.detach(), self.device)]
         self.arr = (L.P * 8)(*[t.data_ptr() for t in self.params])
 
+    def _ensure_tc(self):
+        lib = self.lib
+        if self.ws_tc is None:
+            self.ws_tc = _aligned_empty(lib.sg_mlp_tc_workspace_bytes(self.max_batch), self.device)
+            self.ws_tc[:1024].zero_()
+            self.packed = _aligned_empty(lib.sg_mlp_tc_packed_bytes(), self.device)
+        if self._packed_sig != self._sig:
+            L.check(lib.sg_mlp_tc_pack(self.arr, _p(self.packed), _stream()), "sg_mlp_tc_pack")
+            self._packed_sig = self._sig
+
+    def _score_chunk_tc(self, x, b, logit, prob, loss, status):
+        self._ensure_tc()
+        L.check(self.lib.sg_mlp_score_tc(_p(x), b, self.arr, _p(self.packed), _p(self.ws_tc), _p(logit), _p(prob), _p(loss),
+                                         _p(status), _stream()), "sg_mlp_score_tc")
+
+    def _score_chunk_fp32(self, x, b, logit, prob, loss):
+        L.check(self.lib.sg_mlp_score(_p(x), b, self.arr, _p(self.ws), _p(logit), _p(prob), _p(loss), _stream()),
+                "sg_mlp_score")
+
     def score_into(self, x, logit=None, prob=None, loss=None):
+        """One batch (<= max_batch rows, fp32 CUDA [b,784]) through the fp32 kernels (the in-batch strain block)."""
         b = x.shape[0]
         if b > self.max_batch:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
-        L.check(self.lib.sg_mlp_score(_p(x), b, self.arr, _p(self.ws), _p(logit), _p(prob), _p(loss), _stream()),
-                "sg_mlp_score")
+        self._score_chunk_fp32(x, b, logit, prob, loss)
+
+
+def _d28_modules(discriminator: nn.Module):
+    convs = [m for m in discriminator.modules() if isinstance(m, nn.Conv2d)]
+    bns = [m for m in discriminator.modules() if isinstance(m, nn.BatchNorm2d)]
+    shapes = [tuple(c.weight.shape) for c in convs]
+    ok = shapes == [(64, 1, 4, 4), (128, 64, 4, 4), (1, 128, 7, 7)] and len(bns) == 1 and all(c.bias is None for c in convs)
+    ok = ok and [c.stride for c in convs] == [(2, 2), (2, 2), (1, 1)] and [c.padding for c in convs] == [(1, 1), (1, 1), (0, 0)]
+    return (convs, bns) if ok else None
+
+
+class D28Scorer(_SmallNetScorer):
+    """Scores the DCGAN-28 conv discriminator of BASELINE config 1 (SURVEY 8d C1 option ii; ``oracle.Discriminator28``):
+    conv 1 on the CUDA cores writing the im2col rows of conv 2, conv 2 + folded eval-mode BN + LeakyReLU as one tcgen05
+    GEMM in fp16, conv 3 + sigmoid + BCE as a dot per image.  Eval-mode BatchNorm only."""
+
+    def __init__(self, discriminator: nn.Module, device=None, max_batch: int = 4096, mode: str = "auto"):
+        self.device = _dev(device)
+        if mode not in ("auto", "fp16"):
+            raise ValueError("DCGAN-28 scorer modes: 'auto', 'fp16'")
+        self.mode_name = mode
+        self.max_batch = int(max_batch)
+        self.fallback_chunks = 0
+        lib = self.lib
+        self.packed = _aligned_empty(lib.sg_d28_packed_bytes(), self.device)
+        self.ws = _aligned_empty(lib.sg_d28_workspace_bytes(self.max_batch), self.device)
+        self.ws[:1024].zero_()
+        self._sig = None
+        self.refresh(discriminator)
+
+    @property
+    def lib(self):
+        return _lib_for(self.device)
+
+    def use_tc(self, b: int) -> bool:
+        return True
+
+    def refresh(self, discriminator, force: bool = False):
+        mods = _d28_modules(discriminator)
+        if mods is None:
+            raise NotImplementedError("not the DCGAN-28 discriminator (Conv 1->64 k4s2p1, Conv 64->128 k4s2p1 + BN, Conv 128->1 k7)")
+        convs, bns = mods
+        bn = bns[0]
+        ts = [c.weight for c in convs] + [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        sig = tuple((t.data_ptr(), t._version) for t in ts)
+        if sig == self._sig and not force:
+            return
+        self._sig = sig
+        self.params = [_f32c(t.detach(), self.device) for t in ts]
+        w1, w2, w3, g, bt, m, v = self.params
+        L.check(self.lib.sg_d28_pack(_p(w2), _p(w3), _p(g), _p(bt), _p(m), _p(v), float(bn.eps), _p(self.packed), _stream()),
+                "sg_d28_pack")
+
+    def _score_chunk_tc(self, x, b, logit, prob, loss, status):
+        L.check(self.lib.sg_d28_score(_p(x), b, _p(self.params[0]), _p(self.packed), _p(self.ws), _p(logit), _p(prob), _p(loss),
+                                      _p(status), _stream()), "sg_d28_score")
+
+    def _score_chunk_fp32(self, x, b, logit, prob, loss):
+        raise RuntimeError("strainer_b200: non-finite logit in the DCGAN-28 fp16 tensor-core form (an activation beyond 65504); "
+                           "this scorer has no fp32 form")
+
+    def score_into(self, x, logit=None, prob=None, loss=None, status=None):
+        b = x.shape[0]
+        if b > self.max_batch:
+            raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        self._score_chunk_tc(x, b, logit, prob, loss, status)
 
 
 _MLP_SCORERS: dict = {}
@@ -657,17 +807,43 @@ def _cache_put(cache: dict, key, module: nn.Module, scorer):
     weakref.finalize(module, cache.pop, key, None)
 
 
-def get_mlp_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096) -> "MLPScorer":
+def get_mlp_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096, mode: str = "auto") -> "MLPScorer":
     """Per-module cache: the weights are uploaded again only when a parameter tensor changed."""
     device = _dev(device)
-    key = (id(discriminator), device.index, max_batch)
+    key = (id(discriminator), device.index, max_batch, mode)
     sc = _MLP_SCORERS.get(key)
     if sc is None:
-        sc = MLPScorer(discriminator, device, max_batch)
+        sc = MLPScorer(discriminator, device, max_batch, mode)
         _cache_put(_MLP_SCORERS, key, discriminator, sc)
     else:
         sc.refresh(discriminator)
     return sc
+
+
+def get_d28_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096, mode: str = "auto") -> "D28Scorer":
+    device = _dev(device)
+    key = ("d28", id(discriminator), device.index, max_batch, mode)
+    sc = _MLP_SCORERS.get(key)
+    if sc is None:
+        sc = D28Scorer(discriminator, device, max_batch, mode)
+        _cache_put(_MLP_SCORERS, key, discriminator, sc)
+    else:
+        sc.refresh(discriminator)
+    return sc
+
+
+def _is_d28(netD) -> bool:
+    return _d28_modules(netD) is not None
+
+
+def scorer_for(discriminator: nn.Module, device=None, conv_mode: str = "auto", max_batch: int = 4096):
+    """The scorer of whichever discriminator of the path this is: the 64x64 DCGAN D (tcgen05 implicit-GEMM convs), the
+    28x28 MLP D or the DCGAN-28 conv D (tcgen05 GEMM chains).  All expose ``score(images, want)``."""
+    if _is_mlp(discriminator):
+        return get_mlp_scorer(discriminator, device, max_batch, conv_mode if conv_mode in ("auto", "fp32", "fp16") else "auto")
+    if _is_d28(discriminator):
+        return get_d28_scorer(discriminator, device, max_batch, "auto")
+    return get_scorer(discriminator, device, conv_mode, max_batch)
 
 
 def _is_mlp(netD) -> bool:
@@ -889,7 +1065,7 @@ def evaluate_dataset(netD, dataset, device, *, conv_mode: str = "auto", return_d
     BCE(D(x), 1) with eval-mode BN (sticky ``netD.eval()``); returns np.ndarray (N,) float32."""
     device = _dev(device)
     netD.eval()
-    losses = _score_dataset(get_scorer(netD, device, conv_mode, _chunk_for(len(dataset))), dataset, ("loss",))["loss"]
+    losses = _score_dataset(scorer_for(netD, device, conv_mode, _chunk_for(len(dataset))), dataset, ("loss",))["loss"]
     return losses if return_device else losses.cpu().numpy()
 
 
@@ -901,7 +1077,7 @@ def refine_dataset_by_loss(dataset, discriminator, device, loss_ratio=0.2, *, co
     device = _dev(device)
     discriminator.eval()  # sticky, as in the reference
     n = len(dataset)
-    losses = _score_dataset(get_scorer(discriminator, device, conv_mode, _chunk_for(n)), dataset, ("loss",))["loss"]
+    losses = _score_dataset(scorer_for(discriminator, device, conv_mode, _chunk_for(n)), dataset, ("loss",))["loss"]
     clean_indices, threshold = select_below_percentile(losses, (1 - loss_ratio) * 100)
     if len(clean_indices) == 0:
         # reference fallback on its (N,1,1)-shaped loss array: argsort along the last axis (len 1) -> zeros
@@ -949,7 +1125,7 @@ def strain_shard(images, discriminator, loss_ratio=0.2, *, group=None, index_bas
     Returns (np.int64 kept_global_indices, np.float32 threshold, losses_dev)."""
     device = _dev(device if device is not None else _dev_of(images))
     discriminator.eval()
-    losses = get_scorer(discriminator, device, conv_mode, _chunk_for(images.shape[0])).score(images, ("loss",))["loss"]
+    losses = scorer_for(discriminator, device, conv_mode, _chunk_for(images.shape[0])).score(images, ("loss",))["loss"]
     idx, thr = select_below_percentile(losses, (1 - loss_ratio) * 100, group, index_base, n_global)
     return idx, thr, losses
 
@@ -1499,6 +1675,21 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
         sc = get_mlp_scorer(netD, device, max_batch=max(b, 512))
         sc.score_into(_f32c(real.reshape(b, -1), device), None, prob, None)
         return strain_scores(real, prob, q)
+    if _is_d28(netD):
+        # 28x28 conv path (BASELINE config 1): DCGAN-28 on a tcgen05 GEMM
+        if netD.training:
+            raise NotImplementedError("the DCGAN-28 scorer folds eval-mode BatchNorm; call netD.eval() before straining "
+                                      "(train-mode batch statistics are implemented for the 64x64 discriminator only)")
+        sc = get_d28_scorer(netD, device, max_batch=max(b, 512))
+        status = torch.zeros(2, dtype=torch.int32, device=device)
+        sc.score_into(_f32c(real, device).contiguous(), None, prob, None, status)
+        out = strain_scores(real, prob, q, _extra_status=status)
+        st0, st1 = _last_status(device)
+        if st0:
+            _raise_status(st0)
+        if st1:
+            raise RuntimeError("strainer_b200: non-finite logit in the DCGAN-28 fp16 tensor-core form")
+        return out
     sc = get_scorer(netD, device, conv_mode, max_batch=max(b, 512))
     x = real.contiguous()
     train = netD.training

@@ -14,6 +14,7 @@ extern "C" int sg_select_init_attributes();
 extern "C" int sg_ae_tc_init_attributes();
 extern "C" int sg_dbscan_init_attributes();
 extern "C" int sg_sort_init_attributes();
+extern "C" int sg_gemm_init_attributes();
 
 namespace sg {
 

@@ -316,3 +316,75 @@ def test_device_argument_other_than_current(sb):
     assert thr0b == thr0
     idx, _ = sb.select_below_percentile(l1, 80.0)
     assert np.array_equal(idx, np.asarray(sub1.indices))
+
+
+def test_mlp_tensor_core_chain_dataset_scale(sb):
+    """config 1 at dataset scale with the reference's MLP D: the tcgen05 GEMM chain (fp16 operands) against torch fp32 on
+    the CPU -- losses within 1e-3, the refine mask exact away from the threshold; ragged tails (M and K) included"""
+    torch.manual_seed(3)
+    d = O.MLPDiscriminator().eval()
+    with torch.no_grad():
+        for p in d.parameters():              # logits spread over [-1.1, 0.55]: with fp16 operands the logit error is
+            p.mul_(2.0)                       # ~5e-4 absolute, which IS the relative loss error of a confident sample
+    n = 5000                                  # 2 chunks of 4096 (the second: 904 rows = 7 M tiles + a 8-row tail)
+    x = torch.from_numpy(O.synth_images28(100, n)).reshape(n, 784)
+    with torch.no_grad():
+        want_p = d(x).reshape(-1)
+    want = O.bce_vs_ones(want_p).numpy()
+    sc = sb.MLPScorer(d, "cuda", max_batch=4096, mode="fp16")
+    out = sc.score(x.cuda(), ("loss", "prob", "logit"))
+    loss = out["loss"].cpu().numpy()
+    rel = np.abs(loss - want) / np.maximum(np.abs(want), ATOL)
+    assert rel.max() <= 1e-3, rel.max()
+    assert (out["prob"].cpu() - want_p).abs().max().item() <= 5e-4
+    # host rows, the auto mode (tensor cores from 1024 rows on) and the reference-facing call
+    ds = torch.utils.data.TensorDataset(x.reshape(n, 1, 28, 28), torch.zeros(n))
+    ev = sb.evaluate_dataset(d, ds, "cuda")
+    assert np.array_equal(ev, loss)
+    sub, thr = sb.refine_dataset_by_loss(ds, d, "cuda", 0.2)
+    wthr = np.percentile(want, 80.0)
+    assert abs(thr - wthr) <= 1e-3 * abs(wthr)
+    got = np.zeros(n, bool)
+    got[np.asarray(sub.indices)] = True
+    near = np.abs(want - wthr) <= 1e-3 * abs(wthr)
+    assert not ((got != (want < wthr)) & ~near).any()
+    # small batches keep the fp32 kernels in auto mode (bit-close to torch)
+    small = sb.get_mlp_scorer(d, "cuda", 512).score(x[:64].cuda(), ("prob",))["prob"]
+    assert (small.cpu() - want_p[:64]).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 64, 300, 4096 + 77])
+def test_dcgan28_conv_discriminator(sb, n):
+    """BASELINE config 1 with the repo-defined DCGAN-28 conv D (SURVEY 8d C1 option ii): its oracle is the same net in
+    torch.nn on the CPU; conv 2 runs as a tcgen05 GEMM over im2col rows written by the conv-1 kernel"""
+    d = O.make_discriminator28(O.SEED).eval()
+    with torch.no_grad():
+        d.main[5].weight.mul_(4.0)            # spread the logits
+    x = torch.from_numpy(O.synth_images28(0, n))
+    with torch.no_grad():
+        want_p = d(x).reshape(-1)
+    want = O.bce_vs_ones(want_p).numpy()
+    sc = sb.D28Scorer(d, "cuda", max_batch=4096)
+    out = sc.score(x.cuda(), ("loss", "prob"))
+    rel = np.abs(out["loss"].cpu().numpy() - want) / np.maximum(np.abs(want), ATOL)
+    assert rel.max() <= 1e-3, rel.max()
+    assert (out["prob"].cpu() - want_p).abs().max().item() <= 5e-4
+    if n >= 64:
+        # the in-batch block of config 1: batch 64, top-10 % removal -> 7 strained reals
+        fr_w, ff_w, mask_w, thr_w = O.strain_scores(x[:64], want_p[:64])
+        fr, ff, mask, thr = sb.strain_batch(d, x[:64].cuda())
+        near = (want_p[:64] - thr_w).abs() <= 1e-3 * thr_w.abs()
+        assert not ((mask.cpu() != mask_w) & ~near).any()
+        assert ff.shape[0] == 7 and fr.shape[0] == 57
+        with pytest.raises(NotImplementedError):
+            sb.strain_batch(d.train(), x[:64].cuda())
+        d.eval()
+    if n > 4096:
+        ds = torch.utils.data.TensorDataset(x, torch.zeros(n))
+        sub, thr = sb.refine_dataset_by_loss(ds, d, "cuda", 0.1)
+        wthr = np.percentile(want, 90.0)
+        assert abs(thr - wthr) <= 1e-3 * abs(wthr)
+        got = np.zeros(n, bool)
+        got[np.asarray(sub.indices)] = True
+        near = np.abs(want - wthr) <= 1e-3 * abs(wthr)
+        assert not ((got != (want < wthr)) & ~near).any()
