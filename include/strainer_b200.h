@@ -139,9 +139,11 @@ int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, 
  * h_params: HOST array of 12 DEVICE pointers {w,b} x {enc.0, enc.2, enc.4, dec.0, dec.2, dec.4} in the
  * PyTorch layouts (Conv2d [out,in,k,k], ConvTranspose2d [in,out,k,k]).  x fp32 NCHW [batch,3,64,64];
  * err_out[batch]; recon_out (optional, [batch,3,64,64]) receives the reconstruction. */
+#ifdef SG_AB_VARIANTS   /* plain fp32 on the CUDA cores: experiment builds only (cross-check of the tensor-core pipeline) */
 size_t sg_ae_workspace_bytes(int64_t max_batch);
 int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
                 float* recon_out, void* stream);
+#endif
 
 /* bf16 conv mode of the same auto-encoder (BASELINE.json config 4): the two 7x7 layers (86 % of the FLOPs) as
  * implicit GEMMs on tcgen05 with bf16 operands / fp32 accumulation, bf16 NHWC activations, the small stride-2

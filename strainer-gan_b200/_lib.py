@@ -96,6 +96,7 @@ _SIGS = {
     "sg_hist_uniform": (c_int, [P, c_int64, P, c_int, P, P]),
 }
 
+_OPTIONAL = {"sg_ae_workspace_bytes", "sg_ae_score"}   # only in -DSG_AB_VARIANTS builds (csrc/ae.cu)
 _lib = None
 _inited_devices = set()
 
@@ -110,6 +111,8 @@ def load():
                 "strainer_b200 has no CPU or PyTorch fallback.")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
+            if name in _OPTIONAL and not hasattr(lib, name):
+                continue
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

@@ -1526,8 +1526,7 @@ def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: 
     the 1e-3 fp32 bar (measured 2e-6) -- and chunks whose errors come out non-finite (an activation beyond fp16's range)
     scored again in fp32-parity arithmetic; 'fp16': the same without the recovery; 'fp32': fp32-parity arithmetic on the
     tensor cores (bf16 hi/lo split of activations and 7x7 weights, three GEMM segments; ~1e-7 relative); 'bf16' (BASELINE
-    config 4): bf16 operands and activations; 'fp32_cuda': every layer in plain fp32 on the CUDA cores (the first
-    implementation, kept as a cross-check)."""
+    config 4): bf16 operands and activations; 'fp32_cuda': plain fp32 on the CUDA cores, experiment builds only."""
     device = _dev(device)
     lib = _lib_for(device)
     if conv_mode not in ("auto", "fp32", "fp16", "bf16", "fp32_cuda"):
@@ -1538,6 +1537,9 @@ def ae_errors(autoencoder: nn.Module, images: torch.Tensor, device=None, chunk: 
     err = torch.empty(n, dtype=torch.float32, device=device)
     cb = min(chunk, max(n, 1))
     if conv_mode == "fp32_cuda":
+        if not hasattr(L.load(), "sg_ae_score"):
+            raise RuntimeError("conv_mode='fp32_cuda' (the plain fp32 CUDA-core pipeline) is an experiment-build variant: "
+                               "rebuild with SG_AB_VARIANTS=1 python strainer-gan_b200/build.py --force")
         ws = _Scratch.get(device, "ae", lib.sg_ae_workspace_bytes(cb))
         for i, x in _device_f32_chunks(images, device, chunk):
             L.check(lib.sg_ae_score(_p(x), x.shape[0], arr, _p(ws), _p(err[i:i + chunk]), L.P(0), _stream()), "sg_ae_score")

@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    ab = ["-DSG_AB_VARIANTS"] if os.environ.get("SG_AB_VARIANTS") else []   # experiment build: + csrc/ae.cu (fp32 CUDA-core AE)
+    cmd = [nvcc] + NVCC_FLAGS + ab + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)

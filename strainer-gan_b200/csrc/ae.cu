@@ -9,6 +9,9 @@
 // Transposed convolutions are evaluated in gather form:
 //   out[oc][y][x] = b[oc] + sum_{ic,ky,kx : (y+p-ky) % s == 0, (x+p-kx) % s == 0}
 //                   in[ic][(y+p-ky)/s][(x+p-kx)/s] * w[ic][oc][ky][kx]
+// NOT part of the release library: compiled only with -DSG_AB_VARIANTS (SG_AB_VARIANTS=1 python strainer-gan_b200/build.py),
+// as the plain-fp32 cross-check of the tensor-core pipeline in csrc/ae_tc.cu.
+#ifdef SG_AB_VARIANTS
 #include "common.cuh"
 
 namespace sg {
@@ -186,3 +189,7 @@ int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, voi
 }
 
 }  // extern "C"
+
+#else
+extern "C" int sg_ae_init_attributes() { return 0; }
+#endif  // SG_AB_VARIANTS

@@ -1750,10 +1750,10 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   if (do_pack) {
     // the weight blocks sit in front of the activations: their offsets do not depend on the batch size
     SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
-    if (SEG == 1) pack_k7t_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
+    if constexpr (SEG == 1) pack_k7t_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
     else pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
     SG_LAUNCH_CHECK();
-    if (SEG == 1) {
+    if constexpr (SEG == 1) {
       pack_enc1_kernel<<<3, 256, 0, st>>>(h_params[0], bf(L.w1), HALF);
       SG_LAUNCH_CHECK();
       pack_enc2_kernel<<<(32 * 144 + 255) / 256, 256, 0, st>>>(h_params[2], bf(L.w2), HALF);
@@ -1788,7 +1788,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
   }
   SG_LAUNCH_CHECK();
-  if (SEG == 1) {   // tensor-core form (single-segment modes); the CUDA-core form serves the fp32-parity mode
+  if constexpr (SEG == 1) {   // tensor-core form (single-segment modes); the CUDA-core form serves the fp32-parity mode
     CUtensorMap ta, tb;
     // a1 [n][32][32][16]: box = 16 ch x (16 columns at stride 2) x (8 rows at stride 2) of one image
     cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
@@ -1810,7 +1810,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   }
   SG_LAUNCH_CHECK();
   int r;
-  if (SEG == 1) {
+  if constexpr (SEG == 1) {
     // single-segment modes: both 7x7 layers in row-tap form (input resident in shared memory, column taps on N)
     r = launch_k7t<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
     if (r != SG_OK) return r;
@@ -1834,7 +1834,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     ae_dec1_kernel<SEG, HALF><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
     SG_LAUNCH_CHECK();
   }
-  if (SEG == 1) {   // tensor-core form (single-segment modes)
+  if constexpr (SEG == 1) {   // tensor-core form (single-segment modes)
     CUtensorMap ta, tb;
     // a4 [n][16][16][32]: box = 16 channels (one half) x 16 columns x 8 rows of one image, shifted by (dx, dy)
     cuuint64_t adims[4] = {32, 16, 16, (cuuint64_t)batch};
@@ -1888,12 +1888,8 @@ extern "C" {
 
 int sg_ae_tc_init_attributes() {
   using namespace sg::aetc;
-  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               K7Cfg<64, false, false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<64, false, true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               K7Cfg<32, true, false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
@@ -1902,10 +1898,6 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               K7Cfg<64, false, false>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<false>::kSmemBytes));

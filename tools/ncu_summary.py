@@ -1,67 +1,38 @@
-"""Summarise ncu outputs for profiles/ (run in the build container; needs only the ncu CLI).
-
-  python tools/ncu_summary.py launches gpurun_out/launches.csv > profiles/rN_launches.txt
-  python tools/ncu_summary.py full gpurun_out/prof.ncu-rep   > profiles/rN_kernel.txt
-"""
-import collections
+"""Per-launch summary of an ncu report: duration, DRAM bytes, achieved DRAM GB/s against the measured (6551 GB/s) and
+nominal (8000 GB/s) HBM peaks, tensor-pipe activity, registers.
+    ncu -i file.ncu-rep --page raw --csv > raw.csv ; python tools/ncu_summary.py raw.csv [--json out.json]"""
 import csv
-import subprocess
+import json
 import sys
 
-METRICS = [
-    "gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread",
-    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
-    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
-    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-    "smsp__cycles_active.avg", "sm__cycles_active.avg", "smsp__inst_executed.sum",
-    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
-]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+col = {h: i for i, h in enumerate(hdr)}
 
 
-def launches(path):
-    lines = [l for l in open(path) if not l.startswith("==")]
-    agg = collections.defaultdict(lambda: [0, 0.0])
-    for row in csv.DictReader(lines):
-        v = float(row["Metric Value"].replace(",", ""))
-        u = row["Metric Unit"]
-        v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v * 1e6 if u == "s" else v
-        agg[row["Kernel Name"]][0] += 1
-        agg[row["Kernel Name"]][1] += v
-    tot = sum(v[1] for v in agg.values())
-    print(f"# ncu --metrics gpu__time_duration.sum launch list: {sum(v[0] for v in agg.values())} launches, {tot/1e3:.2f} ms total")
-    print(f"# (cold-cache, serialised: compare SHARES, not absolutes)")
-    print(f"{'us total':>12} {'launches':>8} {'share':>7} {'us/launch':>10}  kernel")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{v[1]:12.1f} {v[0]:8d} {100*v[1]/tot:6.1f}% {v[1]/v[0]:10.1f}  {k[:110]}")
+def num(r, key, default=0.0):
+    i = col.get(key)
+    if i is None or r[i] in ("", "n/a"):
+        return default
+    v = float(r[i].replace(",", ""))
+    u = units[i]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9,
+             "second": 1.0, "us": 1e-6, "ms": 1e-3, "ns": 1e-9}.get(u, 1.0)
+    return v * scale
 
 
-def full(path, every=False):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    hdr, units = rows[0], rows[1]
-    ni = hdr.index("Kernel Name")
-    seen = set()
-    for r in rows[2:]:
-        if r[ni] in seen and not every:   # one instance per kernel name (repeats of a timing loop are identical)
-            continue
-        seen.add(r[ni])
-        print("kernel:", r[ni])
-        for m in METRICS:
-            if m in hdr:
-                i = hdr.index(m)
-                print(f"  {m:75s} {r[i]:>18s} {units[i]}")
-        stalls = []
-        for i, h in enumerate(hdr):
-            if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h and r[i]:
-                stalls.append((float(r[i].replace(",", "")), h.split("issue_stalled_")[1].split("_per_issue")[0]))
-        print("  warp stall reasons (warps per issue-active cycle):",
-              ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:6]))
-        print()
-
-
-if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+out = []
+print(f"{'kernel':46s} {'us':>9s} {'rd MB':>9s} {'wr MB':>9s} {'GB/s':>8s} {'%6551':>6s} {'%8000':>6s} {'tensor%':>8s} {'regs':>5s}")
+for r in rows[2:]:
+    name = r[col["Kernel Name"]]
+    short = name.split("(")[0].replace("void ", "").replace("sg::", "")[:46]
+    t = num(r, "gpu__time_duration.sum")
+    rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
+    gbs = (rd + wr) / t / 1e9 if t else 0.0
+    tens = num(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    regs = num(r, "launch__registers_per_thread")
+    print(f"{short:46s} {t * 1e6:9.1f} {rd / 1e6:9.1f} {wr / 1e6:9.1f} {gbs:8.0f} {100 * gbs / 6551.4:6.1f} {100 * gbs / 8000:6.1f} {tens:8.1f} {regs:5.0f}")
+    out.append({"kernel": short, "us": t * 1e6, "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_gbs": gbs,
+                "tensor_pipe_active_pct": tens, "registers": regs})
+if "--json" in sys.argv:
+    json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
