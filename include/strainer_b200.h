@@ -220,6 +220,22 @@ int sg_d28_score(const float* x, int64_t batch, const float* w1, const void* pac
 int sg_select_begin(uint32_t* ws, int64_t k, void* stream);
 int sg_select_hist(const float* v, int64_t n, uint32_t* ws, int pass, void* stream);
 int sg_select_step(uint32_t* ws, int pass, void* stream);
+/* Multi-GPU without a collective launch: sg_select_step_peer = the all-reduce of pass `pass` (SUM of ws[0..257), MIN of
+ * ws[257] on the last pass) FUSED into sg_select_step, over NVLink peer memory.  Every rank owns a buffer of
+ * sg_peer_buffer_bytes(nranks) that all ranks have mapped; d_peer_buffers is a DEVICE array of the nranks mapped
+ * addresses (own buffer at index `rank`).  One-shot push protocol: each word travels as one 64-bit store tagged with
+ * `seq` (non-zero, incremented by every rank for every call, in the same order on all ranks); a rank polls only its own
+ * buffer.  All ranks must enqueue the call; each rank's GPU must run it concurrently with its peers' (one process per
+ * GPU).  A peer that never arrives is reported by sg_select_check (status 2), not by a hang.
+ * sg_peer_alloc / sg_peer_open: the one allocation the library makes itself (a CUDA IPC handle needs a cudaMalloc'ed
+ * base): h_handle64 is a HOST buffer of 64 bytes to be exchanged between the processes (e.g. all_gather). */
+size_t sg_peer_buffer_bytes(int nranks);
+int sg_peer_alloc(int nranks, void** buffer_out, void* h_handle64_out);
+int sg_peer_open(const void* h_handle64, void** peer_out);
+int sg_peer_close(void* peer);
+int sg_peer_free(void* buffer);
+int sg_select_step_peer(uint32_t* ws, int pass, void* const* d_peer_buffers, int rank, int nranks, uint32_t seq,
+                        void* stream);
 /* out2[0] = x_(k), out2[1] = x_(k+1) (== x_(k) when k is the last index); NaN if any NaN. */
 int sg_select_finish(const uint32_t* ws, float* out2, void* stream);
 /* single-device convenience: all phases back to back (each histogram pass ends with its own bucket step,

@@ -8,7 +8,7 @@ from .api import (D64Scorer, get_scorer, order_stats, percentile_device, quantil
                   synth_images, ae_errors, mean_plus_k_std, strain_shard, MLPScorer, sort_values, dbscan1d_clean_ratio,
                   ResidentSubset, get_mlp_scorer, gmm_fit_device, dbscan_clean_ratio, U8Images, U8ImageDataset,
                   detect_outliers_fixed, detect_outliers_elbow, detect_outliers_ratio, clear_scorer_caches, D28Scorer,
-                  get_d28_scorer, scorer_for)
+                  get_d28_scorer, scorer_for, PeerComm)
 from . import _lib  # noqa: F401
 
 __version__ = "0.1.0"

@@ -61,6 +61,12 @@ _SIGS = {
     "sg_select_begin": (c_int, [P, c_int64, P]),
     "sg_select_hist": (c_int, [P, c_int64, P, c_int, P]),
     "sg_select_step": (c_int, [P, c_int, P]),
+    "sg_peer_buffer_bytes": (c_size_t, [c_int]),
+    "sg_peer_alloc": (c_int, [c_int, P, P]),
+    "sg_peer_open": (c_int, [P, P]),
+    "sg_peer_close": (c_int, [P]),
+    "sg_peer_free": (c_int, [P]),
+    "sg_select_step_peer": (c_int, [P, c_int, P, c_int, c_int, c_uint32, P]),
     "sg_select_finish": (c_int, [P, P, P]),
     "sg_radix_select": (c_int, [P, c_int64, c_int64, P, P, P]),
     "sg_select_workspace_bytes": (c_size_t, [c_int64]),

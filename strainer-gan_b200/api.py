@@ -8,7 +8,9 @@ sm_100 GPU or without the built library every entry point raises.
 """
 from __future__ import annotations
 
+import ctypes
 import math
+import os
 import weakref
 
 import numpy as np
@@ -168,14 +170,86 @@ class _SelectOps:
         L.check(self.lib.sg_select_finish(_p(ws), _p(out2), _stream()), "sg_select_finish")
 
 
-def order_stats(values: torch.Tensor, k: int, group=None, ops=None) -> torch.Tensor:
+class PeerComm:
+    """NVLink peer-memory communicator of one process group (one process per GPU, one node): every rank owns a small
+    buffer that all ranks map through CUDA IPC; ``sg_select_step_peer`` all-reduces the radix histograms through it inside
+    the select's own kernels (one-shot tagged 64-bit stores), so a sharded strain needs no collective launch at all.
+    Built once per group (``PeerComm.for_group``); every rank must build it and use it in the same order."""
+    _cache: dict = {}
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        self.group = group
+        self.device = _dev(device)
+        self.rank = dist.get_rank(group)
+        self.nranks = dist.get_world_size(group)
+        lib = _lib_for(self.device)
+        buf = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        L.check(lib.sg_peer_alloc(self.nranks, ctypes.byref(buf), handle), "sg_peer_alloc")
+        self.buffer = buf.value
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        ptrs = []
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self.buffer)
+                continue
+            p = ctypes.c_void_p()
+            L.check(lib.sg_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), "sg_peer_open")
+            ptrs.append(p.value)
+            self._opened.append(p.value)
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        self.seq = 0
+        dist.barrier(group=group)          # every buffer is zeroed and mapped before the first tagged store
+
+    def next_seq(self) -> int:
+        self.seq = self.seq % 0xFFFFFFF0 + 1       # never 0: a zeroed slot holds no valid word
+        return self.seq
+
+    @classmethod
+    def for_group(cls, group, device):
+        """The group's communicator, or None when it cannot exist (non-NCCL backend, a single rank, SG_NO_PEER set, or
+        the GPUs cannot map each other's memory): callers then all-reduce through torch.distributed."""
+        import torch.distributed as dist
+        if group is None or os.environ.get("SG_NO_PEER") or dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl":
+            return None
+        key = (id(group), _dev(device).index)
+        if key not in cls._cache:
+            ok = torch.ones(1, dtype=torch.int32, device=device)
+            comm = None
+            try:
+                comm = cls(group, device)
+            except Exception as e:      # every rank must agree on the path: vote below
+                ok.zero_()
+                import warnings
+                warnings.warn(f"strainer_b200: NVLink peer buffers unavailable ({e}); using NCCL all-reduces")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            cls._cache[key] = comm if int(ok.item()) == 1 else None
+        return cls._cache[key]
+
+
+def order_stats(values: torch.Tensor, k: int, group=None, ops=None, comm=None) -> torch.Tensor:
     """Device tensor [x_(k), x_(k+1)] of a 1-D fp32 CUDA tensor (radix select, no sort).
     With ``group`` (torch.distributed), ``values`` is this rank's shard and k the GLOBAL rank: the
-    integer digit histograms (+ NaN count) are all-reduced with SUM after each of the 3 passes and the
-    smallest key above the selected bucket with MIN, so every rank derives bit-identical statistics."""
+    integer digit histograms (+ NaN count) are all-reduced with SUM after each of the 4 passes and the
+    smallest key above the selected bucket with MIN, so every rank derives bit-identical statistics.  With ``comm``
+    (a ``PeerComm``) those reductions run inside the select's own step kernels over NVLink peer memory -- no collective
+    launch; without it through torch.distributed (NCCL / gloo)."""
     device = values.device
     n = values.numel()
     out2 = torch.empty(2, dtype=torch.float32, device=device)
+    if comm is not None:
+        lib = _lib_for(device)
+        ws = _Scratch.get(device, "select_peer", L.SG_SELECT_WS_WORDS * 4).view(torch.int32)
+        L.check(lib.sg_select_begin(_p(ws), k, _stream()), "sg_select_begin")
+        for p in range(L.SG_SELECT_NUM_PASSES):
+            L.check(lib.sg_select_hist(_p(values), n, _p(ws), p, _stream()), "sg_select_hist")
+            L.check(lib.sg_select_step_peer(_p(ws), p, _p(comm.table), comm.rank, comm.nranks, comm.next_seq(), _stream()),
+                    "sg_select_step_peer")
+        L.check(lib.sg_select_finish(_p(ws), _p(out2), _stream()), "sg_select_finish")
+        return out2
     if group is None and ops is None:
         # single device: one streaming read for large n (sampled pivots), fused radix passes otherwise
         lib = _lib_for(device)
@@ -208,14 +282,14 @@ def _lerp_dev(stats2: torch.Tensor, weight, kind: int) -> torch.Tensor:
     return thr
 
 
-def percentile_device(values: torch.Tensor, q, group=None, n_global=None, ops=None) -> torch.Tensor:
+def percentile_device(values: torch.Tensor, q, group=None, n_global=None, ops=None, comm=None) -> torch.Tensor:
     """``np.percentile(values_f32, q)`` evaluated on the GPU; returns a 1-element fp32 device tensor
     holding bit-for-bit numpy's result for python-scalar q (numpy evaluates q and the lerp in fp32)."""
     if group is not None and n_global is None:
         n_global = _group_total(values.numel(), group, values.device)   # never rank the global vector by a shard length
     n = values.numel() if n_global is None else int(n_global)
     k0, k1, gamma, gdt = _np_percentile_plan(n, q)
-    stats2 = order_stats(values, k0, group, ops)
+    stats2 = order_stats(values, k0, group, ops, comm)
     if gdt != np.float32:
         # np.float64 q: numpy interpolates in float64 -> host finish on the two order statistics
         a, b = stats2.cpu().numpy().astype(np.float64)
@@ -1093,40 +1167,46 @@ def _group_total(n_local: int, group, device) -> int:
     return int(t.item())
 
 
-def _select_check(device):
-    """After a synchronisation point: raises if the cooperative select kernel of the last call on ``device`` gave up."""
-    ws = _Scratch._cache.get((device.index, "select"))
+def _select_check(device, key="select"):
+    """After a synchronisation point: raises if the select kernels of the last call on ``device`` gave up (a grid barrier
+    of the cooperative kernel, or a peer that never arrived in the NVLink all-reduce)."""
+    ws = _Scratch._cache.get((device.index, key))
     if ws is not None:
         L.check(_lib_for(device).sg_select_check(_p(ws), _stream()), "sg_select_check")
 
 
-def select_below_percentile(losses: torch.Tensor, q, group=None, index_base: int = 0, n_global=None):
+def select_below_percentile(losses: torch.Tensor, q, group=None, index_base: int = 0, n_global=None, comm="auto"):
     """threshold = np.percentile(losses, q); indices = np.where(losses < threshold)[0] -- on device.
     One host sync at the end (count + threshold).  With ``group`` the losses are this rank's shard of a global vector
     of ``n_global`` elements (summed over the group when not given).  Returns (np.int64 indices, np.float32 threshold)."""
     if group is not None and n_global is None:
         n_global = _group_total(losses.numel(), group, losses.device)
-    thr = percentile_device(losses, q, group, n_global)
+    if isinstance(comm, str):      # 'auto': the group's NVLink peer communicator when there is one, else NCCL all-reduces
+        comm = PeerComm.for_group(group, losses.device) if (group is not None and losses.is_cuda) else None
+    thr = percentile_device(losses, q, group, n_global, comm=comm)
     idx, count, _ = compact_indices(losses, thr, L.SG_LT, index_base)
     thr_h = thr.cpu().numpy()[0]
     c = int(count.item())
     if group is None:
         _select_check(losses.device)
+    elif comm is not None:
+        _select_check(losses.device, "select_peer")
     return idx[:c].cpu().numpy(), thr_h
 
 
 def strain_shard(images, discriminator, loss_ratio=0.2, *, group=None, index_base: int = 0,
-                 n_global=None, conv_mode: str = "auto", device=None):
+                 n_global=None, conv_mode: str = "auto", device=None, comm="auto"):
     """Data-parallel ``refine_dataset_by_loss`` ("#strainer gan.py:364-392") for one rank of a
     sharded dataset: this rank scores ``images`` (global indices index_base ...), the threshold is the
-    GLOBAL percentile (only histograms cross NVLink), and the returned kept indices are global.
+    GLOBAL percentile (only the radix histograms cross NVLink: inside the select kernels over peer memory when the group
+    has a ``PeerComm``, else as NCCL all-reduces; ``comm=None`` forces the latter), and the returned kept indices are global.
     Concatenating the per-rank index arrays in rank order reproduces the single-GPU / reference
     ``np.where`` order.  ``n_global``: total sample count over the group (all-reduced when not given).
     Returns (np.int64 kept_global_indices, np.float32 threshold, losses_dev)."""
     device = _dev(device if device is not None else _dev_of(images))
     discriminator.eval()
     losses = scorer_for(discriminator, device, conv_mode, _chunk_for(images.shape[0])).score(images, ("loss",))["loss"]
-    idx, thr = select_below_percentile(losses, (1 - loss_ratio) * 100, group, index_base, n_global)
+    idx, thr = select_below_percentile(losses, (1 - loss_ratio) * 100, group, index_base, n_global, comm)
     return idx, thr, losses
 
 

@@ -388,3 +388,40 @@ def test_dcgan28_conv_discriminator(sb, n):
         got[np.asarray(sub.indices)] = True
         near = np.abs(want - wthr) <= 1e-3 * abs(wthr)
         assert not ((got != (want < wthr)) & ~near).any()
+
+
+def test_select_step_peer_single_rank(sb):
+    """the NVLink peer-memory all-reduce fused into the select step, exercised with ONE rank (its own buffer is the only
+    peer; the 2/4/8-rank identity runs are tools/multi_gpu_check.py and bench.py's multi_gpu_parity): same order
+    statistics as the single-device select over many calls (both parity slots, sequence numbers)"""
+    import ctypes
+    L = sb._lib
+    lib = L.init(torch.cuda.current_device())
+    buf = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    L.check(lib.sg_peer_alloc(1, ctypes.byref(buf), handle), "sg_peer_alloc")
+    try:
+        class OneRank:
+            table = torch.tensor([buf.value], dtype=torch.int64, device="cuda")
+            rank, nranks, seq = 0, 1, 0
+
+            def next_seq(self):
+                self.seq += 1
+                return self.seq
+        comm = OneRank()
+        rng = np.random.default_rng(9)
+        for n in (1, 7, 1000, 70001):
+            v = rng.standard_normal(n).astype(np.float32)
+            if n > 100:
+                v[::7] = np.round(v[::7], 1)            # ties
+            d = torch.from_numpy(v).cuda()
+            s = np.sort(v)
+            for k in sorted({0, n // 10, n // 2, n - 1}):
+                got = sb.order_stats(d, k, comm=comm).cpu().numpy()
+                assert got[0] == s[k] and got[1] == s[min(k + 1, n - 1)], (n, k, got)
+        v[5] = np.nan
+        assert np.isnan(sb.order_stats(torch.from_numpy(v).cuda(), 3, comm=comm).cpu().numpy()).all()
+        assert comm.seq > 40
+    finally:
+        torch.cuda.synchronize()
+        L.check(lib.sg_peer_free(buf), "sg_peer_free")

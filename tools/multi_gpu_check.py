@@ -23,10 +23,15 @@ def main():
     n = per * world
     netD = O.make_discriminator(O.SEED)
     results = {}
-    for mode in ("fp32", "bf16", "fp16"):
+    comm = sb.PeerComm.for_group(dist.group.WORLD, device)
+    assert comm is not None, "NVLink peer buffers could not be mapped"
+    for mode in ("auto", "fp32", "bf16"):
         imgs = sb.synth_images(rank * per, per, O.SEED, device)
         idx, thr, losses = sb.strain_shard(imgs, netD, 0.1, group=dist.group.WORLD, index_base=rank * per,
-                                           n_global=n, conv_mode=mode, device=device)
+                                           n_global=n, conv_mode=mode, device=device)            # NVLink peer all-reduce
+        idx_n, thr_n, _ = sb.strain_shard(imgs, netD, 0.1, group=dist.group.WORLD, index_base=rank * per,
+                                          n_global=n, conv_mode=mode, device=device, comm=None)  # NCCL all-reduces
+        assert thr == thr_n and np.array_equal(idx, idx_n), "peer-memory and NCCL selects disagree"
         gathered = [None] * world
         dist.all_gather_object(gathered, (idx, thr))
         if rank == 0:
@@ -52,7 +57,33 @@ def main():
             assert np.allclose(g[k], g1[k], rtol=1e-9), (k, g[k], g1[k])
         assert g["n_iter"] == g1["n_iter"]
         results["gmm"] = (g["means"].tolist(), g["n_iter"])
+    # adversarial vectors through the peer path: ties at the threshold, NaN, all-equal, tiny shards, every quantile
+    rng = np.random.default_rng(5)
+    cases = {"ties": np.round(rng.standard_normal(50000 * world), 1).astype(np.float32),
+             "equal": np.full(4097 * world, 0.25, np.float32),
+             "nan": np.where(rng.random(3000 * world) < 1e-3, np.nan, rng.random(3000 * world)).astype(np.float32),
+             "tiny": rng.random(3 * world).astype(np.float32)}
+    for name, v in cases.items():
+        m = v.size // world
+        shard = torch.from_numpy(v[rank * m:(rank + 1) * m]).to(device)
+        for q in (0.0, 10.0, 50.0, 90.0, 99.9, 100.0):
+            got = sb.percentile_device(shard, q, dist.group.WORLD, v.size, comm=comm).cpu().numpy()[0]
+            want = np.percentile(v, q)
+            assert (np.isnan(got) and np.isnan(want)) or got == want, (name, q, got, want)
+    # latency of the two select paths on this rank's 12288-loss shard (CUDA events, median of 50)
+    times = {}
+    for tag, c in (("peer", comm), ("nccl", None)):
+        evs = []
+        for i in range(60):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            sb.percentile_device(losses, 90.0, dist.group.WORLD, n, comm=c)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        times[tag] = float(np.median([a.elapsed_time(b) for a, b in evs[10:]]))
     if rank == 0:
+        results["select_ms"] = times
         print("multi_gpu_check OK", world, "ranks", results, flush=True)
     dist.barrier()
     dist.destroy_process_group()
