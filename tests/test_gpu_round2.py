@@ -170,7 +170,13 @@ def test_concat_fake_literal_block(sb, golden2):
     errG = crit(d(fake).view(-1), label_g)
     errG.backward()
     crit(d(fake_ref).view(-1), label_g).backward()
-    assert torch.equal(gz.grad, gz_ref.grad)                # bit-identical to autograd through torch.cat
+    # the two backward passes run the same cuDNN dgrad kernels on identical data, but those kernels are not
+    # bit-reproducible run to run (split-K atomics): compare closely here, exactly on an injected gradient below
+    assert torch.allclose(gz.grad, gz_ref.grad, rtol=1e-4, atol=1e-10)
+    gz3 = gz_host.cuda().requires_grad_(True)
+    up = torch.randn(B, 3, 64, 64, device="cuda")
+    sb.concat_fake(gz3, filtered_fake).backward(up)
+    assert torch.equal(gz3.grad, up[:B - b_size_fake])      # bit-identical to autograd through torch.cat: grad[:B-s]
     assert np.allclose(gz.grad[:, :, ::16, ::16].cpu().numpy(), golden2["g9_grad_sample"], rtol=2e-2, atol=1e-9)
     assert abs(errG.item() - float(golden2["g9_errG"])) <= 1e-3 * abs(float(golden2["g9_errG"]))
     # a strained tensor that is NOT the pre-placed tail goes through the same kernel into a fresh buffer
