@@ -133,6 +133,34 @@ int sg_d64_check(const void* workspace, void* stream);
 int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, int layer, float* out,
                            void* stream);
 
+/* ---- D64 training step: forward with batch-statistics BatchNorm + the whole backward pass ------------------
+ * replaces what autograd runs for `output = netD(x)` and `err.backward()` in the D and G steps of
+ * "#strainer gan.py:586-633" (":589-592" D on real, ":598-603" D on fake.detach(), ":610-615" G through D).
+ * fp16 operands on tcgen05, fp32 accumulation; gradients carry a per-call power-of-two loss scale.
+ *
+ * workspace: sg_d64_train_workspace_bytes(max_batch) bytes, 1024-byte aligned, prepared ONCE by
+ * sg_d64_train_workspace_init (zero borders of the padded activation / gradient tensors); it keeps everything the
+ * backward pass needs, so one workspace serves one forward -> backward pair at a time.
+ * h_params: HOST array of 11 DEVICE pointers {conv1..conv5 weight [Cout][Cin][4][4], bn2 gamma, bn2 beta, bn3 gamma,
+ * bn3 beta, bn4 gamma, bn4 beta}; h_running_stats: HOST array of 6 DEVICE pointers {bn2 mean, bn2 var, ...} updated in
+ * place as nn.BatchNorm2d does in training mode (NULL: no update).  x fp32 NCHW [batch,3,64,64], 2 <= batch <= max_batch.
+ * forward writes prob[batch] = sigmoid(logit) and logit[batch] (either may be NULL).
+ * backward takes grad_prob[batch] = dL/dprob and writes h_grads (HOST array of 11 DEVICE pointers in h_params' order and
+ * PyTorch layouts; NULL skips every parameter gradient, as the G step may) and grad_x [batch,3,64,64] (NULL skips it). */
+size_t sg_d64_train_workspace_bytes(int64_t max_batch);
+int sg_d64_train_workspace_init(void* workspace, int64_t max_batch, void* stream);
+int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const float* const* h_params,
+                         float* const* h_running_stats, float momentum, float bn_eps, void* workspace, float* prob,
+                         float* logit, void* stream);
+int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, void* workspace,
+                          float* const* h_grads, float* grad_x, void* stream);
+/* synchronises `stream`; SG_ECUDA: a GEMM pipeline timed out, SG_EINVAL: a non-finite logit or gradient was produced
+ * (fp16 range); clears the status words */
+int sg_d64_train_check(void* workspace, void* stream);
+/* debugging / tests: one saved tensor as fp32 NCHW.  what: 1 act1, 2..4 raw conv output of layer 2..4, 5..6 normalised
+ * activation of layer 2..3, 7 normalised activation of layer 4 */
+int sg_d64_train_read(const void* workspace, int64_t batch, int64_t max_batch, int what, float* out, void* stream);
+
 /* ---- auto-encoder reconstruction-error scoring -------------------------------------------
  * replaces AutoEncoder.forward "#autoencoder.py:269-291" and the per-sample
  * F.mse_loss(out, img, 'none').view(B,-1).mean(1) of ":315-316".

@@ -9,6 +9,7 @@ from .api import (D64Scorer, get_scorer, order_stats, percentile_device, quantil
                   ResidentSubset, get_mlp_scorer, gmm_fit_device, dbscan_clean_ratio, U8Images, U8ImageDataset,
                   detect_outliers_fixed, detect_outliers_elbow, detect_outliers_ratio, clear_scorer_caches, D28Scorer,
                   get_d28_scorer, scorer_for, PeerComm)
+from .train import TrainableD64, accelerate_discriminator  # noqa: F401
 from . import _lib  # noqa: F401
 
 __version__ = "0.1.0"

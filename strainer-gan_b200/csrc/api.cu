@@ -128,6 +128,7 @@ int sg_init(int device) {
   if (r == SG_OK) r = sg_dbscan_init_attributes();
   if (r == SG_OK) r = sg_sort_init_attributes();
   if (r == SG_OK) r = sg_gemm_init_attributes();
+  if (r == SG_OK) r = sg_d64_train_init_attributes();
   if (r != SG_OK) { st.ready = false; return r; }
   return SG_OK;
 }

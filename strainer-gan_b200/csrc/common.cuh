@@ -15,6 +15,7 @@ extern "C" int sg_ae_tc_init_attributes();
 extern "C" int sg_dbscan_init_attributes();
 extern "C" int sg_sort_init_attributes();
 extern "C" int sg_gemm_init_attributes();
+extern "C" int sg_d64_train_init_attributes();
 
 namespace sg {
 

@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
                                                           const float* __restrict__ gb, float eps, float momentum,
                                                           const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                                           float* __restrict__ new_mean, float* __restrict__ new_var,
-                                                          float* __restrict__ ss, int save_stats) {
+                                                          float* __restrict__ ss) {
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (ch >= c) return;
@@ -943,11 +943,6 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
   const float scale = gb[ch] / sqrtf((float)var + eps);
   ss[ch] = scale;
   ss[512 + ch] = gb[c + ch] - (float)mean * scale;
-  if (save_stats) {   // training forward (d64_train.cu): batch mean | 1 / sqrt(var + eps) | gamma for the BatchNorm backward
-    ss[1024 + ch] = (float)mean;
-    ss[1536 + ch] = 1.0f / sqrtf((float)var + eps);
-    ss[2048 + ch] = gb[ch];
-  }
   if (running_mean) new_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
   if (running_var) {
     const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
@@ -1324,7 +1319,7 @@ int sg_d64_pack(const float* w1, const float* w2, const float* w3, const float* 
 // updating running_stats[2*(layer-2)] / [2*(layer-2)+1] (may be NULL) with `momentum`.
 static int run_layer_impl(const float* x, int64_t batch, const void* packed, void* workspace, int conv_mode, int layer,
                           float* logit, float* prob, float* loss, int bn_train, float* const* running_stats,
-                          float momentum, float eps, int32_t* status, void* stream, float* bn_save = nullptr) {
+                          float momentum, float eps, int32_t* status, void* stream) {
   using namespace sg::d64;
   SG_READY();
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
@@ -1383,9 +1378,7 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   __nv_bfloat16* act = layer == 2 ? act2 : layer == 3 ? act3 : act4;
   const size_t gb = layer == 2 ? P.gb2 : layer == 3 ? P.gb3 : P.gb4;
   double* part = reinterpret_cast<double*>(ws + W.bnpart);
-  // bn_train == 2 (training forward): scale | shift | mean | rstd | gamma go to the caller's per-layer block and the raw
-  // conv output is left as it is (d64_train.cu applies it out of place and keeps the raw copy for the backward)
-  float* ss = bn_save ? bn_save : reinterpret_cast<float*>(ws + W.bnss);
+  float* ss = reinterpret_cast<float*>(ws + W.bnss);
   int blocks = (int)(rows < kBnBlocks ? rows : kBnBlocks);
   bn_stats_kernel<<<blocks, 256, 0, st>>>(act, rows, c, W.sega, half, part);
   SG_LAUNCH_CHECK();
@@ -1394,37 +1387,11 @@ static int run_layer_impl(const float* x, int64_t batch, const void* packed, voi
   // fp16 mode: the new statistics are parked in the workspace until the head has shown that nothing overflowed
   float* pend = reinterpret_cast<float*>(ws + W.bnrun) + (size_t)2 * (layer - 2) * 512;
   bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(part, blocks, rows, c, fq(gb), eps, momentum, rm, rv, half ? pend : rm,
-                                                  half ? pend + 512 : rv, ss, bn_save != nullptr);
+                                                  half ? pend + 512 : rv, ss);
   SG_LAUNCH_CHECK();
-  if (bn_train == 2) return SG_OK;
   int64_t ab = sg::ceil_div(rows * (c / 8), 256);
   if (ab > (int64_t)sg::state().sm_count * 16) ab = (int64_t)sg::state().sm_count * 16;
   bn_apply_kernel<<<(unsigned)ab, 256, 0, st>>>(act, rows, c, W.sega, half, ss);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
-}
-
-// ---- internal hooks of the training path (csrc/d64_train.cu; declared in d64_internal.cuh) ----------------------------
-int sg_d64_train_layer_(const float* x, int64_t batch, const void* packed, void* workspace, int layer, float* prob,
-                        float* logit, float* const* running_stats, float momentum, float eps, float* bn_save,
-                        int32_t* status, void* stream) {
-  return run_layer_impl(x, batch, packed, workspace, SG_CONV_FP16, layer, logit, prob, nullptr, 2, running_stats, momentum, eps,
-                        status, stream, bn_save);
-}
-
-void sg_d64_workspace_offsets_(int64_t batch, size_t* act_off) {
-  const sg::d64::WorkspaceLayout W = sg::d64::workspace_layout(batch, SG_CONV_FP16);
-  act_off[0] = W.flag; act_off[1] = W.act1; act_off[2] = W.act2; act_off[3] = W.act3; act_off[4] = W.act4;
-}
-
-int sg_d64_train_commit_(void* workspace, int64_t batch, float* const* running_stats, const int32_t* status, void* stream) {
-  using namespace sg::d64;
-  const WorkspaceLayout W = workspace_layout(batch, SG_CONV_FP16);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  BnCommitArgs a;
-  for (int i = 0; i < 6; ++i) a.dst[i] = running_stats ? running_stats[i] : nullptr;
-  bn_commit_kernel<<<6, 512, 0, sg::as_stream(stream)>>>(reinterpret_cast<const float*>(ws + W.bnrun), a,
-                                                         status ? reinterpret_cast<const int*>(status) : reinterpret_cast<const int*>(ws + W.flag));
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
