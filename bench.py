@@ -512,8 +512,9 @@ def main():
         del netDg
 
     # ---- second headline metric of BASELINE.json: DCGAN 64x64 train iters/sec (rank 0, N = 1) ------------------------
-    # The G/D update is outside the straining path and stays torch autograd in every arm; the arms
-    # differ in the in-batch strain block only ("# 상위 10% 제거해서 fake image에 concate.py:243-273").
+    # The generator and the optimisers stay torch autograd in every arm; the arms differ in the in-batch strain block
+    # ("# 상위 10% 제거해서 fake image에 concate.py:243-273") and in who runs the discriminator's forward / backward
+    # (*_d_on_tcgen05 = sb.accelerate_discriminator, csrc/d64_train.cu).
     train = None
     if rank == 0 and world == 1 and not args.no_train:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -525,7 +526,10 @@ def main():
                  "plain_dcgan_no_strain": config_bench.train_iters(device, 40, "none"),
                  "reference_eager_strain_block_on_gpu": config_bench.train_iters(device, 40, "torch"),
                  "b200_strain_batch_concat_fake": config_bench.train_iters(device, 40, "b200"),
-                 "note": "G/D forward + backward + Adam = torch autograd in all arms; only the strain block differs"}
+                 "plain_dcgan_d_on_tcgen05": config_bench.train_iters(device, 40, "none_train"),
+                 "b200_strain_and_d_on_tcgen05": config_bench.train_iters(device, 40, "b200_train"),
+                 "note": "generator forward / backward and Adam = torch autograd in all arms; *_d_on_tcgen05: the discriminator's "
+                         "forward + backward of the D and G steps run on this repo's kernels (sb.accelerate_discriminator)"}
 
     if rank == 0:
         line = {"metric": "strained_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,

@@ -138,21 +138,27 @@ int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, 
  * "#strainer gan.py:586-633" (":589-592" D on real, ":598-603" D on fake.detach(), ":610-615" G through D).
  * fp16 operands on tcgen05, fp32 accumulation; gradients carry a per-call power-of-two loss scale.
  *
+ * packed: sg_d64_train_packed_bytes() bytes, 1024-byte aligned: the fp16 operand forms of the five conv weights, written by
+ * sg_d64_train_pack (h_weights: HOST array of 5 DEVICE pointers, conv1..conv5 weight [Cout][Cin][4][4]); repack after
+ * every optimiser step.  The backward pass reads it too: it must still hold the weights its forward ran with.
  * workspace: sg_d64_train_workspace_bytes(max_batch) bytes, 1024-byte aligned, prepared ONCE by
  * sg_d64_train_workspace_init (zero borders of the padded activation / gradient tensors); it keeps everything the
  * backward pass needs, so one workspace serves one forward -> backward pair at a time.
- * h_params: HOST array of 11 DEVICE pointers {conv1..conv5 weight [Cout][Cin][4][4], bn2 gamma, bn2 beta, bn3 gamma,
- * bn3 beta, bn4 gamma, bn4 beta}; h_running_stats: HOST array of 6 DEVICE pointers {bn2 mean, bn2 var, ...} updated in
- * place as nn.BatchNorm2d does in training mode (NULL: no update).  x fp32 NCHW [batch,3,64,64], 2 <= batch <= max_batch.
+ * h_bn_params: HOST array of 6 DEVICE pointers {bn2 gamma, bn2 beta, bn3 gamma, bn3 beta, bn4 gamma, bn4 beta};
+ * h_running_stats: HOST array of 6 DEVICE pointers {bn2 mean, bn2 var, ...} updated in place as nn.BatchNorm2d does in
+ * training mode (NULL: no update).  x fp32 NCHW [batch,3,64,64], 2 <= batch <= max_batch.
  * forward writes prob[batch] = sigmoid(logit) and logit[batch] (either may be NULL).
- * backward takes grad_prob[batch] = dL/dprob and writes h_grads (HOST array of 11 DEVICE pointers in h_params' order and
- * PyTorch layouts; NULL skips every parameter gradient, as the G step may) and grad_x [batch,3,64,64] (NULL skips it). */
+ * backward takes grad_prob[batch] = dL/dprob and writes h_grads (HOST array of 11 DEVICE pointers {dconv1..dconv5 weight,
+ * dgamma2, dbeta2, dgamma3, dbeta3, dgamma4, dbeta4} in PyTorch layouts; NULL skips every parameter gradient, as the G
+ * step may) and grad_x [batch,3,64,64] (NULL skips it). */
+size_t sg_d64_train_packed_bytes(void);
+int sg_d64_train_pack(const float* const* h_weights, void* packed, void* stream);
 size_t sg_d64_train_workspace_bytes(int64_t max_batch);
 int sg_d64_train_workspace_init(void* workspace, int64_t max_batch, void* stream);
-int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const float* const* h_params,
+int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const void* packed, const float* const* h_bn_params,
                          float* const* h_running_stats, float momentum, float bn_eps, void* workspace, float* prob,
                          float* logit, void* stream);
-int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, void* workspace,
+int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, const void* packed, void* workspace,
                           float* const* h_grads, float* grad_x, void* stream);
 /* synchronises `stream`; SG_ECUDA: a GEMM pipeline timed out, SG_EINVAL: a non-finite logit or gradient was produced
  * (fp16 range); clears the status words */

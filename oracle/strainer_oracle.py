@@ -643,6 +643,46 @@ def sample_pool(pool: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
     return pool[indices]
 
 
+# --------------------------------------------------------------------------------------
+# Training step (8f item 3): the D step and the G step's pass through D, "#strainer gan.py:586-615",
+# restated on the CPU in fp32 (torch autograd IS the reference's arithmetic here).
+# --------------------------------------------------------------------------------------
+D64_PARAM_NAMES = ["w1", "w2", "w3", "w4", "w5", "g2", "b2", "g3", "b3", "g4", "b4"]
+
+
+def d64_params(netD: nn.Module):
+    """conv1..conv5 weights, then (gamma, beta) of the three BatchNorm2d, in D64_PARAM_NAMES order."""
+    convs = [m for m in netD.modules() if isinstance(m, nn.Conv2d)]
+    bns = [m for m in netD.modules() if isinstance(m, nn.BatchNorm2d)]
+    return [c.weight for c in convs] + [t for bn in bns for t in (bn.weight, bn.bias)]
+
+
+def train_step_through_d(netD: nn.Module, real: torch.Tensor, fake: torch.Tensor, real_label: float = 1.0,
+                         fake_label: float = 0.0):
+    """``netD.zero_grad(); netD(real) -> errD_real.backward()`` ":586-592", ``netD(fake.detach()) -> errD_fake.backward()``
+    ":598-603", then (without an optimiser step in between, as the fixture does) ``netD(fake) -> errG.backward()``
+    ":610-615".  netD is used as it is (train mode: batch statistics, running statistics updated three times).
+    Returns the three output vectors, errD, errG, the accumulated D-step gradients and d errG / d fake."""
+    criterion = nn.BCELoss()
+    fake = fake.detach().clone().requires_grad_(True)
+    netD.zero_grad()
+    label = torch.full((real.size(0),), real_label, dtype=torch.float, device=real.device)
+    out_real = netD(real).view(-1)
+    errD_real = criterion(out_real, label)
+    errD_real.backward()
+    label = torch.full((fake.size(0),), fake_label, dtype=torch.float, device=real.device)
+    out_fake = netD(fake.detach()).view(-1)
+    errD_fake = criterion(out_fake, label)
+    errD_fake.backward()
+    d_grads = [p.grad.detach().clone() for p in d64_params(netD)]
+    label = torch.full((fake.size(0),), real_label, dtype=torch.float, device=real.device)
+    out_g = netD(fake).view(-1)
+    errG = criterion(out_g, label)
+    errG.backward()
+    return dict(out_real=out_real.detach(), out_fake=out_fake.detach(), out_g=out_g.detach(),
+                errD=(errD_real + errD_fake).detach(), errG=errG.detach(), d_grads=d_grads, dfake=fake.grad.detach())
+
+
 def gmm_fit_deterministic(losses: np.ndarray, max_iter: int = 10, tol: float = 1e-2, reg_covar: float = 5e-4,
                           kmeans_iters: int = 30):
     """float64 restatement of the device EM (csrc/gmm.cu): scikit-learn's GaussianMixture equations

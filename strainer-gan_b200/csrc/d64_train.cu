@@ -472,14 +472,24 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict
   }
 }
 
+// one warp per channel: lanes stride over the row blocks' partial sums (fixed order -> deterministic)
+__device__ __forceinline__ void warp_partial_sums(const float* __restrict__ partial, int blocks, int C, int ch, int lane, double& s,
+                                                  double& q) {
+  s = 0.0; q = 0.0;
+  for (int b = lane; b < blocks; b += 32) { s += (double)partial[((size_t)b * 2) * C + ch]; q += (double)partial[((size_t)b * 2 + 1) * C + ch]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+}
+
 __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, int blocks, int64_t rows, int C,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, float momentum, float* __restrict__ run_mean,
                                                               float* __restrict__ run_var, float* __restrict__ ss) {
-  const int ch = blockIdx.x * 256 + threadIdx.x;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ch >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < blocks; ++b) { s += (double)partial[((size_t)b * 2) * C + ch]; q += (double)partial[((size_t)b * 2 + 1) * C + ch]; }
+  double s, q;
+  warp_partial_sums(partial, blocks, C, ch, lane, s, q);
+  if (lane != 0) return;
   const double mean = s / (double)rows;
   double var = q / (double)rows - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -527,10 +537,11 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
                                                               const float* __restrict__ ss, const float* __restrict__ scal,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               float* __restrict__ coef, int* __restrict__ status) {
-  const int ch = blockIdx.x * 256 + threadIdx.x;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ch >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < blocks; ++b) { s1 += (double)partial[((size_t)b * 2) * C + ch]; s2 += (double)partial[((size_t)b * 2 + 1) * C + ch]; }
+  double s1, s2;
+  warp_partial_sums(partial, blocks, C, ch, lane, s1, s2);
+  if (lane != 0) return;
   const float inv = scal[1];
   const float dg = (float)s2 * inv, db = (float)s1 * inv;
   if (!(fabsf(dg) <= 3.0e38f) || !(fabsf(db) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
@@ -574,12 +585,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __half* __restrict__ act4, int64_t batch, const float* __restrict__ w5p,
                                                        float* __restrict__ logit, float* __restrict__ prob_ws, float* __restrict__ prob,
                                                        int* __restrict__ status) {
-  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (b >= batch) return;
+  __shared__ float red[8];
+  const int64_t b = blockIdx.x;
   const __half* a = act4 + b * 8192;
   float acc = 0.f;
-  for (int c = lane * 8; c < 8192; c += 256) {
+#pragma unroll
+  for (int c = threadIdx.x * 8; c < 8192; c += 2048) {
     float x[8], w[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(a + c)), x);
     load8(w5p + c, w);
@@ -587,7 +598,10 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __half* __restrict_
     for (int j = 0; j < 8; ++j) acc = fmaf(x[j], w[j], acc);
   }
   acc = warp_sum(acc);
-  if (lane == 0) {
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    acc = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
     if (!(fabsf(acc) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
     const float pr = 1.0f / (1.0f + expf(-acc));
     if (logit) logit[b] = acc;
@@ -659,33 +673,33 @@ __global__ void __launch_bounds__(256) head_bwd_dw_kernel(const float* __restric
   dw5[(t & 511) * 16 + (t >> 9)] = acc;
 }
 
-// dW [Cout][Cin][4][4] = (1 / scale) * sum_splits partial[s][co][tap * cstride + ci]
+// dW [Cout][Cin][4][4] = (1 / scale) * sum_splits partial[s][co][tap * cstride + ci].  One block per (co, 16 input channels):
+// thread (tap, ci) sums its column over the splits (64-byte runs), the 16 x 16 tile is transposed through shared memory and
+// written as 256 consecutive floats.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int cstride,
                                                            int ldn, const float* __restrict__ scal, float* __restrict__ dw,
                                                            int* __restrict__ status) {
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= cout * cin) return;
-  const int co = t / cin, ci = t - co * cin;
-  const float inv = scal[1];
-  float v[16];
-  bool bad = false;
-#pragma unroll
-  for (int tap = 0; tap < 16; ++tap) {
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * cout + co) * ldn + tap * cstride + ci];
-    acc *= inv;
-    bad |= !(fabsf(acc) <= 3.0e38f);
-    v[tap] = acc;
+  __shared__ float tile[16][17];
+  const int groups = (cin + 15) >> 4;
+  const int co = blockIdx.x / groups, ci0 = (blockIdx.x - co * groups) * 16;
+  const int tap = threadIdx.x >> 4, cil = threadIdx.x & 15;
+  float acc = 0.f;
+  if (ci0 + cil < cin) {
+    const float* src = partial + (size_t)co * ldn + tap * cstride + ci0 + cil;
+    for (int s = 0; s < splits; ++s) acc += src[(size_t)s * cout * ldn];
   }
-  if (bad) atomicExch(status + 1, kNonFiniteMagic);
-  float* d = dw + (size_t)t * 16;
-#pragma unroll
-  for (int tap = 0; tap < 16; ++tap) d[tap] = v[tap];
+  acc *= scal[1];
+  if (!(fabsf(acc) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
+  tile[cil][tap] = acc;
+  __syncthreads();
+  const int ocil = threadIdx.x >> 4, otap = threadIdx.x & 15;
+  if (ci0 + ocil < cin) dw[((size_t)co * cin + ci0 + ocil) * 16 + otap] = tile[ocil][otap];
 }
 
 // ---- workspace ---------------------------------------------------------------------------------------------------------
+struct PackedTrainLayout { size_t wf1, wd1, wf[3], wd[3], w5p, total; };
 struct TrainLayout {
-  size_t status, scal, wf1, wd1, wf[3], wd[3], w5p;
+  size_t status, scal;
   size_t col1, act1p, raw[3], actp[2], act4n, ss, bnpart, prob, dlogit;
   size_t dx[3], dyp[3], dy1, dcol1, partial, coef;
   size_t zero_begin[6], zero_bytes[6];     // the zero-bordered tensors (cleared once by sg_d64_train_workspace_init)
@@ -694,13 +708,10 @@ struct TrainLayout {
 static const int kC[5] = {3, 64, 128, 256, 512};     // channels after layer l
 static const int kS[5] = {64, 32, 16, 8, 4};         // spatial size after layer l
 
-static TrainLayout train_layout(int64_t cap) {
-  TrainLayout L;
-  const size_t b = (size_t)cap;
+static PackedTrainLayout packed_train_layout() {
+  PackedTrainLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o += align_up(bytes, 1024); return at; };
-  L.status = take(1024);
-  L.scal = take(1024);
   L.wf1 = take(64 * 64 * 2);
   L.wd1 = take(64 * 64 * 2);
   for (int l = 0; l < 3; ++l) {
@@ -708,6 +719,17 @@ static TrainLayout train_layout(int64_t cap) {
     L.wd[l] = take((size_t)kC[l + 2] * 16 * kC[l + 1] * 2);
   }
   L.w5p = take(8192 * 4);
+  L.total = o;
+  return L;
+}
+
+static TrainLayout train_layout(int64_t cap) {
+  TrainLayout L;
+  const size_t b = (size_t)cap;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += align_up(bytes, 1024); return at; };
+  L.status = take(1024);
+  L.scal = take(1024);
   L.col1 = take(b * 1024 * 64 * 2);
   int z = 0;
   L.act1p = take(b * 34 * 34 * 64 * 2);
@@ -816,28 +838,43 @@ int sg_d64_train_workspace_init(void* workspace, int64_t max_batch, void* stream
   return SG_OK;
 }
 
-int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const float* const* h_params,
+size_t sg_d64_train_packed_bytes(void) { return sg::dtr::packed_train_layout().total; }
+
+int sg_d64_train_pack(const float* const* h_weights, void* packed, void* stream) {
+  using namespace sg::dtr;
+  SG_READY();
+  SG_REQUIRE(h_weights && packed && ((uintptr_t)packed & 1023) == 0, "h_weights / 1024-byte aligned packed block");
+  for (int i = 0; i < 5; ++i) SG_REQUIRE(h_weights[i] != nullptr, "h_weights: conv1..conv5 weight");
+  const PackedTrainLayout PL = packed_train_layout();
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  PackArgs pa;
+  for (int i = 0; i < 5; ++i) pa.w[i] = h_weights[i];
+  pa.wf1 = reinterpret_cast<__half*>(pk + PL.wf1);
+  pa.wd1 = reinterpret_cast<__half*>(pk + PL.wd1);
+  for (int l = 0; l < 3; ++l) { pa.wf[l] = reinterpret_cast<__half*>(pk + PL.wf[l]); pa.wd[l] = reinterpret_cast<__half*>(pk + PL.wd[l]); }
+  pa.w5p = reinterpret_cast<float*>(pk + PL.w5p);
+  pack_train_kernel<<<sg::state().sm_count * 4, 256, 0, sg::as_stream(stream)>>>(pa);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const void* packed, const float* const* h_bn_params,
                          float* const* h_running_stats, float momentum, float bn_eps, void* workspace, float* prob,
                          float* logit, void* stream) {
   using namespace sg::dtr;
   SG_READY();
-  SG_REQUIRE(x && h_params && workspace, "null pointer");
-  SG_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  SG_REQUIRE(x && packed && h_bn_params && workspace, "null pointer");
+  SG_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)packed & 1023) == 0, "workspace / packed must be 1024-byte aligned");
   SG_REQUIRE(max_batch >= 1 && max_batch <= 4096 && batch >= 2 && batch <= max_batch, "2 <= batch <= max_batch <= 4096");
-  for (int i = 0; i < 11; ++i) SG_REQUIRE(h_params[i] != nullptr, "h_params: w1..w5, gamma2, beta2, gamma3, beta3, gamma4, beta4");
+  for (int i = 0; i < 6; ++i) SG_REQUIRE(h_bn_params[i] != nullptr, "h_bn_params: gamma2, beta2, gamma3, beta3, gamma4, beta4");
   const TrainLayout L = train_layout(max_batch);
+  const PackedTrainLayout PL = packed_train_layout();
   uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
   cudaStream_t st = sg::as_stream(stream);
   int* status = reinterpret_cast<int*>(ws + L.status);
   auto h16 = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
-
-  PackArgs pa;
-  for (int i = 0; i < 5; ++i) pa.w[i] = h_params[i];
-  pa.wf1 = h16(L.wf1); pa.wd1 = h16(L.wd1);
-  for (int l = 0; l < 3; ++l) { pa.wf[l] = h16(L.wf[l]); pa.wd[l] = h16(L.wd[l]); }
-  pa.w5p = reinterpret_cast<float*>(ws + L.w5p);
-  pack_train_kernel<<<sg::state().sm_count * 4, 256, 0, st>>>(pa);
-  SG_LAUNCH_CHECK();
+  auto p16 = [&](size_t off) { return reinterpret_cast<const __half*>(pk + off); };
 
   im2col1_kernel<<<ew_blocks(batch * 4096), 256, 0, st>>>(x, batch, h16(L.col1));
   SG_LAUNCH_CHECK();
@@ -850,7 +887,7 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
     p.plain = 1; p.tpi = 1; p.bb = 1; p.ohb = 1; p.ow = 1; p.nchunk = 1; p.cin = 64; p.batch = (int)batch;
     p.m_valid = (int)(batch * 1024); p.n_valid = 64; p.ldo = 64; p.out = h16(L.act1p); p.err = status;
     if ((r = encode_mat_map(&ta, h16(L.col1), 64, batch * 1024, 128)) != SG_OK) return r;
-    if ((r = encode_mat_map(&tb, h16(L.wf1), 64, 64, 128)) != SG_OK) return r;
+    if ((r = encode_mat_map(&tb, p16(PL.wf1), 64, 64, 128)) != SG_OK) return r;
     if ((r = launch_trgemm<MODE_FPROP>(ta, tb, p, st)) != SG_OK) return r;
   }
   for (int l = 0; l < 3; ++l) {   // layers 2..4
@@ -863,7 +900,7 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
     p.out = h16(L.raw[l]); p.err = status;
     row_box(S, 128, &p, batch, &p.m_tiles);
     if ((r = encode_act_map(&ta, in, batch, 2 * S, cin, p.ow, p.ohb, p.bb)) != SG_OK) return r;
-    if ((r = encode_mat_map(&tb, h16(L.wf[l]), 16 * cin, cout, 128)) != SG_OK) return r;
+    if ((r = encode_mat_map(&tb, p16(PL.wf[l]), 16 * cin, cout, 128)) != SG_OK) return r;
     if ((r = launch_trgemm<MODE_FPROP>(ta, tb, p, st)) != SG_OK) return r;
 
     float* part = reinterpret_cast<float*>(ws + L.bnpart);
@@ -875,25 +912,25 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
     SG_LAUNCH_CHECK();
     float* rm = h_running_stats ? h_running_stats[2 * l] : nullptr;
     float* rv = h_running_stats ? h_running_stats[2 * l + 1] : nullptr;
-    bn_fwd_finalize_kernel<<<(cout + 255) / 256, 256, 0, st>>>(part, blocks, rows, cout, h_params[5 + 2 * l], h_params[6 + 2 * l], bn_eps,
+    bn_fwd_finalize_kernel<<<(cout + 7) / 8, 256, 0, st>>>(part, blocks, rows, cout, h_bn_params[2 * l], h_bn_params[2 * l + 1], bn_eps,
                                                                momentum, rm, rv, ss);
     SG_LAUNCH_CHECK();
     __half* out = (l < 2) ? h16(L.actp[l]) : h16(L.act4n);
     bn_apply_kernel<<<ew_blocks(rows * (cout / 8)), 256, 0, st>>>(h16(L.raw[l]), ss, rows, cout, ilog2(S), l < 2 ? 1 : 0, out);
     SG_LAUNCH_CHECK();
   }
-  head_fwd_kernel<<<(unsigned)sg::ceil_div(batch, 8), 256, 0, st>>>(h16(L.act4n), batch, reinterpret_cast<const float*>(ws + L.w5p), logit,
+  head_fwd_kernel<<<(unsigned)batch, 256, 0, st>>>(h16(L.act4n), batch, reinterpret_cast<const float*>(pk + PL.w5p), logit,
                                                                     reinterpret_cast<float*>(ws + L.prob), prob, status);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 
-int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, void* workspace, float* const* h_grads,
-                          float* grad_x, void* stream) {
+int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, const void* packed, void* workspace,
+                          float* const* h_grads, float* grad_x, void* stream) {
   using namespace sg::dtr;
   SG_READY();
-  SG_REQUIRE(grad_prob && workspace, "null pointer");
-  SG_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+  SG_REQUIRE(grad_prob && packed && workspace, "null pointer");
+  SG_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)packed & 1023) == 0, "workspace / packed must be 1024-byte aligned");
   SG_REQUIRE(max_batch >= 1 && max_batch <= 4096 && batch >= 2 && batch <= max_batch, "2 <= batch <= max_batch <= 4096");
   if (h_grads) for (int i = 0; i < 11; ++i) SG_REQUIRE(h_grads[i] != nullptr, "h_grads: dw1..dw5, dgamma2, dbeta2, ... (or h_grads = NULL)");
   const TrainLayout L = train_layout(max_batch);
@@ -903,7 +940,10 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
   auto h16 = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
   float* scal = reinterpret_cast<float*>(ws + L.scal);
   float* dlogit = reinterpret_cast<float*>(ws + L.dlogit);
-  const float* w5p = reinterpret_cast<const float*>(ws + L.w5p);
+  const PackedTrainLayout PL = packed_train_layout();
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  auto p16 = [&](size_t off) { return reinterpret_cast<const __half*>(pk + off); };
+  const float* w5p = reinterpret_cast<const float*>(pk + PL.w5p);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
   const bool want_w = h_grads != nullptr;
   const int sms = sg::state().sm_count;
@@ -938,7 +978,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     if (blocks > kBnBlocks) blocks = kBnBlocks;
     bn_reduce_kernel<true><<<blocks, 256, 0, st>>>(h16(L.raw[l]), h16(L.dx[l]), ss, rows, cout, part);
     SG_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(cout + 255) / 256, 256, 0, st>>>(part, blocks, rows, cout, ss, scal, want_w ? h_grads[5 + 2 * l] : nullptr,
+    bn_bwd_finalize_kernel<<<(cout + 7) / 8, 256, 0, st>>>(part, blocks, rows, cout, ss, scal, want_w ? h_grads[5 + 2 * l] : nullptr,
                                                                want_w ? h_grads[6 + 2 * l] : nullptr, coef, status);
     SG_LAUNCH_CHECK();
     bn_bwd_apply_kernel<<<ew_blocks(rows * (cout / 8)), 256, 0, st>>>(h16(L.raw[l]), h16(L.dx[l]), ss, coef, rows, cout, ilog2(S),
@@ -954,7 +994,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
       if ((r = encode_dy_map(&ta, h16(L.dyp[l]), batch, S, cout, p.ow, p.ohb, p.bb)) != SG_OK) return r;
       if ((r = encode_act_map(&tb, in, batch, 2 * S, cin, p.ow, p.ohb, p.bb)) != SG_OK) return r;
       if ((r = launch_trgemm<MODE_WGRAD>(ta, tb, p, st)) != SG_OK) return r;
-      wgrad_reduce_kernel<<<(cout * cin + 255) / 256, 256, 0, st>>>(partial, p.splits, cout, cin, cin, 16 * cin, scal, h_grads[l + 1], status);
+      wgrad_reduce_kernel<<<cout * (cin / 16), 256, 0, st>>>(partial, p.splits, cout, cin, cin, 16 * cin, scal, h_grads[l + 1], status);
       SG_LAUNCH_CHECK();
     }
     {   // dX_{l-1}: one GEMM per input-pixel parity class; layer 2's also applies layer 1's LeakyReLU gate -> dY1
@@ -966,7 +1006,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
       p.err = status;
       row_box(S, 128, &p, batch, &p.m_tiles);
       if ((r = encode_dy_map(&ta, h16(L.dyp[l]), batch, S, cout, p.ow, p.ohb, p.bb)) != SG_OK) return r;
-      if ((r = encode_mat_map(&tb, h16(L.wd[l]), 16 * cout, cin, 128)) != SG_OK) return r;
+      if ((r = encode_mat_map(&tb, p16(PL.wd[l]), 16 * cout, cin, 128)) != SG_OK) return r;
       if ((r = launch_trgemm<MODE_DGRAD>(ta, tb, p, st)) != SG_OK) return r;
     }
   }
@@ -979,7 +1019,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     if ((r = encode_mat_map(&ta, h16(L.dy1), 64, batch * 1024, 64)) != SG_OK) return r;
     if ((r = encode_mat_map(&tb, h16(L.col1), 64, batch * 1024, 64)) != SG_OK) return r;
     if ((r = launch_trgemm<MODE_WGRAD>(ta, tb, p, st)) != SG_OK) return r;
-    wgrad_reduce_kernel<<<1, 256, 0, st>>>(partial, p.splits, 64, 3, 4, 64, scal, h_grads[0], status);
+    wgrad_reduce_kernel<<<64, 256, 0, st>>>(partial, p.splits, 64, 3, 4, 64, scal, h_grads[0], status);
     SG_LAUNCH_CHECK();
   }
   if (grad_x) {   // dcol [B*1024][64] = dY1 . W1, then the col2im gather
@@ -988,7 +1028,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     p.plain = 1; p.tpi = 1; p.bb = 1; p.ohb = 1; p.ow = 1; p.nchunk = 1; p.cin = 64; p.batch = (int)batch;
     p.m_valid = (int)(batch * 1024); p.n_valid = 64; p.ldo = 64; p.out = h16(L.dcol1); p.err = status;
     if ((r = encode_mat_map(&ta, h16(L.dy1), 64, batch * 1024, 128)) != SG_OK) return r;
-    if ((r = encode_mat_map(&tb, h16(L.wd1), 64, 64, 128)) != SG_OK) return r;
+    if ((r = encode_mat_map(&tb, p16(PL.wd1), 64, 64, 128)) != SG_OK) return r;
     if ((r = launch_trgemm<MODE_DGRAD>(ta, tb, p, st)) != SG_OK) return r;
     col2im1_kernel<<<ew_blocks(batch * 4096), 256, 0, st>>>(h16(L.dcol1), batch, scal, grad_x);
     SG_LAUNCH_CHECK();

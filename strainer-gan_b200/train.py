@@ -43,7 +43,8 @@ class _D64TrainFn(torch.autograd.Function):
         ws = owner._take(dev, lib, b)
         prob = torch.empty(b, device=dev, dtype=torch.float32)
         stats = owner._running_stats()
-        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, _ptr_array(params),
+        packed, versions = owner._packed_for(dev, lib, params)
+        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, L.P(packed.data_ptr()), _ptr_array(params[5:]),
                                          _ptr_array(stats) if stats else None, owner.momentum, owner.eps,
                                          L.P(ws.buf.data_ptr()), L.P(prob.data_ptr()), None, A._stream()),
                 "sg_d64_train_forward")
@@ -51,6 +52,7 @@ class _D64TrainFn(torch.autograd.Function):
             A._bump_versions(stats)
             owner._count_batch()
         ctx.owner, ctx.ws, ctx.batch, ctx.param_grads = owner, ws, b, param_grads
+        ctx.packed, ctx.versions, ctx.weights = packed, versions, params[:5]
         ctx.shapes = [p.shape for p in params]
         ctx.x_shape = x.shape
         needs = ctx.needs_input_grad
@@ -64,6 +66,9 @@ class _D64TrainFn(torch.autograd.Function):
         ws = ctx.ws
         if ws is None:
             raise RuntimeError("strainer_b200: this discriminator output was produced without a graph")
+        if [w._version for w in ctx.weights] != ctx.versions or ctx.owner._packed_versions != ctx.versions:
+            raise RuntimeError("strainer_b200: a discriminator weight was modified in place between this forward and its backward "
+                               "(autograd raises in the same situation)")
         dev = grad_out.device
         lib = A._lib_for(dev)
         g = grad_out.reshape(-1).to(torch.float32).contiguous()
@@ -71,7 +76,7 @@ class _D64TrainFn(torch.autograd.Function):
         need_p = ctx.param_grads and any(ctx.needs_input_grad[3:])
         grads = [torch.empty(s, device=dev, dtype=torch.float32) for s in ctx.shapes] if need_p else None
         gx = torch.empty(ctx.x_shape, device=dev, dtype=torch.float32) if need_x else None
-        L.check(lib.sg_d64_train_backward(L.P(g.data_ptr()), ctx.batch, ws.capacity, L.P(ws.buf.data_ptr()),
+        L.check(lib.sg_d64_train_backward(L.P(g.data_ptr()), ctx.batch, ws.capacity, L.P(ctx.packed.data_ptr()), L.P(ws.buf.data_ptr()),
                                           _ptr_array(grads) if grads else None, L.P(gx.data_ptr()) if need_x else None,
                                           A._stream()), "sg_d64_train_backward")
         ctx.owner._give_back(ws)
@@ -98,6 +103,8 @@ class TrainableD64(nn.Module):
         self.eps, self.momentum = float(bns[0].eps), float(bns[0].momentum)
         self.max_batch = int(max_batch)
         self._free = []
+        self._packed = None
+        self._packed_versions = None
 
     # -- workspaces: one per forward whose backward is still to come --------------------------------------------------
     def _take(self, device, lib, batch):
@@ -111,6 +118,17 @@ class TrainableD64(nn.Module):
     def _give_back(self, ws):
         if len(self._free) < 4:
             self._free.append(ws)
+
+    def _packed_for(self, device, lib, params):
+        """fp16 operand forms of the conv weights, repacked when a weight's version counter moved (an optimiser step)"""
+        versions = [w._version for w in params[:5]]
+        if self._packed is None or self._packed.device != device:
+            self._packed = A._aligned_empty(lib.sg_d64_train_packed_bytes(), device)
+            self._packed_versions = None
+        if versions != self._packed_versions:
+            L.check(lib.sg_d64_train_pack(_ptr_array(params[:5]), L.P(self._packed.data_ptr()), A._stream()), "sg_d64_train_pack")
+            self._packed_versions = versions
+        return self._packed, versions
 
     def _running_stats(self):
         return [t for bn in self._bns for t in (bn.running_mean, bn.running_var)]

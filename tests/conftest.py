@@ -24,3 +24,10 @@ def golden2():
     """round-2 fixtures (tests/golden/make_golden_v2.py): in-batch block at B = 256 / 512, concat block + gradient"""
     path = os.path.join(ROOT, "tests", "golden", "golden_v2.npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def golden3():
+    """training-step fixture (tests/golden/make_golden_v3.py): the reference Discriminator through the literal D step / G step"""
+    path = os.path.join(ROOT, "tests", "golden", "golden_v3.npz")
+    return dict(np.load(path, allow_pickle=False))

@@ -200,3 +200,29 @@ def test_dbscan1d_restatement_vs_sklearn():
         assert np.array_equal(want, got), (n, eps, ms, want.sum(), got.sum())
     v = np.round(O.synth_losses(3000, seed=3), 2)  # heavy ties, distances exactly == eps
     assert np.array_equal(O.dbscan1d_noise_sklearn(v, 0.01, 3), O.dbscan1d_noise(v, 0.01, 3))
+
+
+def test_train_step_restatement_vs_reference_golden(golden3):
+    """O.train_step_through_d == the reference Discriminator driven through the literal D step / G step
+    ("#strainer gan.py:586-615", fixture tests/golden/make_golden_v3.py), CPU fp32."""
+    g = golden3
+    B = g["g10_out_real"].shape[0]
+    real = torch.from_numpy(O.synth_images(2000, B))
+    fake = torch.tanh(torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(4321)))
+    netD = O.make_discriminator(O.SEED).train()
+    r = O.train_step_through_d(netD, real, fake)
+    for k in ("out_real", "out_fake", "out_g"):
+        assert np.allclose(r[k].numpy(), g["g10_" + k], rtol=1e-5, atol=1e-7), k
+    assert abs(float(r["errD"]) - float(g["g10_errD"])) <= 1e-5 and abs(float(r["errG"]) - float(g["g10_errG"])) <= 1e-5
+    for n, gr in zip(O.D64_PARAM_NAMES, r["d_grads"]):
+        want = g[f"g10_d_{n}_sample"]
+        got = (gr.reshape(-1)[::61] if gr.numel() > 4096 else gr.reshape(-1)).numpy()
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max(), n
+        assert abs(float(gr.double().norm()) - float(g[f"g10_d_{n}_norm"])) <= 1e-4 * float(g[f"g10_d_{n}_norm"]), n
+    want = g["g10_dfake_sample"]
+    assert np.abs(r["dfake"][:, :, ::8, ::8].numpy() - want).max() <= 1e-4 * np.abs(want).max()
+    bns = [m for m in netD.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for i, bn in enumerate(bns):
+        assert np.allclose(bn.running_mean.numpy(), g[f"g10_bn{i + 2}_mean"], rtol=1e-5, atol=1e-7)
+        assert np.allclose(bn.running_var.numpy(), g[f"g10_bn{i + 2}_var"], rtol=1e-5, atol=1e-7)
+    assert int(bns[0].num_batches_tracked) == int(g["g10_nbt"]) == 3

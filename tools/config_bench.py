@@ -67,7 +67,9 @@ class Generator(nn.Module):
 def train_iters(dev, iters, mode):
     """One DCGAN iteration of "# 상위 10% 제거해서 fake image에 concate.py:236-300" at B = 128:
     strain block -> D step on (filtered real, fake + strained) -> G step.  mode: 'none' (plain DCGAN,
-    "#%basic.py:233-305"), 'torch' (the reference's eager strain block on the GPU), 'b200' (this repo)."""
+    "#%basic.py:233-305"), 'torch' (the reference's eager strain block on the GPU), 'b200' (this repo's strain block),
+    'b200_train' (strain block + the discriminator's forward / backward of the D and G steps on this repo's kernels,
+    sb.accelerate_discriminator), 'none_train' (plain DCGAN with the accelerated discriminator)."""
     torch.manual_seed(999)
     B, nz = 128, 100
     netD = O.make_discriminator(O.SEED).to(dev).train()
@@ -78,11 +80,14 @@ def train_iters(dev, iters, mode):
     crit = nn.BCELoss()
     data = sb.synth_images(0, B * 8, O.SEED, dev)
     state = {"i": 0}
+    accel = mode in ("b200_train", "none_train")
+    D = sb.accelerate_discriminator(netD, max_batch=B) if accel else netD
+    kw = {"param_grads": False} if accel else {}
 
     def step():
         real = data[(state["i"] % 8) * B:(state["i"] % 8 + 1) * B]
         state["i"] += 1
-        if mode == "none":
+        if mode in ("none", "none_train"):
             freal, ffake = real, real[:0]
         elif mode == "torch":
             with torch.no_grad():
@@ -93,22 +98,22 @@ def train_iters(dev, iters, mode):
         else:
             freal, ffake, _, _ = sb.strain_batch(netD, real, 0.1)          # library defaults
         netD.zero_grad()
-        out = netD(freal).view(-1)
+        out = D(freal).view(-1)
         errD_real = crit(out, torch.ones_like(out))
         errD_real.backward()
         noise = torch.randn(freal.shape[0], nz, 1, 1, device=dev)
         fake = netG(noise)
         # ":268": fake = cat([fake, filtered_fake]); D sees fake.detach(), the G step the concatenated batch itself
-        if mode == "b200":
+        if mode in ("b200", "b200_train"):
             fake = sb.concat_fake(fake, ffake)
         elif mode == "torch":
             fake = torch.cat([fake, ffake], dim=0)
-        out = netD(fake.detach()).view(-1)
+        out = D(fake.detach()).view(-1)
         errD_fake = crit(out, torch.zeros_like(out))
         errD_fake.backward()
         optD.step()
         netG.zero_grad()
-        out = netD(fake).view(-1)
+        out = D(fake, **kw).view(-1)      # the G step discards D's parameter gradients (next netD.zero_grad())
         errG = crit(out, torch.ones_like(out))
         errG.backward()
         optG.step()
@@ -245,10 +250,14 @@ def main():
 
     # ---- second headline metric: DCGAN 64x64 train iters/sec, batch 128 --------------------------------------
     out["train_iters_per_sec"] = {
-        "batch": 128, "note": "G/D forward+backward+Adam = torch autograd (cuDNN) in all arms; only the strain block differs",
+        "batch": 128,
+        "note": "generator forward/backward and Adam = torch autograd (cuDNN) in all arms; *_d_on_tcgen05 arms run the "
+                "discriminator's forward + backward (D step and G step) on this repo's kernels (sb.accelerate_discriminator)",
         "plain_dcgan_no_strain": train_iters(dev, a.iters, "none"),
         "reference_eager_strain_block_on_gpu": train_iters(dev, a.iters, "torch"),
         "b200_strain_batch_concat_fake": train_iters(dev, a.iters, "b200"),
+        "plain_dcgan_d_on_tcgen05": train_iters(dev, a.iters, "none_train"),
+        "b200_strain_and_d_on_tcgen05": train_iters(dev, a.iters, "b200_train"),
     }
     print(json.dumps(out))
 

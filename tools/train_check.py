@@ -83,7 +83,8 @@ def main():
     stats = wrapped._running_stats()
     prob = torch.empty(B, device=dev)
     logit = torch.empty(B, device=dev)
-    L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), B, B, T._ptr_array(params), T._ptr_array(stats), 0.1, 1e-5,
+    packed, _ = wrapped._packed_for(dev, lib, params)
+    L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), B, B, L.P(packed.data_ptr()), T._ptr_array(params[5:]), T._ptr_array(stats), 0.1, 1e-5,
                                      L.P(ws.buf.data_ptr()), L.P(prob.data_ptr()), L.P(logit.data_ptr()), A._stream()), "fwd")
     torch.cuda.synchronize()
 
@@ -110,7 +111,7 @@ def main():
     gprob = (-(target / pr.detach()) / B).contiguous()      # d BCE(mean) / d prob for target 1
     grads = [torch.zeros_like(p) for p in params]
     gx = torch.zeros_like(x)
-    L.check(lib.sg_d64_train_backward(L.P(gprob.data_ptr()), B, B, L.P(ws.buf.data_ptr()), T._ptr_array(grads), L.P(gx.data_ptr()),
+    L.check(lib.sg_d64_train_backward(L.P(gprob.data_ptr()), B, B, L.P(packed.data_ptr()), L.P(ws.buf.data_ptr()), T._ptr_array(grads), L.P(gx.data_ptr()),
                                       A._stream()), "bwd")
     torch.cuda.synchronize()
     rc = lib.sg_d64_train_check(L.P(ws.buf.data_ptr()), A._stream())
