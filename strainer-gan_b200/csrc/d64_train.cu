@@ -33,7 +33,7 @@ constexpr int kNonFiniteMagic = 0x4E614E21;   // status word 1: a non-finite log
 constexpr int kStageBytes = 32768;            // A 128 x 64 fp16 | B 128 x 64 fp16
 constexpr int kStages = 6;
 constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
-constexpr int kBnBlocks = 296;
+constexpr int kBnBlocks = 148;
 constexpr float kSlope = 0.2f;
 
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
@@ -662,15 +662,21 @@ __global__ void __launch_bounds__(256) head_bwd_dx_kernel(const float* __restric
   }
 }
 
-// dw5 [1][512][4][4] = sum_b dlogit[b] * act4[b][p][c]
+// dw5 [1][512][4][4] = sum_b dlogit[b] * act4[b][p][c]: 64 columns x 4 batch slices per block, fixed-order slice sum
 __global__ void __launch_bounds__(256) head_bwd_dw_kernel(const float* __restrict__ dlogit, const __half* __restrict__ act4, int64_t batch,
                                                           float* __restrict__ dw5, int* __restrict__ status) {
-  const int t = blockIdx.x * 256 + threadIdx.x;   // p*512 + c
-  if (t >= 8192) return;
+  __shared__ float red[4][64];
+  const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int t = blockIdx.x * 64 + col;   // p*512 + c
   float acc = 0.f;
-  for (int64_t b = 0; b < batch; ++b) acc = fmaf(dlogit[b], __half2float(act4[b * 8192 + t]), acc);
-  if (!(fabsf(acc) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
-  dw5[(t & 511) * 16 + (t >> 9)] = acc;
+  for (int64_t b = slice; b < batch; b += 4) acc = fmaf(dlogit[b], __half2float(act4[b * 8192 + t]), acc);
+  red[slice][col] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    acc = (red[0][col] + red[1][col]) + (red[2][col] + red[3][col]);
+    if (!(fabsf(acc) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
+    dw5[(t & 511) * 16 + (t >> 9)] = acc;
+  }
 }
 
 // dW [Cout][Cin][4][4] = (1 / scale) * sum_splits partial[s][co][tap * cstride + ci].  One block per (co, 16 input channels):
@@ -686,7 +692,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   float acc = 0.f;
   if (ci0 + cil < cin) {
     const float* src = partial + (size_t)co * ldn + tap * cstride + ci0 + cil;
-    for (int s = 0; s < splits; ++s) acc += src[(size_t)s * cout * ldn];
+    const size_t step = (size_t)cout * ldn;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {          // fixed association: deterministic
+      a0 += src[(size_t)s * step]; a1 += src[(size_t)(s + 1) * step]; a2 += src[(size_t)(s + 2) * step]; a3 += src[(size_t)(s + 3) * step];
+    }
+    for (; s < splits; ++s) a0 += src[(size_t)s * step];
+    acc = (a0 + a1) + (a2 + a3);
   }
   acc *= scal[1];
   if (!(fabsf(acc) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
@@ -955,7 +968,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
   head_bwd_dx_kernel<<<ew_blocks(batch * 1024), 256, 0, st>>>(dlogit, w5p, scal, batch, h16(L.dx[2]));
   SG_LAUNCH_CHECK();
   if (want_w) {
-    head_bwd_dw_kernel<<<32, 256, 0, st>>>(dlogit, h16(L.act4n), batch, h_grads[4], status);
+    head_bwd_dw_kernel<<<128, 256, 0, st>>>(dlogit, h16(L.act4n), batch, h_grads[4], status);
     SG_LAUNCH_CHECK();
   }
 
