@@ -172,7 +172,7 @@ def test_concat_fake_literal_block(sb, golden2):
     crit(d(fake_ref).view(-1), label_g).backward()
     # the two backward passes run the same cuDNN dgrad kernels on identical data, but those kernels are not
     # bit-reproducible run to run (split-K atomics): compare closely here, exactly on an injected gradient below
-    assert torch.allclose(gz.grad, gz_ref.grad, rtol=1e-4, atol=1e-10)
+    assert float((gz.grad - gz_ref.grad).norm()) <= 1e-3 * float(gz_ref.grad.norm())
     gz3 = gz_host.cuda().requires_grad_(True)
     up = torch.randn(B, 3, 64, 64, device="cuda")
     sb.concat_fake(gz3, filtered_fake).backward(up)
