@@ -56,6 +56,13 @@ struct TrGemm {
   int* err;
 };
 
+// Programmatic dependent launch: every kernel of this file is launched with programmatic stream serialisation, lets its
+// successor become resident at once (launch_dependents) and waits for its predecessor's completion (and memory flush)
+// before it touches global memory -- the ~40 launches of a forward + backward pass overlap their prologues (barrier
+// init, TMEM allocation, descriptor prefetch) with the tail of the kernel before.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct Unit { int cls, mt, nt, split, ks0, ks1; };
 __device__ __forceinline__ Unit decode_unit(const TrGemm& p, int u) {
   Unit w;
@@ -103,11 +110,13 @@ trgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     *s_abort = 0;
     fence_barrier_init();
   }
+  pdl_launch_dependents();
   if (warp == 2) tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -308,6 +317,8 @@ struct PackArgs {
   float* w5p;
 };
 __global__ void __launch_bounds__(256) pack_train_kernel(const PackArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pairs2 = 128 * 64, pairs3 = 256 * 128, pairs4 = 512 * 256, pairs = pairs2 + pairs3 + pairs4;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * pairs + 4096 + 8192; i += gridDim.x * 256) {
     if (i < 2 * pairs) {
@@ -347,6 +358,8 @@ __global__ void __launch_bounds__(256) pack_train_kernel(const PackArgs a) {
 
 // ---- layer 1 operand: x fp32 NCHW [B][3][64][64] -> im2col rows [B*1024][64] fp16, k = (kh*4 + kw)*4 + c -------------
 __global__ void __launch_bounds__(256) im2col1_kernel(const float* __restrict__ x, int64_t batch, __half* __restrict__ col) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = batch * 1024 * 4;
   for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
     const int kh = (int)(t & 3);
@@ -376,6 +389,8 @@ __global__ void __launch_bounds__(256) im2col1_kernel(const float* __restrict__ 
 // dx fp32 NCHW = (1 / scale) * col2im(dcol [B*1024][64]): the 2 x 2 taps that touch each input pixel
 __global__ void __launch_bounds__(256) col2im1_kernel(const __half* __restrict__ dcol, int64_t batch, const float* __restrict__ scal,
                                                       float* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float inv = scal[1];
   const int64_t total = batch * 4096;
   for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
@@ -432,6 +447,8 @@ template <bool BWD>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict__ raw, const __half* __restrict__ dx,
                                                         const float* __restrict__ ss, int64_t rows, int C,
                                                         float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[256][17];
   const int tpr = C >> 3, rpp = 256 / tpr;
   const int cg = threadIdx.x % tpr, rl = threadIdx.x / tpr;
@@ -485,6 +502,8 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, float momentum, float* __restrict__ run_mean,
                                                               float* __restrict__ run_var, float* __restrict__ ss) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ch >= C) return;
   double s, q;
@@ -510,6 +529,8 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __res
 // y = LeakyReLU(raw * scale + shift) -> interior of the zero-bordered [B][S+2][S+2][C] tensor (pad = 1) or plain rows (pad = 0)
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ ss, int64_t rows, int C,
                                                        int s_log2, int pad, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = C >> 3;
   const int64_t total = rows * tpr;
   const int S = 1 << s_log2;
@@ -537,6 +558,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
                                                               const float* __restrict__ ss, const float* __restrict__ scal,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               float* __restrict__ coef, int* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ch >= C) return;
   double s1, s2;
@@ -556,6 +579,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restrict__ raw, const __half* __restrict__ dx,
                                                            const float* __restrict__ ss, const float* __restrict__ coef, int64_t rows,
                                                            int C, int s_log2, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tpr = C >> 3;
   const int64_t total = rows * tpr;
   const int S = 1 << s_log2;
@@ -585,6 +610,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __half* __restrict__ act4, int64_t batch, const float* __restrict__ w5p,
                                                        float* __restrict__ logit, float* __restrict__ prob_ws, float* __restrict__ prob,
                                                        int* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   const int64_t b = blockIdx.x;
   const __half* a = act4 + b * 8192;
@@ -614,6 +641,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __half* __restrict_
 __global__ void __launch_bounds__(1024) head_bwd_prep_kernel(const float* __restrict__ gout, const float* __restrict__ prob, int64_t batch,
                                                              const float* __restrict__ w5p, float* __restrict__ dlogit,
                                                              float* __restrict__ scal) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][32];
   float m1 = 0.f, m2 = 0.f;
   for (int64_t b = threadIdx.x; b < batch; b += 1024) {
@@ -649,6 +678,8 @@ __global__ void __launch_bounds__(1024) head_bwd_prep_kernel(const float* __rest
 // dX4 [B*16][512] = fp16(scale * dlogit[b] * w5[p][c])
 __global__ void __launch_bounds__(256) head_bwd_dx_kernel(const float* __restrict__ dlogit, const float* __restrict__ w5p,
                                                           const float* __restrict__ scal, int64_t batch, __half* __restrict__ dx4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float s = scal[0];
   const int64_t total = batch * 1024;
   for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
@@ -665,6 +696,8 @@ __global__ void __launch_bounds__(256) head_bwd_dx_kernel(const float* __restric
 // dw5 [1][512][4][4] = sum_b dlogit[b] * act4[b][p][c]: 64 columns x 4 batch slices per block, fixed-order slice sum
 __global__ void __launch_bounds__(256) head_bwd_dw_kernel(const float* __restrict__ dlogit, const __half* __restrict__ act4, int64_t batch,
                                                           float* __restrict__ dw5, int* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[4][64];
   const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
   const int t = blockIdx.x * 64 + col;   // p*512 + c
@@ -685,6 +718,8 @@ __global__ void __launch_bounds__(256) head_bwd_dw_kernel(const float* __restric
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int cout, int cin, int cstride,
                                                            int ldn, const float* __restrict__ scal, float* __restrict__ dw,
                                                            int* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[16][17];
   const int groups = (cin + 15) >> 4;
   const int co = blockIdx.x / groups, ci0 = (blockIdx.x - co * groups) * 16;
@@ -806,13 +841,33 @@ static void row_box(int S, int rows, TrGemm* p, int64_t batch, int* tiles) {
   p->ohb_log2 = ilog2(p->ohb);
 }
 
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  count_launch();
+  return SG_OK;
+}
+#define SG_PDL(...)                              \
+  do {                                           \
+    const int _pr = launch_pdl(__VA_ARGS__);     \
+    if (_pr != SG_OK) return _pr;                \
+  } while (0)
+
 template <int MODE>
 static int launch_trgemm(const CUtensorMap& ta, const CUtensorMap& tb, const TrGemm& p, cudaStream_t st) {
   const int64_t total = (int64_t)p.classes * p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < state().sm_count ? total : state().sm_count);
-  trgemm_kernel<MODE><<<grid, 192, kSmemBytes, st>>>(ta, tb, p);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
+  return launch_pdl(trgemm_kernel<MODE>, (unsigned)grid, 192u, (size_t)kSmemBytes, st, ta, tb, p);
 }
 
 static int ew_blocks(int64_t threads) {
@@ -866,8 +921,7 @@ int sg_d64_train_pack(const float* const* h_weights, void* packed, void* stream)
   pa.wd1 = reinterpret_cast<__half*>(pk + PL.wd1);
   for (int l = 0; l < 3; ++l) { pa.wf[l] = reinterpret_cast<__half*>(pk + PL.wf[l]); pa.wd[l] = reinterpret_cast<__half*>(pk + PL.wd[l]); }
   pa.w5p = reinterpret_cast<float*>(pk + PL.w5p);
-  pack_train_kernel<<<sg::state().sm_count * 4, 256, 0, sg::as_stream(stream)>>>(pa);
-  SG_LAUNCH_CHECK();
+  SG_PDL(pack_train_kernel, (unsigned)(sg::state().sm_count * 4), 256u, (size_t)0, sg::as_stream(stream), pa);
   return SG_OK;
 }
 
@@ -889,8 +943,7 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
   auto h16 = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
   auto p16 = [&](size_t off) { return reinterpret_cast<const __half*>(pk + off); };
 
-  im2col1_kernel<<<ew_blocks(batch * 4096), 256, 0, st>>>(x, batch, h16(L.col1));
-  SG_LAUNCH_CHECK();
+  SG_PDL(im2col1_kernel, (unsigned)(ew_blocks(batch * 4096)), 256u, (size_t)0, st, x, batch, h16(L.col1));
 
   CUtensorMap ta, tb;
   int r;
@@ -921,20 +974,14 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
     const int rpp = 256 / (cout / 8);
     int blocks = (int)sg::ceil_div(rows, rpp * 4);
     if (blocks > kBnBlocks) blocks = kBnBlocks;
-    bn_reduce_kernel<false><<<blocks, 256, 0, st>>>(h16(L.raw[l]), nullptr, nullptr, rows, cout, part);
-    SG_LAUNCH_CHECK();
+    SG_PDL(bn_reduce_kernel<false>, (unsigned)(blocks), 256u, (size_t)0, st, h16(L.raw[l]), nullptr, nullptr, rows, cout, part);
     float* rm = h_running_stats ? h_running_stats[2 * l] : nullptr;
     float* rv = h_running_stats ? h_running_stats[2 * l + 1] : nullptr;
-    bn_fwd_finalize_kernel<<<(cout + 7) / 8, 256, 0, st>>>(part, blocks, rows, cout, h_bn_params[2 * l], h_bn_params[2 * l + 1], bn_eps,
-                                                               momentum, rm, rv, ss);
-    SG_LAUNCH_CHECK();
+    SG_PDL(bn_fwd_finalize_kernel, (unsigned)((cout + 7) / 8), 256u, (size_t)0, st, part, blocks, rows, cout, h_bn_params[2 * l], h_bn_params[2 * l + 1], bn_eps, momentum, rm, rv, ss);
     __half* out = (l < 2) ? h16(L.actp[l]) : h16(L.act4n);
-    bn_apply_kernel<<<ew_blocks(rows * (cout / 8)), 256, 0, st>>>(h16(L.raw[l]), ss, rows, cout, ilog2(S), l < 2 ? 1 : 0, out);
-    SG_LAUNCH_CHECK();
+    SG_PDL(bn_apply_kernel, (unsigned)(ew_blocks(rows * (cout / 8))), 256u, (size_t)0, st, h16(L.raw[l]), ss, rows, cout, ilog2(S), l < 2 ? 1 : 0, out);
   }
-  head_fwd_kernel<<<(unsigned)batch, 256, 0, st>>>(h16(L.act4n), batch, reinterpret_cast<const float*>(pk + PL.w5p), logit,
-                                                                    reinterpret_cast<float*>(ws + L.prob), prob, status);
-  SG_LAUNCH_CHECK();
+  SG_PDL(head_fwd_kernel, (unsigned)((unsigned)batch), 256u, (size_t)0, st, h16(L.act4n), batch, reinterpret_cast<const float*>(pk + PL.w5p), logit, reinterpret_cast<float*>(ws + L.prob), prob, status);
   return SG_OK;
 }
 
@@ -963,13 +1010,10 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
   CUtensorMap ta, tb;
   int r;
 
-  head_bwd_prep_kernel<<<1, 1024, 0, st>>>(grad_prob, reinterpret_cast<const float*>(ws + L.prob), batch, w5p, dlogit, scal);
-  SG_LAUNCH_CHECK();
-  head_bwd_dx_kernel<<<ew_blocks(batch * 1024), 256, 0, st>>>(dlogit, w5p, scal, batch, h16(L.dx[2]));
-  SG_LAUNCH_CHECK();
+  SG_PDL(head_bwd_prep_kernel, (unsigned)(1), 1024u, (size_t)0, st, grad_prob, reinterpret_cast<const float*>(ws + L.prob), batch, w5p, dlogit, scal);
+  SG_PDL(head_bwd_dx_kernel, (unsigned)(ew_blocks(batch * 1024)), 256u, (size_t)0, st, dlogit, w5p, scal, batch, h16(L.dx[2]));
   if (want_w) {
-    head_bwd_dw_kernel<<<128, 256, 0, st>>>(dlogit, h16(L.act4n), batch, h_grads[4], status);
-    SG_LAUNCH_CHECK();
+    SG_PDL(head_bwd_dw_kernel, (unsigned)(128), 256u, (size_t)0, st, dlogit, h16(L.act4n), batch, h_grads[4], status);
   }
 
   auto splits_for = [&](int tiles, int k_steps, int* kps) {
@@ -989,14 +1033,9 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     const int rpp = 256 / (cout / 8);
     int blocks = (int)sg::ceil_div(rows, rpp * 4);
     if (blocks > kBnBlocks) blocks = kBnBlocks;
-    bn_reduce_kernel<true><<<blocks, 256, 0, st>>>(h16(L.raw[l]), h16(L.dx[l]), ss, rows, cout, part);
-    SG_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<(cout + 7) / 8, 256, 0, st>>>(part, blocks, rows, cout, ss, scal, want_w ? h_grads[5 + 2 * l] : nullptr,
-                                                               want_w ? h_grads[6 + 2 * l] : nullptr, coef, status);
-    SG_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<ew_blocks(rows * (cout / 8)), 256, 0, st>>>(h16(L.raw[l]), h16(L.dx[l]), ss, coef, rows, cout, ilog2(S),
-                                                                      h16(L.dyp[l]));
-    SG_LAUNCH_CHECK();
+    SG_PDL(bn_reduce_kernel<true>, (unsigned)(blocks), 256u, (size_t)0, st, h16(L.raw[l]), h16(L.dx[l]), ss, rows, cout, part);
+    SG_PDL(bn_bwd_finalize_kernel, (unsigned)((cout + 7) / 8), 256u, (size_t)0, st, part, blocks, rows, cout, ss, scal, want_w ? h_grads[5 + 2 * l] : nullptr, want_w ? h_grads[6 + 2 * l] : nullptr, coef, status);
+    SG_PDL(bn_bwd_apply_kernel, (unsigned)(ew_blocks(rows * (cout / 8))), 256u, (size_t)0, st, h16(L.raw[l]), h16(L.dx[l]), ss, coef, rows, cout, ilog2(S), h16(L.dyp[l]));
     const void* in = (l == 0) ? h16(L.act1p) : h16(L.actp[l - 1]);
     if (want_w) {   // dW_l [cout][16 cin] = dY^T . im2col(act_{l-1}), split-K over the pixels
       TrGemm p{};
@@ -1007,8 +1046,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
       if ((r = encode_dy_map(&ta, h16(L.dyp[l]), batch, S, cout, p.ow, p.ohb, p.bb)) != SG_OK) return r;
       if ((r = encode_act_map(&tb, in, batch, 2 * S, cin, p.ow, p.ohb, p.bb)) != SG_OK) return r;
       if ((r = launch_trgemm<MODE_WGRAD>(ta, tb, p, st)) != SG_OK) return r;
-      wgrad_reduce_kernel<<<cout * (cin / 16), 256, 0, st>>>(partial, p.splits, cout, cin, cin, 16 * cin, scal, h_grads[l + 1], status);
-      SG_LAUNCH_CHECK();
+      SG_PDL(wgrad_reduce_kernel, (unsigned)(cout * (cin / 16)), 256u, (size_t)0, st, partial, p.splits, cout, cin, cin, 16 * cin, scal, h_grads[l + 1], status);
     }
     {   // dX_{l-1}: one GEMM per input-pixel parity class; layer 2's also applies layer 1's LeakyReLU gate -> dY1
       TrGemm p{};
@@ -1032,8 +1070,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     if ((r = encode_mat_map(&ta, h16(L.dy1), 64, batch * 1024, 64)) != SG_OK) return r;
     if ((r = encode_mat_map(&tb, h16(L.col1), 64, batch * 1024, 64)) != SG_OK) return r;
     if ((r = launch_trgemm<MODE_WGRAD>(ta, tb, p, st)) != SG_OK) return r;
-    wgrad_reduce_kernel<<<64, 256, 0, st>>>(partial, p.splits, 64, 3, 4, 64, scal, h_grads[0], status);
-    SG_LAUNCH_CHECK();
+    SG_PDL(wgrad_reduce_kernel, (unsigned)(64), 256u, (size_t)0, st, partial, p.splits, 64, 3, 4, 64, scal, h_grads[0], status);
   }
   if (grad_x) {   // dcol [B*1024][64] = dY1 . W1, then the col2im gather
     TrGemm p{};
@@ -1043,8 +1080,7 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     if ((r = encode_mat_map(&ta, h16(L.dy1), 64, batch * 1024, 128)) != SG_OK) return r;
     if ((r = encode_mat_map(&tb, p16(PL.wd1), 64, 64, 128)) != SG_OK) return r;
     if ((r = launch_trgemm<MODE_DGRAD>(ta, tb, p, st)) != SG_OK) return r;
-    col2im1_kernel<<<ew_blocks(batch * 4096), 256, 0, st>>>(h16(L.dcol1), batch, scal, grad_x);
-    SG_LAUNCH_CHECK();
+    SG_PDL(col2im1_kernel, (unsigned)(ew_blocks(batch * 4096)), 256u, (size_t)0, st, h16(L.dcol1), batch, scal, grad_x);
   }
   return SG_OK;
 }

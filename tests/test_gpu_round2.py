@@ -177,7 +177,10 @@ def test_concat_fake_literal_block(sb, golden2):
     up = torch.randn(B, 3, 64, 64, device="cuda")
     sb.concat_fake(gz3, filtered_fake).backward(up)
     assert torch.equal(gz3.grad, up[:B - b_size_fake])      # bit-identical to autograd through torch.cat: grad[:B-s]
-    assert np.allclose(gz.grad[:, :, ::16, ::16].cpu().numpy(), golden2["g9_grad_sample"], rtol=2e-2, atol=1e-9)
+    # against the reference's CPU fp32 gradient: D's backward here is torch autograd on the GPU (TF32 convolutions by
+    # default), so the bar is on the vector, not per element
+    got, want = gz.grad[:, :, ::16, ::16].cpu().numpy().astype(np.float64), golden2["g9_grad_sample"].astype(np.float64)
+    assert np.linalg.norm(got - want) <= 2e-2 * np.linalg.norm(want)
     assert abs(errG.item() - float(golden2["g9_errG"])) <= 1e-3 * abs(float(golden2["g9_errG"]))
     # a strained tensor that is NOT the pre-placed tail goes through the same kernel into a fresh buffer
     other = torch.randn(5, 3, 64, 64, device="cuda")
