@@ -146,7 +146,8 @@ int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, 
  * backward pass needs, so one workspace serves one forward -> backward pair at a time.
  * h_bn_params: HOST array of 6 DEVICE pointers {bn2 gamma, bn2 beta, bn3 gamma, bn3 beta, bn4 gamma, bn4 beta};
  * h_running_stats: HOST array of 6 DEVICE pointers {bn2 mean, bn2 var, ...} updated in place as nn.BatchNorm2d does in
- * training mode (NULL: no update).  x fp32 NCHW [batch,3,64,64], 2 <= batch <= max_batch.
+ * training mode (NULL: no update); they are committed at the end of the forward only if every logit of the batch is finite
+ * (an fp16 overflow leaves them untouched, so that the caller can score the batch again in another arithmetic).  x fp32 NCHW [batch,3,64,64], 2 <= batch <= max_batch.
  * forward writes prob[batch] = sigmoid(logit) and logit[batch] (either may be NULL).
  * backward takes grad_prob[batch] = dL/dprob and writes h_grads (HOST array of 11 DEVICE pointers {dconv1..dconv5 weight,
  * dgamma2, dbeta2, dgamma3, dbeta3, dgamma4, dbeta4} in PyTorch layouts; NULL skips every parameter gradient, as the G

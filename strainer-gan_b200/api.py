@@ -1775,6 +1775,14 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
     sc = get_scorer(netD, device, conv_mode, max_batch=max(b, 512))
     x = real.contiguous()
     train = netD.training
+    # train-mode BatchNorm in the fp16 class: the training step's forward (csrc/d64_train.cu: one C call, programmatic
+    # dependent launches, weights packed once per optimiser step and shared with the D step that follows)
+    trainer = None
+    if train and sc.mode_name in ("auto", "fp16") and 2 <= b <= 4096 and x.dtype == torch.float32 and x.is_cuda and \
+            all(t.device == x.device and t.is_contiguous() and (t.dtype == torch.float32 or t.dtype == torch.int64)
+                for t in list(netD.parameters()) + list(netD.buffers())):      # a module living elsewhere: the scorer copies
+        from .train import trainer_for
+        trainer = trainer_for(netD, max(b, 128))
 
     def run(scorer, status):
         if train:
@@ -1783,12 +1791,24 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
             scorer.score_into(x, None, prob, None, status)
         return strain_scores(real, prob, q, _extra_status=status)
 
-    status = torch.zeros(2, dtype=torch.int32, device=device)
-    out = run(sc, status)
+    if trainer is not None:
+        status = trainer.score_train(x, prob)
+        out = strain_scores(real, prob, q, _extra_status=status)
+    else:
+        status = torch.zeros(2, dtype=torch.int32, device=device)
+        out = run(sc, status)
     st0, st1 = _last_status(device)
     if st0:
+        if trainer is not None:
+            status.zero_()
         _raise_status(st0)
+    if trainer is not None and st1 != _FP16_OVERFLOW:
+        trainer.committed()
+        return out
     if st1 == _FP16_OVERFLOW:
+        if trainer is not None:
+            status.zero_()      # sticky words of the training workspace: reported here
+            status = torch.zeros(2, dtype=torch.int32, device=device)
         if sc.mode_name != "auto":
             raise RuntimeError("strainer_b200: non-finite logit in the fp16 conv mode (an activation exceeded 65504); use "
                                "conv_mode='auto', 'fp32' or 'bf16'")

@@ -29,7 +29,7 @@ namespace dtr {
 using namespace ptx;
 
 constexpr int kErrBase = 80;
-constexpr int kNonFiniteMagic = 0x4E614E21;   // status word 1: a non-finite logit or gradient
+constexpr int kNonFiniteMagic = 0x46503136;   // status word 1: a non-finite logit or gradient (the value csrc/d64.cu's head uses)
 constexpr int kStageBytes = 32768;            // A 128 x 64 fp16 | B 128 x 64 fp16
 constexpr int kStages = 6;
 constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
@@ -37,7 +37,7 @@ constexpr int kBnBlocks = 148;
 constexpr float kSlope = 0.2f;
 
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
-enum { EPI_RAW16 = 0, EPI_L1PAD = 1, EPI_SCATTER = 2, EPI_F32 = 3 };
+enum { EPI_RAW16 = 0, EPI_L1PAD = 1, EPI_SCATTER = 2, EPI_F32 = 3 };   // EPI_F32 with splits == 1 also stores the raw conv output
 
 struct TrGemm {
   int epi;
@@ -357,9 +357,11 @@ __global__ void __launch_bounds__(256) pack_train_kernel(const PackArgs a) {
 }
 
 // ---- layer 1 operand: x fp32 NCHW [B][3][64][64] -> im2col rows [B*1024][64] fp16, k = (kh*4 + kw)*4 + c -------------
-__global__ void __launch_bounds__(256) im2col1_kernel(const float* __restrict__ x, int64_t batch, __half* __restrict__ col) {
+__global__ void __launch_bounds__(256) im2col1_kernel(const float* __restrict__ x, int64_t batch, __half* __restrict__ col,
+                                                      int* __restrict__ status) {
   pdl_launch_dependents();
   pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) status[2] = 0;      // this call's non-finite flag (read by bn_commit_kernel)
   const int64_t total = batch * 1024 * 4;
   for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
     const int kh = (int)(t & 3);
@@ -444,7 +446,7 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
 // column sums over rows: forward (sum x, sum x^2) or backward (sum g, sum g * xhat with g = dx * LeakyReLU'(x*scale + shift));
 // partial [gridDim.x][2][C], fixed order -> deterministic
 template <bool BWD>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict__ raw, const __half* __restrict__ dx,
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict__ raw, const __half* __restrict__ dx,
                                                         const float* __restrict__ ss, int64_t rows, int C,
                                                         float* __restrict__ partial) {
   pdl_launch_dependents();
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __half* __restrict
   }
   for (int64_t r = (int64_t)blockIdx.x * rpp + rl; r < rows; r += (int64_t)gridDim.x * rpp) {
     float x[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw + r * C) + cg), x);
+    load8(raw + r * C + cg * 8, x);
     if (!BWD) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
@@ -500,8 +502,9 @@ __device__ __forceinline__ void warp_partial_sums(const float* __restrict__ part
 
 __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, int blocks, int64_t rows, int C,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              float eps, float momentum, float* __restrict__ run_mean,
-                                                              float* __restrict__ run_var, float* __restrict__ ss) {
+                                                              float eps, float momentum, const float* __restrict__ run_mean,
+                                                              const float* __restrict__ run_var, float* __restrict__ pend,
+                                                              float* __restrict__ ss) {
   pdl_launch_dependents();
   pdl_wait();
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -519,15 +522,27 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __res
   ss[1024 + ch] = (float)mean;
   ss[1536 + ch] = rstd;
   ss[2048 + ch] = g;
-  if (run_mean) run_mean[ch] = (1.f - momentum) * run_mean[ch] + momentum * (float)mean;
+  // the new running statistics are parked (pend_mean | pend_var) until the head has shown that the batch stayed finite
+  if (run_mean) pend[ch] = (1.f - momentum) * run_mean[ch] + momentum * (float)mean;
   if (run_var) {
     const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
-    run_var[ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unbiased;
+    pend[512 + ch] = (1.f - momentum) * run_var[ch] + momentum * (float)unbiased;
   }
 }
 
+// running_mean / running_var of the three BatchNorm layers become visible only if no logit of this batch was non-finite:
+// an overflowing batch (re-scored in split arithmetic by the caller) must update them exactly once
+struct CommitArgs { float* dst[6]; };
+__global__ void __launch_bounds__(512) bn_commit_kernel(const float* __restrict__ pending, const CommitArgs a, const int* __restrict__ status) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (status[2] != 0) return;      // word 2: this call's flag (word 1 is the sticky one sg_d64_train_check reports)
+  const int t = blockIdx.x, c = 128 << (t >> 1);
+  if (a.dst[t] && threadIdx.x < c) a.dst[t][threadIdx.x] = pending[t * 512 + threadIdx.x];
+}
+
 // y = LeakyReLU(raw * scale + shift) -> interior of the zero-bordered [B][S+2][S+2][C] tensor (pad = 1) or plain rows (pad = 0)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict__ raw, const float* __restrict__ ss, int64_t rows, int C,
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ raw, const float* __restrict__ ss, int64_t rows, int C,
                                                        int s_log2, int pad, __half* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
@@ -538,7 +553,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __half* __restrict_
     const int cg = (int)(t % tpr);
     const int64_t r = t / tpr;
     float x[8], sc[8], sh[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw + r * C) + cg), x);
+    load8(raw + r * C + cg * 8, x);
     load8(ss + cg * 8, sc);
     load8(ss + 512 + cg * 8, sh);
 #pragma unroll
@@ -576,7 +591,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 }
 
 // dconv = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)) -> interior of the zero-bordered dY tensor [B][S+2][S+2][C]
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restrict__ raw, const __half* __restrict__ dx,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ raw, const __half* __restrict__ dx,
                                                            const float* __restrict__ ss, const float* __restrict__ coef, int64_t rows,
                                                            int C, int s_log2, __half* __restrict__ out) {
   pdl_launch_dependents();
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __half* __restr
     const int cg = (int)(t % tpr);
     const int64_t r = t / tpr;
     float x[8], g[8], sc[8], sh[8], mu[8], rs[8], k0[8], m1[8], m2[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw + r * C) + cg), x);
+    load8(raw + r * C + cg * 8, x);
     unpack8(__ldg(reinterpret_cast<const uint4*>(dx + r * C) + cg), g);
     load8(ss + cg * 8, sc); load8(ss + 512 + cg * 8, sh); load8(ss + 1024 + cg * 8, mu); load8(ss + 1536 + cg * 8, rs);
     load8(coef + cg * 8, k0); load8(coef + 512 + cg * 8, m1); load8(coef + 1024 + cg * 8, m2);
@@ -629,7 +644,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __half* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     acc = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-    if (!(fabsf(acc) <= 3.0e38f)) atomicExch(status + 1, kNonFiniteMagic);
+    if (!(fabsf(acc) <= 3.0e38f)) { atomicExch(status + 1, kNonFiniteMagic); atomicExch(status + 2, 1); }
     const float pr = 1.0f / (1.0f + expf(-acc));
     if (logit) logit[b] = acc;
     prob_ws[b] = pr;
@@ -748,7 +763,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 struct PackedTrainLayout { size_t wf1, wd1, wf[3], wd[3], w5p, total; };
 struct TrainLayout {
   size_t status, scal;
-  size_t col1, act1p, raw[3], actp[2], act4n, ss, bnpart, prob, dlogit;
+  size_t col1, act1p, raw[3], actp[2], act4n, ss, bnpart, bnpend, prob, dlogit;
   size_t dx[3], dyp[3], dy1, dcol1, partial, coef;
   size_t zero_begin[6], zero_bytes[6];     // the zero-bordered tensors (cleared once by sg_d64_train_workspace_init)
   size_t total;
@@ -782,7 +797,7 @@ static TrainLayout train_layout(int64_t cap) {
   int z = 0;
   L.act1p = take(b * 34 * 34 * 64 * 2);
   L.zero_begin[z] = L.act1p; L.zero_bytes[z++] = b * 34 * 34 * 64 * 2;
-  for (int l = 0; l < 3; ++l) L.raw[l] = take(b * kS[l + 2] * kS[l + 2] * kC[l + 2] * 2);
+  for (int l = 0; l < 3; ++l) L.raw[l] = take(b * kS[l + 2] * kS[l + 2] * kC[l + 2] * 4);   // fp32: BatchNorm sees unrounded sums
   for (int l = 0; l < 2; ++l) {
     const size_t bytes = b * (kS[l + 2] + 2) * (kS[l + 2] + 2) * kC[l + 2] * 2;
     L.actp[l] = take(bytes);
@@ -791,6 +806,7 @@ static TrainLayout train_layout(int64_t cap) {
   L.act4n = take(b * 16 * 512 * 2);
   L.ss = take(3 * 5 * 512 * 4);
   L.bnpart = take((size_t)kBnBlocks * 2 * 512 * 4);
+  L.bnpend = take(6 * 512 * 4);
   L.prob = take(b * 4);
   L.dlogit = take(b * 4);
   for (int l = 0; l < 3; ++l) {
@@ -941,9 +957,10 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
   cudaStream_t st = sg::as_stream(stream);
   int* status = reinterpret_cast<int*>(ws + L.status);
   auto h16 = [&](size_t off) { return reinterpret_cast<__half*>(ws + off); };
+  auto f32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
   auto p16 = [&](size_t off) { return reinterpret_cast<const __half*>(pk + off); };
 
-  SG_PDL(im2col1_kernel, (unsigned)(ew_blocks(batch * 4096)), 256u, (size_t)0, st, x, batch, h16(L.col1));
+  SG_PDL(im2col1_kernel, (unsigned)(ew_blocks(batch * 4096)), 256u, (size_t)0, st, x, batch, h16(L.col1), status);
 
   CUtensorMap ta, tb;
   int r;
@@ -961,9 +978,9 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
     const int64_t rows = batch * S * S;
     const void* in = (l == 0) ? h16(L.act1p) : h16(L.actp[l - 1]);
     TrGemm p{};
-    p.epi = EPI_RAW16; p.classes = 1; p.n_tiles = cout / 128; p.k_steps = 16 * (cin / 64); p.splits = 1; p.kps = p.k_steps;
+    p.epi = EPI_F32; p.classes = 1; p.n_tiles = cout / 128; p.k_steps = 16 * (cin / 64); p.splits = 1; p.kps = p.k_steps;
     p.nchunk = cin / 64; p.cin = cin; p.batch = (int)batch; p.m_valid = (int)rows; p.n_valid = cout; p.ldo = cout;
-    p.out = h16(L.raw[l]); p.err = status;
+    p.out = f32(L.raw[l]); p.err = status;
     row_box(S, 128, &p, batch, &p.m_tiles);
     if ((r = encode_act_map(&ta, in, batch, 2 * S, cin, p.ow, p.ohb, p.bb)) != SG_OK) return r;
     if ((r = encode_mat_map(&tb, p16(PL.wf[l]), 16 * cin, cout, 128)) != SG_OK) return r;
@@ -974,14 +991,20 @@ int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const
     const int rpp = 256 / (cout / 8);
     int blocks = (int)sg::ceil_div(rows, rpp * 4);
     if (blocks > kBnBlocks) blocks = kBnBlocks;
-    SG_PDL(bn_reduce_kernel<false>, (unsigned)(blocks), 256u, (size_t)0, st, h16(L.raw[l]), nullptr, nullptr, rows, cout, part);
+    SG_PDL(bn_reduce_kernel<false>, (unsigned)(blocks), 256u, (size_t)0, st, f32(L.raw[l]), nullptr, nullptr, rows, cout, part);
     float* rm = h_running_stats ? h_running_stats[2 * l] : nullptr;
     float* rv = h_running_stats ? h_running_stats[2 * l + 1] : nullptr;
-    SG_PDL(bn_fwd_finalize_kernel, (unsigned)((cout + 7) / 8), 256u, (size_t)0, st, part, blocks, rows, cout, h_bn_params[2 * l], h_bn_params[2 * l + 1], bn_eps, momentum, rm, rv, ss);
+    SG_PDL(bn_fwd_finalize_kernel, (unsigned)((cout + 7) / 8), 256u, (size_t)0, st, part, blocks, rows, cout, h_bn_params[2 * l], h_bn_params[2 * l + 1], bn_eps, momentum, rm, rv,
+           reinterpret_cast<float*>(ws + L.bnpend) + (size_t)l * 1024, ss);
     __half* out = (l < 2) ? h16(L.actp[l]) : h16(L.act4n);
-    SG_PDL(bn_apply_kernel, (unsigned)(ew_blocks(rows * (cout / 8))), 256u, (size_t)0, st, h16(L.raw[l]), ss, rows, cout, ilog2(S), l < 2 ? 1 : 0, out);
+    SG_PDL(bn_apply_kernel, (unsigned)(ew_blocks(rows * (cout / 8))), 256u, (size_t)0, st, f32(L.raw[l]), ss, rows, cout, ilog2(S), l < 2 ? 1 : 0, out);
   }
   SG_PDL(head_fwd_kernel, (unsigned)((unsigned)batch), 256u, (size_t)0, st, h16(L.act4n), batch, reinterpret_cast<const float*>(pk + PL.w5p), logit, reinterpret_cast<float*>(ws + L.prob), prob, status);
+  if (h_running_stats) {
+    CommitArgs ca;
+    for (int i = 0; i < 6; ++i) ca.dst[i] = h_running_stats[i];
+    SG_PDL(bn_commit_kernel, 6u, 512u, (size_t)0, st, reinterpret_cast<const float*>(ws + L.bnpend), ca, status);
+  }
   return SG_OK;
 }
 
@@ -1033,9 +1056,9 @@ int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_bat
     const int rpp = 256 / (cout / 8);
     int blocks = (int)sg::ceil_div(rows, rpp * 4);
     if (blocks > kBnBlocks) blocks = kBnBlocks;
-    SG_PDL(bn_reduce_kernel<true>, (unsigned)(blocks), 256u, (size_t)0, st, h16(L.raw[l]), h16(L.dx[l]), ss, rows, cout, part);
+    SG_PDL(bn_reduce_kernel<true>, (unsigned)(blocks), 256u, (size_t)0, st, reinterpret_cast<const float*>(ws + L.raw[l]), h16(L.dx[l]), ss, rows, cout, part);
     SG_PDL(bn_bwd_finalize_kernel, (unsigned)((cout + 7) / 8), 256u, (size_t)0, st, part, blocks, rows, cout, ss, scal, want_w ? h_grads[5 + 2 * l] : nullptr, want_w ? h_grads[6 + 2 * l] : nullptr, coef, status);
-    SG_PDL(bn_bwd_apply_kernel, (unsigned)(ew_blocks(rows * (cout / 8))), 256u, (size_t)0, st, h16(L.raw[l]), h16(L.dx[l]), ss, coef, rows, cout, ilog2(S), h16(L.dyp[l]));
+    SG_PDL(bn_bwd_apply_kernel, (unsigned)(ew_blocks(rows * (cout / 8))), 256u, (size_t)0, st, reinterpret_cast<const float*>(ws + L.raw[l]), h16(L.dx[l]), ss, coef, rows, cout, ilog2(S), h16(L.dyp[l]));
     const void* in = (l == 0) ? h16(L.act1p) : h16(L.actp[l - 1]);
     if (want_w) {   // dW_l [cout][16 cin] = dY^T . im2col(act_{l-1}), split-K over the pixels
       TrGemm p{};
@@ -1112,14 +1135,15 @@ int sg_d64_train_read(const void* workspace, int64_t batch, int64_t max_batch, i
 
 namespace sg {
 namespace dtr {
-__global__ void __launch_bounds__(256) read_nhwc_kernel(const __half* __restrict__ src, int64_t batch, int S, int C, int pad,
+__global__ void __launch_bounds__(256) read_nhwc_kernel(const __half* __restrict__ src, int64_t batch, int S, int C, int pad, int is_f32,
                                                         float* __restrict__ out) {
   const int64_t total = batch * C * S * S;
   const int P = S + 2 * pad;
   for (int64_t t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
     const int w = (int)(t % S), h = (int)((t / S) % S), c = (int)((t / ((int64_t)S * S)) % C);
     const int64_t b = t / ((int64_t)S * S * C);
-    out[t] = __half2float(src[((b * P + h + pad) * P + w + pad) * C + c]);
+    const int64_t at = ((b * P + h + pad) * P + w + pad) * C + c;
+    out[t] = is_f32 ? reinterpret_cast<const float*>(src)[at] : __half2float(src[at]);
   }
 }
 }  // namespace dtr
@@ -1137,7 +1161,7 @@ extern "C" int sg_d64_train_read(const void* workspace, int64_t batch, int64_t m
   else if (what <= 4) { off = L.raw[what - 2]; S = kS[what]; C = kC[what]; pad = 0; }
   else if (what <= 6) { off = L.actp[what - 5]; S = kS[what - 3]; C = kC[what - 3]; pad = 1; }
   else { off = L.act4n; S = 4; C = 512; pad = 0; }
-  read_nhwc_kernel<<<ew_blocks(batch * C * S * S), 256, 0, sg::as_stream(stream)>>>(reinterpret_cast<const __half*>(ws + off), batch, S, C, pad, out);
+  read_nhwc_kernel<<<ew_blocks(batch * C * S * S), 256, 0, sg::as_stream(stream)>>>(reinterpret_cast<const __half*>(ws + off), batch, S, C, pad, (what >= 2 && what <= 4) ? 1 : 0, out);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -140,6 +140,28 @@ class TrainableD64(nn.Module):
     def _params(self):
         return [c.weight for c in self._convs] + [t for bn in self._bns for t in (bn.weight, bn.bias)]
 
+    def score_train(self, x: torch.Tensor, prob: torch.Tensor) -> torch.Tensor:
+        """``netD(x)`` in training mode without a graph (the in-batch strain block, "# 상위 10% 제거해서 fake image에
+        concate.py:244-245"): batch-statistics BatchNorm, running statistics committed on the device only if every logit is
+        finite.  Writes ``prob[B]``; returns the workspace's two status words (device int32[2], sticky)."""
+        dev = x.device
+        lib = A._lib_for(dev)
+        b = x.shape[0]
+        ws = self._take(dev, lib, b)
+        params = self._params()
+        stats = self._running_stats()
+        packed, _ = self._packed_for(dev, lib, params)
+        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, L.P(packed.data_ptr()), _ptr_array(params[5:]),
+                                         _ptr_array(stats), self.momentum, self.eps, L.P(ws.buf.data_ptr()),
+                                         L.P(prob.data_ptr()), None, A._stream()), "sg_d64_train_forward")
+        self._give_back(ws)
+        return ws.buf[:8].view(torch.int32)
+
+    def committed(self):
+        """module-side effects of one committed training-mode forward: version counters, ``num_batches_tracked``"""
+        A._bump_versions(self._running_stats())
+        self._count_batch()
+
     def check(self):
         """Synchronises and raises if a kernel timed out or an fp16 value left its range since the last check."""
         for ws in self._free:
@@ -160,7 +182,21 @@ class TrainableD64(nn.Module):
         return _D64TrainFn.apply(self, bool(param_grads), xc, *params)
 
 
+def trainer_for(discriminator: nn.Module, max_batch: int = 128) -> TrainableD64:
+    """The module's one TrainableD64 (kept on the module, outside nn.Module's registry): the in-batch strain block and the
+    training step share its packed weights and workspaces."""
+    if isinstance(discriminator, TrainableD64):
+        return discriminator
+    t = discriminator.__dict__.get("_sg_trainer")
+    if t is None:
+        t = TrainableD64(discriminator, max_batch)
+        object.__setattr__(discriminator, "_sg_trainer", t)
+    return t
+
+
 def accelerate_discriminator(discriminator: nn.Module, max_batch: int = 128) -> TrainableD64:
     """``netD = accelerate_discriminator(netD)`` after the optimiser was built: same parameters, same outputs, the
     training-step forward / backward on tcgen05."""
-    return TrainableD64(discriminator, max_batch)
+    t = trainer_for(discriminator, max_batch)
+    t.max_batch = max(t.max_batch, int(max_batch))
+    return t
