@@ -943,7 +943,7 @@ struct Enc2Cfg {
 };
 
 template <bool HALF>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
   using Cfg = Enc2Cfg;
@@ -1803,7 +1803,8 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     r2 = encode_tmap(&tb, 2, bf(L.w2), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r2 != SG_OK) return r2;
     const int64_t tiles = 2 * batch;
-    const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
+    const int64_t ctas2 = (int64_t)state().sm_count * 2;      // 2 CTAs per SM (82 KB of shared memory each): the strided-element
+    const int grid = (int)(tiles < ctas2 ? tiles : ctas2);    // TMA boxes are latency bound, a second CTA doubles the loads in flight
     ae_enc2_tc_kernel<HALF><<<grid, 192, Enc2Cfg::kSmemBytes, st>>>(ta, tb, h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
   } else {
     enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
@@ -1848,7 +1849,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     r = encode_tmap(&tb, 2, bf(L.w5), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r != SG_OK) return r;
     const int64_t tiles = 2 * batch;
-    const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);
+    const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);   // (two CTAs per SM with 3 stages: no gain)
     ae_dec2_tc_kernel<HALF><<<grid, 192, Dec2Cfg::kSmemBytes, st>>>(ta, tb, h_params[9], bf(L.a5), (int)batch, (int)tiles, err);
   } else {
     dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
