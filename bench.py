@@ -315,21 +315,30 @@ def main():
                "conv1_hbm_gbs": float(CHUNK * (49152 + 131072) / (lt[0] * 1e-3) / 1e9)}
 
     # selection + compaction kernels alone (HBM-bound in theory; 0.5 MB here => launch/L2 bound)
-    def sel_only():
-        t = sb.percentile_device(losses, q, group, n_global)
-        return sb.compact_indices(losses, t, 0, base)
-    for _ in range(5):
-        sel_only()
-    torch.cuda.synchronize()
-    evs = []
-    for _ in range(30):
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        sel_only()
-        b_.record()
-        evs.append((a_, b_))
-    torch.cuda.synchronize()
-    ms_sel = float(np.median([a_.elapsed_time(b_) for a_, b_ in evs]))   # median: robust to a host hiccup in the enqueue loop
+    # the step's own path: with a group, the radix histograms are reduced over NVLink peer memory inside the select's
+    # kernels (sb.PeerComm) when the GPUs can map each other, else by NCCL all-reduces; the NCCL form is timed beside it
+    peer = sb.PeerComm.for_group(group, device) if group is not None else None
+
+    def time_select(comm):
+        def sel_only():
+            t = sb.percentile_device(losses, q, group, n_global, comm=comm)
+            return sb.compact_indices(losses, t, 0, base)
+        for _ in range(5):
+            sel_only()
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+        evs = []
+        for _ in range(30):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            sel_only()
+            b_.record()
+            evs.append((a_, b_))
+        torch.cuda.synchronize()
+        return float(np.median([a_.elapsed_time(b_) for a_, b_ in evs]))   # median: robust to a host hiccup in the enqueue loop
+    ms_sel = time_select(peer)
+    ms_sel_nccl = time_select(None) if peer is not None else None
 
     # ---- multi-GPU parity (outside every timed region): the sharded strain of PARITY_TOTAL samples against rank 0's
     #      single-GPU strain of the concatenated shards -- threshold bits and kept-index list must be identical ---------
@@ -421,10 +430,17 @@ def main():
                                                                 n_global=ne * world, device=device, **kw), ne)
             d2h = int(len(idx_)) * 8 + 4
             api = "strain_shard(host pinned fp32 shard, netD, 0.1, group=WORLD, index_base=rank*n, n_global=N*n)"
-            note = ("one host dataset split by rank, global threshold (NCCL all-reduced histograms) and global kept indices; "
+            note = ("one host dataset split by rank, global threshold (radix histograms reduced over NVLink peer memory, NCCL as the fallback) and global kept indices; "
                     "PCIe H2D of 49152 B/sample is inside the timed region")
         e2e = {"value": v, "unit": "samples/s", "h2d_bytes_per_step": ne * 49152, "d2h_bytes_per_step": d2h,
                "samples_per_gpu": ne, "api": api, "note": note, "h2d_gbs_per_gpu_implied": v / world * 49152 / 1e9}
+        if h2d is not None:
+            # what bounds this leg: the rate at which this box feeds its GPUs from pinned host memory when all ranks copy at
+            # once (max-over-ranks timing: the slowest rank sets the step)
+            slow = min(h2d["gbs_per_gpu"])
+            e2e["bound"] = {"by": "host-to-device copies (box limit, measured by h2d_microbench with every rank copying at once)",
+                            "slowest_rank_h2d_gbs": slow, "aggregate_h2d_gbs": h2d["gbs_aggregate"],
+                            "frac_of_h2d_limit": (v / world * 49152 / 1e9) / slow}
         del host
         # the same call on a uint8 host dataset (the pixels the reference's ImageFolder decodes, ToTensor + Normalize
         # applied on the device, bit-identical to the host transform): 12288 B/sample over PCIe
@@ -547,7 +563,10 @@ def main():
                 "gpu_launches_note": "sg_launch_count() difference over the timed region on rank 0 (every launch site of the library)",
                 "fp32_parity_value": fp32_parity_value,
                 "roofline": roofline, "cpu_baseline": cpu, "multi_gpu_parity": parity, "h2d_microbench": h2d,
-                "kernels": kernels, "select_compact_ms": ms_sel, "train_iters_per_sec": train, "torch_eager_gpu": eager,
+                "kernels": kernels, "select_compact_ms": ms_sel,
+                "select_compact": {"ms": ms_sel, "reduction": ("nvlink peer memory inside the select kernels (PeerComm)" if peer is not None
+                                                               else ("nccl all-reduces" if group is not None else "single device")),
+                                   "ms_with_nccl_all_reduces": ms_sel_nccl}, "train_iters_per_sec": train, "torch_eager_gpu": eager,
                 "other_modes": other_modes}
         print(json.dumps(line), flush=True)
     if group is not None:
