@@ -906,8 +906,22 @@ def get_d28_scorer(discriminator: nn.Module, device=None, max_batch: int = 4096,
     return sc
 
 
+_KINDS = weakref.WeakKeyDictionary()      # module -> 'mlp' | 'd28' | 'd64': the structure walk costs ~50 us, a batch call has ~200
+
+
+def _kind(netD) -> str:
+    k = _KINDS.get(netD)
+    if k is None:
+        if any(isinstance(m, nn.Linear) for m in netD.modules()) and not any(isinstance(m, nn.Conv2d) for m in netD.modules()):
+            k = "mlp"
+        else:
+            k = "d28" if _d28_modules(netD) is not None else "d64"
+        _KINDS[netD] = k
+    return k
+
+
 def _is_d28(netD) -> bool:
-    return _d28_modules(netD) is not None
+    return _kind(netD) == "d28"
 
 
 def scorer_for(discriminator: nn.Module, device=None, conv_mode: str = "auto", max_batch: int = 4096):
@@ -921,7 +935,7 @@ def scorer_for(discriminator: nn.Module, device=None, conv_mode: str = "auto", m
 
 
 def _is_mlp(netD) -> bool:
-    return any(isinstance(m, nn.Linear) for m in netD.modules()) and not any(isinstance(m, nn.Conv2d) for m in netD.modules())
+    return _kind(netD) == "mlp"
 
 
 _COPY_STREAMS: dict = {}
@@ -1778,11 +1792,12 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
     # train-mode BatchNorm in the fp16 class: the training step's forward (csrc/d64_train.cu: one C call, programmatic
     # dependent launches, weights packed once per optimiser step and shared with the D step that follows)
     trainer = None
-    if train and sc.mode_name in ("auto", "fp16") and 2 <= b <= 4096 and x.dtype == torch.float32 and x.is_cuda and \
-            all(t.device == x.device and t.is_contiguous() and (t.dtype == torch.float32 or t.dtype == torch.int64)
-                for t in list(netD.parameters()) + list(netD.buffers())):      # a module living elsewhere: the scorer copies
+    if train and sc.mode_name in ("auto", "fp16") and 2 <= b <= 4096 and x.dtype == torch.float32 and x.is_cuda:
         from .train import trainer_for
         trainer = trainer_for(netD, max(b, 128))
+        if not all(t.device == x.device and t.is_contiguous() and t.dtype == torch.float32
+                   for t in trainer._params() + trainer._running_stats()):
+            trainer = None       # a module living elsewhere (or in another dtype): the scorer below converts and copies back
 
     def run(scorer, status):
         if train:

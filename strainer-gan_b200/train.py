@@ -62,10 +62,12 @@ class _D64TrainFn(torch.autograd.Function):
         return prob.view(b, 1, 1, 1)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         ws = ctx.ws
         if ws is None:
-            raise RuntimeError("strainer_b200: this discriminator output was produced without a graph")
+            raise RuntimeError("strainer_b200: the saved tensors of this discriminator pass are gone (a second backward through "
+                               "the same output, e.g. retain_graph=True, is not supported)")
         if [w._version for w in ctx.weights] != ctx.versions or ctx.owner._packed_versions != ctx.versions:
             raise RuntimeError("strainer_b200: a discriminator weight was modified in place between this forward and its backward "
                                "(autograd raises in the same situation)")

@@ -107,3 +107,21 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["impl"] == "reference" and line["metric"] == "strained_samples_per_sec"
     for k in ("value", "unit", "cpu_baseline", "e2e", "config", "higher_is_better"):
         assert k in line
+
+
+def test_trainable_d64_fails_loudly_without_gpu():
+    """the training-step wrapper has no CPU or autograd fallback: CPU input (or a foreign module) raises"""
+    import torch
+    import strainer_b200 as sb
+    from oracle import strainer_oracle as O
+    d = O.make_discriminator(O.SEED).train()
+    w = sb.accelerate_discriminator(d)
+    assert sb.accelerate_discriminator(d) is w                      # one wrapper (packed weights, workspaces) per module
+    assert [id(p) for p in w.parameters()] == [id(p) for p in d.parameters()]
+    with pytest.raises(RuntimeError):
+        w(torch.zeros(4, 3, 64, 64))
+    with pytest.raises(NotImplementedError):
+        sb.accelerate_discriminator(torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3)))
+    w.eval()
+    with torch.no_grad():                                           # eval mode: the wrapped module itself
+        assert torch.equal(w(torch.zeros(2, 3, 64, 64)), d(torch.zeros(2, 3, 64, 64)))
