@@ -136,7 +136,10 @@ int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, 
 /* ---- D64 training step: forward with batch-statistics BatchNorm + the whole backward pass ------------------
  * replaces what autograd runs for `output = netD(x)` and `err.backward()` in the D and G steps of
  * "#strainer gan.py:586-633" (":589-592" D on real, ":598-603" D on fake.detach(), ":610-615" G through D).
- * fp16 operands on tcgen05, fp32 accumulation; gradients carry a per-call power-of-two loss scale.
+ * precision 0: fp16 operands on tcgen05, fp32 accumulation (the arithmetic class of torch's default TF32 convolutions);
+ * precision 1: split operands, x = hi + lo in fp16, every GEMM as A_hi.B_hi + A_lo.B_hi + A_hi.B_lo (three tensor passes, the
+ * fp32-parity arithmetic: gradients within 1e-3 of fp32 autograd).  Packed block, workspace, forward and backward of one
+ * pass must use the same precision.  Gradients carry a per-call power-of-two loss scale.
  *
  * packed: sg_d64_train_packed_bytes() bytes, 1024-byte aligned: the fp16 operand forms of the five conv weights, written by
  * sg_d64_train_pack (h_weights: HOST array of 5 DEVICE pointers, conv1..conv5 weight [Cout][Cin][4][4]); repack after
@@ -152,21 +155,22 @@ int sg_d64_read_activation(const void* workspace, int64_t batch, int conv_mode, 
  * backward takes grad_prob[batch] = dL/dprob and writes h_grads (HOST array of 11 DEVICE pointers {dconv1..dconv5 weight,
  * dgamma2, dbeta2, dgamma3, dbeta3, dgamma4, dbeta4} in PyTorch layouts; NULL skips every parameter gradient, as the G
  * step may) and grad_x [batch,3,64,64] (NULL skips it). */
-size_t sg_d64_train_packed_bytes(void);
-int sg_d64_train_pack(const float* const* h_weights, void* packed, void* stream);
-size_t sg_d64_train_workspace_bytes(int64_t max_batch);
-int sg_d64_train_workspace_init(void* workspace, int64_t max_batch, void* stream);
-int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, const void* packed, const float* const* h_bn_params,
-                         float* const* h_running_stats, float momentum, float bn_eps, void* workspace, float* prob,
-                         float* logit, void* stream);
-int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, const void* packed, void* workspace,
-                          float* const* h_grads, float* grad_x, void* stream);
+size_t sg_d64_train_packed_bytes(int precision);
+int sg_d64_train_pack(const float* const* h_weights, int precision, void* packed, void* stream);
+size_t sg_d64_train_workspace_bytes(int64_t max_batch, int precision);
+int sg_d64_train_workspace_init(void* workspace, int64_t max_batch, int precision, void* stream);
+int sg_d64_train_forward(const float* x, int64_t batch, int64_t max_batch, int precision, const void* packed,
+                         const float* const* h_bn_params, float* const* h_running_stats, float momentum, float bn_eps,
+                         void* workspace, float* prob, float* logit, void* stream);
+int sg_d64_train_backward(const float* grad_prob, int64_t batch, int64_t max_batch, int precision, const void* packed,
+                          void* workspace, float* const* h_grads, float* grad_x, void* stream);
 /* synchronises `stream`; SG_ECUDA: a GEMM pipeline timed out, SG_EINVAL: a non-finite logit or gradient was produced
  * (fp16 range); clears the status words */
 int sg_d64_train_check(void* workspace, void* stream);
 /* debugging / tests: one saved tensor as fp32 NCHW.  what: 1 act1, 2..4 raw conv output of layer 2..4, 5..6 normalised
  * activation of layer 2..3, 7 normalised activation of layer 4 */
-int sg_d64_train_read(const void* workspace, int64_t batch, int64_t max_batch, int what, float* out, void* stream);
+int sg_d64_train_read(const void* workspace, int64_t batch, int64_t max_batch, int precision, int what, float* out,
+                      void* stream);
 
 /* ---- auto-encoder reconstruction-error scoring -------------------------------------------
  * replaces AutoEncoder.forward "#autoencoder.py:269-291" and the per-sample

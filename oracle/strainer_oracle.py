@@ -662,20 +662,22 @@ def train_step_through_d(netD: nn.Module, real: torch.Tensor, fake: torch.Tensor
     """``netD.zero_grad(); netD(real) -> errD_real.backward()`` ":586-592", ``netD(fake.detach()) -> errD_fake.backward()``
     ":598-603", then (without an optimiser step in between, as the fixture does) ``netD(fake) -> errG.backward()``
     ":610-615".  netD is used as it is (train mode: batch statistics, running statistics updated three times).
-    Returns the three output vectors, errD, errG, the accumulated D-step gradients and d errG / d fake."""
+    Returns the three output vectors, errD, errG, the accumulated D-step gradients and d errG / d fake.  The labels take the
+    dtype of ``real`` (the reference's are float32): a float64 module / input gives the float64 truth the fp32 runs are
+    measured against."""
     criterion = nn.BCELoss()
     fake = fake.detach().clone().requires_grad_(True)
     netD.zero_grad()
-    label = torch.full((real.size(0),), real_label, dtype=torch.float, device=real.device)
+    label = torch.full((real.size(0),), real_label, dtype=real.dtype, device=real.device)
     out_real = netD(real).view(-1)
     errD_real = criterion(out_real, label)
     errD_real.backward()
-    label = torch.full((fake.size(0),), fake_label, dtype=torch.float, device=real.device)
+    label = torch.full((fake.size(0),), fake_label, dtype=real.dtype, device=real.device)
     out_fake = netD(fake.detach()).view(-1)
     errD_fake = criterion(out_fake, label)
     errD_fake.backward()
     d_grads = [p.grad.detach().clone() for p in d64_params(netD)]
-    label = torch.full((fake.size(0),), real_label, dtype=torch.float, device=real.device)
+    label = torch.full((fake.size(0),), real_label, dtype=real.dtype, device=real.device)
     out_g = netD(fake).view(-1)
     errG = criterion(out_g, label)
     errG.backward()

@@ -39,14 +39,14 @@ _SIGS = {
     "sg_d64_run_layer": (c_int, [P, c_int64, P, P, c_int, c_int, P, P, P, P]),
     "sg_d64_check": (c_int, [P, P]),
     "sg_d64_read_activation": (c_int, [P, c_int64, c_int, c_int, P, P]),
-    "sg_d64_train_workspace_bytes": (c_size_t, [c_int64]),
-    "sg_d64_train_workspace_init": (c_int, [P, c_int64, P]),
-    "sg_d64_train_packed_bytes": (c_size_t, []),
-    "sg_d64_train_pack": (c_int, [P, P, P]),
-    "sg_d64_train_forward": (c_int, [P, c_int64, c_int64, P, P, P, c_float, c_float, P, P, P, P]),
-    "sg_d64_train_backward": (c_int, [P, c_int64, c_int64, P, P, P, P, P]),
+    "sg_d64_train_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "sg_d64_train_workspace_init": (c_int, [P, c_int64, c_int, P]),
+    "sg_d64_train_packed_bytes": (c_size_t, [c_int]),
+    "sg_d64_train_pack": (c_int, [P, c_int, P, P]),
+    "sg_d64_train_forward": (c_int, [P, c_int64, c_int64, c_int, P, P, P, c_float, c_float, P, P, P, P]),
+    "sg_d64_train_backward": (c_int, [P, c_int64, c_int64, c_int, P, P, P, P, P]),
     "sg_d64_train_check": (c_int, [P, P]),
-    "sg_d64_train_read": (c_int, [P, c_int64, c_int64, c_int, P, P]),
+    "sg_d64_train_read": (c_int, [P, c_int64, c_int64, c_int, c_int, P, P]),
     "sg_ae_workspace_bytes": (c_size_t, [c_int64]),
     "sg_ae_score": (c_int, [P, c_int64, P, P, P, P, P]),
     "sg_ae_bf16_workspace_bytes": (c_size_t, [c_int64]),

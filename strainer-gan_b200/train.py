@@ -24,10 +24,12 @@ from . import api as A
 class _Workspace:
     """One forward -> backward pair's saved tensors (a caller-owned buffer of the C ABI, borders zeroed once)."""
 
-    def __init__(self, device, lib, capacity: int):
+    def __init__(self, device, lib, capacity: int, precision: int = 0):
         self.capacity = int(capacity)
-        self.buf = A._aligned_empty(lib.sg_d64_train_workspace_bytes(self.capacity), device)
-        L.check(lib.sg_d64_train_workspace_init(L.P(self.buf.data_ptr()), self.capacity, A._stream()), "sg_d64_train_workspace_init")
+        self.precision = int(precision)
+        self.buf = A._aligned_empty(lib.sg_d64_train_workspace_bytes(self.capacity, self.precision), device)
+        L.check(lib.sg_d64_train_workspace_init(L.P(self.buf.data_ptr()), self.capacity, self.precision, A._stream()),
+                "sg_d64_train_workspace_init")
 
 
 def _ptr_array(tensors):
@@ -44,8 +46,8 @@ class _D64TrainFn(torch.autograd.Function):
         prob = torch.empty(b, device=dev, dtype=torch.float32)
         stats = owner._running_stats()
         packed, versions = owner._packed_for(dev, lib, params)
-        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, L.P(packed.data_ptr()), _ptr_array(params[5:]),
-                                         _ptr_array(stats) if stats else None, owner.momentum, owner.eps,
+        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, ws.precision, L.P(packed.data_ptr()),
+                                         _ptr_array(params[5:]), _ptr_array(stats) if stats else None, owner.momentum, owner.eps,
                                          L.P(ws.buf.data_ptr()), L.P(prob.data_ptr()), None, A._stream()),
                 "sg_d64_train_forward")
         if stats:
@@ -78,7 +80,8 @@ class _D64TrainFn(torch.autograd.Function):
         need_p = ctx.param_grads and any(ctx.needs_input_grad[3:])
         grads = [torch.empty(s, device=dev, dtype=torch.float32) for s in ctx.shapes] if need_p else None
         gx = torch.empty(ctx.x_shape, device=dev, dtype=torch.float32) if need_x else None
-        L.check(lib.sg_d64_train_backward(L.P(g.data_ptr()), ctx.batch, ws.capacity, L.P(ctx.packed.data_ptr()), L.P(ws.buf.data_ptr()),
+        L.check(lib.sg_d64_train_backward(L.P(g.data_ptr()), ctx.batch, ws.capacity, ws.precision, L.P(ctx.packed.data_ptr()),
+                                          L.P(ws.buf.data_ptr()),
                                           _ptr_array(grads) if grads else None, L.P(gx.data_ptr()) if need_x else None,
                                           A._stream()), "sg_d64_train_backward")
         ctx.owner._give_back(ws)
@@ -91,10 +94,16 @@ class _D64TrainFn(torch.autograd.Function):
 class TrainableD64(nn.Module):
     """``netD`` of the reference with forward + backward on the library's kernels while ``training`` is set; in eval mode
     the wrapped module itself runs.  ``forward(x, param_grads=False)`` skips the parameter gradients of this call (the G
-    step: the reference computes and then discards them with the next ``netD.zero_grad()``)."""
+    step: the reference computes and then discards them with the next ``netD.zero_grad()``).
+    ``precision``: 'fp16' (default: fp16 operands, fp32 accumulation -- the arithmetic class of torch's own default TF32
+    convolutions, gradients within 1-3 % of fp32 autograd like TF32's) or 'fp32' (split operands, three tensor passes:
+    gradients within 1e-3 of fp32 autograd)."""
 
-    def __init__(self, discriminator: nn.Module, max_batch: int = 128):
+    def __init__(self, discriminator: nn.Module, max_batch: int = 128, precision: str = "fp16"):
         super().__init__()
+        if precision not in ("fp16", "fp32"):
+            raise ValueError("precision must be 'fp16' or 'fp32'")
+        self.precision = 1 if precision == "fp32" else 0
         self.netD = discriminator
         convs, bns = A._d64_modules(discriminator)
         if len({bn.eps for bn in bns}) != 1 or len({bn.momentum for bn in bns}) != 1 or bns[0].momentum is None:
@@ -115,7 +124,7 @@ class TrainableD64(nn.Module):
         for i, ws in enumerate(self._free):
             if ws.capacity >= batch and ws.buf.device == device:
                 return self._free.pop(i)
-        return _Workspace(device, lib, self.max_batch)
+        return _Workspace(device, lib, self.max_batch, self.precision)
 
     def _give_back(self, ws):
         if len(self._free) < 4:
@@ -125,10 +134,11 @@ class TrainableD64(nn.Module):
         """fp16 operand forms of the conv weights, repacked when a weight's version counter moved (an optimiser step)"""
         versions = [w._version for w in params[:5]]
         if self._packed is None or self._packed.device != device:
-            self._packed = A._aligned_empty(lib.sg_d64_train_packed_bytes(), device)
+            self._packed = A._aligned_empty(lib.sg_d64_train_packed_bytes(self.precision), device)
             self._packed_versions = None
         if versions != self._packed_versions:
-            L.check(lib.sg_d64_train_pack(_ptr_array(params[:5]), L.P(self._packed.data_ptr()), A._stream()), "sg_d64_train_pack")
+            L.check(lib.sg_d64_train_pack(_ptr_array(params[:5]), self.precision, L.P(self._packed.data_ptr()), A._stream()),
+                    "sg_d64_train_pack")
             self._packed_versions = versions
         return self._packed, versions
 
@@ -153,8 +163,8 @@ class TrainableD64(nn.Module):
         params = self._params()
         stats = self._running_stats()
         packed, _ = self._packed_for(dev, lib, params)
-        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, L.P(packed.data_ptr()), _ptr_array(params[5:]),
-                                         _ptr_array(stats), self.momentum, self.eps, L.P(ws.buf.data_ptr()),
+        L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), b, ws.capacity, ws.precision, L.P(packed.data_ptr()),
+                                         _ptr_array(params[5:]), _ptr_array(stats), self.momentum, self.eps, L.P(ws.buf.data_ptr()),
                                          L.P(prob.data_ptr()), None, A._stream()), "sg_d64_train_forward")
         self._give_back(ws)
         return ws.buf[:8].view(torch.int32)
@@ -184,21 +194,22 @@ class TrainableD64(nn.Module):
         return _D64TrainFn.apply(self, bool(param_grads), xc, *params)
 
 
-def trainer_for(discriminator: nn.Module, max_batch: int = 128) -> TrainableD64:
-    """The module's one TrainableD64 (kept on the module, outside nn.Module's registry): the in-batch strain block and the
-    training step share its packed weights and workspaces."""
+def trainer_for(discriminator: nn.Module, max_batch: int = 128, precision: str = "fp16") -> TrainableD64:
+    """The module's one TrainableD64 per precision (kept on the module, outside nn.Module's registry): the in-batch strain
+    block and the training step share its packed weights and workspaces."""
     if isinstance(discriminator, TrainableD64):
         return discriminator
-    t = discriminator.__dict__.get("_sg_trainer")
+    key = "_sg_trainer_" + precision
+    t = discriminator.__dict__.get(key)
     if t is None:
-        t = TrainableD64(discriminator, max_batch)
-        object.__setattr__(discriminator, "_sg_trainer", t)
+        t = TrainableD64(discriminator, max_batch, precision)
+        object.__setattr__(discriminator, key, t)
     return t
 
 
-def accelerate_discriminator(discriminator: nn.Module, max_batch: int = 128) -> TrainableD64:
+def accelerate_discriminator(discriminator: nn.Module, max_batch: int = 128, precision: str = "fp16") -> TrainableD64:
     """``netD = accelerate_discriminator(netD)`` after the optimiser was built: same parameters, same outputs, the
-    training-step forward / backward on tcgen05."""
-    t = trainer_for(discriminator, max_batch)
+    training-step forward / backward on tcgen05.  ``precision='fp32'``: split-operand arithmetic (3 tensor passes)."""
+    t = trainer_for(discriminator, max_batch, precision)
     t.max_batch = max(t.max_batch, int(max_batch))
     return t

@@ -182,3 +182,30 @@ def test_identical_weight_updates_over_iterations(sb):
         assert float((ua @ ub) / (ua.norm() * ub.norm())) >= 0.995
     o1, o2 = a(real).view(-1), Db(real).view(-1)
     assert torch.allclose(o1, o2, rtol=2e-2, atol=1e-4)
+
+
+@pytest.mark.parametrize("B", [64, 37])
+def test_train_step_fp32_parity_precision(sb, B):
+    """precision='fp32' (split operands x = hi + lo, three tensor passes per GEMM): the D step and the G step's pass through
+    D against the oracle run in FLOAT64 on the CPU (the truth).  Outputs within 1e-4 (measured 1e-5).  Gradients: hi + lo
+    carry 22 significant bits, pre-activations agree with the truth to ~1e-6 -- but LeakyReLU's derivative is discontinuous:
+    an element whose pre-activation is within that distance of 0 takes the other slope, and ONE such flip among the 2 M
+    elements of a layer changes that layer's gradient by ~7e-4 of its norm.  With a handful of flips per pass (fp32 autograd
+    has them too, 7x fewer: its own conv1 gradient is 3e-4 .. 5e-4 from the truth here; in layer 4, 0.5 M elements, one flip
+    is 1.4e-3) the bar is 3e-3 on every tensor with cosine >= 0.99999; tensors without a flip agree to 1e-6 .. 3e-4."""
+    real_h = torch.from_numpy(O.synth_images(900, B))
+    fake_h = torch.tanh(torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(1000 + B)))
+    want = O.train_step_through_d(O.make_discriminator(O.SEED).train().double(), real_h.double(), fake_h.double())
+    f32 = O.train_step_through_d(O.make_discriminator(O.SEED).train(), real_h, fake_h)
+    netD = O.make_discriminator(O.SEED).cuda().train()
+    D = sb.accelerate_discriminator(netD, max_batch=128, precision="fp32")
+    r = _step(D, real_h.cuda(), fake_h.cuda())
+    D.check()
+    for k in ("out_real", "out_fake", "out_g"):
+        assert torch.allclose(r[k].cpu().double(), want[k], rtol=1e-4, atol=1e-7), k
+    for n, got, w, f in zip(O.D64_PARAM_NAMES, r["d_grads"], want["d_grads"], f32["d_grads"]):
+        e = _rel(got, w)
+        assert e <= 3e-3 and _cos(got, w) >= 0.99999, (n, e, _rel(f, w))
+    e = _rel(r["dfake"], want["dfake"])
+    assert e <= 3e-3 and _cos(r["dfake"], want["dfake"]) >= 0.99999, (e, _rel(f32["dfake"], want["dfake"]))
+    assert int([m for m in netD.modules() if isinstance(m, nn.BatchNorm2d)][0].num_batches_tracked) == 3

@@ -49,6 +49,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-time", action="store_true")
+    ap.add_argument("--precision", default="fp16")
     a = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -77,20 +78,22 @@ def main():
 
     # ---- stage check through the C ABI -----------------------------------------------------------------------------------
     lib = A._lib_for(dev)
-    ws = T._Workspace(dev, lib, B)
-    wrapped = sb.TrainableD64(mine, max_batch=B)
+    prec = 1 if a.precision == "fp32" else 0
+    out["precision"] = a.precision
+    ws = T._Workspace(dev, lib, B, prec)
+    wrapped = sb.TrainableD64(mine, max_batch=B, precision=a.precision)
     params = wrapped._params()
     stats = wrapped._running_stats()
     prob = torch.empty(B, device=dev)
     logit = torch.empty(B, device=dev)
     packed, _ = wrapped._packed_for(dev, lib, params)
-    L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), B, B, L.P(packed.data_ptr()), T._ptr_array(params[5:]), T._ptr_array(stats), 0.1, 1e-5,
+    L.check(lib.sg_d64_train_forward(L.P(x.data_ptr()), B, B, prec, L.P(packed.data_ptr()), T._ptr_array(params[5:]), T._ptr_array(stats), 0.1, 1e-5,
                                      L.P(ws.buf.data_ptr()), L.P(prob.data_ptr()), L.P(logit.data_ptr()), A._stream()), "fwd")
     torch.cuda.synchronize()
 
     def read(what, c, s):
         t = torch.empty(B, c, s, s, device=dev)
-        L.check(lib.sg_d64_train_read(L.P(ws.buf.data_ptr()), B, B, what, L.P(t.data_ptr()), A._stream()), "read")
+        L.check(lib.sg_d64_train_read(L.P(ws.buf.data_ptr()), B, B, prec, what, L.P(t.data_ptr()), A._stream()), "read")
         torch.cuda.synchronize()
         return t
     stages = {}
@@ -111,7 +114,7 @@ def main():
     gprob = (-(target / pr.detach()) / B).contiguous()      # d BCE(mean) / d prob for target 1
     grads = [torch.zeros_like(p) for p in params]
     gx = torch.zeros_like(x)
-    L.check(lib.sg_d64_train_backward(L.P(gprob.data_ptr()), B, B, L.P(packed.data_ptr()), L.P(ws.buf.data_ptr()), T._ptr_array(grads), L.P(gx.data_ptr()),
+    L.check(lib.sg_d64_train_backward(L.P(gprob.data_ptr()), B, B, prec, L.P(packed.data_ptr()), L.P(ws.buf.data_ptr()), T._ptr_array(grads), L.P(gx.data_ptr()),
                                       A._stream()), "bwd")
     torch.cuda.synchronize()
     rc = lib.sg_d64_train_check(L.P(ws.buf.data_ptr()), A._stream())
@@ -126,6 +129,19 @@ def main():
     out["grad_x_max_rel"] = maxrel(gx, xr.grad)
     out["grad_norms_ref"] = {n: float(p.grad.norm()) for n, p in zip(names, rparams)}
     out["grad_norms_mine"] = {n: float(g.norm()) for n, g in zip(names, grads)}
+
+    # ---- float64 autograd on the GPU as the truth: what fp32 autograd itself, and this path, differ from it by ---------------
+    r64 = copy.deepcopy(ref).double()
+    for p in r64.parameters():
+        p.grad = None
+    x64 = x.double().clone().requires_grad_(True)
+    nn.functional.binary_cross_entropy(r64(x64).view(-1), target.double()).backward()
+    p64 = [c.weight for c in r64.modules() if isinstance(c, nn.Conv2d)] + \
+        [t for bn in r64.modules() if isinstance(bn, nn.BatchNorm2d) for t in (bn.weight, bn.bias)]
+    out["vs_float64"] = {"this_path": {n: rel(g, p.grad) for n, g, p in zip(names, grads, p64)},
+                         "this_path_grad_x": rel(gx, x64.grad),
+                         "torch_fp32_no_tf32": {n: rel(p.grad, q.grad) for n, p, q in zip(names, rparams, p64)},
+                         "torch_fp32_no_tf32_grad_x": rel(xr.grad, x64.grad)}
 
     # ---- what torch's own default (TF32 convolutions) differs by, for scale ----------------------------------------------
     torch.backends.cudnn.allow_tf32 = True
@@ -145,7 +161,7 @@ def main():
         p.grad = None
     for m, r in zip([m for m in mine2.modules() if isinstance(m, nn.BatchNorm2d)], rbn):
         pass
-    w2 = sb.accelerate_discriminator(mine2, max_batch=B)
+    w2 = sb.accelerate_discriminator(mine2, max_batch=B, precision=a.precision)
     xm = x.clone().requires_grad_(True)
     po = w2(xm)
     out["wrapper_shape"] = list(po.shape)
