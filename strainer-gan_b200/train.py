@@ -57,10 +57,6 @@ class _D64TrainFn(torch.autograd.Function):
         ctx.packed, ctx.versions, ctx.weights = packed, versions, params[:5]
         ctx.shapes = [p.shape for p in params]
         ctx.x_shape = x.shape
-        needs = ctx.needs_input_grad
-        if not any(needs):
-            owner._give_back(ws)
-            ctx.ws = None
         return prob.view(b, 1, 1, 1)
 
     @staticmethod
@@ -191,6 +187,12 @@ class TrainableD64(nn.Module):
         if any(p.device != x.device or p.dtype != torch.float32 or not p.is_contiguous() for p in params):
             raise RuntimeError("strainer_b200: parameters must be contiguous fp32 tensors on the input's device")
         xc = x.to(torch.float32).contiguous()
+        if not torch.is_grad_enabled() or not (xc.requires_grad or any(p.requires_grad for p in params)):
+            # no graph: the workspace goes straight back to the pool
+            prob = torch.empty(xc.shape[0], device=xc.device, dtype=torch.float32)
+            self.score_train(xc, prob)
+            self.committed()
+            return prob.view(-1, 1, 1, 1)
         return _D64TrainFn.apply(self, bool(param_grads), xc, *params)
 
 

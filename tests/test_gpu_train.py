@@ -209,3 +209,30 @@ def test_train_step_fp32_parity_precision(sb, B):
     e = _rel(r["dfake"], want["dfake"])
     assert e <= 3e-3 and _cos(r["dfake"], want["dfake"]) >= 0.99999, (e, _rel(f32["dfake"], want["dfake"]))
     assert int([m for m in netD.modules() if isinstance(m, nn.BatchNorm2d)][0].num_batches_tracked) == 3
+
+
+def test_fp16_overflow_is_reported_and_leaves_running_stats(sb):
+    """an activation beyond fp16's range (conv1 weights scaled up): the pass yields non-finite values, check() reports it,
+    and the BatchNorm running statistics are NOT committed (bn_commit_kernel); the split-operand precision has the same
+    range and reports the same; a following ordinary batch works"""
+    d = O.make_discriminator(O.SEED).cuda().train()
+    with torch.no_grad():
+        d.main[0].weight.mul_(4.0e6)
+    before = [t.clone() for bn in d.modules() if isinstance(bn, nn.BatchNorm2d) for t in (bn.running_mean, bn.running_var)]
+    x = torch.from_numpy(O.synth_images(0, 32)).cuda()
+    for prec in ("fp16", "fp32"):
+        D = sb.accelerate_discriminator(d, precision=prec)
+        with torch.no_grad():
+            D(x)
+        with pytest.raises(RuntimeError, match="non-finite"):
+            D.check()
+        after = [t for bn in d.modules() if isinstance(bn, nn.BatchNorm2d) for t in (bn.running_mean, bn.running_var)]
+        assert all(torch.equal(a, b) for a, b in zip(before, after))
+        D.check()                                # the words are cleared by the report
+    with torch.no_grad():
+        d.main[0].weight.mul_(1.0 / 4.0e6)
+    D = sb.accelerate_discriminator(d)
+    with torch.no_grad():
+        p = D(x)
+    D.check()
+    assert torch.isfinite(p).all() and not torch.equal(before[0], d.main[3].running_mean)
