@@ -1245,6 +1245,12 @@ __global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 // NCHW image), and reduces the squared differences in a fixed order: thread (double) -> warp butterfly -> the four
 // warps in order -> partial[image][tile]; ae_mse_finish_kernel adds the 8 tile sums of an image in order.
 // ------------------------------------------------------------------------------------------
+// tanh(x) = sign(x) (1 - t) / (1 + t), t = exp(-2 |x|) in (0, 1]: one ex2.approx and one fast division; absolute error < 5e-7
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float t = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - t, 1.f + t), x);
+}
+
 struct Dec3Cfg {
   static constexpr int kPart = 128 * 32;
   static constexpr int kStageBytes = 4 * kPart;   // 16 KB per tile
@@ -1361,7 +1367,10 @@ ae_dec3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       const float* xin = x + (size_t)img * 12288;
-      double sq = 0.0;
+      // the epilogue was the kernel's bound (125 M warp instructions per 8192 images, most of them libm tanhf and fp64
+      // adds): tanh through one ex2 + one division (absolute error < 5e-7, far inside the path's 16-bit operand error),
+      // the thread's 12 squares in fp32 (fixed order), fp64 only for the warp / tile sums
+      float sqf = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
@@ -1369,13 +1378,15 @@ ae_dec3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int py = 0; py < 2; ++py) {
           const uint32_t* v = py ? v1 : v0;
           const int off = (c * 64 + 2 * qy + py) * 64 + 2 * qx;
-          const float r0 = tanhf(__uint_as_float(v[c]) + bc), r1 = tanhf(__uint_as_float(v[16 + c]) + bc);
+          const float r0 = fast_tanh(__uint_as_float(v[c]) + bc), r1 = fast_tanh(__uint_as_float(v[16 + c]) + bc);
           const float2 t = __ldg(reinterpret_cast<const float2*>(xin + off));
           const float d0 = r0 - t.x, d1 = r1 - t.y;
-          sq += (double)(d0 * d0) + (double)(d1 * d1);
+          sqf = fmaf(d0, d0, sqf);
+          sqf = fmaf(d1, d1, sqf);
           if (recon) *reinterpret_cast<float2*>(recon + (size_t)img * 12288 + off) = make_float2(r0, r1);
         }
       }
+      double sq = (double)sqf;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       double* sp = s_part + (it & 1) * 4;
