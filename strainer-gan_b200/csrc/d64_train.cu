@@ -4,7 +4,7 @@
 //
 // Everything GEMM-shaped goes through ONE kernel, trgemm_kernel<MODE>: persistent, warp specialised (warp 0 TMA producer,
 // warp 1 tcgen05.mma issuer, warps 2-5 TMEM-drain epilogue), 128 x 128 x 64 tiles, fp16 operands, fp32 accumulation in
-// TMEM (two accumulators ping-pong).  Operands are never im2col'ed in memory: activations live as zero-bordered NHWC
+// TMEM (two accumulator pairs ping-pong).  Operands are never im2col'ed in memory: activations live as zero-bordered NHWC
 // fp16 tensors [B][S+2][S+2][C] and every operand tile is one (or two) multi-dimensional TMA boxes of them:
 //
 //   fprop  Y[(b,oh,ow), co]   = sum_{tap,ci} X[b, 2oh+kh, 2ow+kw, ci] W[co, tap, ci]      A = tap box of X (K-major)
@@ -16,7 +16,15 @@
 // The padded NHWC tensor is addressed by TMA as 5-D (2C, S/2+1, 2, S/2+1, B): (column parity, channel) | column pair |
 // row parity | row pair | image, so that the stride-2 tap (kh, kw) of a tile of output pixels is a dense box.
 // Gradients are carried in fp16 with a power-of-two loss scale chosen per call from max|dL/dlogit| (head_bwd_prep_kernel)
-// and removed when the fp32 results are written.  BatchNorm (training mode): deterministic two-stage column sums.
+// and removed when the fp32 results are written.  The raw conv outputs stay fp32: BatchNorm (training mode, deterministic
+// two-stage column sums), x-hat and the LeakyReLU gate of the backward pass see unrounded sums.
+//
+// precision 1 (the fp32-parity arithmetic): every 16-bit tensor carries hi = fp16(x) | lo' = fp16((x - hi) * 2^11) side by
+// side, every K step runs three segments -- A_hi.B_hi into one accumulator, A_lo'.B_hi and A_hi.B_lo' into a second one --
+// and the epilogue adds the pair with the factor 2^-11: 22 significant bits through the same kernel.
+//
+// Every kernel is launched with programmatic stream serialisation (griddepcontrol): the ~40 launches of a forward +
+// backward pass overlap their prologues with the tail of the kernel before.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
