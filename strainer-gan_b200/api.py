@@ -26,6 +26,8 @@ _c = L  # short alias
 # plumbing
 # ----------------------------------------------------------------------------------------------
 def _dev(device=None) -> torch.device:
+    if type(device) is torch.device and device.type == "cuda" and device.index is not None:
+        return device      # the device of a tensor that already lives there (the per-batch paths call this twice)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
     device = torch.device(device) if device is not None else None
@@ -80,8 +82,14 @@ def _lib_for(device: torch.device):
     return d
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
-    """torch's current stream ON THE DEVICE of the call being assembled (not of torch's current device)."""
+    """torch's current stream ON THE DEVICE of the call being assembled (not of torch's current device).  The raw query
+    costs < 1 us; building a torch.cuda.Stream object per C call cost 6 us of the in-batch block's ~60 us of host time."""
+    if _RAW_STREAM is not None:
+        return L.P(_RAW_STREAM(_ACTIVE[0]))
     return L.P(torch.cuda.current_stream(_ACTIVE[0]).cuda_stream)
 
 
@@ -1746,6 +1754,19 @@ def _read_counts(counts: torch.Tensor, extra_status=None):
     return int(h[0][0]), int(h[0][1])
 
 
+_STATUS_WORDS: dict = {}
+
+
+def _status_words(device) -> torch.Tensor:
+    """A per-device int32[2] for the status words of one in-batch scoring call: zeroed when created and again only after a
+    call that found it set (the kernels write it on an error only), which saves a memset launch per batch."""
+    t = _STATUS_WORDS.get(device.index)
+    if t is None:
+        t = torch.zeros(2, dtype=torch.int32, device=device)
+        _STATUS_WORDS[device.index] = t
+    return t
+
+
 def _last_status(device) -> tuple:
     h = _PINNED[device.index][1]
     return int(h[0]), int(h[1])
@@ -1810,20 +1831,18 @@ def strain_batch(netD, real: torch.Tensor, q: float = 0.1, *, conv_mode: str = "
         status = trainer.score_train(x, prob)
         out = strain_scores(real, prob, q, _extra_status=status)
     else:
-        status = torch.zeros(2, dtype=torch.int32, device=device)
+        status = _status_words(device)      # zero unless the previous call found an error (and cleared it below)
         out = run(sc, status)
     st0, st1 = _last_status(device)
     if st0:
-        if trainer is not None:
-            status.zero_()
+        status.zero_()
         _raise_status(st0)
     if trainer is not None and st1 != _FP16_OVERFLOW:
         trainer.committed()
         return out
     if st1 == _FP16_OVERFLOW:
-        if trainer is not None:
-            status.zero_()      # sticky words of the training workspace: reported here
-            status = torch.zeros(2, dtype=torch.int32, device=device)
+        status.zero_()          # sticky words (the training workspace's, or the per-device pair): reported here
+        status = _status_words(device)
         if sc.mode_name != "auto":
             raise RuntimeError("strainer_b200: non-finite logit in the fp16 conv mode (an activation exceeded 65504); use "
                                "conv_mode='auto', 'fp32' or 'bf16'")
