@@ -65,10 +65,43 @@ int check_ready();  // SG_OK or SG_ENOINIT / SG_EARCH
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Programmatic dependent launch: the kernel may become resident while its predecessor in the stream still runs; it must
+// execute pdl_wait() before it touches global memory the predecessor writes (or that a successor of the predecessor reads).
+template <typename... KArgs, typename... Args>
+static inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+    return SG_ECUDA;
+  }
+  return SG_OK;
+}
+#define SG_LAUNCH_PDL(...)                        \
+  do {                                            \
+    const int _pr = sg::launch_pdl(__VA_ARGS__);  \
+    if (_pr != SG_OK) return _pr;                 \
+  } while (0)
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 // ---- device helpers ----------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 // Monotone fp32 -> uint32 radix key.  NaN (either sign) -> 0xFFFFFFFF (sorts last, as numpy /
 // torch sort do), -0.0 is canonicalised to +0.0.
 __device__ __forceinline__ uint32_t float_to_key(float f) {

@@ -75,8 +75,6 @@ struct TrGemm {
 // successor become resident at once (launch_dependents) and waits for its predecessor's completion (and memory flush)
 // before it touches global memory -- the ~40 launches of a forward + backward pass overlap their prologues (barrier
 // init, TMEM allocation, descriptor prefetch) with the tail of the kernel before.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 struct Unit { int cls, mt, nt, split, ks0, ks1; };
 __device__ __forceinline__ Unit decode_unit(const TrGemm& p, int u) {
@@ -937,25 +935,9 @@ static void row_box(int S, int rows, TrGemm* p, int64_t batch, int* tiles) {
   p->ohb_log2 = ilog2(p->ohb);
 }
 
-template <typename... KArgs, typename... Args>
-static int launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(block, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
-  count_launch();
-  return SG_OK;
-}
 #define SG_PDL(...)                              \
   do {                                           \
-    const int _pr = launch_pdl(__VA_ARGS__);     \
+    const int _pr = sg::launch_pdl(__VA_ARGS__); \
     if (_pr != SG_OK) return _pr;                \
   } while (0)
 
@@ -963,7 +945,7 @@ template <int MODE>
 static int launch_trgemm(const CUtensorMap& ta, const CUtensorMap& tb, const TrGemm& p, cudaStream_t st) {
   const int64_t total = (int64_t)p.classes * p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < state().sm_count ? total : state().sm_count);
-  return launch_pdl(trgemm_kernel<MODE>, (unsigned)grid, 192u, (size_t)kSmemBytes, st, ta, tb, p);
+  return sg::launch_pdl(trgemm_kernel<MODE>, dim3((unsigned)grid), dim3(192), (size_t)kSmemBytes, st, ta, tb, p);
 }
 
 static int ew_blocks(int64_t threads) {
