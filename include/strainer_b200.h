@@ -83,6 +83,17 @@ int sg_synth_images(float* out, int64_t start, int64_t count, uint32_t seed, voi
 int sg_u8_normalize(const uint8_t* x, int64_t count, int channels, int64_t plane, int layout, const float* h_mean,
                     const float* h_std, float* out, void* stream);
 
+/* ---- host-packed PCIe copy of a fp32 host dataset ----------------------------------------------
+ * The DataLoader batches of "#strainer gan.py:364-375" are fp32 in host memory; the fp16 conv mode rounds every input
+ * pixel to fp16 (RN) in conv1.  sg_host_f32_to_f16 does that rounding on the HOST (h_src, h_dst: host pointers; `threads`
+ * host threads, <= 0: all the process may run on; isa 0 = best available, 1 scalar, 2 AVX2+F16C, 3 AVX-512F) so that half
+ * the bytes cross PCIe; sg_f16_expand widens the fp16 bits to fp32 on the device (exact), and the scores are
+ * bit-identical to the ones of the fp32 copy.  Data movement only: nothing is scored on the host.
+ * sg_host_threads: CPUs in the calling process' affinity mask.  Neither host function needs sg_init. */
+int sg_host_threads(void);
+int sg_host_f32_to_f16(const float* h_src, int64_t count, uint16_t* h_dst, int threads, int isa);
+int sg_f16_expand(const uint16_t* x, int64_t count, float* out, void* stream);
+
 /* ---- D64 scoring: Discriminator.forward + BCE vs label 1 ------------------------------
  * replaces "#strainer gan.py:230-256" (5 convs, eval-mode BN, LeakyReLU .2, Sigmoid) and the
  * per-sample BCELoss(reduction='none') of ":369-375" / "#clean...py:279-285".               */

@@ -29,6 +29,9 @@ _SIGS = {
     "sg_launch_count": (ctypes.c_longlong, []),
     "sg_synth_images": (c_int, [P, c_int64, c_int64, c_uint32, P]),
     "sg_u8_normalize": (c_int, [P, c_int64, c_int, c_int64, c_int, P, P, P, P]),
+    "sg_host_threads": (c_int, []),
+    "sg_host_f32_to_f16": (c_int, [P, c_int64, P, c_int, c_int]),
+    "sg_f16_expand": (c_int, [P, c_int64, P, P]),
     "sg_d64_packed_bytes": (c_size_t, [c_int]),
     "sg_d64_pack": (c_int, [P] * 17 + [c_float, c_int, P, P]),
     "sg_d64_workspace_bytes": (c_size_t, [c_int64, c_int]),

@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes
 import math
 import os
+import time
 import weakref
 
 import numpy as np
@@ -409,6 +410,72 @@ def _raise_status(st0: int):
                        "2x mma, 3x accumulator, 4x epilogue); the losses of this call are invalid")
 
 
+class _PackTuner:
+    """Picks the host-packed share of a pinned fp32 source per (device, host thread count) by timing the first few
+    ``score`` calls of at least four chunks: all rows packed first, then 0.1 less per call while that is more than 2 %
+    faster (on the 16-core B200 box: 1.0 with 16 threads, 0.9 with 12, 0.8 with 8; tools/host_pack_sweep.py), then the
+    best share is kept.  A share below 0.3 ends at the plain fp32 copy."""
+    _by_key: dict = {}
+
+    def __init__(self):
+        self.share = 1.0
+        self.best_rate = 0.0
+        self.best_share = 1.0
+        self.locked = False
+
+    @classmethod
+    def get(cls, device) -> "_PackTuner":
+        key = (device.index, _host_threads())
+        t = cls._by_key.get(key)
+        if t is None:
+            t = cls._by_key[key] = cls()
+        return t
+
+    def report(self, share: float, samples_per_s: float):
+        if self.locked or share != self.share:
+            return
+        if samples_per_s > self.best_rate * 1.02:
+            self.best_rate, self.best_share = samples_per_s, share
+            nxt = round(share - 0.1, 2)
+            if share <= 0.0:
+                self.locked = True
+            else:
+                self.share = nxt if nxt >= 0.3 else 0.0
+        else:
+            self.share = self.best_share
+            self.locked = True
+
+
+def _host_threads() -> int:
+    """Host threads of this process for the fp16 staging conversion: its CPU affinity, shared between the ranks of a
+    torchrun launch on this node."""
+    cpus = int(L.load().sg_host_threads())
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, cpus // max(local, 1))
+
+
+_PACK_EXECUTOR = None
+
+
+def _pack_executor():
+    """One background thread that drives the host conversion of the NEXT chunk while the caller queues this one."""
+    global _PACK_EXECUTOR
+    if _PACK_EXECUTOR is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _PACK_EXECUTOR = ThreadPoolExecutor(max_workers=1, thread_name_prefix="sg-host-pack")
+    return _PACK_EXECUTOR
+
+
+def _host_to_f16(src: torch.Tensor, dst: torch.Tensor, isa: int = 0):
+    """dst (host fp16, contiguous) = src (host fp32, contiguous) rounded to nearest even, on the library's host threads."""
+    if src.is_cuda or dst.is_cuda or src.dtype != torch.float32 or dst.dtype != torch.float16:
+        raise ValueError("_host_to_f16: host fp32 source and host fp16 destination")
+    if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
+        raise ValueError("_host_to_f16: contiguous tensors of equal size")
+    L.check(L.load().sg_host_f32_to_f16(src.data_ptr(), src.numel(), dst.data_ptr(), _host_threads(), isa),
+            "sg_host_f32_to_f16")
+
+
 class D64Scorer:
     """Packs a reference ``Discriminator``'s weights for the tcgen05 kernels and scores batches:
     eval-mode BN folded into the conv epilogues, sigmoid and BCE-vs-1 fused into the head.
@@ -435,6 +502,9 @@ class D64Scorer:
         self._fallback = None       # 'auto': fp32-parity scorer, built when the first chunk overflows
         self._stage = {}            # cached staging buffers of the host-streaming path
         self.fallback_chunks = 0    # chunks (or batches) re-scored since construction
+        self.host_pack = "auto"     # fp32 HOST sources: share of each chunk rounded to fp16 on the host before its PCIe copy
+        self.h2d_bytes = 0          # bytes this scorer has copied host -> device (bench.py reports the difference per step)
+        self.last_pack_fraction = 0.0
         self.repack(discriminator)
 
     @property
@@ -575,6 +645,24 @@ class D64Scorer:
             self._stage[key] = t
         return t
 
+    def _host_pack_fraction(self, src: torch.Tensor, pinned_src: bool) -> float:
+        """Share of each chunk of a fp32 HOST source that is rounded to fp16 on the host before its PCIe copy
+        (``host_pack``: 'auto', a float in [0, 1], or False).  Only where conv1 rounds the input to fp16 anyway (modes
+        'auto' / 'fp16') and only for inputs of at least 4 096 images.  'auto': a pageable source is packed entirely
+        (the conversion reads it in place, where the raw copy would need a staging memcpy first); for a pinned source
+        the share comes from ``_PackTuner`` (the host threads and the PCIe copies compete for host memory bandwidth, so
+        the best share is found by timing whole calls, not from the two rates in isolation)."""
+        hp = self.host_pack
+        if hp is False or hp is None or self.mode_name not in ("auto", "fp16") or src.dtype != torch.float32:
+            return 0.0
+        if not isinstance(hp, str):
+            return float(min(max(float(hp), 0.0), 1.0))
+        if src.shape[0] < 4096:
+            return 0.0
+        if not pinned_src:
+            return 1.0
+        return _PackTuner.get(self.device).share
+
     def score(self, images, want=("loss",)):
         """Scores N images: a fp32 tensor [N,3,64,64] or a ``U8Images`` (uint8 pixels + Normalize, converted on the
         device), CUDA resident or on the host (streamed through double buffers with the H2D copies overlapped with
@@ -600,6 +688,7 @@ class D64Scorer:
             self.score_into(x, sl("logit", i, b), sl("prob", i, b), sl("loss", i, b), status[ci])
 
         src = (u8.pixels if u8 is not None else images).contiguous()
+        tuned = None
         if src.is_cuda:
             f32 = self._staging("f32_0", (cb, 3, 64, 64), torch.float32) if u8 is not None else None
             for ci in range(nchunks):
@@ -617,23 +706,67 @@ class D64Scorer:
             row = tuple(src.shape[1:])
             dev = [self._staging(f"dev_{k}", (cb,) + row, src.dtype) for k in range(2)]
             f32 = [self._staging(f"f32_{k}", (cb, 3, 64, 64), torch.float32) for k in range(2)] if u8 is not None else None
-            pin = None if pinned_src else [self._staging(f"pin_{k}", (cb,) + row, src.dtype, pinned=True) for k in range(2)]
+            # host-packed copy (csrc/host_pack.cpp): the last `pk` rows of every chunk are rounded to fp16 by the host
+            # threads -- the rounding conv1 applies anyway -- while the first rows cross PCIe as fp32; the share balances
+            # the two (measured once per process and device).  Bit-identical scores, about half the PCIe bytes.
+            frac = self._host_pack_fraction(src, pinned_src) if u8 is None else 0.0
+            self.last_pack_fraction = frac
+            if u8 is None and self.host_pack == "auto" and pinned_src and nchunks >= 4 and \
+                    self.mode_name in ("auto", "fp16") and src.dtype == torch.float32:
+                tuned = (_PackTuner.get(self.device), frac, time.perf_counter())
+            pack_rows = (lambda b_: b_ if frac >= 1.0 else (int(b_ * frac) // 16) * 16) if frac > 0.0 else (lambda b_: 0)
+            pin16 = dev16 = None
+            if frac > 0.0:
+                if "pin16_0" not in self._stage:
+                    tuned = None               # this call pins its staging buffers (~0.1 s): not a timing to tune on
+                # three pinned fp16 buffers: the conversion of chunk c + 1 runs on the host threads (behind a one-thread
+                # executor, the C call releases the GIL) while this thread queues the copies and kernels of chunk c
+                pin16 = [self._staging(f"pin16_{k}", (cb,) + row, torch.float16, pinned=True) for k in range(3)]
+                dev16 = [self._staging(f"dev16_{k}", (cb,) + row, torch.float16) for k in range(2)]
+            need_pin = not pinned_src and frac < 1.0
+            pin = [self._staging(f"pin_{k}", (cb,) + row, src.dtype, pinned=True) for k in range(2)] if need_pin else None
             copied = [torch.cuda.Event() for _ in range(2)]
+            copied16 = [torch.cuda.Event() for _ in range(3)]
             consumed = [torch.cuda.Event() for _ in range(2)]
-            for ci in range(nchunks):
-                s_ = ci & 1
+            row_elems = int(np.prod(row))
+
+            def split(ci):
                 i = ci * cb
                 b = min(cb, n - i)
-                if ci >= 2 and not pinned_src:
+                pk = pack_rows(b)
+                return i, b, b - pk, pk
+
+            def start_pack(ci):
+                i, b, raw, pk = split(ci)
+                if not pk:
+                    return None
+                if ci >= 3:
+                    copied16[ci % 3].synchronize()     # the H2D copy that last read this pinned buffer has finished
+                return _pack_executor().submit(_host_to_f16, src[i + raw:i + b], pin16[ci % 3][:pk])
+
+            pending = start_pack(0)
+            for ci in range(nchunks):
+                s_ = ci & 1
+                i, b, raw, pk = split(ci)
+                if pending is not None:
+                    pending.result()
+                pending = start_pack(ci + 1) if ci + 1 < nchunks else None
+                if ci >= 2 and need_pin:
                     copied[s_].synchronize()  # the H2D copy that last read pin[s_] has finished
                 with torch.cuda.stream(copy_stream):
                     if ci >= 2:
                         copy_stream.wait_event(consumed[s_])
-                    part = src[i:i + b]
-                    if not pinned_src:
-                        pin[s_][:b].copy_(part)
-                        part = pin[s_][:b]
-                    dev[s_][:b].copy_(part, non_blocking=True)
+                    if pk:
+                        dev16[s_][:pk].copy_(pin16[ci % 3][:pk], non_blocking=True)
+                        copied16[ci % 3].record(copy_stream)
+                        self.h2d_bytes += pk * row_elems * 2
+                    if raw:
+                        part = src[i:i + raw]
+                        if not pinned_src:
+                            pin[s_][:raw].copy_(part)
+                            part = pin[s_][:raw]
+                        dev[s_][:raw].copy_(part, non_blocking=True)
+                        self.h2d_bytes += raw * row_elems * src.element_size()
                     copied[s_].record(copy_stream)
                 main.wait_event(copied[s_])
                 if u8 is not None:
@@ -642,12 +775,16 @@ class D64Scorer:
                     consumed[s_].record(main)
                     score_chunk(x, ci, i, b)
                 else:
+                    if pk:
+                        L.check(lib.sg_f16_expand(_p(dev16[s_]), pk * row_elems, _p(dev[s_][raw:]), _stream()), "sg_f16_expand")
                     score_chunk(dev[s_][:b], ci, i, b)
                     consumed[s_].record(main)
-            if not pinned_src:
-                copied[(nchunks - 1) & 1].synchronize()   # the cached pinned buffers may be reused by the next call
+            if need_pin or frac > 0.0:
+                copy_stream.synchronize()   # the cached pinned buffers may be reused by the next call
         del lib
         self._resolve(status, images, outs, cb)
+        if tuned is not None:
+            tuned[0].report(tuned[1], n / max(time.perf_counter() - tuned[2], 1e-9))   # _resolve has synchronised
         return outs
 
     def _resolve(self, status: torch.Tensor, images, outs, cb: int):

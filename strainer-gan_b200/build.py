@@ -7,11 +7,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libstrainer_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "--threads", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
+    # *.cpp: host-only code (csrc/host_pack.cpp), handed to the host compiler by nvcc
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cpp")))
 
 
 def needs_build():

@@ -7,6 +7,8 @@
 //
 // A pixel has 256 possible values per channel: every CTA builds the [channels][256] fp32 table once (two IEEE
 // divisions per entry) and the streaming loop is one shared-memory look-up per element.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sg {
@@ -110,6 +112,32 @@ __global__ void __launch_bounds__(256) generic_kernel(const uint8_t* __restrict_
   }
 }
 
+// fp16 bits -> fp32 (exact): the device half of the host-packed PCIe copy (csrc/host_pack.cpp).  One thread = 8
+// elements: one 128-bit load, two 128-bit streaming stores; HBM bound (2 B read + 4 B written per element).
+__global__ void __launch_bounds__(256) f16_expand_kernel(const uint4* __restrict__ x, float* __restrict__ out, int64_t groups) {
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    uint4 q;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(x + g));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      const float2 f = __half22float2(h);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+    float* o = out + (g << 3);
+    stg_stream_f4(o, v[0], v[1], v[2], v[3]);
+    stg_stream_f4(o + 4, v[4], v[5], v[6], v[7]);
+  }
+}
+
+__global__ void __launch_bounds__(256) f16_expand_tail_kernel(const uint16_t* __restrict__ x, float* __restrict__ out, int64_t n) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = __half2float(__ushort_as_half(x[e]));
+}
+
 }  // namespace pix
 }  // namespace sg
 
@@ -160,5 +188,31 @@ extern "C" int sg_u8_normalize(const uint8_t* x, int64_t count, int channels, in
     generic_kernel<<<(int)blocks, 256, 0, st>>>(x, out, count, plane, channels, layout == SG_LAYOUT_NHWC, a);
   }
   SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+extern "C" int sg_f16_expand(const uint16_t* x, int64_t count, float* out, void* stream) {
+  using namespace sg::pix;
+  SG_READY();
+  SG_REQUIRE(count >= 0, "count");
+  if (count == 0) return SG_OK;
+  SG_REQUIRE(x != nullptr && out != nullptr, "null pointer");
+  cudaStream_t st = sg::as_stream(stream);
+  const int maxb = sg::state().sm_count * 8;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const int64_t groups = aligned ? count / 8 : 0;
+  if (groups > 0) {
+    int64_t blocks = sg::ceil_div(groups, 256);
+    if (blocks > maxb) blocks = maxb;
+    f16_expand_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), out, groups);
+    SG_LAUNCH_CHECK();
+  }
+  const int64_t rest = count - groups * 8;
+  if (rest > 0) {
+    int64_t blocks = sg::ceil_div(rest, 256);
+    if (blocks > maxb) blocks = maxb;
+    f16_expand_tail_kernel<<<(int)blocks, 256, 0, st>>>(x + groups * 8, out + groups * 8, rest);
+    SG_LAUNCH_CHECK();
+  }
   return SG_OK;
 }
