@@ -2,21 +2,18 @@
 // reconstruction-loss straining, 64x64 RGB, batch 512, bf16 conv mode"; reference "#autoencoder.py:269-291"
 // forward + ":315-316" per-sample MSE).
 //
-// 86 % of the auto-encoder's 46.6 MFLOP/sample sit in its two 7x7 layers; they run as implicit GEMMs on
-// tcgen05 (bf16 operands, fp32 accumulators in TMEM), the four small stride-2 layers (channels 3/16/32) stay
-// on the CUDA cores.  All activations are bf16 NHWC so that a filter tap of a pixel tile is one TMA box:
+// 86 % of the auto-encoder's 46.6 MFLOP/sample sit in its two 7x7 layers.  Every layer of the single-segment modes (bf16 /
+// fp16 operands, fp32 accumulators in TMEM) is a tcgen05 kernel; activations are 16-bit:
 //
-//   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> bf16 [32][32][16]            CUDA cores
-//   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> bf16 [16][16][32]                         CUDA cores
-//   L3 enc Conv 32->64 k7                -> bf16 [10][10][64]     tcgen05: M = the 100 output pixels of one image
-//        (rows 100..127 of the 128-row tile are dead), N = 64, K-step = two horizontally adjacent taps x 32
-//        channels = 64 contiguous bf16 of the NHWC input (an overlapping-stride TMA view), 7 x 4 K-steps
-//        (the 8th tap of a row has zero weights)
-//   L4 dec ConvT 64->32 k7 + ReLU        -> bf16 [16][16][32]     tcgen05, gather form: M = 128 output pixels
-//        (half an image), N = 32, K-step = one tap x 64 channels, 49 K-steps; input coordinates outside the
-//        10x10 map (negative too) are TMA zero fill
-//   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> bf16 [32][32][16]  CUDA cores, one 2x2 output quad per thread
-//   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)
+//   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> [32][32][16]             ae_enc1_tc_kernel (input conversion fused)
+//   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> [ci / 8][16 x 16][8]                   ae_enc2_tc_kernel (stride-2 TMA boxes)
+//   L3 enc Conv 32->64 k7                -> [co / 8][10 x 10][8]                   ae_k7x_kernel<false>: shifted-window form
+//   L4 dec ConvT 64->32 k7 + ReLU        -> [16][16][32]                           ae_k7x_kernel<true>
+//   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> [32][32][16]                        ae_dec2_tc_kernel
+//   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)   ae_dec3_tc_kernel
+//
+// The fp32-parity mode (SEG = 2: every activation as bf16 hi | lo, three tensor passes) keeps the gather forms of the 7x7
+// layers (ae_k7_kernel, ae_dec1_kernel) and CUDA-core small layers.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -50,6 +47,9 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // SEG = 1: bf16 conv mode.  SEG = 2: fp32-parity mode on the same kernels -- every activation is stored as bf16
 // hi | lo (x = hi + lo to ~2^-17), the 7x7 GEMMs run x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the small layers add hi + lo
 // on load and split on store.
+// Every CTA streams the same 7x7 weight stages in the same order: 148 SMs asking one L2 slice for one line at one time.
+// The packed weights are replicated and CTA b reads replica b % kWeightCopies (3.6 MB in all, L2 resident).
+constexpr int kWeightCopies = 8;
 struct Layout {
   size_t flag, w1, w2, w5, w6, w3, w4, w3t, w4t, a1, a2, a3, a4, a5, part, total;
 };
@@ -63,8 +63,8 @@ static Layout layout(int64_t batch, int seg) {
   L.w6 = o; o += align_up((size_t)16 * 144 * 2, 1024);   // dec3 weights, 16-bit [oc (3 of 16)][tap*16 + ic] (tensor-core form)
   L.w3 = o; o += align_up((size_t)64 * (seg == 2 ? kKs3Split : kKs3) * 64 * 2, 1024);
   L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
-  L.w3t = o; o += align_up((size_t)4 * 7 * 128 * 32 * 2, 1024);   // row-tap forms of the 7x7 weights (single-segment modes)
-  L.w4t = o; o += align_up((size_t)2 * 7 * 128 * 64 * 2, 1024);
+  L.w3t = o; o += align_up((size_t)kWeightCopies * 4 * 7 * 128 * 32 * 2, 1024);   // shifted-window forms of the 7x7 weights
+  L.w4t = o; o += align_up((size_t)kWeightCopies * 2 * 7 * 128 * 64 * 2, 1024);   // (single-segment modes), kWeightCopies replicas
   L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
   L.a2 = o; o += align_up(kAct2 * seg * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
   L.a3 = o; o += align_up(kAct3 * seg * batch, 1024);
@@ -454,55 +454,83 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// The two 7x7 layers in ROW-TAP form (single-segment modes).  The gather forms above pay either TMA service (enc3: the
-// 12.8 KB input window is fetched once per K-step, 28 x per image) or shared-memory operand bandwidth (dec1: N = 32
-// MMAs read 5 KB of operands for 16 cycles of tensor work).  Here the seven COLUMN taps kx move from the contraction
-// onto the N side of the GEMM and the column shift is undone in the epilogue:
+// The two 7x7 layers in SHIFTED-WINDOW form (single-segment modes; replaced a row-tap form -- column taps stacked on N,
+// a half-warp shuffle col2im of 448 / 224 accumulator values per thread -- that ran at 438 / 357 us per 8 192 images with the
+// tensor pipe 49 % / 60 % active; this form: 229 / 271 us, 67 % / 92 %).  The GEMM is transposed -- the WEIGHTS are the M operand,
+// the image's pixels are the N operand -- and the image sits in shared memory ONCE, in the un-swizzled core-matrix
+// layout [ci / 8][pixel][8 ci] (16 bytes per pixel and channel group, pixels at a pitch of 16 columns).  In that layout
+// the operand of filter tap (ky, kx) is the same copy at a start address shifted by ky * 16 + kx pixels: a descriptor
+// offset of 16 bytes per pixel, nothing is re-fetched or re-arranged per tap.  Column m of the accumulator is the
+// linearised pixel index, so a COLUMN shift of the filter is a shift along the accumulator's columns:
 //
-//   enc3  T[(oy, ix), (kx, co)] = sum_{ky, ci} in[oy + ky][ix][ci] * w[co][ci][ky][kx]     out[oy][ox] = sum_kx T[(oy, ox + kx), kx]
-//   dec1  T[(oy, ix), (kx, co)] = sum_{ky, ci} in[oy - ky][ix][ci] * w[ci][co][ky][kx]     out[oy][ox] = sum_kx T[(oy, ox - kx), kx]
+//   enc3  D[(kxl, co)][m] = sum_{c, ky, ci} w[co][ci][ky][2c + kxl] * in[m + 16 ky + 2c][ci]     out[co][n] = D[(0, co)][n] + D[(1, co)][n + 1]
+//   dec1  D[(kxl, co)][m] = sum_{c, ky, ci} w[ci][co][ky][4c + kxl] * pad[m - 16 ky - 4c + 112][ci]   out[co][n] = sum_kxl D[(kxl, co)][n - kxl]
 //
-// M rows are (row oy, INPUT column ix) at a pitch of 16 columns, so the A operand of row tap ky is the image's ONE
-// shared-memory copy shifted by whole 16-pixel rows (a swizzle-atom-aligned descriptor offset): the input is loaded
-// once per image, nothing is re-fetched per tap.  N = (kx, co) is cut into chunks of 128 columns (2 kx x 64 co for
-// enc3, 4 kx x 32 co for dec1): M128 x N128 x K16 MMAs read 8 KB of operands for 64 tensor cycles, i.e. the tensor
-// pipe, not shared memory, is the bound; a weight stage (one chunk, one ky: 8 / 16 KB) serves both 128-row tiles of
-// the image.  The column shift is a width-16 warp shuffle (an output pixel and the seven input columns it sums over
-// sit in the same half warp), accumulated in registers across the chunks: no col2im pass, no atomics, fixed order.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: epilogue of tile 0 (rows oy 0..7) | warps 6-9: tile 1
+// (pad: the 10 x 10 input at rows 7..16 of a 23 x 16 zero field -- columns 10..15 of a row are at once its right padding
+// and the next row's left padding, so the flattened 1-D convolution equals the 2-D one; TMA's out-of-bounds zero fill
+// writes the field.)  M = 128 rows = 2 (enc3) / 4 (dec1) column taps x C_out, N = 160 (the 10 output rows of enc3) /
+// 256 pixels, K = 16: 56 MMAs per image accumulate ALL taps in the tensor core.  Accumulator row = co * taps + kxl, so the
+// rows of one output channel are adjacent lanes of one epilogue warp and the remaining sum over kxl is one (enc3) / two
+// (dec1) shfl.xor exchanges per output -- 160 / 256 TMEM values per thread and image, no shared-memory pass, no barrier.
+// M128 x N256 x K16 reads 12 KB of operands for 128 tensor cycles (96 B/clk): the tensor pipe is the bound.
+//   warp 0: TMA producer, weight stages (one dense 8 / 16 KB box per (c, ky); enc3 keeps 14 of its 28 stages resident)
+//   warp 6: TMA producer, images (one dense box per image: the layers before write the [ci / 8][pixel][8] form)
+//   warp 1: MMA issuer (stage loop fully unrolled: ~10 instructions per MMA)
+//   warps 2-5: epilogue (TMEM -> lane exchanges -> bias (+ ReLU) -> 16-bit staging -> 16-byte global stores)
 // ------------------------------------------------------------------------------------------
 template <bool CONVT>
-struct K7TCfg {
+struct K7XCfg {
   static constexpr int kCin = CONVT ? 64 : 32, kCout = CONVT ? 32 : 64;
-  static constexpr int kRowB = kCin * 2;                       // operand row: one pixel's channels (SW128 / SW64)
-  static constexpr int kKxPerChunk = CONVT ? 4 : 2, kChunks = CONVT ? 2 : 4;
-  static constexpr int kK16 = kCin / 16;
-  static constexpr int kSlotRows = 22;                         // enc3: 16 input rows + 6 rows only dead outputs read;
-  static constexpr int kSlotBytes = kSlotRows * 16 * kRowB;    // dec1: 6 zero rows | 10 input rows | 6 zero rows
-  static constexpr int kLoadBytes = (CONVT ? 10 : 16) * 16 * kRowB;
+  static constexpr int kGroups = kCin / 8;                      // channel groups of 8 (one core-matrix column each)
+  static constexpr int kTaps = 128 / kCout;                     // column taps stacked on M: 2 (enc3) / 4 (dec1)
+  static constexpr int kChunks = CONVT ? 2 : 4;                 // kx = chunk * kTaps + kxl (kx == 7: zero weights)
+  static constexpr int kStagesPerImage = kChunks * 7;
+  static constexpr int kPixels = CONVT ? 23 * 16 : 256;         // pixels per channel group in a slot
+  static constexpr int kLboB = kPixels * 16;                    // operand B: bytes between channel groups
+  static constexpr int kSlotBytes = kGroups * kLboB;            // 16 384 / 47 104
   static constexpr int kSlots = 2;
-  static constexpr int kBBytes = 128 * kRowB;                  // one (chunk, ky) weight stage
-  // a stage is consumed in 256 (enc3) / 512 (dec1) tensor cycles, an L2 -> shared-memory TMA takes ~1.5 k cycles to land:
-  // 128 KB of weight stages in flight keep the issuer fed (4 stages left it latency bound: 0.45 ms per 8192 images)
-  static constexpr int kBStages = CONVT ? 8 : 16;
-  static constexpr int kTmemCols = 512;                        // 2 accumulators x (2 tiles x 128 columns)
-  static constexpr int kThreads = 320;
+  static constexpr int kN = CONVT ? 256 : 160;                  // accumulator columns (enc3: output rows 0..9 only)
+  static constexpr int kSteps = kN / 32;
+  static constexpr int kLboA = 128 * 16;                        // operand A: bytes between channel groups of a stage
+  static constexpr int kBBytes = kGroups * kLboA;               // one (chunk, ky) weight stage: 8 / 16 KB
+  // all 148 SMs stream the same 224 KB of weights per image: at ~6 us per image that is the whole L2 -> SM bandwidth
+  // (5.3-6.1 TB/s measured), not the tensor pipe.  enc3 keeps the stages of its first two chunks RESIDENT in shared
+  // memory (loaded once per CTA) and streams only the other half.
+  static constexpr int kResident = CONVT ? 0 : 14;
+  static constexpr int kBStages = CONVT ? 5 : 6;
+  static constexpr int kK16 = kCin / 16;
+  static constexpr int kOutPixels = CONVT ? 256 : 100;
+  static constexpr int kStgBytes = kOutPixels * kCout * 2;      // one image's output block (NHWC); two staging buffers
+  static constexpr int kTmemCols = 512;                         // 2 accumulators x 256 columns
+  static constexpr int kThreads = 224;                          // + warp 6: image producer
   static constexpr int kBarBytes = 512;
-  static constexpr int kSmemBytes = kSlots * kSlotBytes + kBStages * kBBytes + kBarBytes + 256 + 1024;
+  static constexpr int kSpill = 2048;                           // enc3 reads up to 102 pixels past a channel group
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + kSpill + (kResident + kBStages) * kBBytes + 2 * kStgBytes +
+                                    kBarBytes + 256 + 1024;
+  static_assert(kSmemBytes <= 232448, "shared memory");
 };
 
+// K-major operand WITHOUT swizzle: core matrices of 8 rows x 16 bytes (128 contiguous bytes); SBO = bytes between 8-row
+// groups, LBO = bytes between the two core matrices of a K = 16 step (layout type 0).
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+
 template <bool CONVT, bool HALF>
-__global__ void __launch_bounds__(320, 1)
-ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+__global__ void __launch_bounds__(224, 1)
+ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
-  using Cfg = K7TCfg<CONVT>;
+  using Cfg = K7XCfg<CONVT>;
   constexpr int UA = Cfg::kSlots, SB = Cfg::kBStages, COUT = Cfg::kCout;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t b_base = base + UA * Cfg::kSlotBytes;
-  const uint32_t bar0 = b_base + SB * Cfg::kBBytes;
+  const uint32_t r_base = base + UA * Cfg::kSlotBytes + Cfg::kSpill;      // resident weight stages
+  const uint32_t b_base = r_base + Cfg::kResident * Cfg::kBBytes;         // ring of streamed weight stages
+  const uint32_t g_base = b_base + SB * Cfg::kBBytes;
+  const uint32_t bar0 = g_base + 2 * Cfg::kStgBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
   auto afull_bar = [&](int s) { return bar0 + 8u * s; };
   auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
@@ -510,7 +538,8 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   auto bempty_bar = [&](int s) { return bar0 + 8u * (2 * UA + SB + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + 2 + a); };
-  constexpr int kNb = 2 * UA + 2 * SB + 4;
+  constexpr int kNb = 2 * UA + 2 * SB + 5;
+  const uint32_t wres_bar = bar0 + 8u * (kNb - 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
   volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
   static_assert((kNb + 2) * 8 <= Cfg::kBarBytes, "barrier block too small");
@@ -522,14 +551,16 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     prefetch_tensormap(&tmap_b);
     for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wres_bar, 1);
     *s_abort = 0;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
-  // rows of the slots TMA never writes: the zero padding of the transposed conv / rows only dead outputs read
-  for (int i = threadIdx.x; i < UA * Cfg::kSlotBytes / 16; i += Cfg::kThreads)
+  // operand memory starts finite: enc3's windows run up to 102 pixels past a channel group (into the next group, the next
+  // slot or the first weight stage); those products only reach dead columns or meet zero weights, and 0 x finite = 0
+  for (int i = threadIdx.x; i < (int)((g_base - base) / 16); i += Cfg::kThreads)
     *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -538,138 +569,170 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer: weight stages =================
     if (lane == 0) {
-      int aslot = 0, bstage = 0;
-      uint32_t aphase = 0, bphase = 0;
+      int bstage = 0;
+      uint32_t bphase = 0;
       bool ok = true;
+      const int row0 = (int)(blockIdx.x % kWeightCopies) * Cfg::kStagesPerImage * (Cfg::kBBytes / 128);   // this CTA's replica
+      if (Cfg::kResident > 0) {
+        mbar_arrive_expect_tx(wres_bar, Cfg::kResident * Cfg::kBBytes);
+        for (int s = 0; s < Cfg::kResident; ++s)
+          tma_load_2d(r_base + s * Cfg::kBBytes, &tmap_b, wres_bar, 0, row0 + s * (Cfg::kBBytes / 128));
+      }
       for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
-        if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 21)) break;
-        mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kLoadBytes);
-        // enc3: the 16 x 16 input; dec1: the 10 input rows at slot rows 6..15, columns 10..15 zero-filled by TMA
-        tma_load_4d(base + aslot * Cfg::kSlotBytes + (CONVT ? 6 * 16 * Cfg::kRowB : 0), &tmap_a, afull_bar(aslot), 0, 0, 0, img);
-        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
-        for (int s = 0; s < Cfg::kChunks * 7 && ok; ++s) {     // s = chunk * 7 + ky
-          if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 22)) { ok = false; break; }
+        for (int s = Cfg::kResident; s < Cfg::kStagesPerImage && ok; ++s) {     // s = chunk * 7 + ky
+          if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 32)) { ok = false; break; }
           mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
-          tma_load_2d(b_base + bstage * Cfg::kBBytes, &tmap_b, bfull_bar(bstage), 0, s * 128);
+          tma_load_2d(b_base + bstage * Cfg::kBBytes, &tmap_b, bfull_bar(bstage), 0, row0 + s * (Cfg::kBBytes / 128));
           if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
         }
+      }
+    }
+  } else if (warp == 6) {
+    // ================= TMA producer: images (its own warp, so that an image is requested as soon as its slot is free
+    // and never queues behind weight stages the ring has no room for yet) =================
+    if (lane == 0) {
+      int aslot = 0;
+      uint32_t aphase = 0;
+      for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
+        if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 31)) break;
+        mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kSlotBytes);
+        // one dense box: [ci / 8][pixels][8 ci]; dec1: rows -7..15 of 16 pixels, everything outside the 10 x 10 map zero-filled
+        if (CONVT) tma_load_4d(base + aslot * Cfg::kSlotBytes, &tmap_a, afull_bar(aslot), 0, -7, 0, img);
+        else tma_load_4d(base + aslot * Cfg::kSlotBytes, &tmap_a, afull_bar(aslot), 0, 0, 0, img);
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(128, Cfg::kN, HALF);
       int aslot = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, acc_phase = 0;
       bool ok = true;
+      if (Cfg::kResident > 0) ok = mbar_wait(wres_bar, 0, s_abort, err, kErrBase + 37);
+      // One thread issues 56 MMAs of 82 (enc3) / 128 (dec1) tensor cycles per image: the instruction stream between two
+      // MMAs has to be shorter than that.  The loop over the stages is fully unrolled, every tap offset is a constant added
+      // to a base descriptor (the address field holds bytes >> 4 and never carries out of its 14 bits).  With a rolled
+      // loop and descriptors rebuilt per stage the issuer needed ~400 cycles per stage and the tensor pipe idled 55-65 %.
+      const uint64_t res_desc = umma_desc_nosw(r_base, Cfg::kLboA, 128);
       for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
-        if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 23)) break;
+        if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 33)) break;
+        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 34)) break;
         tc_fence_after();
-        const uint32_t ca = base + aslot * Cfg::kSlotBytes;
-        for (int c = 0; c < Cfg::kChunks && ok; ++c) {
-          const int nkx = (7 - c * Cfg::kKxPerChunk) < Cfg::kKxPerChunk ? (7 - c * Cfg::kKxPerChunk) : Cfg::kKxPerChunk;
-          const uint32_t idesc = umma_idesc_16(128, nkx * COUT, HALF);
-          if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 24)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-          uint32_t first = 0;
-          for (int ky = 0; ky < 7 && ok; ++ky) {
-            if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 25)) { ok = false; break; }
-            tc_fence_after();
-            // tile t covers output rows 8t .. 8t+7: enc3 reads input rows oy + ky, dec1 padded rows oy - ky + 6
-            const uint32_t r0 = (uint32_t)(CONVT ? 6 - ky : ky), rowpx = 16u * Cfg::kRowB;
-            uint64_t a0, a1, bd;
-            if (CONVT) {
-              a0 = umma_desc_sw128(ca + r0 * rowpx); a1 = umma_desc_sw128(ca + (r0 + 8) * rowpx);
-              bd = umma_desc_sw128(b_base + bstage * Cfg::kBBytes);
-            } else {
-              a0 = umma_desc_sw64(ca + r0 * rowpx); a1 = umma_desc_sw64(ca + (r0 + 8) * rowpx);
-              bd = umma_desc_sw64(b_base + bstage * Cfg::kBBytes);
-            }
+        const uint64_t img_desc = umma_desc_nosw(base + aslot * Cfg::kSlotBytes, Cfg::kLboB, 128);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
 #pragma unroll
-            for (int k = 0; k < Cfg::kK16; ++k) {
-              umma_f16(tmem_d, a0 + 2 * k, bd + 2 * k, idesc, first);
-              umma_f16(tmem_d + 128, a1 + 2 * k, bd + 2 * k, idesc, first);
-              first = 1u;
-            }
+        for (int s = 0; s < Cfg::kStagesPerImage; ++s) {
+          const int c = s / 7, ky = s % 7;
+          const int px = CONVT ? (112 - 16 * ky - Cfg::kTaps * c) : (16 * ky + Cfg::kTaps * c);
+          uint64_t wdesc;
+          if (s >= Cfg::kResident) {
+            if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 35)) { ok = false; break; }
+            tc_fence_after();
+            wdesc = umma_desc_nosw(b_base + bstage * Cfg::kBBytes, Cfg::kLboA, 128);
+          } else {
+            wdesc = res_desc + (uint64_t)((s * Cfg::kBBytes) >> 4);
+          }
+#pragma unroll
+          for (int k = 0; k < Cfg::kK16; ++k)
+            umma_f16(tmem_d, wdesc + (uint64_t)((2 * k * Cfg::kLboA) >> 4), img_desc + (uint64_t)((px * 16 + 2 * k * Cfg::kLboB) >> 4),
+                     idesc, (uint32_t)((s | k) != 0));
+          if (s >= Cfg::kResident) {
             umma_commit(bempty_bar(bstage));
             if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
           }
-          if (!ok) break;
-          umma_commit(tfull_bar(acc));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (!ok) break;
+        umma_commit(tfull_bar(acc));
         umma_commit(aempty_bar(aslot));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
       }
     }
-  } else {
-    // ================= epilogue: column-tap sums by half-warp shuffles, bias (+ ReLU), 16-bit store =================
-    const int q = warp & 3;                      // TMEM lane quadrant of this warp
-    const int tile = (warp - 2) >> 2;            // warps 2..5: rows 0..7, warps 6..9: rows 8..15
-    const int oy = tile * 8 + 2 * q + (lane >> 4), ix = lane & 15;
-    int acc = 0;
+  } else if (warp >= 2 && warp <= 5) {
+    // ================= epilogue =================
+    // Accumulator row = co * taps + kxl: the rows of one output channel are ADJACENT LANES of one warp, so the sum over
+    // kxl is a lane exchange (shfl.xor) between 2 (enc3) / 4 (dec1) neighbours -- no shared-memory pass, no barriers.
+    // Each lane of a group finishes every 2nd / 4th output position of its channel.
+    const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int L = q * 32 + lane;                      // accumulator row
+    const int kxl = L % Cfg::kTaps, co = L / Cfg::kTaps;
+    const int t = threadIdx.x - 64;                   // 0..127
+    const float my_bias = s_bias[co];
+    int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
     for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
-      float o[COUT];
-#pragma unroll
-      for (int j = 0; j < COUT; ++j) o[j] = s_bias[j];
-      bool ok = true;
-      // fully unrolled over (chunk, kx): the shuffle distance is an immediate (a register distance made SHFL the
-      // bound of the whole kernel: 96 % XU utilisation, tensor pipe 49 % active)
-#pragma unroll
-      for (int c = 0; c < Cfg::kChunks; ++c) {
-        if (!ok) break;
-        if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 26)) { ok = false; break; }
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + tile * 128);
-#pragma unroll
-        for (int kl = 0; kl < Cfg::kKxPerChunk; ++kl) {
-          const int kx = c * Cfg::kKxPerChunk + kl;
-          if (kx >= 7) break;
-#pragma unroll
-          for (int cb = 0; cb < COUT; cb += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + (uint32_t)(kl * COUT + cb), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float t = __uint_as_float(v[j]);
-              if (kx > 0) {
-                if (CONVT) {      // out[oy][ox] += T[(oy, ox - kx)][kx]: from the lane kx to the left (none: zero)
-                  const float u = __shfl_up_sync(0xffffffffu, t, (unsigned)kx, 16);
-                  t = (ix >= kx) ? u : 0.f;
-                } else {          // out[oy][ox] += T[(oy, ox + kx)][kx]: from the lane kx to the right (dead lanes: own value)
-                  t = __shfl_down_sync(0xffffffffu, t, (unsigned)kx, 16);
-                }
-              }
-              o[cb + j] += t;
-            }
-          }
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 36)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      uint16_t* stg = reinterpret_cast<uint16_t*>(smem + (g_base - base) + buf * Cfg::kStgBytes);
+      float c1 = 0.f, c2 = 0.f, c3 = 0.f;             // this lane's columns 32 j - 1, - 2, - 3
+#pragma unroll 1
+      for (int j = 0; j < Cfg::kSteps; ++j) {
+        uint32_t u[32];
+        tmem_ld_32x32(taddr + (uint32_t)(32 * j), u);
+        tmem_ld_wait();
+        if (j == Cfg::kSteps - 1) {                   // the accumulator is free once its last columns are in registers
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
         }
-        tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-      if (!ok) break;
-      const bool valid = CONVT ? true : (oy < 10 && ix < 10);
-      if (valid) {
-        const size_t px = CONVT ? ((size_t)img * 256 + oy * 16 + ix) : ((size_t)img * 100 + oy * 10 + ix);
-        uint4* d = reinterpret_cast<uint4*>(out + px * COUT);
+        float v[32];
 #pragma unroll
-        for (int g = 0; g < COUT / 8; ++g) {
-          uint32_t pk[4];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+        if (CONVT) {
+          // out[n] = sum_g D_g[n - g] over the four lanes g of a group, as a two-level butterfly without divergence:
+          //   level 1 (lanes g ^ 1): P01[c] = D_0[c] + D_1[c - 1], P23[c] = D_2[c] + D_3[c - 1]; the even lane of a pair
+          //     finishes the even columns, the odd lane the odd ones -- for both the own term is v[i] and the partner's
+          //     term is what ONE exchange delivers (the odd lane sends v[i - 1], the even lane v[i + 1]);
+          //   level 2 (lanes g ^ 2): out[n] = P01[n] + P23[n - 2]; lane g finishes n = 4 k + g, own term p[2 k], the
+          //     partner sends p[2 k - 1] (lanes 2, 3) or p[2 k + 1] (lanes 0, 1).
+          const bool odd = (kxl & 1) != 0, hi = (kxl & 2) != 0;
+          float pp[16];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            float a = o[8 * g + 2 * h], b = o[8 * g + 2 * h + 1];
-            if (CONVT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }     // ReLU follows the decoder's first layer only
-            pk[h] = pk2<HALF>(a, b);
+          for (int t2 = 0; t2 < 16; ++t2) {
+            const int i = 2 * t2;                                   // this lane's own column: i (even lane) / i + 1 (odd lane)
+            const float below = t2 == 0 ? c1 : v[t2 == 0 ? 0 : i - 1];
+            const float send = odd ? below : v[i + 1];
+            // even lane: P[i] = v[i] + odd's v[i - 1];   odd lane: P[i + 1] = v[i] (own column i + 1 - 1) + even's v[i + 1]
+            pp[t2] = v[i] + __shfl_xor_sync(0xffffffffu, send, 1);
           }
-          d[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float before = k == 0 ? c2 : pp[k == 0 ? 0 : 2 * k - 1];
+            const float send = hi ? before : pp[2 * k + 1];
+            const float a = my_bias + pp[2 * k] + __shfl_xor_sync(0xffffffffu, send, 2);
+            const int n = 32 * j + 4 * k + kxl;
+            stg[n * 32 + co] = pk1<HALF>(fmaxf(a, 0.f));              // ReLU follows the decoder's first layer
+          }
+          c1 = v[31]; c2 = pp[15];
+          (void)c3;
+        } else {
+          // out[n] = D_0[n] + D_1[n + 1]; one exchange of column 2 k serves both lanes of a pair: the even lane finishes
+          // n = 32 j + 2 k - 1 (own column 2 k - 1), the odd lane n = 32 j + 2 k (own column 2 k + 1)
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float x = __shfl_xor_sync(0xffffffffu, v[2 * k], 1);
+            const float prev = k == 0 ? c1 : v[k == 0 ? 0 : 2 * k - 1];
+            const float own = kxl ? v[2 * k + 1] : prev;
+            const int n = 32 * j + 2 * k - 1 + kxl;
+            const int oy = n >> 4, ox = n & 15;
+            // a3 in channel-group-major form [img][co / 8][100 pixels][8 co] (dec1's operand layout)
+            if (n >= 0 && oy < 10 && ox < 10) stg[((co >> 3) * 100 + oy * 10 + ox) * 8 + (co & 7)] = pk1<HALF>(my_bias + own + x);
+          }
+          c1 = v[31];
         }
       }
+      named_bar_sync(1, 128);
+      // the image's output block is contiguous in global memory (NHWC): 16-byte stores
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(stg);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)img * Cfg::kOutPixels * COUT);
+        for (int i = t; i < Cfg::kStgBytes / 16; i += 128) dst[i] = src[i];
+      }
+      buf ^= 1;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -680,54 +743,55 @@ ae_k7t_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   }
 }
 
-// row-tap weight layouts: [chunk][ky][n = kxl * COUT + co][ci], kx = chunk * kKxPerChunk + kxl (kx >= 7: zero rows)
+// shifted-window weight layouts: stage s = chunk * 7 + ky, [ci / 8][row = co * taps + kxl][ci % 8], kx = chunk * taps + kxl
 //   enc3: w3 [co 64][ci 32][ky][kx] (Conv2d)            dec1: w4 [ci 64][co 32][ky][kx] (ConvTranspose2d)
 template <bool HALF>
-__global__ void pack_k7t_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
+__global__ void pack_k7x_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
                                 __nv_bfloat16* __restrict__ p4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   auto cvt = [](float v) { return __ushort_as_bfloat16(pk1<HALF>(v)); };   // HALF: fp16 bits carried in the bf16 type
-  if (i < 4 * 7 * 128 * 32) {
-    const int ci = i & 31, n = (i >> 5) & 127, s = i >> 12;          // s = chunk * 7 + ky
-    const int ky = s % 7, kx = (s / 7) * 2 + (n >> 6), co = n & 63;
+  if (i < 28 * 4096) {
+    const int e = i & 7, row = (i >> 3) & 127, g = (i >> 10) & 3, s = i >> 12;
+    const int ci = g * 8 + e, ky = s % 7, kx = (s / 7) * 2 + (row & 1), co = row >> 1;
     p3[i] = cvt(kx < 7 ? w3[((co * 32 + ci) * 7 + ky) * 7 + kx] : 0.f);
   }
-  if (i < 2 * 7 * 128 * 64) {
-    const int ci = i & 63, n = (i >> 6) & 127, s = i >> 13;
-    const int ky = s % 7, kx = (s / 7) * 4 + (n >> 5), co = n & 31;
+  if (i < 14 * 8192) {
+    const int e = i & 7, row = (i >> 3) & 127, g = (i >> 10) & 7, s = i >> 13;
+    const int ci = g * 8 + e, ky = s % 7, kx = (s / 7) * 4 + (row & 3), co = row >> 2;
     p4[i] = cvt(kx < 7 ? w4[((ci * 32 + co) * 7 + ky) * 7 + kx] : 0.f);
   }
 }
 
 template <bool CONVT, bool HALF>
-static int launch_k7t(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
+static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
                       int64_t batch, int* err, cudaStream_t st) {
-  using Cfg = K7TCfg<CONVT>;
+  using Cfg = K7XCfg<CONVT>;
   CUtensorMap ta, tb;
   int r;
   if (CONVT) {
-    // a3 [n][10][10][64]: the 10 input rows, 16 columns from 0 (columns 10..15: TMA zero fill)
-    cuuint64_t dims[4] = {64, 10, 10, (cuuint64_t)batch};
-    cuuint64_t strides[3] = {128, 1280, 12800};
-    cuuint32_t box[4] = {64, 16, 10, 1};
-    r = encode_tmap(&ta, 4, act_in, dims, strides, box);
+    // a3 [n][8 groups][10 rows][10 px x 8 ci]: a box row = 16 pixels (256 B, pixels 10..15 zero fill), 23 rows from -7
+    cuuint64_t dims[4] = {80, 10, 8, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {160, 1600, 12800};
+    cuuint32_t box[4] = {128, 23, 8, 1};
+    r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   } else {
-    // a2 [n][16][16][32]: one whole image, 64-byte operand rows
-    cuuint64_t dims[4] = {32, 16, 16, (cuuint64_t)batch};
-    cuuint64_t strides[3] = {64, 1024, 16384};
-    cuuint32_t box[4] = {32, 16, 16, 1};
-    r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    // a2 [n][4 groups][16 rows][16 px x 8 ci]: the whole image, 64 rows of 256 B
+    cuuint64_t dims[4] = {128, 16, 4, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {256, 4096, 16384};
+    cuuint32_t box[4] = {128, 16, 4, 1};
+    r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   if (r != SG_OK) return r;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Cfg::kCin, (cuuint64_t)Cfg::kChunks * 7 * 128};
-    cuuint64_t strides[1] = {(cuuint64_t)Cfg::kRowB};
-    cuuint32_t box[2] = {(cuuint32_t)Cfg::kCin, 128};
-    r = encode_tmap(&tb, 2, wpk, dims, strides, box, CONVT ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    // the packed stages as rows of 128 bytes: a dense copy of one stage
+    cuuint64_t dims[2] = {64, (cuuint64_t)kWeightCopies * Cfg::kStagesPerImage * (Cfg::kBBytes / 128)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)(Cfg::kBBytes / 128)};
+    r = encode_tmap(&tb, 2, wpk, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (r != SG_OK) return r;
   }
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-  ae_k7t_kernel<CONVT, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err);
+  ae_k7x_kernel<CONVT, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1029,7 +1093,9 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int img = tile >> 1;
-      __nv_bfloat16* dst = out + ((size_t)img * 256 + (tile & 1) * 128 + row) * 32;
+      // a2 in channel-group-major form [img][ci / 8][256 pixels][8 ci]: the layout the 7x7 kernel's operand has in shared
+      // memory (one dense TMA box per image), and 512 contiguous bytes per warp and store
+      __nv_bfloat16* dst = out + (size_t)img * 8192 + (size_t)((tile & 1) * 128 + row) * 8;
       if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 14)) break;
       tc_fence_after();
       uint32_t v[32];
@@ -1047,7 +1113,7 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (img < n_img) {
         uint4* d = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) d[q * 256] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -1761,7 +1827,14 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   if (do_pack) {
     // the weight blocks sit in front of the activations: their offsets do not depend on the batch size
     SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
-    if constexpr (SEG == 1) pack_k7t_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
+    if constexpr (SEG == 1) {
+      pack_k7x_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
+      SG_LAUNCH_CHECK();
+      for (int c = 1; c < kWeightCopies; ++c) {
+        SG_CUDA(cudaMemcpyAsync(ws + L.w3t + (size_t)c * 229376, ws + L.w3t, 229376, cudaMemcpyDeviceToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(ws + L.w4t + (size_t)c * 229376, ws + L.w4t, 229376, cudaMemcpyDeviceToDevice, st));
+      }
+    }
     else pack_k7_kernel<SEG, HALF><<<(64 * kKs3Split * 64 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3), bf(L.w4));
     SG_LAUNCH_CHECK();
     if constexpr (SEG == 1) {
@@ -1823,10 +1896,10 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   SG_LAUNCH_CHECK();
   int r;
   if constexpr (SEG == 1) {
-    // single-segment modes: both 7x7 layers in row-tap form (input resident in shared memory, column taps on N)
-    r = launch_k7t<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
+    // single-segment modes: both 7x7 layers in shifted-window form (weights on M, the image's pixels on N, taps = descriptor offsets)
+    r = launch_k7x<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
     if (r != SG_OK) return r;
-    r = launch_k7t<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
+    r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
     if (r != SG_OK) return r;
   } else {
     r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
@@ -1911,10 +1984,10 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<false>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<false>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7t_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7TCfg<true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   return SG_OK;
 }
 
