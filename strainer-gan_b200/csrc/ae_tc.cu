@@ -497,6 +497,9 @@ struct K7XCfg {
   // (5.3-6.1 TB/s measured), not the tensor pipe.  enc3 keeps the stages of its first two chunks RESIDENT in shared
   // memory (loaded once per CTA) and streams only the other half.
   static constexpr int kResident = CONVT ? 0 : 14;
+  // (resident = the FIRST stages of an image: alternating resident / streamed stages was slower, 252 against 229 us)
+  __host__ __device__ static constexpr bool resident(int s) { return s < kResident; }
+  __host__ __device__ static constexpr int resident_index(int s) { return s; }
   static constexpr int kBStages = CONVT ? 5 : 6;
   static constexpr int kK16 = kCin / 16;
   static constexpr int kOutPixels = CONVT ? 256 : 100;
@@ -577,11 +580,13 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       const int row0 = (int)(blockIdx.x % kWeightCopies) * Cfg::kStagesPerImage * (Cfg::kBBytes / 128);   // this CTA's replica
       if (Cfg::kResident > 0) {
         mbar_arrive_expect_tx(wres_bar, Cfg::kResident * Cfg::kBBytes);
-        for (int s = 0; s < Cfg::kResident; ++s)
-          tma_load_2d(r_base + s * Cfg::kBBytes, &tmap_b, wres_bar, 0, row0 + s * (Cfg::kBBytes / 128));
+        for (int s = 0; s < Cfg::kStagesPerImage; ++s)
+          if (Cfg::resident(s))
+            tma_load_2d(r_base + Cfg::resident_index(s) * Cfg::kBBytes, &tmap_b, wres_bar, 0, row0 + s * (Cfg::kBBytes / 128));
       }
       for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
-        for (int s = Cfg::kResident; s < Cfg::kStagesPerImage && ok; ++s) {     // s = chunk * 7 + ky
+        for (int s = 0; s < Cfg::kStagesPerImage && ok; ++s) {     // s = chunk * 7 + ky
+          if (Cfg::resident(s)) continue;
           if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 32)) { ok = false; break; }
           mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
           tma_load_2d(b_base + bstage * Cfg::kBBytes, &tmap_b, bfull_bar(bstage), 0, row0 + s * (Cfg::kBBytes / 128));
@@ -628,18 +633,18 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           const int c = s / 7, ky = s % 7;
           const int px = CONVT ? (112 - 16 * ky - Cfg::kTaps * c) : (16 * ky + Cfg::kTaps * c);
           uint64_t wdesc;
-          if (s >= Cfg::kResident) {
+          if (!Cfg::resident(s)) {
             if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 35)) { ok = false; break; }
             tc_fence_after();
             wdesc = umma_desc_nosw(b_base + bstage * Cfg::kBBytes, Cfg::kLboA, 128);
           } else {
-            wdesc = res_desc + (uint64_t)((s * Cfg::kBBytes) >> 4);
+            wdesc = res_desc + (uint64_t)((Cfg::resident_index(s) * Cfg::kBBytes) >> 4);
           }
 #pragma unroll
           for (int k = 0; k < Cfg::kK16; ++k)
             umma_f16(tmem_d, wdesc + (uint64_t)((2 * k * Cfg::kLboA) >> 4), img_desc + (uint64_t)((px * 16 + 2 * k * Cfg::kLboB) >> 4),
                      idesc, (uint32_t)((s | k) != 0));
-          if (s >= Cfg::kResident) {
+          if (!Cfg::resident(s)) {
             umma_commit(bempty_bar(bstage));
             if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
           }
@@ -1000,10 +1005,10 @@ __global__ void pack_enc1_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 // ------------------------------------------------------------------------------------------
 struct Enc2Cfg {
   static constexpr int kABytes = 128 * 32;     // one tap of one tile
-  static constexpr int kStages = 18;           // two tiles of taps in flight
+  static constexpr int kStages = 6;            // stages of three taps (one filter row): two tiles in flight
   static constexpr int kBBytes = 9 * 32 * 32;  // [tap][32 oc x 16 ic]
   static constexpr int kTmemCols = 64;         // 2 accumulators x 32 columns
-  static constexpr int kSmemBytes = kStages * kABytes + kBBytes + 512 + 1024;
+  static constexpr int kSmemBytes = kStages * 3 * kABytes + kBBytes + 512 + 1024;
 };
 
 template <bool HALF>
@@ -1016,7 +1021,7 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t b_base = base + S * Cfg::kABytes;
+  const uint32_t b_base = base + S * 3 * Cfg::kABytes;
   const uint32_t bar0 = b_base + Cfg::kBBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -1052,10 +1057,15 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       bool ok = true;
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const int img = tile >> 1, oy0 = (tile & 1) * 8;
-        for (int tap = 0; tap < 9; ++tap) {
+        // one stage = the three taps of a filter row (three boxes on one barrier): the MMA issuer waits, issues and commits
+        // once per row instead of once per tap (its instruction stream, not the tensor pipe, bounds a layer of N = 32 MMAs)
+#pragma unroll
+        for (int kr = 0; kr < 3; ++kr) {
           if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 11)) { ok = false; break; }
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kABytes);
-          tma_load_4d(base + stage * Cfg::kABytes, &tmap_a, full_bar(stage), 0, tap % 3 - 1, 2 * oy0 - 1 + tap / 3, img);
+          mbar_arrive_expect_tx(full_bar(stage), 3 * Cfg::kABytes);
+#pragma unroll
+          for (int kc = 0; kc < 3; ++kc)
+            tma_load_4d(base + (stage * 3 + kc) * Cfg::kABytes, &tmap_a, full_bar(stage), 0, kc - 1, 2 * oy0 - 1 + kr, img);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -1066,15 +1076,20 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 12);
+      const uint64_t bdesc0 = umma_desc_sw32(b_base);
       for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 13)) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
-        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int kr = 0; kr < 3; ++kr) {
           if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 12)) { ok = false; break; }
           tc_fence_after();
-          umma_f16(tmem_d, umma_desc_sw32(base + stage * Cfg::kABytes), umma_desc_sw32(b_base + tap * 1024), idesc,
-                   (uint32_t)(tap != 0));
+          const uint64_t adesc = umma_desc_sw32(base + stage * 3 * Cfg::kABytes);
+#pragma unroll
+          for (int kc = 0; kc < 3; ++kc)
+            umma_f16(tmem_d, adesc + (uint64_t)((kc * Cfg::kABytes) >> 4), bdesc0 + (uint64_t)(((kr * 3 + kc) * 1024) >> 4), idesc,
+                     (uint32_t)((kr | kc) != 0));
           umma_commit(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
