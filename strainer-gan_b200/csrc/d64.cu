@@ -315,11 +315,17 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
+    // (the whole warp runs the loop and polls the barriers; elect.sync inside the MMA / commit statements)
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_16(256, BLOCK_N, HALF);
       int aslot = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, acc_phase = 0;
       bool ok = true;
+      // The issuer's instruction stream between two MMAs has to stay well below the MMA's 128 tensor cycles: the four taps of
+      // a unit and the four K = 16 steps of a stage are fully unrolled, every operand is a base descriptor plus a constant
+      // (the address field holds bytes >> 4 and never carries out of its 14 bits).
+      const uint64_t a_desc0 = umma_desc_sw128(base), b_desc0 = umma_desc_sw128(b_base);
+      const uint32_t shift16 = shift_bytes >> 4;
       for (int tile = pair; tile < p.total_tiles && ok; tile += npairs) {
         if (!mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 30)) break;
         tc_fence_after();
@@ -329,30 +335,32 @@ conv_pair2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int aseg = u % SEGA;
           if (!mbar_wait(afull_bar(aslot), aphase, s_abort, p.err, kErrMma + 30)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t ua = base + aslot * Cfg::kUnitBytes;
+          const uint64_t ua = a_desc0 + (uint64_t)((uint32_t)(aslot * Cfg::kUnitBytes) >> 4);
           const int nb = (SEGA == 2 && aseg == 0) ? 2 : 1;
-          for (int t = 0; t < 4 && ok; ++t) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
             // t >> 1: second row tap of the plane (one plane row further), t & 1: second column tap (copy 1)
-            const uint64_t adesc = umma_desc_sw128(ua + (t & 1) * Cfg::kCopyBytes + (t >> 1) * shift_bytes);
+            const uint64_t adesc = ua + (uint64_t)(((t & 1) * Cfg::kCopyBytes) >> 4) + (uint64_t)((t >> 1) * shift16);
             for (int b = 0; b < nb; ++b) {
               if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, p.err, kErrMma + 31)) { ok = false; break; }
               tc_fence_after();
-              const uint64_t bdesc = umma_desc_sw128(b_base + bstage * Cfg::kBBytes);
+              const uint64_t bdesc = b_desc0 + (uint64_t)((uint32_t)(bstage * Cfg::kBBytes) >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first);
+                umma_f16_pair_elect(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first);
                 first = 1u;
               }
-              umma_commit_pair(bempty_bar(bstage), 3);
+              umma_commit_pair_elect(bempty_bar(bstage), 3);
               if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
             }
+            if (!ok) break;
           }
           if (!ok) break;
-          umma_commit_pair(aempty_bar(aslot), 3);
+          umma_commit_pair_elect(aempty_bar(aslot), 3);
           if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
         }
         if (!ok) break;
-        umma_commit_pair(tfull_bar(acc), 3);
+        umma_commit_pair_elect(tfull_bar(acc), 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -520,44 +528,50 @@ conv2_swap2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp runs the loop and polls the barriers, elect.sync inside the MMA / commit statements; units
+    // and taps are unrolled and every operand is a base descriptor plus an offset, so that the instruction stream between
+    // two MMAs stays well below an MMA's 128 tensor cycles (a rolled single-lane loop needed ~100 instructions per stage of
+    // four MMAs and left the tensor pipe waiting)
+    {
       constexpr uint32_t idesc = umma_idesc_16(128, 256, HALF);
       int stage = 0, xslot = 0, acc = 0;
       uint32_t phase = 0, xphase = 0, acc_phase = 0;
       bool ok = true;
+      const uint64_t x_desc0 = umma_desc_sw128(base), w_desc0 = umma_desc_sw128(w_base);
       for (int img = blockIdx.x; img < p.n_img && ok; img += gridDim.x) {
         if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrMmaAcc + 40)) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-        uint32_t first = 0;
-        for (int u = 0; u < 8 * SEGA && ok; ++u) {
+#pragma unroll
+        for (int u = 0; u < 8 * SEGA; ++u) {
           const int xseg = u % SEGA;
           if (!mbar_wait(xfull_bar(xslot), xphase, s_abort, p.err, kErrMma + 40)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t ux = base + xslot * Cfg::kUnitBytes;
+          const uint64_t ux = x_desc0 + (uint64_t)((uint32_t)(xslot * Cfg::kUnitBytes) >> 4);
           const int nb = (SEGA == 2 && xseg == 0) ? 2 : 1;
-          for (int t = 0; t < 2 && ok; ++t) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
             // t: second row tap of this copy (one plane row = 16 pixels x 128 B further)
-            const uint64_t xdesc = umma_desc_sw128(ux + t * 2048);
+            const uint64_t xdesc = ux + (uint64_t)((t * 2048) >> 4);
+#pragma unroll
             for (int b = 0; b < nb; ++b) {
               if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrMma + 41)) { ok = false; break; }
               tc_fence_after();
-              const uint64_t wdesc = umma_desc_sw128(w_base + stage * Cfg::kWBytes);
+              const uint64_t wdesc = w_desc0 + (uint64_t)((uint32_t)(stage * Cfg::kWBytes) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16(tmem_d, wdesc + 2 * k, xdesc + 2 * k, idesc, first);
-                first = 1u;
-              }
-              umma_commit(empty_bar(stage));
+              for (int k = 0; k < 4; ++k)
+                umma_f16_elect(tmem_d, wdesc + 2 * k, xdesc + 2 * k, idesc, (uint32_t)((u | t | b | k) != 0));
+              umma_commit_elect(empty_bar(stage));
               if (++stage == S) { stage = 0; phase ^= 1u; }
             }
+            if (!ok) break;
           }
           if (!ok) break;
-          umma_commit(xempty_bar(xslot));
+          umma_commit_elect(xempty_bar(xslot));
           if (++xslot == UA) { xslot = 0; xphase ^= 1u; }
         }
         if (!ok) break;
-        umma_commit(tfull_bar(acc));
+        umma_commit_elect(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
