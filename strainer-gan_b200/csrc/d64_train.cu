@@ -191,11 +191,16 @@ trgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp runs the loop and polls the barriers; elect.sync inside the MMA / commit statements picks the issuing
+    // lane.  A stage is four M128 x N128 x K16 MMAs = 256 tensor cycles: a single-lane `if (lane == 0)` issuer (a per-lane
+    // serialisation loop around every MMA, ~100 instructions per stage) could not keep up with that.
+    {
       constexpr uint32_t idesc = umma_idesc_16(128, 128, true) | (MODE == MODE_WGRAD ? ((1u << 15) | (1u << 16)) : 0u);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       bool ok = true;
+      const uint64_t a_desc0 = MODE == MODE_WGRAD ? umma_desc_mn_sw128(base) : umma_desc_sw128(base);
+      constexpr uint64_t kBOff = 16384 >> 4, kStep = MODE == MODE_WGRAD ? 128 : 2;
       for (int u = blockIdx.x; u < total && ok; u += gridDim.x) {
         const Unit w = decode_unit(p, u);
         if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, p.err, kErrBase + 3)) break;
@@ -203,26 +208,21 @@ trgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         // accumulator pair of this unit: columns [0, 128) hi x hi, [128, 256) the two lo segments (split operands only)
         const uint32_t tmem_pair = tmem_base + (uint32_t)(acc * 256);
         uint32_t accum[2] = {0, 0};
+        int seg3 = 0;                                    // kss % 3 without a division per stage
         for (int kss = w.ks0 * p.nseg; kss < w.ks1 * p.nseg; ++kss) {
           if (!mbar_wait(full_bar(stage), phase, s_abort, p.err, kErrBase + 2)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t sa = base + stage * kStageBytes;
-          const int which = (p.nseg == 3 && kss % 3 != 0) ? 1 : 0;
+          const int which = (p.nseg == 3 && seg3 != 0) ? 1 : 0;
+          if (++seg3 == 3) seg3 = 0;
           const uint32_t tmem_d = tmem_pair + (uint32_t)(which * 128);
-          if (MODE == MODE_WGRAD) {
-            const uint64_t adesc = umma_desc_mn_sw128(sa), bdesc = umma_desc_mn_sw128(sa + 16384);
+          const uint64_t adesc = a_desc0 + (uint64_t)((uint32_t)(stage * kStageBytes) >> 4), bdesc = adesc + kBOff;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { umma_f16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, accum[which]); accum[which] = 1; }
-          } else {
-            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + 16384);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum[which]); accum[which] = 1; }
-          }
-          umma_commit(empty_bar(stage));
+          for (int k = 0; k < 4; ++k) { umma_f16_elect(tmem_d, adesc + kStep * k, bdesc + kStep * k, idesc, accum[which]); accum[which] = 1; }
+          umma_commit_elect(empty_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         if (!ok) break;
-        umma_commit(tfull_bar(acc));
+        umma_commit_elect(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
