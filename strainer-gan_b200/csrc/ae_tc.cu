@@ -50,6 +50,13 @@ constexpr size_t kAct1 = 32 * 32 * 16 * 2, kAct2 = 16 * 16 * 32 * 2, kAct3 = 100
 // Every CTA streams the same 7x7 weight stages in the same order: 148 SMs asking one L2 slice for one line at one time.
 // The packed weights are replicated and CTA b reads replica b % kWeightCopies (3.6 MB in all, L2 resident).
 constexpr int kWeightCopies = 8;
+// Linear-halo activation forms (single-segment modes, consumed by ae_dec2x_kernel / ae_dec3x_kernel): one plane per group
+// of 8 channels, [group][image][(S + 1) x (S + 1) positions][8 channels], position = y * (S + 1) + x, column S and row S of
+// every image ZERO.  In that form the window of filter shift (dy, dx) is the same bytes at a start address (dy * (S + 1) + dx)
+// positions later, for any run of consecutive positions -- one contiguous copy per group feeds every tap of a tile.
+// Plane sizes in 16-bit elements, including the slack the last tile's window reads.
+__host__ __device__ inline size_t a4x_plane_elems(int64_t batch) { return (size_t)((batch * 289 + 127) / 128 * 128 + 32) * 8; }
+__host__ __device__ inline size_t a5x_plane_elems(int64_t batch) { return (size_t)(batch * 1089 + 64) * 8; }
 struct Layout {
   size_t flag, w1, w2, w5, w6, w3, w4, w3t, w4t, a1, a2, a3, a4, a5, part, total;
 };
@@ -68,9 +75,11 @@ static Layout layout(int64_t batch, int seg) {
   L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
   L.a2 = o; o += align_up(kAct2 * seg * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
   L.a3 = o; o += align_up(kAct3 * seg * batch, 1024);
-  L.a4 = o; o += align_up(kAct4 * seg * batch, 1024);
-  L.a5 = o; o += align_up(kAct5 * seg * batch, 1024);
-  L.part = o; o += align_up((size_t)batch * 8 * sizeof(double), 1024);   // per-tile squared-error sums (dec3 tensor-core form)
+  // single-segment modes: a4 / a5 in the linear-halo forms of ae_dec2x_kernel / ae_dec3x_kernel (a4x_plane_elems ...)
+  const size_t a4b = seg == 1 ? 4 * a4x_plane_elems(batch) * 2 : 0, a5b = seg == 1 ? 2 * a5x_plane_elems(batch) * 2 : 0;
+  L.a4 = o; o += align_up(kAct4 * seg * batch > a4b ? kAct4 * seg * batch : a4b, 1024);
+  L.a5 = o; o += align_up(kAct5 * seg * batch > a5b ? kAct5 * seg * batch : a5b, 1024);
+  L.part = o; o += align_up((size_t)batch * 9 * sizeof(double), 1024);   // per-tile squared-error sums (dec3 tensor-core forms)
   L.total = o;
   return L;
 }
@@ -503,7 +512,8 @@ struct K7XCfg {
   static constexpr int kBStages = CONVT ? 5 : 6;
   static constexpr int kK16 = kCin / 16;
   static constexpr int kOutPixels = CONVT ? 256 : 100;
-  static constexpr int kStgBytes = kOutPixels * kCout * 2;      // one image's output block (NHWC); two staging buffers
+  static constexpr int kOutBytes = kOutPixels * kCout * 2;      // one image's output block
+  static constexpr int kStgBytes = CONVT ? 4 * 289 * 16 : kOutBytes;   // two staging buffers (dec1: room for the linear-halo form)
   static constexpr int kTmemCols = 512;                         // 2 accumulators x 256 columns
   static constexpr int kThreads = 224;                          // + warp 6: image producer
   static constexpr int kBarBytes = 512;
@@ -520,10 +530,13 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t 
          (1ull << 46);
 }
 
-template <bool CONVT, bool HALF>
+// XOUT (dec1 only): the output is written in the linear-halo form [co / 8][image][17 x 17][8] (a4x_plane_elems) that
+// ae_dec2x_kernel consumes; the zero column / row come from the staging buffer, which starts zeroed and is never written there.
+template <bool CONVT, bool HALF, bool XOUT = false>
 __global__ void __launch_bounds__(224, 1)
 ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
+              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err, size_t out_plane) {
+  static_assert(!XOUT || CONVT, "the linear-halo output form belongs to dec1");
   using Cfg = K7XCfg<CONVT>;
   constexpr int UA = Cfg::kSlots, SB = Cfg::kBStages, COUT = Cfg::kCout;
   extern __shared__ uint8_t smem_raw[];
@@ -563,7 +576,7 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
   // operand memory starts finite: enc3's windows run up to 102 pixels past a channel group (into the next group, the next
   // slot or the first weight stage); those products only reach dead columns or meet zero weights, and 0 x finite = 0
-  for (int i = threadIdx.x; i < (int)((g_base - base) / 16); i += Cfg::kThreads)
+  for (int i = threadIdx.x; i < (int)((bar0 - base) / 16); i += Cfg::kThreads)   // (+ the staging buffers: XOUT's zero halo)
     *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -709,7 +722,9 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             const float send = hi ? before : pp[2 * k + 1];
             const float a = my_bias + pp[2 * k] + __shfl_xor_sync(0xffffffffu, send, 2);
             const int n = 32 * j + 4 * k + kxl;
-            stg[n * 32 + co] = pk1<HALF>(fmaxf(a, 0.f));              // ReLU follows the decoder's first layer
+            // ReLU follows the decoder's first layer
+            if (XOUT) stg[((co >> 3) * 289 + (n >> 4) * 17 + (n & 15)) * 8 + (co & 7)] = pk1<HALF>(fmaxf(a, 0.f));
+            else stg[n * 32 + co] = pk1<HALF>(fmaxf(a, 0.f));
           }
           c1 = v[31]; c2 = pp[15];
           (void)c3;
@@ -730,11 +745,18 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         }
       }
       named_bar_sync(1, 128);
-      // the image's output block is contiguous in global memory (NHWC): 16-byte stores
-      {
+      if (XOUT) {
+        // four contiguous runs of 289 positions x 16 bytes, one per channel-group plane
+        const uint4* src = reinterpret_cast<const uint4*>(stg);
+        for (int i = t; i < 4 * 289; i += 128) {
+          const int g = i / 289, k = i - g * 289;
+          reinterpret_cast<uint4*>(out + (size_t)g * out_plane + (size_t)img * (289 * 8))[k] = src[i];
+        }
+      } else {
+        // the image's output block is contiguous in global memory (NHWC): 16-byte stores
         const uint4* src = reinterpret_cast<const uint4*>(stg);
         uint4* dst = reinterpret_cast<uint4*>(out + (size_t)img * Cfg::kOutPixels * COUT);
-        for (int i = t; i < Cfg::kStgBytes / 16; i += 128) dst[i] = src[i];
+        for (int i = t; i < Cfg::kOutBytes / 16; i += 128) dst[i] = src[i];
       }
       buf ^= 1;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -767,7 +789,7 @@ __global__ void pack_k7x_kernel(const float* __restrict__ w3, const float* __res
   }
 }
 
-template <bool CONVT, bool HALF>
+template <bool CONVT, bool HALF, bool XOUT = false>
 static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
                       int64_t batch, int* err, cudaStream_t st) {
   using Cfg = K7XCfg<CONVT>;
@@ -796,7 +818,8 @@ static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
     if (r != SG_OK) return r;
   }
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-  ae_k7x_kernel<CONVT, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err);
+  ae_k7x_kernel<CONVT, HALF, XOUT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err,
+                                                                                   XOUT ? a4x_plane_elems(batch) : 0);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1332,6 +1355,15 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return copysignf(__fdividef(1.f - t, 1.f + t), x);
 }
 
+// tanh(x) = sign(x) (1 - 2 / (1 + 2^(2 log2(e) |x|))): ex2.approx + rcp.approx + 4 FP32 instructions (|x| > 44: 2^.. = inf,
+// 1 / inf = 0 -> +-1); absolute error < 4e-7, the class of fast_tanh above
+__device__ __forceinline__ float fast_tanh2(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return copysignf(fmaf(-2.f, r, 1.f), x);
+}
+
 struct Dec3Cfg {
   static constexpr int kPart = 128 * 32;
   static constexpr int kStageBytes = 4 * kPart;   // 16 KB per tile
@@ -1485,12 +1517,13 @@ ae_dec3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+template <int TILES>
 __global__ void ae_mse_finish_kernel(const double* __restrict__ partial, int64_t n_img, float* __restrict__ err) {
   const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n < n_img) {
     double s = 0.0;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) s += partial[n * 8 + t];
+    for (int t = 0; t < TILES; ++t) s += partial[n * TILES + t];
     err[n] = (float)(s / 12288.0);
   }
 }
@@ -1502,6 +1535,366 @@ __global__ void pack_dec3_kernel(const float* __restrict__ w, __nv_bfloat16* __r
     const int oc = i / 144, r = i - oc * 144, tap = r >> 4, ic = r & 15;
     const float v = oc < 3 ? w[(ic * 3 + oc) * 9 + tap] : 0.f;
     reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// L5 / L6 in LINEAR-HALO form (single-segment modes; the default when the input is 16-byte aligned).  The gather kernels above
+// fetch every shifted window of a tile as its own TMA box of 32-byte rows: 8 boxes = 1024 row requests per 128 quads in L5,
+// 512 in L6 -- both ran at TMA's request rate (~2 cycles per 32-byte row), not at HBM's.  Here the activations are stored as
+// [ci / 8][image][(S + 1)^2 positions][8 ci] with a zero column and row S (a4x_plane_elems / a5x_plane_elems), the operand
+// of shift (dy, dx) is the SAME shared-memory copy at a start address (dy * (S + 1) + dx) * 16 bytes later (un-swizzled
+// core-matrix layout: SBO = 128, LBO = the group plane), and a tile's input is ONE contiguous bulk copy per channel group:
+// 4 x 2.3 KB (L5) / 2 x 2.6 KB (L6) instead of 32 / 16 KB.  The zero column doubles as left padding of the next row, the zero
+// row as bottom padding; accumulator rows that land on halo positions are skipped (L5: they write the zeros of L6's halo).
+//   L5: tiles of 128 consecutive positions of the whole batch (11 % halo rows)
+//   L6: 9 tiles of 121 positions per image (the tile -> image mapping, and with it the order of the squared-error sums,
+//       does not depend on the image's index in the batch: scores are chunk invariant)
+// ------------------------------------------------------------------------------------------
+struct Dec2XCfg {
+  static constexpr int kWin = 128 + 18;               // positions a tile's windows touch (max shift 17 + 1)
+  static constexpr int kGroupBytes = kWin * 16;       // 2 336
+  static constexpr int kStageBytes = 4 * kGroupBytes; // 9 344 per tile
+  static constexpr int kStages = 4;
+  static constexpr int kBBytes = 18 * 512;
+  static constexpr int kTmemCols = 128;               // 2 buffers x 4 classes x 16 columns
+  static constexpr int kSmemBytes = kBBytes + kStages * kStageBytes + 256 + 1024;
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(192, 3)
+ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
+                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t out_plane, int n_img, int total_tiles,
+                int* err) {
+  using Cfg = Dec2XCfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base;                                  // 18 weight tiles (SWIZZLE_32B)
+  const uint32_t a_base = base + Cfg::kBBytes;                   // ring of window stages (un-swizzled)
+  const uint32_t bar0 = a_base + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int t = 0; t < 18; ++t) tma_load_2d(b_base + t * 512, &tmap_b, wbar, t * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (!mbar_wait_sleep(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 21)) break;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = a_base + stage * Cfg::kStageBytes;
+        const __nv_bfloat16* src = in + (size_t)tile * (128 * 8);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bulk_load_1d(sa + g * Cfg::kGroupBytes, src + (size_t)g * in_plane, Cfg::kGroupBytes, full_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait_sleep(wbar, 0, s_abort, err, kErrBase + 22);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait_sleep(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 23)) break;
+        if (!mbar_wait_sleep(full_bar(stage), phase, s_abort, err, kErrBase + 22)) break;
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_nosw(a_base + stage * Cfg::kStageBytes, Cfg::kGroupBytes, 128);
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+          const int py = cls >> 1, px = cls & 1;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
+          bool first = true;
+#pragma unroll
+          for (int dy = 0; dy <= py; ++dy)
+#pragma unroll
+            for (int dx = 0; dx <= px; ++dx) {
+              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {   // channels 16 half .. 16 half + 15 = groups 2 half, 2 half + 1
+                umma_f16(tmem_d, adesc + (uint64_t)(((dy * 17 + dx) * 16 + half * 2 * Cfg::kGroupBytes) >> 4),
+                         umma_desc_sw32(b_base + (tap * 2 + half) * 512), idesc, first ? 0u : 1u);
+                first = false;
+              }
+            }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    float bo[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) bo[c] = __ldg(bias + c);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int p = tile * 128 + row;                   // position in the batch's [image][17 x 17] sequence
+      const int img = p / 289, rem = p - img * 289;
+      const int qy = rem / 17, qx = rem - qy * 17;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 24)) break;
+      tc_fence_after();
+      uint32_t v0[32], v1[32];   // classes (0,0) (0,1) | (1,0) (1,1)
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+      tmem_ld_32x32(taddr, v0);
+      tmem_ld_32x32(taddr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (img < n_img) {
+        __nv_bfloat16* o = out + (size_t)img * (1089 * 8);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (qx < 16 && qy < 16) {
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            const uint32_t* v = py ? v1 : v0;
+            uint32_t pk[16];   // [px][8 channel pairs]
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[(2 * j) & 15], 0.f);
+              const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[(2 * j + 1) & 15], 0.f);
+              pk[j] = pk2<HALF>(a, b);
+            }
+            // pixels (2qx, 2qx + 1) of output row 2qy + py: 32 contiguous bytes in each of the two channel-group planes
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane + (size_t)((2 * qy + py) * 33 + 2 * qx) * 8);
+              d[0] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+              d[1] = make_uint4(pk[8 + 4 * g], pk[8 + 4 * g + 1], pk[8 + 4 * g + 2], pk[8 + 4 * g + 3]);
+            }
+          }
+        } else if (qy < 16) {       // halo column of the input: zero column 32 of output rows 2qy, 2qy + 1
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane);
+            d[(2 * qy) * 33 + 32] = z;
+            d[(2 * qy + 1) * 33 + 32] = z;
+          }
+        } else {                    // halo row of the input: zero row 32 of the output
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane) + 32 * 33;
+            if (qx < 16) { d[2 * qx] = z; d[2 * qx + 1] = z; }
+            else d[32] = z;
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+struct Dec3XCfg {
+  static constexpr int kTilePos = 121, kTilesPerImage = 9;      // 9 x 121 = 1 089 positions
+  static constexpr int kWin = 128 + 34;               // positions a tile's windows touch (max shift 33 + 1)
+  static constexpr int kGroupBytes = kWin * 16;       // 2 592
+  static constexpr int kStageBytes = 2 * kGroupBytes; // 5 184 per tile
+  static constexpr int kStages = 4;
+  static constexpr int kBBytes = 9 * 512;
+  static constexpr int kTmemCols = 128;               // 2 buffers x 4 classes x 16 columns
+  static constexpr int kSmemBytes = 5120 + kStages * kStageBytes + 512 + 256 + 1024;
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(192, 4)
+ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
+                const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ recon,
+                double* __restrict__ partial, int total_tiles, int* err) {
+  using Cfg = Dec3XCfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base;                                  // 9 weight tiles (SWIZZLE_32B), 4 608 of 5 120 bytes
+  const uint32_t a_base = base + 5120;
+  const uint32_t p_base = a_base + S * Cfg::kStageBytes;         // [2][4] warp sums
+  const uint32_t bar0 = p_base + 512;
+  double* s_part = reinterpret_cast<double*>(smem + (p_base - base));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(b_base + t * 512, &tmap_b, wbar, t * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int img = tile / Cfg::kTilesPerImage, t = tile - img * Cfg::kTilesPerImage;
+        if (!mbar_wait_sleep(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 41)) break;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = a_base + stage * Cfg::kStageBytes;
+        const __nv_bfloat16* src = in + ((size_t)img * 1089 + (size_t)t * Cfg::kTilePos) * 8;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) bulk_load_1d(sa + g * Cfg::kGroupBytes, src + (size_t)g * in_plane, Cfg::kGroupBytes, full_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait_sleep(wbar, 0, s_abort, err, kErrBase + 42);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait_sleep(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 43)) break;
+        if (!mbar_wait_sleep(full_bar(stage), phase, s_abort, err, kErrBase + 42)) break;
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_nosw(a_base + stage * Cfg::kStageBytes, Cfg::kGroupBytes, 128);
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+          const int py = cls >> 1, px = cls & 1;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
+          bool first = true;
+#pragma unroll
+          for (int dy = 0; dy <= py; ++dy)
+#pragma unroll
+            for (int dx = 0; dx <= px; ++dx) {
+              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
+              umma_f16(tmem_d, adesc + (uint64_t)(((dy * 33 + dx) * 16) >> 4), umma_desc_sw32(b_base + tap * 512), idesc,
+                       first ? 0u : 1u);
+              first = false;
+            }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+    int acc = 0, it = 0;
+    uint32_t acc_phase = 0;
+    // ncu (profiles/r2l_ae_dec3x_sass.txt): this epilogue is the kernel's bound -- the SM's issue slots, 342 instructions per
+    // thread and tile in the first version.  Hence: the tile -> pixel decode and the 12 input values a thread compares with
+    // are prepared ONE TILE AHEAD (registers; one base pointer, constant offsets; lanes on halo positions load a dummy
+    // address instead of branching), tanh is two MUFU + 4 FP32 instructions, the warp sum is an fp32 butterfly (fixed
+    // order -> deterministic and the same for every image; fp64 from the four warp sums on).
+    auto locate = [&](int tile, const float*& px) -> bool {
+      const int img = tile / Cfg::kTilesPerImage;
+      const int rem = (tile - img * Cfg::kTilesPerImage) * Cfg::kTilePos + row;   // position in the image's 33 x 33 sequence
+      const int qy = rem / 33, qx = rem - qy * 33;
+      const bool valid = tile < total_tiles && row < Cfg::kTilePos && qx < 32 && qy < 32;
+      px = valid ? x + ((size_t)img * 12288 + (size_t)(2 * qy * 64 + 2 * qx)) : x;
+      return valid;
+    };
+    auto load_x = [&](const float* px, float2 (&t)[6]) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t[i] = __ldg(reinterpret_cast<const float2*>(px + (i >> 1) * 4096 + (i & 1) * 64));
+    };
+    const float* pn;
+    bool vn = locate(blockIdx.x, pn);
+    float2 nxt[6];
+    load_x(pn, nxt);
+    float* s_partf = reinterpret_cast<float*>(s_part);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const float* pc = pn;
+      const bool valid = vn;
+      float2 tin[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) tin[i] = nxt[i];
+      vn = locate(tile + (int)gridDim.x, pn);
+      load_x(pn, nxt);
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 44)) break;
+      tc_fence_after();
+      // classes (py, px) at columns 32 py + 16 px; only channels 0..2 of the 16 columns of a class are real
+      uint32_t v[4][4];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int cls = 0; cls < 4; ++cls) tmem_ld_32x32_x4(taddr + cls * 16, v[cls]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      float sqf = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          const float r0 = fast_tanh2(__uint_as_float(v[2 * py][c]) + bc), r1 = fast_tanh2(__uint_as_float(v[2 * py + 1][c]) + bc);
+          const float2 tt = tin[c * 2 + py];
+          const float d0 = r0 - tt.x, d1 = r1 - tt.y;
+          sqf = fmaf(d0, d0, sqf);
+          sqf = fmaf(d1, d1, sqf);
+          if (recon && valid) *reinterpret_cast<float2*>(recon + (pc - x) + c * 4096 + py * 64) = make_float2(r0, r1);
+        }
+      }
+      if (!valid) sqf = 0.f;      // halo rows: accumulator rows of no pixel
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sqf += __shfl_xor_sync(0xffffffffu, sqf, o);
+      float* sp = s_partf + (it & 1) * 4;
+      if (lane == 0) sp[lg] = sqf;
+      named_bar_sync(1, 128);
+      if (row == 0) partial[tile] = (((double)sp[0] + (double)sp[1]) + (double)sp[2]) + (double)sp[3];
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -1865,6 +2258,8 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   }
   if (!do_forward) return SG_OK;
   if (SEG == 2) SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));   // slack the paired-tap view reads
+  // linear-halo forms of a4 / a5 (ae_dec2x_kernel / ae_dec3x_kernel): the default; the gather kernels serve unaligned inputs
+  const bool xform = SEG == 1 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)recon_out & 7) == 0;
   const int64_t cap = (int64_t)state().sm_count * 8;
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
   if (SEG == 1 && ((uintptr_t)x & 15) == 0) {   // tensor-core form (single-segment modes)
@@ -1914,7 +2309,8 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     // single-segment modes: both 7x7 layers in shifted-window form (weights on M, the image's pixels on N, taps = descriptor offsets)
     r = launch_k7x<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
     if (r != SG_OK) return r;
-    r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
+    if (xform) r = launch_k7x<true, HALF, true>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
+    else r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
     if (r != SG_OK) return r;
   } else {
     r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
@@ -1933,6 +2329,32 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
     ae_dec1_kernel<SEG, HALF><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
     SG_LAUNCH_CHECK();
+  }
+  if (SEG == 1 && xform) {
+    CUtensorMap tb;
+    cuuint64_t bdims[2] = {288, 16};
+    cuuint64_t bstr[1] = {576};
+    cuuint32_t bbox[2] = {16, 16};
+    r = encode_tmap(&tb, 2, bf(L.w5), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+    const int64_t tiles = ceil_div(batch * 289, 128);
+    const int64_t ctas = (int64_t)state().sm_count * 3;
+    ae_dec2x_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), 192, Dec2XCfg::kSmemBytes, st>>>(
+        tb, bf(L.a4), a4x_plane_elems(batch), h_params[9], bf(L.a5), a5x_plane_elems(batch), (int)batch, (int)tiles, err);
+    SG_LAUNCH_CHECK();
+    cuuint64_t b6dims[2] = {144, 16};
+    cuuint64_t b6str[1] = {288};
+    r = encode_tmap(&tb, 2, bf(L.w6), b6dims, b6str, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (r != SG_OK) return r;
+    const int64_t tiles6 = batch * Dec3XCfg::kTilesPerImage;
+    double* part = reinterpret_cast<double*>(ws + L.part);
+    const int64_t ctas6 = (int64_t)state().sm_count * 4;
+    ae_dec3x_kernel<HALF><<<(int)(tiles6 < ctas6 ? tiles6 : ctas6), 192, Dec3XCfg::kSmemBytes, st>>>(
+        tb, bf(L.a5), a5x_plane_elems(batch), h_params[11], x, recon_out, part, (int)tiles6, err);
+    SG_LAUNCH_CHECK();
+    ae_mse_finish_kernel<Dec3XCfg::kTilesPerImage><<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
   }
   if constexpr (SEG == 1) {   // tensor-core form (single-segment modes)
     CUtensorMap ta, tb;
@@ -1973,7 +2395,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     ae_dec3_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), 192, Dec3Cfg::kSmemBytes, st>>>(
         ta, tb, h_params[11], x, recon_out, part, (int)tiles, err);
     SG_LAUNCH_CHECK();
-    ae_mse_finish_kernel<<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
+    ae_mse_finish_kernel<8><<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
   } else {
     dec3_mse_kernel<SEG, HALF><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
   }
@@ -2003,6 +2425,12 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3XCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_dec3x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3XCfg::kSmemBytes));
   return SG_OK;
 }
 

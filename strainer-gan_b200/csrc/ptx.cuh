@@ -69,6 +69,23 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
   }
 }
 
+// The same bounded wait with a sleep between polls, for warps whose wake-up latency is not critical (TMA producers and MMA
+// issuers that share an SM with issue-bound epilogue warps: their spin loops took ~20 % of the SM's issue slots).
+__device__ __forceinline__ bool mbar_wait_sleep(uint32_t bar, uint32_t parity, volatile int* s_abort, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  while (true) {
+    __nanosleep(32);
+    if (mbar_try_wait(bar, parity)) return true;
+    if (*s_abort) return false;
+    if (globaltimer_ns() - t0 > 2000000000ull) {
+      *s_abort = 1;
+      atomicCAS(err, 0, code);
+      return false;
+    }
+  }
+}
+
 __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, volatile int* s_abort, int* err, int code) {
   if (mbar_try_wait_cluster(bar, parity)) return true;
   const uint64_t t0 = globaltimer_ns();
@@ -109,6 +126,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       :: "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// 1-D bulk copy global -> shared (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
@@ -196,6 +219,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
+}
+// 32 lanes x 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x32_x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
