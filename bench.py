@@ -578,6 +578,50 @@ def main():
                  "note": "generator forward / backward and Adam = torch autograd in all arms; *_d_on_tcgen05: the discriminator's "
                          "forward + backward of the D and G steps run on this repo's kernels (sb.accelerate_discriminator)"}
 
+    # ---- the other BASELINE.json configs on this box (rank 0, N = 1): parity-test cases, reported beside the headline -----
+    other_configs = None
+    if rank == 0 and world == 1 and not args.no_train:
+        other_configs = {}
+        # config 4: auto-encoder reconstruction-error scoring, 65 536 resident images in 8 192-image launches
+        torch.manual_seed(O.SEED)
+        ae = O.AutoEncoder().eval()
+        na = 65536
+        xa = sb.synth_images(0, na, O.SEED, device)
+        ref_e = O.ae_errors(ae, xa[:64].cpu()).numpy()
+        c4 = {"unit": "samples/s", "images": na, "flop_per_sample": 46.6e6,
+              "what": "sb.ae_errors(ae, images_on_device, chunk=8192): six tcgen05 conv layers + tanh + per-sample MSE"}
+        for m in ("auto", "bf16"):
+            e_ = sb.ae_errors(ae, xa, device, chunk=8192, conv_mode=m)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(5):
+                e_ = sb.ae_errors(ae, xa, device, chunk=8192, conv_mode=m)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_ = ev0.elapsed_time(ev1) / 5
+            rel_ = float((np.abs(e_[:64].cpu().numpy() - ref_e) / np.maximum(ref_e, 1e-6)).max())
+            c4[m] = {"value": na / (ms_ * 1e-3), "ms": ms_, "tflops": na * 46.6e6 / (ms_ * 1e-3) / 1e12,
+                     "max_rel_err_vs_oracle_64": rel_}
+        other_configs["config4_autoencoder"] = c4
+        del xa
+        # config 2: the in-batch strain block at B = 128 (eval-mode and train-mode BatchNorm)
+        real_b = sb.synth_images(0, 128, O.SEED, device)
+        c2 = {"unit": "us per batch", "batch": 128, "what": "sb.strain_batch(netD, real, 0.1): scoring + quantile + mask + "
+              "partition, incl. the host read of the kept count"}
+        for label, train_mode in (("eval_bn", False), ("train_bn", True)):
+            nd_ = O.make_discriminator(O.SEED).to(device)
+            nd_.train(train_mode)
+            for _ in range(10):
+                sb.strain_batch(nd_, real_b, LOSS_RATIO)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(100):
+                sb.strain_batch(nd_, real_b, LOSS_RATIO)
+            torch.cuda.synchronize()
+            c2[label] = (time.perf_counter() - t0) / 100 * 1e6
+        other_configs["config2_strain_block"] = c2
+
     if rank == 0:
         line = {"metric": "strained_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -598,7 +642,7 @@ def main():
                 "select_compact": {"ms": ms_sel, "reduction": ("nvlink peer memory inside the select kernels (PeerComm)" if peer is not None
                                                                else ("nccl all-reduces" if group is not None else "single device")),
                                    "ms_with_nccl_all_reduces": ms_sel_nccl}, "train_iters_per_sec": train, "torch_eager_gpu": eager,
-                "other_modes": other_modes}
+                "other_modes": other_modes, "other_configs": other_configs}
         print(json.dumps(line), flush=True)
     if group is not None:
         dist.destroy_process_group()

@@ -472,7 +472,7 @@ def test_autoencoder_linear_halo_forms_reconstruction_and_unaligned_fallback(sb)
             assert (np.abs(e - mse) / mse).max() <= 1e-5, (mode, n)
             # the same images 4 bytes further (not 16-byte aligned): the gather kernels
             buf = torch.empty(n * 12288 + 4, device=dev)
-            xu = buf[1:].view(n, 3, 64, 64)
+            xu = buf[1:1 + n * 12288].view(n, 3, 64, 64)
             xu.copy_(xd)
             assert xu.data_ptr() % 16 == 4
             err_u = torch.empty(n, device=dev)
