@@ -188,7 +188,9 @@ int sg_d64_train_read(const void* workspace, int64_t batch, int64_t max_batch, i
  * F.mse_loss(out, img, 'none').view(B,-1).mean(1) of ":315-316".
  * h_params: HOST array of 12 DEVICE pointers {w,b} x {enc.0, enc.2, enc.4, dec.0, dec.2, dec.4} in the
  * PyTorch layouts (Conv2d [out,in,k,k], ConvTranspose2d [in,out,k,k]).  x fp32 NCHW [batch,3,64,64];
- * err_out[batch]; recon_out (optional, [batch,3,64,64]) receives the reconstruction. */
+ * err_out[batch]; recon_out (optional, [batch,3,64,64]) receives the reconstruction.  x and recon_out must be 16-byte
+ * aligned (TMA boxes and vector accesses; every sample offset of an aligned tensor is: 49 152 bytes per sample), else
+ * SG_EINVAL. */
 #ifdef SG_AB_VARIANTS   /* plain fp32 on the CUDA cores: experiment builds only (cross-check of the tensor-core pipeline) */
 size_t sg_ae_workspace_bytes(int64_t max_batch);
 int sg_ae_score(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,

@@ -8,9 +8,9 @@
 //   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> [32][32][16]             ae_enc1_tc_kernel (input conversion fused)
 //   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> [ci / 8][16 x 16][8]                   ae_enc2_tc_kernel (stride-2 TMA boxes)
 //   L3 enc Conv 32->64 k7                -> [co / 8][10 x 10][8]                   ae_k7x_kernel<false>: shifted-window form
-//   L4 dec ConvT 64->32 k7 + ReLU        -> [16][16][32]                           ae_k7x_kernel<true>
-//   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> [32][32][16]                        ae_dec2_tc_kernel
-//   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)   ae_dec3_tc_kernel
+//   L4 dec ConvT 64->32 k7 + ReLU        -> [co / 8][17 x 17 with zero halo][8]    ae_k7x_kernel<true>
+//   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> [co / 8][33 x 33 with zero halo][8]  ae_dec2x_kernel (linear-halo form)
+//   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)   ae_dec3x_kernel
 //
 // The fp32-parity mode (SEG = 2: every activation as bf16 hi | lo, three tensor passes) keeps the gather forms of the 7x7
 // layers (ae_k7_kernel, ae_dec1_kernel) and CUDA-core small layers.
@@ -530,13 +530,13 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t 
          (1ull << 46);
 }
 
-// XOUT (dec1 only): the output is written in the linear-halo form [co / 8][image][17 x 17][8] (a4x_plane_elems) that
-// ae_dec2x_kernel consumes; the zero column / row come from the staging buffer, which starts zeroed and is never written there.
-template <bool CONVT, bool HALF, bool XOUT = false>
+// dec1 writes its output in the linear-halo form [co / 8][image][17 x 17][8] (a4x_plane_elems) that ae_dec2x_kernel consumes;
+// the zero column / row come from the staging buffer, which starts zeroed and is never written there.
+template <bool CONVT, bool HALF>
 __global__ void __launch_bounds__(224, 1)
 ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err, size_t out_plane) {
-  static_assert(!XOUT || CONVT, "the linear-halo output form belongs to dec1");
+  constexpr bool XOUT = CONVT;
   using Cfg = K7XCfg<CONVT>;
   constexpr int UA = Cfg::kSlots, SB = Cfg::kBStages, COUT = Cfg::kCout;
   extern __shared__ uint8_t smem_raw[];
@@ -789,7 +789,7 @@ __global__ void pack_k7x_kernel(const float* __restrict__ w3, const float* __res
   }
 }
 
-template <bool CONVT, bool HALF, bool XOUT = false>
+template <bool CONVT, bool HALF>
 static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
                       int64_t batch, int* err, cudaStream_t st) {
   using Cfg = K7XCfg<CONVT>;
@@ -818,8 +818,8 @@ static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
     if (r != SG_OK) return r;
   }
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-  ae_k7x_kernel<CONVT, HALF, XOUT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err,
-                                                                                   XOUT ? a4x_plane_elems(batch) : 0);
+  ae_k7x_kernel<CONVT, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err,
+                                                                             CONVT ? a4x_plane_elems(batch) : 0);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -1174,161 +1174,11 @@ __global__ void pack_enc2_kernel(const float* __restrict__ w, __nv_bfloat16* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// L5 (dec ConvT 32->16 k3 s2 p1 op1 + ReLU) on tcgen05 (bf16 conv mode), gather form by output parity class:
-// out(2qy + py, 2qx + px) = sum over the taps whose parity matches of in(qy + dy, qx + dx) * w (see tap_k below).
-// One tile = 8 x 16 quads of one image (M = 128); the four classes (py, px) have their own N = 16 accumulators
-// side by side in TMEM.  The A operands are the FOUR shifted windows in(qy + dy, qx + dx) (row / column 16 = TMA
-// zero fill), each as two 16-channel halves of dense 32-byte rows (SWIZZLE_32B): 8 TMA boxes = 32 KB per tile, read
-// by 18 MMAs (9 taps x 2 halves, K = 16).  The 18 weight tiles [16 oc x 16 ic] stay in shared memory.
-// ------------------------------------------------------------------------------------------
-struct Dec2Cfg {
-  static constexpr int kPart = 128 * 32;          // one (shift, half) window of a tile
-  static constexpr int kStageBytes = 8 * kPart;   // 32 KB per tile
-  static constexpr int kStages = 4;
-  static constexpr int kBBytes = 18 * 512;
-  static constexpr int kTmemCols = 128;           // 2 buffers x 4 classes x 16 columns
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 256 + 1024;
-};
+// L5 / L6 are transposed stride-2 convolutions in gather form by output parity class:
+//   out(2qy + py, 2qx + px) = sum over the taps whose parity matches of in(qy + dy, qx + dx) * w[tap], dy <= py, dx <= px,
+// kernel tap index along one axis = dec2_tap_k(parity, shift); the four classes have their own N = 16 accumulators side by
+// side in TMEM (ae_dec2x_kernel / ae_dec3x_kernel below).
 __host__ __device__ constexpr int dec2_tap_k(int parity, int d) { return parity == 0 ? 1 : (d ? 0 : 2); }
-
-template <bool HALF>
-__global__ void __launch_bounds__(192, 1)
-ae_dec2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
-  using Cfg = Dec2Cfg;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t b_base = base + S * Cfg::kStageBytes;
-  const uint32_t bar0 = b_base + Cfg::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
-    mbar_init(wbar, 1);
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
-      for (int t = 0; t < 18; ++t) tma_load_2d(b_base + t * 512, &tmap_b, wbar, t * 16, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int img = tile >> 1, qy0 = (tile & 1) * 8;
-        if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 21)) break;
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        const uint32_t sa = base + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int part = 0; part < 8; ++part) {   // part = (dy*2 + dx)*2 + half
-          const int half = part & 1, dx = (part >> 1) & 1, dy = part >> 2;
-          tma_load_4d(sa + part * Cfg::kPart, &tmap_a, full_bar(stage), half * 16, dx, qy0 + dy, img);
-        }
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 22);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 23)) break;
-        if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 22)) break;
-        tc_fence_after();
-        const uint32_t sa = base + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int cls = 0; cls < 4; ++cls) {
-          const int py = cls >> 1, px = cls & 1;
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
-          bool first = true;
-#pragma unroll
-          for (int dy = 0; dy <= py; ++dy)
-#pragma unroll
-            for (int dx = 0; dx <= px; ++dx) {
-              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                umma_f16(tmem_d, umma_desc_sw32(sa + ((dy * 2 + dx) * 2 + half) * Cfg::kPart),
-                         umma_desc_sw32(b_base + (tap * 2 + half) * 512), idesc, first ? 0u : 1u);
-                first = false;
-              }
-            }
-        }
-        umma_commit(empty_bar(stage));
-        umma_commit(tfull_bar(acc));
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    const int qyl = row >> 4, qx = row & 15;
-    float bo[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) bo[c] = __ldg(bias + c);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int img = tile >> 1, qy = (tile & 1) * 8 + qyl;
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 24)) break;
-      tc_fence_after();
-      uint32_t v0[32], v1[32];   // classes (0,0) (0,1) | (1,0) (1,1)
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
-      tmem_ld_32x32(taddr, v0);
-      tmem_ld_32x32(taddr + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      if (img < n_img) {
-#pragma unroll
-        for (int py = 0; py < 2; ++py) {
-          const uint32_t* v = py ? v1 : v0;
-          uint32_t pk[16];   // pixels (2qx, 2qx + 1) of output row 2qy + py: 2 x 16 channels = 64 contiguous bytes
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[(2 * j) & 15], 0.f);
-            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[(2 * j + 1) & 15], 0.f);
-            pk[j] = pk2<HALF>(a, b);
-          }
-          uint4* d = reinterpret_cast<uint4*>(out + (((size_t)img * 32 + 2 * qy + py) * 32 + 2 * qx) * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
 
 // dec2 weights [32][16][3][3] (ConvTranspose2d: in, out, ky, kx) -> bf16 [oc][(tap*2 + half)*16 + icl], ic = half*16 + icl
 __global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
@@ -1341,180 +1191,13 @@ __global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __r
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// L6 (dec ConvT 16->3 k3 s2 p1 op1 + tanh) + squared error against the input, on tcgen05.  Same gather form as L5:
-// one tile = 4 x 32 quads of one image (M = 128, 8 tiles per image), four shifted 16-channel windows per tile (4 TMA
-// boxes of 4 KB), nine K = 16 MMAs into four N = 16 accumulators (3 of the 16 columns are real output channels).
-// The epilogue adds the bias, applies tanh, reads the matching 12 input values (coalesced float2 rows of the fp32
-// NCHW image), and reduces the squared differences in a fixed order: thread (double) -> warp butterfly -> the four
-// warps in order -> partial[image][tile]; ae_mse_finish_kernel adds the 8 tile sums of an image in order.
-// ------------------------------------------------------------------------------------------
-// tanh(x) = sign(x) (1 - t) / (1 + t), t = exp(-2 |x|) in (0, 1]: one ex2.approx and one fast division; absolute error < 5e-7
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float t = __expf(-2.f * fabsf(x));
-  return copysignf(__fdividef(1.f - t, 1.f + t), x);
-}
-
 // tanh(x) = sign(x) (1 - 2 / (1 + 2^(2 log2(e) |x|))): ex2.approx + rcp.approx + 4 FP32 instructions (|x| > 44: 2^.. = inf,
-// 1 / inf = 0 -> +-1); absolute error < 4e-7, the class of fast_tanh above
+// 1 / inf = 0 -> +-1); absolute error < 4e-7, far inside the path's 16-bit operand error
 __device__ __forceinline__ float fast_tanh2(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * 2.8853900817779268f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
   return copysignf(fmaf(-2.f, r, 1.f), x);
-}
-
-struct Dec3Cfg {
-  static constexpr int kPart = 128 * 32;
-  static constexpr int kStageBytes = 4 * kPart;   // 16 KB per tile
-  static constexpr int kStages = 3;
-  static constexpr int kBBytes = 9 * 512;
-  static constexpr int kTmemCols = 128;           // 2 buffers x 4 classes x 16 columns
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBBytes + 512 + 256 + 1024;
-};
-
-template <bool HALF>
-__global__ void __launch_bounds__(192, 3)
-ae_dec3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ recon,
-                  double* __restrict__ partial, int total_tiles, int* err) {
-  using Cfg = Dec3Cfg;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t b_base = base + S * Cfg::kStageBytes;
-  const uint32_t bar0 = b_base + Cfg::kBBytes + 512;
-  double* s_part = reinterpret_cast<double*>(smem + (b_base + Cfg::kBBytes - base));   // [2][4] warp sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
-    mbar_init(wbar, 1);
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
-      for (int t = 0; t < 9; ++t) tma_load_2d(b_base + t * 512, &tmap_b, wbar, t * 16, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int img = tile >> 3, qy0 = (tile & 7) * 4;
-        if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 41)) break;
-        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        const uint32_t sa = base + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int part = 0; part < 4; ++part)     // part = dy*2 + dx
-          tma_load_4d(sa + part * Cfg::kPart, &tmap_a, full_bar(stage), 0, part & 1, qy0 + (part >> 1), img);
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_16(128, 16, HALF);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 42);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 43)) break;
-        if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 42)) break;
-        tc_fence_after();
-        const uint32_t sa = base + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int cls = 0; cls < 4; ++cls) {
-          const int py = cls >> 1, px = cls & 1;
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
-          bool first = true;
-#pragma unroll
-          for (int dy = 0; dy <= py; ++dy)
-#pragma unroll
-            for (int dx = 0; dx <= px; ++dx) {
-              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
-              umma_f16(tmem_d, umma_desc_sw32(sa + (dy * 2 + dx) * Cfg::kPart), umma_desc_sw32(b_base + tap * 512), idesc,
-                       first ? 0u : 1u);
-              first = false;
-            }
-        }
-        umma_commit(empty_bar(stage));
-        umma_commit(tfull_bar(acc));
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    const int qyl = row >> 5, qx = row & 31;
-    const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
-    int acc = 0, it = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int img = tile >> 3, qy = (tile & 7) * 4 + qyl;
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 44)) break;
-      tc_fence_after();
-      uint32_t v0[32], v1[32];   // classes (0,0) (0,1) | (1,0) (1,1), 16 columns each, channels 0..2 real
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
-      tmem_ld_32x32(taddr, v0);
-      tmem_ld_32x32(taddr + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      const float* xin = x + (size_t)img * 12288;
-      // the epilogue was the kernel's bound (125 M warp instructions per 8192 images, most of them libm tanhf and fp64
-      // adds): tanh through one ex2 + one division (absolute error < 5e-7, far inside the path's 16-bit operand error),
-      // the thread's 12 squares in fp32 (fixed order), fp64 only for the warp / tile sums
-      float sqf = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
-#pragma unroll
-        for (int py = 0; py < 2; ++py) {
-          const uint32_t* v = py ? v1 : v0;
-          const int off = (c * 64 + 2 * qy + py) * 64 + 2 * qx;
-          const float r0 = fast_tanh(__uint_as_float(v[c]) + bc), r1 = fast_tanh(__uint_as_float(v[16 + c]) + bc);
-          const float2 t = __ldg(reinterpret_cast<const float2*>(xin + off));
-          const float d0 = r0 - t.x, d1 = r1 - t.y;
-          sqf = fmaf(d0, d0, sqf);
-          sqf = fmaf(d1, d1, sqf);
-          if (recon) *reinterpret_cast<float2*>(recon + (size_t)img * 12288 + off) = make_float2(r0, r1);
-        }
-      }
-      double sq = (double)sqf;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      double* sp = s_part + (it & 1) * 4;
-      if (lane == 0) sp[lg] = sq;
-      named_bar_sync(1, 128);
-      if (row == 0) partial[tile] = ((sp[0] + sp[1]) + sp[2]) + sp[3];
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
 }
 
 template <int TILES>
@@ -2258,11 +1941,9 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   }
   if (!do_forward) return SG_OK;
   if (SEG == 2) SG_CUDA(cudaMemsetAsync(ws + L.a2 + kAct2 * SEG * batch, 0, 1024, st));   // slack the paired-tap view reads
-  // linear-halo forms of a4 / a5 (ae_dec2x_kernel / ae_dec3x_kernel): the default; the gather kernels serve unaligned inputs
-  const bool xform = SEG == 1 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)recon_out & 7) == 0;
   const int64_t cap = (int64_t)state().sm_count * 8;
   auto blocks = [&](int64_t items) { int64_t b = ceil_div(items, 256); return (unsigned)(b < cap ? b : cap); };
-  if (SEG == 1 && ((uintptr_t)x & 15) == 0) {   // tensor-core form (single-segment modes)
+  if constexpr (SEG == 1) {   // tensor-core form (single-segment modes; x is 16-byte aligned: ae_tc_args)
     CUtensorMap tx, tb;
     cuuint64_t xdims[4] = {64, 64, 3, (cuuint64_t)batch};        // fp32 NCHW input: (w, h, c, n)
     cuuint64_t xstr[3] = {64 * 4, 64 * 64 * 4, 3 * 64 * 64 * 4};
@@ -2309,8 +1990,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     // single-segment modes: both 7x7 layers in shifted-window form (weights on M, the image's pixels on N, taps = descriptor offsets)
     r = launch_k7x<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
     if (r != SG_OK) return r;
-    if (xform) r = launch_k7x<true, HALF, true>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
-    else r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);
+    r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);   // a4 in linear-halo form
     if (r != SG_OK) return r;
   } else {
     r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
@@ -2330,7 +2010,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     ae_dec1_kernel<SEG, HALF><<<grid, 192, Dec1Cfg::kSmemBytes, st>>>(ta, tb, h_params[7], bf(L.a4), (int)batch, err);
     SG_LAUNCH_CHECK();
   }
-  if (SEG == 1 && xform) {
+  if constexpr (SEG == 1) {   // L5 / L6 in linear-halo form
     CUtensorMap tb;
     cuuint64_t bdims[2] = {288, 16};
     cuuint64_t bstr[1] = {576};
@@ -2353,50 +2033,9 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
         tb, bf(L.a5), a5x_plane_elems(batch), h_params[11], x, recon_out, part, (int)tiles6, err);
     SG_LAUNCH_CHECK();
     ae_mse_finish_kernel<Dec3XCfg::kTilesPerImage><<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
-    SG_LAUNCH_CHECK();
-    return SG_OK;
-  }
-  if constexpr (SEG == 1) {   // tensor-core form (single-segment modes)
-    CUtensorMap ta, tb;
-    // a4 [n][16][16][32]: box = 16 channels (one half) x 16 columns x 8 rows of one image, shifted by (dx, dy)
-    cuuint64_t adims[4] = {32, 16, 16, (cuuint64_t)batch};
-    cuuint64_t astr[3] = {64, 1024, 16384};
-    cuuint32_t abox[4] = {16, 16, 8, 1};
-    r = encode_tmap(&ta, 4, bf(L.a4), adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (r != SG_OK) return r;
-    cuuint64_t bdims[2] = {288, 16};
-    cuuint64_t bstr[1] = {576};
-    cuuint32_t bbox[2] = {16, 16};
-    r = encode_tmap(&tb, 2, bf(L.w5), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (r != SG_OK) return r;
-    const int64_t tiles = 2 * batch;
-    const int grid = (int)(tiles < state().sm_count ? tiles : state().sm_count);   // (two CTAs per SM with 3 stages: no gain)
-    ae_dec2_tc_kernel<HALF><<<grid, 192, Dec2Cfg::kSmemBytes, st>>>(ta, tb, h_params[9], bf(L.a5), (int)batch, (int)tiles, err);
   } else {
     dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
-  }
-  SG_LAUNCH_CHECK();
-  if (SEG == 1 && ((uintptr_t)x & 7) == 0 && ((uintptr_t)recon_out & 7) == 0) {
-    CUtensorMap ta, tb;
-    // a5 [n][32][32][16]: box = 16 ch x 32 columns x 4 rows of one image, shifted by (dx, dy); row / column 32 -> zeros
-    cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
-    cuuint64_t astr[3] = {32, 1024, 32768};
-    cuuint32_t abox[4] = {16, 32, 4, 1};
-    r = encode_tmap(&ta, 4, bf(L.a5), adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (r != SG_OK) return r;
-    cuuint64_t bdims[2] = {144, 16};
-    cuuint64_t bstr[1] = {288};
-    cuuint32_t bbox[2] = {16, 16};
-    r = encode_tmap(&tb, 2, bf(L.w6), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (r != SG_OK) return r;
-    const int64_t tiles = 8 * batch;
-    const int64_t ctas = (int64_t)state().sm_count * 3;
-    double* part = reinterpret_cast<double*>(ws + L.part);
-    ae_dec3_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), 192, Dec3Cfg::kSmemBytes, st>>>(
-        ta, tb, h_params[11], x, recon_out, part, (int)tiles, err);
     SG_LAUNCH_CHECK();
-    ae_mse_finish_kernel<8><<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
-  } else {
     dec3_mse_kernel<SEG, HALF><<<(unsigned)batch, 256, 0, st>>>(bf(L.a5), h_params[10], h_params[11], x, recon_out, err_out);
   }
   SG_LAUNCH_CHECK();
@@ -2412,21 +2051,15 @@ int sg_ae_tc_init_attributes() {
   using namespace sg::aetc;
   SG_CUDA(cudaFuncSetAttribute(ae_k7_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                K7Cfg<64, false, true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_dec2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3XCfg::kSmemBytes));
@@ -2439,9 +2072,11 @@ size_t sg_ae_tc_workspace_bytes(int64_t max_batch, int conv_mode) {
   return sg::aetc::layout(max_batch < 1 ? 1 : max_batch, conv_mode == SG_CONV_BF16X3 ? 2 : 1).total;
 }
 
-static int ae_tc_args(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out) {
+static int ae_tc_args(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
+                      const float* recon_out) {
   SG_READY();
   SG_REQUIRE(x && h_params && workspace && err_out, "null pointer");
+  SG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)recon_out & 15) == 0, "x and recon_out must be 16-byte aligned");
   SG_REQUIRE(batch >= 0 && batch <= (1 << 20), "batch out of range");
   SG_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
   for (int i = 0; i < 12; ++i) SG_REQUIRE(h_params[i] != nullptr, "h_params must hold 12 device pointers (w, b) x 6");
@@ -2450,7 +2085,7 @@ static int ae_tc_args(const float* x, int64_t batch, const float* const* h_param
 
 int sg_ae_score_bf16(const float* x, int64_t batch, const float* const* h_params, void* workspace, float* err_out,
                      float* recon_out, void* stream) {
-  int r = ae_tc_args(x, batch, h_params, workspace, err_out);
+  int r = ae_tc_args(x, batch, h_params, workspace, err_out, recon_out);
   if (r != SG_OK || batch == 0) return r;
   return sg::aetc::score_impl<1>(x, batch, h_params, workspace, err_out, recon_out, sg::as_stream(stream));
 }
@@ -2467,7 +2102,7 @@ static int ae_tc_dispatch(const float* x, int64_t batch, const float* const* h_p
 int sg_ae_score_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
                    float* err_out, float* recon_out, void* stream) {
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
-  int r = ae_tc_args(x, batch, h_params, workspace, err_out);
+  int r = ae_tc_args(x, batch, h_params, workspace, err_out, recon_out);
   if (r != SG_OK || batch == 0) return r;
   return ae_tc_dispatch(x, batch, h_params, workspace, conv_mode, err_out, recon_out, stream, true, true);
 }
@@ -2483,7 +2118,7 @@ int sg_ae_pack_tc(const float* const* h_params, void* workspace, int conv_mode, 
 int sg_ae_forward_tc(const float* x, int64_t batch, const float* const* h_params, void* workspace, int conv_mode,
                      float* err_out, float* recon_out, void* stream) {
   SG_REQUIRE(conv_mode == SG_CONV_BF16 || conv_mode == SG_CONV_BF16X3 || conv_mode == SG_CONV_FP16, "conv_mode");
-  int r = ae_tc_args(x, batch, h_params, workspace, err_out);
+  int r = ae_tc_args(x, batch, h_params, workspace, err_out, recon_out);
   if (r != SG_OK || batch == 0) return r;
   return ae_tc_dispatch(x, batch, h_params, workspace, conv_mode, err_out, recon_out, stream, false, true);
 }

@@ -559,7 +559,20 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float* __restrict_
 __device__ __forceinline__ void warp_partial_sums(const float* __restrict__ partial, int blocks, int C, int ch, int lane, double& s,
                                                   double& q) {
   s = 0.0; q = 0.0;
-  for (int b = lane; b < blocks; b += 32) { s += (double)partial[((size_t)b * 2) * C + ch]; q += (double)partial[((size_t)b * 2 + 1) * C + ch]; }
+  // eight row blocks per trip, all sixteen loads issued before the first add: the rolled loop paid one L2 round trip per
+  // block (14 us for the 512 blocks of layer 2); the order of the adds is unchanged
+  for (int b0 = lane; b0 < blocks; b0 += 32 * 8) {
+    float a[8], c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = b0 + 32 * u;
+      const bool in = b < blocks;
+      a[u] = in ? partial[((size_t)b * 2) * C + ch] : 0.f;
+      c[u] = in ? partial[((size_t)b * 2 + 1) * C + ch] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s += (double)a[u]; q += (double)c[u]; }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
 }
@@ -788,10 +801,20 @@ __global__ void __launch_bounds__(256) head_bwd_dw_kernel(const float* __restric
   float acc = 0.f;
   const int Cp = split ? 1024 : 512;
   const int at = (t >> 9) * Cp + (t & 511);
-  for (int64_t b = slice; b < batch; b += 4) {
-    float a = __half2float(act4[b * 16 * Cp + at]);
-    if (split) a = fmaf(__half2float(act4[b * 16 * Cp + at + 512]), kLoInv, a);
-    acc = fmaf(dlogit[b], a, acc);
+  for (int64_t b0 = slice; b0 < batch; b0 += 32) {    // eight images per trip, loads first (same order of the adds)
+    float av[8], dv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t b = b0 + 4 * u;
+      const bool in = b < batch;
+      float a = in ? __half2float(act4[b * 16 * Cp + at]) : 0.f;
+      if (split && in) a = fmaf(__half2float(act4[b * 16 * Cp + at + 512]), kLoInv, a);
+      av[u] = a;
+      dv[u] = in ? dlogit[b] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (b0 + 4 * u < batch) acc = fmaf(dv[u], av[u], acc);
   }
   red[slice][col] = acc;
   __syncthreads();
@@ -820,6 +843,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const size_t step = (size_t)cout * ldn;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int s = 0;
+    for (; s + 16 <= splits; s += 16) {        // sixteen loads in flight per trip (one L2 round trip instead of four); the
+      float v[16];                             // association below is that of the 4-wide loop: bit-identical sums
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = src[(size_t)(s + u) * step];
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) { a0 += v[u]; a1 += v[u + 1]; a2 += v[u + 2]; a3 += v[u + 3]; }
+    }
     for (; s + 4 <= splits; s += 4) {          // fixed association: deterministic
       a0 += src[(size_t)s * step]; a1 += src[(size_t)(s + 1) * step]; a2 += src[(size_t)(s + 2) * step]; a3 += src[(size_t)(s + 3) * step];
     }

@@ -436,12 +436,13 @@ def test_select_step_peer_single_rank(sb):
         L.check(lib.sg_peer_free(buf), "sg_peer_free")
 
 
-def test_autoencoder_linear_halo_forms_reconstruction_and_unaligned_fallback(sb):
-    """The decoder's last two layers run in linear-halo form when the input is 16-byte aligned (one contiguous bulk copy per
-    channel group, filter shifts as descriptor offsets) and in the gather form otherwise.  Through the C ABI: the
-    reconstruction written by the linear-halo path equals the oracle's AutoEncoder forward ("#autoencoder.py:269-291"), the
-    per-sample errors equal the mean squared difference of that reconstruction, and an input shifted by 4 bytes (gather
-    path) gives the same errors within the mode's operand rounding -- for image counts around the tile sizes."""
+def test_autoencoder_linear_halo_forms_reconstruction_and_alignment_contract(sb):
+    """The decoder's last two layers run in linear-halo form (one contiguous bulk copy per channel group, filter shifts as
+    descriptor offsets, zero halo written by the producing layer).  Through the C ABI: the reconstruction equals the oracle's
+    AutoEncoder forward ("#autoencoder.py:269-291"), the per-sample errors equal the mean squared difference of that
+    reconstruction ("#autoencoder.py:315-316") -- for image counts around the tile sizes, twice in the same workspace (the
+    halo must survive reuse with another batch size) -- and an input that is not 16-byte aligned is refused with SG_EINVAL
+    instead of reaching a kernel."""
     from strainer_gan_b200 import api
     dev = torch.device("cuda", 0)
     lib = api._lib_for(dev)
@@ -454,12 +455,13 @@ def test_autoencoder_linear_halo_forms_reconstruction_and_unaligned_fallback(sb)
     params = api._ae_params(ae, dev)
     arr = (api.L.P * 12)(*[t.data_ptr() for t in params])
     for mode, tol in ((api.L.SG_CONV_FP16, 2e-3), (api.L.SG_CONV_BF16, 2e-2)):
-        for n in (1, 2, 9, 150):
+        ws = api._aligned_empty(lib.sg_ae_tc_workspace_bytes(150, mode), dev)
+        ws.fill_(0x7f)                                     # NaN patterns wherever a kernel forgets to write a halo
+        for n in (150, 1, 9, 2, 150):
             x = torch.from_numpy(O.synth_images(40, n))
             with torch.no_grad():
                 want = ae(x).numpy()
             xd = x.to(dev)
-            ws = api._aligned_empty(lib.sg_ae_tc_workspace_bytes(n, mode), dev)
             err = torch.empty(n, device=dev)
             rec = torch.full((n, 3, 64, 64), float("nan"), device=dev)
             api.L.check(lib.sg_ae_score_tc(api._p(xd), n, arr, api._p(ws), mode, api._p(err), api._p(rec), api._stream()), "ae")
@@ -470,12 +472,10 @@ def test_autoencoder_linear_halo_forms_reconstruction_and_unaligned_fallback(sb)
             mse = ((r.astype(np.float64) - x.numpy()) ** 2).reshape(n, -1).mean(1)
             e = err.cpu().numpy()
             assert (np.abs(e - mse) / mse).max() <= 1e-5, (mode, n)
-            # the same images 4 bytes further (not 16-byte aligned): the gather kernels
-            buf = torch.empty(n * 12288 + 4, device=dev)
-            xu = buf[1:1 + n * 12288].view(n, 3, 64, 64)
-            xu.copy_(xd)
-            assert xu.data_ptr() % 16 == 4
-            err_u = torch.empty(n, device=dev)
-            api.L.check(lib.sg_ae_score_tc(api._p(xu), n, arr, api._p(ws), mode, api._p(err_u), api.L.P(0), api._stream()), "ae")
-            api.L.check(lib.sg_ae_bf16_check(api._p(ws), api._stream()), "check")
-            assert (np.abs(err_u.cpu().numpy() - e) / e).max() <= tol, (mode, n)    # other kernels, same 16-bit operand class
+        # the same images 4 bytes further: refused, nothing launched
+        buf = torch.empty(2 * 12288 + 4, device=dev)
+        xu = buf[1:1 + 2 * 12288].view(2, 3, 64, 64)
+        assert xu.data_ptr() % 16 == 4
+        rc = lib.sg_ae_score_tc(api._p(xu), 2, arr, api._p(ws), mode, api._p(err), api.L.P(0), api._stream())
+        assert rc == -1, rc          # SG_EINVAL
+        torch.cuda.synchronize()
