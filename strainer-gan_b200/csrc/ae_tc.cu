@@ -849,7 +849,7 @@ struct Enc1Cfg {
 };
 
 template <bool HALF>
-__global__ void __launch_bounds__(320, 2)
+__global__ void __launch_bounds__(320, 3)
 ae_enc1_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int total_tiles, int* err) {
   using Cfg = Enc1Cfg;
@@ -1956,7 +1956,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     r1 = encode_tmap(&tb, 2, bf(L.w1), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r1 != SG_OK) return r1;
     const int64_t tiles = batch * 8;
-    const int64_t ctas = (int64_t)state().sm_count * 2;
+    const int64_t ctas = (int64_t)state().sm_count * 3;    // 3 CTAs per SM: the kernel is latency bound (34 % issue-active at 2)
     ae_enc1_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), Enc1Cfg::kThreads, Enc1Cfg::kSmemBytes, st>>>(
         tx, tb, h_params[1], bf(L.a1), (int)tiles, err);
   } else {
