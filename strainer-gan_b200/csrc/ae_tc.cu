@@ -57,6 +57,11 @@ constexpr int kWeightCopies = 8;
 // Plane sizes in 16-bit elements, including the slack the last tile's window reads.
 __host__ __device__ inline size_t a4x_plane_elems(int64_t batch) { return (size_t)((batch * 289 + 127) / 128 * 128 + 32) * 8; }
 __host__ __device__ inline size_t a5x_plane_elems(int64_t batch) { return (size_t)(batch * 1089 + 64) * 8; }
+// a1 (input of the stride-2 layer L2) additionally split by pixel parity: [ci / 8][row parity * 2 + column parity][image]
+// [17 x 17][8], position = (i + 1) * 17 + (j + 1) for pixel (2 i + ry, 2 j + rx) -- zero row 0 and column 0 (the padding of
+// Conv2d(k3, s2, p1): tap (ky, kx) of output (oy, ox) is plane ((ky != 1), (kx != 1)) at position oy * 17 + ox + shift,
+// shift = (ky ? 17 : 0) + (kx ? 1 : 0)).  Same plane size as a4.
+__host__ __device__ inline size_t a1x_plane_elems(int64_t batch) { return a4x_plane_elems(batch); }
 struct Layout {
   size_t flag, w1, w2, w5, w6, w3, w4, w3t, w4t, a1, a2, a3, a4, a5, part, total;
 };
@@ -72,7 +77,8 @@ static Layout layout(int64_t batch, int seg) {
   L.w4 = o; o += align_up((size_t)32 * kKs4 * seg * 64 * 2, 1024);
   L.w3t = o; o += align_up((size_t)kWeightCopies * 4 * 7 * 128 * 32 * 2, 1024);   // shifted-window forms of the 7x7 weights
   L.w4t = o; o += align_up((size_t)kWeightCopies * 2 * 7 * 128 * 64 * 2, 1024);   // (single-segment modes), kWeightCopies replicas
-  L.a1 = o; o += align_up(kAct1 * seg * batch, 1024);
+  const size_t a1b = seg == 1 ? 8 * a1x_plane_elems(batch) * 2 : 0;
+  L.a1 = o; o += align_up(kAct1 * seg * batch > a1b ? kAct1 * seg * batch : a1b, 1024);
   L.a2 = o; o += align_up(kAct2 * seg * batch + 1024, 1024);   // + zeroed slack: the paired-tap view reads one pixel past the end
   L.a3 = o; o += align_up(kAct3 * seg * batch, 1024);
   // single-segment modes: a4 / a5 in the linear-halo forms of ae_dec2x_kernel / ae_dec3x_kernel (a4x_plane_elems ...)
@@ -851,7 +857,7 @@ struct Enc1Cfg {
 template <bool HALF>
 __global__ void __launch_bounds__(320, 3)
 ae_enc1_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int total_tiles, int* err) {
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t out_plane, int total_tiles, int* err) {
   using Cfg = Enc1Cfg;
   constexpr int SA = Cfg::kAStages, SR = Cfg::kRawStages;
   extern __shared__ uint8_t smem_raw[];
@@ -994,9 +1000,21 @@ ae_enc1_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         pk[j] = pk2<HALF>(fmaxf(__uint_as_float(v[2 * j]) + bo[2 * j], 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + bo[2 * j + 1], 0.f));
-      uint4* d = reinterpret_cast<uint4*>(out + (((size_t)n * 32 + oh0 + (row >> 5)) * 32 + (row & 31)) * 16);
-      d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      // a1 in parity-plane linear-halo form (a1x_plane_elems): the pixel's two channel groups go to plane (oh & 1, ow & 1) at
+      // position ((oh >> 1) + 1) * 17 + (ow >> 1) + 1; the pixels of the first two rows / columns also write the zero row /
+      // column in front of their plane
+      const int oh = oh0 + (row >> 5), ow = row & 31;
+      const int pos = ((oh >> 1) + 1) * 17 + (ow >> 1) + 1;
+      __nv_bfloat16* o0 = out + (size_t)((oh & 1) * 2 + (ow & 1)) * out_plane + ((size_t)n * 289 + pos) * 8;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint4* d = reinterpret_cast<uint4*>(o0 + (size_t)g * 4 * out_plane);
+        d[0] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        if (ow < 2) d[-1] = z;
+        if (oh < 2) d[-17] = z;
+        if (ow < 2 && oh < 2) d[-18] = z;
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -1150,6 +1168,147 @@ ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (img < n_img) {
         uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q * 256] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// L2 in LINEAR-HALO form (see ae_dec2x_kernel below for the idea): a1 arrives split by pixel parity (a1x_plane_elems), so
+// the stride-2 taps become plain shifts: tap (ky, kx) of the 128 consecutive output positions of a tile (17-pitch, column 16
+// and row 16 of an image are dead positions) is plane ((ky != 1), (kx != 1)) of the SAME contiguous copy, (ky ? 17 : 0) +
+// (kx ? 1 : 0) positions further.  A tile's input: 8 bulk copies of 2.3 KB (2 channel groups x 4 planes) instead of 9
+// element-strided TMA boxes of 4 KB whose 32-byte rows ran at TMA's request rate.
+struct Enc2XCfg {
+  static constexpr int kWin = 128 + 18;
+  static constexpr int kPartBytes = kWin * 16;          // 2 336: one (group, plane) window
+  static constexpr int kStageBytes = 8 * kPartBytes;    // 18 688 per tile
+  static constexpr int kStages = 3;
+  static constexpr int kBBytes = 9 * 32 * 32;           // [tap][32 oc x 16 ic], SWIZZLE_32B
+  static constexpr int kTmemCols = 64;                  // 2 accumulators x 32 columns
+  static constexpr int kSmemBytes = kBBytes + kStages * kStageBytes + 256 + 1024;
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(192, 3)
+ae_enc2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
+                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
+  using Cfg = Enc2XCfg;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t b_base = base;
+  const uint32_t a_base = base + Cfg::kBBytes;
+  const uint32_t bar0 = a_base + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(wbar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_base + tap * 1024, &tmap_b, wbar, tap * 16, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (!mbar_wait_sleep(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 11)) break;
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const uint32_t sa = a_base + stage * Cfg::kStageBytes;
+        const __nv_bfloat16* src = in + (size_t)tile * (128 * 8);
+#pragma unroll
+        for (int part = 0; part < 8; ++part)     // part = group * 4 + plane
+          bulk_load_1d(sa + part * Cfg::kPartBytes, src + (size_t)part * in_plane, Cfg::kPartBytes, full_bar(stage));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(128, 32, HALF);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool ok = mbar_wait_sleep(wbar, 0, s_abort, err, kErrBase + 12);
+      const uint64_t bdesc0 = umma_desc_sw32(b_base);
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait_sleep(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 13)) break;
+        if (!mbar_wait_sleep(full_bar(stage), phase, s_abort, err, kErrBase + 12)) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
+        // K = 16 = the two channel groups: LBO = the distance between the groups' copies of one plane
+        const uint64_t adesc = umma_desc_nosw(a_base + stage * Cfg::kStageBytes, 4 * Cfg::kPartBytes, 128);
+#pragma unroll
+        for (int kr = 0; kr < 3; ++kr)
+#pragma unroll
+          for (int kc = 0; kc < 3; ++kc) {
+            const int plane = (kr != 1 ? 2 : 0) + (kc != 1 ? 1 : 0);
+            const int shift = (kr ? 17 : 0) + (kc ? 1 : 0);
+            umma_f16(tmem_d, adesc + (uint64_t)((plane * Cfg::kPartBytes + shift * 16) >> 4),
+                     bdesc0 + (uint64_t)(((kr * 3 + kc) * 1024) >> 4), idesc, (uint32_t)((kr | kc) != 0));
+          }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    float bo[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bo[c] = __ldg(bias + c);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int p = tile * 128 + row;                 // position in the batch's [image][17 x 17] sequence
+      const int img = p / 289, rem = p - img * 289;
+      const int oy = rem / 17, ox = rem - oy * 17;
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 14)) break;
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (img < n_img && oy < 16 && ox < 16) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[2 * j], 0.f);
+          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[2 * j + 1], 0.f);
+          pk[j] = pk2<HALF>(a, b);
+        }
+        // a2 in channel-group-major form [img][ci / 8][256 pixels][8 ci] (the 7x7 kernel's operand layout)
+        uint4* d = reinterpret_cast<uint4*>(out + (size_t)img * 8192 + (size_t)(oy * 16 + ox) * 8);
 #pragma unroll
         for (int q = 0; q < 4; ++q) d[q * 256] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
@@ -1958,29 +2117,22 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     const int64_t tiles = batch * 8;
     const int64_t ctas = (int64_t)state().sm_count * 3;    // 3 CTAs per SM: the kernel is latency bound (34 % issue-active at 2)
     ae_enc1_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), Enc1Cfg::kThreads, Enc1Cfg::kSmemBytes, st>>>(
-        tx, tb, h_params[1], bf(L.a1), (int)tiles, err);
+        tx, tb, h_params[1], bf(L.a1), a1x_plane_elems(batch), (int)tiles, err);
   } else {
     enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
   }
   SG_LAUNCH_CHECK();
   if constexpr (SEG == 1) {   // tensor-core form (single-segment modes); the CUDA-core form serves the fp32-parity mode
-    CUtensorMap ta, tb;
-    // a1 [n][32][32][16]: box = 16 ch x (16 columns at stride 2) x (8 rows at stride 2) of one image
-    cuuint64_t adims[4] = {16, 32, 32, (cuuint64_t)batch};
-    cuuint64_t astr[3] = {32, 1024, 32768};
-    cuuint32_t abox[4] = {16, 32, 16, 1};
-    cuuint32_t aes[4] = {1, 2, 2, 1};
-    int r2 = encode_tmap(&ta, 4, bf(L.a1), adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, aes);
-    if (r2 != SG_OK) return r2;
+    CUtensorMap tb;
     cuuint64_t bdims[2] = {144, 32};
     cuuint64_t bstr[1] = {288};
     cuuint32_t bbox[2] = {16, 32};
-    r2 = encode_tmap(&tb, 2, bf(L.w2), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
+    int r2 = encode_tmap(&tb, 2, bf(L.w2), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r2 != SG_OK) return r2;
-    const int64_t tiles = 2 * batch;
-    const int64_t ctas2 = (int64_t)state().sm_count * 2;      // 2 CTAs per SM (82 KB of shared memory each): the strided-element
-    const int grid = (int)(tiles < ctas2 ? tiles : ctas2);    // TMA boxes are latency bound, a second CTA doubles the loads in flight
-    ae_enc2_tc_kernel<HALF><<<grid, 192, Enc2Cfg::kSmemBytes, st>>>(ta, tb, h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
+    const int64_t tiles = ceil_div(batch * 289, 128);
+    const int64_t ctas2 = (int64_t)state().sm_count * 3;
+    ae_enc2x_kernel<HALF><<<(int)(tiles < ctas2 ? tiles : ctas2), 192, Enc2XCfg::kSmemBytes, st>>>(
+        tb, bf(L.a1), a1x_plane_elems(batch), h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
   } else {
     enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
   }
@@ -2053,8 +2205,8 @@ int sg_ae_tc_init_attributes() {
                                K7Cfg<64, false, true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc1Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_enc2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2XCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_enc2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
