@@ -5,8 +5,8 @@
 // 86 % of the auto-encoder's 46.6 MFLOP/sample sit in its two 7x7 layers.  Every layer of the single-segment modes (bf16 /
 // fp16 operands, fp32 accumulators in TMEM) is a tcgen05 kernel; activations are 16-bit:
 //
-//   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> [32][32][16]             ae_enc1_tc_kernel (input conversion fused)
-//   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> [ci / 8][16 x 16][8]                   ae_enc2_tc_kernel (stride-2 TMA boxes)
+//   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> [ci / 8][pixel parity][17 x 17 with zero halo][8]   ae_enc1_tc_kernel (input conversion fused)
+//   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> [ci / 8][16 x 16][8]                   ae_enc2x_kernel (linear-halo form over parity planes)
 //   L3 enc Conv 32->64 k7                -> [co / 8][10 x 10][8]                   ae_k7x_kernel<false>: shifted-window form
 //   L4 dec ConvT 64->32 k7 + ReLU        -> [co / 8][17 x 17 with zero halo][8]    ae_k7x_kernel<true>
 //   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> [co / 8][33 x 33 with zero halo][8]  ae_dec2x_kernel (linear-halo form)
@@ -1037,151 +1037,11 @@ __global__ void pack_enc1_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------
-// L2 (enc Conv 16->32 k3 s2 p1 + ReLU) on tcgen05 (bf16 conv mode).  One tile = 8 x 16 output pixels of one image
-// (M = 128), N = 32, one MMA (K = 16 input channels) per filter tap.  The A operand of tap (ky, kx) is the set of
-// input pixels (2 oy - 1 + ky, 2 ox - 1 + kx): ONE 4-D TMA box with traversal stride 2 in x and y (start coordinate
-// -1 = the zero padding), landing as 128 dense 32-byte rows (SWIZZLE_32B).  The nine 1 KB weight tiles stay in shared
-// memory for the whole kernel.  The CUDA-core form (one output pixel per thread, 4 FMAs per shared-memory load)
-// took 0.67 ms per 8 192 images = 29 TFLOP/s.
+// L2 (enc Conv 16->32 k3 s2 p1 + ReLU) on tcgen05: one tile = 128 output positions (M = 128), N = 32, one MMA (K = 16 input
+// channels) per filter tap, the nine 1 KB weight tiles resident in shared memory.  (The first tensor-core form fetched the
+// input pixels (2 oy - 1 + ky, 2 ox - 1 + kx) of every tap as its own 4-D TMA box with traversal stride 2: 97 us per 8 192
+// images, bound by TMA's rate of 32-byte row requests; the CUDA-core form before it: 0.67 ms.)
 // ------------------------------------------------------------------------------------------
-struct Enc2Cfg {
-  static constexpr int kABytes = 128 * 32;     // one tap of one tile
-  static constexpr int kStages = 6;            // stages of three taps (one filter row): two tiles in flight
-  static constexpr int kBBytes = 9 * 32 * 32;  // [tap][32 oc x 16 ic]
-  static constexpr int kTmemCols = 64;         // 2 accumulators x 32 columns
-  static constexpr int kSmemBytes = kStages * 3 * kABytes + kBBytes + 512 + 1024;
-};
-
-template <bool HALF>
-__global__ void __launch_bounds__(192, 2)
-ae_enc2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
-  using Cfg = Enc2Cfg;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t b_base = base + S * 3 * Cfg::kABytes;
-  const uint32_t bar0 = b_base + Cfg::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
-  const uint32_t wbar = bar0 + 8u * (2 * S + 4);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * S + 5);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * S + 6);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
-    mbar_init(wbar, 1);
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, Cfg::kBBytes);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_base + tap * 1024, &tmap_b, wbar, tap * 16, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        const int img = tile >> 1, oy0 = (tile & 1) * 8;
-        // one stage = the three taps of a filter row (three boxes on one barrier): the MMA issuer waits, issues and commits
-        // once per row instead of once per tap (its instruction stream, not the tensor pipe, bounds a layer of N = 32 MMAs)
-#pragma unroll
-        for (int kr = 0; kr < 3; ++kr) {
-          if (!mbar_wait(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 11)) { ok = false; break; }
-          mbar_arrive_expect_tx(full_bar(stage), 3 * Cfg::kABytes);
-#pragma unroll
-          for (int kc = 0; kc < 3; ++kc)
-            tma_load_4d(base + (stage * 3 + kc) * Cfg::kABytes, &tmap_a, full_bar(stage), 0, kc - 1, 2 * oy0 - 1 + kr, img);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_16(128, 32, HALF);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      bool ok = mbar_wait(wbar, 0, s_abort, err, kErrBase + 12);
-      const uint64_t bdesc0 = umma_desc_sw32(b_base);
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 13)) break;
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 32);
-#pragma unroll
-        for (int kr = 0; kr < 3; ++kr) {
-          if (!mbar_wait(full_bar(stage), phase, s_abort, err, kErrBase + 12)) { ok = false; break; }
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_sw32(base + stage * 3 * Cfg::kABytes);
-#pragma unroll
-          for (int kc = 0; kc < 3; ++kc)
-            umma_f16(tmem_d, adesc + (uint64_t)((kc * Cfg::kABytes) >> 4), bdesc0 + (uint64_t)(((kr * 3 + kc) * 1024) >> 4), idesc,
-                     (uint32_t)((kr | kc) != 0));
-          umma_commit(empty_bar(stage));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        if (!ok) break;
-        umma_commit(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
-    }
-  } else {
-    const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    float bo[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) bo[c] = __ldg(bias + c);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int img = tile >> 1;
-      // a2 in channel-group-major form [img][ci / 8][256 pixels][8 ci]: the layout the 7x7 kernel's operand has in shared
-      // memory (one dense TMA box per image), and 512 contiguous bytes per warp and store
-      __nv_bfloat16* dst = out + (size_t)img * 8192 + (size_t)((tile & 1) * 128 + row) * 8;
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 14)) break;
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 32), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[2 * j], 0.f);
-        const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[2 * j + 1], 0.f);
-        pk[j] = pk2<HALF>(a, b);
-      }
-      if (img < n_img) {
-        uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d[q * 256] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
 // L2 in LINEAR-HALO form (see ae_dec2x_kernel below for the idea): a1 arrives split by pixel parity (a1x_plane_elems), so
 // the stride-2 taps become plain shifts: tap (ky, kx) of the 128 consecutive output positions of a tile (17-pitch, column 16
 // and row 16 of an image are dead positions) is plane ((ky != 1), (kx != 1)) of the SAME contiguous copy, (ky ? 17 : 0) +
