@@ -56,7 +56,11 @@ constexpr int kWeightCopies = 8;
 // positions later, for any run of consecutive positions -- one contiguous copy per group feeds every tap of a tile.
 // Plane sizes in 16-bit elements, including the slack the last tile's window reads.
 __host__ __device__ inline size_t a4x_plane_elems(int64_t batch) { return (size_t)((batch * 289 + 127) / 128 * 128 + 32) * 8; }
-__host__ __device__ inline size_t a5x_plane_elems(int64_t batch) { return (size_t)(batch * 1089 + 64) * 8; }
+// a5: rows at a pitch of 34 positions (33 x 34 per image; column 33 is never read by a live row): every pixel PAIR (2 qx,
+// 2 qx + 1) then starts at an even position = 32-byte aligned, and L5's epilogue writes it with ONE 256-bit store -- a warp
+// covers 1 KB of whole sectors (16-byte stores at a 32-byte stride sent half-written sectors to L2 twice).
+constexpr int kA5Pitch = 34, kA5Image = 33 * 34;
+__host__ __device__ inline size_t a5x_plane_elems(int64_t batch) { return (size_t)(batch * kA5Image + 64) * 8; }
 // a1 (input of the stride-2 layer L2) additionally split by pixel parity: [ci / 8][row parity * 2 + column parity][image]
 // [17 x 17][8], position = (i + 1) * 17 + (j + 1) for pixel (2 i + ry, 2 j + rx) -- zero row 0 and column 0 (the padding of
 // Conv2d(k3, s2, p1): tap (ky, kx) of output (oy, ox) is plane ((ky != 1), (kx != 1)) at position oy * 17 + ox + shift,
@@ -85,7 +89,7 @@ static Layout layout(int64_t batch, int seg) {
   const size_t a4b = seg == 1 ? 4 * a4x_plane_elems(batch) * 2 : 0, a5b = seg == 1 ? 2 * a5x_plane_elems(batch) * 2 : 0;
   L.a4 = o; o += align_up(kAct4 * seg * batch > a4b ? kAct4 * seg * batch : a4b, 1024);
   L.a5 = o; o += align_up(kAct5 * seg * batch > a5b ? kAct5 * seg * batch : a5b, 1024);
-  L.part = o; o += align_up((size_t)batch * 9 * sizeof(double), 1024);   // per-tile squared-error sums (dec3 tensor-core forms)
+  L.part = o; o += align_up((size_t)batch * 9 * 4 * sizeof(float), 1024);   // squared-error sums per (tile, epilogue warp) of L6
   L.total = o;
   return L;
 }
@@ -1198,13 +1202,24 @@ __global__ void pack_enc2_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 // kernel tap index along one axis = dec2_tap_k(parity, shift); the four classes have their own N = 16 accumulators side by
 // side in TMEM (ae_dec2x_kernel / ae_dec3x_kernel below).
 __host__ __device__ constexpr int dec2_tap_k(int parity, int d) { return parity == 0 ? 1 : (d ? 0 : 2); }
+// The classes sit in TMEM in the order (0,0) (0,1) (1,1) (1,0) (16 columns each): the classes that use one input shift are
+// then ADJACENT columns, and one MMA per shift serves all of them -- shift (0,0): all four (N = 64), (0,1): the px = 1 classes
+// (N = 32 from column 16), (1,0): the py = 1 classes (N = 32 from column 32), (1,1): class (1,1) (N = 16 at column 32).
+// 4 MMAs per K = 16 instead of 9, and the activation window of a shift is read from shared memory once instead of once per
+// tap (the N = 16 MMAs were bound by exactly those reads: 4 KB of A operand per 8 tensor cycles).  The weights are packed as
+// nine 16-row sub-tiles in that order; sub-tile slot -> filter tap ky * 3 + kx:
+__host__ __device__ constexpr int dec2_slot_tap(int slot) {
+  return slot == 0 ? 4 : slot == 1 ? 5 : slot == 2 ? 8 : slot == 3 ? 7 : slot == 4 ? 3 : slot == 5 ? 6 : slot == 6 ? 2 : slot == 7 ? 1 : 0;
+}
+__host__ __device__ constexpr int dec2_class_pos(int py, int px) { return py == 0 ? px : (px ? 2 : 3); }
 
-// dec2 weights [32][16][3][3] (ConvTranspose2d: in, out, ky, kx) -> bf16 [oc][(tap*2 + half)*16 + icl], ic = half*16 + icl
+// dec2 weights [32][16][3][3] (ConvTranspose2d: in, out, ky, kx) -> 16-bit [oc][(half*9 + slot)*16 + icl], ic = half*16 + icl,
+// tap = dec2_slot_tap(slot)
 __global__ void pack_dec2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 16 * 288) {
-    const int oc = i / 288, r = i - oc * 288, t = r >> 4, icl = r & 15;
-    const int tap = t >> 1, ic = (t & 1) * 16 + icl;
+    const int oc = i / 288, r = i - oc * 288, t = r >> 4, icl = r & 15;      // sub-tile t = half * 9 + slot
+    const int tap = dec2_slot_tap(t % 9), ic = (t / 9) * 16 + icl;
     const float v = w[(ic * 16 + oc) * 9 + tap];
     reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
   }
@@ -1219,22 +1234,28 @@ __device__ __forceinline__ float fast_tanh2(float x) {
   return copysignf(fmaf(-2.f, r, 1.f), x);
 }
 
+// per-sample mean of the squared errors from the fp32 partial sums [image][tile][epilogue warp]: the four warps of a tile,
+// then the tiles, in fp64 and in a fixed order
 template <int TILES>
-__global__ void ae_mse_finish_kernel(const double* __restrict__ partial, int64_t n_img, float* __restrict__ err) {
+__global__ void ae_mse_finish_kernel(const float* __restrict__ partial, int64_t n_img, float* __restrict__ err) {
   const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n < n_img) {
+    const float4* p = reinterpret_cast<const float4*>(partial + n * (TILES * 4));
     double s = 0.0;
 #pragma unroll
-    for (int t = 0; t < TILES; ++t) s += partial[n * TILES + t];
+    for (int t = 0; t < TILES; ++t) {
+      const float4 w = p[t];
+      s += (((double)w.x + (double)w.y) + (double)w.z) + (double)w.w;
+    }
     err[n] = (float)(s / 12288.0);
   }
 }
 
-// dec3 weights [16][3][3][3] (ConvTranspose2d: in, out, ky, kx) -> 16-bit [oc][tap*16 + ic], rows oc >= 3 zero
+// dec3 weights [16][3][3][3] (ConvTranspose2d: in, out, ky, kx) -> 16-bit [oc][slot*16 + ic], tap = dec2_slot_tap(slot), rows oc >= 3 zero
 __global__ void pack_dec3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 16 * 144) {
-    const int oc = i / 144, r = i - oc * 144, tap = r >> 4, ic = r & 15;
+    const int oc = i / 144, r = i - oc * 144, tap = dec2_slot_tap(r >> 4), ic = r & 15;
     const float v = oc < 3 ? w[(ic * 3 + oc) * 9 + tap] : 0.f;
     reinterpret_cast<uint16_t*>(p)[i] = half ? pk1<true>(v) : pk1<false>(v);
   }
@@ -1250,7 +1271,7 @@ __global__ void pack_dec3_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 // 4 x 2.3 KB (L5) / 2 x 2.6 KB (L6) instead of 32 / 16 KB.  The zero column doubles as left padding of the next row, the zero
 // row as bottom padding; accumulator rows that land on halo positions are skipped (L5: they write the zeros of L6's halo).
 //   L5: tiles of 128 consecutive positions of the whole batch (11 % halo rows)
-//   L6: 9 tiles of 121 positions per image (the tile -> image mapping, and with it the order of the squared-error sums,
+//   L6: 9 tiles of 125 positions per image (rows at a pitch of 34, see kA5Pitch) (the tile -> image mapping, and with it the order of the squared-error sums,
 //       does not depend on the image's index in the batch: scores are chunk invariant)
 // ------------------------------------------------------------------------------------------
 struct Dec2XCfg {
@@ -1264,7 +1285,7 @@ struct Dec2XCfg {
 };
 
 template <bool HALF>
-__global__ void __launch_bounds__(192, 3)
+__global__ void __launch_bounds__(192, 4)
 ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t out_plane, int n_img, int total_tiles,
                 int* err) {
@@ -1328,23 +1349,15 @@ ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
         if (!mbar_wait_sleep(full_bar(stage), phase, s_abort, err, kErrBase + 22)) break;
         tc_fence_after();
         const uint64_t adesc = umma_desc_nosw(a_base + stage * Cfg::kStageBytes, Cfg::kGroupBytes, 128);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
 #pragma unroll
-        for (int cls = 0; cls < 4; ++cls) {
-          const int py = cls >> 1, px = cls & 1;
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
-          bool first = true;
-#pragma unroll
-          for (int dy = 0; dy <= py; ++dy)
-#pragma unroll
-            for (int dx = 0; dx <= px; ++dx) {
-              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {   // channels 16 half .. 16 half + 15 = groups 2 half, 2 half + 1
-                umma_f16(tmem_d, adesc + (uint64_t)(((dy * 17 + dx) * 16 + half * 2 * Cfg::kGroupBytes) >> 4),
-                         umma_desc_sw32(b_base + (tap * 2 + half) * 512), idesc, first ? 0u : 1u);
-                first = false;
-              }
-            }
+        for (int half = 0; half < 2; ++half) {   // channels 16 half .. 16 half + 15 = groups 2 half, 2 half + 1
+          const uint64_t a = adesc + (uint64_t)((half * 2 * Cfg::kGroupBytes) >> 4);
+          const uint32_t b = b_base + half * 9 * 512;
+          umma_f16(tmem_d, a, umma_desc_sw32(b), umma_idesc_16(128, 64, HALF), (uint32_t)(half != 0));                 // shift (0, 0)
+          umma_f16(tmem_d + 16, a + (uint64_t)((1 * 16) >> 4), umma_desc_sw32(b + 4 * 512), umma_idesc_16(128, 32, HALF), 1u);   // (0, 1)
+          umma_f16(tmem_d + 32, a + (uint64_t)((17 * 16) >> 4), umma_desc_sw32(b + 6 * 512), umma_idesc_16(128, 32, HALF), 1u);  // (1, 0)
+          umma_f16(tmem_d + 32, a + (uint64_t)((18 * 16) >> 4), umma_desc_sw32(b + 8 * 512), umma_idesc_16(128, 16, HALF), 1u);  // (1, 1)
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
@@ -1366,46 +1379,50 @@ ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
       const int qy = rem / 17, qx = rem - qy * 17;
       if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 24)) break;
       tc_fence_after();
-      uint32_t v0[32], v1[32];   // classes (0,0) (0,1) | (1,0) (1,1)
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
-      tmem_ld_32x32(taddr, v0);
-      tmem_ld_32x32(taddr + 32, v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      if (img < n_img) {
-        __nv_bfloat16* o = out + (size_t)img * (1089 * 8);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        if (qx < 16 && qy < 16) {
+      const bool live = img < n_img;
+      const bool pixel = live && qx < 16 && qy < 16;
+      __nv_bfloat16* o = out + (size_t)img * (kA5Image * 8);
+      // one output row (py) at a time: 32 accumulator columns in registers instead of 64, so that four CTAs fit an SM (the
+      // kernel is latency bound: 30 % issue-active at three)
 #pragma unroll
-          for (int py = 0; py < 2; ++py) {
-            const uint32_t* v = py ? v1 : v0;
-            uint32_t pk[16];   // [px][8 channel pairs]
+      for (int py = 0; py < 2; ++py) {
+        uint32_t v[32];            // py = 0: classes (0, 0) | (0, 1); py = 1: (1, 1) | (1, 0) (dec2_class_pos)
+        tmem_ld_32x32(taddr + py * 32, v);
+        tmem_ld_wait();
+        if (py == 1) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        if (pixel) {
+          uint32_t pk[16];   // [px][8 channel pairs]
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = fmaxf(__uint_as_float(v[2 * j]) + bo[(2 * j) & 15], 0.f);
-              const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bo[(2 * j + 1) & 15], 0.f);
-              pk[j] = pk2<HALF>(a, b);
-            }
-            // pixels (2qx, 2qx + 1) of output row 2qy + py: 32 contiguous bytes in each of the two channel-group planes
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane + (size_t)((2 * qy + py) * 33 + 2 * qx) * 8);
-              d[0] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-              d[1] = make_uint4(pk[8 + 4 * g], pk[8 + 4 * g + 1], pk[8 + 4 * g + 2], pk[8 + 4 * g + 3]);
-            }
+          for (int j = 0; j < 16; ++j) {
+            const int col = (2 * j + (py ? 16 : 0)) & 31;      // pk[0..7]: pixel 2qx, pk[8..15]: pixel 2qx + 1
+            const float a = fmaxf(__uint_as_float(v[col]) + bo[(2 * j) & 15], 0.f);
+            const float b = fmaxf(__uint_as_float(v[col + 1]) + bo[(2 * j + 1) & 15], 0.f);
+            pk[j] = pk2<HALF>(a, b);
           }
-        } else if (qy < 16) {       // halo column of the input: zero column 32 of output rows 2qy, 2qy + 1
+          // pixels (2qx, 2qx + 1) of output row 2qy + py: 32 contiguous, 32-byte aligned bytes in each channel-group plane
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            st_global_v8(o + (size_t)g * out_plane + (size_t)((2 * qy + py) * kA5Pitch + 2 * qx) * 8, pk[4 * g], pk[4 * g + 1],
+                         pk[4 * g + 2], pk[4 * g + 3], pk[8 + 4 * g], pk[8 + 4 * g + 1], pk[8 + 4 * g + 2], pk[8 + 4 * g + 3]);
+        }
+      }
+      if (live && !pixel) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (qy < 16) {              // halo column of the input: zero column 32 of output rows 2qy, 2qy + 1
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane);
-            d[(2 * qy) * 33 + 32] = z;
-            d[(2 * qy + 1) * 33 + 32] = z;
+            d[(2 * qy) * kA5Pitch + 32] = z;
+            d[(2 * qy + 1) * kA5Pitch + 32] = z;
           }
         } else {                    // halo row of the input: zero row 32 of the output
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane) + 32 * 33;
+            uint4* d = reinterpret_cast<uint4*>(o + (size_t)g * out_plane) + 32 * kA5Pitch;
             if (qx < 16) { d[2 * qx] = z; d[2 * qx + 1] = z; }
             else d[32] = z;
           }
@@ -1423,21 +1440,21 @@ ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
 }
 
 struct Dec3XCfg {
-  static constexpr int kTilePos = 121, kTilesPerImage = 9;      // 9 x 121 = 1 089 positions
-  static constexpr int kWin = 128 + 34;               // positions a tile's windows touch (max shift 33 + 1)
-  static constexpr int kGroupBytes = kWin * 16;       // 2 592
-  static constexpr int kStageBytes = 2 * kGroupBytes; // 5 184 per tile
+  static constexpr int kTilePos = 125, kTilesPerImage = 9;      // 9 x 125 = 1 125 >= 33 x 34 positions
+  static constexpr int kWin = 128 + kA5Pitch + 2;     // positions a tile's windows touch (max shift 34 + 1)
+  static constexpr int kGroupBytes = kWin * 16;       // 2 624
+  static constexpr int kStageBytes = 2 * kGroupBytes; // 5 248 per tile
   static constexpr int kStages = 4;
   static constexpr int kBBytes = 9 * 512;
   static constexpr int kTmemCols = 128;               // 2 buffers x 4 classes x 16 columns
-  static constexpr int kSmemBytes = 5120 + kStages * kStageBytes + 512 + 256 + 1024;
+  static constexpr int kSmemBytes = 5120 + kStages * kStageBytes + 256 + 1024;
 };
 
 template <bool HALF>
 __global__ void __launch_bounds__(192, 4)
 ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
                 const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ recon,
-                double* __restrict__ partial, int total_tiles, int* err) {
+                float* __restrict__ partial, int total_tiles, int* err) {
   using Cfg = Dec3XCfg;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1446,9 +1463,7 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t b_base = base;                                  // 9 weight tiles (SWIZZLE_32B), 4 608 of 5 120 bytes
   const uint32_t a_base = base + 5120;
-  const uint32_t p_base = a_base + S * Cfg::kStageBytes;         // [2][4] warp sums
-  const uint32_t bar0 = p_base + 512;
-  double* s_part = reinterpret_cast<double*>(smem + (p_base - base));
+  const uint32_t bar0 = a_base + S * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -1484,7 +1499,7 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
         if (!mbar_wait_sleep(empty_bar(stage), phase ^ 1u, s_abort, err, kErrBase + 41)) break;
         mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
         const uint32_t sa = a_base + stage * Cfg::kStageBytes;
-        const __nv_bfloat16* src = in + ((size_t)img * 1089 + (size_t)t * Cfg::kTilePos) * 8;
+        const __nv_bfloat16* src = in + ((size_t)img * kA5Image + (size_t)t * Cfg::kTilePos) * 8;
 #pragma unroll
         for (int g = 0; g < 2; ++g) bulk_load_1d(sa + g * Cfg::kGroupBytes, src + (size_t)g * in_plane, Cfg::kGroupBytes, full_bar(stage));
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -1501,21 +1516,11 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
         if (!mbar_wait_sleep(full_bar(stage), phase, s_abort, err, kErrBase + 42)) break;
         tc_fence_after();
         const uint64_t adesc = umma_desc_nosw(a_base + stage * Cfg::kStageBytes, Cfg::kGroupBytes, 128);
-#pragma unroll
-        for (int cls = 0; cls < 4; ++cls) {
-          const int py = cls >> 1, px = cls & 1;
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64 + cls * 16);
-          bool first = true;
-#pragma unroll
-          for (int dy = 0; dy <= py; ++dy)
-#pragma unroll
-            for (int dx = 0; dx <= px; ++dx) {
-              const int tap = dec2_tap_k(py, dy) * 3 + dec2_tap_k(px, dx);
-              umma_f16(tmem_d, adesc + (uint64_t)(((dy * 33 + dx) * 16) >> 4), umma_desc_sw32(b_base + tap * 512), idesc,
-                       first ? 0u : 1u);
-              first = false;
-            }
-        }
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 64);
+        umma_f16(tmem_d, adesc, umma_desc_sw32(b_base), umma_idesc_16(128, 64, HALF), 0u);                                     // shift (0, 0)
+        umma_f16(tmem_d + 16, adesc + (uint64_t)((1 * 16) >> 4), umma_desc_sw32(b_base + 4 * 512), umma_idesc_16(128, 32, HALF), 1u);   // (0, 1)
+        umma_f16(tmem_d + 32, adesc + (uint64_t)((kA5Pitch * 16) >> 4), umma_desc_sw32(b_base + 6 * 512), umma_idesc_16(128, 32, HALF), 1u);  // (1, 0)
+        umma_f16(tmem_d + 32, adesc + (uint64_t)(((kA5Pitch + 1) * 16) >> 4), umma_desc_sw32(b_base + 8 * 512), umma_idesc_16(128, 16, HALF), 1u);  // (1, 1)
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -1526,7 +1531,7 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
-    int acc = 0, it = 0;
+    int acc = 0;
     uint32_t acc_phase = 0;
     // ncu (profiles/r2l_ae_dec3x_sass.txt): this epilogue is the kernel's bound -- the SM's issue slots, 342 instructions per
     // thread and tile in the first version.  Hence: the tile -> pixel decode and the 12 input values a thread compares with
@@ -1535,8 +1540,8 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
     // order -> deterministic and the same for every image; fp64 from the four warp sums on).
     auto locate = [&](int tile, const float*& px) -> bool {
       const int img = tile / Cfg::kTilesPerImage;
-      const int rem = (tile - img * Cfg::kTilesPerImage) * Cfg::kTilePos + row;   // position in the image's 33 x 33 sequence
-      const int qy = rem / 33, qx = rem - qy * 33;
+      const int rem = (tile - img * Cfg::kTilesPerImage) * Cfg::kTilePos + row;   // position in the image's 33 x 34 sequence
+      const int qy = rem / kA5Pitch, qx = rem - qy * kA5Pitch;
       const bool valid = tile < total_tiles && row < Cfg::kTilePos && qx < 32 && qy < 32;
       px = valid ? x + ((size_t)img * 12288 + (size_t)(2 * qy * 64 + 2 * qx)) : x;
       return valid;
@@ -1549,8 +1554,7 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
     bool vn = locate(blockIdx.x, pn);
     float2 nxt[6];
     load_x(pn, nxt);
-    float* s_partf = reinterpret_cast<float*>(s_part);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const float* pc = pn;
       const bool valid = vn;
       float2 tin[6];
@@ -1560,7 +1564,7 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
       load_x(pn, nxt);
       if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 44)) break;
       tc_fence_after();
-      // classes (py, px) at columns 32 py + 16 px; only channels 0..2 of the 16 columns of a class are real
+      // class (py, px) at columns 16 * dec2_class_pos(py, px); only channels 0..2 of the 16 columns of a class are real
       uint32_t v[4][4];
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 64);
 #pragma unroll
@@ -1574,7 +1578,8 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
         const float bc = c == 0 ? b0 : (c == 1 ? b1 : b2);
 #pragma unroll
         for (int py = 0; py < 2; ++py) {
-          const float r0 = fast_tanh2(__uint_as_float(v[2 * py][c]) + bc), r1 = fast_tanh2(__uint_as_float(v[2 * py + 1][c]) + bc);
+          const float r0 = fast_tanh2(__uint_as_float(v[dec2_class_pos(py, 0)][c]) + bc);
+          const float r1 = fast_tanh2(__uint_as_float(v[dec2_class_pos(py, 1)][c]) + bc);
           const float2 tt = tin[c * 2 + py];
           const float d0 = r0 - tt.x, d1 = r1 - tt.y;
           sqf = fmaf(d0, d0, sqf);
@@ -1585,10 +1590,9 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
       if (!valid) sqf = 0.f;      // halo rows: accumulator rows of no pixel
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sqf += __shfl_xor_sync(0xffffffffu, sqf, o);
-      float* sp = s_partf + (it & 1) * 4;
-      if (lane == 0) sp[lg] = sqf;
-      named_bar_sync(1, 128);
-      if (row == 0) partial[tile] = (((double)sp[0] + (double)sp[1]) + (double)sp[2]) + (double)sp[3];
+      // one partial per (tile, warp): no barrier between the epilogue warps (it was the kernel's top stall reason);
+      // ae_mse_finish_kernel adds the four warps of a tile, then the tiles, in a fixed order
+      if (lane == 0) partial[(size_t)tile * 4 + lg] = sqf;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -2030,7 +2034,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     r = encode_tmap(&tb, 2, bf(L.w5), bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r != SG_OK) return r;
     const int64_t tiles = ceil_div(batch * 289, 128);
-    const int64_t ctas = (int64_t)state().sm_count * 3;
+    const int64_t ctas = (int64_t)state().sm_count * 4;
     ae_dec2x_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), 192, Dec2XCfg::kSmemBytes, st>>>(
         tb, bf(L.a4), a4x_plane_elems(batch), h_params[9], bf(L.a5), a5x_plane_elems(batch), (int)batch, (int)tiles, err);
     SG_LAUNCH_CHECK();
@@ -2039,7 +2043,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     r = encode_tmap(&tb, 2, bf(L.w6), b6dims, b6str, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
     if (r != SG_OK) return r;
     const int64_t tiles6 = batch * Dec3XCfg::kTilesPerImage;
-    double* part = reinterpret_cast<double*>(ws + L.part);
+    float* part = reinterpret_cast<float*>(ws + L.part);
     const int64_t ctas6 = (int64_t)state().sm_count * 4;
     ae_dec3x_kernel<HALF><<<(int)(tiles6 < ctas6 ? tiles6 : ctas6), 192, Dec3XCfg::kSmemBytes, st>>>(
         tb, bf(L.a5), a5x_plane_elems(batch), h_params[11], x, recon_out, part, (int)tiles6, err);
