@@ -835,6 +835,245 @@ static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
 }
 
 // ------------------------------------------------------------------------------------------
+// L3 (enc3) on CTA PAIRS (cta_group::2), the default of the single-segment modes.  ae_k7x_kernel<false> ran at 65 % tensor-pipe
+// active: an M128 x N160 x K16 MMA reads 9 KB of operands for 80 tensor cycles (115 B/clk of the 128 B/clk shared memory
+// delivers) while TMA streams half of the 224 KB of weights through the same memory for every image.  As a pair, the two
+// CTAs split the OUTPUT CHANNELS (M = 256 = 2 x (32 co x 4 column taps)) and share the image: each CTA feeds 80 of the 160
+// pixel columns of B (its shared-memory copy of the image starts 5 rows = 80 pixels later, so one descriptor addresses both
+// halves), i.e. 6.5 KB of operand reads per CTA and MMA, and a CTA's half of the weights -- 14 stages x 8 KB -- is RESIDENT:
+// nothing but the 16 KB image moves per image.  Stage s = c * 7 + ky accumulates
+//   D[(co, g)][m] += sum_ci w[co][ci][ky][4 c + 3 - g] * in[m + 16 ky + 4 c][ci]        (kx = 4 c + 3 - g; kx == 7: zero weights)
+// and out[co][n] = sum_g D[(co, g)][n + 3 - g] = o[n + 3] with o[m] = sum_g D_g[m - g]: the two-level lane butterfly of dec1's
+// epilogue, shifted by three columns.
+// ------------------------------------------------------------------------------------------
+struct K7PCfg {
+  static constexpr int kGroups = 4, kStages = 14;
+  static constexpr int kLboB = 256 * 16;                 // image: bytes between channel groups
+  static constexpr int kSlotBytes = kGroups * kLboB;     // 16 384
+  static constexpr int kSlots = 2;
+  static constexpr int kN = 160, kSteps = kN / 32;
+  static constexpr int kLboA = 128 * 16;                 // weights: bytes between channel groups of a stage
+  static constexpr int kBBytes = kGroups * kLboA;        // 8 192 per stage
+  static constexpr int kWBytes = kStages * kBBytes;      // 114 688, resident
+  static constexpr int kStgBytes = 100 * 32 * 2;         // this CTA's 32 output channels of one image
+  static constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns (160 used)
+  // Two epilogue warpgroups: with one (a single warp per scheduler) the dependent tcgen05.ld -> shuffle -> shuffle -> store
+  // chain of an image took ~4 200 cycles against 2 240 cycles of MMAs -- the kernel (and ae_k7x_kernel<false> before it) was
+  // bound by its epilogue's latency, not by the tensor pipe or shared memory.  Group 0 finishes accumulator columns 0..95,
+  // group 1 columns 96..159 (it re-derives the two carries of the butterfly from columns 93..95).
+  static constexpr int kThreads = 352;                   // warps 0 weights, 1 MMA, 2-5 epilogue group 0, 6 images, 7-10 group 1
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + kWBytes + 2 * kStgBytes + kBarBytes + 256 + 1024;
+};
+
+template <bool HALF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1)
+ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
+  using Cfg = K7PCfg;
+  constexpr int UA = Cfg::kSlots;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t w_base = base + UA * Cfg::kSlotBytes;          // resident weight stages of this CTA's 32 output channels
+  const uint32_t g_base = w_base + Cfg::kWBytes;                // two output staging buffers
+  const uint32_t bar0 = g_base + 2 * Cfg::kStgBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto afull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 + a); };
+  const uint32_t wres_bar = bar0 + 8u * (2 * UA + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * UA + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * UA + 6);
+  float* s_bias = reinterpret_cast<float*>(smem + (bar0 - base) + Cfg::kBarBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // 8 epilogue warps x 2 CTAs
+    mbar_init(wres_bar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = bias[rank * 32 + threadIdx.x];
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= weights: this CTA's 14 stages, once; the transaction bytes of both CTAs go to the leader's barrier
+    if (lane == 0) {
+      const uint32_t lead_wres = mapa_shared(wres_bar, 0);
+      if (leader) mbar_arrive_expect_tx(wres_bar, 2 * Cfg::kWBytes);
+      const int row0 = (int)((pair % kWeightCopies) * 2 + rank) * Cfg::kStages * (Cfg::kBBytes / 128);
+      for (int s = 0; s < Cfg::kStages; ++s)
+        tma_load_2d_pair(w_base + s * Cfg::kBBytes, &tmap_b, lead_wres, 0, row0 + s * (Cfg::kBBytes / 128));
+    }
+  } else if (warp == 6) {
+    // ================= images: each CTA loads its own view (rank 1: from row 5 = pixel 80 on, rows past 15 zero-filled)
+    if (lane == 0) {
+      int aslot = 0;
+      uint32_t aphase = 0;
+      for (int img = pair; img < n_img; img += npairs) {
+        if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 31)) break;
+        const uint32_t lead_afull = mapa_shared(afull_bar(aslot), 0);
+        if (leader) mbar_arrive_expect_tx(afull_bar(aslot), 2 * Cfg::kSlotBytes);
+        tma_load_4d_pair(base + aslot * Cfg::kSlotBytes, &tmap_a, lead_afull, 0, (int)rank * 5, 0, img);
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA): 28 MMAs of M256 x N160 x K16 per image, fully unrolled
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(256, Cfg::kN, HALF);
+      int aslot = 0, acc = 0;
+      uint32_t aphase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wres_bar, 0, s_abort, err, kErrBase + 37);
+      const uint64_t wdesc0 = umma_desc_nosw(w_base, Cfg::kLboA, 128);
+      for (int img = pair; img < n_img && ok; img += npairs) {
+        if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 33)) break;
+        if (!mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 34)) break;
+        tc_fence_after();
+        const uint64_t img_desc = umma_desc_nosw(base + aslot * Cfg::kSlotBytes, Cfg::kLboB, 128);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+#pragma unroll
+        for (int s = 0; s < Cfg::kStages; ++s) {
+          const int c = s / 7, ky = s % 7;
+          const int px = 16 * ky + 4 * c;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16_pair(tmem_d, wdesc0 + (uint64_t)((s * Cfg::kBBytes + 2 * k * Cfg::kLboA) >> 4),
+                          img_desc + (uint64_t)((px * 16 + 2 * k * Cfg::kLboB) >> 4), idesc, (uint32_t)((s | k) != 0));
+        }
+        umma_commit_pair(tfull_bar(acc), 3);
+        umma_commit_pair(aempty_bar(aslot), 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+      }
+    }
+  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+    // ================= epilogue (both CTAs, two warpgroups): accumulator row = co_local * 4 + g; o[m] = sum_g D_g[m - g] by
+    // the two-level butterfly of dec1's epilogue (level 1 between lanes g ^ 1, level 2 between lanes g ^ 2); out[n] = o[n + 3]
+    const int grp = warp >= 7 ? 1 : 0;
+    const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int L = q * 32 + lane;
+    const int g = L & 3, co = L >> 2;                 // co: 0..31 of this CTA
+    const int t = grp ? (int)threadIdx.x - 224 + 128 : (int)threadIdx.x - 64;     // 0..255 over both groups
+    const int j0 = grp ? 3 : 0, j1 = grp ? Cfg::kSteps : 3;
+    const float my_bias = s_bias[co];
+    const bool odd = (g & 1) != 0, hi = (g & 2) != 0;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0;
+    for (int img = pair; img < n_img; img += npairs) {
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 36)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      uint16_t* stg = reinterpret_cast<uint16_t*>(smem + (g_base - base) + buf * Cfg::kStgBytes);
+      float c1 = 0.f, c2 = 0.f;                       // this lane's column 32 j - 1 / its last level-1 sum of the step before
+      if (grp) {                                      // carries into column 96 from columns 93..95
+        uint32_t w4[4];
+        tmem_ld_32x32_x4(taddr + 92u, w4);
+        tmem_ld_wait();
+        const float v93 = __uint_as_float(w4[1]), v94 = __uint_as_float(w4[2]), v95 = __uint_as_float(w4[3]);
+        c1 = v95;
+        c2 = v94 + __shfl_xor_sync(0xffffffffu, odd ? v93 : v95, 1);
+      }
+#pragma unroll 1
+      for (int j = j0; j < j1; ++j) {
+        uint32_t u[32];
+        tmem_ld_32x32(taddr + (uint32_t)(32 * j), u);
+        tmem_ld_wait();
+        if (j == j1 - 1) {                            // this group's last columns are in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+        float pp[16];
+#pragma unroll
+        for (int t2 = 0; t2 < 16; ++t2) {
+          const int i = 2 * t2;
+          const float below = t2 == 0 ? c1 : v[t2 == 0 ? 0 : i - 1];
+          const float send = odd ? below : v[i + 1];
+          pp[t2] = v[i] + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float before = k == 0 ? c2 : pp[k == 0 ? 0 : 2 * k - 1];
+          const float send = hi ? before : pp[2 * k + 1];
+          const float a = my_bias + pp[2 * k] + __shfl_xor_sync(0xffffffffu, send, 2);
+          const int n = 32 * j + 4 * k + g - 3;       // o[m] is output position m - 3
+          const int oy = n >> 4, ox = n & 15;
+          // a3 in channel-group-major form [img][co / 8][100 pixels][8 co] (dec1's operand layout); this CTA's four groups
+          if (n >= 0 && oy < 10 && ox < 10) stg[((co >> 3) * 100 + oy * 10 + ox) * 8 + (co & 7)] = pk1<HALF>(a);
+        }
+        c1 = v[31]; c2 = pp[15];
+      }
+      named_bar_sync(1, 256);
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(stg);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)img * 6400 + (size_t)rank * 3200);
+        for (int i = t; i < Cfg::kStgBytes / 16; i += 256) dst[i] = src[i];
+      }
+      buf ^= 1;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// enc3 weights for the pair kernel: [rank][stage s = c * 7 + ky][ci / 8][row = co_local * 4 + g][ci % 8], co = 32 rank + co_local,
+// kx = 4 c + 3 - g (kx == 7: zero)
+template <bool HALF>
+__global__ void pack_k7p_kernel(const float* __restrict__ w3, __nv_bfloat16* __restrict__ p3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * 14 * 4096) {
+    const int e = i & 7, row = (i >> 3) & 127, grp = (i >> 10) & 3, s = (i >> 12) % 14, r = i / (14 * 4096);
+    const int ci = grp * 8 + e, ky = s % 7, kx = 4 * (s / 7) + 3 - (row & 3), co = r * 32 + (row >> 2);
+    p3[i] = __ushort_as_bfloat16(pk1<HALF>(kx < 7 ? w3[((co * 32 + ci) * 7 + ky) * 7 + kx] : 0.f));
+  }
+}
+
+template <bool HALF>
+static int launch_k7p(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
+                      int64_t batch, int* err, cudaStream_t st) {
+  using Cfg = K7PCfg;
+  CUtensorMap ta, tb;
+  // a2 [n][4 groups][16 rows][16 px x 8 ci]: a CTA's view = 16 rows from row 0 / 5 on (rows past the image: zero fill)
+  cuuint64_t dims[4] = {128, 16, 4, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {256, 4096, 16384};
+  cuuint32_t box[4] = {128, 16, 4, 1};
+  int r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (r != SG_OK) return r;
+  cuuint64_t wdims[2] = {64, (cuuint64_t)kWeightCopies * 2 * Cfg::kStages * (Cfg::kBBytes / 128)};
+  cuuint64_t wstr[1] = {128};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)(Cfg::kBBytes / 128)};
+  r = encode_tmap(&tb, 2, wpk, wdims, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (r != SG_OK) return r;
+  const int64_t pairs_max = state().sm_count / 2;
+  const int pairs = (int)(batch < pairs_max ? batch : pairs_max);
+  ae_k7p_kernel<HALF><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // L1 (enc Conv 3->16 k3 s2 p1 + ReLU) on tcgen05, fused with the fp32 -> 16-bit input conversion (the structure of
 // d64.cu's conv1_fused_kernel: a 3x3 stride-2 pad-1 filter is that kernel's 4x4 stride-2 pad-1 geometry with the
 // fourth filter row / column absent).  One tile = 4 output rows x 32 columns of one image (M = 128), N = 16:
@@ -1944,6 +2183,8 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     if constexpr (SEG == 1) {
       pack_k7x_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
       SG_LAUNCH_CHECK();
+      pack_k7p_kernel<HALF><<<(2 * 14 * 4096 + 255) / 256, 256, 0, st>>>(h_params[4], bf(L.w3t));   // enc3: the pair kernel's form
+      SG_LAUNCH_CHECK();
       for (int c = 1; c < kWeightCopies; ++c) {
         SG_CUDA(cudaMemcpyAsync(ws + L.w3t + (size_t)c * 229376, ws + L.w3t, 229376, cudaMemcpyDeviceToDevice, st));
         SG_CUDA(cudaMemcpyAsync(ws + L.w4t + (size_t)c * 229376, ws + L.w4t, 229376, cudaMemcpyDeviceToDevice, st));
@@ -2004,7 +2245,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
   int r;
   if constexpr (SEG == 1) {
     // single-segment modes: both 7x7 layers in shifted-window form (weights on M, the image's pixels on N, taps = descriptor offsets)
-    r = launch_k7x<false, HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);
+    r = launch_k7p<HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);   // enc3 on CTA pairs
     if (r != SG_OK) return r;
     r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);   // a4 in linear-halo form
     if (r != SG_OK) return r;
@@ -2072,6 +2313,8 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_enc2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
