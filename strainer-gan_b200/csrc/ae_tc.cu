@@ -850,24 +850,26 @@ struct K7PCfg {
   static constexpr int kGroups = 4, kStages = 14;
   static constexpr int kLboB = 256 * 16;                 // image: bytes between channel groups
   static constexpr int kSlotBytes = kGroups * kLboB;     // 16 384
-  static constexpr int kSlots = 2;
+  static constexpr int kSlots = 2;                     // (four slots: no change -- the image loads are not what the MMAs wait for)
   static constexpr int kN = 160, kSteps = kN / 32;
   static constexpr int kLboA = 128 * 16;                 // weights: bytes between channel groups of a stage
   static constexpr int kBBytes = kGroups * kLboA;        // 8 192 per stage
   static constexpr int kWBytes = kStages * kBBytes;      // 114 688, resident
   static constexpr int kStgBytes = 100 * 32 * 2;         // this CTA's 32 output channels of one image
   static constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns (160 used)
-  // Two epilogue warpgroups: with one (a single warp per scheduler) the dependent tcgen05.ld -> shuffle -> shuffle -> store
-  // chain of an image took ~4 200 cycles against 2 240 cycles of MMAs -- the kernel (and ae_k7x_kernel<false> before it) was
-  // bound by its epilogue's latency, not by the tensor pipe or shared memory.  Group 0 finishes accumulator columns 0..95,
-  // group 1 columns 96..159 (it re-derives the two carries of the butterfly from columns 93..95).
-  static constexpr int kThreads = 352;                   // warps 0 weights, 1 MMA, 2-5 epilogue group 0, 6 images, 7-10 group 1
+  // FIVE epilogue warpgroups, one per 32 accumulator columns: with one group (a single warp per scheduler) the dependent
+  // tcgen05.ld -> shuffle -> shuffle -> store chain of an image took ~4 200 cycles against 2 240 cycles of MMAs -- the kernel
+  // (and ae_k7x_kernel<false> before it) was bound by its epilogue's latency, not by the tensor pipe or shared memory
+  // (one group: 247 us per 8 192 images, two: 207 us).  Group j > 0 re-derives the two carries of the butterfly from the three
+  // columns in front of its own.
+  static constexpr int kEpiGroups = kSteps;
+  static constexpr int kThreads = 128 + kEpiGroups * 128;   // warps 0 weights, 1 MMA, 2 images (+ TMEM alloc), 3 idle, 4.. epilogue
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kSlots * kSlotBytes + kWBytes + 2 * kStgBytes + kBarBytes + 256 + 1024;
 };
 
 template <bool HALF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(K7PCfg::kThreads, 1)
 ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
   using Cfg = K7PCfg;
@@ -897,7 +899,7 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_b);
     for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // 8 epilogue warps x 2 CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * Cfg::kEpiGroups); }   // epilogue warps x 2 CTAs
     mbar_init(wres_bar, 1);
     *s_abort = 0;
     fence_barrier_init();
@@ -918,7 +920,7 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       for (int s = 0; s < Cfg::kStages; ++s)
         tma_load_2d_pair(w_base + s * Cfg::kBBytes, &tmap_b, lead_wres, 0, row0 + s * (Cfg::kBBytes / 128));
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ================= images: each CTA loads its own view (rank 1: from row 5 = pixel 80 on, rows past 15 zero-filled)
     if (lane == 0) {
       int aslot = 0;
@@ -960,15 +962,15 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
       }
     }
-  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+  } else if (warp >= 4) {
     // ================= epilogue (both CTAs, two warpgroups): accumulator row = co_local * 4 + g; o[m] = sum_g D_g[m - g] by
     // the two-level butterfly of dec1's epilogue (level 1 between lanes g ^ 1, level 2 between lanes g ^ 2); out[n] = o[n + 3]
-    const int grp = warp >= 7 ? 1 : 0;
+    const int grp = (warp - 4) >> 2;                  // this group's 32 accumulator columns
     const int q = warp & 3;                           // TMEM lane quadrant of this warp
     const int L = q * 32 + lane;
     const int g = L & 3, co = L >> 2;                 // co: 0..31 of this CTA
-    const int t = grp ? (int)threadIdx.x - 224 + 128 : (int)threadIdx.x - 64;     // 0..255 over both groups
-    const int j0 = grp ? 3 : 0, j1 = grp ? Cfg::kSteps : 3;
+    const int t = (int)threadIdx.x - 128;             // 0 .. 128 kEpiGroups - 1
+    const int j0 = grp, j1 = grp + 1;
     const float my_bias = s_bias[co];
     const bool odd = (g & 1) != 0, hi = (g & 2) != 0;
     int acc = 0, buf = 0;
@@ -979,13 +981,13 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       uint16_t* stg = reinterpret_cast<uint16_t*>(smem + (g_base - base) + buf * Cfg::kStgBytes);
       float c1 = 0.f, c2 = 0.f;                       // this lane's column 32 j - 1 / its last level-1 sum of the step before
-      if (grp) {                                      // carries into column 96 from columns 93..95
+      if (grp) {                                      // carries into this group's first column from the three before it
         uint32_t w4[4];
-        tmem_ld_32x32_x4(taddr + 92u, w4);
+        tmem_ld_32x32_x4(taddr + (uint32_t)(32 * grp - 4), w4);
         tmem_ld_wait();
-        const float v93 = __uint_as_float(w4[1]), v94 = __uint_as_float(w4[2]), v95 = __uint_as_float(w4[3]);
-        c1 = v95;
-        c2 = v94 + __shfl_xor_sync(0xffffffffu, odd ? v93 : v95, 1);
+        const float b3 = __uint_as_float(w4[1]), b2 = __uint_as_float(w4[2]), b1 = __uint_as_float(w4[3]);   // columns -3, -2, -1
+        c1 = b1;
+        c2 = b2 + __shfl_xor_sync(0xffffffffu, odd ? b3 : b1, 1);
       }
 #pragma unroll 1
       for (int j = j0; j < j1; ++j) {
@@ -995,7 +997,7 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         if (j == j1 - 1) {                            // this group's last columns are in registers
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // (a relaxed arrive measured the same)
         }
         float v[32];
 #pragma unroll
@@ -1020,11 +1022,16 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         }
         c1 = v[31]; c2 = pp[15];
       }
-      named_bar_sync(1, 256);
+      // copy-out per group (its own named barrier: the four warps of a group run in step anyway): the group's 32 columns are
+      // output positions 32 grp - 3 .. 32 grp + 28; thread (channel group, position) moves one 16-byte run if the position exists
+      named_bar_sync(1 + grp, 128);
       {
-        const uint4* src = reinterpret_cast<const uint4*>(stg);
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)img * 6400 + (size_t)rank * 3200);
-        for (int i = t; i < Cfg::kStgBytes / 16; i += 256) dst[i] = src[i];
+        const int cg = (t & 127) >> 5, n = 32 * grp - 3 + (t & 31);
+        const int oy = n >> 4, ox = n & 15;
+        if (n >= 0 && oy < 10 && ox < 10) {
+          const int e = (cg * 100 + oy * 10 + ox) * 8;
+          *reinterpret_cast<uint4*>(out + (size_t)img * 6400 + (size_t)rank * 3200 + e) = *reinterpret_cast<const uint4*>(stg + e);
+        }
       }
       buf ^= 1;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
