@@ -546,6 +546,7 @@ template <bool CONVT, bool HALF>
 __global__ void __launch_bounds__(224, 1)
 ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err, size_t out_plane) {
+  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
   constexpr bool XOUT = CONVT;
   using Cfg = K7XCfg<CONVT>;
   constexpr int UA = Cfg::kSlots, SB = Cfg::kBStages, COUT = Cfg::kCout;
@@ -593,6 +594,7 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
 
   if (warp == 0) {
     // ================= TMA producer: weight stages =================
@@ -828,9 +830,8 @@ static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
     if (r != SG_OK) return r;
   }
   const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-  ae_k7x_kernel<CONVT, HALF><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err,
-                                                                             CONVT ? a4x_plane_elems(batch) : 0);
-  SG_LAUNCH_CHECK();
+  SG_LAUNCH_PDL(ae_k7x_kernel<CONVT, HALF>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, ta, tb, bias, act_out, (int)batch,
+                err, CONVT ? a4x_plane_elems(batch) : (size_t)0);
   return SG_OK;
 }
 
@@ -872,6 +873,7 @@ template <bool HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(K7PCfg::kThreads, 1)
 ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err) {
+  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
   using Cfg = K7PCfg;
   constexpr int UA = Cfg::kSlots;
   extern __shared__ uint8_t smem_raw[];
@@ -910,6 +912,7 @@ ae_k7p_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
 
   if (warp == 0) {
     // ================= weights: this CTA's 14 stages, once; the transaction bytes of both CTAs go to the leader's barrier
@@ -1075,8 +1078,7 @@ static int launch_k7p(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
   if (r != SG_OK) return r;
   const int64_t pairs_max = state().sm_count / 2;
   const int pairs = (int)(batch < pairs_max ? batch : pairs_max);
-  ae_k7p_kernel<HALF><<<2 * pairs, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, bias, act_out, (int)batch, err);
-  SG_LAUNCH_CHECK();
+  SG_LAUNCH_PDL(ae_k7p_kernel<HALF>, dim3(2 * pairs), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, ta, tb, bias, act_out, (int)batch, err);
   return SG_OK;
 }
 
@@ -1108,6 +1110,7 @@ template <bool HALF>
 __global__ void __launch_bounds__(320, 3)
 ae_enc1_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t out_plane, int total_tiles, int* err) {
+  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
   using Cfg = Enc1Cfg;
   constexpr int SA = Cfg::kAStages, SR = Cfg::kRawStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1145,6 +1148,7 @@ ae_enc1_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1311,6 +1315,7 @@ template <bool HALF>
 __global__ void __launch_bounds__(192, 3)
 ae_enc2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int total_tiles, int* err) {
+  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
   using Cfg = Enc2XCfg;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1343,6 +1348,7 @@ ae_enc2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1484,6 +1490,8 @@ __device__ __forceinline__ float fast_tanh2(float x) {
 // then the tiles, in fp64 and in a fixed order
 template <int TILES>
 __global__ void ae_mse_finish_kernel(const float* __restrict__ partial, int64_t n_img, float* __restrict__ err) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n < n_img) {
     const float4* p = reinterpret_cast<const float4*>(partial + n * (TILES * 4));
@@ -1535,6 +1543,7 @@ __global__ void __launch_bounds__(192, 4)
 ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t out_plane, int n_img, int total_tiles,
                 int* err) {
+  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
   using Cfg = Dec2XCfg;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1567,6 +1576,7 @@ ae_dec2x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1701,6 +1711,7 @@ __global__ void __launch_bounds__(192, 4)
 ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16* __restrict__ in, size_t in_plane,
                 const float* __restrict__ bias, const float* __restrict__ x, float* __restrict__ recon,
                 float* __restrict__ partial, int total_tiles, int* err) {
+  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
   using Cfg = Dec3XCfg;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -1733,6 +1744,7 @@ ae_dec3x_kernel(const __grid_constant__ CUtensorMap tmap_b, const __nv_bfloat16*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -2228,8 +2240,8 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     if (r1 != SG_OK) return r1;
     const int64_t tiles = batch * 8;
     const int64_t ctas = (int64_t)state().sm_count * 3;    // 3 CTAs per SM: the kernel is latency bound (34 % issue-active at 2)
-    ae_enc1_tc_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), Enc1Cfg::kThreads, Enc1Cfg::kSmemBytes, st>>>(
-        tx, tb, h_params[1], bf(L.a1), a1x_plane_elems(batch), (int)tiles, err);
+    SG_LAUNCH_PDL(ae_enc1_tc_kernel<HALF>, dim3((unsigned)(tiles < ctas ? tiles : ctas)), dim3(Enc1Cfg::kThreads), (size_t)Enc1Cfg::kSmemBytes,
+                  st, tx, tb, h_params[1], bf(L.a1), a1x_plane_elems(batch), (int)tiles, err);
   } else {
     enc1_kernel<SEG, HALF><<<blocks(batch * 1024), 256, 0, st>>>(x, h_params[0], h_params[1], bf(L.a1), batch);
   }
@@ -2243,8 +2255,8 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     if (r2 != SG_OK) return r2;
     const int64_t tiles = ceil_div(batch * 289, 128);
     const int64_t ctas2 = (int64_t)state().sm_count * 3;
-    ae_enc2x_kernel<HALF><<<(int)(tiles < ctas2 ? tiles : ctas2), 192, Enc2XCfg::kSmemBytes, st>>>(
-        tb, bf(L.a1), a1x_plane_elems(batch), h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
+    SG_LAUNCH_PDL(ae_enc2x_kernel<HALF>, dim3((unsigned)(tiles < ctas2 ? tiles : ctas2)), dim3(192), (size_t)Enc2XCfg::kSmemBytes, st, tb,
+                  (const __nv_bfloat16*)bf(L.a1), a1x_plane_elems(batch), h_params[3], bf(L.a2), (int)batch, (int)tiles, err);
   } else {
     enc2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a1), h_params[2], h_params[3], bf(L.a2), batch);
   }
@@ -2283,9 +2295,9 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     if (r != SG_OK) return r;
     const int64_t tiles = ceil_div(batch * 289, 128);
     const int64_t ctas = (int64_t)state().sm_count * 4;
-    ae_dec2x_kernel<HALF><<<(int)(tiles < ctas ? tiles : ctas), 192, Dec2XCfg::kSmemBytes, st>>>(
-        tb, bf(L.a4), a4x_plane_elems(batch), h_params[9], bf(L.a5), a5x_plane_elems(batch), (int)batch, (int)tiles, err);
-    SG_LAUNCH_CHECK();
+    SG_LAUNCH_PDL(ae_dec2x_kernel<HALF>, dim3((unsigned)(tiles < ctas ? tiles : ctas)), dim3(192), (size_t)Dec2XCfg::kSmemBytes, st, tb,
+                  (const __nv_bfloat16*)bf(L.a4), a4x_plane_elems(batch), h_params[9], bf(L.a5), a5x_plane_elems(batch), (int)batch, (int)tiles,
+                  err);
     cuuint64_t b6dims[2] = {144, 16};
     cuuint64_t b6str[1] = {288};
     r = encode_tmap(&tb, 2, bf(L.w6), b6dims, b6str, bbox, CU_TENSOR_MAP_SWIZZLE_32B);
@@ -2293,10 +2305,11 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     const int64_t tiles6 = batch * Dec3XCfg::kTilesPerImage;
     float* part = reinterpret_cast<float*>(ws + L.part);
     const int64_t ctas6 = (int64_t)state().sm_count * 4;
-    ae_dec3x_kernel<HALF><<<(int)(tiles6 < ctas6 ? tiles6 : ctas6), 192, Dec3XCfg::kSmemBytes, st>>>(
-        tb, bf(L.a5), a5x_plane_elems(batch), h_params[11], x, recon_out, part, (int)tiles6, err);
-    SG_LAUNCH_CHECK();
-    ae_mse_finish_kernel<Dec3XCfg::kTilesPerImage><<<(unsigned)ceil_div(batch, 256), 256, 0, st>>>(part, batch, err_out);
+    SG_LAUNCH_PDL(ae_dec3x_kernel<HALF>, dim3((unsigned)(tiles6 < ctas6 ? tiles6 : ctas6)), dim3(192), (size_t)Dec3XCfg::kSmemBytes, st, tb,
+                  (const __nv_bfloat16*)bf(L.a5), a5x_plane_elems(batch), h_params[11], x, recon_out, part, (int)tiles6, err);
+    SG_LAUNCH_PDL(ae_mse_finish_kernel<Dec3XCfg::kTilesPerImage>, dim3((unsigned)ceil_div(batch, 256)), dim3(256), (size_t)0, st,
+                  (const float*)part, batch, err_out);
+    return SG_OK;
   } else {
     dec2_kernel<SEG><<<blocks(batch * 256), 256, 0, st>>>(bf(L.a4), h_params[8], h_params[9], bf(L.a5), batch);
     SG_LAUNCH_CHECK();
@@ -2322,8 +2335,6 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<false>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
