@@ -525,7 +525,10 @@ struct K7XCfg {
   static constexpr int kOutBytes = kOutPixels * kCout * 2;      // one image's output block
   static constexpr int kStgBytes = CONVT ? 4 * 289 * 16 : kOutBytes;   // two staging buffers (dec1: room for the linear-halo form)
   static constexpr int kTmemCols = 512;                         // 2 accumulators x 256 columns
-  static constexpr int kThreads = 224;                          // + warp 6: image producer
+  // dec1: four epilogue warpgroups of 64 accumulator columns each (one group -- one warp per scheduler -- needs ~6 700 cycles
+  // of dependent tcgen05.ld -> shuffle -> shuffle -> st.shared per image, more than the image's 4 500 cycles of MMAs)
+  static constexpr int kEpiGroups = CONVT ? 4 : 1;
+  static constexpr int kThreads = 224 + (kEpiGroups - 1) * 128;  // warps 0 weights, 1 MMA, 2-5 epilogue group 0, 6 images, 7.. groups 1..
   static constexpr int kBarBytes = 512;
   static constexpr int kSpill = 2048;                           // enc3 reads up to 102 pixels past a channel group
   static constexpr int kSmemBytes = kSlots * kSlotBytes + kSpill + (kResident + kBStages) * kBBytes + 2 * kStgBytes +
@@ -543,7 +546,7 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t 
 // dec1 writes its output in the linear-halo form [co / 8][image][17 x 17][8] (a4x_plane_elems) that ae_dec2x_kernel consumes;
 // the zero column / row come from the staging buffer, which starts zeroed and is never written there.
 template <bool CONVT, bool HALF>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(K7XCfg<CONVT>::kThreads, 1)
 ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err, size_t out_plane) {
   pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
@@ -578,7 +581,7 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     prefetch_tensormap(&tmap_b);
     for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128 * Cfg::kEpiGroups); }
     mbar_init(wres_bar, 1);
     *s_abort = 0;
     fence_barrier_init();
@@ -638,6 +641,11 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_16(128, Cfg::kN, HALF);
+      // dec1: tap row ky only reaches the output rows ky .. ky + 9 (the 10 input rows): instead of multiplying the zero rows of
+      // the padded field, every MMA but the first covers N = 160 columns and lands 16 ky columns further in the accumulator;
+      // the operand window (input rows 0..9 and the zero row / columns in front) no longer depends on ky.  The first MMA of an
+      // image runs over all 256 columns without accumulation and so clears the rest.  7 168 -> 4 528 tensor cycles per image.
+      constexpr uint32_t idesc160 = umma_idesc_16(128, 160, HALF);
       int aslot = 0, bstage = 0, acc = 0;
       uint32_t aphase = 0, bphase = 0, acc_phase = 0;
       bool ok = true;
@@ -656,7 +664,7 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 #pragma unroll
         for (int s = 0; s < Cfg::kStagesPerImage; ++s) {
           const int c = s / 7, ky = s % 7;
-          const int px = CONVT ? (112 - 16 * ky - Cfg::kTaps * c) : (16 * ky + Cfg::kTaps * c);
+          const int px = CONVT ? (112 - Cfg::kTaps * c) : (16 * ky + Cfg::kTaps * c);
           uint64_t wdesc;
           if (!Cfg::resident(s)) {
             if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 35)) { ok = false; break; }
@@ -667,8 +675,9 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           }
 #pragma unroll
           for (int k = 0; k < Cfg::kK16; ++k)
-            umma_f16(tmem_d, wdesc + (uint64_t)((2 * k * Cfg::kLboA) >> 4), img_desc + (uint64_t)((px * 16 + 2 * k * Cfg::kLboB) >> 4),
-                     idesc, (uint32_t)((s | k) != 0));
+            umma_f16(tmem_d + (uint32_t)(CONVT ? 16 * ky : 0), wdesc + (uint64_t)((2 * k * Cfg::kLboA) >> 4),
+                     img_desc + (uint64_t)((px * 16 + 2 * k * Cfg::kLboB) >> 4), (CONVT && (s | k) != 0) ? idesc160 : idesc,
+                     (uint32_t)((s | k) != 0));
           if (!Cfg::resident(s)) {
             umma_commit(bempty_bar(bstage));
             if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
@@ -681,15 +690,18 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // ================= epilogue =================
+  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
+    // ================= epilogue (dec1: four warpgroups, 64 accumulator columns each) =================
     // Accumulator row = co * taps + kxl: the rows of one output channel are ADJACENT LANES of one warp, so the sum over
     // kxl is a lane exchange (shfl.xor) between 2 (enc3) / 4 (dec1) neighbours -- no shared-memory pass, no barriers.
     // Each lane of a group finishes every 2nd / 4th output position of its channel.
     const int q = warp & 3;                           // TMEM lane quadrant of this warp
     const int L = q * 32 + lane;                      // accumulator row
     const int kxl = L % Cfg::kTaps, co = L / Cfg::kTaps;
-    const int t = threadIdx.x - 64;                   // 0..127
+    const int grp = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;
+    const int t = warp >= 7 ? (int)threadIdx.x - 96 : (int)threadIdx.x - 64;     // 0 .. 128 kEpiGroups - 1
+    constexpr int kStepsPerGroup = Cfg::kSteps / Cfg::kEpiGroups;
+    const int j0 = grp * kStepsPerGroup, j1 = j0 + kStepsPerGroup;
     const float my_bias = s_bias[co];
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
@@ -698,13 +710,21 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       uint16_t* stg = reinterpret_cast<uint16_t*>(smem + (g_base - base) + buf * Cfg::kStgBytes);
-      float c1 = 0.f, c2 = 0.f, c3 = 0.f;             // this lane's columns 32 j - 1, - 2, - 3
+      float c1 = 0.f, c2 = 0.f;                       // this lane's column 32 j - 1 / its last level-1 sum of the step before
+      if (CONVT && grp) {                             // carries into this group's first column from the three before it
+        uint32_t w4[4];
+        tmem_ld_32x32_x4(taddr + (uint32_t)(32 * j0 - 4), w4);
+        tmem_ld_wait();
+        const float b3 = __uint_as_float(w4[1]), b2 = __uint_as_float(w4[2]), b1 = __uint_as_float(w4[3]);   // columns -3, -2, -1
+        c1 = b1;
+        c2 = b2 + __shfl_xor_sync(0xffffffffu, (kxl & 1) ? b3 : b1, 1);
+      }
 #pragma unroll 1
-      for (int j = 0; j < Cfg::kSteps; ++j) {
+      for (int j = j0; j < j1; ++j) {
         uint32_t u[32];
         tmem_ld_32x32(taddr + (uint32_t)(32 * j), u);
         tmem_ld_wait();
-        if (j == Cfg::kSteps - 1) {                   // the accumulator is free once its last columns are in registers
+        if (j == j1 - 1) {                            // this group's last columns are in registers
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
@@ -739,7 +759,6 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             else stg[n * 32 + co] = pk1<HALF>(fmaxf(a, 0.f));
           }
           c1 = v[31]; c2 = pp[15];
-          (void)c3;
         } else {
           // out[n] = D_0[n] + D_1[n + 1]; one exchange of column 2 k serves both lanes of a pair: the even lane finishes
           // n = 32 j + 2 k - 1 (own column 2 k - 1), the odd lane n = 32 j + 2 k (own column 2 k + 1)
@@ -756,11 +775,11 @@ ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           c1 = v[31];
         }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 128 * Cfg::kEpiGroups);
       if (XOUT) {
         // four contiguous runs of 289 positions x 16 bytes, one per channel-group plane
         const uint4* src = reinterpret_cast<const uint4*>(stg);
-        for (int i = t; i < 4 * 289; i += 128) {
+        for (int i = t; i < 4 * 289; i += 128 * Cfg::kEpiGroups) {
           const int g = i / 289, k = i - g * 289;
           reinterpret_cast<uint4*>(out + (size_t)g * out_plane + (size_t)img * (289 * 8))[k] = src[i];
         }
