@@ -1102,6 +1102,259 @@ static int launch_k7p(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
 }
 
 // ------------------------------------------------------------------------------------------
+// L4 (dec1) on CTA PAIRS.  ae_k7x_kernel<true> streams the layer's 224 KB of weights through shared memory for every image:
+// with the N = 160 form of its MMAs that L2 -> SM traffic (148 SMs x 224 KB per 4.4 us) became its bound.  As a pair the two
+// CTAs split the output channels, M = 256 = 2 x (16 co x 8 column taps): all eight kx (kx == 7: zero weights) are rows, so
+//   D[(co, g)][m] = sum_{ky, ci} w[ci][co][ky][g] * in[m - 16 ky][ci]          out[co][n] = sum_g D[(co, g)][n - g]
+// needs NO shifted operand windows at all: tap row ky lands 16 ky columns further in the accumulator (N = 160 = the ten
+// input rows at a pitch of 16, each CTA feeding five of them), the column taps are summed by a three-level lane butterfly.
+// A CTA's half of the weights -- 7 stages x 16 KB -- is RESIDENT; per image only 10 KB of input move per CTA.  Columns
+// 160..255 of a fresh accumulator are cleared by one N = 96 MMA on a zero operand.  Four epilogue warpgroups of 64 columns.
+// ------------------------------------------------------------------------------------------
+struct K7QCfg {
+  static constexpr int kGroups = 8, kStages = 7, kK16 = 4;
+  static constexpr int kLboB = 80 * 16;                  // image half: bytes between channel groups (5 rows x 16 px)
+  static constexpr int kSlotBytes = kGroups * kLboB;     // 10 240
+  static constexpr int kSlots = 3;
+  static constexpr int kLboA = 128 * 16;
+  static constexpr int kBBytes = kGroups * kLboA;        // 16 384 per stage
+  static constexpr int kWBytes = kStages * kBBytes;      // 114 688, resident
+  static constexpr int kZeroBytes = 2 * 48 * 16;         // zero operand of the clearing MMA: 2 channel groups x 48 pixels
+  static constexpr int kStgBytes = 2 * 289 * 16;         // this CTA's two channel-group planes of one image (linear-halo form)
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSteps = 8, kEpiGroups = 4;
+  static constexpr int kThreads = 128 + kEpiGroups * 128;   // warps 0 weights, 1 MMA, 2 images (+ TMEM alloc), 3 idle, 4.. epilogue
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + kWBytes + kZeroBytes + 2 * kStgBytes + kBarBytes + 256 + 1024;
+};
+
+template <bool HALF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(K7QCfg::kThreads, 1)
+ae_k7q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err, size_t out_plane) {
+  pdl_launch_dependents();
+  using Cfg = K7QCfg;
+  constexpr int UA = Cfg::kSlots;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t w_base = base + UA * Cfg::kSlotBytes;          // resident weight stages of this CTA's 16 output channels
+  const uint32_t z_base = w_base + Cfg::kWBytes;                // zero operand
+  const uint32_t g_base = z_base + Cfg::kZeroBytes;             // two output staging buffers
+  const uint32_t bar0 = g_base + 2 * Cfg::kStgBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
+  auto afull_bar = [&](int s) { return bar0 + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 + a); };
+  const uint32_t wres_bar = bar0 + 8u * (2 * UA + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * UA + 5);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + 2 * UA + 6);
+  float* s_bias = reinterpret_cast<float*>(smem + (bar0 - base) + Cfg::kBarBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * Cfg::kEpiGroups); }   // epilogue warps x 2 CTAs
+    mbar_init(wres_bar, 1);
+    *s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  if (threadIdx.x < 16) s_bias[threadIdx.x] = bias[rank * 16 + threadIdx.x];
+  // the zero operand and the staging buffers (their halo positions are never written) start zeroed
+  for (int i = threadIdx.x; i < (int)((bar0 - z_base) / 16); i += Cfg::kThreads)
+    *reinterpret_cast<uint4*>(smem + (z_base - base) + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================= weights: this CTA's 7 stages, once; the transaction bytes of both CTAs go to the leader's barrier
+    if (lane == 0) {
+      const uint32_t lead_wres = mapa_shared(wres_bar, 0);
+      if (leader) mbar_arrive_expect_tx(wres_bar, 2 * Cfg::kWBytes);
+      const int row0 = (int)((pair % kWeightCopies) * 2 + rank) * Cfg::kStages * (Cfg::kBBytes / 128);
+      for (int s = 0; s < Cfg::kStages; ++s)
+        tma_load_2d_pair(w_base + s * Cfg::kBBytes, &tmap_b, lead_wres, 0, row0 + s * (Cfg::kBBytes / 128));
+    }
+  } else if (warp == 2) {
+    // ================= images: each CTA loads its five input rows (16 pixels per row: columns 10..15 zero-filled)
+    if (lane == 0) {
+      int aslot = 0;
+      uint32_t aphase = 0;
+      for (int img = pair; img < n_img; img += npairs) {
+        if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 31)) break;
+        const uint32_t lead_afull = mapa_shared(afull_bar(aslot), 0);
+        if (leader) mbar_arrive_expect_tx(afull_bar(aslot), 2 * Cfg::kSlotBytes);
+        tma_load_4d_pair(base + aslot * Cfg::kSlotBytes, &tmap_a, lead_afull, 0, (int)rank * 5, 0, img);
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA): 28 MMAs of M256 x N160 x K16 (+ the clearing one) per image
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_16(256, 160, HALF), idesc_z = umma_idesc_16(256, 96, HALF);
+      int aslot = 0, acc = 0;
+      uint32_t aphase = 0, acc_phase = 0;
+      bool ok = mbar_wait(wres_bar, 0, s_abort, err, kErrBase + 37);
+      const uint64_t wdesc0 = umma_desc_nosw(w_base, Cfg::kLboA, 128);
+      const uint64_t zdesc = umma_desc_nosw(z_base, 48 * 16, 128);
+      for (int img = pair; img < n_img && ok; img += npairs) {
+        if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 33)) break;
+        if (!mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 34)) break;
+        tc_fence_after();
+        const uint64_t img_desc = umma_desc_nosw(base + aslot * Cfg::kSlotBytes, Cfg::kLboB, 128);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        umma_f16_pair(tmem_d + 160, wdesc0, zdesc, idesc_z, 0u);      // columns 160..255 := 0 (finite weights x zeros)
+#pragma unroll
+        for (int ky = 0; ky < Cfg::kStages; ++ky)
+#pragma unroll
+          for (int k = 0; k < Cfg::kK16; ++k)
+            umma_f16_pair(tmem_d + (uint32_t)(16 * ky), wdesc0 + (uint64_t)((ky * Cfg::kBBytes + 2 * k * Cfg::kLboA) >> 4),
+                          img_desc + (uint64_t)((2 * k * Cfg::kLboB) >> 4), idesc, (uint32_t)((ky | k) != 0));
+        umma_commit_pair(tfull_bar(acc), 3);
+        umma_commit_pair(aempty_bar(aslot), 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs, four warpgroups of 64 columns): accumulator row = co_local * 8 + g;
+    // out[n] = sum_{g < 8} D_g[n - g] as a three-level butterfly:
+    //   level 1 (lanes g ^ 1): P[c] = D_even[c] + D_odd[c - 1]   -- the even lane finishes the even columns, the odd lane the odd ones
+    //   level 2 (lanes g ^ 2): Q[c] = P_lo[c] + P_hi[c - 2]       -- lane g finishes the columns c = 4 k + (g & 3)
+    //   level 3 (lanes g ^ 4): o[c] = Q_0[c] + Q_1[c - 4]         -- lanes 0..3 finish the even k, lanes 4..7 the odd k
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int L = q * 32 + lane;
+    const int g = L & 7, gm = g & 3, co = L >> 3;     // co: 0..15 of this CTA
+    const int t = (int)threadIdx.x - 128;             // 0 .. 511
+    const int j0 = 2 * grp, j1 = j0 + 2;
+    const float my_bias = s_bias[co];
+    const bool odd = (g & 1) != 0, hi2 = (g & 2) != 0, hi4 = (g & 4) != 0;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0;
+    for (int img = pair; img < n_img; img += npairs) {
+      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 36)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      uint16_t* stg = reinterpret_cast<uint16_t*>(smem + (g_base - base) + buf * Cfg::kStgBytes);
+      float c1 = 0.f, c2 = 0.f, c3 = 0.f;             // carries of the three levels from the columns before this step
+      if (grp) {                                      // ... re-derived from the seven columns in front of this group's first
+        uint32_t w8[8];
+        tmem_ld_32x32_x8(taddr + (uint32_t)(32 * j0 - 8), w8);
+        tmem_ld_wait();
+        const float v25 = __uint_as_float(w8[1]), v26 = __uint_as_float(w8[2]), v27 = __uint_as_float(w8[3]),
+                    v28 = __uint_as_float(w8[4]), v29 = __uint_as_float(w8[5]), v30 = __uint_as_float(w8[6]),
+                    v31 = __uint_as_float(w8[7]);
+        const float p13 = v26 + __shfl_xor_sync(0xffffffffu, odd ? v25 : v27, 1);
+        const float p14 = v28 + __shfl_xor_sync(0xffffffffu, odd ? v27 : v29, 1);
+        const float p15 = v30 + __shfl_xor_sync(0xffffffffu, odd ? v29 : v31, 1);
+        c1 = v31;
+        c2 = p15;
+        c3 = p14 + __shfl_xor_sync(0xffffffffu, hi2 ? p13 : p15, 2);
+      }
+#pragma unroll 1
+      for (int j = j0; j < j1; ++j) {
+        uint32_t u[32];
+        tmem_ld_32x32(taddr + (uint32_t)(32 * j), u);
+        tmem_ld_wait();
+        if (j == j1 - 1) {                            // this group's last columns are in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+        float pp[16];
+#pragma unroll
+        for (int t2 = 0; t2 < 16; ++t2) {
+          const int i = 2 * t2;
+          const float below = t2 == 0 ? c1 : v[t2 == 0 ? 0 : i - 1];
+          pp[t2] = v[i] + __shfl_xor_sync(0xffffffffu, odd ? below : v[i + 1], 1);
+        }
+        float qv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float before = k == 0 ? c2 : pp[k == 0 ? 0 : 2 * k - 1];
+          qv[k] = pp[2 * k] + __shfl_xor_sync(0xffffffffu, hi2 ? before : pp[2 * k + 1], 2);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float prev = kk == 0 ? c3 : qv[kk == 0 ? 0 : 2 * kk - 1];
+          const float a = my_bias + qv[2 * kk] + __shfl_xor_sync(0xffffffffu, hi4 ? prev : qv[2 * kk + 1], 4);
+          const int n = 32 * j + 4 * (2 * kk + (hi4 ? 1 : 0)) + gm;
+          // a4 in linear-halo form, this CTA's two channel-group planes; ReLU follows the decoder's first layer
+          stg[((co >> 3) * 289 + (n >> 4) * 17 + (n & 15)) * 8 + (co & 7)] = pk1<HALF>(fmaxf(a, 0.f));
+        }
+        c1 = v[31]; c2 = pp[15]; c3 = qv[7];
+      }
+      named_bar_sync(1, 128 * Cfg::kEpiGroups);
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(stg);
+        for (int i = t; i < 2 * 289; i += 128 * Cfg::kEpiGroups) {
+          const int cg = i / 289, k = i - cg * 289;
+          reinterpret_cast<uint4*>(out + (size_t)(2 * rank + cg) * out_plane + (size_t)img * (289 * 8))[k] = src[i];
+        }
+      }
+      buf ^= 1;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// dec1 weights for the pair kernel: [rank][ky][ci / 8][row = co_local * 8 + g][ci % 8], co = 16 rank + co_local, kx = g (7: zero)
+template <bool HALF>
+__global__ void pack_k7q_kernel(const float* __restrict__ w4, __nv_bfloat16* __restrict__ p4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * 7 * 8192) {
+    const int e = i & 7, row = (i >> 3) & 127, grp = (i >> 10) & 7, ky = (i >> 13) % 7, r = i / (7 * 8192);
+    const int ci = grp * 8 + e, kx = row & 7, co = r * 16 + (row >> 3);
+    p4[i] = __ushort_as_bfloat16(pk1<HALF>(kx < 7 ? w4[((ci * 32 + co) * 7 + ky) * 7 + kx] : 0.f));
+  }
+}
+
+template <bool HALF>
+static int launch_k7q(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
+                      int64_t batch, int* err, cudaStream_t st) {
+  using Cfg = K7QCfg;
+  CUtensorMap ta, tb;
+  // a3 [n][8 groups][10 rows][10 px x 8 ci]: a CTA's half = 5 rows of 16 pixels (pixels 10..15 zero fill)
+  cuuint64_t dims[4] = {80, 10, 8, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {160, 1600, 12800};
+  cuuint32_t box[4] = {128, 5, 8, 1};
+  int r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (r != SG_OK) return r;
+  cuuint64_t wdims[2] = {64, (cuuint64_t)kWeightCopies * 2 * Cfg::kStages * (Cfg::kBBytes / 128)};
+  cuuint64_t wstr[1] = {128};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)(Cfg::kBBytes / 128)};
+  r = encode_tmap(&tb, 2, wpk, wdims, wstr, wbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (r != SG_OK) return r;
+  const int64_t pairs_max = state().sm_count / 2;
+  const int pairs = (int)(batch < pairs_max ? batch : pairs_max);
+  SG_LAUNCH_PDL(ae_k7q_kernel<HALF>, dim3(2 * pairs), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, ta, tb, bias, act_out, (int)batch, err,
+                a4x_plane_elems(batch));
+  return SG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // L1 (enc Conv 3->16 k3 s2 p1 + ReLU) on tcgen05, fused with the fp32 -> 16-bit input conversion (the structure of
 // d64.cu's conv1_fused_kernel: a 3x3 stride-2 pad-1 filter is that kernel's 4x4 stride-2 pad-1 geometry with the
 // fourth filter row / column absent).  One tile = 4 output rows x 32 columns of one image (M = 128), N = 16:
@@ -2219,9 +2472,9 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     // the weight blocks sit in front of the activations: their offsets do not depend on the batch size
     SG_CUDA(cudaMemsetAsync(ws + L.flag, 0, 1024, st));
     if constexpr (SEG == 1) {
-      pack_k7x_kernel<HALF><<<(4 * 7 * 128 * 32 + 255) / 256, 256, 0, st>>>(h_params[4], h_params[6], bf(L.w3t), bf(L.w4t));
-      SG_LAUNCH_CHECK();
       pack_k7p_kernel<HALF><<<(2 * 14 * 4096 + 255) / 256, 256, 0, st>>>(h_params[4], bf(L.w3t));   // enc3: the pair kernel's form
+      SG_LAUNCH_CHECK();
+      pack_k7q_kernel<HALF><<<(2 * 7 * 8192 + 255) / 256, 256, 0, st>>>(h_params[6], bf(L.w4t));    // dec1: the pair kernel's form
       SG_LAUNCH_CHECK();
       for (int c = 1; c < kWeightCopies; ++c) {
         SG_CUDA(cudaMemcpyAsync(ws + L.w3t + (size_t)c * 229376, ws + L.w3t, 229376, cudaMemcpyDeviceToDevice, st));
@@ -2285,7 +2538,7 @@ static int score_impl(const float* x, int64_t batch, const float* const* h_param
     // single-segment modes: both 7x7 layers in shifted-window form (weights on M, the image's pixels on N, taps = descriptor offsets)
     r = launch_k7p<HALF>(bf(L.a2), bf(L.w3t), h_params[5], bf(L.a3), batch, err, st);   // enc3 on CTA pairs
     if (r != SG_OK) return r;
-    r = launch_k7x<true, HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);   // a4 in linear-halo form
+    r = launch_k7q<HALF>(bf(L.a3), bf(L.w4t), h_params[7], bf(L.a4), batch, err, st);   // dec1 on CTA pairs, a4 in linear-halo form
     if (r != SG_OK) return r;
   } else {
     r = launch_k7<64, false, SEG == 2, HALF>(bf(L.a2), bf(L.w3), h_params[5], bf(L.a3), batch, err, st);
@@ -2352,6 +2605,8 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_enc2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_enc2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Enc2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec1Cfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7QCfg::kSmemBytes));
+  SG_CUDA(cudaFuncSetAttribute(ae_k7q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7QCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
