@@ -7,8 +7,8 @@
 //
 //   L1 enc Conv 3->16  k3 s2 p1 + ReLU   fp32 NCHW in -> [ci / 8][pixel parity][17 x 17 with zero halo][8]   ae_enc1_tc_kernel (input conversion fused)
 //   L2 enc Conv 16->32 k3 s2 p1 + ReLU   -> [ci / 8][16 x 16][8]                   ae_enc2x_kernel (linear-halo form over parity planes)
-//   L3 enc Conv 32->64 k7                -> [co / 8][10 x 10][8]                   ae_k7x_kernel<false>: shifted-window form
-//   L4 dec ConvT 64->32 k7 + ReLU        -> [co / 8][17 x 17 with zero halo][8]    ae_k7x_kernel<true>
+//   L3 enc Conv 32->64 k7                -> [co / 8][10 x 10][8]                   ae_k7p_kernel: shifted-window form on CTA pairs
+//   L4 dec ConvT 64->32 k7 + ReLU        -> [co / 8][17 x 17 with zero halo][8]    ae_k7q_kernel: the same, taps as accumulator offsets
 //   L5 dec ConvT 32->16 k3 s2 p1 op1 + ReLU -> [co / 8][33 x 33 with zero halo][8]  ae_dec2x_kernel (linear-halo form)
 //   L6 dec ConvT 16->3  k3 s2 p1 op1 + tanh + squared error vs the input + per-sample mean (fixed order)   ae_dec3x_kernel
 //
@@ -473,69 +473,17 @@ ae_dec1_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// The two 7x7 layers in SHIFTED-WINDOW form (single-segment modes; replaced a row-tap form -- column taps stacked on N,
-// a half-warp shuffle col2im of 448 / 224 accumulator values per thread -- that ran at 438 / 357 us per 8 192 images with the
-// tensor pipe 49 % / 60 % active; this form: 229 / 271 us, 67 % / 92 %).  The GEMM is transposed -- the WEIGHTS are the M operand,
-// the image's pixels are the N operand -- and the image sits in shared memory ONCE, in the un-swizzled core-matrix
-// layout [ci / 8][pixel][8 ci] (16 bytes per pixel and channel group, pixels at a pitch of 16 columns).  In that layout
-// the operand of filter tap (ky, kx) is the same copy at a start address shifted by ky * 16 + kx pixels: a descriptor
-// offset of 16 bytes per pixel, nothing is re-fetched or re-arranged per tap.  Column m of the accumulator is the
-// linearised pixel index, so a COLUMN shift of the filter is a shift along the accumulator's columns:
-//
-//   enc3  D[(kxl, co)][m] = sum_{c, ky, ci} w[co][ci][ky][2c + kxl] * in[m + 16 ky + 2c][ci]     out[co][n] = D[(0, co)][n] + D[(1, co)][n + 1]
-//   dec1  D[(kxl, co)][m] = sum_{c, ky, ci} w[ci][co][ky][4c + kxl] * pad[m - 16 ky - 4c + 112][ci]   out[co][n] = sum_kxl D[(kxl, co)][n - kxl]
-//
-// (pad: the 10 x 10 input at rows 7..16 of a 23 x 16 zero field -- columns 10..15 of a row are at once its right padding
-// and the next row's left padding, so the flattened 1-D convolution equals the 2-D one; TMA's out-of-bounds zero fill
-// writes the field.)  M = 128 rows = 2 (enc3) / 4 (dec1) column taps x C_out, N = 160 (the 10 output rows of enc3) /
-// 256 pixels, K = 16: 56 MMAs per image accumulate ALL taps in the tensor core.  Accumulator row = co * taps + kxl, so the
-// rows of one output channel are adjacent lanes of one epilogue warp and the remaining sum over kxl is one (enc3) / two
-// (dec1) shfl.xor exchanges per output -- 160 / 256 TMEM values per thread and image, no shared-memory pass, no barrier.
-// M128 x N256 x K16 reads 12 KB of operands for 128 tensor cycles (96 B/clk): the tensor pipe is the bound.
-//   warp 0: TMA producer, weight stages (one dense 8 / 16 KB box per (c, ky); enc3 keeps 14 of its 28 stages resident)
-//   warp 6: TMA producer, images (one dense box per image: the layers before write the [ci / 8][pixel][8] form)
-//   warp 1: MMA issuer (stage loop fully unrolled: ~10 instructions per MMA)
-//   warps 2-5: epilogue (TMEM -> lane exchanges -> bias (+ ReLU) -> 16-bit staging -> 16-byte global stores)
+// The two 7x7 layers of the single-segment modes in SHIFTED-WINDOW form on CTA pairs (ae_k7p_kernel, ae_k7q_kernel below).
+// The GEMM is transposed -- the WEIGHTS are the M operand, the image's pixels are the N operand -- and the image sits in shared
+// memory ONCE, in the un-swizzled core-matrix layout [ci / 8][pixel][8 ci] (16 bytes per pixel and channel group, pixels at a
+// pitch of 16 columns).  In that layout a filter tap is the same copy at a shifted start address (a descriptor offset of 16
+// bytes per pixel) or the same product landing at a shifted accumulator column; column taps are stacked on the M rows
+// (row = co * taps + tap), so the rows of one output channel are adjacent lanes of one epilogue warp and their sum is a lane
+// butterfly (shfl.xor) -- no im2col, no shared-memory pass.  All 49 taps accumulate in the tensor core.
+// History (per 8 192 images, enc3 / dec1): row-tap form with a shuffle col2im 438 / 357 us; single-CTA shifted-window form
+// (weights streamed through shared memory per image, one epilogue warpgroup) 246 / 272 us; pairs + resident weights + one
+// epilogue warpgroup per 32 / 64 columns + (dec1) tap rows as accumulator column offsets: 212 / 229 us.
 // ------------------------------------------------------------------------------------------
-template <bool CONVT>
-struct K7XCfg {
-  static constexpr int kCin = CONVT ? 64 : 32, kCout = CONVT ? 32 : 64;
-  static constexpr int kGroups = kCin / 8;                      // channel groups of 8 (one core-matrix column each)
-  static constexpr int kTaps = 128 / kCout;                     // column taps stacked on M: 2 (enc3) / 4 (dec1)
-  static constexpr int kChunks = CONVT ? 2 : 4;                 // kx = chunk * kTaps + kxl (kx == 7: zero weights)
-  static constexpr int kStagesPerImage = kChunks * 7;
-  static constexpr int kPixels = CONVT ? 23 * 16 : 256;         // pixels per channel group in a slot
-  static constexpr int kLboB = kPixels * 16;                    // operand B: bytes between channel groups
-  static constexpr int kSlotBytes = kGroups * kLboB;            // 16 384 / 47 104
-  static constexpr int kSlots = 2;
-  static constexpr int kN = CONVT ? 256 : 160;                  // accumulator columns (enc3: output rows 0..9 only)
-  static constexpr int kSteps = kN / 32;
-  static constexpr int kLboA = 128 * 16;                        // operand A: bytes between channel groups of a stage
-  static constexpr int kBBytes = kGroups * kLboA;               // one (chunk, ky) weight stage: 8 / 16 KB
-  // all 148 SMs stream the same 224 KB of weights per image: at ~6 us per image that is the whole L2 -> SM bandwidth
-  // (5.3-6.1 TB/s measured), not the tensor pipe.  enc3 keeps the stages of its first two chunks RESIDENT in shared
-  // memory (loaded once per CTA) and streams only the other half.
-  static constexpr int kResident = CONVT ? 0 : 14;
-  // (resident = the FIRST stages of an image: alternating resident / streamed stages was slower, 252 against 229 us)
-  __host__ __device__ static constexpr bool resident(int s) { return s < kResident; }
-  __host__ __device__ static constexpr int resident_index(int s) { return s; }
-  static constexpr int kBStages = CONVT ? 5 : 6;
-  static constexpr int kK16 = kCin / 16;
-  static constexpr int kOutPixels = CONVT ? 256 : 100;
-  static constexpr int kOutBytes = kOutPixels * kCout * 2;      // one image's output block
-  static constexpr int kStgBytes = CONVT ? 4 * 289 * 16 : kOutBytes;   // two staging buffers (dec1: room for the linear-halo form)
-  static constexpr int kTmemCols = 512;                         // 2 accumulators x 256 columns
-  // dec1: four epilogue warpgroups of 64 accumulator columns each (one group -- one warp per scheduler -- needs ~6 700 cycles
-  // of dependent tcgen05.ld -> shuffle -> shuffle -> st.shared per image, more than the image's 4 500 cycles of MMAs)
-  static constexpr int kEpiGroups = CONVT ? 4 : 1;
-  static constexpr int kThreads = 224 + (kEpiGroups - 1) * 128;  // warps 0 weights, 1 MMA, 2-5 epilogue group 0, 6 images, 7.. groups 1..
-  static constexpr int kBarBytes = 512;
-  static constexpr int kSpill = 2048;                           // enc3 reads up to 102 pixels past a channel group
-  static constexpr int kSmemBytes = kSlots * kSlotBytes + kSpill + (kResident + kBStages) * kBBytes + 2 * kStgBytes +
-                                    kBarBytes + 256 + 1024;
-  static_assert(kSmemBytes <= 232448, "shared memory");
-};
-
 // K-major operand WITHOUT swizzle: core matrices of 8 rows x 16 bytes (128 contiguous bytes); SBO = bytes between 8-row
 // groups, LBO = bytes between the two core matrices of a K = 16 step (layout type 0).
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -543,319 +491,8 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t 
          (1ull << 46);
 }
 
-// dec1 writes its output in the linear-halo form [co / 8][image][17 x 17][8] (a4x_plane_elems) that ae_dec2x_kernel consumes;
-// the zero column / row come from the staging buffer, which starts zeroed and is never written there.
-template <bool CONVT, bool HALF>
-__global__ void __launch_bounds__(K7XCfg<CONVT>::kThreads, 1)
-ae_k7x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-              const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n_img, int* err, size_t out_plane) {
-  pdl_launch_dependents();   // the next kernel of the chain may set up (barriers, TMEM, descriptors) behind this one
-  constexpr bool XOUT = CONVT;
-  using Cfg = K7XCfg<CONVT>;
-  constexpr int UA = Cfg::kSlots, SB = Cfg::kBStages, COUT = Cfg::kCout;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
-  const uint32_t r_base = base + UA * Cfg::kSlotBytes + Cfg::kSpill;      // resident weight stages
-  const uint32_t b_base = r_base + Cfg::kResident * Cfg::kBBytes;         // ring of streamed weight stages
-  const uint32_t g_base = b_base + SB * Cfg::kBBytes;
-  const uint32_t bar0 = g_base + 2 * Cfg::kStgBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar0 - base));
-  auto afull_bar = [&](int s) { return bar0 + 8u * s; };
-  auto aempty_bar = [&](int s) { return bar0 + 8u * (UA + s); };
-  auto bfull_bar = [&](int s) { return bar0 + 8u * (2 * UA + s); };
-  auto bempty_bar = [&](int s) { return bar0 + 8u * (2 * UA + SB + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * UA + 2 * SB + 2 + a); };
-  constexpr int kNb = 2 * UA + 2 * SB + 5;
-  const uint32_t wres_bar = bar0 + 8u * (kNb - 1);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNb);
-  volatile int* s_abort = reinterpret_cast<volatile int*>(bars + kNb + 1);
-  static_assert((kNb + 2) * 8 <= Cfg::kBarBytes, "barrier block too small");
-  float* s_bias = reinterpret_cast<float*>(smem + (bar0 - base) + Cfg::kBarBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_a);
-    prefetch_tensormap(&tmap_b);
-    for (int s = 0; s < UA; ++s) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128 * Cfg::kEpiGroups); }
-    mbar_init(wres_bar, 1);
-    *s_abort = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-  if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
-  // operand memory starts finite: enc3's windows run up to 102 pixels past a channel group (into the next group, the next
-  // slot or the first weight stage); those products only reach dead columns or meet zero weights, and 0 x finite = 0
-  for (int i = threadIdx.x; i < (int)((bar0 - base) / 16); i += Cfg::kThreads)   // (+ the staging buffers: XOUT's zero halo)
-    *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                // everything below reads what the previous kernel of the chain wrote
-
-  if (warp == 0) {
-    // ================= TMA producer: weight stages =================
-    if (lane == 0) {
-      int bstage = 0;
-      uint32_t bphase = 0;
-      bool ok = true;
-      const int row0 = (int)(blockIdx.x % kWeightCopies) * Cfg::kStagesPerImage * (Cfg::kBBytes / 128);   // this CTA's replica
-      if (Cfg::kResident > 0) {
-        mbar_arrive_expect_tx(wres_bar, Cfg::kResident * Cfg::kBBytes);
-        for (int s = 0; s < Cfg::kStagesPerImage; ++s)
-          if (Cfg::resident(s))
-            tma_load_2d(r_base + Cfg::resident_index(s) * Cfg::kBBytes, &tmap_b, wres_bar, 0, row0 + s * (Cfg::kBBytes / 128));
-      }
-      for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
-        for (int s = 0; s < Cfg::kStagesPerImage && ok; ++s) {     // s = chunk * 7 + ky
-          if (Cfg::resident(s)) continue;
-          if (!mbar_wait(bempty_bar(bstage), bphase ^ 1u, s_abort, err, kErrBase + 32)) { ok = false; break; }
-          mbar_arrive_expect_tx(bfull_bar(bstage), Cfg::kBBytes);
-          tma_load_2d(b_base + bstage * Cfg::kBBytes, &tmap_b, bfull_bar(bstage), 0, row0 + s * (Cfg::kBBytes / 128));
-          if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 6) {
-    // ================= TMA producer: images (its own warp, so that an image is requested as soon as its slot is free
-    // and never queues behind weight stages the ring has no room for yet) =================
-    if (lane == 0) {
-      int aslot = 0;
-      uint32_t aphase = 0;
-      for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
-        if (!mbar_wait(aempty_bar(aslot), aphase ^ 1u, s_abort, err, kErrBase + 31)) break;
-        mbar_arrive_expect_tx(afull_bar(aslot), Cfg::kSlotBytes);
-        // one dense box: [ci / 8][pixels][8 ci]; dec1: rows -7..15 of 16 pixels, everything outside the 10 x 10 map zero-filled
-        if (CONVT) tma_load_4d(base + aslot * Cfg::kSlotBytes, &tmap_a, afull_bar(aslot), 0, -7, 0, img);
-        else tma_load_4d(base + aslot * Cfg::kSlotBytes, &tmap_a, afull_bar(aslot), 0, 0, 0, img);
-        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_16(128, Cfg::kN, HALF);
-      // dec1: tap row ky only reaches the output rows ky .. ky + 9 (the 10 input rows): instead of multiplying the zero rows of
-      // the padded field, every MMA but the first covers N = 160 columns and lands 16 ky columns further in the accumulator;
-      // the operand window (input rows 0..9 and the zero row / columns in front) no longer depends on ky.  The first MMA of an
-      // image runs over all 256 columns without accumulation and so clears the rest.  7 168 -> 4 528 tensor cycles per image.
-      constexpr uint32_t idesc160 = umma_idesc_16(128, 160, HALF);
-      int aslot = 0, bstage = 0, acc = 0;
-      uint32_t aphase = 0, bphase = 0, acc_phase = 0;
-      bool ok = true;
-      if (Cfg::kResident > 0) ok = mbar_wait(wres_bar, 0, s_abort, err, kErrBase + 37);
-      // One thread issues 56 MMAs of 82 (enc3) / 128 (dec1) tensor cycles per image: the instruction stream between two
-      // MMAs has to be shorter than that.  The loop over the stages is fully unrolled, every tap offset is a constant added
-      // to a base descriptor (the address field holds bytes >> 4 and never carries out of its 14 bits).  With a rolled
-      // loop and descriptors rebuilt per stage the issuer needed ~400 cycles per stage and the tensor pipe idled 55-65 %.
-      const uint64_t res_desc = umma_desc_nosw(r_base, Cfg::kLboA, 128);
-      for (int img = blockIdx.x; img < n_img && ok; img += gridDim.x) {
-        if (!mbar_wait(afull_bar(aslot), aphase, s_abort, err, kErrBase + 33)) break;
-        if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1u, s_abort, err, kErrBase + 34)) break;
-        tc_fence_after();
-        const uint64_t img_desc = umma_desc_nosw(base + aslot * Cfg::kSlotBytes, Cfg::kLboB, 128);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-#pragma unroll
-        for (int s = 0; s < Cfg::kStagesPerImage; ++s) {
-          const int c = s / 7, ky = s % 7;
-          const int px = CONVT ? (112 - Cfg::kTaps * c) : (16 * ky + Cfg::kTaps * c);
-          uint64_t wdesc;
-          if (!Cfg::resident(s)) {
-            if (!mbar_wait(bfull_bar(bstage), bphase, s_abort, err, kErrBase + 35)) { ok = false; break; }
-            tc_fence_after();
-            wdesc = umma_desc_nosw(b_base + bstage * Cfg::kBBytes, Cfg::kLboA, 128);
-          } else {
-            wdesc = res_desc + (uint64_t)((Cfg::resident_index(s) * Cfg::kBBytes) >> 4);
-          }
-#pragma unroll
-          for (int k = 0; k < Cfg::kK16; ++k)
-            umma_f16(tmem_d + (uint32_t)(CONVT ? 16 * ky : 0), wdesc + (uint64_t)((2 * k * Cfg::kLboA) >> 4),
-                     img_desc + (uint64_t)((px * 16 + 2 * k * Cfg::kLboB) >> 4), (CONVT && (s | k) != 0) ? idesc160 : idesc,
-                     (uint32_t)((s | k) != 0));
-          if (!Cfg::resident(s)) {
-            umma_commit(bempty_bar(bstage));
-            if (++bstage == SB) { bstage = 0; bphase ^= 1u; }
-          }
-        }
-        if (!ok) break;
-        umma_commit(tfull_bar(acc));
-        umma_commit(aempty_bar(aslot));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        if (++aslot == UA) { aslot = 0; aphase ^= 1u; }
-      }
-    }
-  } else if ((warp >= 2 && warp <= 5) || warp >= 7) {
-    // ================= epilogue (dec1: four warpgroups, 64 accumulator columns each) =================
-    // Accumulator row = co * taps + kxl: the rows of one output channel are ADJACENT LANES of one warp, so the sum over
-    // kxl is a lane exchange (shfl.xor) between 2 (enc3) / 4 (dec1) neighbours -- no shared-memory pass, no barriers.
-    // Each lane of a group finishes every 2nd / 4th output position of its channel.
-    const int q = warp & 3;                           // TMEM lane quadrant of this warp
-    const int L = q * 32 + lane;                      // accumulator row
-    const int kxl = L % Cfg::kTaps, co = L / Cfg::kTaps;
-    const int grp = warp >= 7 ? 1 + ((warp - 7) >> 2) : 0;
-    const int t = warp >= 7 ? (int)threadIdx.x - 96 : (int)threadIdx.x - 64;     // 0 .. 128 kEpiGroups - 1
-    constexpr int kStepsPerGroup = Cfg::kSteps / Cfg::kEpiGroups;
-    const int j0 = grp * kStepsPerGroup, j1 = j0 + kStepsPerGroup;
-    const float my_bias = s_bias[co];
-    int acc = 0, buf = 0;
-    uint32_t acc_phase = 0;
-    for (int img = blockIdx.x; img < n_img; img += gridDim.x) {
-      if (!mbar_wait(tfull_bar(acc), acc_phase, s_abort, err, kErrBase + 36)) break;
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      uint16_t* stg = reinterpret_cast<uint16_t*>(smem + (g_base - base) + buf * Cfg::kStgBytes);
-      float c1 = 0.f, c2 = 0.f;                       // this lane's column 32 j - 1 / its last level-1 sum of the step before
-      if (CONVT && grp) {                             // carries into this group's first column from the three before it
-        uint32_t w4[4];
-        tmem_ld_32x32_x4(taddr + (uint32_t)(32 * j0 - 4), w4);
-        tmem_ld_wait();
-        const float b3 = __uint_as_float(w4[1]), b2 = __uint_as_float(w4[2]), b1 = __uint_as_float(w4[3]);   // columns -3, -2, -1
-        c1 = b1;
-        c2 = b2 + __shfl_xor_sync(0xffffffffu, (kxl & 1) ? b3 : b1, 1);
-      }
-#pragma unroll 1
-      for (int j = j0; j < j1; ++j) {
-        uint32_t u[32];
-        tmem_ld_32x32(taddr + (uint32_t)(32 * j), u);
-        tmem_ld_wait();
-        if (j == j1 - 1) {                            // this group's last columns are in registers
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
-        if (CONVT) {
-          // out[n] = sum_g D_g[n - g] over the four lanes g of a group, as a two-level butterfly without divergence:
-          //   level 1 (lanes g ^ 1): P01[c] = D_0[c] + D_1[c - 1], P23[c] = D_2[c] + D_3[c - 1]; the even lane of a pair
-          //     finishes the even columns, the odd lane the odd ones -- for both the own term is v[i] and the partner's
-          //     term is what ONE exchange delivers (the odd lane sends v[i - 1], the even lane v[i + 1]);
-          //   level 2 (lanes g ^ 2): out[n] = P01[n] + P23[n - 2]; lane g finishes n = 4 k + g, own term p[2 k], the
-          //     partner sends p[2 k - 1] (lanes 2, 3) or p[2 k + 1] (lanes 0, 1).
-          const bool odd = (kxl & 1) != 0, hi = (kxl & 2) != 0;
-          float pp[16];
-#pragma unroll
-          for (int t2 = 0; t2 < 16; ++t2) {
-            const int i = 2 * t2;                                   // this lane's own column: i (even lane) / i + 1 (odd lane)
-            const float below = t2 == 0 ? c1 : v[t2 == 0 ? 0 : i - 1];
-            const float send = odd ? below : v[i + 1];
-            // even lane: P[i] = v[i] + odd's v[i - 1];   odd lane: P[i + 1] = v[i] (own column i + 1 - 1) + even's v[i + 1]
-            pp[t2] = v[i] + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float before = k == 0 ? c2 : pp[k == 0 ? 0 : 2 * k - 1];
-            const float send = hi ? before : pp[2 * k + 1];
-            const float a = my_bias + pp[2 * k] + __shfl_xor_sync(0xffffffffu, send, 2);
-            const int n = 32 * j + 4 * k + kxl;
-            // ReLU follows the decoder's first layer
-            if (XOUT) stg[((co >> 3) * 289 + (n >> 4) * 17 + (n & 15)) * 8 + (co & 7)] = pk1<HALF>(fmaxf(a, 0.f));
-            else stg[n * 32 + co] = pk1<HALF>(fmaxf(a, 0.f));
-          }
-          c1 = v[31]; c2 = pp[15];
-        } else {
-          // out[n] = D_0[n] + D_1[n + 1]; one exchange of column 2 k serves both lanes of a pair: the even lane finishes
-          // n = 32 j + 2 k - 1 (own column 2 k - 1), the odd lane n = 32 j + 2 k (own column 2 k + 1)
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float x = __shfl_xor_sync(0xffffffffu, v[2 * k], 1);
-            const float prev = k == 0 ? c1 : v[k == 0 ? 0 : 2 * k - 1];
-            const float own = kxl ? v[2 * k + 1] : prev;
-            const int n = 32 * j + 2 * k - 1 + kxl;
-            const int oy = n >> 4, ox = n & 15;
-            // a3 in channel-group-major form [img][co / 8][100 pixels][8 co] (dec1's operand layout)
-            if (n >= 0 && oy < 10 && ox < 10) stg[((co >> 3) * 100 + oy * 10 + ox) * 8 + (co & 7)] = pk1<HALF>(my_bias + own + x);
-          }
-          c1 = v[31];
-        }
-      }
-      named_bar_sync(1, 128 * Cfg::kEpiGroups);
-      if (XOUT) {
-        // four contiguous runs of 289 positions x 16 bytes, one per channel-group plane
-        const uint4* src = reinterpret_cast<const uint4*>(stg);
-        for (int i = t; i < 4 * 289; i += 128 * Cfg::kEpiGroups) {
-          const int g = i / 289, k = i - g * 289;
-          reinterpret_cast<uint4*>(out + (size_t)g * out_plane + (size_t)img * (289 * 8))[k] = src[i];
-        }
-      } else {
-        // the image's output block is contiguous in global memory (NHWC): 16-byte stores
-        const uint4* src = reinterpret_cast<const uint4*>(stg);
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)img * Cfg::kOutPixels * COUT);
-        for (int i = t; i < Cfg::kOutBytes / 16; i += 128) dst[i] = src[i];
-      }
-      buf ^= 1;
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// shifted-window weight layouts: stage s = chunk * 7 + ky, [ci / 8][row = co * taps + kxl][ci % 8], kx = chunk * taps + kxl
-//   enc3: w3 [co 64][ci 32][ky][kx] (Conv2d)            dec1: w4 [ci 64][co 32][ky][kx] (ConvTranspose2d)
-template <bool HALF>
-__global__ void pack_k7x_kernel(const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ p3,
-                                __nv_bfloat16* __restrict__ p4) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  auto cvt = [](float v) { return __ushort_as_bfloat16(pk1<HALF>(v)); };   // HALF: fp16 bits carried in the bf16 type
-  if (i < 28 * 4096) {
-    const int e = i & 7, row = (i >> 3) & 127, g = (i >> 10) & 3, s = i >> 12;
-    const int ci = g * 8 + e, ky = s % 7, kx = (s / 7) * 2 + (row & 1), co = row >> 1;
-    p3[i] = cvt(kx < 7 ? w3[((co * 32 + ci) * 7 + ky) * 7 + kx] : 0.f);
-  }
-  if (i < 14 * 8192) {
-    const int e = i & 7, row = (i >> 3) & 127, g = (i >> 10) & 7, s = i >> 13;
-    const int ci = g * 8 + e, ky = s % 7, kx = (s / 7) * 4 + (row & 3), co = row >> 2;
-    p4[i] = cvt(kx < 7 ? w4[((ci * 32 + co) * 7 + ky) * 7 + kx] : 0.f);
-  }
-}
-
-template <bool CONVT, bool HALF>
-static int launch_k7x(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* act_out,
-                      int64_t batch, int* err, cudaStream_t st) {
-  using Cfg = K7XCfg<CONVT>;
-  CUtensorMap ta, tb;
-  int r;
-  if (CONVT) {
-    // a3 [n][8 groups][10 rows][10 px x 8 ci]: a box row = 16 pixels (256 B, pixels 10..15 zero fill), 23 rows from -7
-    cuuint64_t dims[4] = {80, 10, 8, (cuuint64_t)batch};
-    cuuint64_t strides[3] = {160, 1600, 12800};
-    cuuint32_t box[4] = {128, 23, 8, 1};
-    r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-  } else {
-    // a2 [n][4 groups][16 rows][16 px x 8 ci]: the whole image, 64 rows of 256 B
-    cuuint64_t dims[4] = {128, 16, 4, (cuuint64_t)batch};
-    cuuint64_t strides[3] = {256, 4096, 16384};
-    cuuint32_t box[4] = {128, 16, 4, 1};
-    r = encode_tmap(&ta, 4, act_in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-  }
-  if (r != SG_OK) return r;
-  {
-    // the packed stages as rows of 128 bytes: a dense copy of one stage
-    cuuint64_t dims[2] = {64, (cuuint64_t)kWeightCopies * Cfg::kStagesPerImage * (Cfg::kBBytes / 128)};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)(Cfg::kBBytes / 128)};
-    r = encode_tmap(&tb, 2, wpk, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (r != SG_OK) return r;
-  }
-  const int grid = (int)(batch < state().sm_count ? batch : state().sm_count);
-  SG_LAUNCH_PDL(ae_k7x_kernel<CONVT, HALF>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, st, ta, tb, bias, act_out, (int)batch,
-                err, CONVT ? a4x_plane_elems(batch) : (size_t)0);
-  return SG_OK;
-}
-
 // ------------------------------------------------------------------------------------------
-// L3 (enc3) on CTA PAIRS (cta_group::2), the default of the single-segment modes.  ae_k7x_kernel<false> ran at 65 % tensor-pipe
+// L3 (enc3) on CTA PAIRS (cta_group::2), the default of the single-segment modes.  The single-CTA form ran at 65 % tensor-pipe
 // active: an M128 x N160 x K16 MMA reads 9 KB of operands for 80 tensor cycles (115 B/clk of the 128 B/clk shared memory
 // delivers) while TMA streams half of the 224 KB of weights through the same memory for every image.  As a pair, the two
 // CTAs split the OUTPUT CHANNELS (M = 256 = 2 x (32 co x 4 column taps)) and share the image: each CTA feeds 80 of the 160
@@ -879,7 +516,7 @@ struct K7PCfg {
   static constexpr int kTmemCols = 512;                  // 2 accumulators x 256 columns (160 used)
   // FIVE epilogue warpgroups, one per 32 accumulator columns: with one group (a single warp per scheduler) the dependent
   // tcgen05.ld -> shuffle -> shuffle -> store chain of an image took ~4 200 cycles against 2 240 cycles of MMAs -- the kernel
-  // (and ae_k7x_kernel<false> before it) was bound by its epilogue's latency, not by the tensor pipe or shared memory
+  // (and the single-CTA form before it) was bound by its epilogue's latency, not by the tensor pipe or shared memory
   // (one group: 247 us per 8 192 images, two: 207 us).  Group j > 0 re-derives the two carries of the butterfly from the three
   // columns in front of its own.
   static constexpr int kEpiGroups = kSteps;
@@ -1102,7 +739,7 @@ static int launch_k7p(const __nv_bfloat16* act_in, const __nv_bfloat16* wpk, con
 }
 
 // ------------------------------------------------------------------------------------------
-// L4 (dec1) on CTA PAIRS.  ae_k7x_kernel<true> streams the layer's 224 KB of weights through shared memory for every image:
+// L4 (dec1) on CTA PAIRS.  The single-CTA form streamed the layer's 224 KB of weights through shared memory for every image:
 // with the N = 160 form of its MMAs that L2 -> SM traffic (148 SMs x 224 KB per 4.4 us) became its bound.  As a pair the two
 // CTAs split the output channels, M = 256 = 2 x (16 co x 8 column taps): all eight kx (kx == 7: zero weights) are rows, so
 //   D[(co, g)][m] = sum_{ky, ci} w[ci][co][ky][g] * in[m - 16 ky][ci]          out[co][n] = sum_g D[(co, g)][n - g]
@@ -2609,8 +2246,6 @@ int sg_ae_tc_init_attributes() {
   SG_CUDA(cudaFuncSetAttribute(ae_k7q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7QCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_k7p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7PCfg::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
-  SG_CUDA(cudaFuncSetAttribute(ae_k7x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K7XCfg<true>::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec2x_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec2XCfg::kSmemBytes));
   SG_CUDA(cudaFuncSetAttribute(ae_dec3x_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Dec3XCfg::kSmemBytes));
