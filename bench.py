@@ -416,6 +416,10 @@ def main():
         ne = shard
         while ne > 8192 and ne * 49152 * max(world, 1) > 0.5 * psutil.virtual_memory().available:
             ne //= 2
+        if group is not None:       # the ranks read "available" at different moments: agree on the smallest shard
+            ne_t = torch.tensor([ne], dtype=torch.int64, device=device)
+            dist.all_reduce(ne_t, op=dist.ReduceOp.MIN)
+            ne = int(ne_t.item())
         host = torch.empty((ne, 3, 64, 64), dtype=torch.float32).pin_memory()
         for i in range(0, ne, CHUNK):
             host[i:i + CHUNK].copy_(images[i:i + CHUNK])
@@ -442,7 +446,15 @@ def main():
             tuner = sb.api._PackTuner.get(device)
             for _ in range(8):                          # untimed: pins the staging buffers, then lets the tuner settle its share
                 run_e2e()
-                if host_pack is False or tuner.locked:
+                done = host_pack is False or tuner.locked
+                if group is not None:
+                    # every run_e2e() holds a collective (the global select): all ranks must make the SAME number of calls.
+                    # The tuners time their own rank and lock after different numbers of calls (an 8-GPU run deadlocked here:
+                    # some ranks were already in e2e_leg's barrier while others still tuned), so the ranks agree on "done".
+                    flag = torch.tensor([1 if done else 0], dtype=torch.int32, device=device)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                    done = bool(flag.item())
+                if done:
                     break
             b0 = e2e_scorer.h2d_bytes
             v_, out_ = e2e_leg(run_e2e, ne)

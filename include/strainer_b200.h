@@ -278,7 +278,7 @@ int sg_select_step(uint32_t* ws, int pass, void* stream);
  * addresses (own buffer at index `rank`).  One-shot push protocol: each word travels as one 64-bit store tagged with
  * `seq` (non-zero, incremented by every rank for every call, in the same order on all ranks); a rank polls only its own
  * buffer.  All ranks must enqueue the call; each rank's GPU must run it concurrently with its peers' (one process per
- * GPU).  A peer that has not arrived after 120 s is reported by sg_select_check (status 2), not by a hang (the bound covers the
+ * GPU).  A peer that has not arrived after 20 s is reported by sg_select_check (status 2), not by a hang (the bound covers the
  * skew between ranks whose host-to-device copies finish seconds apart).
  * sg_peer_alloc / sg_peer_open: the one allocation the library makes itself (a CUDA IPC handle needs a cudaMalloc'ed
  * base): h_handle64 is a HOST buffer of 64 bytes to be exchanged between the processes (e.g. all_gather). */

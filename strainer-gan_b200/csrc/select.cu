@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256) step_kernel(uint32_t* ws, int pass) { ste
 // cost 0.27 ms per strain in round 1).  Two parity slots suffice: a rank can only start call s+2 after it has read every
 // peer's words of call s+1, which each peer writes after it finished reading call s.
 // SUM for the 256 digit counters + the NaN counter, MIN for the smallest key above the bucket (last pass).
-constexpr unsigned long long kPeerTimeoutNs = 120000000000ull;   // 120 s (NCCL's own watchdog default is minutes)
+constexpr unsigned long long kPeerTimeoutNs = 20000000000ull;    // 20 s (NCCL's own watchdog default is minutes)
 constexpr int kPeerWords = 258;                                  // ws[0 .. 258): hist[256], nan count, min-above
 __host__ __device__ inline size_t peer_slot_words(int nranks) { return (size_t)nranks * 264; }   // 264: 64-byte multiple
 
@@ -535,8 +535,8 @@ __global__ void __launch_bounds__(288) step_peer_kernel(uint32_t* ws, int pass, 
         unsigned long long w = own[(size_t)r * 264 + t];
         while ((uint32_t)(w >> 32) != seq) {
           // a peer never arrived: report, do not hang.  The bound has to cover the SKEW between ranks, not a latency: in an
-          // end-to-end strain every rank reaches its select when its own host-to-device copies are done, and the first call of
-          // eight ranks that pin their staging buffers at the same time spread over several seconds (a 2 s bound failed there)
+          // end-to-end strain every rank reaches its select when its own host-to-device copies are done (the first call of
+          // eight ranks that pin their staging buffers at the same time can spread over seconds)
           if (gtimer_ns() - t0 > kPeerTimeoutNs) { ws[W_ERR] = 2u; break; }
           w = own[(size_t)r * 264 + t];
         }
@@ -808,7 +808,7 @@ int sg_select_check(const void* workspace, void* stream) {
   SG_CUDA(cudaMemcpyAsync(&flag, ws + sg::sel::W_ERR, 4, cudaMemcpyDeviceToHost, sg::as_stream(stream)));
   SG_CUDA(cudaStreamSynchronize(sg::as_stream(stream)));
   if (flag != 0) {
-    sg::set_error(flag == 2 ? "radix select: a peer rank never arrived in the NVLink all-reduce of a pass (120 s); the order "
+    sg::set_error(flag == 2 ? "radix select: a peer rank never arrived in the NVLink all-reduce of a pass (20 s); the order "
                               "statistics of that call are invalid"
                             : "radix select: a grid barrier of the cooperative kernel timed out (device time-sliced?); the "
                               "order statistics of that call were returned as NaN");
