@@ -444,6 +444,8 @@ def main():
             hp0 = getattr(e2e_scorer, "host_pack", None)
             e2e_scorer.host_pack = host_pack
             tuner = sb.api._PackTuner.get(device)
+            if group is not None:
+                dist.barrier()                          # the ranks pinned their host shards at different speeds: start together
             for _ in range(8):                          # untimed: pins the staging buffers, then lets the tuner settle its share
                 run_e2e()
                 done = host_pack is False or tuner.locked
